@@ -1,0 +1,82 @@
+"""
+build_ref.py — compile the reference's own Cython hot kernel where it lies.
+
+Builds /root/reference/scarmapper/SlidingWindow.pyx (the only native module the reference
+builds, scarmapper/setup.py:14) into oracle/_ref/SlidingWindow.<abi>.so.  Nothing is copied:
+Cython reads the .pyx in place, the generated C goes to a temporary directory, and only the
+shared object lands in oracle/_ref/ (git-ignored, travels to the GPU box with gpurun).
+
+The reference's own scarmapper/setup.py is NOT run (it copies files and rmtree's a directory).
+
+TEST INFRASTRUCTURE ONLY — used to pin oracle/scar_oracle.c and as the "reference" CPU baseline.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+REFERENCE = os.environ.get("SCARMAPPER_REFERENCE", "/root/reference")
+PYX = os.path.join(REFERENCE, "scarmapper", "SlidingWindow.pyx")
+
+
+def ref_so() -> str | None:
+    hits = sorted(glob.glob(os.path.join(REF_DIR, "SlidingWindow.*.so")))
+    return hits[0] if hits else None
+
+
+def build(force: bool = False) -> str | None:
+    """Returns the path of the built module, or None when the reference tree is absent
+    (e.g. on the GPU box, where the prebuilt file is used as is)."""
+    have = ref_so()
+    if not os.path.exists(PYX):
+        return have
+    if have and not force and os.path.getmtime(have) >= os.path.getmtime(PYX):
+        return have
+    from Cython.Build import cythonize
+    from setuptools import Distribution
+    from setuptools.command.build_ext import build_ext
+
+    os.makedirs(REF_DIR, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="scar_ref_build_")
+    try:
+        exts = cythonize([PYX], build_dir=tmp, quiet=True, language_level=3)
+        for e in exts:
+            e.name = "SlidingWindow"
+        dist = Distribution({"name": "scar_ref", "ext_modules": exts})
+        cmd = build_ext(dist)
+        cmd.build_lib = os.path.join(tmp, "lib")
+        cmd.build_temp = os.path.join(tmp, "tmp")
+        cmd.ensure_finalized()
+        cmd.run()
+        built = glob.glob(os.path.join(tmp, "lib", "**", "SlidingWindow*.so"), recursive=True)
+        if not built:
+            raise RuntimeError("cythonize produced no SlidingWindow shared object")
+        for old in glob.glob(os.path.join(REF_DIR, "SlidingWindow.*.so")):
+            os.remove(old)
+        dst = os.path.join(REF_DIR, os.path.basename(built[0]))
+        shutil.copy2(built[0], dst)
+        return dst
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def load():
+    """Import the compiled reference module (oracle/_ref/SlidingWindow.*.so) or return None."""
+    so = ref_so()
+    if so is None:
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("SlidingWindow", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+if __name__ == "__main__":
+    out = build(force="--force" in sys.argv)
+    print(out or "reference tree not present and no prebuilt module")
