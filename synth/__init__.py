@@ -181,12 +181,18 @@ def _random_seq(rng, n):
     return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
 
 
-def make_target(rng, length: int, sgrna: str, reverse_comp: bool) -> str:
-    """Uniform-random locus with the sgRNA (or its reverse complement) implanted at the centre."""
-    body = _random_seq(rng, length)
+def make_target(rng, length: int, sgrna: str, reverse_comp: bool, allow_repeats: bool = False) -> str:
+    """Uniform-random locus with the sgRNA (or its reverse complement) implanted at the centre.
+    Unless allow_repeats, redraw until every 10-mer of the locus is unique (a chance repeat, about
+    0.3 expected in 800 nt, makes wild-type reads hit a far window; kept for one parity fixture)."""
     work = rcomp(sgrna) if reverse_comp else sgrna
-    p = length // 2 - len(work) // 2
-    return body[:p] + work + body[p + len(work):]
+    while True:
+        body = _random_seq(rng, length)
+        p = length // 2 - len(work) // 2
+        t = body[:p] + work + body[p + len(work):]
+        kmers = [t[i:i + 10] for i in range(length - 9)]
+        if allow_repeats or len(set(kmers)) == len(kmers):
+            return t
 
 
 def _insertion_pool(rng, n_pool=256, stride=24):
@@ -219,7 +225,8 @@ def _mh_pairs(targets, cutsites, reach=30, max_per_m=64):
             np.asarray(off, dtype=np.int64))
 
 
-def make_config(name: str, n_reads: int | None = None, seed: int = 20260101, **over) -> SynthConfig:
+def make_config(name: str, n_reads: int | None = None, seed: int = 20260101, allow_repeats: bool = False,
+                **over) -> SynthConfig:
     """name in {C1, C2, C3, C4, C5}: the BASELINE.json configs, in order."""
     rng = np.random.Generator(np.random.PCG64(seed))
     defaults = {"C1": 1_000_000, "C2": 10_000_000, "C3": 10_000_000, "C4": 10_000_000, "C5": 200_000_000}
@@ -235,7 +242,7 @@ def make_config(name: str, n_reads: int | None = None, seed: int = 20260101, **o
         cfg.read_len = cfg.min_len = 300
         rows = [("LONG800", 800, _random_seq(rng, 20), False)]
     for nm, ln, sg, rc in rows:
-        t = make_target(rng, ln, sg, rc)
+        t = make_target(rng, ln, sg, rc, allow_repeats)
         cfg.target_names.append(nm)
         cfg.targets.append(t)
         cfg.sgrnas.append(sg)

@@ -163,6 +163,11 @@ def build_cases():
     cases["c2_96_samples"] = case_from_synth(synth.make_config("C2", seed=12), 5000)
     cases["c3_12_targets_mh"] = case_from_synth(synth.make_config("C3", seed=13), 5000)
     cases["c4_long_300bp"] = case_from_synth(synth.make_config("C4", seed=14), 1500)
+    # a locus with a chance 10-mer repeat across the cut: wild-type reads hit a far window first
+    rep = synth.make_config("C4", seed=14, allow_repeats=True)
+    kmers = [rep.targets[0][i:i + 10] for i in range(len(rep.targets[0]) - 9)]
+    assert len(set(kmers)) < len(kmers), "seed 14 no longer yields a repeat; pick another"
+    cases["c4_repeat_locus"] = case_from_synth(rep, 1500)
 
     # ragged lengths around the loop bounds and the Minimum_Length filter, N-rich reads, odd index
     # fields (short / long / N), HR donor
@@ -194,8 +199,7 @@ def build_cases():
                 reads[i] = reads[i][:p] + reads[i][p:p + 10].lower() + reads[i][p + 10:]
         return reads, f0, f1
 
-    donor_src = cfg.generate(0, 1)
-    donor = cfg.reads_as_strings(donor_src)[0][40:52]
+    donor = next(r for r in cfg.reads_as_strings(cfg.generate(0, 200)) if len(r) >= 140)[40:52]
     cases["ragged_hr_donor"] = case_from_synth(cfg, 4000, hr_donor=donor, mutate=mutate)
 
     # TruSeq: 6-nt indices at both read ends, threshold 0, stored sequence seq[6:-6]
