@@ -1,0 +1,156 @@
+/*
+ * scar_b200.h — C ABI of libscar_b200.so: the B200 (sm_100a) implementation of ScarMapper's
+ * per-read scar-classification path.  This is the drop-in boundary: everything the reference's
+ * two hot call sites need, as plain pointers and sizes (no torch / C++ types).
+ *
+ * Reference interfaces replaced (paths under the reference tree):
+ *   scarmapper/SlidingWindow.pyx:20-22      sliding_window(...)            -> scar_classify_dev / scar_process_host
+ *   scarmapper/INDEL_Processing.py:135-196  ScarSearch.data_processing loop -> scar_process_host + scar_table_read
+ *   scarmapper/INDEL_Processing.py:891-1024 consensus_demultiplex loop      -> scar_demux_dev (+ phasing in scar_classify_dev)
+ *   scarmapper/INDEL_Processing.py:1126-1201 index_matching                 -> scar_demux_dev
+ *   Valkyries/Sequence_Magic.py:123-136     match_maker(query, unknown)     -> scar_match_maker_batch
+ *   scarmapper/INDEL_Processing.py:57-80,759-795 window_mapping/cutsite_search -> scar_ctx_create (tables), scar_cutsite_search
+ *
+ * Conventions: every function returns 0 on success or a negative SCAR_ERR_* code;
+ * scar_last_error() gives the text for the calling thread.  No exceptions cross the boundary.
+ * The caller owns every buffer.  "_dev" functions take DEVICE pointers and a cudaStream_t
+ * (passed as void*; NULL = default stream) and are asynchronous on that stream; "_host"
+ * functions take HOST pointers and do their own host<->device copies.  A context is bound to one
+ * device and is thread-compatible (one thread at a time).  There is no CPU fallback: every entry
+ * point that computes fails with SCAR_ERR_CUDA when no device is usable.
+ */
+#ifndef SCAR_B200_H
+#define SCAR_B200_H
+
+#include <stdint.h>
+#include "scar_records.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    SCAR_OK = 0,
+    SCAR_ERR_CUDA = -1,          /* CUDA runtime error (no device, launch failure, ...) */
+    SCAR_ERR_INVALID = -2,       /* bad argument */
+    SCAR_ERR_UNSUPPORTED = -3,   /* input outside the supported envelope */
+    SCAR_ERR_TABLE_FULL = -4,    /* scar table capacity exhausted (grow and retry) */
+    SCAR_ERR_NOMEM = -5,
+    SCAR_ERR_HASH_COLLISION = -6 /* verification found two keys under one 128-bit tag */
+};
+
+enum { SCAR_PLATFORM_ILLUMINA = 0, SCAR_PLATFORM_TRUSEQ = 1, SCAR_PLATFORM_RAMSDEN = 2 };
+
+/* A list of byte strings.  Either CSR (offsets != NULL, item i = bytes[offsets[i] .. offsets[i+1]))
+ * or fixed stride (offsets == NULL, item i starts at i*stride and is lengths[i] long, or `stride`
+ * long when lengths == NULL). */
+typedef struct scar_ragged {
+    const uint8_t *bytes;
+    const int64_t *offsets;
+    const int32_t *lengths;
+    int64_t stride;
+} scar_ragged;
+
+/* Static description of a run: what ScarSearch.__init__/window_mapping/cutsite_search,
+ * DataProcessing.dictionary_build and TargetMapper.phasing compute once per run. */
+typedef struct scar_config {
+    int32_t device;               /* CUDA device ordinal */
+    int32_t platform;             /* SCAR_PLATFORM_* (args.Platform) */
+    int32_t mismatch;             /* index match threshold; -1 = platform default 1/0/3 (INDEL_Processing.py:1142-1147) */
+    int32_t n_targets;
+    const uint8_t *target_bytes;  /* upper-cased target regions, concatenated */
+    const int64_t *target_off;    /* [n_targets+1] */
+    const int32_t *target_cutsite;/* [n_targets] (scar_cutsite_search) */
+    int32_t n_samples;            /* manifest rows, manifest order */
+    const int32_t *sample_target; /* [n_samples] target id of each sample (index_dict[s][7]) */
+    const uint8_t *left_index_bytes;  /* index_dict[s][0]: Master_Index_File column 3, upper-cased */
+    const int64_t *left_index_off;    /* [n_samples+1] */
+    const uint8_t *right_index_bytes; /* index_dict[s][2]: Master_Index_File column 2, upper-cased */
+    const int64_t *right_index_off;   /* [n_samples+1] */
+    /* TargetMapper.phasing lists, concatenated over targets; target t owns phases
+     * [phase_off[t], phase_off[t+1]).  NULL phase_off = no phasing. */
+    const int32_t *phase_off;         /* [n_targets+1] */
+    const uint8_t *phase_r1_bytes; const int64_t *phase_r1_off;
+    const uint8_t *phase_r2_bytes; const int64_t *phase_r2_off;
+    const uint8_t *hr_donor; int32_t hr_len;   /* args.HR_Donor ("" = off) */
+    double n_limit;               /* args.N_Limit */
+    int32_t min_length;           /* args.Minimum_Length */
+    int32_t max_read_len;         /* longest read the context must accept (<= 1024) */
+    int64_t table_capacity;       /* scar-table slots, power of two; 0 = default */
+    /* per-read drop-in only: a 10-nt cutwindow per target for the SlidingWindow.pyx:56-60 test
+     * (the driver always passes 8 nt, which can never match; NULL = none) */
+    const uint8_t *cutwindow_bytes;   /* [n_targets][10] or NULL */
+} scar_config;
+
+typedef struct scar_ctx scar_ctx;
+
+const char *scar_last_error(void);
+int scar_version(void);
+
+/* ScarSearch.cutsite_search (INDEL_Processing.py:759-795) on the host; returns the cutsite in
+ * *cutsite, or SCAR_ERR_INVALID when the sgRNA does not map (the reference exits). */
+int scar_cutsite_search(const uint8_t *target, int32_t len, const uint8_t *sgrna, int32_t sg_len,
+                        int32_t reverse_comp, int32_t *cutsite);
+
+int scar_ctx_create(const scar_config *cfg, scar_ctx **out);
+void scar_ctx_destroy(scar_ctx *ctx);
+
+/* Layout of the packed read batch in HBM. */
+int scar_cells_per_read(const scar_ctx *ctx);        /* 64-bit cells per read row */
+int scar_window_counts(const scar_ctx *ctx, int32_t target, int32_t *n_left, int32_t *n_right);
+
+/* K1: raw bytes -> packed rows (2-bit codes + ACGT mask + N mask), applying the platform's stored-
+ * sequence transform (Illumina as is, TruSeq seq[6:-6], Ramsden rcomp; INDEL_Processing.py:946,978,981). */
+int scar_pack_dev(scar_ctx *ctx, const scar_ragged *seq, int64_t n_reads,
+                  uint64_t *cells, uint16_t *lens, void *stream);
+
+/* K2: sample assignment per read (manifest position or SCAR_SAMPLE_NONE).
+ * Illumina: f0/f1 = name.split(":")[-1].split("+")[0..1]; TruSeq/Ramsden: taken from seq. */
+int scar_demux_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_ragged *f0, const scar_ragged *f1,
+                   int64_t n_reads, uint16_t *samples, void *stream);
+
+/* K3: phasing + filters + sliding-window junction search + junction call. */
+int scar_classify_dev(scar_ctx *ctx, const uint64_t *cells, const uint16_t *lens,
+                      const uint16_t *samples, int64_t n_reads, scar_record *records, void *stream);
+
+/* K4: accumulate per-sample counters, phase histograms and the scar table.  first_index is the
+ * global index of read 0 of this batch (first-seen order across batches and ranks). */
+int scar_aggregate_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_record *records,
+                       int64_t n_reads, uint64_t first_index, void *stream);
+
+/* Whole path over a batch already resident in HBM: K2 -> K1 -> K3 -> K4 on `stream`.
+ * cells/lens/samples/records are caller-provided device scratch/outputs. */
+int scar_run_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_ragged *f0, const scar_ragged *f1,
+                 int64_t n_reads, uint64_t first_index, uint64_t *cells, uint16_t *lens,
+                 uint16_t *samples, scar_record *records, void *stream);
+
+/* Whole path from HOST buffers: chunks the batch, overlaps H2D / kernels / D2H on internal
+ * streams.  records may be NULL (tables and counters only). */
+int scar_process_host(scar_ctx *ctx, const scar_ragged *seq, const scar_ragged *f0, const scar_ragged *f1,
+                      int64_t n_reads, uint64_t first_index, scar_record *records);
+
+/* Results accumulated so far (synchronises the context's streams). */
+int scar_counters_read(scar_ctx *ctx, int64_t *counters /* [n_samples][SCAR_N_COUNTERS] */,
+                       int64_t *unassigned);
+int scar_phase_hist_read(scar_ctx *ctx, int64_t *hist /* [n_samples][2][SCAR_PHASE_BINS] */);
+#define SCAR_PHASE_BINS 34   /* bin 0 = "No Read N Phasing", bin 1+k = phase k, last = n/a */
+int scar_table_size(scar_ctx *ctx, int64_t *n_entries);
+/* entries sorted by (sample, first_idx): the reference's first-seen dict order per sample. */
+int scar_table_read(scar_ctx *ctx, scar_entry *entries, int64_t capacity, int64_t *n_entries);
+int scar_verify_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_record *records, int64_t n_reads,
+                    uint64_t first_index, int64_t *n_collisions, void *stream);
+int scar_reset(scar_ctx *ctx);
+
+/* Multi-GPU: export this rank's table, merge another rank's into it (count SUM, first_idx MIN). */
+int scar_table_export_dev(scar_ctx *ctx, scar_entry *entries, int64_t capacity, int64_t *n_entries, void *stream);
+int scar_table_merge_dev(scar_ctx *ctx, const scar_entry *entries, int64_t n_entries, void *stream);
+int scar_counters_ptr(scar_ctx *ctx, void **counters_dev, int64_t *n_int64);
+
+/* Sequence_Magic.match_maker over a batch on the device (host buffers): out[i] = lev(q_i,u_i) - (|u_i|-|q_i|). */
+int scar_match_maker_batch(int32_t device, const scar_ragged *query, const scar_ragged *unknown,
+                           int64_t n, int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

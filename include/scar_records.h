@@ -79,12 +79,13 @@ enum {
 
 /* one aggregated scar pattern (results_freq_dict entry, INDEL_Processing.py:186-196) */
 typedef struct scar_entry {
-    uint64_t key_hash;   /* 64-bit hash of the full key (sample, tlj, trj, ins/mh bytes, hr) */
+    uint64_t h1, h2;     /* 128-bit identity of the key (sample, tlj, trj, ins|mh bytes, hr): two
+                            independent 64-bit hashes; both must agree for two reads to share an entry */
     uint64_t first_idx;  /* global index of the FIRST read with this key (:193-196) */
     uint32_t count;      /* results_freq_dict[key][0] */
     uint16_t sample;
     uint16_t pad;
-} scar_entry;            /* 24 bytes */
+} scar_entry;            /* 32 bytes */
 
 #ifdef __cplusplus
 }

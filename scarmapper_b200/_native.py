@@ -1,0 +1,119 @@
+"""
+_native.py — ctypes binding of libscar_b200.so (include/scar_b200.h).
+
+There is no fallback: if the shared library is missing or cannot be loaded, importing the
+compute path raises.  Build it with `python -m scarmapper_b200.build` (or __graft_entry__.build()).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libscar_b200.so")
+
+SCAR_N_COUNTERS = 16
+SCAR_PHASE_BINS = 34
+SAMPLE_NONE = 0xFFFF
+
+RECORD_DTYPE = np.dtype([
+    ("status", "u1"), ("flags", "u1"), ("sample", "<u2"),
+    ("clj", "<u2"), ("crj", "<u2"), ("tlj", "<u2"), ("trj", "<u2"),
+    ("hr_n", "<u2"), ("phase_r1", "i1"), ("phase_r2", "i1"),
+])
+ENTRY_DTYPE = np.dtype([
+    ("h1", "<u8"), ("h2", "<u8"), ("first_idx", "<u8"), ("count", "<u4"), ("sample", "<u2"), ("pad", "<u2"),
+])
+assert RECORD_DTYPE.itemsize == 16 and ENTRY_DTYPE.itemsize == 32
+
+ST_UNASSIGNED, ST_FILTERED, ST_NO_JUNCTION, ST_NO_CUT, ST_N_INSERTION, ST_SCAR = range(6)
+FL_LEFT_DEL, FL_RIGHT_DEL, FL_INSERTION, FL_MICROHOM, FL_HR, FL_CUTWINDOW = 1, 2, 4, 8, 16, 32
+(CT_ASSIGNED, CT_PASSING, CT_LEFT_DEL, CT_RIGHT_DEL, CT_INSERTION, CT_MICROHOM, CT_NO_JUNCTION, CT_NO_CUT,
+ CT_FILTERED, CT_HR_FIRST, CT_HR_MORE, CT_N_INSERTION, CT_SCAR) = range(13)
+PLATFORMS = {"Illumina": 0, "TruSeq": 1, "Ramsden": 2}
+
+ERRORS = {-1: "SCAR_ERR_CUDA", -2: "SCAR_ERR_INVALID", -3: "SCAR_ERR_UNSUPPORTED", -4: "SCAR_ERR_TABLE_FULL",
+          -5: "SCAR_ERR_NOMEM", -6: "SCAR_ERR_HASH_COLLISION"}
+
+
+class ScarError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("{} ({}): {}".format(ERRORS.get(code, "SCAR_ERR"), code, text))
+        self.code = code
+
+
+class Ragged(C.Structure):
+    """struct scar_ragged"""
+    _fields_ = [("bytes", C.c_void_p), ("offsets", C.c_void_p), ("lengths", C.c_void_p), ("stride", C.c_int64)]
+
+
+class Config(C.Structure):
+    """struct scar_config"""
+    _fields_ = [
+        ("device", C.c_int32), ("platform", C.c_int32), ("mismatch", C.c_int32), ("n_targets", C.c_int32),
+        ("target_bytes", C.c_void_p), ("target_off", C.c_void_p), ("target_cutsite", C.c_void_p),
+        ("n_samples", C.c_int32), ("sample_target", C.c_void_p),
+        ("left_index_bytes", C.c_void_p), ("left_index_off", C.c_void_p),
+        ("right_index_bytes", C.c_void_p), ("right_index_off", C.c_void_p),
+        ("phase_off", C.c_void_p),
+        ("phase_r1_bytes", C.c_void_p), ("phase_r1_off", C.c_void_p),
+        ("phase_r2_bytes", C.c_void_p), ("phase_r2_off", C.c_void_p),
+        ("hr_donor", C.c_void_p), ("hr_len", C.c_int32),
+        ("n_limit", C.c_double), ("min_length", C.c_int32), ("max_read_len", C.c_int32),
+        ("table_capacity", C.c_int64), ("cutwindow_bytes", C.c_void_p),
+    ]
+
+
+# every symbol include/scar_b200.h declares: (restype, argtypes)
+_P = C.c_void_p
+_RP = C.POINTER(Ragged)
+PROTOTYPES = {
+    "scar_last_error": (C.c_char_p, []),
+    "scar_version": (C.c_int, []),
+    "scar_cutsite_search": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "scar_ctx_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
+    "scar_ctx_destroy": (None, [_P]),
+    "scar_cells_per_read": (C.c_int, [_P]),
+    "scar_window_counts": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "scar_pack_dev": (C.c_int, [_P, _RP, C.c_int64, _P, _P, _P]),
+    "scar_demux_dev": (C.c_int, [_P, _RP, _RP, _RP, C.c_int64, _P, _P]),
+    "scar_classify_dev": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P]),
+    "scar_aggregate_dev": (C.c_int, [_P, _RP, _P, C.c_int64, C.c_uint64, _P]),
+    "scar_run_dev": (C.c_int, [_P, _RP, _RP, _RP, C.c_int64, C.c_uint64, _P, _P, _P, _P, _P]),
+    "scar_process_host": (C.c_int, [_P, _RP, _RP, _RP, C.c_int64, C.c_uint64, _P]),
+    "scar_counters_read": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
+    "scar_phase_hist_read": (C.c_int, [_P, _P]),
+    "scar_table_size": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "scar_table_read": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "scar_verify_dev": (C.c_int, [_P, _RP, _P, C.c_int64, C.c_uint64, C.POINTER(C.c_int64), _P]),
+    "scar_reset": (C.c_int, [_P]),
+    "scar_table_export_dev": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
+    "scar_table_merge_dev": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "scar_counters_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "scar_match_maker_batch": (C.c_int, [C.c_int32, _RP, _RP, C.c_int64, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libscar_b200.so and bind every prototype.  Raises if the library is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libscar_b200.so is not built ({}); run `python -m scarmapper_b200.build`. "
+                              "There is no CPU fallback.".format(LIB_PATH))
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise ScarError(rc, lib().scar_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,688 @@
+// scar_api.cu — the C ABI of libscar_b200.so (include/scar_b200.h): context set-up (what
+// window_mapping / dictionary_build / TargetMapper.phasing compute once per run, reference
+// scarmapper/INDEL_Processing.py:57-80,1063-1124 and TargetMapper.py:30-71), the stage entry points
+// and the host-buffer pipeline.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "scar_internal.cuh"
+
+// ---- errors ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SCAR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *scar_last_error(void) { return g_err; }
+extern "C" int scar_version(void) { return 100; }
+
+// ---- host helpers ---------------------------------------------------------------------------------
+static uint8_t comp_host(uint8_t c)
+{
+    static const char *from = "ACGTMRWSYKVHDBXNacgtmrwsykvhdbxn", *to = "TGCAKYWSRMBDHVXNtgcakywsrmbdhvxn";
+    const char *p = strchr(from, c);
+    return (p && c) ? (uint8_t)to[p - from] : c;
+}
+
+extern "C" int scar_cutsite_search(const uint8_t *target, int32_t len, const uint8_t *sgrna, int32_t sg_len,
+                                   int32_t reverse_comp, int32_t *cutsite)
+{
+    if (!target || !sgrna || !cutsite || len < 0 || sg_len < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    std::string work(sg_len, 'N');
+    for (int i = 0; i < sg_len; ++i) work[i] = reverse_comp ? (char)comp_host(sgrna[sg_len - 1 - i]) : (char)sgrna[i];
+    // INDEL_Processing.py:773-791: windows [lft, lft+sg_len) while rt < len-1, first occurrence
+    for (int lft = 0; lft + sg_len < len - 1; ++lft) {
+        if (memcmp(target + lft, work.data(), (size_t)sg_len) == 0) {
+            *cutsite = reverse_comp ? lft + 3 : lft + sg_len - 3;
+            return SCAR_OK;
+        }
+    }
+    return fail(SCAR_ERR_INVALID, "sgRNA does not map to the target region");
+}
+
+static bool acgt_only(const uint8_t *p, int n)
+{
+    for (int i = 0; i < n; ++i) if (!scar_base_valid(p[i])) return false;
+    return true;
+}
+static uint64_t encode_bases(const uint8_t *p, int n)
+{
+    uint64_t c = 0;
+    for (int i = 0; i < n; ++i) c |= (uint64_t)scar_base_code(p[i]) << (2 * i);
+    return c;
+}
+
+struct BucketTable { std::vector<uint2> buckets; uint32_t mult, shift; };
+
+// window list -> bucketed perfect hash "10-mer -> smallest i" (two entries per bucket, one probe)
+static bool build_table(const std::vector<std::pair<uint32_t, uint32_t>> &kv /* key, min i */, BucketTable &out)
+{
+    size_t n = kv.size();
+    uint32_t log2b = 6;
+    while ((1u << log2b) < 4 * n) ++log2b;
+    uint64_t rng = 0x853C49E6748FEA9Bull ^ (n * 0x9E3779B97F4A7C15ull);
+    for (; log2b <= 16; ++log2b) {
+        const uint32_t B = 1u << log2b;
+        for (int attempt = 0; attempt < 4096; ++attempt) {
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            const uint32_t mult = (uint32_t)(rng >> 32) | 1u;
+            std::vector<uint2> b(B, make_uint2(0u, 0u));
+            bool ok = true;
+            for (const auto &e : kv) {
+                const uint32_t slot = (e.first * mult) >> (32 - log2b);
+                const uint32_t val = ((e.first | SCAR_KEY_TAG) << 11) | e.second;
+                if (b[slot].x == 0) b[slot].x = val;
+                else if (b[slot].y == 0) b[slot].y = val;
+                else { ok = false; break; }
+            }
+            if (ok) { out.buckets.swap(b); out.mult = mult; out.shift = 32 - log2b; return true; }
+        }
+    }
+    return false;
+}
+
+// ---- context --------------------------------------------------------------------------------------
+static const int NBUF = 3;
+
+struct HostBuf {   // device scratch of one in-flight chunk of scar_process_host
+    uint8_t *seq = nullptr, *f0 = nullptr, *f1 = nullptr; size_t seq_cap = 0, f0_cap = 0, f1_cap = 0;
+    int64_t *seq_off = nullptr, *f0_off = nullptr, *f1_off = nullptr;
+    int32_t *seq_len = nullptr, *f0_len = nullptr, *f1_len = nullptr;
+    uint64_t *cells = nullptr; uint16_t *lens = nullptr, *samples = nullptr; scar_record *records = nullptr;
+    int64_t reads_cap = 0;
+    cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
+};
+
+struct scar_ctx {
+    int device = 0, sm_count = 148, platform = 0, mismatch = 1, n_targets = 0, n_samples = 0;
+    int W = 0, max_read_len = 0, min_length = 0, hr_len = 0, do_phasing = 0;
+    double n_limit = 0.0; uint64_t hr_code = 0;
+    std::vector<ScarTargetMeta> h_targets;
+    int32_t *d_sample_target = nullptr; ScarTargetMeta *d_targets = nullptr; ScarPhase *d_phases = nullptr;
+    uint2 *d_tables = nullptr; uint32_t table_bytes = 0; bool smem_tables = true;
+    uint8_t *d_class_map = nullptr; DemuxString *d_right = nullptr, *d_left = nullptr; uint64_t *d_peq = nullptr;
+    uint16_t *d_first_sample = nullptr; int n_right = 0, n_left = 0, n_classes = 0;
+    ScarTableSlot *d_slots = nullptr; uint64_t capacity = 0;
+    unsigned long long *d_acc = nullptr;   // [n_entries, unassigned, collisions, export_count] + counters + phase hist
+    unsigned long long *d_n_entries = nullptr, *d_unassigned = nullptr, *d_collisions = nullptr, *d_export_n = nullptr;
+    unsigned long long *d_counters = nullptr, *d_phase_hist = nullptr; size_t acc_words = 0;
+    int32_t *d_status = nullptr;
+    HostBuf buf[NBUF]; int64_t chunk_reads = 1 << 20;
+    int launches = 0;
+};
+
+static void free_hostbuf(HostBuf &b)
+{
+    cudaFree(b.seq); cudaFree(b.f0); cudaFree(b.f1); cudaFree(b.seq_off); cudaFree(b.f0_off); cudaFree(b.f1_off);
+    cudaFree(b.seq_len); cudaFree(b.f0_len); cudaFree(b.f1_len);
+    cudaFree(b.cells); cudaFree(b.lens); cudaFree(b.samples); cudaFree(b.records);
+    if (b.stream) cudaStreamDestroy(b.stream);
+    if (b.done) cudaEventDestroy(b.done);
+    b = HostBuf();
+}
+
+extern "C" void scar_ctx_destroy(scar_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto &b : c->buf) free_hostbuf(b);
+    cudaFree(c->d_sample_target); cudaFree(c->d_targets); cudaFree(c->d_phases); cudaFree(c->d_tables);
+    cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample);
+    cudaFree(c->d_slots); cudaFree(c->d_acc); cudaFree(c->d_status);
+    delete c;
+}
+
+template <typename T> static int upload(T **dst, const std::vector<T> &v)
+{
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CU(cudaMalloc((void **)dst, bytes));
+    if (!v.empty()) CU(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SCAR_OK;
+}
+
+static int build_demux(scar_ctx *c, const scar_config *cfg)
+{
+    // distinct index strings per side, class map over every byte that occurs in an index string
+    std::vector<uint8_t> cmap(256, 0);
+    int n_classes = 1;
+    auto str_of = [](const uint8_t *b, const int64_t *off, int s) {
+        return std::string((const char *)b + off[s], (size_t)(off[s + 1] - off[s]));
+    };
+    std::vector<std::string> right_s, left_s;
+    std::map<std::string, int> right_id, left_id;
+    std::vector<int> s_right(c->n_samples), s_left(c->n_samples);
+    for (int s = 0; s < c->n_samples; ++s) {
+        std::string r = cfg->right_index_bytes ? str_of(cfg->right_index_bytes, cfg->right_index_off, s) : std::string();
+        std::string l = cfg->left_index_bytes ? str_of(cfg->left_index_bytes, cfg->left_index_off, s) : std::string();
+        if (r.size() > SCAR_MAX_INDEX_LEN || l.size() > SCAR_MAX_INDEX_LEN)
+            return fail(SCAR_ERR_UNSUPPORTED, "index sequence longer than %d nt (sample %d)", SCAR_MAX_INDEX_LEN, s);
+        if (!right_id.count(r)) { right_id[r] = (int)right_s.size(); right_s.push_back(r); }
+        if (!left_id.count(l)) { left_id[l] = (int)left_s.size(); left_s.push_back(l); }
+        s_right[s] = right_id[r]; s_left[s] = left_id[l];
+        for (unsigned char ch : r + l)
+            if (!cmap[ch]) {
+                if (n_classes >= SCAR_MAX_CLASSES)
+                    return fail(SCAR_ERR_UNSUPPORTED, "index sequences use more than %d distinct symbols", SCAR_MAX_CLASSES - 1);
+                cmap[ch] = (uint8_t)n_classes++;
+            }
+    }
+    if (right_s.size() > 64 || left_s.size() > 64)
+        return fail(SCAR_ERR_UNSUPPORTED, "more than 64 distinct index sequences on one side (%zu, %zu)", right_s.size(), left_s.size());
+    std::vector<uint64_t> peq;
+    auto make = [&](const std::vector<std::string> &v, std::vector<DemuxString> &out) {
+        for (const auto &s : v) {
+            DemuxString d; d.len = (int)s.size(); d.peq_off = (int)peq.size(); d.code[0] = d.code[1] = 0;
+            peq.resize(peq.size() + n_classes, 0ull);
+            for (int i = 0; i < d.len; ++i) {
+                const int cl = cmap[(unsigned char)s[i]];
+                peq[d.peq_off + cl] |= 1ull << i;
+                if (i < 32) d.code[i >> 4] |= (uint64_t)cl << (4 * (i & 15));
+            }
+            out.push_back(d);
+        }
+    };
+    std::vector<DemuxString> hr, hl;
+    make(right_s, hr); make(left_s, hl);
+    std::vector<uint16_t> first(std::max<size_t>(hr.size() * hl.size(), 1), SCAR_SAMPLE_NONE);
+    for (int s = c->n_samples - 1; s >= 0; --s) first[s_right[s] * hl.size() + s_left[s]] = (uint16_t)s;
+    c->n_right = (int)hr.size(); c->n_left = (int)hl.size(); c->n_classes = n_classes;
+    int rc;
+    if ((rc = upload(&c->d_class_map, cmap))) return rc;
+    if ((rc = upload(&c->d_right, hr))) return rc;
+    if ((rc = upload(&c->d_left, hl))) return rc;
+    if ((rc = upload(&c->d_peq, peq))) return rc;
+    if ((rc = upload(&c->d_first_sample, first))) return rc;
+    return SCAR_OK;
+}
+
+extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
+{
+    if (!cfg || !out) return fail(SCAR_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->n_targets < 1 || cfg->n_samples < 1 || cfg->n_samples >= 0xFFFF)
+        return fail(SCAR_ERR_INVALID, "n_targets/n_samples out of range");
+    if (cfg->platform < 0 || cfg->platform > 2) return fail(SCAR_ERR_INVALID, "unknown platform %d", cfg->platform);
+    if (cfg->max_read_len < 1 || cfg->max_read_len > 1024)
+        return fail(SCAR_ERR_UNSUPPORTED, "max_read_len %d outside 1..1024", cfg->max_read_len);
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SCAR_ERR_CUDA, "CUDA device %d not present (%d devices)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(SCAR_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    scar_ctx *c = new scar_ctx();
+    struct Guard { scar_ctx *c; ~Guard() { if (c) scar_ctx_destroy(c); } } guard{c};
+    c->device = cfg->device; c->sm_count = prop.multiProcessorCount; c->platform = cfg->platform;
+    c->mismatch = cfg->mismatch >= 0 ? cfg->mismatch : (cfg->platform == 0 ? 1 : cfg->platform == 1 ? 0 : 3);
+    c->n_targets = cfg->n_targets; c->n_samples = cfg->n_samples;
+    c->max_read_len = cfg->max_read_len; c->W = (cfg->max_read_len + 15) / 16;
+    c->n_limit = cfg->n_limit; c->min_length = cfg->min_length;
+    if (const char *e = getenv("SCAR_CHUNK_READS")) { long v = atol(e); if (v >= 1024) c->chunk_reads = v; }
+
+    // HR donor (SlidingWindow.pyx:102-117)
+    if (cfg->hr_len > 0) {
+        if (cfg->hr_len > 32 || !acgt_only(cfg->hr_donor, cfg->hr_len))
+            return fail(SCAR_ERR_UNSUPPORTED, "HR donor must be 1..32 nt of ACGT");
+        c->hr_len = cfg->hr_len; c->hr_code = encode_bases(cfg->hr_donor, cfg->hr_len);
+    }
+
+    // targets: window tables (window_mapping, INDEL_Processing.py:57-80)
+    std::vector<uint2> blob;
+    std::vector<ScarPhase> phases;
+    for (int t = 0; t < cfg->n_targets; ++t) {
+        const uint8_t *T = cfg->target_bytes + cfg->target_off[t];
+        const int L = (int)(cfg->target_off[t + 1] - cfg->target_off[t]);
+        const int cut = cfg->target_cutsite[t];
+        if (cut < 0 || cut > L || L > 0xFFFF) return fail(SCAR_ERR_INVALID, "target %d: cutsite %d outside 0..%d", t, cut, L);
+        ScarTargetMeta m; memset(&m, 0, sizeof(m));
+        m.cutsite = cut; m.length = L;
+        m.n_left = cut > 15 ? cut - 15 : 0;                 // while rt_position > 15
+        m.n_right = L - 15 - cut > 0 ? L - 15 - cut : 0;    // while lft_position < L - 15
+        if (m.n_left > SCAR_MAX_WINDOWS || m.n_right > SCAR_MAX_WINDOWS)
+            return fail(SCAR_ERR_UNSUPPORTED, "target %d: more than %d windows on one side", t, SCAR_MAX_WINDOWS);
+        for (int side = 0; side < 2; ++side) {
+            std::map<uint32_t, uint32_t> mn;
+            const int n = side == 0 ? m.n_left : m.n_right;
+            for (int i = 0; i < n; ++i) {
+                const int a = side == 0 ? cut - 10 - i : cut + i;
+                if (a < 0 || a + 10 > L) continue;          // Python slice shorter than 10: can never equal a read window
+                if (!acgt_only(T + a, 10))
+                    return fail(SCAR_ERR_UNSUPPORTED, "target %d: window at %d contains a non-ACGT base", t, a);
+                const uint32_t key = (uint32_t)encode_bases(T + a, 10);
+                if (!mn.count(key)) mn[key] = (uint32_t)i;  // list order: the smallest i wins
+            }
+            std::vector<std::pair<uint32_t, uint32_t>> kv(mn.begin(), mn.end());
+            BucketTable bt;
+            if (!build_table(kv, bt)) return fail(SCAR_ERR_UNSUPPORTED, "target %d: could not build a window table", t);
+            if (side == 0) { m.left_off = (uint32_t)blob.size(); m.left_mult = bt.mult; m.left_shift = bt.shift; }
+            else { m.right_off = (uint32_t)blob.size(); m.right_mult = bt.mult; m.right_shift = bt.shift; }
+            blob.insert(blob.end(), bt.buckets.begin(), bt.buckets.end());
+        }
+        m.cutwindow_key = 0xFFFFFFFFu;
+        if (cfg->cutwindow_bytes && acgt_only(cfg->cutwindow_bytes + 10 * t, 10))
+            m.cutwindow_key = (uint32_t)encode_bases(cfg->cutwindow_bytes + 10 * t, 10);
+        // phasing (TargetMapper.py:54-69 lists; compared at INDEL_Processing.py:965-970)
+        m.phase_off = (int)phases.size(); m.n_phase = 0;
+        if (cfg->phase_off && cfg->platform == SCAR_PLATFORM_ILLUMINA) {
+            const int k0 = cfg->phase_off[t], k1 = cfg->phase_off[t + 1];
+            if (k1 - k0 > SCAR_MAX_PHASES) return fail(SCAR_ERR_UNSUPPORTED, "target %d: more than %d phases", t, SCAR_MAX_PHASES);
+            for (int k = k0; k < k1; ++k) {
+                ScarPhase p; memset(&p, 0, sizeof(p));
+                const uint8_t *a = cfg->phase_r1_bytes + cfg->phase_r1_off[k];
+                const int na = (int)(cfg->phase_r1_off[k + 1] - cfg->phase_r1_off[k]);
+                const uint8_t *b = cfg->phase_r2_bytes + cfg->phase_r2_off[k];
+                const int nb = (int)(cfg->phase_r2_off[k + 1] - cfg->phase_r2_off[k]);
+                if (na > 16 || nb > 16) return fail(SCAR_ERR_UNSUPPORTED, "phasing string longer than 16 nt");
+                if (na == 0) p.r1_len = 0;
+                else if (!acgt_only(a, na)) p.r1_len = 0xFF;
+                else { p.r1_len = (uint8_t)na; p.r1_code = (uint32_t)encode_bases(a, na); }
+                if (nb == 0) p.r2_len = 0;
+                else if (!acgt_only(b, nb)) p.r2_len = 0xFF;
+                else {
+                    uint8_t rcb[16];
+                    for (int i = 0; i < nb; ++i) rcb[i] = comp_host(b[nb - 1 - i]);   // read suffix == rcomp(R2 string)
+                    p.r2_len = (uint8_t)nb; p.r2_code = (uint32_t)encode_bases(rcb, nb);
+                }
+                phases.push_back(p);
+            }
+            m.n_phase = k1 - k0;
+        }
+        c->h_targets.push_back(m);
+    }
+    c->do_phasing = (cfg->phase_off && cfg->platform == SCAR_PLATFORM_ILLUMINA) ? 1 : 0;
+    if (blob.size() % 2) blob.push_back(make_uint2(0u, 0u));   // 16-byte multiple for the bulk copy
+    c->table_bytes = (uint32_t)(blob.size() * sizeof(uint2));
+    c->smem_tables = c->table_bytes <= 160 * 1024;
+
+    int rc;
+    if ((rc = upload(&c->d_tables, blob))) return rc;
+    if ((rc = upload(&c->d_targets, c->h_targets))) return rc;
+    if ((rc = upload(&c->d_phases, phases))) return rc;
+    std::vector<int32_t> st(cfg->sample_target, cfg->sample_target + cfg->n_samples);
+    for (int s = 0; s < cfg->n_samples; ++s)
+        if (st[s] < 0 || st[s] >= cfg->n_targets) return fail(SCAR_ERR_INVALID, "sample %d: target id %d out of range", s, st[s]);
+    if ((rc = upload(&c->d_sample_target, st))) return rc;
+    if ((rc = build_demux(c, cfg))) return rc;
+
+    // accumulators
+    uint64_t cap = cfg->table_capacity > 0 ? (uint64_t)cfg->table_capacity : (1ull << 22);
+    if (cap & (cap - 1)) return fail(SCAR_ERR_INVALID, "table_capacity must be a power of two");
+    c->capacity = cap;
+    CU(cudaMalloc((void **)&c->d_slots, cap * sizeof(ScarTableSlot)));
+    c->acc_words = 8 + (size_t)c->n_samples * SCAR_N_COUNTERS + (size_t)c->n_samples * 2 * SCAR_PHASE_BINS;
+    CU(cudaMalloc((void **)&c->d_acc, c->acc_words * sizeof(unsigned long long)));
+    c->d_n_entries = c->d_acc; c->d_unassigned = c->d_acc + 1; c->d_collisions = c->d_acc + 2; c->d_export_n = c->d_acc + 3;
+    c->d_counters = c->d_acc + 8; c->d_phase_hist = c->d_counters + (size_t)c->n_samples * SCAR_N_COUNTERS;
+    CU(cudaMalloc((void **)&c->d_status, sizeof(int32_t)));
+    if ((rc = scar_reset(c))) return rc;
+    guard.c = nullptr;
+    *out = c;
+    return SCAR_OK;
+}
+
+extern "C" int scar_reset(scar_ctx *c)
+{
+    if (!c) return fail(SCAR_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemset(c->d_slots, 0, c->capacity * sizeof(ScarTableSlot)));
+    CU(cudaMemset(c->d_acc, 0, c->acc_words * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_status, 0, sizeof(int32_t)));
+    CU(cudaDeviceSynchronize());
+    return SCAR_OK;
+}
+
+extern "C" int scar_cells_per_read(const scar_ctx *c) { return c ? c->W : 0; }
+
+extern "C" int scar_window_counts(const scar_ctx *c, int32_t t, int32_t *n_left, int32_t *n_right)
+{
+    if (!c || t < 0 || t >= c->n_targets) return fail(SCAR_ERR_INVALID, "bad target");
+    if (n_left) *n_left = c->h_targets[t].n_left;
+    if (n_right) *n_right = c->h_targets[t].n_right;
+    return SCAR_OK;
+}
+
+// ---- stage entry points (device pointers) ---------------------------------------------------------
+extern "C" int scar_pack_dev(scar_ctx *c, const scar_ragged *seq, int64_t n, uint64_t *cells, uint16_t *lens, void *stream)
+{
+    if (!c || !seq || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(scar_launch_pack(*seq, n, c->W, c->platform, cells, lens, c->d_status, c->sm_count, (cudaStream_t)stream, &c->launches));
+    return SCAR_OK;
+}
+
+extern "C" int scar_demux_dev(scar_ctx *c, const scar_ragged *seq, const scar_ragged *f0, const scar_ragged *f1,
+                              int64_t n, uint16_t *samples, void *stream)
+{
+    if (!c || n < 0 || !samples) return fail(SCAR_ERR_INVALID, "bad argument");
+    if (c->platform == SCAR_PLATFORM_ILLUMINA ? (!f0 || !f1) : !seq)
+        return fail(SCAR_ERR_INVALID, "demux inputs missing for platform %d", c->platform);
+    CU(cudaSetDevice(c->device));
+    K2Params P; memset(&P, 0, sizeof(P));
+    if (seq) P.seq = *seq; if (f0) P.f0 = *f0; if (f1) P.f1 = *f1;
+    P.samples = samples; P.n_reads = n; P.class_map = c->d_class_map; P.right = c->d_right; P.left = c->d_left;
+    P.peq = c->d_peq; P.first_sample = c->d_first_sample; P.n_right = c->n_right; P.n_left = c->n_left;
+    P.n_classes = c->n_classes; P.platform = c->platform; P.mismatch = c->mismatch;
+    CU(scar_launch_demux(P, c->sm_count, (cudaStream_t)stream, &c->launches));
+    return SCAR_OK;
+}
+
+extern "C" int scar_classify_dev(scar_ctx *c, const uint64_t *cells, const uint16_t *lens, const uint16_t *samples,
+                                 int64_t n, scar_record *records, void *stream)
+{
+    if (!c || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    if (n == 0) return SCAR_OK;
+    CU(cudaSetDevice(c->device));
+    K3Params P; memset(&P, 0, sizeof(P));
+    P.cells = cells; P.lens = lens; P.samples = samples; P.records = records; P.sample_target = c->d_sample_target;
+    P.targets = c->d_targets; P.phases = c->d_phases; P.tables = c->d_tables; P.table_bytes = c->table_bytes;
+    P.n_reads = n; P.W = c->W; P.n_samples = c->n_samples; P.do_phasing = c->do_phasing; P.min_length = c->min_length;
+    P.n_limit = c->n_limit; P.hr_code = c->hr_code; P.hr_len = c->hr_len; P.row_entries = c->W + 2;
+    CU(scar_launch_window(P, c->smem_tables, c->sm_count, (cudaStream_t)stream, &c->launches));
+    return SCAR_OK;
+}
+
+static K4Params k4_params(scar_ctx *c)
+{
+    K4Params P; memset(&P, 0, sizeof(P));
+    P.slots = c->d_slots; P.slot_mask = c->capacity - 1; P.n_entries = c->d_n_entries; P.counters = c->d_counters;
+    P.unassigned = c->d_unassigned; P.phase_hist = c->d_phase_hist; P.status = c->d_status; P.n_samples = c->n_samples;
+    P.platform = c->platform; P.max_probe = (uint32_t)std::min<uint64_t>(c->capacity - 1, 1u << 16);
+    return P;
+}
+
+extern "C" int scar_aggregate_dev(scar_ctx *c, const scar_ragged *seq, const scar_record *records, int64_t n,
+                                  uint64_t first_index, void *stream)
+{
+    if (!c || !seq || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    K4Params P = k4_params(c);
+    P.seq = *seq; P.records = records; P.n_reads = n; P.first_index = first_index;
+    CU(scar_launch_aggregate(P, c->sm_count, (cudaStream_t)stream, &c->launches));
+    return SCAR_OK;
+}
+
+extern "C" int scar_run_dev(scar_ctx *c, const scar_ragged *seq, const scar_ragged *f0, const scar_ragged *f1, int64_t n,
+                            uint64_t first_index, uint64_t *cells, uint16_t *lens, uint16_t *samples,
+                            scar_record *records, void *stream)
+{
+    int rc;
+    if ((rc = scar_demux_dev(c, seq, f0, f1, n, samples, stream))) return rc;
+    if ((rc = scar_pack_dev(c, seq, n, cells, lens, stream))) return rc;
+    if ((rc = scar_classify_dev(c, cells, lens, samples, n, records, stream))) return rc;
+    return scar_aggregate_dev(c, seq, records, n, first_index, stream);
+}
+
+static int check_status(scar_ctx *c)
+{
+    int32_t st = 0;
+    CU(cudaMemcpy(&st, c->d_status, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st & 1) return fail(SCAR_ERR_UNSUPPORTED, "a read is longer than max_read_len=%d", c->max_read_len);
+    if (st & 2) return fail(SCAR_ERR_TABLE_FULL, "scar table full (capacity %llu)", (unsigned long long)c->capacity);
+    return SCAR_OK;
+}
+
+extern "C" int scar_verify_dev(scar_ctx *c, const scar_ragged *seq, const scar_record *records, int64_t n,
+                               uint64_t first_index, int64_t *n_collisions, void *stream)
+{
+    if (!c || !seq || !n_collisions) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(c->d_collisions, 0, sizeof(unsigned long long), s));
+    K4VerifyParams P; memset(&P, 0, sizeof(P));
+    P.seq = *seq; P.records = records; P.n_reads = n; P.first_index = first_index; P.slots = c->d_slots;
+    P.slot_mask = c->capacity - 1; P.n_collisions = c->d_collisions; P.platform = c->platform;
+    P.max_probe = (uint32_t)std::min<uint64_t>(c->capacity - 1, 1u << 16);
+    CU(scar_launch_verify(P, c->sm_count, s));
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, c->d_collisions, sizeof(v), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *n_collisions = (int64_t)v;
+    return v ? fail(SCAR_ERR_HASH_COLLISION, "%llu reads disagree with their table entry", v) : SCAR_OK;
+}
+
+// ---- results --------------------------------------------------------------------------------------
+extern "C" int scar_counters_read(scar_ctx *c, int64_t *counters, int64_t *unassigned)
+{
+    if (!c) return fail(SCAR_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    int rc = check_status(c);
+    if (rc) return rc;
+    if (counters) CU(cudaMemcpy(counters, c->d_counters, (size_t)c->n_samples * SCAR_N_COUNTERS * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (unassigned) CU(cudaMemcpy(unassigned, c->d_unassigned, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return SCAR_OK;
+}
+
+extern "C" int scar_phase_hist_read(scar_ctx *c, int64_t *hist)
+{
+    if (!c || !hist) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(hist, c->d_phase_hist, (size_t)c->n_samples * 2 * SCAR_PHASE_BINS * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return SCAR_OK;
+}
+
+extern "C" int scar_table_size(scar_ctx *c, int64_t *n)
+{
+    if (!c || !n) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    int rc = check_status(c);
+    if (rc) return rc;
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, c->d_n_entries, sizeof(v), cudaMemcpyDeviceToHost));
+    *n = (int64_t)v;
+    return SCAR_OK;
+}
+
+extern "C" int scar_table_export_dev(scar_ctx *c, scar_entry *entries, int64_t capacity, int64_t *n_entries, void *stream)
+{
+    if (!c || !n_entries || capacity < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(c->d_export_n, 0, sizeof(unsigned long long), s));
+    CU(scar_launch_export(c->d_slots, c->capacity, entries, (uint64_t)capacity, c->d_export_n, c->sm_count, s));
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, c->d_export_n, sizeof(v), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *n_entries = (int64_t)v;
+    if ((int64_t)v > capacity) return fail(SCAR_ERR_INVALID, "export buffer too small: %llu entries, capacity %lld", v, (long long)capacity);
+    return SCAR_OK;
+}
+
+extern "C" int scar_table_merge_dev(scar_ctx *c, const scar_entry *entries, int64_t n, void *stream)
+{
+    if (!c || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    K4Params P = k4_params(c);
+    CU(scar_launch_merge(P, entries, (uint64_t)n, c->sm_count, (cudaStream_t)stream));
+    return SCAR_OK;
+}
+
+extern "C" int scar_counters_ptr(scar_ctx *c, void **counters_dev, int64_t *n_int64)
+{
+    if (!c || !counters_dev || !n_int64) return fail(SCAR_ERR_INVALID, "bad argument");
+    // [n_entries(not summed), unassigned, ...] + counters + phase histograms: one contiguous int64 block
+    *counters_dev = c->d_acc; *n_int64 = (int64_t)c->acc_words;
+    return SCAR_OK;
+}
+
+extern "C" int scar_table_read(scar_ctx *c, scar_entry *entries, int64_t capacity, int64_t *n_entries)
+{
+    if (!c || !n_entries) return fail(SCAR_ERR_INVALID, "bad argument");
+    int64_t n = 0;
+    int rc = scar_table_size(c, &n);
+    if (rc) return rc;
+    *n_entries = n;
+    if (!entries) return SCAR_OK;
+    if (capacity < n) return fail(SCAR_ERR_INVALID, "entries buffer too small: need %lld", (long long)n);
+    if (n == 0) return SCAR_OK;
+    scar_entry *d = nullptr;
+    CU(cudaMalloc((void **)&d, (size_t)n * sizeof(scar_entry)));
+    int64_t got = 0;
+    rc = scar_table_export_dev(c, d, n, &got, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy(entries, d, (size_t)n * sizeof(scar_entry), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(SCAR_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    if (rc) return rc;
+    // results_freq_dict order: per sample, first-seen (INDEL_Processing.py:193-196)
+    std::sort(entries, entries + n, [](const scar_entry &a, const scar_entry &b) {
+        return a.sample != b.sample ? a.sample < b.sample : a.first_idx < b.first_idx;
+    });
+    return SCAR_OK;
+}
+
+// ---- host-buffer pipeline -------------------------------------------------------------------------
+template <typename T> static int ensure(T **p, size_t *cap, size_t need)
+{
+    if (need <= *cap && *p) return SCAR_OK;
+    if (*p) CU(cudaFree(*p));
+    *p = nullptr;
+    size_t n = std::max<size_t>(need + need / 8, 256);
+    CU(cudaMalloc((void **)p, n * sizeof(T)));
+    *cap = n;
+    return SCAR_OK;
+}
+
+struct Span { int64_t byte0, byte1; };   // host byte range of items [a, b)
+static Span span_of(const scar_ragged &R, int64_t a, int64_t b)
+{
+    if (R.offsets) return {R.offsets[a], R.offsets[b]};
+    return {a * R.stride, b * R.stride};
+}
+
+// copy items [a,b) of a host ragged list to the device; returns the device-side descriptor
+static int stage_ragged(const scar_ragged &H, int64_t a, int64_t b, uint8_t **dbytes, size_t *dcap,
+                        int64_t **doff, int32_t **dlen, int64_t reads_cap_changed, cudaStream_t s, scar_ragged *D,
+                        int64_t *h2d)
+{
+    (void)reads_cap_changed;
+    const Span sp = span_of(H, a, b);
+    const size_t nbytes = (size_t)(sp.byte1 - sp.byte0);
+    int rc = ensure(dbytes, dcap, nbytes + 16);
+    if (rc) return rc;
+    if (nbytes) CU(cudaMemcpyAsync(*dbytes, H.bytes + sp.byte0, nbytes, cudaMemcpyHostToDevice, s));
+    *h2d += (int64_t)nbytes;
+    memset(D, 0, sizeof(*D));
+    D->stride = H.stride;
+    if (H.offsets) {
+        CU(cudaMemcpyAsync(*doff, H.offsets + a, (size_t)(b - a + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        *h2d += (int64_t)((b - a + 1) * sizeof(int64_t));
+        D->offsets = *doff;
+        D->bytes = *dbytes - sp.byte0;       // original offsets stay valid
+    } else {
+        D->bytes = *dbytes;
+        if (H.lengths) {
+            CU(cudaMemcpyAsync(*dlen, H.lengths + a, (size_t)(b - a) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+            *h2d += (int64_t)((b - a) * sizeof(int32_t));
+            D->lengths = *dlen;
+        }
+    }
+    return SCAR_OK;
+}
+
+static int ensure_hostbuf(scar_ctx *c, HostBuf &b, int64_t reads)
+{
+    if (!b.stream) { CU(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming)); }
+    if (reads <= b.reads_cap) return SCAR_OK;
+    cudaFree(b.seq_off); cudaFree(b.f0_off); cudaFree(b.f1_off); cudaFree(b.seq_len); cudaFree(b.f0_len); cudaFree(b.f1_len);
+    cudaFree(b.cells); cudaFree(b.lens); cudaFree(b.samples); cudaFree(b.records);
+    b.reads_cap = 0;
+    const size_t n = (size_t)reads;
+    CU(cudaMalloc((void **)&b.seq_off, (n + 1) * sizeof(int64_t)));
+    CU(cudaMalloc((void **)&b.f0_off, (n + 1) * sizeof(int64_t)));
+    CU(cudaMalloc((void **)&b.f1_off, (n + 1) * sizeof(int64_t)));
+    CU(cudaMalloc((void **)&b.seq_len, n * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&b.f0_len, n * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&b.f1_len, n * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&b.cells, n * c->W * sizeof(uint64_t)));
+    CU(cudaMalloc((void **)&b.lens, n * sizeof(uint16_t)));
+    CU(cudaMalloc((void **)&b.samples, n * sizeof(uint16_t)));
+    CU(cudaMalloc((void **)&b.records, n * sizeof(scar_record)));
+    b.reads_cap = reads;
+    return SCAR_OK;
+}
+
+extern "C" int scar_process_host(scar_ctx *c, const scar_ragged *seq, const scar_ragged *f0, const scar_ragged *f1,
+                                 int64_t n, uint64_t first_index, scar_record *records)
+{
+    if (!c || !seq || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    if (c->platform == SCAR_PLATFORM_ILLUMINA && (!f0 || !f1)) return fail(SCAR_ERR_INVALID, "Illumina needs the two header index fields");
+    CU(cudaSetDevice(c->device));
+    const int64_t chunk = std::min<int64_t>(c->chunk_reads, std::max<int64_t>(n, 1));
+    int k = 0;
+    int64_t h2d = 0;
+    for (int64_t a = 0; a < n; a += chunk, ++k) {
+        const int64_t b = std::min(n, a + chunk);
+        HostBuf &B = c->buf[k % NBUF];
+        int rc = ensure_hostbuf(c, B, chunk);
+        if (rc) return rc;
+        if (k >= NBUF) CU(cudaEventSynchronize(B.done));     // buffer reuse: its previous chunk has drained
+        scar_ragged dseq, df0, df1;
+        if ((rc = stage_ragged(*seq, a, b, &B.seq, &B.seq_cap, &B.seq_off, &B.seq_len, 0, B.stream, &dseq, &h2d))) return rc;
+        if (c->platform == SCAR_PLATFORM_ILLUMINA) {
+            if ((rc = stage_ragged(*f0, a, b, &B.f0, &B.f0_cap, &B.f0_off, &B.f0_len, 0, B.stream, &df0, &h2d))) return rc;
+            if ((rc = stage_ragged(*f1, a, b, &B.f1, &B.f1_cap, &B.f1_off, &B.f1_len, 0, B.stream, &df1, &h2d))) return rc;
+        }
+        // device descriptors index items from 0 of the chunk
+        if (dseq.offsets) dseq.offsets = B.seq_off;
+        if ((rc = scar_run_dev(c, &dseq, c->platform == SCAR_PLATFORM_ILLUMINA ? &df0 : nullptr,
+                               c->platform == SCAR_PLATFORM_ILLUMINA ? &df1 : nullptr, b - a, first_index + (uint64_t)a,
+                               B.cells, B.lens, B.samples, B.records, B.stream))) return rc;
+        if (records)
+            CU(cudaMemcpyAsync(records + a, B.records, (size_t)(b - a) * sizeof(scar_record), cudaMemcpyDeviceToHost, B.stream));
+        CU(cudaEventRecord(B.done, B.stream));
+    }
+    for (int i = 0; i < NBUF; ++i) if (c->buf[i].stream) CU(cudaStreamSynchronize(c->buf[i].stream));
+    return check_status(c);
+}
+
+// ---- Sequence_Magic.match_maker batch -------------------------------------------------------------
+extern "C" int scar_match_maker_batch(int32_t device, const scar_ragged *query, const scar_ragged *unknown, int64_t n, int32_t *out)
+{
+    if (!query || !unknown || !out || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    if (n == 0) return SCAR_OK;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SCAR_ERR_CUDA, "CUDA device %d not present", device);
+    CU(cudaSetDevice(device));
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t m = query->offsets ? query->offsets[i + 1] - query->offsets[i] : (query->lengths ? query->lengths[i] : query->stride);
+        if (m > 64) return fail(SCAR_ERR_UNSUPPORTED, "query %lld longer than 64", (long long)i);
+    }
+    uint8_t *dq = nullptr, *du = nullptr; int64_t *dqo = nullptr, *duo = nullptr; int32_t *dql = nullptr, *dul = nullptr, *dout = nullptr;
+    size_t cq = 0, cu_ = 0;
+    int rc = SCAR_OK;
+    int64_t h2d = 0;
+    scar_ragged Dq, Du;
+    auto cleanup = [&]() { cudaFree(dq); cudaFree(du); cudaFree(dqo); cudaFree(duo); cudaFree(dql); cudaFree(dul); cudaFree(dout); };
+    if (cudaMalloc((void **)&dqo, (n + 1) * sizeof(int64_t)) != cudaSuccess || cudaMalloc((void **)&duo, (n + 1) * sizeof(int64_t)) != cudaSuccess ||
+        cudaMalloc((void **)&dql, n * sizeof(int32_t)) != cudaSuccess || cudaMalloc((void **)&dul, n * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&dout, n * sizeof(int32_t)) != cudaSuccess) { cleanup(); return fail(SCAR_ERR_NOMEM, "cudaMalloc failed"); }
+    if (!(rc = stage_ragged(*query, 0, n, &dq, &cq, &dqo, &dql, 0, nullptr, &Dq, &h2d)) &&
+        !(rc = stage_ragged(*unknown, 0, n, &du, &cu_, &duo, &dul, 0, nullptr, &Du, &h2d))) {
+        cudaError_t e = scar_launch_match_maker(Dq, Du, n, dout, nullptr);
+        if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(SCAR_ERR_CUDA, "match_maker kernel failed: %s", cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
+}

@@ -1,0 +1,150 @@
+// scar_internal.cuh — shared device/host definitions of libscar_b200 (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/scar_b200.h"
+#include "scar_demux_core.h"
+
+#define SCAR_KMER 10                 // hard-coded window (INDEL_Processing.py:67,76; SlidingWindow.pyx:49-50)
+#define SCAR_KEY_MASK 0xFFFFFu       // 10 bases x 2 bits
+#define SCAR_KEY_TAG 0x100000u       // bit 20 set in every stored key so that an empty slot (0) never matches
+#define SCAR_MAX_WINDOWS 2048        // window index i is stored in 11 bits
+#define SCAR_MAX_PHASES 32
+#define SCAR_MAX_INDEX_LEN 64        // Myers bit-vector width
+#define SCAR_MAX_CLASSES 16          // distinct byte values over all index sequences (+ class 0 = other)
+
+// ---- base encoding --------------------------------------------------------------------------------
+// code = (byte >> 1) & 3 : A=0 C=1 T=2 G=3 ; complement = code ^ 2.
+__host__ __device__ __forceinline__ uint32_t scar_base_code(uint8_t b) { return (b >> 1) & 3u; }
+__host__ __device__ __forceinline__ bool scar_base_valid(uint8_t b)
+{
+    return b == 'A' || b == 'C' || b == 'G' || b == 'T';
+}
+
+// A packed read row is `cells` 64-bit cells; cell j covers bases [16j, 16j+16):
+//   bits  0..31  2-bit codes, base k of the cell at bits 2k..2k+1
+//   bits 32..47  ACGT mask (1 = byte is one of A,C,G,T)
+//   bits 48..63  N mask    (1 = byte is 'N')
+// bases past the read's length have all three fields 0.
+
+struct ScarTargetMeta {
+    int32_t cutsite, length;
+    int32_t n_left, n_right;
+    uint32_t left_off, right_off;      // bucket (uint2) offsets into the table blob
+    uint32_t left_mult, right_mult;    // bucket = (key * mult) >> shift
+    uint32_t left_shift, right_shift;
+    uint32_t cutwindow_key;            // SlidingWindow.pyx:56-60 test; 0xFFFFFFFF = none
+    int32_t phase_off, n_phase;
+    int32_t pad;
+};
+
+struct ScarPhase {
+    uint32_t r1_code, r2_code;         // r2_code = codes of rcomp(R2 string): compared with the read's suffix
+    uint8_t r1_len, r2_len;            // 0 = empty string; 0xFF = contains non-ACGT bytes (can never match)
+    uint8_t pad[2];
+};
+
+// 64-bit mixers (splitmix64 / murmur3 finalisers) for the scar-key identity
+__host__ __device__ __forceinline__ uint64_t scar_mix1(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t scar_mix2(uint64_t k)
+{
+    k ^= k >> 33; k *= 0xFF51AFD7ED558CCDull;
+    k ^= k >> 33; k *= 0xC4CEB9FE1A85EC53ull;
+    return k ^ (k >> 33);
+}
+
+struct ScarTableSlot {                  // 32 bytes, zero-initialised
+    unsigned long long h1;              // 0 = empty
+    unsigned long long h2;              // 0 = not yet published
+    unsigned long long inv_first;       // ~first_idx, combined with atomicMax
+    uint32_t count;
+    uint32_t sample;
+};
+
+// ---- kernel parameter blocks and launchers ---------------------------------------------------------
+struct K1Params {
+    scar_ragged seq;      // device pointers
+    uint64_t *cells;      // [n][W]
+    uint16_t *lens;       // [n]
+    int64_t n_reads;
+    int32_t W;
+    int32_t platform;
+    int32_t *status;      // device flag: bit 0 set when a read is longer than 16*W
+};
+
+struct K2Params {
+    scar_ragged seq, f0, f1;   // device pointers
+    uint16_t *samples;         // [n] out
+    int64_t n_reads;
+    const uint8_t *class_map;  // [256] byte -> class (0 = appears in no index string)
+    const DemuxString *right;  // distinct right_index strings (scored against u0)
+    const DemuxString *left;   // distinct left_index strings (scored against u1)
+    const uint64_t *peq;
+    const uint16_t *first_sample; // [n_right][n_left] first manifest row with that pair, 0xFFFF = none
+    int32_t n_right, n_left, n_classes;
+    int32_t platform, mismatch;
+};
+
+struct K3Params {
+    const uint64_t *cells;        // [n][W]
+    const uint16_t *lens;         // [n]
+    const uint16_t *samples;      // [n]
+    scar_record *records;         // [n]
+    const int32_t *sample_target; // [n_samples]
+    const ScarTargetMeta *targets;
+    const ScarPhase *phases;
+    const uint2 *tables;          // bucket blob, all targets
+    uint32_t table_bytes;         // multiple of 16
+    int64_t n_reads;
+    int32_t W;                    // cells per read
+    int32_t n_samples;
+    int32_t do_phasing;
+    int32_t min_length;
+    double n_limit;
+    uint64_t hr_code;             // donor, 2 bits/base
+    int32_t hr_len;
+    int32_t row_entries;          // per-warp staging entries (W + 2)
+};
+
+struct K4Params {
+    scar_ragged seq;             // raw bytes (device), for the ins / mh segment
+    const scar_record *records;
+    int64_t n_reads;
+    uint64_t first_index;
+    ScarTableSlot *slots;
+    uint64_t slot_mask;          // capacity - 1
+    unsigned long long *n_entries;
+    unsigned long long *counters;   // [n_samples][SCAR_N_COUNTERS]
+    unsigned long long *unassigned;
+    unsigned long long *phase_hist; // [n_samples][2][SCAR_PHASE_BINS]
+    int32_t *status;             // bit 1: table full
+    int32_t n_samples;
+    int32_t platform;
+    int32_t use_smem;            // counters + phase histograms staged in shared memory
+    uint32_t max_probe;
+};
+
+struct K4VerifyParams {
+    scar_ragged seq; const scar_record *records; int64_t n_reads; uint64_t first_index;
+    const ScarTableSlot *slots; uint64_t slot_mask; unsigned long long *n_collisions; int32_t platform;
+    uint32_t max_probe;
+};
+
+cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count, cudaStream_t stream, int *launches);
+cudaError_t scar_launch_pack(const scar_ragged &seq, int64_t n, int W, int platform, uint64_t *cells,
+                             uint16_t *lens, int32_t *status, int sm_count, cudaStream_t stream, int *launches);
+cudaError_t scar_launch_demux(const K2Params &P, int sm_count, cudaStream_t stream, int *launches);
+cudaError_t scar_launch_match_maker(const scar_ragged &q, const scar_ragged &u, int64_t n, int32_t *out,
+                                    cudaStream_t stream);
+cudaError_t scar_launch_aggregate(K4Params P, int sm_count, cudaStream_t stream, int *launches);
+cudaError_t scar_launch_verify(const K4VerifyParams &P, int sm_count, cudaStream_t stream);
+cudaError_t scar_launch_export(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint64_t out_capacity,
+                               unsigned long long *n_out, int sm_count, cudaStream_t stream);
+cudaError_t scar_launch_merge(const K4Params &P, const scar_entry *in, uint64_t n_in, int sm_count, cudaStream_t stream);

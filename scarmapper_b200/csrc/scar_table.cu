@@ -1,0 +1,306 @@
+// scar_table.cu — K4: per-sample counters, phase histograms and the scar frequency table.
+//
+// Replaces stage 4 of ScarSearch.data_processing (reference scarmapper/INDEL_Processing.py:186-196:
+// results_freq_dict[key] = [count, first sub_list]) and the summary_data / read_count_dict /
+// phase_count bookkeeping (:94,147-169,948-975,1173-1198) for a whole batch.
+//
+// The reference key is the text "ldel|rdel|ins|mh|hr".  For one sample (= one target) ldel and rdel
+// are determined by (tlj, trj), and ins / mh are read[clj:crj] / read[crj:clj], so the key is
+// (sample, tlj, trj, kind, segment bytes, hr).  It is identified by two independent 64-bit hashes
+// (128 bits; both must agree).  The table is open-addressed in HBM; a slot keeps the count and the
+// smallest global read index (the reference stores the FIRST read's record and orders ties by
+// first-seen rank).  Reads of one warp that carry the same key are combined before touching memory.
+#include "scar_internal.cuh"
+
+
+__device__ __forceinline__ uint8_t comp_byte(uint8_t c)
+{
+    // Sequence_Magic.rcomp's translate table (Valkyries/Sequence_Magic.py:97-118); unmapped bytes pass
+    switch (c) {
+    case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+    case 'M': return 'K'; case 'R': return 'Y'; case 'Y': return 'R'; case 'K': return 'M';
+    case 'V': return 'B'; case 'H': return 'D'; case 'D': return 'H'; case 'B': return 'V';
+    case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+    case 'm': return 'k'; case 'r': return 'y'; case 'y': return 'r'; case 'k': return 'm';
+    case 'v': return 'b'; case 'h': return 'd'; case 'd': return 'h'; case 'b': return 'v';
+    default: return c;
+    }
+}
+
+// byte q of the STORED sequence (after the platform transform) of a raw read
+__device__ __forceinline__ uint8_t stored_byte(const uint8_t *raw, int rawlen, int platform, int q)
+{
+    if (platform == SCAR_PLATFORM_TRUSEQ) return raw[q + 6];
+    if (platform == SCAR_PLATFORM_RAMSDEN) return comp_byte(raw[rawlen - 1 - q]);
+    return raw[q];
+}
+
+// the two key hashes of a SCAR record
+__device__ __forceinline__ void key_hashes(const scar_record &rec, const uint8_t *raw, int rawlen, int platform,
+                                           uint64_t &h1, uint64_t &h2)
+{
+    int lo = 0, hi = 0; uint64_t kind = 0;
+    if (rec.flags & SCAR_FL_INSERTION) { lo = rec.clj; hi = rec.crj; kind = 1; }
+    else if (rec.flags & SCAR_FL_MICROHOM) { lo = rec.crj; hi = rec.clj; kind = 2; }
+    const uint64_t hdr = (uint64_t)rec.sample | ((uint64_t)rec.tlj << 16) | ((uint64_t)rec.trj << 32) |
+                         (kind << 48) | ((uint64_t)((rec.flags & SCAR_FL_HR) ? 1 : 0) << 50) |
+                         ((uint64_t)(hi - lo) << 51);
+    h1 = scar_mix1(hdr ^ 0x9E3779B97F4A7C15ull);
+    h2 = scar_mix2(hdr + 0xD6E8FEB86659FD93ull);
+    for (int q = lo; q < hi; q += 8) {
+        uint64_t w = 0;
+        const int n = min(8, hi - q);
+        for (int k = 0; k < n; ++k) w |= (uint64_t)stored_byte(raw, rawlen, platform, q + k) << (8 * k);
+        h1 = scar_mix1(h1 ^ w);
+        h2 = scar_mix2(h2 + w * 0xA24BAED4963EE407ull + 1ull);
+    }
+    if (h1 == 0) h1 = 1;
+    if (h2 == 0) h2 = 1;
+}
+
+__device__ __forceinline__ void table_insert(const K4Params &P, uint64_t h1, uint64_t h2, uint32_t n,
+                                             uint64_t first, uint32_t sample)
+{
+    uint64_t slot = h1 & P.slot_mask;
+    for (uint32_t probe = 0; probe <= P.max_probe; ++probe) {
+        ScarTableSlot *s = P.slots + slot;
+        const unsigned long long prev = atomicCAS(&s->h1, 0ull, (unsigned long long)h1);
+        if (prev == 0ull || prev == h1) {
+            if (prev == 0ull) atomicAdd(P.n_entries, 1ull);
+            // the first thread to publish h2 defines the slot; a different h2 under the same h1 is
+            // a different key and keeps probing
+            const unsigned long long p2 = atomicCAS(&s->h2, 0ull, (unsigned long long)h2);
+            if (p2 == 0ull || p2 == h2) {
+                atomicAdd(&s->count, n);
+                atomicMax(&s->inv_first, ~(unsigned long long)first);
+                s->sample = sample;
+                return;
+            }
+        }
+        slot = (slot + 1) & P.slot_mask;
+    }
+    atomicOr(P.status, 2);
+}
+
+__global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
+{
+    extern __shared__ unsigned int s_hist[];   // [n_samples][SCAR_N_COUNTERS + 2*SCAR_PHASE_BINS] when use_smem
+    const int per_sample = SCAR_N_COUNTERS + 2 * SCAR_PHASE_BINS;
+    __shared__ unsigned int s_unassigned;
+    if (P.use_smem) {
+        for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) s_hist[i] = 0;
+    }
+    if (threadIdx.x == 0) s_unassigned = 0;
+    __syncthreads();
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+
+    const int64_t n_round = (P.n_reads + 31) & ~(int64_t)31;   // keep warps converged for the collectives
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_round;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const bool in_range = r < P.n_reads;
+        __align__(16) scar_record rec;
+        if (in_range) *reinterpret_cast<uint4 *>(&rec) = __ldg(reinterpret_cast<const uint4 *>(P.records + r));
+        else { rec.status = 0xFF; rec.flags = 0; rec.sample = 0; rec.hr_n = 0; rec.phase_r1 = rec.phase_r2 = SCAR_PHASE_NA; }
+
+        // ---- counters (summary_data, read_count_dict, phase_count)
+        if (in_range) {
+            if (rec.status == SCAR_ST_UNASSIGNED) atomicAdd(&s_unassigned, 1u);
+            else {
+                const uint32_t s = rec.sample;
+                uint32_t inc = 1u << SCAR_CT_ASSIGNED;
+                if (rec.status >= SCAR_ST_NO_JUNCTION) inc |= 1u << SCAR_CT_PASSING;
+                if (rec.status == SCAR_ST_FILTERED) inc |= 1u << SCAR_CT_FILTERED;
+                if (rec.status == SCAR_ST_NO_JUNCTION) inc |= 1u << SCAR_CT_NO_JUNCTION;
+                if (rec.status == SCAR_ST_NO_CUT) inc |= 1u << SCAR_CT_NO_CUT;
+                if (rec.status == SCAR_ST_N_INSERTION) inc |= 1u << SCAR_CT_N_INSERTION;
+                if (rec.status == SCAR_ST_SCAR) {
+                    inc |= 1u << SCAR_CT_SCAR;
+                    if (rec.flags & SCAR_FL_LEFT_DEL) inc |= 1u << SCAR_CT_LEFT_DEL;
+                    if (rec.flags & SCAR_FL_RIGHT_DEL) inc |= 1u << SCAR_CT_RIGHT_DEL;
+                    if (rec.flags & SCAR_FL_INSERTION) inc |= 1u << SCAR_CT_INSERTION;
+                    if (rec.flags & SCAR_FL_MICROHOM) inc |= 1u << SCAR_CT_MICROHOM;
+                }
+                if (rec.hr_n) inc |= 1u << SCAR_CT_HR_FIRST;
+                const int b1 = rec.phase_r1 == SCAR_PHASE_NA ? SCAR_PHASE_BINS - 1 : rec.phase_r1 + 1;
+                const int b2 = rec.phase_r2 == SCAR_PHASE_NA ? SCAR_PHASE_BINS - 1 : rec.phase_r2 + 1;
+                if (P.use_smem) {
+                    unsigned int *h = s_hist + s * per_sample;
+                    for (uint32_t m = inc; m; m &= m - 1) atomicAdd(h + (__ffs(m) - 1), 1u);
+                    if (rec.hr_n > 1) atomicAdd(h + SCAR_CT_HR_MORE, (unsigned)(rec.hr_n - 1));
+                    atomicAdd(h + SCAR_N_COUNTERS + b1, 1u);
+                    atomicAdd(h + SCAR_N_COUNTERS + SCAR_PHASE_BINS + b2, 1u);
+                } else {
+                    unsigned long long *c = P.counters + (size_t)s * SCAR_N_COUNTERS;
+                    for (uint32_t m = inc; m; m &= m - 1) atomicAdd(c + (__ffs(m) - 1), 1ull);
+                    if (rec.hr_n > 1) atomicAdd(c + SCAR_CT_HR_MORE, (unsigned long long)(rec.hr_n - 1));
+                    unsigned long long *ph = P.phase_hist + (size_t)s * 2 * SCAR_PHASE_BINS;
+                    atomicAdd(ph + b1, 1ull);
+                    atomicAdd(ph + SCAR_PHASE_BINS + b2, 1ull);
+                }
+            }
+        }
+
+        // ---- scar table
+        const bool scar = in_range && rec.status == SCAR_ST_SCAR;
+        const uint32_t active = __ballot_sync(FULL, scar);
+        if (scar) {
+            const uint8_t *raw; int rawlen;
+            if (P.seq.offsets) { const int64_t st = P.seq.offsets[r]; raw = P.seq.bytes + st; rawlen = (int)(P.seq.offsets[r + 1] - st); }
+            else { raw = P.seq.bytes + r * P.seq.stride; rawlen = P.seq.lengths ? P.seq.lengths[r] : (int)P.seq.stride; }
+            uint64_t h1, h2;
+            key_hashes(rec, raw, rawlen, P.platform, h1, h2);
+            // combine the lanes of this warp that carry the same key
+            const uint32_t peers = __match_any_sync(active, (unsigned long long)h1);
+            const int leader = __ffs(peers) - 1;
+            const uint64_t lh2 = __shfl_sync(peers, (unsigned long long)h2, leader);
+            const bool same = lh2 == h2;
+            const uint32_t agg = __ballot_sync(peers, same);
+            if (same) {
+                const uint32_t rmin = __reduce_min_sync(agg, (uint32_t)(r & 0xFFFFFFFFll));
+                if (lane == leader) {
+                    const uint64_t base = (uint64_t)r - (uint32_t)(r & 0xFFFFFFFFll);
+                    table_insert(P, h1, h2, (uint32_t)__popc(agg), P.first_index + base + rmin, rec.sample);
+                }
+            } else {
+                table_insert(P, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample);
+            }
+        }
+    }
+    __syncthreads();
+    if (P.use_smem) {
+        for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) {
+            const unsigned int v = s_hist[i];
+            if (!v) continue;
+            const int s = i / per_sample, c = i - s * per_sample;
+            if (c < SCAR_N_COUNTERS) atomicAdd(P.counters + (size_t)s * SCAR_N_COUNTERS + c, (unsigned long long)v);
+            else atomicAdd(P.phase_hist + (size_t)s * 2 * SCAR_PHASE_BINS + (c - SCAR_N_COUNTERS), (unsigned long long)v);
+        }
+    }
+    if (threadIdx.x == 0 && s_unassigned) atomicAdd(P.unassigned, (unsigned long long)s_unassigned);
+}
+
+// ---- verification: every SCAR read's full key equals the key of its slot's first read ------------
+
+__global__ void __launch_bounds__(256) scar_verify_kernel(const K4VerifyParams P)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        __align__(16) scar_record rec;
+        *reinterpret_cast<uint4 *>(&rec) = __ldg(reinterpret_cast<const uint4 *>(P.records + r));
+        if (rec.status != SCAR_ST_SCAR) continue;
+        const uint8_t *raw; int rawlen;
+        if (P.seq.offsets) { const int64_t st = P.seq.offsets[r]; raw = P.seq.bytes + st; rawlen = (int)(P.seq.offsets[r + 1] - st); }
+        else { raw = P.seq.bytes + r * P.seq.stride; rawlen = P.seq.lengths ? P.seq.lengths[r] : (int)P.seq.stride; }
+        uint64_t h1, h2;
+        key_hashes(rec, raw, rawlen, P.platform, h1, h2);
+        uint64_t slot = h1 & P.slot_mask;
+        bool found = false;
+        for (uint32_t probe = 0; probe <= P.max_probe; ++probe) {
+            const ScarTableSlot s = P.slots[slot];
+            if (s.h1 == 0) break;
+            if (s.h1 == h1 && s.h2 == h2) {
+                found = true;
+                const uint64_t first = ~s.inv_first;
+                // the representative is compared only when it lies in this resident batch
+                if (first >= P.first_index && first < P.first_index + (uint64_t)P.n_reads) {
+                    const int64_t q = (int64_t)(first - P.first_index);
+                    __align__(16) scar_record rr;
+                    *reinterpret_cast<uint4 *>(&rr) = __ldg(reinterpret_cast<const uint4 *>(P.records + q));
+                    const uint8_t *raw2; int rawlen2;
+                    if (P.seq.offsets) { const int64_t st = P.seq.offsets[q]; raw2 = P.seq.bytes + st; rawlen2 = (int)(P.seq.offsets[q + 1] - st); }
+                    else { raw2 = P.seq.bytes + q * P.seq.stride; rawlen2 = P.seq.lengths ? P.seq.lengths[q] : (int)P.seq.stride; }
+                    bool eq = rr.status == SCAR_ST_SCAR && rr.sample == rec.sample && rr.tlj == rec.tlj && rr.trj == rec.trj &&
+                              ((rr.flags ^ rec.flags) & (SCAR_FL_INSERTION | SCAR_FL_MICROHOM | SCAR_FL_HR)) == 0;
+                    int lo = 0, hi = 0, lo2 = 0, hi2 = 0;
+                    if (rec.flags & SCAR_FL_INSERTION) { lo = rec.clj; hi = rec.crj; } else if (rec.flags & SCAR_FL_MICROHOM) { lo = rec.crj; hi = rec.clj; }
+                    if (rr.flags & SCAR_FL_INSERTION) { lo2 = rr.clj; hi2 = rr.crj; } else if (rr.flags & SCAR_FL_MICROHOM) { lo2 = rr.crj; hi2 = rr.clj; }
+                    eq = eq && (hi - lo) == (hi2 - lo2);
+                    for (int k = 0; eq && k < hi - lo; ++k)
+                        eq = stored_byte(raw, rawlen, P.platform, lo + k) == stored_byte(raw2, rawlen2, P.platform, lo2 + k);
+                    if (!eq) atomicAdd(P.n_collisions, 1ull);
+                }
+                break;
+            }
+            slot = (slot + 1) & P.slot_mask;
+        }
+        if (!found) atomicAdd(P.n_collisions, 1ull);
+    }
+}
+
+// ---- export (compaction) and merge ---------------------------------------------------------------
+__global__ void scar_export_kernel(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out,
+                                   uint64_t out_capacity, unsigned long long *n_out)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const ScarTableSlot s = slots[i];
+        if (s.h1 == 0) continue;
+        const unsigned long long pos = atomicAdd(n_out, 1ull);
+        if (pos < out_capacity) {
+            scar_entry e; e.h1 = s.h1; e.h2 = s.h2; e.first_idx = ~s.inv_first; e.count = s.count;
+            e.sample = (uint16_t)s.sample; e.pad = 0;
+            out[pos] = e;
+        }
+    }
+}
+
+__global__ void scar_merge_kernel(K4Params P, const scar_entry *in, uint64_t n_in)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const scar_entry e = in[i];
+        table_insert(P, e.h1, e.h2, e.count, e.first_idx, e.sample);
+    }
+}
+
+cudaError_t scar_launch_aggregate(K4Params P, int sm_count, cudaStream_t stream, int *launches)
+{
+    if (P.n_reads <= 0) return cudaSuccess;
+    const int threads = 256;
+    const size_t per_sample = (SCAR_N_COUNTERS + 2 * SCAR_PHASE_BINS) * sizeof(unsigned int);
+    size_t smem = (size_t)P.n_samples * per_sample;
+    P.use_smem = smem <= 96 * 1024;
+    if (!P.use_smem) smem = 0;
+    cudaError_t e = cudaFuncSetAttribute(scar_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
+    if (e != cudaSuccess) return e;
+    int64_t blocks = (P.n_reads + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count * 4;
+    if (blocks > cap) blocks = cap;
+    scar_aggregate_kernel<<<(unsigned)blocks, threads, smem, stream>>>(P);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t scar_launch_verify(const K4VerifyParams &P, int sm_count, cudaStream_t stream)
+{
+    if (P.n_reads <= 0) return cudaSuccess;
+    const int threads = 256;
+    int64_t blocks = (P.n_reads + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    scar_verify_kernel<<<(unsigned)blocks, threads, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t scar_launch_export(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint64_t out_capacity,
+                               unsigned long long *n_out, int sm_count, cudaStream_t stream)
+{
+    const int threads = 256;
+    int64_t blocks = (int64_t)((capacity + threads - 1) / threads);
+    const int64_t cap = (int64_t)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    scar_export_kernel<<<(unsigned)blocks, threads, 0, stream>>>(slots, capacity, out, out_capacity, n_out);
+    return cudaGetLastError();
+}
+
+cudaError_t scar_launch_merge(const K4Params &P, const scar_entry *in, uint64_t n_in, int sm_count, cudaStream_t stream)
+{
+    if (n_in == 0) return cudaSuccess;
+    const int threads = 256;
+    int64_t blocks = (int64_t)((n_in + threads - 1) / threads);
+    const int64_t cap = (int64_t)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    scar_merge_kernel<<<(unsigned)blocks, threads, 0, stream>>>(P, in, n_in);
+    return cudaGetLastError();
+}

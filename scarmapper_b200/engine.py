@@ -1,0 +1,304 @@
+"""
+engine.py — Python face of the C ABI: one ScarEngine per GPU.
+
+ScarEngine holds what the reference computes once per run (window tables, index tables, phasing
+tables: INDEL_Processing.py:57-80,1063-1124; TargetMapper.py:30-71) and runs the batched hot path
+K2 demux -> K1 pack -> K3 sliding window -> K4 aggregation on its device.  Two ways in:
+
+  process_host(reads, f0, f1)   host buffers; H2D / kernels / D2H are pipelined inside the library
+  run_resident(batch)           inputs already in HBM (torch uint8 tensors), kernels only
+
+Both accumulate into the engine's per-sample counters, phase histograms and scar table, read back
+with counters() / phase_hist() / table().
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _native as N
+
+
+def _b(x) -> bytes:
+    return x.encode("latin-1") if isinstance(x, str) else bytes(x)
+
+
+def _csr(strings):
+    bs = [_b(s) for s in strings]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs])
+    data = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if off[-1] else np.zeros(1, np.uint8)
+    return data, off
+
+
+class HostRagged:
+    """A list of byte strings in host memory: CSR (bytes + int64 offsets) or fixed stride
+    (2-D uint8 array, optional int32 lengths).  Keeps the numpy arrays alive for the C call."""
+
+    def __init__(self, bytes_, offsets=None, lengths=None, stride=0, n=None):
+        self.bytes = np.ascontiguousarray(bytes_, dtype=np.uint8)
+        self.offsets = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+        self.lengths = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int32)
+        self.stride = int(stride)
+        self.n = int(n if n is not None else (len(self.offsets) - 1 if self.offsets is not None else
+                                              self.bytes.size // max(self.stride, 1)))
+
+    @classmethod
+    def from_strings(cls, strings):
+        data, off = _csr(strings)
+        return cls(data, offsets=off)
+
+    @classmethod
+    def from_matrix(cls, mat, lengths=None):
+        mat = np.ascontiguousarray(mat, dtype=np.uint8)
+        return cls(mat.reshape(-1), lengths=lengths, stride=mat.shape[1], n=mat.shape[0])
+
+    def max_len(self) -> int:
+        if self.offsets is not None:
+            return int(np.max(np.diff(self.offsets))) if self.n else 0
+        if self.lengths is not None:
+            return int(self.lengths.max()) if self.n else 0
+        return self.stride
+
+    def c_struct(self) -> N.Ragged:
+        return N.Ragged(self.bytes.ctypes.data,
+                        None if self.offsets is None else self.offsets.ctypes.data,
+                        None if self.lengths is None else self.lengths.ctypes.data, self.stride)
+
+
+def as_ragged(x):
+    if x is None or isinstance(x, HostRagged):
+        return x
+    if isinstance(x, np.ndarray) and x.ndim == 2:
+        return HostRagged.from_matrix(x)
+    return HostRagged.from_strings(x)
+
+
+@dataclass
+class ScarProblem:
+    """Static inputs of a run, in the reference's own terms."""
+    targets: list                      # upper-cased target regions (ScarSearch.target_region)
+    cutsites: list                     # ScarSearch.cutsite per target
+    sample_target: list                # target id per manifest row
+    left_index: list = None            # index_dict[s][0] (Master_Index_File column 3, upper-cased)
+    right_index: list = None           # index_dict[s][2] (Master_Index_File column 2, upper-cased)
+    platform: str = "Illumina"
+    mismatch: int = -1                 # -1: platform default (INDEL_Processing.py:1142-1147)
+    phasing: list = None               # per target ([R1 strings], [R2 strings]) (TargetMapper.phasing)
+    hr_donor: str = ""
+    n_limit: float = 0.01
+    min_length: int = 100
+    max_read_len: int = 160
+    table_capacity: int = 0
+    cutwindows: list = None            # per-read drop-in only: 10-nt cutwindow per target
+    extra: dict = field(default_factory=dict)
+
+
+def cutsite_search(target, sgrna, reverse_comp: bool) -> int:
+    """ScarSearch.cutsite_search (INDEL_Processing.py:759-795); raises ScarError when the sgRNA does not map."""
+    t, s = _b(target), _b(sgrna)
+    out = C.c_int32(-1)
+    N.check(N.lib().scar_cutsite_search(t, len(t), s, len(s), int(bool(reverse_comp)), C.byref(out)))
+    return out.value
+
+
+class ScarEngine:
+    def __init__(self, prob: ScarProblem, device: int = 0):
+        L = N.lib()
+        self.prob = prob
+        self.device = device
+        self.n_samples = len(prob.sample_target)
+        self.n_targets = len(prob.targets)
+        keep = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data
+
+        tb, to = _csr(prob.targets)
+        lb, lo = _csr(prob.left_index if prob.left_index is not None else [""] * self.n_samples)
+        rb, ro = _csr(prob.right_index if prob.right_index is not None else [""] * self.n_samples)
+        cfg = N.Config()
+        cfg.device = device
+        cfg.platform = N.PLATFORMS[prob.platform] if isinstance(prob.platform, str) else int(prob.platform)
+        cfg.mismatch = prob.mismatch
+        cfg.n_targets = self.n_targets
+        cfg.target_bytes, cfg.target_off = arr(tb, np.uint8), arr(to, np.int64)
+        cfg.target_cutsite = arr(prob.cutsites, np.int32)
+        cfg.n_samples = self.n_samples
+        cfg.sample_target = arr(prob.sample_target, np.int32)
+        cfg.left_index_bytes, cfg.left_index_off = arr(lb, np.uint8), arr(lo, np.int64)
+        cfg.right_index_bytes, cfg.right_index_off = arr(rb, np.uint8), arr(ro, np.int64)
+        if prob.phasing is not None and cfg.platform == 0:
+            r1, r2, poff = [], [], [0]
+            for p1, p2 in prob.phasing:
+                r1 += list(p1); r2 += list(p2); poff.append(len(r1))
+            b1, o1 = _csr(r1)
+            b2, o2 = _csr(r2)
+            cfg.phase_off = arr(poff, np.int32)
+            cfg.phase_r1_bytes, cfg.phase_r1_off = arr(b1, np.uint8), arr(o1, np.int64)
+            cfg.phase_r2_bytes, cfg.phase_r2_off = arr(b2, np.uint8), arr(o2, np.int64)
+        hr = _b(prob.hr_donor or "")
+        if hr:
+            cfg.hr_donor = arr(np.frombuffer(hr, dtype=np.uint8), np.uint8)
+            cfg.hr_len = len(hr)
+        cfg.n_limit = float(prob.n_limit)
+        cfg.min_length = int(prob.min_length)
+        cfg.max_read_len = int(prob.max_read_len)
+        cfg.table_capacity = int(prob.table_capacity)
+        if prob.cutwindows is not None:
+            cw = b"".join((_b(w) + b"\0" * 10)[:10] if len(_b(w)) == 10 else b"\0" * 10 for w in prob.cutwindows)
+            cfg.cutwindow_bytes = arr(np.frombuffer(cw, dtype=np.uint8), np.uint8)
+        ctx = C.c_void_p()
+        N.check(L.scar_ctx_create(C.byref(cfg), C.byref(ctx)))
+        self._ctx = ctx
+        self._L = L
+        self.cells_per_read = L.scar_cells_per_read(ctx)
+
+    # ---- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.scar_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        N.check(self._L.scar_reset(self._ctx))
+
+    def window_counts(self, target: int):
+        a, b = C.c_int32(), C.c_int32()
+        N.check(self._L.scar_window_counts(self._ctx, target, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # ---- host path ------------------------------------------------------------------------------
+    def process_host(self, reads, f0=None, f1=None, first_index: int = 0, want_records: bool = True,
+                     out: np.ndarray | None = None):
+        """Whole path from host buffers.  Returns the per-read records (or None)."""
+        seq, f0, f1 = as_ragged(reads), as_ragged(f0), as_ragged(f1)
+        n = seq.n
+        rec = None
+        if want_records:
+            rec = out if out is not None else np.empty(n, dtype=N.RECORD_DTYPE)
+            assert rec.dtype == N.RECORD_DTYPE and rec.size >= n
+        s, a, b = seq.c_struct(), (f0.c_struct() if f0 else None), (f1.c_struct() if f1 else None)
+        N.check(self._L.scar_process_host(self._ctx, C.byref(s), C.byref(a) if a else None,
+                                          C.byref(b) if b else None, n, first_index,
+                                          rec.ctypes.data if rec is not None else None))
+        return rec
+
+    # ---- device-resident path -------------------------------------------------------------------
+    def make_resident(self, reads, f0=None, f1=None):
+        """Copy a host batch into HBM (torch tensors) and allocate its scratch/outputs."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        seq, f0, f1 = as_ragged(reads), as_ragged(f0), as_ragged(f1)
+
+        def up(r):
+            if r is None:
+                return None
+            d = {"bytes": torch.from_numpy(np.concatenate([r.bytes, np.zeros(16, np.uint8)])).to(dev),
+                 "offsets": None if r.offsets is None else torch.from_numpy(r.offsets).to(dev),
+                 "lengths": None if r.lengths is None else torch.from_numpy(r.lengths).to(dev),
+                 "stride": r.stride}
+            return d
+
+        n = seq.n
+        batch = {"n": n, "seq": up(seq), "f0": up(f0), "f1": up(f1),
+                 "cells": torch.empty((n, self.cells_per_read), dtype=torch.int64, device=dev),
+                 "lens": torch.empty(n, dtype=torch.int16, device=dev),
+                 "samples": torch.empty(n, dtype=torch.int16, device=dev),
+                 "records": torch.empty((n, 16), dtype=torch.uint8, device=dev)}
+        return batch
+
+    @staticmethod
+    def _dev_ragged(d):
+        if d is None:
+            return None
+        return N.Ragged(d["bytes"].data_ptr(), None if d["offsets"] is None else d["offsets"].data_ptr(),
+                        None if d["lengths"] is None else d["lengths"].data_ptr(), d["stride"])
+
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def demux_resident(self, batch):
+        s, a, b = (self._dev_ragged(batch[k]) for k in ("seq", "f0", "f1"))
+        N.check(self._L.scar_demux_dev(self._ctx, C.byref(s), C.byref(a) if a else None, C.byref(b) if b else None,
+                                       batch["n"], batch["samples"].data_ptr(), self._stream()))
+
+    def pack_resident(self, batch):
+        s = self._dev_ragged(batch["seq"])
+        N.check(self._L.scar_pack_dev(self._ctx, C.byref(s), batch["n"], batch["cells"].data_ptr(),
+                                      batch["lens"].data_ptr(), self._stream()))
+
+    def classify_resident(self, batch):
+        N.check(self._L.scar_classify_dev(self._ctx, batch["cells"].data_ptr(), batch["lens"].data_ptr(),
+                                          batch["samples"].data_ptr(), batch["n"], batch["records"].data_ptr(),
+                                          self._stream()))
+
+    def aggregate_resident(self, batch, first_index: int = 0):
+        s = self._dev_ragged(batch["seq"])
+        N.check(self._L.scar_aggregate_dev(self._ctx, C.byref(s), batch["records"].data_ptr(), batch["n"],
+                                           first_index, self._stream()))
+
+    def run_resident(self, batch, first_index: int = 0):
+        """K2 -> K1 -> K3 -> K4 on the current torch stream; asynchronous."""
+        s, a, b = (self._dev_ragged(batch[k]) for k in ("seq", "f0", "f1"))
+        N.check(self._L.scar_run_dev(self._ctx, C.byref(s), C.byref(a) if a else None, C.byref(b) if b else None,
+                                     batch["n"], first_index, batch["cells"].data_ptr(), batch["lens"].data_ptr(),
+                                     batch["samples"].data_ptr(), batch["records"].data_ptr(), self._stream()))
+
+    def verify_resident(self, batch, first_index: int = 0) -> int:
+        s = self._dev_ragged(batch["seq"])
+        ncol = C.c_int64(0)
+        N.check(self._L.scar_verify_dev(self._ctx, C.byref(s), batch["records"].data_ptr(), batch["n"], first_index,
+                                        C.byref(ncol), self._stream()))
+        return ncol.value
+
+    @staticmethod
+    def records_of(batch) -> np.ndarray:
+        return batch["records"].cpu().numpy().view(N.RECORD_DTYPE).reshape(-1)
+
+    # ---- results --------------------------------------------------------------------------------
+    def counters(self):
+        out = np.zeros((self.n_samples, N.SCAR_N_COUNTERS), dtype=np.int64)
+        un = C.c_int64(0)
+        N.check(self._L.scar_counters_read(self._ctx, out.ctypes.data, C.byref(un)))
+        return out, un.value
+
+    def phase_hist(self):
+        out = np.zeros((self.n_samples, 2, N.SCAR_PHASE_BINS), dtype=np.int64)
+        N.check(self._L.scar_phase_hist_read(self._ctx, out.ctypes.data))
+        return out
+
+    def table_size(self) -> int:
+        n = C.c_int64(0)
+        N.check(self._L.scar_table_size(self._ctx, C.byref(n)))
+        return n.value
+
+    def table(self) -> np.ndarray:
+        """Entries sorted by (sample, first_idx): the reference's per-sample first-seen dict order."""
+        n = self.table_size()
+        out = np.zeros(max(n, 1), dtype=N.ENTRY_DTYPE)
+        got = C.c_int64(0)
+        N.check(self._L.scar_table_read(self._ctx, out.ctypes.data, out.size, C.byref(got)))
+        return out[:got.value]
+
+
+def match_maker_batch(queries, unknowns, device: int = 0) -> np.ndarray:
+    """Sequence_Magic.match_maker over a batch on the GPU (Valkyries/Sequence_Magic.py:123-136)."""
+    q, u = as_ragged(queries), as_ragged(unknowns)
+    assert q.n == u.n
+    out = np.zeros(q.n, dtype=np.int32)
+    a, b = q.c_struct(), u.c_struct()
+    N.check(N.lib().scar_match_maker_batch(device, C.byref(a), C.byref(b), q.n, out.ctypes.data))
+    return out

@@ -1,0 +1,331 @@
+"""
+GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI
+(libscar_b200.so via scarmapper_b200.engine) and is compared bit for bit with
+  (a) the golden vectors captured from the unmodified reference driver, and
+  (b) the CPU oracle on seeded synthetic inputs of the BASELINE.json shapes.
+"""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import synth
+from oracle import scar_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_for(pin, max_read_len, **kw):
+    from scarmapper_b200.engine import ScarEngine, ScarProblem
+    return ScarEngine(ScarProblem(max_read_len=max_read_len, **pin, **kw), device=0)
+
+
+def assert_records_equal(got, want, reads=None):
+    if got.tobytes() == want.tobytes():
+        return
+    bad = np.nonzero(got != want)[0]
+    i = int(bad[0])
+    raise AssertionError("{} of {} records differ; first at {}: got {} want {} read {}".format(
+        len(bad), len(got), i, got[i], want[i], None if reads is None else reads[i]))
+
+
+def table_of(eng, s):
+    tab = eng.table()
+    sel = tab[tab["sample"] == s]
+    return [(int(e["count"]), int(e["first_idx"])) for e in sel]
+
+
+@pytest.mark.parametrize("name", gu.golden_names())
+def test_golden_vectors_through_c_abi(name):
+    blob = gu.load(name)
+    case, golden = blob["case"], blob["golden"]
+    pin = gu.problem_inputs(case)
+    f0, f1 = gu.index_fields(case)
+    reads = case["reads"]
+    eng = engine_for(pin, max(16, max(len(r) for r in reads)))
+    rec = eng.process_host(reads, f0, f1)
+    want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
+    assert_records_equal(rec, want, reads)
+    tab = eng.table()
+    by_sample = {}
+    for e in tab:
+        by_sample.setdefault(int(e["sample"]), []).append((int(e["count"]), int(e["first_idx"])))
+    cnt = gu.compare_with_golden(case, golden, rec, table_fn=lambda s: by_sample.get(s, []))
+    mine, un = eng.counters()
+    assert (mine == cnt).all()
+    assert un == golden["read_count_dict"].get("unidentified", 0)
+    eng.close()
+
+
+def synth_problem(cfg, **over):
+    pin = dict(targets=cfg.targets, cutsites=cfg.cutsites, sample_target=cfg.sample_target,
+               left_index=cfg.index_d5, right_index=cfg.index_d7, platform="Illumina",
+               phasing=cfg.phasing_lists(), n_limit=cfg.n_limit, min_length=cfg.min_length, hr_donor=cfg.hr_donor)
+    pin.update(over)
+    return pin
+
+
+@pytest.mark.parametrize("name,n,kw", [
+    ("C1", 60000, {}), ("C2", 60000, {}), ("C3", 60000, {}), ("C4", 20000, {}),
+    ("C3", 40000, {"min_len": 20, "p_n": 0.05}),
+])
+def test_synthetic_configs_match_oracle(name, n, kw):
+    cfg = synth.make_config(name, n_reads=n, seed=101, **kw)
+    batch = cfg.generate(0, n)
+    reads = cfg.reads_as_strings(batch)
+    f0, f1 = cfg.fields_as_strings(batch)
+    pin = synth_problem(cfg)
+    prob = orc.Problem(**pin)
+    want = orc.classify_batch(prob, reads, f0, f1)
+    eng = engine_for(pin, cfg.read_len)
+    # fixed-stride host input (what the synthetic generator and the batched loader produce)
+    from scarmapper_b200.engine import HostRagged
+    seq = HostRagged.from_matrix(batch["seq"], lengths=batch["len"])
+    rec = eng.process_host(seq, batch["f0"], batch["f1"])
+    assert_records_equal(rec, want, reads)
+    # aggregated table: (sample, first_idx, count) in the reference's first-seen order
+    tables = orc.aggregate(prob, want, reads)
+    ref = [(s, v[1], v[0]) for s, d in enumerate(tables) for v in d.values()]
+    mine = [(int(e["sample"]), int(e["first_idx"]), int(e["count"])) for e in eng.table()]
+    assert mine == ref
+    cnt, un = eng.counters()
+    assert (cnt == orc.counters(prob, want)).all()
+    assert un == int((want["status"] == orc.ST_UNASSIGNED).sum())
+    # phase histograms
+    ph = eng.phase_hist()
+    ok = want["status"] != orc.ST_UNASSIGNED
+    for s in range(0, prob.n_samples, 7):
+        sel = ok & (want["sample"] == s)
+        for side, col in enumerate(("phase_r1", "phase_r2")):
+            v = want[col][sel].astype(int)
+            assert ph[s, side, 0] == int((v == -1).sum())
+            for k in range(6):
+                assert ph[s, side, 1 + k] == int((v == k).sum())
+    eng.close()
+
+
+def test_resident_path_equals_host_path_and_verifies():
+    cfg = synth.make_config("C3", n_reads=50000, seed=77)
+    batch = cfg.generate(0, 50000)
+    pin = synth_problem(cfg)
+    eng = engine_for(pin, cfg.read_len)
+    from scarmapper_b200.engine import HostRagged
+    seq = HostRagged.from_matrix(batch["seq"], lengths=batch["len"])
+    rec_host = eng.process_host(seq, batch["f0"], batch["f1"]).copy()
+    tab_host = eng.table().copy()
+    cnt_host = eng.counters()[0].copy()
+    eng.reset()
+    import torch
+    res = eng.make_resident(seq, batch["f0"], batch["f1"])
+    eng.run_resident(res)
+    torch.cuda.synchronize()
+    assert_records_equal(eng.records_of(res), rec_host)
+    assert eng.table().tobytes() == tab_host.tobytes()
+    assert (eng.counters()[0] == cnt_host).all()
+    assert eng.verify_resident(res) == 0
+    # idempotence of the accumulators: a second pass doubles every count and keeps first_idx
+    eng.run_resident(res)
+    torch.cuda.synchronize()
+    t2 = eng.table()
+    assert (t2["count"] == 2 * tab_host["count"]).all() and (t2["first_idx"] == tab_host["first_idx"]).all()
+    eng.close()
+
+
+def test_multi_chunk_pipeline_keeps_global_first_index(monkeypatch):
+    monkeypatch.setenv("SCAR_CHUNK_READS", "4096")
+    cfg = synth.make_config("C2", n_reads=30000, seed=55)
+    batch = cfg.generate(0, 30000)
+    reads = cfg.reads_as_strings(batch)
+    f0, f1 = cfg.fields_as_strings(batch)
+    pin = synth_problem(cfg)
+    prob = orc.Problem(**pin)
+    want = orc.classify_batch(prob, reads, f0, f1)
+    eng = engine_for(pin, cfg.read_len)
+    rec = eng.process_host(reads, f0, f1, first_index=1000)     # CSR input, 8 chunks
+    assert_records_equal(rec, want, reads)
+    tables = orc.aggregate(prob, want, reads)
+    ref = [(s, v[1] + 1000, v[0]) for s, d in enumerate(tables) for v in d.values()]
+    assert [(int(e["sample"]), int(e["first_idx"]), int(e["count"])) for e in eng.table()] == ref
+    eng.close()
+
+
+def pack_reference(reads, W):
+    """numpy restatement of the packed row layout (scar_internal.cuh)."""
+    out = np.zeros((len(reads), W), dtype=np.uint64)
+    code = {ord("A"): 0, ord("C"): 1, ord("T"): 2, ord("G"): 3}
+    for r, s in enumerate(reads):
+        b = s.encode("latin-1") if isinstance(s, str) else s
+        for k, ch in enumerate(b):
+            j, o = divmod(k, 16)
+            if ch in code:
+                out[r, j] |= np.uint64(code[ch] << (2 * o)) | np.uint64(1 << (32 + o))
+            elif ch == ord("N"):
+                out[r, j] |= np.uint64(1 << (48 + o))
+    return out
+
+
+@pytest.mark.parametrize("platform", ["Illumina", "TruSeq", "Ramsden"])
+def test_pack_kernel_layout_and_transforms(platform):
+    import random
+    import torch
+    rng = random.Random(4)
+    reads = []
+    for i in range(3000):
+        n = rng.choice([0, 1, 5, 6, 11, 12, 13, 15, 16, 17, 31, 32, 33, 100, 149, 150, 151, 160])
+        reads.append("".join(rng.choice("ACGTACGTACGTNacgtRY.") for _ in range(n)))
+    pin = dict(targets=["ACGT" * 40], cutsites=[80], sample_target=[0], left_index=["ACGTAC"], right_index=["TTGACA"],
+               platform=platform)
+    eng = engine_for(pin, 160)
+    res = eng.make_resident(reads)
+    eng.pack_resident(res)
+    torch.cuda.synchronize()
+    pf = orc.PLATFORMS[platform]
+    stored = [orc.platform_seq(pf, r.encode("latin-1")).decode("latin-1") for r in reads]
+    want = pack_reference(stored, eng.cells_per_read)
+    got = res["cells"].cpu().numpy().view(np.uint64)
+    assert (got == want).all()
+    lens = res["lens"].cpu().numpy().view(np.uint16)
+    assert list(lens) == [len(s) for s in stored]
+    eng.close()
+
+
+def test_demux_kernel_all_platform_rules():
+    import random
+    import torch
+    rng = random.Random(8)
+    # Illumina with odd index fields: short, long, empty, N, shifted
+    idx = synth.illumina_dual_indices()
+    right = [d7 for _, d7, _ in idx]
+    left = [d5 for _, _, d5 in idx]
+    f0, f1 = [], []
+    for i in range(20000):
+        s = rng.randrange(96)
+        a, b = right[s], left[s]
+        u = rng.random()
+        if u < 0.2:
+            p = rng.randrange(8); a = a[:p] + rng.choice("ACGTN") + a[p + 1:]
+        elif u < 0.3:
+            a = a[1:]
+        elif u < 0.4:
+            b = b + rng.choice("ACGT")
+        elif u < 0.45:
+            b = rng.choice("ACGT") + b
+        elif u < 0.5:
+            a = ""
+        elif u < 0.55:
+            a = a[:3] + a[4:] + "G"
+        f0.append(a); f1.append(b)
+    pin = dict(targets=["ACGT" * 40], cutsites=[80], sample_target=[0] * 96, left_index=left, right_index=right,
+               platform="Illumina")
+    eng = engine_for(pin, 160)
+    res = eng.make_resident(["ACGT"] * len(f0), f0, f1)
+    eng.demux_resident(res)
+    torch.cuda.synchronize()
+    got = res["samples"].cpu().numpy().view(np.uint16).astype(np.int64)
+    L = orc.lib()
+    lb, lo = orc.csr(left); rb, ro = orc.csr(right)
+    for i in range(len(f0)):
+        a, b = f0[i].encode(), f1[i].encode()
+        w = L.orc_index_matching(0, 1, 96, lb.ctypes.data, lo.ctypes.data, rb.ctypes.data, ro.ctypes.data,
+                                 b"", 0, a, len(a), b, len(b))
+        assert (got[i] if got[i] != 0xFFFF else -1) == w, (i, f0[i], f1[i], got[i], w)
+    eng.close()
+
+
+def test_match_maker_batch_matches_oracle():
+    import random
+    from scarmapper_b200.engine import match_maker_batch
+    rng = random.Random(12)
+    q = ["".join(rng.choice("ACGTN") for _ in range(rng.randint(0, 40))) for _ in range(5000)]
+    u = []
+    for s in q:
+        t = list(s)
+        for _ in range(rng.randint(0, 4)):
+            op = rng.random()
+            if op < 0.4 and t:
+                t[rng.randrange(len(t))] = rng.choice("ACGT")
+            elif op < 0.7 and t:
+                del t[rng.randrange(len(t))]
+            else:
+                t.insert(rng.randint(0, len(t)), rng.choice("ACGT"))
+        u.append("".join(t))
+    got = match_maker_batch(q, u)
+    want = [orc.match_maker(a, b) for a, b in zip(q, u)]
+    assert list(got) == want
+
+
+def test_edge_cases_empty_and_degenerate_batches():
+    cfg = synth.make_config("C1", n_reads=10, seed=3)
+    pin = synth_problem(cfg)
+    eng = engine_for(pin, 300)
+    # empty batch
+    rec = eng.process_host([], [], [])
+    assert rec.size == 0 and eng.table_size() == 0
+    # reads around every loop bound, all-N, lowercase, and one wild-type
+    t, cut = cfg.targets[0], cfg.cutsites[0]
+    reads = ["", "A", "ACGT" * 8 + "AC", "N" * 150, t[cut - 75:cut + 75], t[cut - 75:cut + 75].lower(),
+             t[cut - 18:cut + 18], t[cut - 17:cut + 18], t[cut - 150:cut + 150], t[:101], t[:100]]
+    f0 = [cfg.index_d7[0]] * len(reads)
+    f1 = [cfg.index_d5[0]] * len(reads)
+    want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
+    rec = eng.process_host(reads, f0, f1)
+    assert_records_equal(rec, want, reads)
+    eng.close()
+
+
+def test_read_longer_than_context_limit_is_an_error():
+    from scarmapper_b200._native import ScarError
+    cfg = synth.make_config("C1", n_reads=10, seed=3)
+    eng = engine_for(synth_problem(cfg), 150)
+    with pytest.raises(ScarError) as e:
+        eng.process_host(["A" * 200], [cfg.index_d7[0]], [cfg.index_d5[0]])
+    assert e.value.code == -3
+    eng.close()
+
+
+def test_unsupported_inputs_fail_loudly():
+    from scarmapper_b200._native import ScarError
+    with pytest.raises(ScarError):
+        engine_for(dict(targets=["ACGT" * 20 + "N" + "ACGT" * 20], cutsites=[80], sample_target=[0],
+                        left_index=["ACGTACGT"], right_index=["ACGTACGT"]), 150)
+    with pytest.raises(ScarError):
+        engine_for(dict(targets=["ACGT" * 40], cutsites=[80], sample_target=[0], left_index=["ACGTACGT"],
+                        right_index=["ACGTACGT"], hr_donor="ACGTNACGTAC"), 150)
+
+
+@pytest.mark.slow
+def test_full_size_properties_config1():
+    """BASELINE config 1 at full size (1M reads): size-independent properties instead of the oracle:
+    counters add up, table counts add up to the SCAR counter, shuffling the batch order leaves every
+    (sample, key) count unchanged, and an oracle spot-check on a stride sample."""
+    n = 1_000_000
+    cfg = synth.make_config("C1", n_reads=n, seed=2024)
+    batch = cfg.generate(0, n)
+    pin = synth_problem(cfg)
+    eng = engine_for(pin, cfg.read_len, table_capacity=1 << 22)
+    from scarmapper_b200.engine import HostRagged
+    rec = eng.process_host(HostRagged.from_matrix(batch["seq"], lengths=batch["len"]), batch["f0"], batch["f1"])
+    cnt, un = eng.counters()
+    tab = eng.table()
+    assert cnt[:, 0].sum() + un == n
+    assert int(tab["count"].sum()) == int(cnt[:, 12].sum()) == int((rec["status"] == orc.ST_SCAR).sum())
+    assert (cnt[:, 1] == cnt[:, 6] + cnt[:, 7] + cnt[:, 11] + cnt[:, 12]).all()
+    # first_idx really is the first read carrying that key
+    firsts = tab["first_idx"].astype(np.int64)
+    assert (rec["status"][firsts] == orc.ST_SCAR).all()
+    # permutation invariance of the counts
+    perm = np.random.default_rng(1).permutation(n)
+    eng.reset()
+    eng.process_host(HostRagged.from_matrix(batch["seq"][perm], lengths=batch["len"][perm]),
+                     batch["f0"][perm], batch["f1"][perm], want_records=False)
+    tab2 = eng.table()
+    a = np.sort(np.stack([tab["h1"], tab["h2"], tab["count"].astype(np.uint64)], 1).view("u8,u8,u8").ravel())
+    b = np.sort(np.stack([tab2["h1"], tab2["h2"], tab2["count"].astype(np.uint64)], 1).view("u8,u8,u8").ravel())
+    assert (a == b).all()
+    # oracle spot check on every 97th read
+    sel = np.arange(0, n, 97)
+    sub = {k: (v[sel] if v is not None else None) for k, v in batch.items()}
+    reads = cfg.reads_as_strings(sub)
+    f0, f1 = cfg.fields_as_strings(sub)
+    want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
+    assert_records_equal(rec[sel], want, reads)
+    eng.close()
