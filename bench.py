@@ -1,0 +1,367 @@
+"""
+bench.py — merged reads classified per second on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[1] — synthetic PEAR-merged 150-bp amplicon reads
+demultiplexed across the 96 Illumina dual-index samples, Rosa26a-shaped 472-bp locus, 10 M reads per
+GPU (weak scaling: rank g owns global reads [g*10M, (g+1)*10M)).
+
+A step is one pass of the hot path over the rank's batch:
+  value : inputs (packed rows, raw bytes, index fields) already resident in HBM; the timed region is
+          reset -> K2 demux -> K3 sliding window -> K4 aggregation (-> table merge across ranks when
+          N > 1), CUDA events on the launching stream, barrier + synchronize on both sides, max over
+          ranks.  K1 (pack) is timed separately (stages_ms.k1_pack), as SURVEY.md §8d defines.
+  e2e   : the same batch from pinned HOST buffers through the public API (ScarEngine.process_host ->
+          scar_process_host): H2D of reads + index fields, K2, K1, K3, K4, D2H of the 16-byte records.
+  roofline : K3 (scar_window_kernel): algorithmic bytes = 182 B/read (150 read + 16 index + 16 record,
+          SURVEY.md §8d) x reads per launch / mean K3 launch time, against the measured HBM copy peak.
+  cpu_baseline : the reference's CPU path (oracle/cpu_reference.py) on a bounded sample, N=1 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_READ = 182          # 150 (1 B/base) + 16 (i7+i5) + 16 (result record)
+METRIC = "merged_reads_classified_per_sec"
+WORKLOAD = ("C2: synthetic PEAR-merged 150-bp amplicon reads, 96 Illumina dual-index samples "
+            "(Levenshtein index matching + per-sample scar tables), Rosa26a-shaped 472-bp locus")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=50_000, help="reads of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=20260101)
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_case(args, rank, world):
+    import numpy as np
+    import synth
+    cfg = synth.make_config("C2", n_reads=args.reads * world, seed=args.seed)
+    pin = dict(targets=cfg.targets, cutsites=cfg.cutsites, sample_target=cfg.sample_target,
+               left_index=cfg.index_d5, right_index=cfg.index_d7, platform="Illumina",
+               phasing=cfg.phasing_lists(), n_limit=cfg.n_limit, min_length=cfg.min_length)
+    return cfg, pin
+
+
+def cpu_sample_inputs(cfg, n):
+    batch = cfg.generate(0, n)
+    reads = cfg.reads_as_strings(batch)
+    f0, f1 = cfg.fields_as_strings(batch)
+    names = ["SYN:1:FC:1:{}:{}:{} 1:N:0:{}+{}".format(i % 97, i, i * 7 % 1013, a, b)
+             for i, (a, b) in enumerate(zip(f0, f1))]
+    return names, reads
+
+
+def run_cpu_reference(cfg, n_sample, cores=None, repeats=1, warm=0):
+    from oracle import cpu_reference as cr
+    names, reads = cpu_sample_inputs(cfg, n_sample)
+    ref = cr.CpuReference(cores)
+    try:
+        kw = dict(sample_ids=cfg.sample_ids, left_index=cfg.index_d5, right_index=cfg.index_d7,
+                  sample_target=cfg.sample_target, targets=cfg.targets, cutsites=cfg.cutsites,
+                  platform=0, mismatch=1, n_limit=cfg.n_limit, min_length=cfg.min_length)
+        for _ in range(warm):
+            ref.run(names, reads, **kw)
+        runs = [ref.run(names, reads, **kw) for _ in range(repeats)]
+    finally:
+        cores_used = ref.cores
+        ref.close()
+    return runs, cores_used, cr.baseline_kind()
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import synth  # noqa: F401
+    cfg, _ = build_case(args, 0, 1)
+    # size each step so that the whole run ends within a few minutes: calibrate on a small sample
+    cal, cores, kind = run_cpu_reference(cfg, 12_000)
+    rate = cal[0]["n_reads"] / cal[0]["total_s"]
+    budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
+    n_sample = int(max(10_000, min(200_000, rate * budget)))
+    runs, cores, kind = run_cpu_reference(cfg, n_sample, repeats=args.steps, warm=args.warmup)
+    total = sum(r["total_s"] for r in runs)
+    value = n_sample * len(runs) / total
+    demux = n_sample * len(runs) / sum(r["demux_s"] for r in runs)
+    search = n_sample * len(runs) / sum(r["search_s"] for r in runs)
+    sample = ("{} reads of the workload per step; stage 1 serial in the main process ({:.0f} reads/s), stages 2-4 "
+              "one process per sample on {} workers ({:.0f} reads/s); {}").format(
+        n_sample, demux, cores, search,
+        "compiled reference SlidingWindow.pyx (oracle/_ref) inside the restated driver loops" if kind == "reference"
+        else "oracle C port (oracle/_ref absent)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(runs),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reads_per_step": n_sample, "read_len": 150, "n_samples": cfg.n_samples},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from scarmapper_b200.engine import HostRagged, ScarEngine, ScarProblem
+    from scarmapper_b200.distributed import DistributedScar
+    from scarmapper_b200._native import RECORD_DTYPE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE {} != --gpus {}".format(world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # the CPU baseline runs first (rank 0, N=1 only), before this process touches the GPU
+    cpu_baseline = None
+    cfg, pin = build_case(args, rank, world)
+    if world == 1 and not args.no_cpu_baseline:
+        runs, cores, kind = run_cpu_reference(cfg, args.cpu_sample)
+        r = runs[0]
+        cpu_baseline = {
+            "value": r["n_reads"] / r["total_s"], "unit": "reads/s", "cores": cores, "kind": kind,
+            "sample": "first {} reads of the workload: stage 1 serial {:.1f} s, stages 2-4 on {} processes {:.1f} s"
+                      .format(r["n_reads"], r["demux_s"], cores, r["search_s"]),
+        }
+
+    n = args.reads
+    first = rank * n
+    batch = cfg.generate(first, n)
+    eng = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=1 << 22, **pin), device=local)
+
+    # pinned host buffers for the end-to-end arm
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.uint8, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    p_seq, p_f0, p_f1 = pinned(batch["seq"]), pinned(batch["f0"]), pinned(batch["f1"])
+    h_seq = HostRagged.from_matrix(p_seq.numpy())
+    h_f0 = HostRagged.from_matrix(p_f0.numpy())
+    h_f1 = HostRagged.from_matrix(p_f1.numpy())
+    p_rec = torch.empty((n, 16), dtype=torch.uint8, pin_memory=True)
+    rec_out = p_rec.numpy().view(RECORD_DTYPE).reshape(-1)
+
+    # small parity check against the oracle before any timing (outside every timed region)
+    from oracle import scar_oracle as orc
+    chk = 4000
+    sub = {k: (v[:chk] if v is not None else None) for k, v in batch.items()}
+    want = orc.classify_batch(orc.Problem(**pin), cfg.reads_as_strings(sub), *cfg.fields_as_strings(sub))
+    got = eng.process_host(HostRagged.from_matrix(batch["seq"][:chk]), batch["f0"][:chk], batch["f1"][:chk])
+    if got.tobytes() != want.tobytes():
+        raise SystemExit("bench: CUDA records differ from the oracle on the first {} reads".format(chk))
+    eng.reset()
+
+    res = eng.make_resident(h_seq, h_f0, h_f1)
+    dscar = DistributedScar(eng, entry_capacity=1 << 21) if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    # K1 (pack) timed on its own
+    for _ in range(2):
+        eng.pack_resident(res)
+    torch.cuda.synchronize()
+    a = ev()
+    for _ in range(3):
+        eng.pack_resident(res)
+    b = ev()
+    torch.cuda.synchronize()
+    k1_ms = a.elapsed_time(b) / 3
+
+    marks = []
+
+    def step(record_marks):
+        eng.reset_async()
+        m0 = ev() if record_marks else None
+        eng.demux_resident(res)
+        m1 = ev() if record_marks else None
+        eng.classify_resident(res)
+        m2 = ev() if record_marks else None
+        eng.aggregate_resident(res, first_index=first)
+        m3 = ev() if record_marks else None
+        if dscar:
+            dscar.merge()
+        if record_marks:
+            marks.append((m0, m1, m2, m3))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    t_start = ev()
+    for _ in range(args.steps):
+        step(True)
+    t_end = ev()
+    barrier()
+    launches = eng.launch_count() - launches0
+    elapsed_ms = t_start.elapsed_time(t_end)
+    k2 = sum(m[0].elapsed_time(m[1]) for m in marks) / len(marks)
+    k3 = sum(m[1].elapsed_time(m[2]) for m in marks) / len(marks)
+    k4 = sum(m[2].elapsed_time(m[3]) for m in marks) / len(marks)
+    n_entries = eng.table_size()
+    cnt, un = eng.counters()
+
+    # end-to-end arm: host buffers -> records on the host, through the public API
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        eng.reset_async()
+        eng.process_host(h_seq, h_f0, h_f1, first_index=first, out=rec_out)
+        if dscar:
+            dscar.merge()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.reset_async()
+        eng.process_host(h_seq, h_f0, h_f1, first_index=first, out=rec_out)
+        if dscar:
+            dscar.merge()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_s, k3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_s, k3 = (float(x) for x in t.tolist())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = ALGO_BYTES_PER_READ * n / (k3 * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "k3_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        h2d = int(p_seq.numel() + p_f0.numel() + p_f1.numel())
+        line = {
+            "metric": METRIC, "value": world * n * args.steps / (elapsed_ms * 1e-3), "unit": "reads/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "reads_per_gpu": n, "read_len": cfg.read_len, "n_samples": cfg.n_samples,
+                       "n_targets": len(cfg.targets), "global_reads_per_step": world * n,
+                       "parallelism": "reads sharded in contiguous blocks, dp{}".format(world),
+                       "l2": "inputs_exceed_l2 ({} MB packed rows + {} MB raw per step vs 126 MB L2)".format(
+                           n * eng.cells_per_read * 8 // 2 ** 20, n * cfg.read_len // 2 ** 20),
+                       "timed_region": "reset, K2 demux, K3 sliding window, K4 aggregation" +
+                                       (", table merge over NCCL" if world > 1 else ""),
+                       "scar_patterns": int(n_entries), "unassigned_reads": int(un)},
+            "stages_ms": {"k1_pack": k1_ms, "k2_demux": k2, "k3_window": k3, "k4_aggregate": k4},
+            "roofline": {"bound": "hbm", "kernel": "scar_window_kernel (K3)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ},
+            "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(n * 16), "steps": e2e_steps,
+                    "path": "ScarEngine.process_host -> scar_process_host (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -140,11 +140,18 @@ int scar_table_read(scar_ctx *ctx, scar_entry *entries, int64_t capacity, int64_
 int scar_verify_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_record *records, int64_t n_reads,
                     uint64_t first_index, int64_t *n_collisions, void *stream);
 int scar_reset(scar_ctx *ctx);
+int scar_reset_dev(scar_ctx *ctx, void *stream);      /* asynchronous on `stream` */
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t scar_launch_count(const scar_ctx *ctx);
 
 /* Multi-GPU: export this rank's table, merge another rank's into it (count SUM, first_idx MIN). */
 int scar_table_export_dev(scar_ctx *ctx, scar_entry *entries, int64_t capacity, int64_t *n_entries, void *stream);
 int scar_table_merge_dev(scar_ctx *ctx, const scar_entry *entries, int64_t n_entries, void *stream);
-int scar_counters_ptr(scar_ctx *ctx, void **counters_dev, int64_t *n_int64);
+/* Dense accumulators as one int64 block [unassigned, counters[n_samples][16], phase_hist[n_samples][2][34]]
+ * for an all-reduce(SUM) across ranks: export to / import from caller-owned device memory. */
+int64_t scar_accumulator_words(const scar_ctx *ctx);
+int scar_accumulators_export_dev(scar_ctx *ctx, int64_t *out, void *stream);
+int scar_accumulators_import_dev(scar_ctx *ctx, const int64_t *in, void *stream);
 
 /* Sequence_Magic.match_maker over a batch on the device (host buffers): out[i] = lev(q_i,u_i) - (|u_i|-|q_i|). */
 int scar_match_maker_batch(int32_t device, const scar_ragged *query, const scar_ragged *unknown,

@@ -91,7 +91,11 @@ PROTOTYPES = {
     "scar_reset": (C.c_int, [_P]),
     "scar_table_export_dev": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
     "scar_table_merge_dev": (C.c_int, [_P, _P, C.c_int64, _P]),
-    "scar_counters_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "scar_reset_dev": (C.c_int, [_P, _P]),
+    "scar_launch_count": (C.c_int64, [_P]),
+    "scar_accumulator_words": (C.c_int64, [_P]),
+    "scar_accumulators_export_dev": (C.c_int, [_P, _P, _P]),
+    "scar_accumulators_import_dev": (C.c_int, [_P, _P, _P]),
     "scar_match_maker_batch": (C.c_int, [C.c_int32, _RP, _RP, C.c_int64, _P]),
 }
 

@@ -347,6 +347,18 @@ extern "C" int scar_reset(scar_ctx *c)
     return SCAR_OK;
 }
 
+extern "C" int scar_reset_dev(scar_ctx *c, void *stream)
+{
+    if (!c) return fail(SCAR_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(c->d_slots, 0, c->capacity * sizeof(ScarTableSlot), s));
+    CU(cudaMemsetAsync(c->d_acc, 0, c->acc_words * sizeof(unsigned long long), s));
+    return SCAR_OK;
+}
+
+extern "C" int64_t scar_launch_count(const scar_ctx *c) { return c ? c->launches : 0; }
+
 extern "C" int scar_cells_per_read(const scar_ctx *c) { return c ? c->W : 0; }
 
 extern "C" int scar_window_counts(const scar_ctx *c, int32_t t, int32_t *n_left, int32_t *n_right)
@@ -498,6 +510,7 @@ extern "C" int scar_table_export_dev(scar_ctx *c, scar_entry *entries, int64_t c
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaMemsetAsync(c->d_export_n, 0, sizeof(unsigned long long), s));
     CU(scar_launch_export(c->d_slots, c->capacity, entries, (uint64_t)capacity, c->d_export_n, c->sm_count, s));
+    ++c->launches;
     unsigned long long v = 0;
     CU(cudaMemcpyAsync(&v, c->d_export_n, sizeof(v), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -512,14 +525,29 @@ extern "C" int scar_table_merge_dev(scar_ctx *c, const scar_entry *entries, int6
     CU(cudaSetDevice(c->device));
     K4Params P = k4_params(c);
     CU(scar_launch_merge(P, entries, (uint64_t)n, c->sm_count, (cudaStream_t)stream));
+    if (n) ++c->launches;
     return SCAR_OK;
 }
 
-extern "C" int scar_counters_ptr(scar_ctx *c, void **counters_dev, int64_t *n_int64)
+extern "C" int64_t scar_accumulator_words(const scar_ctx *c) { return c ? (int64_t)(c->acc_words - 7) : 0; }
+
+extern "C" int scar_accumulators_export_dev(scar_ctx *c, int64_t *out, void *stream)
 {
-    if (!c || !counters_dev || !n_int64) return fail(SCAR_ERR_INVALID, "bad argument");
-    // [n_entries(not summed), unassigned, ...] + counters + phase histograms: one contiguous int64 block
-    *counters_dev = c->d_acc; *n_int64 = (int64_t)c->acc_words;
+    if (!c || !out) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(out, c->d_unassigned, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(out + 1, c->d_counters, (c->acc_words - 8) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    return SCAR_OK;
+}
+
+extern "C" int scar_accumulators_import_dev(scar_ctx *c, const int64_t *in, void *stream)
+{
+    if (!c || !in) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(c->d_unassigned, in, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(c->d_counters, in + 1, (c->acc_words - 8) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
     return SCAR_OK;
 }
 

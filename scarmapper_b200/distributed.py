@@ -1,0 +1,86 @@
+"""
+distributed.py — multi-GPU plumbing: one process per GPU, reads sharded, one exchange at the end.
+
+The reference's only parallelism is one pathos process per sample library
+(INDEL_Processing.py:1047-1059).  Here every read is independent through demux / pack / classify,
+so the global read stream is cut into contiguous blocks, rank g owning reads
+[shard_bounds(n, G)[g], shard_bounds(n, G)[g+1]) with GLOBAL read indices (the reference keeps the
+first-seen record per scar key and orders ties by first-seen rank, so first_idx must be global).
+No data-path collective runs until the tables are complete; then
+
+  1. dense accumulators (unassigned, per-sample counters, phase histograms): all_reduce(SUM, int64)
+  2. scar tables (sparse): all_gather of entry counts, all_gather of the compacted 32-byte entries
+     padded to the largest rank, and every rank folds the other ranks' entries into its own table
+     on its GPU (count SUM, first_idx MIN) — so all ranks end with the identical merged table.
+
+Payload is unique-keys x 32 B (KB..MB): latency-bound over NVLink 5 / NVSwitch.  torch.distributed
+is the transport (NCCL on GPUs, gloo in the CPU tests); the fold itself is the library's merge kernel.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_reads: int, world: int):
+    """Contiguous blocks: [b[g], b[g+1]) for rank g; sizes differ by at most one."""
+    base, rem = divmod(int(n_reads), int(world))
+    b = [0]
+    for g in range(world):
+        b.append(b[-1] + base + (1 if g < rem else 0))
+    return b
+
+
+def merge_tables(export_fn, merge_fn, entry_buf: torch.Tensor, group=None):
+    """All-gather merge of sparse tables.
+
+    export_fn(buf) -> n      compacts the local table into buf ([cap, 32] uint8) and returns the count
+    merge_fn(buf, n)         folds n foreign entries into the local table
+    entry_buf                scratch on the rank's device, at least as large as the largest local table
+
+    Returns the list of per-rank entry counts.  Every rank folds every other rank's entries, so all
+    ranks hold the same merged table afterwards.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_local = int(export_fn(entry_buf))
+    counts = torch.zeros(world, dtype=torch.int64, device=entry_buf.device)
+    mine = torch.tensor([n_local], dtype=torch.int64, device=entry_buf.device)
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    counts_h = [int(c) for c in counts.tolist()]
+    n_max = max(counts_h)
+    if n_max > entry_buf.shape[0]:
+        raise RuntimeError("entry buffer too small: {} < {}".format(entry_buf.shape[0], n_max))
+    if world == 1 or n_max == 0:
+        return counts_h
+    gathered = torch.empty((world, n_max, entry_buf.shape[1]), dtype=entry_buf.dtype, device=entry_buf.device)
+    dist.all_gather_into_tensor(gathered, entry_buf[:n_max].contiguous(), group=group)
+    for g in range(world):
+        if g != rank and counts_h[g]:
+            merge_fn(gathered[g], counts_h[g])
+    return counts_h
+
+
+def reduce_accumulators(export_fn, import_fn, words: int, device, group=None):
+    """all_reduce(SUM) of the dense int64 accumulator block."""
+    buf = torch.empty(words, dtype=torch.int64, device=device)
+    export_fn(buf)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    import_fn(buf)
+    return buf
+
+
+class DistributedScar:
+    """Glue between a ScarEngine and the process group."""
+
+    def __init__(self, engine, entry_capacity: int = 1 << 20, group=None):
+        self.engine = engine
+        self.group = group
+        self.device = torch.device("cuda", engine.device)
+        self.entry_buf = torch.empty((entry_capacity, 32), dtype=torch.uint8, device=self.device)
+
+    def merge(self):
+        e = self.engine
+        reduce_accumulators(e.export_accumulators_dev, e.import_accumulators_dev, e.accumulator_words(),
+                            self.device, self.group)
+        return merge_tables(e.export_table_dev, e.merge_table_dev, self.entry_buf, self.group)

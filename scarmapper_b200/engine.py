@@ -174,6 +174,13 @@ class ScarEngine:
     def reset(self):
         N.check(self._L.scar_reset(self._ctx))
 
+    def reset_async(self):
+        """Clear table and accumulators on the current torch stream (no host synchronisation)."""
+        N.check(self._L.scar_reset_dev(self._ctx, self._stream()))
+
+    def launch_count(self) -> int:
+        return int(self._L.scar_launch_count(self._ctx))
+
     def window_counts(self, target: int):
         a, b = C.c_int32(), C.c_int32()
         N.check(self._L.scar_window_counts(self._ctx, target, C.byref(a), C.byref(b)))
@@ -263,6 +270,26 @@ class ScarEngine:
         N.check(self._L.scar_verify_dev(self._ctx, C.byref(s), batch["records"].data_ptr(), batch["n"], first_index,
                                         C.byref(ncol), self._stream()))
         return ncol.value
+
+    # ---- multi-GPU building blocks (see distributed.py) -------------------------------------------
+    def export_table_dev(self, buf) -> int:
+        """Compact this rank's table into `buf` (torch uint8 [cap, 32] on this device); returns the entry count."""
+        n = C.c_int64(0)
+        N.check(self._L.scar_table_export_dev(self._ctx, buf.data_ptr(), buf.shape[0], C.byref(n), self._stream()))
+        return n.value
+
+    def merge_table_dev(self, buf, n: int):
+        """Merge `n` foreign entries (count SUM, first_idx MIN) into this rank's table."""
+        N.check(self._L.scar_table_merge_dev(self._ctx, buf.data_ptr(), int(n), self._stream()))
+
+    def accumulator_words(self) -> int:
+        return int(self._L.scar_accumulator_words(self._ctx))
+
+    def export_accumulators_dev(self, out):
+        N.check(self._L.scar_accumulators_export_dev(self._ctx, out.data_ptr(), self._stream()))
+
+    def import_accumulators_dev(self, src):
+        N.check(self._L.scar_accumulators_import_dev(self._ctx, src.data_ptr(), self._stream()))
 
     @staticmethod
     def records_of(batch) -> np.ndarray:
