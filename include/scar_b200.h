@@ -95,8 +95,10 @@ int scar_cutsite_search(const uint8_t *target, int32_t len, const uint8_t *sgrna
 int scar_ctx_create(const scar_config *cfg, scar_ctx **out);
 void scar_ctx_destroy(scar_ctx *ctx);
 
-/* Layout of the packed read batch in HBM. */
-int scar_cells_per_read(const scar_ctx *ctx);        /* 64-bit cells per read row */
+/* Layout of the packed read batch in HBM: W = scar_cells_per_read() 64-bit cells per read, stored
+ * CELL-MAJOR: cell j of read r of an n-read batch is cells[j * n + r] (2-bit codes | ACGT mask << 32 |
+ * N mask << 48 for bases 16j .. 16j+15). */
+int scar_cells_per_read(const scar_ctx *ctx);
 int scar_window_counts(const scar_ctx *ctx, int32_t target, int32_t *n_left, int32_t *n_right);
 
 /* K1: raw bytes -> packed rows (2-bit codes + ACGT mask + N mask), applying the platform's stored-

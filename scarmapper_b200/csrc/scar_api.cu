@@ -73,20 +73,21 @@ static bool build_table(const std::vector<std::pair<uint32_t, uint32_t>> &kv /* 
 {
     size_t n = kv.size();
     uint32_t log2b = 6;
-    while ((1u << log2b) < 4 * n) ++log2b;
+    while ((1u << log2b) < 2 * n) ++log2b;      // load <= 0.5 keys per bucket; a few hundred tries find a multiplier
     uint64_t rng = 0x853C49E6748FEA9Bull ^ (n * 0x9E3779B97F4A7C15ull);
     for (; log2b <= 16; ++log2b) {
         const uint32_t B = 1u << log2b;
-        for (int attempt = 0; attempt < 4096; ++attempt) {
+        for (int attempt = 0; attempt < 20000; ++attempt) {
             rng = rng * 6364136223846793005ull + 1442695040888963407ull;
             const uint32_t mult = (uint32_t)(rng >> 32) | 1u;
-            std::vector<uint2> b(B, make_uint2(0u, 0u));
+            std::vector<uint2> b(B, make_uint2(SCAR_TABLE_EMPTY, SCAR_TABLE_EMPTY));
             bool ok = true;
             for (const auto &e : kv) {
-                const uint32_t slot = (e.first * mult) >> (32 - log2b);
-                const uint32_t val = ((e.first | SCAR_KEY_TAG) << 11) | e.second;
-                if (b[slot].x == 0) b[slot].x = val;
-                else if (b[slot].y == 0) b[slot].y = val;
+                const uint32_t t = e.first << 12;                  // key in the top 20 bits, as the kernel forms it
+                const uint32_t slot = (t * mult) >> (32 - log2b);
+                const uint32_t val = t | e.second;
+                if (b[slot].x == SCAR_TABLE_EMPTY) b[slot].x = val;
+                else if (b[slot].y == SCAR_TABLE_EMPTY) b[slot].y = val;
                 else { ok = false; break; }
             }
             if (ok) { out.buckets.swap(b); out.mult = mult; out.shift = 32 - log2b; return true; }
@@ -112,8 +113,9 @@ struct scar_ctx {
     int W = 0, max_read_len = 0, min_length = 0, hr_len = 0, do_phasing = 0;
     double n_limit = 0.0; uint64_t hr_code = 0;
     std::vector<ScarTargetMeta> h_targets;
-    int32_t *d_sample_target = nullptr; ScarTargetMeta *d_targets = nullptr; ScarPhase *d_phases = nullptr;
-    uint2 *d_tables = nullptr; uint32_t table_bytes = 0; bool smem_tables = true;
+    int32_t *d_sample_target = nullptr;
+    unsigned char *d_blob = nullptr; uint32_t blob_bytes = 0, meta_off = 0, phase_off = 0, nmax_off = 0;
+    bool smem_tables = true;
     uint8_t *d_class_map = nullptr; DemuxString *d_right = nullptr, *d_left = nullptr; uint64_t *d_peq = nullptr;
     uint16_t *d_first_sample = nullptr; int n_right = 0, n_left = 0, n_classes = 0;
     ScarTableSlot *d_slots = nullptr; uint64_t capacity = 0;
@@ -140,7 +142,7 @@ extern "C" void scar_ctx_destroy(scar_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto &b : c->buf) free_hostbuf(b);
-    cudaFree(c->d_sample_target); cudaFree(c->d_targets); cudaFree(c->d_phases); cudaFree(c->d_tables);
+    cudaFree(c->d_sample_target); cudaFree(c->d_blob);
     cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample);
     cudaFree(c->d_slots); cudaFree(c->d_acc); cudaFree(c->d_status);
     delete c;
@@ -306,14 +308,35 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
         c->h_targets.push_back(m);
     }
     c->do_phasing = (cfg->phase_off && cfg->platform == SCAR_PLATFORM_ILLUMINA) ? 1 : 0;
-    if (blob.size() % 2) blob.push_back(make_uint2(0u, 0u));   // 16-byte multiple for the bulk copy
-    c->table_bytes = (uint32_t)(blob.size() * sizeof(uint2));
-    c->smem_tables = c->table_bytes <= 160 * 1024;
+    // one blob, staged into shared memory by a single bulk copy: tables | target metas | phases | nmax
+    // nmax[len] = largest n with double(n)/double(len) <= N_Limit: the reference's filter
+    // seq.count("N")/len(seq) > N_Limit (INDEL_Processing.py:147) evaluated once per length on the host
+    // with the same IEEE-754 double division Python performs.
+    std::vector<uint16_t> nmax((size_t)16 * c->W + 1, 0);
+    for (int len = 1; len <= 16 * c->W; ++len) {
+        int n = 0;
+        while (n < len && !((double)(n + 1) / (double)len > cfg->n_limit)) ++n;
+        nmax[len] = (uint16_t)n;
+        // monotone in n, so the first n+1 that exceeds the limit ends the search
+    }
+    auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    std::vector<unsigned char> bytes;
+    bytes.resize(align16(blob.size() * sizeof(uint2)));
+    if (!blob.empty()) memcpy(bytes.data(), blob.data(), blob.size() * sizeof(uint2));
+    c->meta_off = (uint32_t)bytes.size();
+    bytes.resize(align16(bytes.size() + c->h_targets.size() * sizeof(ScarTargetMeta)));
+    memcpy(bytes.data() + c->meta_off, c->h_targets.data(), c->h_targets.size() * sizeof(ScarTargetMeta));
+    c->phase_off = (uint32_t)bytes.size();
+    bytes.resize(align16(bytes.size() + std::max<size_t>(phases.size(), 1) * sizeof(ScarPhase)));
+    if (!phases.empty()) memcpy(bytes.data() + c->phase_off, phases.data(), phases.size() * sizeof(ScarPhase));
+    c->nmax_off = (uint32_t)bytes.size();
+    bytes.resize(align16(bytes.size() + nmax.size() * sizeof(uint16_t)));
+    memcpy(bytes.data() + c->nmax_off, nmax.data(), nmax.size() * sizeof(uint16_t));
+    c->blob_bytes = (uint32_t)bytes.size();
+    c->smem_tables = c->blob_bytes <= 200 * 1024;
 
     int rc;
-    if ((rc = upload(&c->d_tables, blob))) return rc;
-    if ((rc = upload(&c->d_targets, c->h_targets))) return rc;
-    if ((rc = upload(&c->d_phases, phases))) return rc;
+    if ((rc = upload(&c->d_blob, bytes))) return rc;
     std::vector<int32_t> st(cfg->sample_target, cfg->sample_target + cfg->n_samples);
     for (int s = 0; s < cfg->n_samples; ++s)
         if (st[s] < 0 || st[s] >= cfg->n_targets) return fail(SCAR_ERR_INVALID, "sample %d: target id %d out of range", s, st[s]);
@@ -374,7 +397,7 @@ extern "C" int scar_pack_dev(scar_ctx *c, const scar_ragged *seq, int64_t n, uin
 {
     if (!c || !seq || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));
-    CU(scar_launch_pack(*seq, n, c->W, c->platform, cells, lens, c->d_status, c->sm_count, (cudaStream_t)stream, &c->launches));
+    CU(scar_launch_pack(*seq, n, c->W, c->platform, cells, n, lens, c->d_status, c->sm_count, (cudaStream_t)stream, &c->launches));
     return SCAR_OK;
 }
 
@@ -402,9 +425,9 @@ extern "C" int scar_classify_dev(scar_ctx *c, const uint64_t *cells, const uint1
     CU(cudaSetDevice(c->device));
     K3Params P; memset(&P, 0, sizeof(P));
     P.cells = cells; P.lens = lens; P.samples = samples; P.records = records; P.sample_target = c->d_sample_target;
-    P.targets = c->d_targets; P.phases = c->d_phases; P.tables = c->d_tables; P.table_bytes = c->table_bytes;
-    P.n_reads = n; P.W = c->W; P.n_samples = c->n_samples; P.do_phasing = c->do_phasing; P.min_length = c->min_length;
-    P.n_limit = c->n_limit; P.hr_code = c->hr_code; P.hr_len = c->hr_len; P.row_entries = c->W + 2;
+    P.blob = c->d_blob; P.blob_bytes = c->blob_bytes; P.meta_off = c->meta_off; P.phase_off = c->phase_off;
+    P.nmax_off = c->nmax_off; P.n_reads = n; P.stride = n; P.W = c->W; P.n_samples = c->n_samples;
+    P.do_phasing = c->do_phasing; P.min_length = c->min_length; P.hr_code = c->hr_code; P.hr_len = c->hr_len;
     CU(scar_launch_window(P, c->smem_tables, c->sm_count, (cudaStream_t)stream, &c->launches));
     return SCAR_OK;
 }

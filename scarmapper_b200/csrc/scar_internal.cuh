@@ -9,8 +9,8 @@
 
 #define SCAR_KMER 10                 // hard-coded window (INDEL_Processing.py:67,76; SlidingWindow.pyx:49-50)
 #define SCAR_KEY_MASK 0xFFFFFu       // 10 bases x 2 bits
-#define SCAR_KEY_TAG 0x100000u       // bit 20 set in every stored key so that an empty slot (0) never matches
-#define SCAR_MAX_WINDOWS 2048        // window index i is stored in 11 bits
+#define SCAR_TABLE_EMPTY 0xFFFFFFFFu // table entry = key << 12 | i ; i = 4095 is reserved for the empty pattern
+#define SCAR_MAX_WINDOWS 4095        // window index i is stored in 12 bits (0..4094)
 #define SCAR_MAX_PHASES 32
 #define SCAR_MAX_INDEX_LEN 64        // Myers bit-vector width
 #define SCAR_MAX_CLASSES 16          // distinct byte values over all index sequences (+ class 0 = other)
@@ -23,7 +23,9 @@ __host__ __device__ __forceinline__ bool scar_base_valid(uint8_t b)
     return b == 'A' || b == 'C' || b == 'G' || b == 'T';
 }
 
-// A packed read row is `cells` 64-bit cells; cell j covers bases [16j, 16j+16):
+// A packed read is W 64-bit cells, stored CELL-MAJOR in HBM (cell j of read r at cells[j*stride + r],
+// stride = reads in the batch) so that one-thread-per-read kernels load coalesced.  Cell j covers
+// bases [16j, 16j+16):
 //   bits  0..31  2-bit codes, base k of the cell at bits 2k..2k+1
 //   bits 32..47  ACGT mask (1 = byte is one of A,C,G,T)
 //   bits 48..63  N mask    (1 = byte is 'N')
@@ -71,7 +73,8 @@ struct ScarTableSlot {                  // 32 bytes, zero-initialised
 // ---- kernel parameter blocks and launchers ---------------------------------------------------------
 struct K1Params {
     scar_ragged seq;      // device pointers
-    uint64_t *cells;      // [n][W]
+    uint64_t *cells;      // cell-major [W][stride]
+    int64_t stride;
     uint16_t *lens;       // [n]
     int64_t n_reads;
     int32_t W;
@@ -93,24 +96,23 @@ struct K2Params {
 };
 
 struct K3Params {
-    const uint64_t *cells;        // [n][W]
+    const uint64_t *cells;        // cell-major: cell j of read r at cells[j * stride + r]
     const uint16_t *lens;         // [n]
     const uint16_t *samples;      // [n]
     scar_record *records;         // [n]
     const int32_t *sample_target; // [n_samples]
-    const ScarTargetMeta *targets;
-    const ScarPhase *phases;
-    const uint2 *tables;          // bucket blob, all targets
-    uint32_t table_bytes;         // multiple of 16
+    const void *blob;             // static data staged in shared memory: tables | metas | phases | nmax
+    uint32_t blob_bytes;          // multiple of 16
+    uint32_t meta_off, phase_off, nmax_off;   // byte offsets into the blob (tables start at 0)
     int64_t n_reads;
+    int64_t stride;               // reads per cell row
     int32_t W;                    // cells per read
     int32_t n_samples;
     int32_t do_phasing;
     int32_t min_length;
-    double n_limit;
     uint64_t hr_code;             // donor, 2 bits/base
     int32_t hr_len;
-    int32_t row_entries;          // per-warp staging entries (W + 2)
+    int32_t pad;
 };
 
 struct K4Params {
@@ -139,7 +141,7 @@ struct K4VerifyParams {
 
 cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t scar_launch_pack(const scar_ragged &seq, int64_t n, int W, int platform, uint64_t *cells,
-                             uint16_t *lens, int32_t *status, int sm_count, cudaStream_t stream, int *launches);
+                             int64_t stride, uint16_t *lens, int32_t *status, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t scar_launch_demux(const K2Params &P, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t scar_launch_match_maker(const scar_ragged &q, const scar_ragged &u, int64_t n, int32_t *out,
                                     cudaStream_t stream);

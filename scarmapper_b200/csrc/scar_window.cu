@@ -4,25 +4,27 @@
 // (reference scarmapper/INDEL_Processing.py:135-196) and SlidingWindow.sliding_window
 // (scarmapper/SlidingWindow.pyx:20-171), plus the phasing scan of consensus_demultiplex
 // (INDEL_Processing.py:948-975).  Not a translation: the reference compares every 10-nt read
-// window with every target window; here each target side is a bucketed perfect-hash table
-// "10-mer -> smallest window index i" staged in shared memory by one TMA bulk copy, a warp owns
-// a read, its 32 lanes test 32 consecutive read positions per round with one shared-memory probe
-// each, and the first hit in scan order is picked with a ballot.
+// window with every target window.  Here each target side is a bucketed perfect-hash table
+// "10-mer -> smallest window index i" (two entries per 8-byte bucket, one probe, no chains) staged in
+// shared memory by one TMA bulk copy per CTA; ONE THREAD owns a read.  The packed batch is
+// cell-major ([cell][read]), so a warp's loads of cell j are one coalesced 256-byte request, and the
+// per-read bookkeeping (filters, phasing, junction call) costs one instruction per 32 reads instead of
+// one per read.  A thread walks its read 16 positions (one cell) at a time: the 16 window keys are
+// independent funnel shifts of a 64-bit register pair, the 16 probes are issued back to back
+// (16 shared-memory loads in flight per thread), and the first hit in scan order is kept with a
+// max / min of (position << 12 | i).
 //
 //   left  search: positions p = len-20 .. 16 descending, first hit -> clj = p+10, tlj = cut - i
 //   right search: positions p = 10 .. len-26 ascending,  first hit -> crj = p,    trj = cut + i
-//
-// Work per read: (positions scanned)/32 rounds x (1 LDS.128 + 1 LDS.64 + ~20 integer ops).
 #include "scar_internal.cuh"
-
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-// One TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the whole table blob into shared memory,
-// completion signalled on an mbarrier.
+// One TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a blob into shared memory, completion signalled
+// on an mbarrier; every thread of the CTA waits for it.
 __device__ __forceinline__ void stage_tables_tma(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     if (threadIdx.x == 0) {
@@ -39,7 +41,6 @@ __device__ __forceinline__ void stage_tables_tma(void *dst, const void *src, uin
             "l"(src), "r"(bytes), "r"(smem_u32(bar))
             : "memory");
     }
-    // every thread waits for phase 0
     uint32_t done = 0;
     while (!done) {
         asm volatile(
@@ -54,43 +55,79 @@ __device__ __forceinline__ void stage_tables_tma(void *dst, const void *src, uin
     }
 }
 
-// probe one side's table: returns the stored entry ((key|TAG) << 11 | i) or 0
+// Table access.  In shared memory the table is addressed with 32-bit shared-window addresses and a
+// plain ld.shared.v2 (no generic-address conversion in the loop); otherwise it is read through the
+// read-only global path.  Entries are (key << 12 | i), i <= 4094, empty = 0xFFFFFFFF.
+template <bool SMEM> struct TableRef;
+template <> struct TableRef<true> {
+    uint32_t base;
+    __device__ __forceinline__ TableRef(const void *smem_tab, const void *, uint32_t off)
+        : base(smem_u32(smem_tab) + off * 8u) {}
+    __device__ __forceinline__ uint2 load(uint32_t bucket) const
+    {
+        uint2 v;
+        // volatile: the 16 loads of a cell stay in program order, ahead of their consumers
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(base + bucket * 8u));
+        return v;
+    }
+};
+template <> struct TableRef<false> {
+    const uint2 *base;
+    __device__ __forceinline__ TableRef(const void *, const void *gmem_tab, uint32_t off)
+        : base(reinterpret_cast<const uint2 *>(gmem_tab) + off) {}
+    __device__ __forceinline__ uint2 load(uint32_t bucket) const { return __ldg(base + bucket); }
+};
+
+// The 16 windows of one cell: t[o] holds the window's 20 key bits in its TOP bits (raw << 12); the 16
+// table loads are issued back to back (16 independent shared-memory loads in flight per thread), then
+// m[o] = i (< 4095) on a hit and a value >= 4095 otherwise.
 template <bool SMEM>
-__device__ __forceinline__ uint32_t probe(const uint2 *tab, uint32_t key, uint32_t mult, uint32_t shift)
+__device__ __forceinline__ void probe16(const TableRef<SMEM> &tab, uint32_t wlo, uint32_t whi, uint32_t mult,
+                                        uint32_t shift, uint32_t (&m)[16])
 {
-    const uint32_t b = (key * mult) >> shift;
-    uint2 e;
-    if (SMEM) e = tab[b]; else e = __ldg(tab + b);
-    const uint32_t want = key | SCAR_KEY_TAG;
-    uint32_t hit = 0;
-    if ((e.x >> 11) == want) hit = e.x;
-    if ((e.y >> 11) == want) hit = e.y;
-    return hit;
+    uint32_t t[16];
+    uint2 e[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        t[o] = __funnelshift_r(wlo, whi, 2 * o) << 12;
+        e[o] = tab.load((t[o] * mult) >> shift);
+    }
+#pragma unroll
+    for (int o = 0; o < 16; ++o) m[o] = min(e[o].x ^ t[o], e[o].y ^ t[o]);
+}
+
+// bit o set iff bases o .. o+9 of the 32-base window are all ACGT
+__device__ __forceinline__ uint32_t runs_of_ten(uint32_t vwin)
+{
+    const uint32_t a = vwin & (vwin >> 1);      // runs of 2
+    const uint32_t b = a & (a >> 2);            // runs of 4
+    const uint32_t c = b & (b >> 4);            // runs of 8
+    return c & (a >> 8);                        // runs of 10
+}
+
+__device__ __forceinline__ void store_record(scar_record *dst, const scar_record &rec)
+{
+    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(&rec);
 }
 
 template <bool SMEM, bool HR>
 __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [mbarrier 16 B][tables (SMEM only)][per-warp staging rows of uint4]
+    // layout: [mbarrier 16 B][static blob: tables | target metas | phases | N-limit table]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    const uint2 *tab = P.tables;
-    uint32_t off = 16;
+    const unsigned char *blob = reinterpret_cast<const unsigned char *>(P.blob);
     if (SMEM) {
-        uint2 *stab = reinterpret_cast<uint2 *>(smem_raw + off);
-        stage_tables_tma(stab, P.tables, P.table_bytes, bar);
-        tab = stab;
-        off += P.table_bytes;
+        stage_tables_tma(smem_raw + 16, P.blob, P.blob_bytes, bar);
+        blob = smem_raw + 16;
     }
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int warps_per_cta = blockDim.x >> 5;
-    uint4 *row = reinterpret_cast<uint4 *>(smem_raw + off) + (size_t)warp * P.row_entries;
-    const uint32_t FULL = 0xFFFFFFFFu;
-    const int W = P.W;
+    const ScarTargetMeta *metas = reinterpret_cast<const ScarTargetMeta *>(blob + P.meta_off);
+    const ScarPhase *phases = reinterpret_cast<const ScarPhase *>(blob + P.phase_off);
+    const uint16_t *nmax = reinterpret_cast<const uint16_t *>(blob + P.nmax_off);
+    const int64_t S = P.stride;      // reads per cell row
 
-    for (int64_t r = (int64_t)blockIdx.x * warps_per_cta + warp; r < P.n_reads;
-         r += (int64_t)gridDim.x * warps_per_cta) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads;
+         r += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t sample = P.samples[r];
         __align__(16) scar_record rec;
         rec.status = SCAR_ST_UNASSIGNED; rec.flags = 0; rec.sample = (uint16_t)sample;
@@ -98,121 +135,130 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
         rec.phase_r1 = SCAR_PHASE_NA; rec.phase_r2 = SCAR_PHASE_NA;
         if (sample >= (uint32_t)P.n_samples) {          // unidentified (INDEL_Processing.py:1194-1198)
             rec.sample = SCAR_SAMPLE_NONE;
-            if (lane == 0) *reinterpret_cast<uint4 *>(P.records + r) = *reinterpret_cast<uint4 *>(&rec);
+            store_record(P.records + r, rec);
             continue;
         }
         const int len = P.lens[r];
-        const ScarTargetMeta T = P.targets[P.sample_target[sample]];
-        const uint64_t *crow = P.cells + r * W;
+        const int tid = __ldg(P.sample_target + sample);
+        const ScarTargetMeta &T = metas[tid];
+        const uint64_t *col = P.cells + r;               // cell j of this read = col[j * S]
+        const int Wr = (len + 15) >> 4;                  // cells that hold bases
 
-        // ---- stage the row: entry j = {codes[j], codes[j+1], valid[j]|valid[j+1]<<16, N[j]|N[j+1]<<16}
-        __syncwarp();
+        // ---- N count over the whole read
         int n_count = 0;
-        for (int j = lane; j < P.row_entries; j += 32) {
-            const uint64_t c0 = j < W ? crow[j] : 0ull;
-            const uint64_t c1 = j + 1 < W ? crow[j + 1] : 0ull;
-            uint4 e;
-            e.x = (uint32_t)c0; e.y = (uint32_t)c1;
-            e.z = ((uint32_t)(c0 >> 32) & 0xFFFFu) | (((uint32_t)(c1 >> 32) & 0xFFFFu) << 16);
-            e.w = (uint32_t)(c0 >> 48) | ((uint32_t)(c1 >> 48) << 16);
-            row[j] = e;
-            n_count += __popc((uint32_t)(c0 >> 48));
-        }
-        n_count = __reduce_add_sync(FULL, n_count);
-        __syncwarp();
+        for (int j = 0; j < Wr; ++j) n_count += __popc((uint32_t)(__ldg(col + j * S) >> 48));
 
-        // ---- phasing (INDEL_Processing.py:948-975): lane k owns phase k of the read's locus
+        // ---- phasing (INDEL_Processing.py:948-975): first k matching the prefix / the suffix
         if (P.do_phasing && T.n_phase > 0) {
-            bool m1 = false, m2 = false;
-            if (lane < T.n_phase) {
-                const ScarPhase ph = P.phases[T.phase_off + lane];
-                if (ph.r1_len != 0) {                       // empty R1 string: phase skipped (:954-957)
-                    if (ph.r1_len <= 16 && len >= ph.r1_len) {
-                        const uint4 e = row[0];
-                        const uint32_t vm = (1u << ph.r1_len) - 1u;
-                        const uint32_t cm = ph.r1_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r1_len)) - 1u);
-                        m1 = ((e.z & vm) == vm) && ((e.x & cm) == ph.r1_code);
-                    }
-                    if (ph.r2_len != 0 && ph.r2_len <= 16 && len >= ph.r2_len) {
-                        const int p = len - ph.r2_len;
-                        const uint4 e = row[p >> 4];
-                        const int o = p & 15;
-                        const uint32_t vm = (1u << ph.r2_len) - 1u;
-                        const uint32_t cm = ph.r2_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r2_len)) - 1u);
-                        m2 = (((e.z >> o) & vm) == vm) && ((__funnelshift_r(e.x, e.y, 2 * o) & cm) == ph.r2_code);
-                    }
+            const uint64_t c0 = Wr > 0 ? __ldg(col) : 0ull;
+            int f1 = -1, f2 = -1;
+            for (int k = 0; k < T.n_phase; ++k) {
+                const ScarPhase ph = phases[T.phase_off + k];
+                if (ph.r1_len == 0) continue;            // empty R1 string: phase skipped (:954-957)
+                if (f2 < 0 && ph.r2_len != 0 && ph.r2_len <= 16 && len >= ph.r2_len) {
+                    const int p = len - ph.r2_len, j = p >> 4, o = p & 15;
+                    const uint64_t a = __ldg(col + j * S);
+                    const uint64_t b = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
+                    const uint32_t vwin = ((uint32_t)(a >> 32) & 0xFFFFu) | ((uint32_t)(b >> 32) << 16);
+                    const uint32_t vm = (1u << ph.r2_len) - 1u;
+                    const uint32_t cm = ph.r2_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r2_len)) - 1u);
+                    if ((((vwin >> o) & vm) == vm) &&
+                        ((__funnelshift_r((uint32_t)a, (uint32_t)b, 2 * o) & cm) == ph.r2_code)) f2 = k;
+                }
+                if (f1 < 0 && ph.r1_len <= 16 && len >= ph.r1_len) {
+                    const uint32_t vm = (1u << ph.r1_len) - 1u;
+                    const uint32_t cm = ph.r1_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r1_len)) - 1u);
+                    if (((((uint32_t)(c0 >> 32)) & vm) == vm) && (((uint32_t)c0 & cm) == ph.r1_code)) f1 = k;
                 }
             }
-            const uint32_t b1 = __ballot_sync(FULL, m1), b2 = __ballot_sync(FULL, m2);
-            rec.phase_r1 = b1 ? (int8_t)(__ffs(b1) - 1) : (int8_t)SCAR_PHASE_NONE;
-            rec.phase_r2 = b2 ? (int8_t)(__ffs(b2) - 1) : (int8_t)SCAR_PHASE_NONE;
+            rec.phase_r1 = (int8_t)(f1 < 0 ? SCAR_PHASE_NONE : f1);
+            rec.phase_r2 = (int8_t)(f2 < 0 ? SCAR_PHASE_NONE : f2);
         }
 
-        // ---- read filters (INDEL_Processing.py:147-154); Python int/int is an IEEE double divide
-        if (len == 0 || (double)n_count / (double)len > P.n_limit || len <= P.min_length) {
+        // ---- read filters (INDEL_Processing.py:147-154).  nmax[len] is the largest N count with
+        // double(n)/double(len) <= N_Limit, tabulated on the host with the same IEEE division.
+        if (len == 0 || n_count > (int)nmax[len] || len <= P.min_length) {
             rec.status = SCAR_ST_FILTERED;
-            if (lane == 0) *reinterpret_cast<uint4 *>(P.records + r) = *reinterpret_cast<uint4 *>(&rec);
+            store_record(P.records + r, rec);
             continue;
         }
 
-        int clj = 0, crj = 0, tlj = T.cutsite, trj = T.cutsite;
-        bool cutwindow_exit = false;
+        const int cut = T.cutsite;
+        int clj = 0, crj = 0, tlj = cut, trj = cut;
 
         // ---- left junction (SlidingWindow.pyx:49-69): p = len-20 .. 16, descending
         {
-            const uint2 *ltab = tab + T.left_off;
-            for (int pstart = len - 20; pstart >= 16; pstart -= 32) {
-                const int p = pstart - lane;
-                uint32_t hit = 0;
-                if (p >= 16) {
-                    const uint4 e = row[p >> 4];
-                    const int o = p & 15;
-                    if (((e.z >> o) & 0x3FFu) == 0x3FFu) {
-                        const uint32_t key = __funnelshift_r(e.x, e.y, 2 * o) & SCAR_KEY_MASK;
-                        hit = probe<SMEM>(ltab, key, T.left_mult, T.left_shift);
+            const TableRef<SMEM> ltab(blob, P.blob, T.left_off);
+            const uint32_t mult = T.left_mult, shift = T.left_shift;
+            const int p0 = len - 20;
+            if (p0 >= 16) {
+                int j = p0 >> 4;
+                uint64_t hi = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
+                uint32_t best = 0;
+                for (; j >= 1; --j) {
+                    const uint64_t lo = __ldg(col + j * S);
+                    const uint32_t wlo = (uint32_t)lo, whi = (uint32_t)hi;
+                    const uint32_t vwin = ((uint32_t)(lo >> 32) & 0xFFFFu) | ((uint32_t)(hi >> 32) << 16);
+                    const int pbase = 16 * j;
+                    // positions of this cell that are scanned (<= p0) and whose window is all ACGT
+                    const int top = p0 - pbase;                       // >= 0 here
+                    const uint32_t okmask = runs_of_ten(vwin) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
+                    uint32_t m[16];
+                    probe16<SMEM>(ltab, wlo, whi, mult, shift, m);
+#pragma unroll
+                    for (int o = 15; o >= 0; --o) {
+                        const uint32_t cand = ((uint32_t)(pbase + o) << 12) + m[o];
+                        if (m[o] < 4095u && ((okmask >> o) & 1u)) best = max(best, cand);
                     }
+                    if (best) break;
+                    hi = lo;
                 }
-                const uint32_t bal = __ballot_sync(FULL, hit != 0);
-                if (bal) {
-                    const int src = __ffs(bal) - 1;            // lowest lane = highest position
-                    const uint32_t h = __shfl_sync(FULL, hit, src);
-                    if (((h >> 11) & SCAR_KEY_MASK) == T.cutwindow_key) cutwindow_exit = true;  // :56-60
-                    clj = pstart - src + 10;
-                    tlj = T.cutsite - (int)(h & 0x7FFu);
-                    break;
+                if (best) {
+                    const int p = (int)(best >> 12), i = (int)(best & 0xFFFu);
+                    // SlidingWindow.pyx:56-60 (reachable only through the per-read drop-in)
+                    if (T.cutwindow_key != 0xFFFFFFFFu) {
+                        const int jj = p >> 4, o = p & 15;
+                        const uint64_t a = __ldg(col + jj * S);
+                        const uint64_t b = jj + 1 < Wr ? __ldg(col + (jj + 1) * S) : 0ull;
+                        if ((__funnelshift_r((uint32_t)a, (uint32_t)b, 2 * o) & SCAR_KEY_MASK) == T.cutwindow_key) {
+                            rec.status = SCAR_ST_NO_CUT; rec.flags = SCAR_FL_CUTWINDOW;
+                            rec.tlj = rec.trj = (uint16_t)cut;
+                            store_record(P.records + r, rec);
+                            continue;
+                        }
+                    }
+                    clj = p + 10; tlj = cut - i;
                 }
             }
-        }
-        if (cutwindow_exit) {
-            rec.status = SCAR_ST_NO_CUT; rec.flags = SCAR_FL_CUTWINDOW;
-            rec.tlj = rec.trj = (uint16_t)T.cutsite;
-            if (lane == 0) *reinterpret_cast<uint4 *>(P.records + r) = *reinterpret_cast<uint4 *>(&rec);
-            continue;
         }
 
         // ---- right junction (SlidingWindow.pyx:79-93): p = 10 .. len-26, ascending
         {
-            const uint2 *rtab = tab + T.right_off;
+            const TableRef<SMEM> rtab(blob, P.blob, T.right_off);
+            const uint32_t mult = T.right_mult, shift = T.right_shift;
             const int plast = len - 26;
-            for (int pstart = 10; pstart <= plast; pstart += 32) {
-                const int p = pstart + lane;
-                uint32_t hit = 0;
-                if (p <= plast) {
-                    const uint4 e = row[p >> 4];
-                    const int o = p & 15;
-                    if (((e.z >> o) & 0x3FFu) == 0x3FFu) {
-                        const uint32_t key = __funnelshift_r(e.x, e.y, 2 * o) & SCAR_KEY_MASK;
-                        hit = probe<SMEM>(rtab, key, T.right_mult, T.right_shift);
+            if (plast >= 10) {
+                uint64_t lo = __ldg(col);
+                uint32_t best = 0xFFFFFFFFu;
+                for (int j = 0; 16 * j <= plast; ++j) {
+                    const uint64_t hi = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
+                    const uint32_t wlo = (uint32_t)lo, whi = (uint32_t)hi;
+                    const uint32_t vwin = ((uint32_t)(lo >> 32) & 0xFFFFu) | ((uint32_t)(hi >> 32) << 16);
+                    const int pbase = 16 * j;
+                    const int top = plast - pbase;                    // >= 0 here
+                    uint32_t okmask = runs_of_ten(vwin) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
+                    if (j == 0) okmask &= 0xFC00u;                    // p >= 10
+                    uint32_t m[16];
+                    probe16<SMEM>(rtab, wlo, whi, mult, shift, m);
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) {
+                        const uint32_t cand = ((uint32_t)(pbase + o) << 12) + m[o];
+                        if (m[o] < 4095u && ((okmask >> o) & 1u)) best = min(best, cand);
                     }
+                    if (best != 0xFFFFFFFFu) break;
+                    lo = hi;
                 }
-                const uint32_t bal = __ballot_sync(FULL, hit != 0);
-                if (bal) {
-                    const int src = __ffs(bal) - 1;
-                    const uint32_t h = __shfl_sync(FULL, hit, src);
-                    crj = pstart + src;
-                    trj = T.cutsite + (int)(h & 0x7FFu);
-                    break;
-                }
+                if (best != 0xFFFFFFFFu) { crj = (int)(best >> 12); trj = cut + (int)(best & 0xFFFu); }
             }
         }
 
@@ -220,7 +266,7 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
 
         if (clj < 1 && crj < 1) {                            // :96-98
             rec.status = SCAR_ST_NO_JUNCTION;
-            if (lane == 0) *reinterpret_cast<uint4 *>(P.records + r) = *reinterpret_cast<uint4 *>(&rec);
+            store_record(P.records + r, rec);
             continue;
         }
 
@@ -231,19 +277,21 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
             const uint64_t cm = h == 32 ? ~0ull : ((1ull << (2 * h)) - 1ull);
             const uint64_t vm = h == 32 ? 0xFFFFFFFFull : ((1ull << h) - 1ull);
             int n = 0;
-            for (int pstart = 25; pstart <= plast; pstart += 32) {
-                const int p = pstart + lane;
-                bool m = false;
-                if (p <= plast) {
-                    const int j = p >> 4, o = p & 15;
-                    const uint4 e0 = row[j], e1 = row[j + 1];      // cells j, j+1 | j+1, j+2
-                    const uint32_t lo = __funnelshift_r(e0.x, e0.y, 2 * o);
-                    const uint32_t hi = __funnelshift_r(e1.x, e1.y, 2 * o);
-                    const uint64_t code = ((uint64_t)hi << 32 | lo) & cm;
-                    const uint64_t v48 = (uint64_t)e0.z | ((uint64_t)(e1.z >> 16) << 32);
-                    m = (((v48 >> o) & vm) == vm) && code == P.hr_code;
+            if (plast >= 25) {
+                int j = 25 >> 4;
+                uint64_t c0 = __ldg(col + j * S);
+                uint64_t c1 = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
+                uint64_t c2 = j + 2 < Wr ? __ldg(col + (j + 2) * S) : 0ull;
+                for (int p = 25; p <= plast; ++p) {
+                    if ((p >> 4) != j) { j = p >> 4; c0 = c1; c1 = c2; c2 = j + 2 < Wr ? __ldg(col + (j + 2) * S) : 0ull; }
+                    const int o = p & 15;
+                    const uint32_t lo = __funnelshift_r((uint32_t)c0, (uint32_t)c1, 2 * o);
+                    const uint32_t hi = __funnelshift_r((uint32_t)c1, (uint32_t)c2, 2 * o);
+                    const uint64_t code = (((uint64_t)hi << 32) | lo) & cm;
+                    const uint64_t v48 = ((c0 >> 32) & 0xFFFFull) | (((c1 >> 32) & 0xFFFFull) << 16) |
+                                         (((c2 >> 32) & 0xFFFFull) << 32);
+                    n += ((((v48 >> o) & vm) == vm) && code == P.hr_code) ? 1 : 0;
                 }
-                n += __popc(__ballot_sync(FULL, m));
             }
             rec.hr_n = (uint16_t)n;
             if (n) rec.flags |= SCAR_FL_HR;
@@ -254,25 +302,23 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
         if (0 < clj && clj < crj) {
             // literal 'N' anywhere in read[clj:crj] drops the read with no counter (:140-141)
             bool has_n = false;
-            for (int j = lane; j < W; j += 32) {
+            for (int j = clj >> 4; 16 * j < crj; ++j) {
                 const int lo = max(clj, 16 * j) - 16 * j, hi = min(crj, 16 * j + 16) - 16 * j;
-                if (hi > lo) {
-                    const uint32_t m = ((1u << (hi - lo)) - 1u) << lo;
-                    has_n |= ((row[j].w & 0xFFFFu) & m) != 0;
-                }
+                const uint32_t m = ((1u << (hi - lo)) - 1u) << lo;
+                has_n |= (((uint32_t)(__ldg(col + j * S) >> 48)) & m) != 0;
             }
-            if (__any_sync(FULL, has_n)) {
+            if (has_n) {
                 rec.status = SCAR_ST_N_INSERTION;
-                if (lane == 0) *reinterpret_cast<uint4 *>(P.records + r) = *reinterpret_cast<uint4 *>(&rec);
+                store_record(P.records + r, rec);
                 continue;
             }
             cut_found = true; rec.flags |= SCAR_FL_INSERTION;
         }
-        if (tlj < T.cutsite) { cut_found = true; rec.flags |= SCAR_FL_LEFT_DEL; }
-        if (trj > T.cutsite) { cut_found = true; rec.flags |= SCAR_FL_RIGHT_DEL; }
+        if (tlj < cut) { cut_found = true; rec.flags |= SCAR_FL_LEFT_DEL; }
+        if (trj > cut) { cut_found = true; rec.flags |= SCAR_FL_RIGHT_DEL; }
         if (clj > crj && crj > 0) { cut_found = true; rec.flags |= SCAR_FL_MICROHOM; }
         rec.status = cut_found ? SCAR_ST_SCAR : SCAR_ST_NO_CUT;
-        if (lane == 0) *reinterpret_cast<uint4 *>(P.records + r) = *reinterpret_cast<uint4 *>(&rec);
+        store_record(P.records + r, rec);
     }
 }
 
@@ -280,9 +326,9 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
 cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count, cudaStream_t stream,
                                int *launches)
 {
+    if (P.n_reads <= 0) return cudaSuccess;
     const int threads = 256;
-    const size_t row_bytes = (size_t)(threads / 32) * P.row_entries * sizeof(uint4);
-    const size_t smem = 16 + (smem_tables ? P.table_bytes : 0) + row_bytes;
+    const size_t smem = 16 + (smem_tables ? P.blob_bytes : 0);
     const bool hr = P.hr_len > 0;
     void (*kern)(const K3Params) =
         smem_tables ? (hr ? scar_window_kernel<true, true> : scar_window_kernel<true, false>)
@@ -294,10 +340,9 @@ cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     // persistent grid: a whole number of resident CTAs per SM, never more than the work needs
-    int64_t want = (P.n_reads + (threads / 32) - 1) / (threads / 32);
+    int64_t want = (P.n_reads + threads - 1) / threads;
     int64_t grid = (int64_t)sm_count * per_sm;
     if (grid > want) grid = want;
-    if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, threads, smem, stream>>>(P);
     if (launches) ++*launches;
     return cudaGetLastError();

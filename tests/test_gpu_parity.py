@@ -149,17 +149,17 @@ def test_multi_chunk_pipeline_keeps_global_first_index(monkeypatch):
 
 
 def pack_reference(reads, W):
-    """numpy restatement of the packed row layout (scar_internal.cuh)."""
-    out = np.zeros((len(reads), W), dtype=np.uint64)
+    """numpy restatement of the packed layout (scar_internal.cuh): cell-major [W][n_reads]."""
+    out = np.zeros((W, len(reads)), dtype=np.uint64)
     code = {ord("A"): 0, ord("C"): 1, ord("T"): 2, ord("G"): 3}
     for r, s in enumerate(reads):
         b = s.encode("latin-1") if isinstance(s, str) else s
         for k, ch in enumerate(b):
             j, o = divmod(k, 16)
             if ch in code:
-                out[r, j] |= np.uint64(code[ch] << (2 * o)) | np.uint64(1 << (32 + o))
+                out[j, r] |= np.uint64(code[ch] << (2 * o)) | np.uint64(1 << (32 + o))
             elif ch == ord("N"):
-                out[r, j] |= np.uint64(1 << (48 + o))
+                out[j, r] |= np.uint64(1 << (48 + o))
     return out
 
 
