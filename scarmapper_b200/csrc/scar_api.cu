@@ -66,7 +66,7 @@ static uint64_t encode_bases(const uint8_t *p, int n)
     return c;
 }
 
-struct BucketTable { std::vector<uint2> buckets; uint32_t mult, shift; };
+struct BucketTable { std::vector<uint2> buckets; uint32_t mult, nbuckets; };
 
 // window list -> bucketed perfect hash "10-mer -> smallest i" (two entries per bucket, one probe)
 static bool build_table(const std::vector<std::pair<uint32_t, uint32_t>> &kv /* key, min i */, BucketTable &out)
@@ -90,7 +90,7 @@ static bool build_table(const std::vector<std::pair<uint32_t, uint32_t>> &kv /* 
                 else if (b[slot].y == SCAR_TABLE_EMPTY) b[slot].y = val;
                 else { ok = false; break; }
             }
-            if (ok) { out.buckets.swap(b); out.mult = mult; out.shift = 32 - log2b; return true; }
+            if (ok) { out.buckets.swap(b); out.mult = mult; out.nbuckets = B; return true; }
         }
     }
     return false;
@@ -118,6 +118,7 @@ struct scar_ctx {
     bool smem_tables = true;
     uint8_t *d_class_map = nullptr; DemuxString *d_right = nullptr, *d_left = nullptr; uint64_t *d_peq = nullptr;
     uint16_t *d_first_sample = nullptr; int n_right = 0, n_left = 0, n_classes = 0;
+    uint8_t *d_fast_codes = nullptr; int demux_fast = 0;
     ScarTableSlot *d_slots = nullptr; uint64_t capacity = 0;
     unsigned long long *d_acc = nullptr;   // [n_entries, unassigned, collisions, export_count] + counters + phase hist
     unsigned long long *d_n_entries = nullptr, *d_unassigned = nullptr, *d_collisions = nullptr, *d_export_n = nullptr;
@@ -143,7 +144,7 @@ extern "C" void scar_ctx_destroy(scar_ctx *c)
     cudaSetDevice(c->device);
     for (auto &b : c->buf) free_hostbuf(b);
     cudaFree(c->d_sample_target); cudaFree(c->d_blob);
-    cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample);
+    cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample); cudaFree(c->d_fast_codes);
     cudaFree(c->d_slots); cudaFree(c->d_acc); cudaFree(c->d_status);
     delete c;
 }
@@ -202,7 +203,20 @@ static int build_demux(scar_ctx *c, const scar_config *cfg)
     std::vector<uint16_t> first(std::max<size_t>(hr.size() * hl.size(), 1), SCAR_SAMPLE_NONE);
     for (int s = c->n_samples - 1; s >= 0; --s) first[s_right[s] * hl.size() + s_left[s]] = (uint16_t)s;
     c->n_right = (int)hr.size(); c->n_left = (int)hl.size(); c->n_classes = n_classes;
+    // fast path: every distinct string is ACGT-only and <= 16 nt -> 2-bit Hamming shortcut in K2
+    std::vector<uint8_t> fast((hr.size() + hl.size()) * 16 + 1, 0);
+    bool all_fast = true;
+    for (size_t side = 0; side < 2; ++side) {
+        const auto &v = side ? left_s : right_s;
+        for (size_t d = 0; d < v.size(); ++d) {
+            if (v[d].size() > 16 || !acgt_only((const uint8_t *)v[d].data(), (int)v[d].size())) { all_fast = false; continue; }
+            for (size_t k = 0; k < v[d].size(); ++k)
+                fast[(side ? hr.size() : 0) * 16 + d * 16 + k] = (uint8_t)scar_base_code((uint8_t)v[d][k]);
+        }
+    }
+    c->demux_fast = all_fast ? 1 : 0;
     int rc;
+    if ((rc = upload(&c->d_fast_codes, fast))) return rc;
     if ((rc = upload(&c->d_class_map, cmap))) return rc;
     if ((rc = upload(&c->d_right, hr))) return rc;
     if ((rc = upload(&c->d_left, hl))) return rc;
@@ -272,8 +286,8 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
             std::vector<std::pair<uint32_t, uint32_t>> kv(mn.begin(), mn.end());
             BucketTable bt;
             if (!build_table(kv, bt)) return fail(SCAR_ERR_UNSUPPORTED, "target %d: could not build a window table", t);
-            if (side == 0) { m.left_off = (uint32_t)blob.size(); m.left_mult = bt.mult; m.left_shift = bt.shift; }
-            else { m.right_off = (uint32_t)blob.size(); m.right_mult = bt.mult; m.right_shift = bt.shift; }
+            if (side == 0) { m.left_off = (uint32_t)blob.size(); m.left_mult = bt.mult; m.left_buckets = bt.nbuckets; }
+            else { m.right_off = (uint32_t)blob.size(); m.right_mult = bt.mult; m.right_buckets = bt.nbuckets; }
             blob.insert(blob.end(), bt.buckets.begin(), bt.buckets.end());
         }
         m.cutwindow_key = 0xFFFFFFFFu;
@@ -413,6 +427,7 @@ extern "C" int scar_demux_dev(scar_ctx *c, const scar_ragged *seq, const scar_ra
     P.samples = samples; P.n_reads = n; P.class_map = c->d_class_map; P.right = c->d_right; P.left = c->d_left;
     P.peq = c->d_peq; P.first_sample = c->d_first_sample; P.n_right = c->n_right; P.n_left = c->n_left;
     P.n_classes = c->n_classes; P.platform = c->platform; P.mismatch = c->mismatch;
+    P.fast_codes = c->d_fast_codes; P.fast = c->demux_fast;
     CU(scar_launch_demux(P, c->sm_count, (cudaStream_t)stream, &c->launches));
     return SCAR_OK;
 }

@@ -20,11 +20,54 @@
 #include "scar_internal.cuh"
 
 
+// 2-bit codes + ACGT mask of a string of <= 16 bytes (aligned word loads + SWAR classification)
+__device__ __forceinline__ void encode16(const uint8_t *u, int n, uint32_t &code, uint32_t &valid)
+{
+    const uintptr_t a = (uintptr_t)u, a0 = a & ~(uintptr_t)3;
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t w[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const uintptr_t wa = a0 + 4 * i;
+        w[i] = (wa < a + (uintptr_t)n) ? __ldg(reinterpret_cast<const uint32_t *>(wa)) : 0u;
+    }
+    code = 0; valid = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t c8, v4, n4;
+        classify4(__funnelshift_r(w[i], w[i + 1], sh), c8, v4, n4);
+        code |= c8 << (8 * i); valid |= v4 << (4 * i);
+    }
+    valid &= n >= 16 ? 0xFFFFu : ((1u << n) - 1u);
+    code &= n >= 16 ? 0xFFFFFFFFu : ((1u << (2 * n)) - 1u);    // bytes past the string belong to the next item
+}
+
+// every position that is invalid or past the length counts as a mismatch: bit 2k set
+__device__ __forceinline__ uint32_t spread_invalid(uint32_t valid, int n)
+{
+    uint32_t m = ~valid & (n >= 16 ? 0xFFFFu : ((1u << n) - 1u));
+    m = (m | (m << 8)) & 0x00FF00FFu; m = (m | (m << 4)) & 0x0F0F0F0Fu;
+    m = (m | (m << 2)) & 0x33333333u; m = (m | (m << 1)) & 0x55555555u;
+    return m;
+}
+
+template <bool FAST>
 __global__ void __launch_bounds__(256) scar_demux_kernel(const K2Params P)
 {
     __shared__ uint8_t cmap[256];
+    __shared__ uint32_t s_code[2][64];     // 2-bit codes of the distinct index strings (FAST)
+    __shared__ int32_t s_len[2][64];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = P.class_map[i];
+    for (int i = threadIdx.x; i < P.n_right + P.n_left; i += blockDim.x) {
+        const int side = i >= P.n_right, d = side ? i - P.n_right : i;
+        const DemuxString ds = side ? P.left[d] : P.right[d];
+        s_len[side][d] = ds.len;
+        uint32_t c = 0;    // class ids 1..4 were assigned in order of first appearance; re-encode to 2-bit base codes
+        if (FAST) for (int k = 0; k < ds.len; ++k) c |= (uint32_t)P.fast_codes[(side ? P.n_right : 0) * 16 + d * 16 + k] << (2 * k);
+        s_code[side][d] = c;
+    }
     __syncthreads();
+    const int thr = P.mismatch;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads;
          r += (int64_t)gridDim.x * blockDim.x) {
         const uint8_t *u0 = nullptr, *u1 = nullptr, *seq = nullptr;
@@ -41,30 +84,54 @@ __global__ void __launch_bounds__(256) scar_demux_kernel(const K2Params P)
         }
         uint64_t c0[2], c1[2];
         int cached0 = -1, cached1 = -1;
-        if (P.platform != SCAR_PLATFORM_RAMSDEN) {
+        uint32_t e0 = 0, x0 = 0, e1 = 0, x1 = 0;        // FAST: codes and spread invalid masks of u0 / u1
+        const bool ramsden = P.platform == SCAR_PLATFORM_RAMSDEN;
+        if (FAST && !ramsden) {
+            uint32_t v;
+            if (n0 <= 16) { encode16(u0, n0, e0, v); x0 = spread_invalid(v, n0); }
+            if (n1 <= 16) { encode16(u1, n1, e1, v); x1 = spread_invalid(v, n1); }
+        } else if (!ramsden) {
             class_codes(u0, n0, cmap, c0);
             class_codes(u1, n1, cmap, c1);
         }
         uint64_t ok_r = 0, ok_l = 0;   // bit d set: distinct string d accepted
         for (int d = 0; d < P.n_right; ++d) {
-            const DemuxString ds = P.right[d];
-            if (P.platform == SCAR_PLATFORM_RAMSDEN) {
-                u0 = seq; n0 = slen < ds.len ? slen : ds.len;             // seq[:len(right_index)]
+            const int m = s_len[0][d];
+            if (ramsden) {
+                u0 = seq; n0 = slen < m ? slen : m;                       // seq[:len(right_index)]
                 if (cached0 != n0) { class_codes(u0, n0, cmap, c0); cached0 = n0; }
             }
-            if (accepts(ds, P.peq, u0, n0, c0, cmap, P.mismatch)) ok_r |= 1ull << d;
+            bool acc;
+            if (FAST && !ramsden && n0 == m && m <= 16) {
+                const uint32_t x = e0 ^ s_code[0][d];
+                const int ham = __popc(((x | (x >> 1)) & 0x55555555u) | x0);
+                acc = ham <= thr;
+                if (!acc && thr > 1) acc = accepts(P.right[d], P.peq, u0, n0, c0, cmap, thr, false);
+            } else {
+                acc = accepts(P.right[d], P.peq, u0, n0, c0, cmap, thr, !(FAST && !ramsden));
+            }
+            if (acc) ok_r |= 1ull << d;
         }
         uint32_t best = SCAR_SAMPLE_NONE;
         if (ok_r) {
             for (int d = 0; d < P.n_left; ++d) {
-                const DemuxString ds = P.left[d];
-                if (P.platform == SCAR_PLATFORM_RAMSDEN) {
+                const int m = s_len[1][d];
+                if (ramsden) {
                     // seq[-len(left_index):] ; seq[-0:] is the whole string
-                    n1 = (ds.len == 0 || ds.len >= slen) ? slen : ds.len;
+                    n1 = (m == 0 || m >= slen) ? slen : m;
                     u1 = seq + (slen - n1);
                     if (cached1 != n1) { class_codes(u1, n1, cmap, c1); cached1 = n1; }
                 }
-                if (accepts(ds, P.peq, u1, n1, c1, cmap, P.mismatch)) ok_l |= 1ull << d;
+                bool acc;
+                if (FAST && !ramsden && n1 == m && m <= 16) {
+                    const uint32_t x = e1 ^ s_code[1][d];
+                    const int ham = __popc(((x | (x >> 1)) & 0x55555555u) | x1);
+                    acc = ham <= thr;
+                    if (!acc && thr > 1) acc = accepts(P.left[d], P.peq, u1, n1, c1, cmap, thr, false);
+                } else {
+                    acc = accepts(P.left[d], P.peq, u1, n1, c1, cmap, thr, !(FAST && !ramsden));
+                }
+                if (acc) ok_l |= 1ull << d;
             }
             // first manifest row whose (right, left) strings are both acceptable
             for (uint64_t a = ok_r; a; a &= a - 1) {
@@ -87,7 +154,8 @@ cudaError_t scar_launch_demux(const K2Params &P, int sm_count, cudaStream_t stre
     int64_t blocks = (P.n_reads + threads - 1) / threads;
     const int64_t cap = (int64_t)sm_count * 8 * 4;
     if (blocks > cap) blocks = cap;
-    scar_demux_kernel<<<(unsigned)blocks, threads, 0, stream>>>(P);
+    if (P.fast) scar_demux_kernel<true><<<(unsigned)blocks, threads, 0, stream>>>(P);
+    else scar_demux_kernel<false><<<(unsigned)blocks, threads, 0, stream>>>(P);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -63,7 +63,6 @@ SCAR_HD void class_codes(const uint8_t *u, int n, const uint8_t *class_map, uint
 SCAR_HD int hamming_classes(const uint64_t a[2], const uint64_t b[2])
 {
     int h = 0;
-#pragma unroll
     for (int i = 0; i < 2; ++i) {
         uint64_t x = a[i] ^ b[i];
         x = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x1111111111111111ull;
@@ -73,11 +72,13 @@ SCAR_HD int hamming_classes(const uint64_t a[2], const uint64_t b[2])
 }
 
 // does match_maker(d, u) <= t hold?
+// use_codes = false skips the class-code Hamming shortcut (ucode not available / already decided)
 SCAR_HD bool accepts(const DemuxString &d, const uint64_t *peq, const uint8_t *u, int n,
-                                        const uint64_t ucode[2], const uint8_t *class_map, int t)
+                                        const uint64_t ucode[2], const uint8_t *class_map, int t,
+                                        bool use_codes = true)
 {
     const int m = d.len;
-    if (n == m && m <= 32) {
+    if (use_codes && n == m && m <= 32) {
         // class 0 ("other") never equals an index symbol (classes >= 1) so the XOR test is exact
         const int h = hamming_classes(d.code, ucode);
         if (h <= t) return true;          // lev <= hamming

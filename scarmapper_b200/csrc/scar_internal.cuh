@@ -35,8 +35,8 @@ struct ScarTargetMeta {
     int32_t cutsite, length;
     int32_t n_left, n_right;
     uint32_t left_off, right_off;      // bucket (uint2) offsets into the table blob
-    uint32_t left_mult, right_mult;    // bucket = (key * mult) >> shift
-    uint32_t left_shift, right_shift;
+    uint32_t left_mult, right_mult;    // bucket = mulhi((key << 12) * mult, buckets)  (top log2(buckets) bits)
+    uint32_t left_buckets, right_buckets;
     uint32_t cutwindow_key;            // SlidingWindow.pyx:56-60 test; 0xFFFFFFFF = none
     int32_t phase_off, n_phase;
     int32_t pad;
@@ -62,13 +62,39 @@ __host__ __device__ __forceinline__ uint64_t scar_mix2(uint64_t k)
     return k ^ (k >> 33);
 }
 
-struct ScarTableSlot {                  // 32 bytes, zero-initialised
-    unsigned long long h1;              // 0 = empty
-    unsigned long long h2;              // 0 = not yet published
+struct __align__(16) ScarTableSlot {    // 32 bytes, zero-initialised
+    unsigned __int128 tag;              // h1 | h2 << 64 ; 0 = empty.  Claimed with ONE 128-bit CAS (ATOMG.CAS.128)
     unsigned long long inv_first;       // ~first_idx, combined with atomicMax
     uint32_t count;
     uint32_t sample;
 };
+
+#ifdef __CUDACC__
+// ---- SWAR byte classification shared by K1 (pack) and K2 (demux fast path) --------------------------
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
+{
+    // 0x80 in every byte of x that is zero (exact, no borrow propagation)
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+
+// four bytes -> 8-bit codes, 4-bit ACGT mask, 4-bit N mask
+__device__ __forceinline__ void classify4(uint32_t w, uint32_t &code8, uint32_t &valid4, uint32_t &n4)
+{
+    uint32_t c = (w >> 1) & 0x03030303u;           // A=0 C=1 T=2 G=3 in each byte
+    uint32_t t = c | (c >> 6);
+    code8 = (t | (t >> 12)) & 0xFFu;
+    // canonical letter of each code, then compare with the input byte
+    uint32_t sel = (c & 0x3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
+    uint32_t canon = __byte_perm(0x47544341u /* 'A','C','T','G' */, 0u, sel);
+    uint32_t v = zero_bytes(w ^ canon);            // 0x80 per valid byte
+    v = (v >> 7);
+    valid4 = (v | (v >> 7) | (v >> 14) | (v >> 21)) & 0xFu;
+    uint32_t n = zero_bytes(w ^ 0x4E4E4E4Eu) >> 7; // 'N'
+    n4 = (n | (n >> 7) | (n >> 14) | (n >> 21)) & 0xFu;
+}
+
+
+#endif
 
 // ---- kernel parameter blocks and launchers ---------------------------------------------------------
 struct K1Params {
@@ -91,8 +117,11 @@ struct K2Params {
     const DemuxString *left;   // distinct left_index strings (scored against u1)
     const uint64_t *peq;
     const uint16_t *first_sample; // [n_right][n_left] first manifest row with that pair, 0xFFFF = none
+    const uint8_t *fast_codes;    // [(n_right + n_left)][16] 2-bit base codes of the distinct strings (fast only)
     int32_t n_right, n_left, n_classes;
     int32_t platform, mismatch;
+    int32_t fast;              // every index string is ACGT-only and <= 16 nt: 2-bit Hamming shortcut
+    int32_t pad;
 };
 
 struct K3Params {

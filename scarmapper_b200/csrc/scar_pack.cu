@@ -12,29 +12,6 @@
 // the one-thread-per-read kernels downstream load coalesced.
 #include "scar_internal.cuh"
 
-__device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
-{
-    // 0x80 in every byte of x that is zero (exact, no borrow propagation)
-    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
-}
-
-// four bytes -> 8-bit codes, 4-bit ACGT mask, 4-bit N mask
-__device__ __forceinline__ void classify4(uint32_t w, uint32_t &code8, uint32_t &valid4, uint32_t &n4)
-{
-    uint32_t c = (w >> 1) & 0x03030303u;           // A=0 C=1 T=2 G=3 in each byte
-    uint32_t t = c | (c >> 6);
-    code8 = (t | (t >> 12)) & 0xFFu;
-    // canonical letter of each code, then compare with the input byte
-    uint32_t sel = (c & 0x3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
-    uint32_t canon = __byte_perm(0x47544341u /* 'A','C','T','G' */, 0u, sel);
-    uint32_t v = zero_bytes(w ^ canon);            // 0x80 per valid byte
-    v = (v >> 7);
-    valid4 = (v | (v >> 7) | (v >> 14) | (v >> 21)) & 0xFu;
-    uint32_t n = zero_bytes(w ^ 0x4E4E4E4Eu) >> 7; // 'N'
-    n4 = (n | (n >> 7) | (n >> 14) | (n >> 21)) & 0xFu;
-}
-
-
 __global__ void __launch_bounds__(256) scar_pack_kernel(const K1Params P)
 {
     // a CTA owns a tile of blockDim.x consecutive reads and walks their cells j = 0..W-1: the tile's

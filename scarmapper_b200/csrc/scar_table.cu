@@ -58,39 +58,58 @@ __device__ __forceinline__ void key_hashes(const scar_record &rec, const uint8_t
     if (h2 == 0) h2 = 1;
 }
 
-__device__ __forceinline__ void table_insert(const K4Params &P, uint64_t h1, uint64_t h2, uint32_t n,
-                                             uint64_t first, uint32_t sample)
+__device__ __forceinline__ unsigned __int128 make_tag(uint64_t h1, uint64_t h2)
 {
+    return (unsigned __int128)h1 | ((unsigned __int128)h2 << 64);
+}
+
+// 16-byte load of a slot's tag that bypasses L1 (other SMs publish tags with L2 atomics)
+__device__ __forceinline__ unsigned __int128 load_tag(const ScarTableSlot *s)
+{
+    unsigned long long lo, hi;
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(&s->tag));
+    return (unsigned __int128)lo | ((unsigned __int128)hi << 64);
+}
+
+// Insert (or find) the key and fold n occurrences with smallest global index `first` into it.
+// One slot visit = one plain 16-byte load; only an empty slot costs an atomic (one 128-bit CAS that
+// publishes both hashes at once); count and first_idx are fire-and-forget reductions.
+// Returns 1 when a new slot was claimed.
+__device__ __forceinline__ int table_insert(const K4Params &P, uint64_t h1, uint64_t h2, uint32_t n,
+                                            uint64_t first, uint32_t sample)
+{
+    const unsigned __int128 tag = make_tag(h1, h2);
     uint64_t slot = h1 & P.slot_mask;
     for (uint32_t probe = 0; probe <= P.max_probe; ++probe) {
         ScarTableSlot *s = P.slots + slot;
-        const unsigned long long prev = atomicCAS(&s->h1, 0ull, (unsigned long long)h1);
-        if (prev == 0ull || prev == h1) {
-            if (prev == 0ull) atomicAdd(P.n_entries, 1ull);
-            // the first thread to publish h2 defines the slot; a different h2 under the same h1 is
-            // a different key and keeps probing
-            const unsigned long long p2 = atomicCAS(&s->h2, 0ull, (unsigned long long)h2);
-            if (p2 == 0ull || p2 == h2) {
-                atomicAdd(&s->count, n);
-                atomicMax(&s->inv_first, ~(unsigned long long)first);
-                s->sample = sample;
-                return;
-            }
+        unsigned __int128 cur = load_tag(s);
+        int claimed = 0;
+        if (cur == 0) {
+            cur = atomicCAS(&s->tag, (unsigned __int128)0, tag);
+            claimed = cur == 0;
+            if (claimed) cur = tag;
+        }
+        if (cur == tag) {
+            atomicAdd(&s->count, n);
+            atomicMax(&s->inv_first, ~(unsigned long long)first);
+            if (claimed) s->sample = sample;
+            return claimed;
         }
         slot = (slot + 1) & P.slot_mask;
     }
     atomicOr(P.status, 2);
+    return 0;
 }
 
 __global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
 {
     extern __shared__ unsigned int s_hist[];   // [n_samples][SCAR_N_COUNTERS + 2*SCAR_PHASE_BINS] when use_smem
     const int per_sample = SCAR_N_COUNTERS + 2 * SCAR_PHASE_BINS;
-    __shared__ unsigned int s_unassigned;
+    __shared__ unsigned int s_unassigned, s_new;
     if (P.use_smem) {
         for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) s_hist[i] = 0;
     }
-    if (threadIdx.x == 0) s_unassigned = 0;
+    if (threadIdx.x == 0) { s_unassigned = 0; s_new = 0; }
     __syncthreads();
     const uint32_t FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -160,10 +179,11 @@ __global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
                 const uint32_t rmin = __reduce_min_sync(agg, (uint32_t)(r & 0xFFFFFFFFll));
                 if (lane == leader) {
                     const uint64_t base = (uint64_t)r - (uint32_t)(r & 0xFFFFFFFFll);
-                    table_insert(P, h1, h2, (uint32_t)__popc(agg), P.first_index + base + rmin, rec.sample);
+                    if (table_insert(P, h1, h2, (uint32_t)__popc(agg), P.first_index + base + rmin, rec.sample))
+                        atomicAdd(&s_new, 1u);
                 }
             } else {
-                table_insert(P, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample);
+                if (table_insert(P, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample)) atomicAdd(&s_new, 1u);
             }
         }
     }
@@ -178,6 +198,7 @@ __global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
         }
     }
     if (threadIdx.x == 0 && s_unassigned) atomicAdd(P.unassigned, (unsigned long long)s_unassigned);
+    if (threadIdx.x == 0 && s_new) atomicAdd(P.n_entries, (unsigned long long)s_new);
 }
 
 // ---- verification: every SCAR read's full key equals the key of its slot's first read ------------
@@ -198,8 +219,8 @@ __global__ void __launch_bounds__(256) scar_verify_kernel(const K4VerifyParams P
         bool found = false;
         for (uint32_t probe = 0; probe <= P.max_probe; ++probe) {
             const ScarTableSlot s = P.slots[slot];
-            if (s.h1 == 0) break;
-            if (s.h1 == h1 && s.h2 == h2) {
+            if (s.tag == 0) break;
+            if (s.tag == make_tag(h1, h2)) {
                 found = true;
                 const uint64_t first = ~s.inv_first;
                 // the representative is compared only when it lies in this resident batch
@@ -235,10 +256,10 @@ __global__ void scar_export_kernel(const ScarTableSlot *slots, uint64_t capacity
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const ScarTableSlot s = slots[i];
-        if (s.h1 == 0) continue;
+        if (s.tag == 0) continue;
         const unsigned long long pos = atomicAdd(n_out, 1ull);
         if (pos < out_capacity) {
-            scar_entry e; e.h1 = s.h1; e.h2 = s.h2; e.first_idx = ~s.inv_first; e.count = s.count;
+            scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = (uint64_t)(s.tag >> 64); e.first_idx = ~s.inv_first; e.count = s.count;
             e.sample = (uint16_t)s.sample; e.pad = 0;
             out[pos] = e;
         }
@@ -250,7 +271,7 @@ __global__ void scar_merge_kernel(K4Params P, const scar_entry *in, uint64_t n_i
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const scar_entry e = in[i];
-        table_insert(P, e.h1, e.h2, e.count, e.first_idx, e.sample);
+        if (table_insert(P, e.h1, e.h2, e.count, e.first_idx, e.sample)) atomicAdd(P.n_entries, 1ull);
     }
 }
 
@@ -265,7 +286,7 @@ cudaError_t scar_launch_aggregate(K4Params P, int sm_count, cudaStream_t stream,
     cudaError_t e = cudaFuncSetAttribute(scar_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
     if (e != cudaSuccess) return e;
     int64_t blocks = (P.n_reads + threads - 1) / threads;
-    const int64_t cap = (int64_t)sm_count * 4;
+    const int64_t cap = (int64_t)sm_count * 6;
     if (blocks > cap) blocks = cap;
     scar_aggregate_kernel<<<(unsigned)blocks, threads, smem, stream>>>(P);
     if (launches) ++*launches;

@@ -67,7 +67,7 @@ template <> struct TableRef<true> {
     {
         uint2 v;
         // volatile: the 16 loads of a cell stay in program order, ahead of their consumers
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(base + bucket * 8u));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(bucket * 8u + base));
         return v;
     }
 };
@@ -78,22 +78,27 @@ template <> struct TableRef<false> {
     __device__ __forceinline__ uint2 load(uint32_t bucket) const { return __ldg(base + bucket); }
 };
 
-// The 16 windows of one cell: t[o] holds the window's 20 key bits in its TOP bits (raw << 12); the 16
-// table loads are issued back to back (16 independent shared-memory loads in flight per thread), then
-// m[o] = i (< 4095) on a hit and a value >= 4095 otherwise.
+// The 16 windows of one cell.  t[o] holds the window's 20 key bits in its TOP bits (raw << 12); the
+// bucket is the top log2(B) bits of t * mult, taken as mulhi(t * mult, B) (both on the FMA pipe); the
+// 16 table loads are issued back to back (16 independent shared-memory loads in flight per thread);
+// m[o] = i (< 4095) on a hit and a value >= 4095 otherwise.  Returns min(m): "any window of this cell
+// is in the table" costs one compare per cell, and the scan-order resolution runs only then.
 template <bool SMEM>
-__device__ __forceinline__ void probe16(const TableRef<SMEM> &tab, uint32_t wlo, uint32_t whi, uint32_t mult,
-                                        uint32_t shift, uint32_t (&m)[16])
+__device__ __forceinline__ uint32_t probe16(const TableRef<SMEM> &tab, uint32_t wlo, uint32_t whi, uint32_t mult,
+                                            uint32_t nbuckets, uint32_t (&m)[16])
 {
     uint32_t t[16];
     uint2 e[16];
 #pragma unroll
     for (int o = 0; o < 16; ++o) {
         t[o] = __funnelshift_r(wlo, whi, 2 * o) << 12;
-        e[o] = tab.load((t[o] * mult) >> shift);
+        e[o] = tab.load(__umulhi(t[o] * mult, nbuckets));
     }
 #pragma unroll
     for (int o = 0; o < 16; ++o) m[o] = min(e[o].x ^ t[o], e[o].y ^ t[o]);
+    const uint32_t a = min(min(m[0], m[1]), min(m[2], m[3])), b = min(min(m[4], m[5]), min(m[6], m[7]));
+    const uint32_t c = min(min(m[8], m[9]), min(m[10], m[11])), d = min(min(m[12], m[13]), min(m[14], m[15]));
+    return min(min(a, b), min(c, d));
 }
 
 // bit o set iff bases o .. o+9 of the 32-base window are all ACGT
@@ -126,70 +131,73 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
     const uint16_t *nmax = reinterpret_cast<const uint16_t *>(blob + P.nmax_off);
     const int64_t S = P.stride;      // reads per cell row
 
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads;
+    // Warps walk the batch in lock step (uniform trip count) and early exits are flags, not jumps, so
+    // that the lanes of a warp re-converge (__syncwarp) after each variable-length scan instead of
+    // running the rest of the body in separate passes.
+    const int64_t n_round = (P.n_reads + 31) & ~(int64_t)31;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_round;
          r += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t sample = P.samples[r];
+        bool live = r < P.n_reads;
         __align__(16) scar_record rec;
-        rec.status = SCAR_ST_UNASSIGNED; rec.flags = 0; rec.sample = (uint16_t)sample;
+        rec.status = SCAR_ST_UNASSIGNED; rec.flags = 0; rec.sample = SCAR_SAMPLE_NONE;
         rec.clj = rec.crj = rec.tlj = rec.trj = 0; rec.hr_n = 0;
         rec.phase_r1 = SCAR_PHASE_NA; rec.phase_r2 = SCAR_PHASE_NA;
-        if (sample >= (uint32_t)P.n_samples) {          // unidentified (INDEL_Processing.py:1194-1198)
-            rec.sample = SCAR_SAMPLE_NONE;
-            store_record(P.records + r, rec);
-            continue;
-        }
-        const int len = P.lens[r];
-        const int tid = __ldg(P.sample_target + sample);
+        const bool in_range = live;
+        const uint32_t sample = live ? (uint32_t)P.samples[r] : 0xFFFFu;
+        if (sample >= (uint32_t)P.n_samples) live = false;      // unidentified (INDEL_Processing.py:1194-1198)
+        else rec.sample = (uint16_t)sample;
+        const int len = live ? (int)P.lens[r] : 0;
+        const int tid = live ? __ldg(P.sample_target + sample) : 0;
         const ScarTargetMeta &T = metas[tid];
-        const uint64_t *col = P.cells + r;               // cell j of this read = col[j * S]
-        const int Wr = (len + 15) >> 4;                  // cells that hold bases
-
-        // ---- N count over the whole read
-        int n_count = 0;
-        for (int j = 0; j < Wr; ++j) n_count += __popc((uint32_t)(__ldg(col + j * S) >> 48));
-
-        // ---- phasing (INDEL_Processing.py:948-975): first k matching the prefix / the suffix
-        if (P.do_phasing && T.n_phase > 0) {
-            const uint64_t c0 = Wr > 0 ? __ldg(col) : 0ull;
-            int f1 = -1, f2 = -1;
-            for (int k = 0; k < T.n_phase; ++k) {
-                const ScarPhase ph = phases[T.phase_off + k];
-                if (ph.r1_len == 0) continue;            // empty R1 string: phase skipped (:954-957)
-                if (f2 < 0 && ph.r2_len != 0 && ph.r2_len <= 16 && len >= ph.r2_len) {
-                    const int p = len - ph.r2_len, j = p >> 4, o = p & 15;
-                    const uint64_t a = __ldg(col + j * S);
-                    const uint64_t b = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
-                    const uint32_t vwin = ((uint32_t)(a >> 32) & 0xFFFFu) | ((uint32_t)(b >> 32) << 16);
-                    const uint32_t vm = (1u << ph.r2_len) - 1u;
-                    const uint32_t cm = ph.r2_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r2_len)) - 1u);
-                    if ((((vwin >> o) & vm) == vm) &&
-                        ((__funnelshift_r((uint32_t)a, (uint32_t)b, 2 * o) & cm) == ph.r2_code)) f2 = k;
-                }
-                if (f1 < 0 && ph.r1_len <= 16 && len >= ph.r1_len) {
-                    const uint32_t vm = (1u << ph.r1_len) - 1u;
-                    const uint32_t cm = ph.r1_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r1_len)) - 1u);
-                    if (((((uint32_t)(c0 >> 32)) & vm) == vm) && (((uint32_t)c0 & cm) == ph.r1_code)) f1 = k;
-                }
-            }
-            rec.phase_r1 = (int8_t)(f1 < 0 ? SCAR_PHASE_NONE : f1);
-            rec.phase_r2 = (int8_t)(f2 < 0 ? SCAR_PHASE_NONE : f2);
-        }
-
-        // ---- read filters (INDEL_Processing.py:147-154).  nmax[len] is the largest N count with
-        // double(n)/double(len) <= N_Limit, tabulated on the host with the same IEEE division.
-        if (len == 0 || n_count > (int)nmax[len] || len <= P.min_length) {
-            rec.status = SCAR_ST_FILTERED;
-            store_record(P.records + r, rec);
-            continue;
-        }
-
+        const uint64_t *col = P.cells + (in_range ? r : 0);     // cell j of this read = col[j * S]
+        const int Wr = (len + 15) >> 4;                          // cells that hold bases
         const int cut = T.cutsite;
         int clj = 0, crj = 0, tlj = cut, trj = cut;
 
+        if (live) {
+            // ---- N count over the whole read
+            int n_count = 0;
+            for (int j = 0; j < Wr; ++j) n_count += __popc((uint32_t)(__ldg(col + j * S) >> 48));
+
+            // ---- phasing (INDEL_Processing.py:948-975): first k matching the prefix / the suffix
+            if (P.do_phasing && T.n_phase > 0) {
+                const uint64_t c0 = Wr > 0 ? __ldg(col) : 0ull;
+                int f1 = -1, f2 = -1;
+                for (int k = 0; k < T.n_phase; ++k) {
+                    const ScarPhase ph = phases[T.phase_off + k];
+                    if (ph.r1_len == 0) continue;            // empty R1 string: phase skipped (:954-957)
+                    if (f2 < 0 && ph.r2_len != 0 && ph.r2_len <= 16 && len >= ph.r2_len) {
+                        const int p = len - ph.r2_len, j = p >> 4, o = p & 15;
+                        const uint64_t a = __ldg(col + j * S);
+                        const uint64_t b = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
+                        const uint32_t vwin = ((uint32_t)(a >> 32) & 0xFFFFu) | ((uint32_t)(b >> 32) << 16);
+                        const uint32_t vm = (1u << ph.r2_len) - 1u;
+                        const uint32_t cm = ph.r2_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r2_len)) - 1u);
+                        if ((((vwin >> o) & vm) == vm) &&
+                            ((__funnelshift_r((uint32_t)a, (uint32_t)b, 2 * o) & cm) == ph.r2_code)) f2 = k;
+                    }
+                    if (f1 < 0 && ph.r1_len <= 16 && len >= ph.r1_len) {
+                        const uint32_t vm = (1u << ph.r1_len) - 1u;
+                        const uint32_t cm = ph.r1_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r1_len)) - 1u);
+                        if (((((uint32_t)(c0 >> 32)) & vm) == vm) && (((uint32_t)c0 & cm) == ph.r1_code)) f1 = k;
+                    }
+                }
+                rec.phase_r1 = (int8_t)(f1 < 0 ? SCAR_PHASE_NONE : f1);
+                rec.phase_r2 = (int8_t)(f2 < 0 ? SCAR_PHASE_NONE : f2);
+            }
+
+            // ---- read filters (INDEL_Processing.py:147-154).  nmax[len] is the largest N count with
+            // double(n)/double(len) <= N_Limit, tabulated on the host with the same IEEE division.
+            if (len == 0 || n_count > (int)nmax[len] || len <= P.min_length) {
+                rec.status = SCAR_ST_FILTERED;
+                live = false;
+            }
+        }
+
         // ---- left junction (SlidingWindow.pyx:49-69): p = len-20 .. 16, descending
-        {
+        if (live) {
             const TableRef<SMEM> ltab(blob, P.blob, T.left_off);
-            const uint32_t mult = T.left_mult, shift = T.left_shift;
+            const uint32_t mult = T.left_mult, nb = T.left_buckets;
             const int p0 = len - 20;
             if (p0 >= 16) {
                 int j = p0 >> 4;
@@ -198,23 +206,25 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
                 for (; j >= 1; --j) {
                     const uint64_t lo = __ldg(col + j * S);
                     const uint32_t wlo = (uint32_t)lo, whi = (uint32_t)hi;
-                    const uint32_t vwin = ((uint32_t)(lo >> 32) & 0xFFFFu) | ((uint32_t)(hi >> 32) << 16);
-                    const int pbase = 16 * j;
-                    // positions of this cell that are scanned (<= p0) and whose window is all ACGT
-                    const int top = p0 - pbase;                       // >= 0 here
-                    const uint32_t okmask = runs_of_ten(vwin) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
                     uint32_t m[16];
-                    probe16<SMEM>(ltab, wlo, whi, mult, shift, m);
+                    if (probe16<SMEM>(ltab, wlo, whi, mult, nb, m) < 4095u) {
+                        // some window of this cell is in the table: keep the first in scan order among
+                        // the positions that are scanned (<= p0) and whose window is all ACGT
+                        const uint32_t vwin = ((uint32_t)(lo >> 32) & 0xFFFFu) | ((uint32_t)(hi >> 32) << 16);
+                        const int pbase = 16 * j, top = p0 - pbase;       // top >= 0 here
+                        const uint32_t okmask = runs_of_ten(vwin) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
 #pragma unroll
-                    for (int o = 15; o >= 0; --o) {
-                        const uint32_t cand = ((uint32_t)(pbase + o) << 12) + m[o];
-                        if (m[o] < 4095u && ((okmask >> o) & 1u)) best = max(best, cand);
+                        for (int o = 15; o >= 0; --o) {
+                            const uint32_t cand = ((uint32_t)(pbase + o) << 12) + m[o];
+                            if (m[o] < 4095u && (okmask & (1u << o))) best = max(best, cand);
+                        }
+                        if (best) break;
                     }
-                    if (best) break;
                     hi = lo;
                 }
                 if (best) {
                     const int p = (int)(best >> 12), i = (int)(best & 0xFFFu);
+                    clj = p + 10; tlj = cut - i;
                     // SlidingWindow.pyx:56-60 (reachable only through the per-read drop-in)
                     if (T.cutwindow_key != 0xFFFFFFFFu) {
                         const int jj = p >> 4, o = p & 15;
@@ -223,19 +233,18 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
                         if ((__funnelshift_r((uint32_t)a, (uint32_t)b, 2 * o) & SCAR_KEY_MASK) == T.cutwindow_key) {
                             rec.status = SCAR_ST_NO_CUT; rec.flags = SCAR_FL_CUTWINDOW;
                             rec.tlj = rec.trj = (uint16_t)cut;
-                            store_record(P.records + r, rec);
-                            continue;
+                            live = false;
                         }
                     }
-                    clj = p + 10; tlj = cut - i;
                 }
             }
         }
+        __syncwarp();
 
         // ---- right junction (SlidingWindow.pyx:79-93): p = 10 .. len-26, ascending
-        {
+        if (live) {
             const TableRef<SMEM> rtab(blob, P.blob, T.right_off);
-            const uint32_t mult = T.right_mult, shift = T.right_shift;
+            const uint32_t mult = T.right_mult, nb = T.right_buckets;
             const int plast = len - 26;
             if (plast >= 10) {
                 uint64_t lo = __ldg(col);
@@ -243,35 +252,36 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
                 for (int j = 0; 16 * j <= plast; ++j) {
                     const uint64_t hi = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
                     const uint32_t wlo = (uint32_t)lo, whi = (uint32_t)hi;
-                    const uint32_t vwin = ((uint32_t)(lo >> 32) & 0xFFFFu) | ((uint32_t)(hi >> 32) << 16);
-                    const int pbase = 16 * j;
-                    const int top = plast - pbase;                    // >= 0 here
-                    uint32_t okmask = runs_of_ten(vwin) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
-                    if (j == 0) okmask &= 0xFC00u;                    // p >= 10
                     uint32_t m[16];
-                    probe16<SMEM>(rtab, wlo, whi, mult, shift, m);
+                    if (probe16<SMEM>(rtab, wlo, whi, mult, nb, m) < 4095u) {
+                        const uint32_t vwin = ((uint32_t)(lo >> 32) & 0xFFFFu) | ((uint32_t)(hi >> 32) << 16);
+                        const int pbase = 16 * j, top = plast - pbase;    // top >= 0 here
+                        uint32_t okmask = runs_of_ten(vwin) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
+                        if (j == 0) okmask &= 0xFC00u;                    // p >= 10
 #pragma unroll
-                    for (int o = 0; o < 16; ++o) {
-                        const uint32_t cand = ((uint32_t)(pbase + o) << 12) + m[o];
-                        if (m[o] < 4095u && ((okmask >> o) & 1u)) best = min(best, cand);
+                        for (int o = 0; o < 16; ++o) {
+                            const uint32_t cand = ((uint32_t)(pbase + o) << 12) + m[o];
+                            if (m[o] < 4095u && (okmask & (1u << o))) best = min(best, cand);
+                        }
+                        if (best != 0xFFFFFFFFu) break;
                     }
-                    if (best != 0xFFFFFFFFu) break;
                     lo = hi;
                 }
                 if (best != 0xFFFFFFFFu) { crj = (int)(best >> 12); trj = cut + (int)(best & 0xFFFu); }
             }
         }
+        __syncwarp();
 
-        rec.clj = (uint16_t)clj; rec.crj = (uint16_t)crj; rec.tlj = (uint16_t)tlj; rec.trj = (uint16_t)trj;
-
-        if (clj < 1 && crj < 1) {                            // :96-98
-            rec.status = SCAR_ST_NO_JUNCTION;
-            store_record(P.records + r, rec);
-            continue;
+        if (live) {
+            rec.clj = (uint16_t)clj; rec.crj = (uint16_t)crj; rec.tlj = (uint16_t)tlj; rec.trj = (uint16_t)trj;
+            if (clj < 1 && crj < 1) {                            // :96-98
+                rec.status = SCAR_ST_NO_JUNCTION;
+                live = false;
+            }
         }
 
         // ---- HR donor scan (:102-117): occurrences at p = 25 .. len-26-h
-        if (HR) {
+        if (HR && live) {
             const int h = P.hr_len;
             const int plast = len - 26 - h;
             const uint64_t cm = h == 32 ? ~0ull : ((1ull << (2 * h)) - 1ull);
@@ -298,27 +308,26 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
         }
 
         // ---- junction call (:134-171)
-        bool cut_found = false;
-        if (0 < clj && clj < crj) {
-            // literal 'N' anywhere in read[clj:crj] drops the read with no counter (:140-141)
-            bool has_n = false;
-            for (int j = clj >> 4; 16 * j < crj; ++j) {
-                const int lo = max(clj, 16 * j) - 16 * j, hi = min(crj, 16 * j + 16) - 16 * j;
-                const uint32_t m = ((1u << (hi - lo)) - 1u) << lo;
-                has_n |= (((uint32_t)(__ldg(col + j * S) >> 48)) & m) != 0;
+        if (live) {
+            bool cut_found = false, has_n = false;
+            if (0 < clj && clj < crj) {
+                // literal 'N' anywhere in read[clj:crj] drops the read with no counter (:140-141)
+                for (int j = clj >> 4; 16 * j < crj; ++j) {
+                    const int lo = max(clj, 16 * j) - 16 * j, hi = min(crj, 16 * j + 16) - 16 * j;
+                    const uint32_t m = ((1u << (hi - lo)) - 1u) << lo;
+                    has_n |= (((uint32_t)(__ldg(col + j * S) >> 48)) & m) != 0;
+                }
+                if (!has_n) { cut_found = true; rec.flags |= SCAR_FL_INSERTION; }
             }
-            if (has_n) {
-                rec.status = SCAR_ST_N_INSERTION;
-                store_record(P.records + r, rec);
-                continue;
+            if (has_n) rec.status = SCAR_ST_N_INSERTION;
+            else {
+                if (tlj < cut) { cut_found = true; rec.flags |= SCAR_FL_LEFT_DEL; }
+                if (trj > cut) { cut_found = true; rec.flags |= SCAR_FL_RIGHT_DEL; }
+                if (clj > crj && crj > 0) { cut_found = true; rec.flags |= SCAR_FL_MICROHOM; }
+                rec.status = cut_found ? SCAR_ST_SCAR : SCAR_ST_NO_CUT;
             }
-            cut_found = true; rec.flags |= SCAR_FL_INSERTION;
         }
-        if (tlj < cut) { cut_found = true; rec.flags |= SCAR_FL_LEFT_DEL; }
-        if (trj > cut) { cut_found = true; rec.flags |= SCAR_FL_RIGHT_DEL; }
-        if (clj > crj && crj > 0) { cut_found = true; rec.flags |= SCAR_FL_MICROHOM; }
-        rec.status = cut_found ? SCAR_ST_SCAR : SCAR_ST_NO_CUT;
-        store_record(P.records + r, rec);
+        if (in_range) store_record(P.records + r, rec);
     }
 }
 
