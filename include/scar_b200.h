@@ -41,9 +41,12 @@ enum {
 
 enum { SCAR_PLATFORM_ILLUMINA = 0, SCAR_PLATFORM_TRUSEQ = 1, SCAR_PLATFORM_RAMSDEN = 2 };
 
-/* A list of byte strings.  Either CSR (offsets != NULL, item i = bytes[offsets[i] .. offsets[i+1]))
- * or fixed stride (offsets == NULL, item i starts at i*stride and is lengths[i] long, or `stride`
- * long when lengths == NULL). */
+/* A list of byte strings, three layouts:
+ *   CSR     offsets != NULL, lengths == NULL: item i = bytes[offsets[i] .. offsets[i+1])  (n+1 offsets)
+ *   views   offsets != NULL, lengths != NULL: item i = bytes[offsets[i] .. offsets[i]+lengths[i]), offsets
+ *           non-decreasing (fields inside a FASTQ text buffer, see scar_fastq_index)
+ *   stride  offsets == NULL: item i starts at i*stride and is lengths[i] long, or `stride` long when
+ *           lengths == NULL. */
 typedef struct scar_ragged {
     const uint8_t *bytes;
     const int64_t *offsets;
@@ -154,6 +157,15 @@ int scar_table_merge_dev(scar_ctx *ctx, const scar_entry *entries, int64_t n_ent
 int64_t scar_accumulator_words(const scar_ctx *ctx);
 int scar_accumulators_export_dev(scar_ctx *ctx, int64_t *out, void *stream);
 int scar_accumulators_import_dev(scar_ctx *ctx, const int64_t *in, void *stream);
+
+/* FASTQ_Reader.seq_read + the header split of index_matching over a text buffer (host only): emits
+ * (offset, length) views into `text` for the sequence and, when want_index_fields, for
+ * name.split(":")[-1].split("+")[0] and [1].  Parses whole records only; *consumed is where the next
+ * call must resume (is_final accepts a last record without a newline).  Returns SCAR_ERR_INVALID where
+ * the reference raises (sequence / quality length mismatch, header without '+'). */
+int scar_fastq_index(const uint8_t *text, int64_t n_bytes, int32_t is_final, int32_t want_index_fields,
+                     int64_t capacity, int64_t *seq_off, int32_t *seq_len, int64_t *f0_off, int32_t *f0_len,
+                     int64_t *f1_off, int32_t *f1_len, int64_t *n_records, int64_t *consumed);
 
 /* Sequence_Magic.match_maker over a batch on the device (host buffers): out[i] = lev(q_i,u_i) - (|u_i|-|q_i|). */
 int scar_match_maker_batch(int32_t device, const scar_ragged *query, const scar_ragged *unknown,

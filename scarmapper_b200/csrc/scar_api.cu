@@ -20,6 +20,11 @@ static int fail(int code, const char *fmt, ...)
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return code;
 }
+int scar_fail(int code, const char *fmt, ...)      // for the other translation units
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -631,38 +636,48 @@ template <typename T> static int ensure(T **p, size_t *cap, size_t need)
 struct Span { int64_t byte0, byte1; };   // host byte range of items [a, b)
 static Span span_of(const scar_ragged &R, int64_t a, int64_t b)
 {
+    if (b <= a) return {0, 0};
+    if (R.offsets && R.lengths) return {R.offsets[a], R.offsets[b - 1] + R.lengths[b - 1]};   // views, monotone offsets
     if (R.offsets) return {R.offsets[a], R.offsets[b]};
     return {a * R.stride, b * R.stride};
 }
 
+// copy the index arrays of items [a,b) to the device and point the descriptor at device bytes that hold
+// host bytes [byte0, ...) at dbytes
+static int stage_index(const scar_ragged &H, int64_t a, int64_t b, const uint8_t *dbytes, int64_t byte0,
+                       int64_t *doff, int32_t *dlen, cudaStream_t s, scar_ragged *D, int64_t *h2d)
+{
+    memset(D, 0, sizeof(*D));
+    D->stride = H.stride;
+    if (H.offsets) {
+        const size_t n_off = (size_t)(b - a) + (H.lengths ? 0 : 1);
+        CU(cudaMemcpyAsync(doff, H.offsets + a, n_off * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        *h2d += (int64_t)(n_off * sizeof(int64_t));
+        D->offsets = doff;
+        D->bytes = dbytes - byte0;           // original offsets stay valid
+    } else {
+        D->bytes = dbytes;
+    }
+    if (H.lengths) {
+        CU(cudaMemcpyAsync(dlen, H.lengths + a, (size_t)(b - a) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        *h2d += (int64_t)((b - a) * sizeof(int32_t));
+        D->lengths = dlen;
+    }
+    return SCAR_OK;
+}
+
 // copy items [a,b) of a host ragged list to the device; returns the device-side descriptor
 static int stage_ragged(const scar_ragged &H, int64_t a, int64_t b, uint8_t **dbytes, size_t *dcap,
-                        int64_t **doff, int32_t **dlen, int64_t reads_cap_changed, cudaStream_t s, scar_ragged *D,
+                        int64_t **doff, int32_t **dlen, int64_t, cudaStream_t s, scar_ragged *D,
                         int64_t *h2d)
 {
-    (void)reads_cap_changed;
     const Span sp = span_of(H, a, b);
     const size_t nbytes = (size_t)(sp.byte1 - sp.byte0);
     int rc = ensure(dbytes, dcap, nbytes + 16);
     if (rc) return rc;
     if (nbytes) CU(cudaMemcpyAsync(*dbytes, H.bytes + sp.byte0, nbytes, cudaMemcpyHostToDevice, s));
     *h2d += (int64_t)nbytes;
-    memset(D, 0, sizeof(*D));
-    D->stride = H.stride;
-    if (H.offsets) {
-        CU(cudaMemcpyAsync(*doff, H.offsets + a, (size_t)(b - a + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-        *h2d += (int64_t)((b - a + 1) * sizeof(int64_t));
-        D->offsets = *doff;
-        D->bytes = *dbytes - sp.byte0;       // original offsets stay valid
-    } else {
-        D->bytes = *dbytes;
-        if (H.lengths) {
-            CU(cudaMemcpyAsync(*dlen, H.lengths + a, (size_t)(b - a) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-            *h2d += (int64_t)((b - a) * sizeof(int32_t));
-            D->lengths = *dlen;
-        }
-    }
-    return SCAR_OK;
+    return stage_index(H, a, b, *dbytes, H.offsets ? sp.byte0 : 0, *doff, *dlen, s, D, h2d);
 }
 
 static int ensure_hostbuf(scar_ctx *c, HostBuf &b, int64_t reads)
@@ -703,13 +718,27 @@ extern "C" int scar_process_host(scar_ctx *c, const scar_ragged *seq, const scar
         if (rc) return rc;
         if (k >= NBUF) CU(cudaEventSynchronize(B.done));     // buffer reuse: its previous chunk has drained
         scar_ragged dseq, df0, df1;
-        if ((rc = stage_ragged(*seq, a, b, &B.seq, &B.seq_cap, &B.seq_off, &B.seq_len, 0, B.stream, &dseq, &h2d))) return rc;
-        if (c->platform == SCAR_PLATFORM_ILLUMINA) {
-            if ((rc = stage_ragged(*f0, a, b, &B.f0, &B.f0_cap, &B.f0_off, &B.f0_len, 0, B.stream, &df0, &h2d))) return rc;
-            if ((rc = stage_ragged(*f1, a, b, &B.f1, &B.f1_cap, &B.f1_off, &B.f1_len, 0, B.stream, &df1, &h2d))) return rc;
+        const bool illumina = c->platform == SCAR_PLATFORM_ILLUMINA;
+        const bool shared = illumina && seq->offsets && f0->offsets && f1->offsets && f0->bytes == seq->bytes &&
+                            f1->bytes == seq->bytes;
+        if (shared) {
+            // the three lists are views into ONE text buffer (FASTQ text): copy its span once
+            const Span s0 = span_of(*seq, a, b), s1 = span_of(*f0, a, b), s2 = span_of(*f1, a, b);
+            const int64_t lo = std::min(s0.byte0, std::min(s1.byte0, s2.byte0));
+            const int64_t hi = std::max(s0.byte1, std::max(s1.byte1, s2.byte1));
+            if ((rc = ensure(&B.seq, &B.seq_cap, (size_t)(hi - lo) + 16))) return rc;
+            if (hi > lo) CU(cudaMemcpyAsync(B.seq, seq->bytes + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, B.stream));
+            h2d += hi - lo;
+            if ((rc = stage_index(*seq, a, b, B.seq, lo, B.seq_off, B.seq_len, B.stream, &dseq, &h2d))) return rc;
+            if ((rc = stage_index(*f0, a, b, B.seq, lo, B.f0_off, B.f0_len, B.stream, &df0, &h2d))) return rc;
+            if ((rc = stage_index(*f1, a, b, B.seq, lo, B.f1_off, B.f1_len, B.stream, &df1, &h2d))) return rc;
+        } else {
+            if ((rc = stage_ragged(*seq, a, b, &B.seq, &B.seq_cap, &B.seq_off, &B.seq_len, 0, B.stream, &dseq, &h2d))) return rc;
+            if (illumina) {
+                if ((rc = stage_ragged(*f0, a, b, &B.f0, &B.f0_cap, &B.f0_off, &B.f0_len, 0, B.stream, &df0, &h2d))) return rc;
+                if ((rc = stage_ragged(*f1, a, b, &B.f1, &B.f1_cap, &B.f1_off, &B.f1_len, 0, B.stream, &df1, &h2d))) return rc;
+            }
         }
-        // device descriptors index items from 0 of the chunk
-        if (dseq.offsets) dseq.offsets = B.seq_off;
         if ((rc = scar_run_dev(c, &dseq, c->platform == SCAR_PLATFORM_ILLUMINA ? &df0 : nullptr,
                                c->platform == SCAR_PLATFORM_ILLUMINA ? &df1 : nullptr, b - a, first_index + (uint64_t)a,
                                B.cells, B.lens, B.samples, B.records, B.stream))) return rc;
@@ -731,7 +760,7 @@ extern "C" int scar_match_maker_batch(int32_t device, const scar_ragged *query, 
     if (device < 0 || device >= ndev) return fail(SCAR_ERR_CUDA, "CUDA device %d not present", device);
     CU(cudaSetDevice(device));
     for (int64_t i = 0; i < n; ++i) {
-        const int64_t m = query->offsets ? query->offsets[i + 1] - query->offsets[i] : (query->lengths ? query->lengths[i] : query->stride);
+        const int64_t m = query->lengths ? query->lengths[i] : (query->offsets ? query->offsets[i + 1] - query->offsets[i] : query->stride);
         if (m > 64) return fail(SCAR_ERR_UNSUPPORTED, "query %lld longer than 64", (long long)i);
     }
     uint8_t *dq = nullptr, *du = nullptr; int64_t *dqo = nullptr, *duo = nullptr; int32_t *dql = nullptr, *dul = nullptr, *dout = nullptr;

@@ -47,10 +47,15 @@ SCAR_HD int myers_global(const uint64_t *peq, int m, const uint8_t *text, int n,
     return score;
 }
 
+// item r of a ragged list: CSR (offsets only), views (offsets + lengths: item r starts at offsets[r] and is
+// lengths[r] long, e.g. fields inside a FASTQ text buffer), or fixed stride
 SCAR_HD void get_item(const scar_ragged &R, int64_t r, const uint8_t *&p, int &len)
 {
-    if (R.offsets) { const int64_t s = R.offsets[r]; p = R.bytes + s; len = (int)(R.offsets[r + 1] - s); }
-    else { p = R.bytes + r * R.stride; len = R.lengths ? R.lengths[r] : (int)R.stride; }
+    if (R.offsets) {
+        const int64_t s = R.offsets[r];
+        p = R.bytes + s;
+        len = R.lengths ? R.lengths[r] : (int)(R.offsets[r + 1] - s);
+    } else { p = R.bytes + r * R.stride; len = R.lengths ? R.lengths[r] : (int)R.stride; }
 }
 
 SCAR_HD void class_codes(const uint8_t *u, int n, const uint8_t *class_map, uint64_t code[2])

@@ -20,9 +20,9 @@ __global__ void __launch_bounds__(256) scar_pack_kernel(const K1Params P)
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t r = tile * blockDim.x + threadIdx.x;
         if (r >= P.n_reads) continue;
-        int64_t start; int len;
-        if (P.seq.offsets) { start = P.seq.offsets[r]; len = (int)(P.seq.offsets[r + 1] - start); }
-        else { start = r * P.seq.stride; len = P.seq.lengths ? P.seq.lengths[r] : (int)P.seq.stride; }
+        const uint8_t *rp; int len;
+        get_item(P.seq, r, rp, len);
+        const int64_t start = rp - P.seq.bytes;
         int slen = len, shift = 0;
         if (P.platform == SCAR_PLATFORM_TRUSEQ) { slen = len > 12 ? len - 12 : 0; shift = 6; }
         if (slen > 16 * P.W) { atomicOr(P.status, 1); slen = 16 * P.W; }

@@ -165,8 +165,7 @@ __global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
         const uint32_t active = __ballot_sync(FULL, scar);
         if (scar) {
             const uint8_t *raw; int rawlen;
-            if (P.seq.offsets) { const int64_t st = P.seq.offsets[r]; raw = P.seq.bytes + st; rawlen = (int)(P.seq.offsets[r + 1] - st); }
-            else { raw = P.seq.bytes + r * P.seq.stride; rawlen = P.seq.lengths ? P.seq.lengths[r] : (int)P.seq.stride; }
+            get_item(P.seq, r, raw, rawlen);
             uint64_t h1, h2;
             key_hashes(rec, raw, rawlen, P.platform, h1, h2);
             // combine the lanes of this warp that carry the same key
@@ -211,8 +210,7 @@ __global__ void __launch_bounds__(256) scar_verify_kernel(const K4VerifyParams P
         *reinterpret_cast<uint4 *>(&rec) = __ldg(reinterpret_cast<const uint4 *>(P.records + r));
         if (rec.status != SCAR_ST_SCAR) continue;
         const uint8_t *raw; int rawlen;
-        if (P.seq.offsets) { const int64_t st = P.seq.offsets[r]; raw = P.seq.bytes + st; rawlen = (int)(P.seq.offsets[r + 1] - st); }
-        else { raw = P.seq.bytes + r * P.seq.stride; rawlen = P.seq.lengths ? P.seq.lengths[r] : (int)P.seq.stride; }
+        get_item(P.seq, r, raw, rawlen);
         uint64_t h1, h2;
         key_hashes(rec, raw, rawlen, P.platform, h1, h2);
         uint64_t slot = h1 & P.slot_mask;
@@ -229,8 +227,7 @@ __global__ void __launch_bounds__(256) scar_verify_kernel(const K4VerifyParams P
                     __align__(16) scar_record rr;
                     *reinterpret_cast<uint4 *>(&rr) = __ldg(reinterpret_cast<const uint4 *>(P.records + q));
                     const uint8_t *raw2; int rawlen2;
-                    if (P.seq.offsets) { const int64_t st = P.seq.offsets[q]; raw2 = P.seq.bytes + st; rawlen2 = (int)(P.seq.offsets[q + 1] - st); }
-                    else { raw2 = P.seq.bytes + q * P.seq.stride; rawlen2 = P.seq.lengths ? P.seq.lengths[q] : (int)P.seq.stride; }
+                    get_item(P.seq, q, raw2, rawlen2);
                     bool eq = rr.status == SCAR_ST_SCAR && rr.sample == rec.sample && rr.tlj == rec.tlj && rr.trj == rec.trj &&
                               ((rr.flags ^ rec.flags) & (SCAR_FL_INSERTION | SCAR_FL_MICROHOM | SCAR_FL_HR)) == 0;
                     int lo = 0, hi = 0, lo2 = 0, hi2 = 0;

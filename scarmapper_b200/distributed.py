@@ -53,8 +53,9 @@ def merge_tables(export_fn, merge_fn, entry_buf: torch.Tensor, group=None):
         raise RuntimeError("entry buffer too small: {} < {}".format(entry_buf.shape[0], n_max))
     if world == 1 or n_max == 0:
         return counts_h
-    gathered = torch.empty((world, n_max, entry_buf.shape[1]), dtype=entry_buf.dtype, device=entry_buf.device)
-    dist.all_gather_into_tensor(gathered, entry_buf[:n_max].contiguous(), group=group)
+    flat = torch.empty((world * n_max, entry_buf.shape[1]), dtype=entry_buf.dtype, device=entry_buf.device)
+    dist.all_gather_into_tensor(flat, entry_buf[:n_max].contiguous(), group=group)
+    gathered = flat.view(world, n_max, entry_buf.shape[1])
     for g in range(world):
         if g != rank and counts_h[g]:
             merge_fn(gathered[g], counts_h[g])

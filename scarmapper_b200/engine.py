@@ -43,8 +43,12 @@ class HostRagged:
         self.offsets = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
         self.lengths = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int32)
         self.stride = int(stride)
-        self.n = int(n if n is not None else (len(self.offsets) - 1 if self.offsets is not None else
-                                              self.bytes.size // max(self.stride, 1)))
+        if n is None:
+            if self.offsets is not None:
+                n = len(self.lengths) if self.lengths is not None else len(self.offsets) - 1
+            else:
+                n = self.bytes.size // max(self.stride, 1)
+        self.n = int(n)
 
     @classmethod
     def from_strings(cls, strings):
@@ -56,12 +60,26 @@ class HostRagged:
         mat = np.ascontiguousarray(mat, dtype=np.uint8)
         return cls(mat.reshape(-1), lengths=lengths, stride=mat.shape[1], n=mat.shape[0])
 
+    @classmethod
+    def from_views(cls, text, offsets, lengths):
+        """Items are (offset, length) views into one text buffer (scar_ragged views mode)."""
+        return cls(text, offsets=offsets, lengths=lengths, n=len(lengths))
+
     def max_len(self) -> int:
-        if self.offsets is not None:
-            return int(np.max(np.diff(self.offsets))) if self.n else 0
         if self.lengths is not None:
             return int(self.lengths.max()) if self.n else 0
+        if self.offsets is not None:
+            return int(np.max(np.diff(self.offsets))) if self.n else 0
         return self.stride
+
+    def item(self, i: int) -> bytes:
+        if self.offsets is not None:
+            a = int(self.offsets[i])
+            b = a + int(self.lengths[i]) if self.lengths is not None else int(self.offsets[i + 1])
+        else:
+            a = i * self.stride
+            b = a + (int(self.lengths[i]) if self.lengths is not None else self.stride)
+        return self.bytes[a:b].tobytes()
 
     def c_struct(self) -> N.Ragged:
         return N.Ragged(self.bytes.ctypes.data,

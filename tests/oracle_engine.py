@@ -1,0 +1,48 @@
+"""
+Test double with ScarEngine's result interface, computed by the CPU oracle.  Lets the drop-in glue
+(scarmapper_b200/dropin.py: unpacking GPU results into the reference's objects and files) be tested in
+the build container, where the reference is present but no GPU is.  Lives in tests/ only.
+"""
+import numpy as np
+
+from oracle import scar_oracle as orc
+
+
+class OracleEngine:
+    def __init__(self, prob, device=0):
+        self.prob = prob
+        self.o = orc.Problem(targets=prob.targets, cutsites=prob.cutsites, sample_target=prob.sample_target,
+                             left_index=prob.left_index, right_index=prob.right_index, platform=prob.platform,
+                             phasing=prob.phasing, hr_donor=prob.hr_donor, n_limit=prob.n_limit,
+                             min_length=prob.min_length)
+        self.records = None
+        self.reads = None
+
+    def process_host(self, seq, f0=None, f1=None, first_index=0, want_records=True, out=None):
+        reads = [seq.item(i).decode("latin-1") for i in range(seq.n)]
+        a = [f0.item(i).decode("latin-1") for i in range(f0.n)] if f0 is not None else None
+        b = [f1.item(i).decode("latin-1") for i in range(f1.n)] if f1 is not None else None
+        self.reads = reads
+        self.records = orc.classify_batch(self.o, reads, a, b)
+        return self.records
+
+    def counters(self):
+        return orc.counters(self.o, self.records), int((self.records["status"] == orc.ST_UNASSIGNED).sum())
+
+    def phase_hist(self):
+        h = np.zeros((self.o.n_samples, 2, 34), dtype=np.int64)
+        ok = self.records["status"] != orc.ST_UNASSIGNED
+        for side, col in enumerate(("phase_r1", "phase_r2")):
+            v = self.records[col].astype(np.int64)
+            bins = np.where(v == -2, 33, v + 1)
+            np.add.at(h[:, side, :], (self.records["sample"][ok].astype(np.int64), bins[ok]), 1)
+        return h
+
+    def table(self):
+        from scarmapper_b200._native import ENTRY_DTYPE
+        tabs = orc.aggregate(self.o, self.records, self.reads)
+        rows = [(0, 0, v[1], v[0], s, 0) for s, d in enumerate(tabs) for v in d.values()]
+        return np.array(rows, dtype=ENTRY_DTYPE) if rows else np.zeros(0, dtype=ENTRY_DTYPE)
+
+    def close(self):
+        pass

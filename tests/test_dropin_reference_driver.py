@@ -1,0 +1,73 @@
+"""
+The drop-in glue end to end, in the build container: the UNMODIFIED reference driver
+(DataProcessing.main_loop, frequency_output, raw_data_output, data_output) runs with
+scarmapper_b200.dropin installed, and the files it writes must equal the golden files the reference
+wrote on its own (tests/golden/*.json.gz "files": Frequency and Summary outputs minus wall-clock lines).
+The engine is the oracle-backed test double (no GPU here); tests/test_gpu_parity.py proves
+engine == oracle on the GPU box, so the two together cover FASTQ -> files.
+Skipped where /root/reference is absent.
+"""
+import argparse
+import os
+import shutil
+import sys
+import tempfile
+
+import pytest
+
+import golden_util as gu
+from oracle import ref_shims
+
+pytestmark = pytest.mark.skipif(not ref_shims.available(), reason="reference tree not present")
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+
+
+@pytest.mark.parametrize("name", ["c1_single_target", "c3_12_targets_mh", "ragged_hr_donor", "truseq", "ramsden"])
+def test_reference_driver_with_dropin_writes_identical_files(name):
+    import make_golden
+    from oracle_engine import OracleEngine
+    blob = gu.load(name)
+    case, golden = blob["case"], blob["golden"]
+    ref_shims.install()
+    from scarmapper import INDEL_Processing, TargetMapper
+    from Valkyries import Tool_Box
+    from scarmapper_b200 import dropin
+
+    saved = (INDEL_Processing.DataProcessing.consensus_demultiplex, INDEL_Processing.ScarSearch.data_processing)
+    wd = tempfile.mkdtemp(prefix="scar_dropin_") + os.sep
+    try:
+        make_golden.write_inputs(wd, case)
+        args = argparse.Namespace(
+            WorkingFolder=wd, Job_Name="golden", Verbose="ERROR", Platform=case["platform"], PEAR=True,
+            Demultiplex=False, HR_Donor=case["hr_donor"], N_Limit=case["n_limit"],
+            Minimum_Length=case["min_length"], OutputRawData=True, PatternThreshold=0.0001,
+            RefSeq=wd + "refseq.fa", TargetFile=wd + "targets.tsv", SampleManifest=wd + "manifest.tsv",
+            Master_Index_File=wd + "master_index.tsv", Spawn=1, FASTQ1=wd + "reads.fastq.gz", FASTQ2=None,
+            Search_KMER=10, FigureType="pdf", IndelProcessing=True)
+        log = Tool_Box.Logger(args)
+        dropin._ENGINE_FACTORY[0] = OracleEngine
+        dropin.install(INDEL_Processing)
+
+        class _Fastq:
+            input_file = args.FASTQ1
+
+        manifest = Tool_Box.FileParser.indices(log, args.SampleManifest)
+        dp = INDEL_Processing.DataProcessing(log, args, "run-start", "golden",
+                                             TargetMapper.TargetMapper(log, args, manifest), _Fastq(), None)
+        dp.main_loop()
+        assert dp.read_count == golden["read_count"]
+        assert dict(dp.read_count_dict) == golden["read_count_dict"]
+        assert {k: dict(v) for k, v in dp.phase_count.items()} == golden["phase_count"]
+        seen = 0
+        for fn, want in golden["files"].items():
+            got = open(os.path.join(wd, fn)).read().split("\n")
+            got = "\n".join(ln for ln in got if not ln.startswith(("# Run Start", "# Run End", "Start:", "End:",
+                                                                   "FASTQ1:", "FASTQ2:")))
+            assert got == want, fn
+            seen += 1
+        assert seen == len(golden["files"]) and seen >= 2
+    finally:
+        dropin._ENGINE_FACTORY[0] = None
+        INDEL_Processing.DataProcessing.consensus_demultiplex, INDEL_Processing.ScarSearch.data_processing = saved
+        shutil.rmtree(wd, ignore_errors=True)

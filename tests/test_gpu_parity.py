@@ -329,3 +329,74 @@ def test_full_size_properties_config1():
     want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
     assert_records_equal(rec[sel], want, reads)
     eng.close()
+
+
+def test_per_read_dropin_matches_compiled_reference(ref_sliding_window):
+    """scarmapper_b200.SlidingWindow.sliding_window (same signature as the Cython module) against the
+    reference's own compiled SlidingWindow.pyx: return value and summary_data mutation."""
+    import random
+    from scarmapper_b200 import SlidingWindow as mine
+    import test_oracle_vs_reference as tov
+    rng = random.Random(21)
+    targets = []
+    for _ in range(6):
+        L = rng.choice([120, 235, 251, 472])
+        t = tov.rand_seq(rng, L, "ACGT")
+        targets.append((t, rng.randint(L // 3, 2 * L // 3)))
+    n_scar = 0
+    for k in range(600):
+        target, cut = targets[k % len(targets)]
+        rl = rng.choice([20, 35, 36, 37, 60, 100, 150, 150, 151, 200])
+        dl, dr = rng.choice([0, 0, 1, 5, 20]), rng.choice([0, 0, 2, 7, 30])
+        ins = tov.rand_seq(rng, rng.choice([0, 0, 1, 3, 12]), rng.choice(["ACGT", "ACGTN", "acgt"]))
+        a = rl // 2 - rng.randint(0, 5)
+        lo = max(0, cut - dl - a)
+        read = (target[lo:max(lo, cut - dl)] + ins + target[min(len(target), cut + dr):])[:rl]
+        read += tov.rand_seq(rng, rl - len(read), "ACGT")
+        hr = read[40:52] if (k % 5 == 0 and len(read) > 100 and set(read[40:52]) <= set("ACGT")) else ""
+        left, right = orc.window_mapping(target, cut)
+        cw = target[cut - 4:cut + 4]
+        s_ref, s_mine = tov.fresh_summary(), tov.fresh_summary()
+        want, s1 = ref_sliding_window.sliding_window(read, target, cut, len(target), 15, len(target) - 15, s_ref,
+                                                     left, right, cw, hr)
+        got, s2 = mine.sliding_window(read, target, cut, len(target), 15, len(target) - 15, s_mine, left, right, cw, hr)
+        assert got == want, (read, target, cut, hr)
+        assert s2 is s_mine and s_mine == s_ref
+        n_scar += bool(want)
+    assert n_scar > 100
+
+
+def test_sequence_magic_dropin():
+    from scarmapper_b200 import Sequence_Magic as sm
+    assert sm.match_maker("ATTACTCG", "ATTACTCGA") == orc.match_maker("ATTACTCG", "ATTACTCGA") == 0
+    assert sm.match_maker("ATTACTCG", "TTACTCG") == orc.match_maker("ATTACTCG", "TTACTCG")
+    assert sm.rcomp("ACGTNacgtRYX.") == orc.rcomp("ACGTNacgtRYX.")
+
+
+def test_fastq_text_views_path_matches_oracle():
+    """FASTQ text -> scar_fastq_index views -> one shared H2D copy -> whole path, vs the oracle on the
+    parsed strings (CRLF line ends, a record without a final newline, odd headers)."""
+    from scarmapper_b200 import fastq
+    cfg = synth.make_config("C3", n_reads=20000, seed=31, min_len=60, p_n=0.02)
+    batch = cfg.generate(0, 20000)
+    reads = cfg.reads_as_strings(batch)
+    f0, f1 = cfg.fields_as_strings(batch)
+    eol = ["\n", "\r\n"]
+    parts = []
+    for i, (r, a, b) in enumerate(zip(reads, f0, f1)):
+        e = eol[i % 2]
+        parts.append("@SYN:1:FC:1:{}:{}:{} 1:N:0:{}+{}{}{}{}+{}{}{}".format(i % 97, i, i * 7 % 1013, a, b, e, r, e, e,
+                                                                             "I" * len(r), e))
+    text = "".join(parts).rstrip("\r\n")          # last record without a newline
+    fb = fastq.index_text(np.frombuffer(text.encode(), dtype=np.uint8))
+    assert fb.n == len(reads)
+    assert [fb.read(i) for i in range(0, fb.n, 501)] == reads[::501]
+    pin = synth_problem(cfg)
+    want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
+    eng = engine_for(pin, cfg.read_len)
+    rec = eng.process_host(fb.seq, fb.f0, fb.f1)
+    assert_records_equal(rec, want, reads)
+    tables = orc.aggregate(orc.Problem(**pin), want, reads)
+    ref = [(s, v[1], v[0]) for s, d in enumerate(tables) for v in d.values()]
+    assert [(int(e["sample"]), int(e["first_idx"]), int(e["count"])) for e in eng.table()] == ref
+    eng.close()
