@@ -266,6 +266,7 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
     // targets: window tables (window_mapping, INDEL_Processing.py:57-80)
     std::vector<uint2> blob;
     std::vector<ScarPhase> phases;
+    std::vector<std::vector<uint32_t>> locus_words;
     for (int t = 0; t < cfg->n_targets; ++t) {
         const uint8_t *T = cfg->target_bytes + cfg->target_off[t];
         const int L = (int)(cfg->target_off[t + 1] - cfg->target_off[t]);
@@ -277,7 +278,33 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
         m.n_right = L - 15 - cut > 0 ? L - 15 - cut : 0;    // while lft_position < L - 15
         if (m.n_left > SCAR_MAX_WINDOWS || m.n_right > SCAR_MAX_WINDOWS)
             return fail(SCAR_ERR_UNSUPPORTED, "target %d: more than %d windows on one side", t, SCAR_MAX_WINDOWS);
-        for (int side = 0; side < 2; ++side) {
+        // anchor-and-extend path: the locus is all ACGT, every 10-mer of it occurs once, both window lists
+        // are non-empty and positions fit the 12-bit table payload
+        bool fast = m.n_left >= 1 && m.n_right >= 1 && L >= 10 && L - 10 <= 4094 && acgt_only(T, L) &&
+                    !getenv("SCAR_NO_ANCHOR");
+        std::vector<std::pair<uint32_t, uint32_t>> pos_kv;
+        if (fast) {
+            std::map<uint32_t, uint32_t> seen;
+            for (int p = 0; p + 10 <= L && fast; ++p) {
+                const uint32_t key = (uint32_t)encode_bases(T + p, 10);
+                if (seen.count(key)) fast = false; else seen[key] = (uint32_t)p;
+            }
+            if (fast) pos_kv.assign(seen.begin(), seen.end());
+        }
+        m.fast = fast ? 1 : 0;
+        if (fast) {
+            BucketTable bt;
+            if (!build_table(pos_kv, bt)) return fail(SCAR_ERR_UNSUPPORTED, "target %d: could not build a position table", t);
+            m.pos_off = (uint32_t)blob.size(); m.pos_mult = bt.mult; m.pos_buckets = bt.nbuckets;
+            blob.insert(blob.end(), bt.buckets.begin(), bt.buckets.end());
+            // packed locus: one word (16 bases) of padding in front, two behind
+            std::vector<uint32_t> tw((size_t)(L + 15) / 16 + 3, 0u);
+            for (int p = 0; p < L; ++p) tw[1 + p / 16] |= scar_base_code(T[p]) << (2 * (p % 16));
+            locus_words.push_back(tw);
+        } else {
+            locus_words.push_back(std::vector<uint32_t>());
+        }
+        for (int side = 0; side < 2 && !fast; ++side) {
             std::map<uint32_t, uint32_t> mn;
             const int n = side == 0 ? m.n_left : m.n_right;
             for (int i = 0; i < n; ++i) {
@@ -342,6 +369,13 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
     std::vector<unsigned char> bytes;
     bytes.resize(align16(blob.size() * sizeof(uint2)));
     if (!blob.empty()) memcpy(bytes.data(), blob.data(), blob.size() * sizeof(uint2));
+    for (int t = 0; t < cfg->n_targets; ++t) {
+        if (!c->h_targets[t].fast) continue;
+        c->h_targets[t].tw_off = (uint32_t)bytes.size();
+        const auto &tw = locus_words[t];
+        bytes.resize(align16(bytes.size() + tw.size() * sizeof(uint32_t)));
+        memcpy(bytes.data() + c->h_targets[t].tw_off, tw.data(), tw.size() * sizeof(uint32_t));
+    }
     c->meta_off = (uint32_t)bytes.size();
     bytes.resize(align16(bytes.size() + c->h_targets.size() * sizeof(ScarTargetMeta)));
     memcpy(bytes.data() + c->meta_off, c->h_targets.data(), c->h_targets.size() * sizeof(ScarTargetMeta));

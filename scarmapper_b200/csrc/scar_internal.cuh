@@ -39,6 +39,11 @@ struct ScarTargetMeta {
     uint32_t left_buckets, right_buckets;
     uint32_t cutwindow_key;            // SlidingWindow.pyx:56-60 test; 0xFFFFFFFF = none
     int32_t phase_off, n_phase;
+    // anchor-and-extend path (locus is all ACGT and every 10-mer of it is unique): ONE table
+    // "10-mer -> position t in the locus" and the locus itself 2-bit packed, 16 bases per word
+    int32_t fast;                      // 1: use pos_* / tw_off, the left/right tables are not built
+    uint32_t pos_off, pos_mult, pos_buckets;
+    uint32_t tw_off;                   // byte offset in the blob of the packed locus (word 0 = 16 bases of padding)
     int32_t pad;
 };
 

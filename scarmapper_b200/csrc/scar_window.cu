@@ -110,6 +110,103 @@ __device__ __forceinline__ uint32_t runs_of_ten(uint32_t vwin)
     return c & (a >> 8);                        // runs of 10
 }
 
+// ---- anchor-and-extend (loci whose 10-mers are all distinct) -----------------------------------------
+// A probe of the position table tells where in the locus a read window lies.  When it lies on the far
+// side of the cut, the flank the scan is walking through is compared with the locus 16 bases per XOR
+// (2-bit packed words); every window inside the verified stretch is a locus window at a known
+// position, and because each 10-mer occurs once in the locus, whether it is a left / right window is
+// decided by that position alone — so the scan jumps over the stretch instead of probing each window.
+// Positions around a mismatch or the junction are still probed one by one: results are identical to
+// the exhaustive scan.
+struct ReadCursor {
+    const uint64_t *col; int64_t S; int Wr;
+    int j; uint64_t c0, c1;                       // cells j and j+1 of the read
+    __device__ __forceinline__ uint64_t cell(int k) const { return (k >= 0 && k < Wr) ? __ldg(col + k * S) : 0ull; }
+    __device__ __forceinline__ void ensure(int jj)
+    {
+        if (jj == j) return;
+        if (jj == j + 1) { c0 = c1; c1 = cell(jj + 1); }           // walking right
+        else if (jj == j - 1) { c1 = c0; c0 = cell(jj); }          // walking left
+        else { c0 = cell(jj); c1 = cell(jj + 1); }
+        j = jj;
+    }
+    // 16 bases starting at base b >= 0: 2-bit codes and ACGT mask
+    __device__ __forceinline__ void word16(int b, uint32_t &code, uint32_t &valid)
+    {
+        const int o = b & 15;
+        ensure(b >> 4);
+        code = __funnelshift_r((uint32_t)c0, (uint32_t)c1, 2 * o);
+        const uint32_t vwin = ((uint32_t)(c0 >> 32) & 0xFFFFu) | ((uint32_t)(c1 >> 32) << 16);
+        valid = (vwin >> o) & 0xFFFFu;
+    }
+};
+
+// 16 bases of the packed locus starting at base b (b >= -16; the blob pads one word in front)
+template <bool SMEM>
+__device__ __forceinline__ uint32_t locus16(const uint32_t *tw, int b)
+{
+    const int bb = b + 16, w = bb >> 4, o = bb & 15;
+    return __funnelshift_r(tw[w], tw[w + 1], 2 * o);
+}
+
+// mismatch bits (bit 2k set: base k differs or the read base is not ACGT)
+__device__ __forceinline__ uint32_t mismatch16(uint32_t rcode, uint32_t rvalid, uint32_t tcode)
+{
+    const uint32_t x = rcode ^ tcode;
+    uint32_t inv = ~rvalid & 0xFFFFu;
+    inv = (inv | (inv << 8)) & 0x00FF00FFu; inv = (inv | (inv << 4)) & 0x0F0F0F0Fu;
+    inv = (inv | (inv << 2)) & 0x33333333u; inv = (inv | (inv << 1)) & 0x55555555u;
+    return ((x | (x >> 1)) & 0x55555555u) | inv;
+}
+
+// number of bases, going LEFT from read base q-1 / locus base tq-1, that match; at most n
+template <bool SMEM>
+__device__ __forceinline__ int match_left(ReadCursor &rc, const uint32_t *tw, int q, int tq, int n)
+{
+    int k = 0;
+    while (k < n) {
+        uint32_t code, valid;
+        rc.word16(q - k - 16, code, valid);                       // bases q-k-16 .. q-k-1 (q-k >= 16 always)
+        const uint32_t mm = mismatch16(code, valid, locus16<SMEM>(tw, tq - k - 16));
+        const int run = __clz(mm) >> 1;                           // matches counted from the top base down
+        const int c = min(16, n - k);
+        if (run < c) return k + run;
+        k += c;
+    }
+    return n;
+}
+
+// number of bases, going RIGHT from read base q / locus base tq, that match; at most n
+template <bool SMEM>
+__device__ __forceinline__ int match_right(ReadCursor &rc, const uint32_t *tw, int q, int tq, int n)
+{
+    int k = 0;
+    while (k < n) {
+        uint32_t code, valid;
+        rc.word16(q + k, code, valid);
+        const uint32_t mm = mismatch16(code, valid, locus16<SMEM>(tw, tq + k));
+        const int run = mm ? ((__ffs(mm) - 1) >> 1) : 16;
+        const int c = min(16, n - k);
+        if (run < c) return k + run;
+        k += c;
+    }
+    return n;
+}
+
+// position in the locus of the read window at p, or 0xFFFFFFFF (not a locus 10-mer / not all ACGT)
+template <bool SMEM>
+__device__ __forceinline__ uint32_t locus_position(ReadCursor &rc, const TableRef<SMEM> &ptab, uint32_t mult,
+                                                   uint32_t nbuckets, int p)
+{
+    uint32_t code, valid;
+    rc.word16(p, code, valid);
+    if ((valid & 0x3FFu) != 0x3FFu) return 0xFFFFFFFFu;
+    const uint32_t t = code << 12;
+    const uint2 e = ptab.load(__umulhi(t * mult, nbuckets));
+    const uint32_t m = min(e.x ^ t, e.y ^ t);
+    return m < 4095u ? m : 0xFFFFFFFFu;
+}
+
 __device__ __forceinline__ void store_record(scar_record *dst, const scar_record &rec)
 {
     *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(&rec);
@@ -194,8 +291,64 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
             }
         }
 
+        // ---- both junctions, anchor-and-extend path
+        if (live && T.fast) {
+            const TableRef<SMEM> ptab(blob, P.blob, T.pos_off);
+            const uint32_t *tw = reinterpret_cast<const uint32_t *>(blob + T.tw_off);
+            const uint32_t mult = T.pos_mult, nb = T.pos_buckets;
+            ReadCursor rc; rc.col = col; rc.S = S; rc.Wr = Wr; rc.j = -100; rc.c0 = rc.c1 = 0ull;
+            const int L = T.length;
+            // left junction (SlidingWindow.pyx:49-69): the largest p in 16 .. len-20 whose window is a left
+            // window, i.e. lies at locus position 6 <= t <= cut-10 (window i = cut-10-t)
+            for (int p = len - 20; p >= 16; --p) {
+                const uint32_t t = locus_position<SMEM>(rc, ptab, mult, nb, p);
+                if (t == 0xFFFFFFFFu) continue;
+                if ((int)t <= cut - 10) {
+                    if (t >= 6u) { clj = p + 10; tlj = (int)t + 10; break; }
+                } else {
+                    const int need = (int)t - (cut - 10), limit = min(need, p - 16);
+                    const int k = match_left<SMEM>(rc, tw, p, (int)t, limit);
+                    if (k == limit) {                              // the whole stretch is locus sequence
+                        if (limit == need) { clj = p - need + 10; tlj = cut; }
+                        break;                                     // else: ran out of read positions, no left window
+                    }
+                    p -= k;                                        // windows p-1 .. p-k are right of the cut
+                }
+            }
+            if (clj && T.cutwindow_key != 0xFFFFFFFFu) {           // SlidingWindow.pyx:56-60 (per-read drop-in only)
+                uint32_t code, valid;
+                rc.word16(clj - 10, code, valid);
+                if ((code & SCAR_KEY_MASK) == T.cutwindow_key) {
+                    rec.status = SCAR_ST_NO_CUT; rec.flags = SCAR_FL_CUTWINDOW;
+                    rec.tlj = rec.trj = (uint16_t)cut;
+                    live = false;
+                }
+            }
+            // right junction (SlidingWindow.pyx:79-93): the smallest p in 10 .. len-26 whose window is a right
+            // window, i.e. lies at locus position cut <= t <= L-16 (window i = t-cut)
+            if (live) {
+                const int plast = len - 26;
+                for (int p = 10; p <= plast; ++p) {
+                    const uint32_t t = locus_position<SMEM>(rc, ptab, mult, nb, p);
+                    if (t == 0xFFFFFFFFu) continue;
+                    if ((int)t >= cut) {
+                        if ((int)t <= L - 16) { crj = p; trj = (int)t; break; }
+                    } else {
+                        const int need = cut - (int)t, limit = min(need, plast - p);
+                        const int k = match_right<SMEM>(rc, tw, p + 10, (int)t + 10, limit);
+                        if (k == limit) {
+                            if (limit == need) { crj = p + need; trj = cut; }
+                            break;
+                        }
+                        p += k;                                    // windows p+1 .. p+k are left of the cut
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
         // ---- left junction (SlidingWindow.pyx:49-69): p = len-20 .. 16, descending
-        if (live) {
+        if (live && !T.fast) {
             const TableRef<SMEM> ltab(blob, P.blob, T.left_off);
             const uint32_t mult = T.left_mult, nb = T.left_buckets;
             const int p0 = len - 20;
@@ -242,7 +395,7 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
         __syncwarp();
 
         // ---- right junction (SlidingWindow.pyx:79-93): p = 10 .. len-26, ascending
-        if (live) {
+        if (live && !T.fast) {
             const TableRef<SMEM> rtab(blob, P.blob, T.right_off);
             const uint32_t mult = T.right_mult, nb = T.right_buckets;
             const int plast = len - 26;

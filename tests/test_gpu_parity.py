@@ -34,8 +34,12 @@ def table_of(eng, s):
     return [(int(e["count"]), int(e["first_idx"])) for e in sel]
 
 
+@pytest.mark.parametrize("anchor", ["anchor", "scan"])
 @pytest.mark.parametrize("name", gu.golden_names())
-def test_golden_vectors_through_c_abi(name):
+def test_golden_vectors_through_c_abi(name, anchor, monkeypatch):
+    # both K3 junction searches: anchor-and-extend (unique-10-mer loci) and the exhaustive cell scan
+    if anchor == "scan":
+        monkeypatch.setenv("SCAR_NO_ANCHOR", "1")
     blob = gu.load(name)
     case, golden = blob["case"], blob["golden"]
     pin = gu.problem_inputs(case)
@@ -66,9 +70,12 @@ def synth_problem(cfg, **over):
 
 @pytest.mark.parametrize("name,n,kw", [
     ("C1", 60000, {}), ("C2", 60000, {}), ("C3", 60000, {}), ("C4", 20000, {}),
-    ("C3", 40000, {"min_len": 20, "p_n": 0.05}),
+    ("C3", 40000, {"min_len": 20, "p_n": 0.05}), ("C1", 40000, {"p_sub": 0.5, "p_n": 0.2, "min_len": 100}),
+    ("C4", 20001, {"p_sub": 0.3}),
 ])
-def test_synthetic_configs_match_oracle(name, n, kw):
+def test_synthetic_configs_match_oracle(name, n, kw, monkeypatch):
+    if name == "C4" and n == 20000:
+        monkeypatch.setenv("SCAR_NO_ANCHOR", "1")     # exhaustive scan on the long-amplicon shape
     cfg = synth.make_config(name, n_reads=n, seed=101, **kw)
     batch = cfg.generate(0, n)
     reads = cfg.reads_as_strings(batch)
