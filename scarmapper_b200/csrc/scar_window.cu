@@ -120,24 +120,15 @@ __device__ __forceinline__ uint32_t runs_of_ten(uint32_t vwin)
 // the exhaustive scan.
 struct ReadCursor {
     const uint64_t *col; int64_t S; int Wr;
-    int j; uint64_t c0, c1;                       // cells j and j+1 of the read
-    __device__ __forceinline__ uint64_t cell(int k) const { return (k >= 0 && k < Wr) ? __ldg(col + k * S) : 0ull; }
-    __device__ __forceinline__ void ensure(int jj)
+    // 16 bases starting at base b >= 0: 2-bit codes and ACGT mask (two L1-resident cell loads)
+    __device__ __forceinline__ void word16(int b, uint32_t &code, uint32_t &valid) const
     {
-        if (jj == j) return;
-        if (jj == j + 1) { c0 = c1; c1 = cell(jj + 1); }           // walking right
-        else if (jj == j - 1) { c1 = c0; c0 = cell(jj); }          // walking left
-        else { c0 = cell(jj); c1 = cell(jj + 1); }
-        j = jj;
-    }
-    // 16 bases starting at base b >= 0: 2-bit codes and ACGT mask
-    __device__ __forceinline__ void word16(int b, uint32_t &code, uint32_t &valid)
-    {
-        const int o = b & 15;
-        ensure(b >> 4);
+        const int j = b >> 4, o = b & 15;
+        const uint64_t *pc = col + (int64_t)j * S;
+        const uint64_t c0 = j < Wr ? __ldg(pc) : 0ull;
+        const uint64_t c1 = j + 1 < Wr ? __ldg(pc + S) : 0ull;
         code = __funnelshift_r((uint32_t)c0, (uint32_t)c1, 2 * o);
-        const uint32_t vwin = ((uint32_t)(c0 >> 32) & 0xFFFFu) | ((uint32_t)(c1 >> 32) << 16);
-        valid = (vwin >> o) & 0xFFFFu;
+        valid = __funnelshift_r((uint32_t)(c0 >> 32) << 16, (uint32_t)(c1 >> 32), 16 + o) & 0xFFFFu;
     }
 };
 
@@ -146,17 +137,27 @@ template <bool SMEM>
 __device__ __forceinline__ uint32_t locus16(const uint32_t *tw, int b)
 {
     const int bb = b + 16, w = bb >> 4, o = bb & 15;
-    return __funnelshift_r(tw[w], tw[w + 1], 2 * o);
+    uint32_t lo, hi;
+    if (SMEM) {
+        const uint32_t a = smem_u32(tw) + (uint32_t)w * 4u;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(a));
+        asm("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(a + 4u));
+    } else { lo = __ldg(tw + w); hi = __ldg(tw + w + 1); }
+    return __funnelshift_r(lo, hi, 2 * o);
 }
 
 // mismatch bits (bit 2k set: base k differs or the read base is not ACGT)
 __device__ __forceinline__ uint32_t mismatch16(uint32_t rcode, uint32_t rvalid, uint32_t tcode)
 {
     const uint32_t x = rcode ^ tcode;
-    uint32_t inv = ~rvalid & 0xFFFFu;
-    inv = (inv | (inv << 8)) & 0x00FF00FFu; inv = (inv | (inv << 4)) & 0x0F0F0F0Fu;
-    inv = (inv | (inv << 2)) & 0x33333333u; inv = (inv | (inv << 1)) & 0x55555555u;
-    return ((x | (x >> 1)) & 0x55555555u) | inv;
+    uint32_t mm = (x | (x >> 1)) & 0x55555555u;
+    if (rvalid != 0xFFFFu) {                      // rare: a non-ACGT read base counts as a mismatch
+        uint32_t inv = ~rvalid & 0xFFFFu;
+        inv = (inv | (inv << 8)) & 0x00FF00FFu; inv = (inv | (inv << 4)) & 0x0F0F0F0Fu;
+        inv = (inv | (inv << 2)) & 0x33333333u; inv = (inv | (inv << 1)) & 0x55555555u;
+        mm |= inv;
+    }
+    return mm;
 }
 
 // number of bases, going LEFT from read base q-1 / locus base tq-1, that match; at most n
@@ -213,7 +214,7 @@ __device__ __forceinline__ void store_record(scar_record *dst, const scar_record
 }
 
 template <bool SMEM, bool HR>
-__global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
+__global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [mbarrier 16 B][static blob: tables | target metas | phases | N-limit table]
@@ -256,27 +257,28 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
             int n_count = 0;
             for (int j = 0; j < Wr; ++j) n_count += __popc((uint32_t)(__ldg(col + j * S) >> 48));
 
-            // ---- phasing (INDEL_Processing.py:948-975): first k matching the prefix / the suffix
+            // ---- phasing (INDEL_Processing.py:948-975): first k matching the prefix / the suffix.
+            // The first 16 bases and the last 16 bases are extracted once; a phase is a shift + compare.
             if (P.do_phasing && T.n_phase > 0) {
-                const uint64_t c0 = Wr > 0 ? __ldg(col) : 0ull;
+                ReadCursor pc; pc.col = col; pc.S = S; pc.Wr = Wr;
+                uint32_t hcode, hvalid, scode, svalid;
+                pc.word16(0, hcode, hvalid);
+                const int sb = len > 16 ? len - 16 : 0;          // suffix window = bases sb .. sb+15
+                pc.word16(sb, scode, svalid);
                 int f1 = -1, f2 = -1;
                 for (int k = 0; k < T.n_phase; ++k) {
                     const ScarPhase ph = phases[T.phase_off + k];
                     if (ph.r1_len == 0) continue;            // empty R1 string: phase skipped (:954-957)
                     if (f2 < 0 && ph.r2_len != 0 && ph.r2_len <= 16 && len >= ph.r2_len) {
-                        const int p = len - ph.r2_len, j = p >> 4, o = p & 15;
-                        const uint64_t a = __ldg(col + j * S);
-                        const uint64_t b = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
-                        const uint32_t vwin = ((uint32_t)(a >> 32) & 0xFFFFu) | ((uint32_t)(b >> 32) << 16);
+                        const int o = len - ph.r2_len - sb;      // offset of the suffix inside the window
                         const uint32_t vm = (1u << ph.r2_len) - 1u;
                         const uint32_t cm = ph.r2_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r2_len)) - 1u);
-                        if ((((vwin >> o) & vm) == vm) &&
-                            ((__funnelshift_r((uint32_t)a, (uint32_t)b, 2 * o) & cm) == ph.r2_code)) f2 = k;
+                        if ((((svalid >> o) & vm) == vm) && (((scode >> (2 * o)) & cm) == ph.r2_code)) f2 = k;
                     }
                     if (f1 < 0 && ph.r1_len <= 16 && len >= ph.r1_len) {
                         const uint32_t vm = (1u << ph.r1_len) - 1u;
                         const uint32_t cm = ph.r1_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r1_len)) - 1u);
-                        if (((((uint32_t)(c0 >> 32)) & vm) == vm) && (((uint32_t)c0 & cm) == ph.r1_code)) f1 = k;
+                        if (((hvalid & vm) == vm) && ((hcode & cm) == ph.r1_code)) f1 = k;
                     }
                 }
                 rec.phase_r1 = (int8_t)(f1 < 0 ? SCAR_PHASE_NONE : f1);
@@ -291,31 +293,59 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
             }
         }
 
-        // ---- both junctions, anchor-and-extend path
-        if (live && T.fast) {
+        // ---- both junctions, anchor-and-extend path.  The loops are warp-synchronous: every round does
+        // (1) one anchor probe + flank verification and (2) one batch of 16 back-to-back probes, for all
+        // lanes that are still scanning, so the lanes of a warp stay in step.
+        {
+            const bool fast = live && T.fast;
             const TableRef<SMEM> ptab(blob, P.blob, T.pos_off);
             const uint32_t *tw = reinterpret_cast<const uint32_t *>(blob + T.tw_off);
             const uint32_t mult = T.pos_mult, nb = T.pos_buckets;
-            ReadCursor rc; rc.col = col; rc.S = S; rc.Wr = Wr; rc.j = -100; rc.c0 = rc.c1 = 0ull;
+            ReadCursor rc; rc.col = col; rc.S = S; rc.Wr = Wr;
             const int L = T.length;
+
             // left junction (SlidingWindow.pyx:49-69): the largest p in 16 .. len-20 whose window is a left
             // window, i.e. lies at locus position 6 <= t <= cut-10 (window i = cut-10-t)
-            for (int p = len - 20; p >= 16; --p) {
-                const uint32_t t = locus_position<SMEM>(rc, ptab, mult, nb, p);
-                if (t == 0xFFFFFFFFu) continue;
-                if ((int)t <= cut - 10) {
-                    if (t >= 6u) { clj = p + 10; tlj = (int)t + 10; break; }
-                } else {
-                    const int need = (int)t - (cut - 10), limit = min(need, p - 16);
-                    const int k = match_left<SMEM>(rc, tw, p, (int)t, limit);
-                    if (k == limit) {                              // the whole stretch is locus sequence
-                        if (limit == need) { clj = p - need + 10; tlj = cut; }
-                        break;                                     // else: ran out of read positions, no left window
-                    }
-                    p -= k;                                        // windows p-1 .. p-k are right of the cut
+            int p = len - 20;
+            bool scanning = fast && p >= 16;
+            while (__any_sync(0xFFFFFFFFu, scanning)) {
+                if (scanning) {                                    // (1) anchor at p
+                    const uint32_t t = locus_position<SMEM>(rc, ptab, mult, nb, p);
+                    if (t != 0xFFFFFFFFu && (int)t > cut - 10) {
+                        const int need = (int)t - (cut - 10), limit = min(need, p - 16);
+                        const int k = match_left<SMEM>(rc, tw, p, (int)t, limit);
+                        if (k == limit) {                          // the whole stretch is locus sequence
+                            if (limit == need) { clj = p - need + 10; tlj = cut; }
+                            scanning = false;                      // else: ran out of read positions
+                        } else p -= k + 1;                         // windows p-1 .. p-k are right of the cut
+                    } else if (t != 0xFFFFFFFFu && t >= 6u) {
+                        clj = p + 10; tlj = (int)t + 10; scanning = false;
+                    } else if (--p < 16) scanning = false;
                 }
+                __syncwarp();
+                if (scanning) {                                    // (2) positions p, p-1, .. p-15 in one batch
+                    const int b = p - 15;                          // >= 1 because p >= 16
+                    uint32_t wlo, whi, vlo, vhi, m[16];
+                    rc.word16(b + 16, whi, vhi);
+                    rc.word16(b, wlo, vlo);
+                    probe16<SMEM>(ptab, wlo, whi, mult, nb, m);
+                    uint32_t any = 0xFFFFFFFFu;                    // min over (t - 6): left window iff <= cut-16
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) any = min(any, m[o] - 6u);
+                    if (any <= (uint32_t)(cut - 16)) {
+                        const uint32_t okmask = runs_of_ten(vlo | (vhi << 16)) & (b >= 16 ? 0xFFFFu : (0xFFFFu << (16 - b)));
+                        uint32_t best = 0;
+#pragma unroll
+                        for (int o = 15; o >= 0; --o)
+                            if ((m[o] - 6u) <= (uint32_t)(cut - 16) && (okmask & (1u << o)))
+                                best = max(best, ((uint32_t)(b + o) << 12) + m[o]);
+                        if (best) { clj = (int)(best >> 12) + 10; tlj = (int)(best & 0xFFFu) + 10; scanning = false; }
+                    }
+                    if (scanning) { p = b - 1; if (p < 16) scanning = false; }
+                }
+                __syncwarp();
             }
-            if (clj && T.cutwindow_key != 0xFFFFFFFFu) {           // SlidingWindow.pyx:56-60 (per-read drop-in only)
+            if (fast && clj && T.cutwindow_key != 0xFFFFFFFFu) {   // SlidingWindow.pyx:56-60 (per-read drop-in only)
                 uint32_t code, valid;
                 rc.word16(clj - 10, code, valid);
                 if ((code & SCAR_KEY_MASK) == T.cutwindow_key) {
@@ -324,28 +354,51 @@ __global__ void __launch_bounds__(256) scar_window_kernel(const K3Params P)
                     live = false;
                 }
             }
+
             // right junction (SlidingWindow.pyx:79-93): the smallest p in 10 .. len-26 whose window is a right
             // window, i.e. lies at locus position cut <= t <= L-16 (window i = t-cut)
-            if (live) {
-                const int plast = len - 26;
-                for (int p = 10; p <= plast; ++p) {
+            const int plast = len - 26;
+            p = 10;
+            scanning = live && T.fast && plast >= 10;
+            while (__any_sync(0xFFFFFFFFu, scanning)) {
+                if (scanning) {
                     const uint32_t t = locus_position<SMEM>(rc, ptab, mult, nb, p);
-                    if (t == 0xFFFFFFFFu) continue;
-                    if ((int)t >= cut) {
-                        if ((int)t <= L - 16) { crj = p; trj = (int)t; break; }
-                    } else {
+                    if (t != 0xFFFFFFFFu && (int)t < cut) {
                         const int need = cut - (int)t, limit = min(need, plast - p);
                         const int k = match_right<SMEM>(rc, tw, p + 10, (int)t + 10, limit);
                         if (k == limit) {
                             if (limit == need) { crj = p + need; trj = cut; }
-                            break;
-                        }
-                        p += k;                                    // windows p+1 .. p+k are left of the cut
-                    }
+                            scanning = false;
+                        } else p += k + 1;                         // windows p+1 .. p+k are left of the cut
+                    } else if (t != 0xFFFFFFFFu && (int)t <= L - 16) {
+                        crj = p; trj = (int)t; scanning = false;
+                    } else if (++p > plast) scanning = false;
                 }
+                __syncwarp();
+                if (scanning) {                                    // positions p .. p+15 in one batch
+                    uint32_t wlo, whi, vlo, vhi, m[16];
+                    rc.word16(p, wlo, vlo);
+                    rc.word16(p + 16, whi, vhi);
+                    probe16<SMEM>(ptab, wlo, whi, mult, nb, m);
+                    const uint32_t span = (uint32_t)(L - 16 - cut);   // right window iff (t - cut) <= span
+                    uint32_t any = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) any = min(any, m[o] - (uint32_t)cut);
+                    if (any <= span) {
+                        const int top = plast - p;                 // >= 0
+                        const uint32_t okmask = runs_of_ten(vlo | (vhi << 16)) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
+                        uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int o = 0; o < 16; ++o)
+                            if ((m[o] - (uint32_t)cut) <= span && (okmask & (1u << o)))
+                                best = min(best, ((uint32_t)(p + o) << 12) + m[o]);
+                        if (best != 0xFFFFFFFFu) { crj = (int)(best >> 12); trj = (int)(best & 0xFFFu); scanning = false; }
+                    }
+                    if (scanning) { p += 16; if (p > plast) scanning = false; }
+                }
+                __syncwarp();
             }
         }
-        __syncwarp();
 
         // ---- left junction (SlidingWindow.pyx:49-69): p = len-20 .. 16, descending
         if (live && !T.fast) {
