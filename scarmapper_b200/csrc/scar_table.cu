@@ -250,15 +250,27 @@ __global__ void __launch_bounds__(256) scar_verify_kernel(const K4VerifyParams P
 __global__ void scar_export_kernel(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out,
                                    uint64_t out_capacity, unsigned long long *n_out)
 {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
+    // compaction with one atomic per warp: ballot the occupied slots, the first lane reserves the range
+    const uint64_t n_round = (capacity + 31) & ~(uint64_t)31;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
          i += (uint64_t)gridDim.x * blockDim.x) {
-        const ScarTableSlot s = slots[i];
-        if (s.tag == 0) continue;
-        const unsigned long long pos = atomicAdd(n_out, 1ull);
-        if (pos < out_capacity) {
-            scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = (uint64_t)(s.tag >> 64); e.first_idx = ~s.inv_first; e.count = s.count;
-            e.sample = (uint16_t)s.sample; e.pad = 0;
-            out[pos] = e;
+        ScarTableSlot s;
+        s.tag = 0;
+        if (i < capacity) s = slots[i];
+        const bool used = s.tag != 0;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, used);
+        if (!bal) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (used) {
+            const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
+            if (pos < out_capacity) {
+                scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = (uint64_t)(s.tag >> 64); e.first_idx = ~s.inv_first;
+                e.count = s.count; e.sample = (uint16_t)s.sample; e.pad = 0;
+                out[pos] = e;
+            }
         }
     }
 }
