@@ -107,7 +107,7 @@ int scar_window_counts(const scar_ctx *ctx, int32_t target, int32_t *n_left, int
 /* K1: raw bytes -> packed rows (2-bit codes + ACGT mask + N mask), applying the platform's stored-
  * sequence transform (Illumina as is, TruSeq seq[6:-6], Ramsden rcomp; INDEL_Processing.py:946,978,981). */
 int scar_pack_dev(scar_ctx *ctx, const scar_ragged *seq, int64_t n_reads,
-                  uint64_t *cells, uint16_t *lens, void *stream);
+                  uint64_t *cells, uint32_t *lens, void *stream);   /* lens[r] = stored length | N count << 16 */
 
 /* K2: sample assignment per read (manifest position or SCAR_SAMPLE_NONE).
  * Illumina: f0/f1 = name.split(":")[-1].split("+")[0..1]; TruSeq/Ramsden: taken from seq. */
@@ -115,7 +115,7 @@ int scar_demux_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_ragged *f0,
                    int64_t n_reads, uint16_t *samples, void *stream);
 
 /* K3: phasing + filters + sliding-window junction search + junction call. */
-int scar_classify_dev(scar_ctx *ctx, const uint64_t *cells, const uint16_t *lens,
+int scar_classify_dev(scar_ctx *ctx, const uint64_t *cells, const uint32_t *lens,
                       const uint16_t *samples, int64_t n_reads, scar_record *records, void *stream);
 
 /* K4: accumulate per-sample counters, phase histograms and the scar table.  first_index is the
@@ -126,7 +126,7 @@ int scar_aggregate_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_record 
 /* Whole path over a batch already resident in HBM: K2 -> K1 -> K3 -> K4 on `stream`.
  * cells/lens/samples/records are caller-provided device scratch/outputs. */
 int scar_run_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_ragged *f0, const scar_ragged *f1,
-                 int64_t n_reads, uint64_t first_index, uint64_t *cells, uint16_t *lens,
+                 int64_t n_reads, uint64_t first_index, uint64_t *cells, uint32_t *lens,
                  uint16_t *samples, scar_record *records, void *stream);
 
 /* Whole path from HOST buffers: chunks the batch, overlaps H2D / kernels / D2H on internal

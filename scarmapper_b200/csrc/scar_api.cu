@@ -108,7 +108,7 @@ struct HostBuf {   // device scratch of one in-flight chunk of scar_process_host
     uint8_t *seq = nullptr, *f0 = nullptr, *f1 = nullptr; size_t seq_cap = 0, f0_cap = 0, f1_cap = 0;
     int64_t *seq_off = nullptr, *f0_off = nullptr, *f1_off = nullptr;
     int32_t *seq_len = nullptr, *f0_len = nullptr, *f1_len = nullptr;
-    uint64_t *cells = nullptr; uint16_t *lens = nullptr, *samples = nullptr; scar_record *records = nullptr;
+    uint64_t *cells = nullptr; uint32_t *lens = nullptr; uint16_t *samples = nullptr; scar_record *records = nullptr;
     int64_t reads_cap = 0;
     cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
 };
@@ -267,6 +267,7 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
     std::vector<uint2> blob;
     std::vector<ScarPhase> phases;
     std::vector<std::vector<uint32_t>> locus_words;
+    std::vector<std::vector<uint8_t>> phase_luts;
     for (int t = 0; t < cfg->n_targets; ++t) {
         const uint8_t *T = cfg->target_bytes + cfg->target_off[t];
         const int L = (int)(cfg->target_off[t + 1] - cfg->target_off[t]);
@@ -350,7 +351,27 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
                 phases.push_back(p);
             }
             m.n_phase = k1 - k0;
-        }
+            // phasing lookup tables when every non-empty string of a side has one length <= 6 and is ACGT
+            int n1 = 0, n2 = 0; bool lut_ok = true;
+            for (int k = k0; k < k1 && lut_ok; ++k) {
+                const ScarPhase &p = phases[m.phase_off + (k - k0)];
+                if (p.r1_len == 0) continue;                 // skipped phase (both sides)
+                if (p.r1_len > 6 || (n1 && p.r1_len != n1)) lut_ok = false; else n1 = p.r1_len;
+                if (p.r2_len != 0) { if (p.r2_len > 6 || (n2 && p.r2_len != n2)) lut_ok = false; else n2 = p.r2_len; }
+            }
+            if (lut_ok && n1) {
+                const int stride = 1 << (2 * std::max(n1, n2));      // 4^n entries per side
+                std::vector<uint8_t> lut((size_t)2 * stride, 0);
+                for (int k = k1 - 1; k >= k0; --k) {          // descending so that the first k wins
+                    const ScarPhase &p = phases[m.phase_off + (k - k0)];
+                    if (p.r1_len == 0) continue;
+                    lut[p.r1_code] = (uint8_t)(k - k0 + 1);
+                    if (p.r2_len != 0) lut[stride + p.r2_code] = (uint8_t)(k - k0 + 1);
+                }
+                phase_luts.push_back(lut); m.ph_n1 = n1; m.ph_n2 = n2; m.ph_lut_off = 1;   // offset fixed up below
+            } else phase_luts.push_back(std::vector<uint8_t>());
+        } else phase_luts.push_back(std::vector<uint8_t>());
+        if ((int)phase_luts.size() < t + 1) phase_luts.push_back(std::vector<uint8_t>());
         c->h_targets.push_back(m);
     }
     c->do_phasing = (cfg->phase_off && cfg->platform == SCAR_PLATFORM_ILLUMINA) ? 1 : 0;
@@ -375,6 +396,12 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
         const auto &tw = locus_words[t];
         bytes.resize(align16(bytes.size() + tw.size() * sizeof(uint32_t)));
         memcpy(bytes.data() + c->h_targets[t].tw_off, tw.data(), tw.size() * sizeof(uint32_t));
+    }
+    for (int t = 0; t < cfg->n_targets; ++t) {
+        if (!c->h_targets[t].ph_lut_off) continue;
+        c->h_targets[t].ph_lut_off = (uint32_t)bytes.size();
+        bytes.resize(align16(bytes.size() + phase_luts[t].size()));
+        memcpy(bytes.data() + c->h_targets[t].ph_lut_off, phase_luts[t].data(), phase_luts[t].size());
     }
     c->meta_off = (uint32_t)bytes.size();
     bytes.resize(align16(bytes.size() + c->h_targets.size() * sizeof(ScarTargetMeta)));
@@ -446,7 +473,7 @@ extern "C" int scar_window_counts(const scar_ctx *c, int32_t t, int32_t *n_left,
 }
 
 // ---- stage entry points (device pointers) ---------------------------------------------------------
-extern "C" int scar_pack_dev(scar_ctx *c, const scar_ragged *seq, int64_t n, uint64_t *cells, uint16_t *lens, void *stream)
+extern "C" int scar_pack_dev(scar_ctx *c, const scar_ragged *seq, int64_t n, uint64_t *cells, uint32_t *lens, void *stream)
 {
     if (!c || !seq || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));
@@ -471,7 +498,7 @@ extern "C" int scar_demux_dev(scar_ctx *c, const scar_ragged *seq, const scar_ra
     return SCAR_OK;
 }
 
-extern "C" int scar_classify_dev(scar_ctx *c, const uint64_t *cells, const uint16_t *lens, const uint16_t *samples,
+extern "C" int scar_classify_dev(scar_ctx *c, const uint64_t *cells, const uint32_t *lens, const uint16_t *samples,
                                  int64_t n, scar_record *records, void *stream)
 {
     if (!c || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
@@ -507,7 +534,7 @@ extern "C" int scar_aggregate_dev(scar_ctx *c, const scar_ragged *seq, const sca
 }
 
 extern "C" int scar_run_dev(scar_ctx *c, const scar_ragged *seq, const scar_ragged *f0, const scar_ragged *f1, int64_t n,
-                            uint64_t first_index, uint64_t *cells, uint16_t *lens, uint16_t *samples,
+                            uint64_t first_index, uint64_t *cells, uint32_t *lens, uint16_t *samples,
                             scar_record *records, void *stream)
 {
     int rc;
@@ -729,7 +756,7 @@ static int ensure_hostbuf(scar_ctx *c, HostBuf &b, int64_t reads)
     CU(cudaMalloc((void **)&b.f0_len, n * sizeof(int32_t)));
     CU(cudaMalloc((void **)&b.f1_len, n * sizeof(int32_t)));
     CU(cudaMalloc((void **)&b.cells, n * c->W * sizeof(uint64_t)));
-    CU(cudaMalloc((void **)&b.lens, n * sizeof(uint16_t)));
+    CU(cudaMalloc((void **)&b.lens, n * sizeof(uint32_t)));
     CU(cudaMalloc((void **)&b.samples, n * sizeof(uint16_t)));
     CU(cudaMalloc((void **)&b.records, n * sizeof(scar_record)));
     b.reads_cap = reads;

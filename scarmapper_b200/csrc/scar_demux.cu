@@ -34,9 +34,11 @@ __device__ __forceinline__ void encode16(const uint8_t *u, int n, uint32_t &code
     code = 0; valid = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        uint32_t c8, v4, n4;
-        classify4(__funnelshift_r(w[i], w[i + 1], sh), c8, v4, n4);
-        code |= c8 << (8 * i); valid |= v4 << (4 * i);
+        if (4 * i < n) {                          // (8-nt Illumina fields: two words)
+            uint32_t c8, v4, n4;
+            classify4(__funnelshift_r(w[i], w[i + 1], sh), c8, v4, n4);
+            code |= c8 << (8 * i); valid |= v4 << (4 * i);
+        }
     }
     valid &= n >= 16 ? 0xFFFFu : ((1u << n) - 1u);
     code &= n >= 16 ? 0xFFFFFFFFu : ((1u << (2 * n)) - 1u);    // bytes past the string belong to the next item
@@ -95,44 +97,59 @@ __global__ void __launch_bounds__(256) scar_demux_kernel(const K2Params P)
             class_codes(u1, n1, cmap, c1);
         }
         uint64_t ok_r = 0, ok_l = 0;   // bit d set: distinct string d accepted
-        for (int d = 0; d < P.n_right; ++d) {
-            const int m = s_len[0][d];
-            if (ramsden) {
-                u0 = seq; n0 = slen < m ? slen : m;                       // seq[:len(right_index)]
-                if (cached0 != n0) { class_codes(u0, n0, cmap, c0); cached0 = n0; }
-            }
-            bool acc;
-            if (FAST && !ramsden && n0 == m && m <= 16) {
+        if (FAST && !ramsden) {
+            // equal lengths: 2-bit Hamming decides (exact for t <= 1; for t > 1 a miss goes to the slow list);
+            // other lengths go to the slow list (quick reject / bit-vector edit distance)
+            uint64_t slow = 0;
+            for (int d = 0; d < P.n_right; ++d) {
                 const uint32_t x = e0 ^ s_code[0][d];
-                const int ham = __popc(((x | (x >> 1)) & 0x55555555u) | x0);
-                acc = ham <= thr;
-                if (!acc && thr > 1) acc = accepts(P.right[d], P.peq, u0, n0, c0, cmap, thr, false);
-            } else {
-                acc = accepts(P.right[d], P.peq, u0, n0, c0, cmap, thr, !(FAST && !ramsden));
+                const bool hit = __popc(((x | (x >> 1)) & 0x55555555u) | x0) <= thr;
+                const bool eq = s_len[0][d] == n0 && n0 <= 16;
+                ok_r |= (uint64_t)(eq && hit) << d;
+                slow |= (uint64_t)(!eq || (!hit && thr > 1)) << d;
             }
-            if (acc) ok_r |= 1ull << d;
+            for (uint64_t a = slow; a; a &= a - 1) {
+                const int d = __ffsll((long long)a) - 1;
+                if (accepts(P.right[d], P.peq, u0, n0, c0, cmap, thr, false)) ok_r |= 1ull << d;
+            }
+            if (ok_r) {
+                slow = 0;
+                for (int d = 0; d < P.n_left; ++d) {
+                    const uint32_t x = e1 ^ s_code[1][d];
+                    const bool hit = __popc(((x | (x >> 1)) & 0x55555555u) | x1) <= thr;
+                    const bool eq = s_len[1][d] == n1 && n1 <= 16;
+                    ok_l |= (uint64_t)(eq && hit) << d;
+                    slow |= (uint64_t)(!eq || (!hit && thr > 1)) << d;
+                }
+                for (uint64_t a = slow; a; a &= a - 1) {
+                    const int d = __ffsll((long long)a) - 1;
+                    if (accepts(P.left[d], P.peq, u1, n1, c1, cmap, thr, false)) ok_l |= 1ull << d;
+                }
+            }
+        } else {
+            for (int d = 0; d < P.n_right; ++d) {
+                const int m = s_len[0][d];
+                if (ramsden) {
+                    u0 = seq; n0 = slen < m ? slen : m;                       // seq[:len(right_index)]
+                    if (cached0 != n0) { class_codes(u0, n0, cmap, c0); cached0 = n0; }
+                }
+                if (accepts(P.right[d], P.peq, u0, n0, c0, cmap, thr, true)) ok_r |= 1ull << d;
+            }
+            if (ok_r) {
+                for (int d = 0; d < P.n_left; ++d) {
+                    const int m = s_len[1][d];
+                    if (ramsden) {
+                        // seq[-len(left_index):] ; seq[-0:] is the whole string
+                        n1 = (m == 0 || m >= slen) ? slen : m;
+                        u1 = seq + (slen - n1);
+                        if (cached1 != n1) { class_codes(u1, n1, cmap, c1); cached1 = n1; }
+                    }
+                    if (accepts(P.left[d], P.peq, u1, n1, c1, cmap, thr, true)) ok_l |= 1ull << d;
+                }
+            }
         }
         uint32_t best = SCAR_SAMPLE_NONE;
-        if (ok_r) {
-            for (int d = 0; d < P.n_left; ++d) {
-                const int m = s_len[1][d];
-                if (ramsden) {
-                    // seq[-len(left_index):] ; seq[-0:] is the whole string
-                    n1 = (m == 0 || m >= slen) ? slen : m;
-                    u1 = seq + (slen - n1);
-                    if (cached1 != n1) { class_codes(u1, n1, cmap, c1); cached1 = n1; }
-                }
-                bool acc;
-                if (FAST && !ramsden && n1 == m && m <= 16) {
-                    const uint32_t x = e1 ^ s_code[1][d];
-                    const int ham = __popc(((x | (x >> 1)) & 0x55555555u) | x1);
-                    acc = ham <= thr;
-                    if (!acc && thr > 1) acc = accepts(P.left[d], P.peq, u1, n1, c1, cmap, thr, false);
-                } else {
-                    acc = accepts(P.left[d], P.peq, u1, n1, c1, cmap, thr, !(FAST && !ramsden));
-                }
-                if (acc) ok_l |= 1ull << d;
-            }
+        if (ok_r && ok_l) {
             // first manifest row whose (right, left) strings are both acceptable
             for (uint64_t a = ok_r; a; a &= a - 1) {
                 const int dr = __ffsll((long long)a) - 1;

@@ -44,6 +44,10 @@ struct ScarTargetMeta {
     int32_t fast;                      // 1: use pos_* / tw_off, the left/right tables are not built
     uint32_t pos_off, pos_mult, pos_buckets;
     uint32_t tw_off;                   // byte offset in the blob of the packed locus (word 0 = 16 bases of padding)
+    // phasing lookup (all non-empty phase strings of a side share one length <= 6): 2 x 4^n bytes in the
+    // blob, entry = 1 + first matching k (0 = none), indexed by the prefix / suffix 2-bit code
+    uint32_t ph_lut_off;               // 0 = no table, use the phase list
+    int32_t ph_n1, ph_n2;
     int32_t pad;
 };
 
@@ -106,7 +110,7 @@ struct K1Params {
     scar_ragged seq;      // device pointers
     uint64_t *cells;      // cell-major [W][stride]
     int64_t stride;
-    uint16_t *lens;       // [n]
+    uint32_t *lens;       // [n] stored length | N count << 16
     int64_t n_reads;
     int32_t W;
     int32_t platform;
@@ -131,7 +135,7 @@ struct K2Params {
 
 struct K3Params {
     const uint64_t *cells;        // cell-major: cell j of read r at cells[j * stride + r]
-    const uint16_t *lens;         // [n]
+    const uint32_t *lens;         // [n] stored length | N count << 16
     const uint16_t *samples;      // [n]
     scar_record *records;         // [n]
     const int32_t *sample_target; // [n_samples]
@@ -175,7 +179,7 @@ struct K4VerifyParams {
 
 cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t scar_launch_pack(const scar_ragged &seq, int64_t n, int W, int platform, uint64_t *cells,
-                             int64_t stride, uint16_t *lens, int32_t *status, int sm_count, cudaStream_t stream, int *launches);
+                             int64_t stride, uint32_t *lens, int32_t *status, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t scar_launch_demux(const K2Params &P, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t scar_launch_match_maker(const scar_ragged &q, const scar_ragged &u, int64_t n, int32_t *out,
                                     cudaStream_t stream);

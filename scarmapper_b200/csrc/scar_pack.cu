@@ -26,9 +26,9 @@ __global__ void __launch_bounds__(256) scar_pack_kernel(const K1Params P)
         int slen = len, shift = 0;
         if (P.platform == SCAR_PLATFORM_TRUSEQ) { slen = len > 12 ? len - 12 : 0; shift = 6; }
         if (slen > 16 * P.W) { atomicOr(P.status, 1); slen = 16 * P.W; }
-        P.lens[r] = (uint16_t)slen;
         const bool rc = P.platform == SCAR_PLATFORM_RAMSDEN;
         const uintptr_t base = (uintptr_t)P.seq.bytes;
+        int n_count = 0;
         for (int j = 0; j < P.W; ++j) {
             uint64_t *out = P.cells + (int64_t)j * P.stride + r;
             int nb = slen - 16 * j;                    // bases of this cell
@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256) scar_pack_kernel(const K1Params P)
             if (rc) code ^= 0xAAAAAAAAu;                               // complement: code ^ 2
             const uint32_t bm = nb == 16 ? 0xFFFFu : ((1u << nb) - 1u);
             valid &= bm; nmask &= bm;
+            n_count += __popc(nmask);
             // spread the ACGT mask to 2 bits per base to clear the codes of non-ACGT / absent bases
             uint32_t m2 = valid;
             m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
@@ -75,11 +76,12 @@ __global__ void __launch_bounds__(256) scar_pack_kernel(const K1Params P)
             code &= m2 * 3u;
             *out = (uint64_t)code | ((uint64_t)valid << 32) | ((uint64_t)nmask << 48);
         }
+        P.lens[r] = (uint32_t)slen | ((uint32_t)n_count << 16);     // length and literal-'N' count for the filter
     }
 }
 
 cudaError_t scar_launch_pack(const scar_ragged &seq, int64_t n, int W, int platform, uint64_t *cells,
-                             int64_t stride, uint16_t *lens, int32_t *status, int sm_count, cudaStream_t stream,
+                             int64_t stride, uint32_t *lens, int32_t *status, int sm_count, cudaStream_t stream,
                              int *launches)
 {
     if (n <= 0) return cudaSuccess;

@@ -9,7 +9,7 @@
 // (sample, tlj, trj, kind, segment bytes, hr).  It is identified by two independent 64-bit hashes
 // (128 bits; both must agree).  The table is open-addressed in HBM; a slot keeps the count and the
 // smallest global read index (the reference stores the FIRST read's record and orders ties by
-// first-seen rank).  Reads of one warp that carry the same key are combined before touching memory.
+// first-seen rank).
 #include "scar_internal.cuh"
 
 
@@ -111,10 +111,7 @@ __global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
     }
     if (threadIdx.x == 0) { s_unassigned = 0; s_new = 0; }
     __syncthreads();
-    const uint32_t FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-
-    const int64_t n_round = (P.n_reads + 31) & ~(int64_t)31;   // keep warps converged for the collectives
+    const int64_t n_round = (P.n_reads + 31) & ~(int64_t)31;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_round;
          r += (int64_t)gridDim.x * blockDim.x) {
         const bool in_range = r < P.n_reads;
@@ -160,30 +157,15 @@ __global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
             }
         }
 
-        // ---- scar table
-        const bool scar = in_range && rec.status == SCAR_ST_SCAR;
-        const uint32_t active = __ballot_sync(FULL, scar);
-        if (scar) {
+        // ---- scar table: every SCAR read inserts its own key.  (Combining equal keys inside a warp with
+        // __match_any_sync / per-group shuffles was measured slower: most keys of a warp are distinct and
+        // every distinct group is a separate divergent pass; the L2 atomics of equal keys coalesce anyway.)
+        if (in_range && rec.status == SCAR_ST_SCAR) {
             const uint8_t *raw; int rawlen;
             get_item(P.seq, r, raw, rawlen);
             uint64_t h1, h2;
             key_hashes(rec, raw, rawlen, P.platform, h1, h2);
-            // combine the lanes of this warp that carry the same key
-            const uint32_t peers = __match_any_sync(active, (unsigned long long)h1);
-            const int leader = __ffs(peers) - 1;
-            const uint64_t lh2 = __shfl_sync(peers, (unsigned long long)h2, leader);
-            const bool same = lh2 == h2;
-            const uint32_t agg = __ballot_sync(peers, same);
-            if (same) {
-                const uint32_t rmin = __reduce_min_sync(agg, (uint32_t)(r & 0xFFFFFFFFll));
-                if (lane == leader) {
-                    const uint64_t base = (uint64_t)r - (uint32_t)(r & 0xFFFFFFFFll);
-                    if (table_insert(P, h1, h2, (uint32_t)__popc(agg), P.first_index + base + rmin, rec.sample))
-                        atomicAdd(&s_new, 1u);
-                }
-            } else {
-                if (table_insert(P, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample)) atomicAdd(&s_new, 1u);
-            }
+            if (table_insert(P, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample)) atomicAdd(&s_new, 1u);
         }
     }
     __syncthreads();

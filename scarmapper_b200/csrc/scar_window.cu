@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
         const uint32_t sample = live ? (uint32_t)P.samples[r] : 0xFFFFu;
         if (sample >= (uint32_t)P.n_samples) live = false;      // unidentified (INDEL_Processing.py:1194-1198)
         else rec.sample = (uint16_t)sample;
-        const int len = live ? (int)P.lens[r] : 0;
+        const uint32_t info = live ? P.lens[r] : 0u;             // stored length | N count << 16 (from K1)
+        const int len = (int)(info & 0xFFFFu);
         const int tid = live ? __ldg(P.sample_target + sample) : 0;
         const ScarTargetMeta &T = metas[tid];
         const uint64_t *col = P.cells + (in_range ? r : 0);     // cell j of this read = col[j * S]
@@ -253,10 +254,7 @@ __global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
         int clj = 0, crj = 0, tlj = cut, trj = cut;
 
         if (live) {
-            // ---- N count over the whole read
-            int n_count = 0;
-            for (int j = 0; j < Wr; ++j) n_count += __popc((uint32_t)(__ldg(col + j * S) >> 48));
-
+            const int n_count = (int)(info >> 16);
             // ---- phasing (INDEL_Processing.py:948-975): first k matching the prefix / the suffix.
             // The first 16 bases and the last 16 bases are extracted once; a phase is a shift + compare.
             if (P.do_phasing && T.n_phase > 0) {
@@ -266,19 +264,33 @@ __global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
                 const int sb = len > 16 ? len - 16 : 0;          // suffix window = bases sb .. sb+15
                 pc.word16(sb, scode, svalid);
                 int f1 = -1, f2 = -1;
-                for (int k = 0; k < T.n_phase; ++k) {
-                    const ScarPhase ph = phases[T.phase_off + k];
-                    if (ph.r1_len == 0) continue;            // empty R1 string: phase skipped (:954-957)
-                    if (f2 < 0 && ph.r2_len != 0 && ph.r2_len <= 16 && len >= ph.r2_len) {
-                        const int o = len - ph.r2_len - sb;      // offset of the suffix inside the window
-                        const uint32_t vm = (1u << ph.r2_len) - 1u;
-                        const uint32_t cm = ph.r2_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r2_len)) - 1u);
-                        if ((((svalid >> o) & vm) == vm) && (((scode >> (2 * o)) & cm) == ph.r2_code)) f2 = k;
+                if (T.ph_lut_off) {
+                    // every non-empty phase string of a side has the same length (<= 6): the first matching
+                    // k is tabulated per prefix / suffix code at context creation
+                    const uint8_t *lut = blob + T.ph_lut_off;
+                    const int n1 = T.ph_n1, n2 = T.ph_n2;
+                    if (n1 && len >= n1 && (hvalid & ((1u << n1) - 1u)) == ((1u << n1) - 1u))
+                        f1 = (int)lut[hcode & ((1u << (2 * n1)) - 1u)] - 1;
+                    if (n2 && len >= n2) {
+                        const int o = len - n2 - sb;
+                        if (((svalid >> o) & ((1u << n2) - 1u)) == ((1u << n2) - 1u))
+                            f2 = (int)lut[(1u << (2 * max(n1, n2))) + ((scode >> (2 * o)) & ((1u << (2 * n2)) - 1u))] - 1;
                     }
-                    if (f1 < 0 && ph.r1_len <= 16 && len >= ph.r1_len) {
-                        const uint32_t vm = (1u << ph.r1_len) - 1u;
-                        const uint32_t cm = ph.r1_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r1_len)) - 1u);
-                        if (((hvalid & vm) == vm) && ((hcode & cm) == ph.r1_code)) f1 = k;
+                } else {
+                    for (int k = 0; k < T.n_phase; ++k) {
+                        const ScarPhase ph = phases[T.phase_off + k];
+                        if (ph.r1_len == 0) continue;            // empty R1 string: phase skipped (:954-957)
+                        if (f2 < 0 && ph.r2_len != 0 && ph.r2_len <= 16 && len >= ph.r2_len) {
+                            const int o = len - ph.r2_len - sb;      // offset of the suffix inside the window
+                            const uint32_t vm = (1u << ph.r2_len) - 1u;
+                            const uint32_t cm = ph.r2_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r2_len)) - 1u);
+                            if ((((svalid >> o) & vm) == vm) && (((scode >> (2 * o)) & cm) == ph.r2_code)) f2 = k;
+                        }
+                        if (f1 < 0 && ph.r1_len <= 16 && len >= ph.r1_len) {
+                            const uint32_t vm = (1u << ph.r1_len) - 1u;
+                            const uint32_t cm = ph.r1_len == 16 ? 0xFFFFFFFFu : ((1u << (2 * ph.r1_len)) - 1u);
+                            if (((hvalid & vm) == vm) && ((hcode & cm) == ph.r1_code)) f1 = k;
+                        }
                     }
                 }
                 rec.phase_r1 = (int8_t)(f1 < 0 ? SCAR_PHASE_NONE : f1);

@@ -239,7 +239,7 @@ class ScarEngine:
         n = seq.n
         batch = {"n": n, "seq": up(seq), "f0": up(f0), "f1": up(f1),
                  "cells": torch.empty((self.cells_per_read, max(n, 1)), dtype=torch.int64, device=dev),  # cell-major
-                 "lens": torch.empty(n, dtype=torch.int16, device=dev),
+                 "lens": torch.empty(n, dtype=torch.int32, device=dev),        # stored length | N count << 16
                  "samples": torch.empty(n, dtype=torch.int16, device=dev),
                  "records": torch.empty((n, 16), dtype=torch.uint8, device=dev)}
         return batch

@@ -190,8 +190,9 @@ def test_pack_kernel_layout_and_transforms(platform):
     want = pack_reference(stored, eng.cells_per_read)
     got = res["cells"].cpu().numpy().view(np.uint64)
     assert (got == want).all()
-    lens = res["lens"].cpu().numpy().view(np.uint16)
-    assert list(lens) == [len(s) for s in stored]
+    lens = res["lens"].cpu().numpy().view(np.uint32)
+    assert list(lens & 0xFFFF) == [len(s) for s in stored]
+    assert list(lens >> 16) == [s.count("N") for s in stored]
     eng.close()
 
 
