@@ -160,17 +160,68 @@ __device__ __forceinline__ uint32_t mismatch16(uint32_t rcode, uint32_t rvalid, 
     return mm;
 }
 
-// number of bases, going LEFT from read base q-1 / locus base tq-1, that match; at most n
+// 32 bases starting at base b >= 0 of the read (2-bit codes, ACGT mask) and of the locus
+struct Word32 { uint64_t code; uint32_t valid; };
+__device__ __forceinline__ Word32 read32(const ReadCursor &rc, int b)
+{
+    const int j = b >> 4, o = b & 15;
+    const uint64_t *pc = rc.col + (int64_t)j * rc.S;
+    const uint64_t c0 = j < rc.Wr ? __ldg(pc) : 0ull;
+    const uint64_t c1 = j + 1 < rc.Wr ? __ldg(pc + rc.S) : 0ull;
+    const uint64_t c2 = j + 2 < rc.Wr ? __ldg(pc + 2 * rc.S) : 0ull;
+    Word32 w;
+    const uint32_t lo = __funnelshift_r((uint32_t)c0, (uint32_t)c1, 2 * o);
+    const uint32_t hi = __funnelshift_r((uint32_t)c1, (uint32_t)c2, 2 * o);
+    w.code = ((uint64_t)hi << 32) | lo;
+    const uint64_t v48 = ((c0 >> 32) & 0xFFFFull) | (((c1 >> 32) & 0xFFFFull) << 16) | (((c2 >> 32) & 0xFFFFull) << 32);
+    w.valid = (uint32_t)(v48 >> o);
+    return w;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ uint64_t locus32(const uint32_t *tw, int b)     // b >= -16
+{
+    const int bb = b + 16, w = bb >> 4, o = bb & 15;
+    uint32_t a0, a1, a2;
+    if (SMEM) {
+        const uint32_t a = smem_u32(tw) + (uint32_t)w * 4u;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(a0) : "r"(a));
+        asm("ld.shared.u32 %0, [%1];" : "=r"(a1) : "r"(a + 4u));
+        asm("ld.shared.u32 %0, [%1];" : "=r"(a2) : "r"(a + 8u));
+    } else { a0 = __ldg(tw + w); a1 = __ldg(tw + w + 1); a2 = __ldg(tw + w + 2); }
+    return ((uint64_t)__funnelshift_r(a1, a2, 2 * o) << 32) | __funnelshift_r(a0, a1, 2 * o);
+}
+
+// mismatch bits of 32 bases (bit 2k set: base k differs or the read base is not ACGT)
+__device__ __forceinline__ uint64_t mismatch32(const Word32 &r, uint64_t tcode)
+{
+    const uint64_t x = r.code ^ tcode;
+    uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
+    if (r.valid != 0xFFFFFFFFu) {                 // rare: a non-ACGT read base counts as a mismatch
+        uint64_t inv = (uint64_t)(~r.valid);
+        inv = (inv | (inv << 16)) & 0x0000FFFF0000FFFFull; inv = (inv | (inv << 8)) & 0x00FF00FF00FF00FFull;
+        inv = (inv | (inv << 4)) & 0x0F0F0F0F0F0F0F0Full; inv = (inv | (inv << 2)) & 0x3333333333333333ull;
+        inv = (inv | (inv << 1)) & 0x5555555555555555ull;
+        mm |= inv;
+    }
+    return mm;
+}
+
+// number of bases, going LEFT from read base q-1 / locus base tq-1, that match; at most n.
+// 32 bases per step; the window may start before base 0 of the read on the last step (q-k >= 16 only
+// guarantees 16 bases), so the step is clamped to what exists.
 template <bool SMEM>
 __device__ __forceinline__ int match_left(ReadCursor &rc, const uint32_t *tw, int q, int tq, int n)
 {
     int k = 0;
     while (k < n) {
-        uint32_t code, valid;
-        rc.word16(q - k - 16, code, valid);                       // bases q-k-16 .. q-k-1 (q-k >= 16 always)
-        const uint32_t mm = mismatch16(code, valid, locus16<SMEM>(tw, tq - k - 16));
-        const int run = __clz(mm) >> 1;                           // matches counted from the top base down
-        const int c = min(16, n - k);
+        const int e = q - k;                                      // bases e-w .. e-1, w = min(32, e)
+        const int w = min(32, min(e, tq - k + 16));
+        const Word32 r = read32(rc, e - w);
+        uint64_t mm = mismatch32(r, locus32<SMEM>(tw, tq - k - w));
+        mm <<= 2 * (32 - w);                                      // align the top base to bit 62
+        const int run = mm ? (__clzll((long long)mm) >> 1) : 32;  // matches counted from the top base down
+        const int c = min(w, n - k);
         if (run < c) return k + run;
         k += c;
     }
@@ -183,11 +234,10 @@ __device__ __forceinline__ int match_right(ReadCursor &rc, const uint32_t *tw, i
 {
     int k = 0;
     while (k < n) {
-        uint32_t code, valid;
-        rc.word16(q + k, code, valid);
-        const uint32_t mm = mismatch16(code, valid, locus16<SMEM>(tw, tq + k));
-        const int run = mm ? ((__ffs(mm) - 1) >> 1) : 16;
-        const int c = min(16, n - k);
+        const Word32 r = read32(rc, q + k);
+        const uint64_t mm = mismatch32(r, locus32<SMEM>(tw, tq + k));
+        const int run = mm ? ((__ffsll((long long)mm) - 1) >> 1) : 32;
+        const int c = min(32, n - k);
         if (run < c) return k + run;
         k += c;
     }
@@ -341,10 +391,7 @@ __global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
                     rc.word16(b + 16, whi, vhi);
                     rc.word16(b, wlo, vlo);
                     probe16<SMEM>(ptab, wlo, whi, mult, nb, m);
-                    uint32_t any = 0xFFFFFFFFu;                    // min over (t - 6): left window iff <= cut-16
-#pragma unroll
-                    for (int o = 0; o < 16; ++o) any = min(any, m[o] - 6u);
-                    if (any <= (uint32_t)(cut - 16)) {
+                    {                                              // left window iff (t - 6) <= cut-16
                         const uint32_t okmask = runs_of_ten(vlo | (vhi << 16)) & (b >= 16 ? 0xFFFFu : (0xFFFFu << (16 - b)));
                         uint32_t best = 0;
 #pragma unroll
@@ -393,10 +440,7 @@ __global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
                     rc.word16(p + 16, whi, vhi);
                     probe16<SMEM>(ptab, wlo, whi, mult, nb, m);
                     const uint32_t span = (uint32_t)(L - 16 - cut);   // right window iff (t - cut) <= span
-                    uint32_t any = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int o = 0; o < 16; ++o) any = min(any, m[o] - (uint32_t)cut);
-                    if (any <= span) {
+                    {
                         const int top = plast - p;                 // >= 0
                         const uint32_t okmask = runs_of_ten(vlo | (vhi << 16)) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
                         uint32_t best = 0xFFFFFFFFu;
