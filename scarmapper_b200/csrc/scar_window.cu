@@ -391,14 +391,17 @@ __global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
                     rc.word16(b + 16, whi, vhi);
                     rc.word16(b, wlo, vlo);
                     probe16<SMEM>(ptab, wlo, whi, mult, nb, m);
-                    {                                              // left window iff (t - 6) <= cut-16
-                        const uint32_t okmask = runs_of_ten(vlo | (vhi << 16)) & (b >= 16 ? 0xFFFFu : (0xFFFFu << (16 - b)));
-                        uint32_t best = 0;
+                    // left window iff (t - 6) <= cut-16: one bit per position, then the first in scan order
+                    uint32_t hm = 0;
 #pragma unroll
-                        for (int o = 15; o >= 0; --o)
-                            if ((m[o] - 6u) <= (uint32_t)(cut - 16) && (okmask & (1u << o)))
-                                best = max(best, ((uint32_t)(b + o) << 12) + m[o]);
-                        if (best) { clj = (int)(best >> 12) + 10; tlj = (int)(best & 0xFFFu) + 10; scanning = false; }
+                    for (int o = 0; o < 16; ++o) hm |= ((m[o] - 6u) <= (uint32_t)(cut - 16)) ? (1u << o) : 0u;
+                    if (hm) hm &= runs_of_ten(vlo | (vhi << 16)) & (b >= 16 ? 0xFFFFu : (0xFFFFu << (16 - b)));
+                    if (hm) {
+                        const int o = 31 - __clz(hm);              // highest position = first going down
+                        uint32_t t = 0;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) t = (q == o) ? m[q] : t;
+                        clj = b + o + 10; tlj = (int)t + 10; scanning = false;
                     }
                     if (scanning) { p = b - 1; if (p < 16) scanning = false; }
                 }
@@ -440,15 +443,19 @@ __global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
                     rc.word16(p + 16, whi, vhi);
                     probe16<SMEM>(ptab, wlo, whi, mult, nb, m);
                     const uint32_t span = (uint32_t)(L - 16 - cut);   // right window iff (t - cut) <= span
-                    {
-                        const int top = plast - p;                 // >= 0
-                        const uint32_t okmask = runs_of_ten(vlo | (vhi << 16)) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
-                        uint32_t best = 0xFFFFFFFFu;
+                    uint32_t hm = 0;                               // right window iff (t - cut) <= span
 #pragma unroll
-                        for (int o = 0; o < 16; ++o)
-                            if ((m[o] - (uint32_t)cut) <= span && (okmask & (1u << o)))
-                                best = min(best, ((uint32_t)(p + o) << 12) + m[o]);
-                        if (best != 0xFFFFFFFFu) { crj = (int)(best >> 12); trj = (int)(best & 0xFFFu); scanning = false; }
+                    for (int o = 0; o < 16; ++o) hm |= ((m[o] - (uint32_t)cut) <= span) ? (1u << o) : 0u;
+                    if (hm) {
+                        const int top = plast - p;                 // >= 0
+                        hm &= runs_of_ten(vlo | (vhi << 16)) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
+                    }
+                    if (hm) {
+                        const int o = __ffs(hm) - 1;               // lowest position = first going up
+                        uint32_t t = 0;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) t = (q == o) ? m[q] : t;
+                        crj = p + o; trj = (int)t; scanning = false;
                     }
                     if (scanning) { p += 16; if (p > plast) scanning = false; }
                 }
