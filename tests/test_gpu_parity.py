@@ -408,3 +408,53 @@ def test_fastq_text_views_path_matches_oracle():
     ref = [(s, v[1], v[0]) for s, d in enumerate(tables) for v in d.values()]
     assert [(int(e["sample"]), int(e["first_idx"]), int(e["count"])) for e in eng.table()] == ref
     eng.close()
+
+
+@pytest.mark.slow
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size (10 M reads, 96 samples, device-resident path): counter identities,
+    table counts add up, first_idx really first, two-shard processing with global indices + table merge
+    equals one pass, verification finds no tag collision, and an oracle spot check on a stride sample."""
+    import torch
+    n = 10_000_000
+    cfg = synth.make_config("C2", n_reads=n, seed=2025)
+    batch = cfg.generate(0, n)
+    pin = synth_problem(cfg)
+    from scarmapper_b200.engine import HostRagged
+    eng = engine_for(pin, cfg.read_len, table_capacity=1 << 22)
+    res = eng.make_resident(HostRagged.from_matrix(batch["seq"]), batch["f0"], batch["f1"])
+    eng.run_resident(res)
+    torch.cuda.synchronize()
+    rec = eng.records_of(res)
+    cnt, un = eng.counters()
+    tab = eng.table()
+    assert eng.verify_resident(res) == 0
+    assert cnt[:, 0].sum() + un == n
+    assert int(tab["count"].sum()) == int(cnt[:, 12].sum()) == int((rec["status"] == orc.ST_SCAR).sum())
+    assert (cnt[:, 1] == cnt[:, 6] + cnt[:, 7] + cnt[:, 11] + cnt[:, 12]).all()
+    firsts = tab["first_idx"].astype(np.int64)
+    assert (rec["status"][firsts] == orc.ST_SCAR).all() and (rec["sample"][firsts] == tab["sample"]).all()
+    assert (np.diff(tab["sample"].astype(np.int64)) >= 0).all()          # sorted by sample, then first_idx
+    # two shards with global indices, exported and merged into one table == one pass (the multi-GPU fold)
+    half = n // 2
+    a = engine_for(pin, cfg.read_len, table_capacity=1 << 22)
+    b = engine_for(pin, cfg.read_len, table_capacity=1 << 22)
+    a.process_host(HostRagged.from_matrix(batch["seq"][:half]), batch["f0"][:half], batch["f1"][:half],
+                   first_index=0, want_records=False)
+    b.process_host(HostRagged.from_matrix(batch["seq"][half:]), batch["f0"][half:], batch["f1"][half:],
+                   first_index=half, want_records=False)
+    buf = torch.empty((b.table_size() + 8, 32), dtype=torch.uint8, device="cuda")
+    nb = b.export_table_dev(buf)
+    a.merge_table_dev(buf, nb)
+    torch.cuda.synchronize()
+    merged = a.table()
+    assert merged.tobytes() == tab.tobytes()
+    a.close(); b.close()
+    # oracle spot check on every 997th read
+    sel = np.arange(0, n, 997)
+    sub = {k: (v[sel] if v is not None else None) for k, v in batch.items()}
+    reads = cfg.reads_as_strings(sub)
+    f0, f1 = cfg.fields_as_strings(sub)
+    want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
+    assert_records_equal(rec[sel], want, reads)
+    eng.close()
