@@ -213,7 +213,10 @@ def main():
     n = args.reads
     first = rank * n
     batch = cfg.generate(first, n)
-    eng = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=1 << 22, **pin), device=local)
+    # scar-table slots: ~1 M patterns per 10 M reads of this spectrum, ~3.7 M after an 8-rank merge; keep the
+    # load factor under 0.5 so that probe sequences stay short during the fold
+    table_capacity = 1 << (22 if world <= 2 else 23)
+    eng = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=table_capacity, **pin), device=local)
 
     # pinned host buffers for the end-to-end arm
     def pinned(a):
@@ -245,10 +248,12 @@ def main():
     engines = [eng]
     dscars = [dscar]
     if world > 1:
-        eng_b = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=1 << 22, **pin), device=local)
+        eng_b = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=table_capacity, **pin), device=local)
         engines.append(eng_b)
         dscars.append(DistributedScar(eng_b, entry_capacity=1 << 21))
     side = torch.cuda.Stream() if world > 1 else None
+    # owner-partitioned merge: a rank sends each peer the entries that peer owns (~1.1 M / world per region)
+    region_capacity = 1 << max(10, int(np.ceil(np.log2(2.2 * 1.1e6 * (n / 1e7) / world + 16))))
     merge_done = [None, None]
     step_no = [0]
 
@@ -304,7 +309,7 @@ def main():
             side.wait_event(computed)
             ms = torch.cuda.Event(enable_timing=True)
             ms.record(side)
-            dscars[k].merge()
+            dscars[k].merge_partitioned(region_capacity=region_capacity)
             me = torch.cuda.Event(enable_timing=True)
             me.record(side)
         merge_done[k] = me
@@ -344,8 +349,12 @@ def main():
     k4 = sum(m[2].elapsed_time(m[3]) for m in marks) / len(marks)
     merge_ms = sum(a.elapsed_time(b) for a, b in merge_marks) / len(merge_marks) if merge_marks else 0.0
     last = engines[(step_no[0] - 1) % len(engines)]
-    n_entries = last.table_size()
+    n_entries = last.table_size()                     # N > 1: the entries this rank owns after the merge
     cnt, un = last.counters()
+    if world > 1:
+        t = torch.tensor([n_entries], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        n_entries = int(t.item())
 
     # end-to-end arm: host buffers -> records on the host, through the public API
     e2e_steps = max(3, min(args.steps, 10))
@@ -353,14 +362,14 @@ def main():
         eng.reset_async()
         eng.process_host(h_seq, h_f0, h_f1, first_index=first, out=rec_out)
         if dscar:
-            dscar.merge()
+            dscar.merge_partitioned(region_capacity=region_capacity)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         eng.reset_async()
         eng.process_host(h_seq, h_f0, h_f1, first_index=first, out=rec_out)
         if dscar:
-            dscar.merge()
+            dscar.merge_partitioned(region_capacity=region_capacity)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -392,10 +401,12 @@ def main():
                        "l2": "inputs_exceed_l2 ({} MB packed rows + {} MB raw per step vs 126 MB L2)".format(
                            n * eng.cells_per_read * 8 // 2 ** 20, n * cfg.read_len // 2 ** 20),
                        "timed_region": "reset, K2 demux, K3 sliding window, K4 aggregation" +
-                                       (", table merge over NCCL every step (side stream, overlapped with the "
-                                        "next step's kernels; the last merges drain inside the timed region)"
+                                       (", owner-partitioned table merge over NCCL all-to-all + accumulator all-reduce every "
+                                        "step (side stream, overlapped with the next step's kernels; the last merge "
+                                        "drains inside the timed region)"
                                         if world > 1 else ""),
-                       "scar_patterns": int(n_entries), "unassigned_reads": int(un)},
+                       "scar_patterns": int(n_entries), "unassigned_reads": int(un),
+                       "table_slots": table_capacity},
             "stages_ms": {"k1_pack": k1_ms, "k2_demux": k2, "k3_window": k3, "k4_aggregate": k4,
                           "merge": merge_ms if world > 1 else 0.0},
             "roofline": {"bound": "hbm", "kernel": "scar_window_kernel (K3)", "achieved": achieved, "peak": peak,

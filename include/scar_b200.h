@@ -152,6 +152,14 @@ int64_t scar_launch_count(const scar_ctx *ctx);
 /* Multi-GPU: export this rank's table, merge another rank's into it (count SUM, first_idx MIN). */
 int scar_table_export_dev(scar_ctx *ctx, scar_entry *entries, int64_t capacity, int64_t *n_entries, void *stream);
 int scar_table_merge_dev(scar_ctx *ctx, const scar_entry *entries, int64_t n_entries, void *stream);
+/* Owner-partitioned merge (cost independent of the GPU count): region o of `regions` ([n_parts][region_capacity]
+ * entries; entry 0 of a region is a header whose h1 is the count) receives this rank's entries owned by rank o
+ * (owner = (h2 >> 40) % n_parts).  Exchange the regions with one all-to-all, scar_table_clear_dev, then fold the
+ * received regions: every rank ends up holding the merged entries it owns.  All three are stream-ordered. */
+int scar_table_export_parts_dev(scar_ctx *ctx, scar_entry *regions, int32_t n_parts, int64_t region_capacity, void *stream);
+int scar_table_clear_dev(scar_ctx *ctx, void *stream);
+int scar_table_merge_parts_dev(scar_ctx *ctx, const scar_entry *regions, int32_t n_parts, int64_t region_capacity, void *stream);
+
 /* Dense accumulators as one int64 block [unassigned, counters[n_samples][16], phase_hist[n_samples][2][34]]
  * for an all-reduce(SUM) across ranks: export to / import from caller-owned device memory. */
 int64_t scar_accumulator_words(const scar_ctx *ctx);

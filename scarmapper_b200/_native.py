@@ -91,6 +91,9 @@ PROTOTYPES = {
     "scar_reset": (C.c_int, [_P]),
     "scar_table_export_dev": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
     "scar_table_merge_dev": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "scar_table_export_parts_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
+    "scar_table_clear_dev": (C.c_int, [_P, _P]),
+    "scar_table_merge_parts_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
     "scar_reset_dev": (C.c_int, [_P, _P]),
     "scar_launch_count": (C.c_int64, [_P]),
     "scar_accumulator_words": (C.c_int64, [_P]),

@@ -551,6 +551,7 @@ static int check_status(scar_ctx *c)
     CU(cudaMemcpy(&st, c->d_status, sizeof(st), cudaMemcpyDeviceToHost));
     if (st & 1) return fail(SCAR_ERR_UNSUPPORTED, "a read is longer than max_read_len=%d", c->max_read_len);
     if (st & 2) return fail(SCAR_ERR_TABLE_FULL, "scar table full (capacity %llu)", (unsigned long long)c->capacity);
+    if (st & 4) return fail(SCAR_ERR_TABLE_FULL, "an export region overflowed (raise region_capacity)");
     return SCAR_OK;
 }
 
@@ -631,6 +632,41 @@ extern "C" int scar_table_merge_dev(scar_ctx *c, const scar_entry *entries, int6
     K4Params P = k4_params(c);
     CU(scar_launch_merge(P, entries, (uint64_t)n, c->sm_count, (cudaStream_t)stream));
     if (n) ++c->launches;
+    return SCAR_OK;
+}
+
+extern "C" int scar_table_export_parts_dev(scar_ctx *c, scar_entry *regions, int32_t n_parts, int64_t region_capacity,
+                                           void *stream)
+{
+    if (!c || !regions || n_parts < 1 || region_capacity < 2) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int g = 0; g < n_parts; ++g)        // headers (count = 0)
+        CU(cudaMemsetAsync(regions + (size_t)g * region_capacity, 0, sizeof(scar_entry), s));
+    CU(scar_launch_export_parts(c->d_slots, c->capacity, regions, (uint32_t)n_parts, (uint64_t)region_capacity,
+                                c->d_status, c->sm_count, s));
+    ++c->launches;
+    return SCAR_OK;
+}
+
+extern "C" int scar_table_clear_dev(scar_ctx *c, void *stream)
+{
+    if (!c) return fail(SCAR_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(c->d_slots, 0, c->capacity * sizeof(ScarTableSlot), s));
+    CU(cudaMemsetAsync(c->d_n_entries, 0, sizeof(unsigned long long), s));
+    return SCAR_OK;
+}
+
+extern "C" int scar_table_merge_parts_dev(scar_ctx *c, const scar_entry *regions, int32_t n_parts, int64_t region_capacity,
+                                          void *stream)
+{
+    if (!c || !regions || n_parts < 1 || region_capacity < 2) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    K4Params P = k4_params(c);
+    CU(scar_launch_merge_parts(P, regions, (uint32_t)n_parts, (uint64_t)region_capacity, c->sm_count, (cudaStream_t)stream));
+    ++c->launches;
     return SCAR_OK;
 }
 

@@ -188,3 +188,7 @@ cudaError_t scar_launch_verify(const K4VerifyParams &P, int sm_count, cudaStream
 cudaError_t scar_launch_export(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint64_t out_capacity,
                                unsigned long long *n_out, int sm_count, cudaStream_t stream);
 cudaError_t scar_launch_merge(const K4Params &P, const scar_entry *in, uint64_t n_in, int sm_count, cudaStream_t stream);
+cudaError_t scar_launch_export_parts(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint32_t n_parts,
+                                     uint64_t region, int32_t *status, int sm_count, cudaStream_t stream);
+cudaError_t scar_launch_merge_parts(const K4Params &P, const scar_entry *in, uint32_t n_parts, uint64_t region,
+                                    int sm_count, cudaStream_t stream);

@@ -266,6 +266,70 @@ __global__ void scar_merge_kernel(K4Params P, const scar_entry *in, uint64_t n_i
     }
 }
 
+// ---- owner-partitioned export / fold (multi-GPU merge whose cost does not grow with the GPU count) -----
+// The table is cut by key ownership: owner = (h2 >> 40) % n_parts.  Region o of the output (capacity
+// `region` entries, entry 0 is a header whose h1 holds the count) receives this rank's entries owned by
+// rank o; the regions are exchanged with one all-to-all and every rank folds what it receives.  The
+// counts travel in band, so the whole merge is stream-ordered: no host synchronisation.
+__global__ void scar_export_parts_kernel(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out,
+                                         uint32_t n_parts, uint64_t region, int32_t *status)
+{
+    const uint64_t n_round = (capacity + 31) & ~(uint64_t)31;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        ScarTableSlot s;
+        s.tag = 0;
+        if (i < capacity) s = slots[i];
+        if (s.tag == 0) continue;
+        const uint64_t h2 = (uint64_t)(s.tag >> 64);
+        const uint32_t owner = (uint32_t)(h2 >> 40) % n_parts;
+        scar_entry *reg = out + (uint64_t)owner * region;
+        const unsigned long long pos = 1ull + atomicAdd(reinterpret_cast<unsigned long long *>(&reg->h1), 1ull);
+        if (pos < region) {
+            scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = h2; e.first_idx = ~s.inv_first; e.count = s.count;
+            e.sample = (uint16_t)s.sample; e.pad = 0;
+            reg[pos] = e;
+        } else atomicOr(status, 4);
+    }
+}
+
+__global__ void scar_merge_parts_kernel(K4Params P, const scar_entry *in, uint32_t n_parts, uint64_t region)
+{
+    __shared__ unsigned int s_new;
+    if (threadIdx.x == 0) s_new = 0;
+    __syncthreads();
+    for (uint32_t g = 0; g < n_parts; ++g) {
+        const scar_entry *reg = in + (uint64_t)g * region;
+        uint64_t cnt = reg->h1;
+        if (cnt > region - 1) cnt = region - 1;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt;
+             i += (uint64_t)gridDim.x * blockDim.x) {
+            const scar_entry e = reg[1 + i];
+            if (table_insert(P, e.h1, e.h2, e.count, e.first_idx, e.sample)) atomicAdd(&s_new, 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_new) atomicAdd(P.n_entries, (unsigned long long)s_new);
+}
+
+cudaError_t scar_launch_export_parts(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint32_t n_parts,
+                                     uint64_t region, int32_t *status, int sm_count, cudaStream_t stream)
+{
+    const int threads = 256;
+    int64_t blocks = (int64_t)((capacity + threads - 1) / threads);
+    const int64_t cap = (int64_t)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    scar_export_parts_kernel<<<(unsigned)blocks, threads, 0, stream>>>(slots, capacity, out, n_parts, region, status);
+    return cudaGetLastError();
+}
+
+cudaError_t scar_launch_merge_parts(const K4Params &P, const scar_entry *in, uint32_t n_parts, uint64_t region,
+                                    int sm_count, cudaStream_t stream)
+{
+    scar_merge_parts_kernel<<<(unsigned)(sm_count * 8), 256, 0, stream>>>(P, in, n_parts, region);
+    return cudaGetLastError();
+}
+
 cudaError_t scar_launch_aggregate(K4Params P, int sm_count, cudaStream_t stream, int *launches)
 {
     if (P.n_reads <= 0) return cudaSuccess;

@@ -71,6 +71,32 @@ def reduce_accumulators(export_fn, import_fn, words: int, device, group=None):
     return buf
 
 
+def exchange_regions(send: torch.Tensor, recv: torch.Tensor, group=None):
+    """Region o of `send` goes to rank o; region g of `recv` comes from rank g.  One all-to-all on NCCL; on
+    backends without it (gloo, CPU tests) the same exchange is spelled with an all-gather."""
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv, send, group=group)
+        return
+    rank = dist.get_rank(group)
+    per = send.shape[0] // world
+    everything = torch.empty((world * send.shape[0],) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    dist.all_gather_into_tensor(everything, send.contiguous(), group=group)
+    for g in range(world):
+        src = everything[g * send.shape[0] + rank * per: g * send.shape[0] + (rank + 1) * per]
+        recv[g * per:(g + 1) * per] = src
+
+
+def merge_tables_partitioned(export_parts_fn, clear_fn, merge_parts_fn, send: torch.Tensor, recv: torch.Tensor, group=None):
+    """Owner-partitioned merge: every rank ends up with the merged entries it owns.  Stream-ordered, no host
+    synchronisation: the per-region counts travel inside the regions."""
+    world = dist.get_world_size(group)
+    export_parts_fn(send, world)
+    exchange_regions(send, recv, group)
+    clear_fn()
+    merge_parts_fn(recv, world)
+
+
 class DistributedScar:
     """Glue between a ScarEngine and the process group."""
 
@@ -79,6 +105,20 @@ class DistributedScar:
         self.group = group
         self.device = torch.device("cuda", engine.device)
         self.entry_buf = torch.empty((entry_capacity, 32), dtype=torch.uint8, device=self.device)
+        self._send = self._recv = None
+
+    def merge_partitioned(self, region_capacity: int = 1 << 18):
+        """Owner-partitioned merge (cost independent of the GPU count): afterwards this rank's table holds the
+        merged entries whose key it owns; the dense accumulators are all-reduced.  Fully asynchronous."""
+        e = self.engine
+        world = dist.get_world_size(self.group)
+        if self._send is None or self._send.shape[0] != world * region_capacity:
+            self._send = torch.empty((world * region_capacity, 32), dtype=torch.uint8, device=self.device)
+            self._recv = torch.empty_like(self._send)
+        merge_tables_partitioned(e.export_parts_dev, e.clear_table_dev, e.merge_parts_dev, self._send, self._recv,
+                                 self.group)
+        reduce_accumulators(e.export_accumulators_dev, e.import_accumulators_dev, e.accumulator_words(),
+                            self.device, self.group)
 
     def merge(self):
         e = self.engine

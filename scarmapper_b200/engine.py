@@ -300,6 +300,18 @@ class ScarEngine:
         """Merge `n` foreign entries (count SUM, first_idx MIN) into this rank's table."""
         N.check(self._L.scar_table_merge_dev(self._ctx, buf.data_ptr(), int(n), self._stream()))
 
+    def export_parts_dev(self, regions, n_parts: int):
+        """Owner-partitioned export into `regions` (torch uint8 [n_parts * region_capacity, 32])."""
+        N.check(self._L.scar_table_export_parts_dev(self._ctx, regions.data_ptr(), n_parts, regions.shape[0] // n_parts,
+                                                    self._stream()))
+
+    def clear_table_dev(self):
+        N.check(self._L.scar_table_clear_dev(self._ctx, self._stream()))
+
+    def merge_parts_dev(self, regions, n_parts: int):
+        N.check(self._L.scar_table_merge_parts_dev(self._ctx, regions.data_ptr(), n_parts, regions.shape[0] // n_parts,
+                                                   self._stream()))
+
     def accumulator_words(self) -> int:
         return int(self._L.scar_accumulator_words(self._ctx))
 

@@ -57,6 +57,29 @@ class NumpyTable:
         buf[:raw.shape[0]] = raw
         return raw.shape[0]
 
+    def export_parts(self, regions, n_parts):
+        per = regions.shape[0] // n_parts
+        regions.zero_()
+        parts = [[] for _ in range(n_parts)]
+        for (h1, h2), (c, f, s) in sorted(self.d.items()):
+            parts[(h2 >> 40) % n_parts].append((h1, h2, f, c, s, 0))
+        for o, rows in enumerate(parts):
+            arr = np.zeros(per, dtype=ENTRY)
+            arr[0]["h1"] = len(rows)
+            if rows:
+                arr[1:1 + len(rows)] = np.array(rows, dtype=ENTRY)
+            regions[o * per:(o + 1) * per] = torch.from_numpy(arr.view(np.uint8).reshape(-1, 32).copy())
+
+    def clear(self):
+        self.d = {}
+
+    def merge_parts(self, regions, n_parts):
+        per = regions.shape[0] // n_parts
+        for g in range(n_parts):
+            arr = regions[g * per:(g + 1) * per].contiguous().numpy().reshape(-1).view(ENTRY)
+            for e in arr[1:1 + int(arr[0]["h1"])]:
+                self.insert(int(e["h1"]), int(e["h2"]), int(e["count"]), int(e["first_idx"]), int(e["sample"]))
+
     def merge(self, buf, n):
         arr = buf[:n].contiguous().numpy().reshape(-1).view(ENTRY)
         for e in arr:
@@ -65,16 +88,17 @@ class NumpyTable:
 
 def worker(rank, world, port, n_total, out_dir):
     sys.path.insert(0, ROOT)
-    from scarmapper_b200.distributed import merge_tables, reduce_accumulators, shard_bounds
+    from scarmapper_b200.distributed import merge_tables, merge_tables_partitioned, reduce_accumulators, shard_bounds
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     keys, samples = synthetic_keys(n_total, 5)
     b = shard_bounds(n_total, world)
-    tab = NumpyTable()
+    tab, tab2 = NumpyTable(), NumpyTable()
     acc = np.zeros(1 + 7 * 16, dtype=np.int64)
     for r in range(b[rank], b[rank + 1]):                 # GLOBAL read indices
-        tab.insert(int(keys[r]), int(keys[r]) * 31 + 7, 1, r, int(samples[r]))
+        tab.insert(int(keys[r]), (int(keys[r]) * 0x9E3779B97F4A7C15) & (2 ** 64 - 1), 1, r, int(samples[r]))
+        tab2.insert(int(keys[r]), (int(keys[r]) * 0x9E3779B97F4A7C15) & (2 ** 64 - 1), 1, r, int(samples[r]))
         acc[1 + int(samples[r]) * 16] += 1
     acc[0] = rank + 1
     buf = torch.zeros((1024, 32), dtype=torch.uint8)
@@ -88,6 +112,12 @@ def worker(rank, world, port, n_total, out_dir):
         holder["acc"] = t.numpy().copy()
 
     reduce_accumulators(exp, imp, acc.size, torch.device("cpu"))
+    # owner-partitioned merge on a second copy: the union over ranks must be the same table, disjointly
+    send = torch.zeros((world * 512, 32), dtype=torch.uint8)
+    recv = torch.zeros_like(send)
+    merge_tables_partitioned(tab2.export_parts, tab2.clear, tab2.merge_parts, send, recv)
+    part = sorted((k[0], v[0], v[1], v[2]) for k, v in tab2.d.items())
+    np.save(os.path.join(out_dir, "part{}.npy".format(rank)), np.array(part, dtype=np.int64).reshape(-1, 4))
     final = sorted((k[0], v[0], v[1], v[2]) for k, v in tab.d.items())
     np.save(os.path.join(out_dir, "rank{}.npy".format(rank)), np.array(final, dtype=np.int64))
     np.save(os.path.join(out_dir, "acc{}.npy".format(rank)), holder["acc"])
@@ -116,3 +146,6 @@ def test_merge_over_gloo_equals_single_process(tmp_path, world):
         assert acc[1:].reshape(7, 16)[:, 0].sum() == n_total
         counts = np.load(tmp_path / "counts{}.npy".format(rank))
         assert len(counts) == world and counts.sum() >= len(ref)
+    parts = np.concatenate([np.load(tmp_path / "part{}.npy".format(r)) for r in range(world)])
+    assert len(parts) == len(want)                       # ownership is a partition: no key on two ranks
+    assert (parts[np.argsort(parts[:, 0])] == want).all()

@@ -458,3 +458,19 @@ def test_full_size_properties_config2():
     want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
     assert_records_equal(rec[sel], want, reads)
     eng.close()
+
+
+def test_multi_gpu_merges_match_single_gpu():
+    """Both table merges under real NCCL (needs >= 2 GPUs; skipped on a one-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
