@@ -47,6 +47,8 @@ enum { SCAR_PLATFORM_ILLUMINA = 0, SCAR_PLATFORM_TRUSEQ = 1, SCAR_PLATFORM_RAMSD
  *           non-decreasing (fields inside a FASTQ text buffer, see scar_fastq_index)
  *   stride  offsets == NULL: item i starts at i*stride and is lengths[i] long, or `stride` long when
  *           lengths == NULL. */
+/* DEVICE buffers handed to the _dev entry points must be readable for 16 bytes past the last item (the kernels
+ * use aligned 4/8-byte loads that may straddle the end of an item). */
 typedef struct scar_ragged {
     const uint8_t *bytes;
     const int64_t *offsets;

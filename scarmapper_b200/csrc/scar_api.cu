@@ -520,6 +520,10 @@ static K4Params k4_params(scar_ctx *c)
     P.slots = c->d_slots; P.slot_mask = c->capacity - 1; P.n_entries = c->d_n_entries; P.counters = c->d_counters;
     P.unassigned = c->d_unassigned; P.phase_hist = c->d_phase_hist; P.status = c->d_status; P.n_samples = c->n_samples;
     P.platform = c->platform; P.max_probe = (uint32_t)std::min<uint64_t>(c->capacity - 1, 1u << 16);
+    int max_phase = 0;
+    for (const auto &m : c->h_targets) max_phase = std::max(max_phase, (int)m.n_phase);
+    const int pb = max_phase + 2;                 // bins: none, 0..max_phase-1, n/a
+    P.phase_joint = pb * pb <= 128 ? pb : 0;
     return P;
 }
 

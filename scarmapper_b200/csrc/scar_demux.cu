@@ -24,6 +24,14 @@
 __device__ __forceinline__ void encode16(const uint8_t *u, int n, uint32_t &code, uint32_t &valid)
 {
     const uintptr_t a = (uintptr_t)u, a0 = a & ~(uintptr_t)3;
+    if (n == 8 && (a & 7) == 0) {                 // the usual Illumina field: one aligned 8-byte load
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a));
+        uint32_t c8, v4, n4, c8b, v4b;
+        classify4(v.x, c8, v4, n4);
+        classify4(v.y, c8b, v4b, n4);
+        code = c8 | (c8b << 8); valid = v4 | (v4b << 4);
+        return;
+    }
     const uint32_t sh = (uint32_t)(a & 3) * 8;
     uint32_t w[5];
 #pragma unroll
@@ -59,6 +67,7 @@ __global__ void __launch_bounds__(256) scar_demux_kernel(const K2Params P)
     __shared__ uint8_t cmap[256];
     __shared__ uint32_t s_code[2][64];     // 2-bit codes of the distinct index strings (FAST)
     __shared__ int32_t s_len[2][64];
+    __shared__ unsigned long long s_lenmask[2][17];   // bit d set: string d of that side is n nt long (FAST)
     for (int i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = P.class_map[i];
     for (int i = threadIdx.x; i < P.n_right + P.n_left; i += blockDim.x) {
         const int side = i >= P.n_right, d = side ? i - P.n_right : i;
@@ -67,6 +76,13 @@ __global__ void __launch_bounds__(256) scar_demux_kernel(const K2Params P)
         uint32_t c = 0;    // class ids 1..4 were assigned in order of first appearance; re-encode to 2-bit base codes
         if (FAST) for (int k = 0; k < ds.len; ++k) c |= (uint32_t)P.fast_codes[(side ? P.n_right : 0) * 16 + d * 16 + k] << (2 * k);
         s_code[side][d] = c;
+    }
+    __syncthreads();
+    if (FAST && threadIdx.x < 34) {
+        const int side = threadIdx.x / 17, n = threadIdx.x % 17, cnt = side ? P.n_left : P.n_right;
+        unsigned long long m = 0;
+        for (int q = 0; q < cnt; ++q) m |= (unsigned long long)(s_len[side][q] == n) << q;
+        s_lenmask[side][n] = m;
     }
     __syncthreads();
     const int thr = P.mismatch;
@@ -100,27 +116,35 @@ __global__ void __launch_bounds__(256) scar_demux_kernel(const K2Params P)
         if (FAST && !ramsden) {
             // equal lengths: 2-bit Hamming decides (exact for t <= 1; for t > 1 a miss goes to the slow list);
             // other lengths go to the slow list (quick reject / bit-vector edit distance)
-            uint64_t slow = 0;
+            // bit d of `hit`: Hamming(u, string d) <= t over the first 16 positions; strings of another length
+            // are masked out with the per-length bit mask and go to the slow list
+            const uint64_t all_r = P.n_right >= 64 ? ~0ull : ((1ull << P.n_right) - 1ull);
+            uint32_t hit_lo = 0, hit_hi = 0;
             for (int d = 0; d < P.n_right; ++d) {
                 const uint32_t x = e0 ^ s_code[0][d];
-                const bool hit = __popc(((x | (x >> 1)) & 0x55555555u) | x0) <= thr;
-                const bool eq = s_len[0][d] == n0 && n0 <= 16;
-                ok_r |= (uint64_t)(eq && hit) << d;
-                slow |= (uint64_t)(!eq || (!hit && thr > 1)) << d;
+                const uint32_t h = __popc(((x | (x >> 1)) & 0x55555555u) | x0) <= thr ? 1u : 0u;
+                if (d < 32) hit_lo |= h << d; else hit_hi |= h << (d - 32);
             }
+            uint64_t hit = ((uint64_t)hit_hi << 32) | hit_lo;
+            uint64_t eq = n0 <= 16 ? s_lenmask[0][n0] : 0ull;
+            ok_r = hit & eq;
+            uint64_t slow = all_r & (~eq | (thr > 1 ? ~hit : 0ull));
             for (uint64_t a = slow; a; a &= a - 1) {
                 const int d = __ffsll((long long)a) - 1;
                 if (accepts(P.right[d], P.peq, u0, n0, c0, cmap, thr, false)) ok_r |= 1ull << d;
             }
             if (ok_r) {
-                slow = 0;
+                const uint64_t all_l = P.n_left >= 64 ? ~0ull : ((1ull << P.n_left) - 1ull);
+                hit_lo = hit_hi = 0;
                 for (int d = 0; d < P.n_left; ++d) {
                     const uint32_t x = e1 ^ s_code[1][d];
-                    const bool hit = __popc(((x | (x >> 1)) & 0x55555555u) | x1) <= thr;
-                    const bool eq = s_len[1][d] == n1 && n1 <= 16;
-                    ok_l |= (uint64_t)(eq && hit) << d;
-                    slow |= (uint64_t)(!eq || (!hit && thr > 1)) << d;
+                    const uint32_t h = __popc(((x | (x >> 1)) & 0x55555555u) | x1) <= thr ? 1u : 0u;
+                    if (d < 32) hit_lo |= h << d; else hit_hi |= h << (d - 32);
                 }
+                hit = ((uint64_t)hit_hi << 32) | hit_lo;
+                eq = n1 <= 16 ? s_lenmask[1][n1] : 0ull;
+                ok_l = hit & eq;
+                slow = all_l & (~eq | (thr > 1 ? ~hit : 0ull));
                 for (uint64_t a = slow; a; a &= a - 1) {
                     const int d = __ffsll((long long)a) - 1;
                     if (accepts(P.left[d], P.peq, u1, n1, c1, cmap, thr, false)) ok_l |= 1ull << d;

@@ -169,6 +169,8 @@ struct K4Params {
     int32_t platform;
     int32_t use_smem;            // counters + phase histograms staged in shared memory
     uint32_t max_probe;
+    int32_t phase_joint;         // PB > 0: joint [PB][PB] phase histogram in shared memory (PB = max phases + 2)
+    int32_t pad;
 };
 
 struct K4VerifyParams {

@@ -50,7 +50,18 @@ __device__ __forceinline__ void key_hashes(const scar_record &rec, const uint8_t
     for (int q = lo; q < hi; q += 8) {
         uint64_t w = 0;
         const int n = min(8, hi - q);
-        for (int k = 0; k < n; ++k) w |= (uint64_t)stored_byte(raw, rawlen, platform, q + k) << (8 * k);
+        if (platform != SCAR_PLATFORM_RAMSDEN) {
+            // eight segment bytes with two aligned 8-byte loads (every raw buffer is padded by >= 16 bytes)
+            const uintptr_t a = (uintptr_t)(raw + q + (platform == SCAR_PLATFORM_TRUSEQ ? 6 : 0));
+            const uintptr_t a0 = a & ~(uintptr_t)7;
+            const uint32_t sh = (uint32_t)(a & 7) * 8;
+            const uint64_t lo8 = __ldg(reinterpret_cast<const unsigned long long *>(a0));
+            const uint64_t hi8 = sh ? __ldg(reinterpret_cast<const unsigned long long *>(a0 + 8)) : 0ull;
+            w = sh ? ((lo8 >> sh) | (hi8 << (64 - sh))) : lo8;
+            if (n < 8) w &= (1ull << (8 * n)) - 1ull;
+        } else {
+            for (int k = 0; k < n; ++k) w |= (uint64_t)stored_byte(raw, rawlen, platform, q + k) << (8 * k);
+        }
         h1 = scar_mix1(h1 ^ w);
         h2 = scar_mix2(h2 + w * 0xA24BAED4963EE407ull + 1ull);
     }
@@ -101,19 +112,67 @@ __device__ __forceinline__ int table_insert(const K4Params &P, uint64_t h1, uint
     return 0;
 }
 
+// Shared-memory accumulators of one sample (32-bit words): six words of two 16-bit counters each (one
+// atomic bumps two counters; a CTA flushes before any field can reach 2^16), HR_MORE, and
+// the phase bins: a joint [PB][PB] histogram of (phase_r1, phase_r2) when PB*PB <= 128 (one atomic per
+// read instead of two), else two [SCAR_PHASE_BINS] marginals.
+//   word A: ASSIGNED | PASSING << 16 | FILTERED << 32 | NO_JUNCTION << 48
+//   word B: NO_CUT | N_INSERTION << 16 | SCAR << 32 | LEFT_DEL << 48
+//   word C: RIGHT_DEL | INSERTION << 16 | MICROHOM << 32 | HR_FIRST << 48
+#define K4_FIXED_WORDS 8
+#define K4_EPOCH_ITERS 255          // 255 x 256 threads < 65536 reads per CTA between flushes
+
+__device__ __forceinline__ void k4_flush(const K4Params &P, unsigned int *s_hist, int per_sample, int pb)
+{
+    static const int fieldA[4] = {SCAR_CT_ASSIGNED, SCAR_CT_PASSING, SCAR_CT_FILTERED, SCAR_CT_NO_JUNCTION};
+    static const int fieldB[4] = {SCAR_CT_NO_CUT, SCAR_CT_N_INSERTION, SCAR_CT_SCAR, SCAR_CT_LEFT_DEL};
+    static const int fieldC[4] = {SCAR_CT_RIGHT_DEL, SCAR_CT_INSERTION, SCAR_CT_MICROHOM, SCAR_CT_HR_FIRST};
+    for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) {
+        const unsigned int v = s_hist[i];
+        if (!v) continue;
+        s_hist[i] = 0;
+        const int s = i / per_sample, c = i - s * per_sample;
+        unsigned long long *cnt = P.counters + (size_t)s * SCAR_N_COUNTERS;
+        unsigned long long *ph = P.phase_hist + (size_t)s * 2 * SCAR_PHASE_BINS;
+        if (c < 6) {                                   // half of a packed 64-bit word: two 16-bit fields
+            const int *f = c < 2 ? fieldA : (c < 4 ? fieldB : fieldC);
+            const int k = (c & 1) * 2;
+            if (v & 0xFFFFu) atomicAdd(cnt + f[k], (unsigned long long)(v & 0xFFFFu));
+            if (v >> 16) atomicAdd(cnt + f[k + 1], (unsigned long long)(v >> 16));
+        } else if (c == 6) {
+            atomicAdd(cnt + SCAR_CT_HR_MORE, (unsigned long long)v);
+        } else if (c >= K4_FIXED_WORDS) {
+            const int b = c - K4_FIXED_WORDS;
+            if (pb) {                                  // joint bin (b1, b2): NA is the last joint index
+                const int b1 = b / pb, b2 = b - b1 * pb;
+                atomicAdd(ph + (b1 == pb - 1 ? SCAR_PHASE_BINS - 1 : b1), (unsigned long long)v);
+                atomicAdd(ph + SCAR_PHASE_BINS + (b2 == pb - 1 ? SCAR_PHASE_BINS - 1 : b2), (unsigned long long)v);
+            } else atomicAdd(ph + b, (unsigned long long)v);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
 {
-    extern __shared__ unsigned int s_hist[];   // [n_samples][SCAR_N_COUNTERS + 2*SCAR_PHASE_BINS] when use_smem
-    const int per_sample = SCAR_N_COUNTERS + 2 * SCAR_PHASE_BINS;
+    extern __shared__ __align__(8) unsigned int s_hist[];
+    const int pb = P.phase_joint;                       // 0: separate marginals
+    const int per_sample = K4_FIXED_WORDS + (pb ? pb * pb : 2 * SCAR_PHASE_BINS);
     __shared__ unsigned int s_unassigned, s_new;
     if (P.use_smem) {
         for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) s_hist[i] = 0;
     }
     if (threadIdx.x == 0) { s_unassigned = 0; s_new = 0; }
     __syncthreads();
-    const int64_t n_round = (P.n_reads + 31) & ~(int64_t)31;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_round;
-         r += (int64_t)gridDim.x * blockDim.x) {
+    int iter = 0;
+    // the trip count is the same for every thread of a CTA (the epoch flush below is a CTA barrier)
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < P.n_reads; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = base + threadIdx.x;
+        if (P.use_smem && ++iter > K4_EPOCH_ITERS) {
+            __syncthreads();
+            k4_flush(P, s_hist, per_sample, pb);
+            __syncthreads();
+            iter = 1;
+        }
         const bool in_range = r < P.n_reads;
         __align__(16) scar_record rec;
         if (in_range) *reinterpret_cast<uint4 *>(&rec) = __ldg(reinterpret_cast<const uint4 *>(P.records + r));
@@ -124,32 +183,58 @@ __global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
             if (rec.status == SCAR_ST_UNASSIGNED) atomicAdd(&s_unassigned, 1u);
             else {
                 const uint32_t s = rec.sample;
-                uint32_t inc = 1u << SCAR_CT_ASSIGNED;
-                if (rec.status >= SCAR_ST_NO_JUNCTION) inc |= 1u << SCAR_CT_PASSING;
-                if (rec.status == SCAR_ST_FILTERED) inc |= 1u << SCAR_CT_FILTERED;
-                if (rec.status == SCAR_ST_NO_JUNCTION) inc |= 1u << SCAR_CT_NO_JUNCTION;
-                if (rec.status == SCAR_ST_NO_CUT) inc |= 1u << SCAR_CT_NO_CUT;
-                if (rec.status == SCAR_ST_N_INSERTION) inc |= 1u << SCAR_CT_N_INSERTION;
-                if (rec.status == SCAR_ST_SCAR) {
-                    inc |= 1u << SCAR_CT_SCAR;
-                    if (rec.flags & SCAR_FL_LEFT_DEL) inc |= 1u << SCAR_CT_LEFT_DEL;
-                    if (rec.flags & SCAR_FL_RIGHT_DEL) inc |= 1u << SCAR_CT_RIGHT_DEL;
-                    if (rec.flags & SCAR_FL_INSERTION) inc |= 1u << SCAR_CT_INSERTION;
-                    if (rec.flags & SCAR_FL_MICROHOM) inc |= 1u << SCAR_CT_MICROHOM;
-                }
-                if (rec.hr_n) inc |= 1u << SCAR_CT_HR_FIRST;
+                const bool scar = rec.status == SCAR_ST_SCAR;
                 const int b1 = rec.phase_r1 == SCAR_PHASE_NA ? SCAR_PHASE_BINS - 1 : rec.phase_r1 + 1;
                 const int b2 = rec.phase_r2 == SCAR_PHASE_NA ? SCAR_PHASE_BINS - 1 : rec.phase_r2 + 1;
                 if (P.use_smem) {
+                    unsigned long long a = 1ull, b = 0ull, c = 0ull;
+                    if (rec.status >= SCAR_ST_NO_JUNCTION) a |= 1ull << 16;
+                    if (rec.status == SCAR_ST_FILTERED) a |= 1ull << 32;
+                    if (rec.status == SCAR_ST_NO_JUNCTION) a |= 1ull << 48;
+                    if (rec.status == SCAR_ST_NO_CUT) b |= 1ull;
+                    if (rec.status == SCAR_ST_N_INSERTION) b |= 1ull << 16;
+                    if (scar) {
+                        b |= 1ull << 32;
+                        if (rec.flags & SCAR_FL_LEFT_DEL) b |= 1ull << 48;
+                        if (rec.flags & SCAR_FL_RIGHT_DEL) c |= 1ull;
+                        if (rec.flags & SCAR_FL_INSERTION) c |= 1ull << 16;
+                        if (rec.flags & SCAR_FL_MICROHOM) c |= 1ull << 32;
+                    }
+                    if (rec.hr_n) c |= 1ull << 48;
+                    // 32-bit shared atomics (two 16-bit counters each); 64-bit shared atomics are a CAS loop
                     unsigned int *h = s_hist + s * per_sample;
-                    for (uint32_t m = inc; m; m &= m - 1) atomicAdd(h + (__ffs(m) - 1), 1u);
-                    if (rec.hr_n > 1) atomicAdd(h + SCAR_CT_HR_MORE, (unsigned)(rec.hr_n - 1));
-                    atomicAdd(h + SCAR_N_COUNTERS + b1, 1u);
-                    atomicAdd(h + SCAR_N_COUNTERS + SCAR_PHASE_BINS + b2, 1u);
+                    atomicAdd(h, (unsigned int)a);
+                    if (a >> 32) atomicAdd(h + 1, (unsigned int)(a >> 32));
+                    if ((unsigned int)b) atomicAdd(h + 2, (unsigned int)b);
+                    if (b >> 32) atomicAdd(h + 3, (unsigned int)(b >> 32));
+                    if ((unsigned int)c) atomicAdd(h + 4, (unsigned int)c);
+                    if (c >> 32) atomicAdd(h + 5, (unsigned int)(c >> 32));
+                    if (rec.hr_n > 1) atomicAdd(h + 6, (unsigned)(rec.hr_n - 1));
+                    if (pb) {
+                        const int j1 = b1 == SCAR_PHASE_BINS - 1 ? pb - 1 : b1, j2 = b2 == SCAR_PHASE_BINS - 1 ? pb - 1 : b2;
+                        atomicAdd(h + K4_FIXED_WORDS + j1 * pb + j2, 1u);
+                    } else {
+                        atomicAdd(h + K4_FIXED_WORDS + b1, 1u);
+                        atomicAdd(h + K4_FIXED_WORDS + SCAR_PHASE_BINS + b2, 1u);
+                    }
                 } else {
-                    unsigned long long *c = P.counters + (size_t)s * SCAR_N_COUNTERS;
-                    for (uint32_t m = inc; m; m &= m - 1) atomicAdd(c + (__ffs(m) - 1), 1ull);
-                    if (rec.hr_n > 1) atomicAdd(c + SCAR_CT_HR_MORE, (unsigned long long)(rec.hr_n - 1));
+                    uint32_t inc = 1u << SCAR_CT_ASSIGNED;
+                    if (rec.status >= SCAR_ST_NO_JUNCTION) inc |= 1u << SCAR_CT_PASSING;
+                    if (rec.status == SCAR_ST_FILTERED) inc |= 1u << SCAR_CT_FILTERED;
+                    if (rec.status == SCAR_ST_NO_JUNCTION) inc |= 1u << SCAR_CT_NO_JUNCTION;
+                    if (rec.status == SCAR_ST_NO_CUT) inc |= 1u << SCAR_CT_NO_CUT;
+                    if (rec.status == SCAR_ST_N_INSERTION) inc |= 1u << SCAR_CT_N_INSERTION;
+                    if (scar) {
+                        inc |= 1u << SCAR_CT_SCAR;
+                        if (rec.flags & SCAR_FL_LEFT_DEL) inc |= 1u << SCAR_CT_LEFT_DEL;
+                        if (rec.flags & SCAR_FL_RIGHT_DEL) inc |= 1u << SCAR_CT_RIGHT_DEL;
+                        if (rec.flags & SCAR_FL_INSERTION) inc |= 1u << SCAR_CT_INSERTION;
+                        if (rec.flags & SCAR_FL_MICROHOM) inc |= 1u << SCAR_CT_MICROHOM;
+                    }
+                    if (rec.hr_n) inc |= 1u << SCAR_CT_HR_FIRST;
+                    unsigned long long *cnt = P.counters + (size_t)s * SCAR_N_COUNTERS;
+                    for (uint32_t m = inc; m; m &= m - 1) atomicAdd(cnt + (__ffs(m) - 1), 1ull);
+                    if (rec.hr_n > 1) atomicAdd(cnt + SCAR_CT_HR_MORE, (unsigned long long)(rec.hr_n - 1));
                     unsigned long long *ph = P.phase_hist + (size_t)s * 2 * SCAR_PHASE_BINS;
                     atomicAdd(ph + b1, 1ull);
                     atomicAdd(ph + SCAR_PHASE_BINS + b2, 1ull);
@@ -169,15 +254,7 @@ __global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
         }
     }
     __syncthreads();
-    if (P.use_smem) {
-        for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) {
-            const unsigned int v = s_hist[i];
-            if (!v) continue;
-            const int s = i / per_sample, c = i - s * per_sample;
-            if (c < SCAR_N_COUNTERS) atomicAdd(P.counters + (size_t)s * SCAR_N_COUNTERS + c, (unsigned long long)v);
-            else atomicAdd(P.phase_hist + (size_t)s * 2 * SCAR_PHASE_BINS + (c - SCAR_N_COUNTERS), (unsigned long long)v);
-        }
-    }
+    if (P.use_smem) k4_flush(P, s_hist, per_sample, pb);
     if (threadIdx.x == 0 && s_unassigned) atomicAdd(P.unassigned, (unsigned long long)s_unassigned);
     if (threadIdx.x == 0 && s_new) atomicAdd(P.n_entries, (unsigned long long)s_new);
 }
@@ -334,7 +411,8 @@ cudaError_t scar_launch_aggregate(K4Params P, int sm_count, cudaStream_t stream,
 {
     if (P.n_reads <= 0) return cudaSuccess;
     const int threads = 256;
-    const size_t per_sample = (SCAR_N_COUNTERS + 2 * SCAR_PHASE_BINS) * sizeof(unsigned int);
+    const int pb = P.phase_joint;
+    const size_t per_sample = (K4_FIXED_WORDS + (pb ? pb * pb : 2 * SCAR_PHASE_BINS)) * sizeof(unsigned int);
     size_t smem = (size_t)P.n_samples * per_sample;
     P.use_smem = smem <= 96 * 1024;
     if (!P.use_smem) smem = 0;
