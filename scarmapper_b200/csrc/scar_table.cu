@@ -352,21 +352,35 @@ __global__ void scar_export_parts_kernel(const ScarTableSlot *slots, uint64_t ca
                                          uint32_t n_parts, uint64_t region, int32_t *status)
 {
     const uint64_t n_round = (capacity + 31) & ~(uint64_t)31;
+    const int lane = threadIdx.x & 31;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
          i += (uint64_t)gridDim.x * blockDim.x) {
         ScarTableSlot s;
         s.tag = 0;
         if (i < capacity) s = slots[i];
-        if (s.tag == 0) continue;
+        const bool used = s.tag != 0;
+        if (!__any_sync(0xFFFFFFFFu, used)) continue;
         const uint64_t h2 = (uint64_t)(s.tag >> 64);
-        const uint32_t owner = (uint32_t)(h2 >> 40) % n_parts;
-        scar_entry *reg = out + (uint64_t)owner * region;
-        const unsigned long long pos = 1ull + atomicAdd(reinterpret_cast<unsigned long long *>(&reg->h1), 1ull);
-        if (pos < region) {
-            scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = h2; e.first_idx = ~s.inv_first; e.count = s.count;
-            e.sample = (uint16_t)s.sample; e.pad = 0;
-            reg[pos] = e;
-        } else atomicOr(status, 4);
+        const uint32_t owner = used ? (uint32_t)(h2 >> 40) % n_parts : 0xFFFFFFFFu;
+        // one atomic per (warp, owner): the region cursors are only n_parts addresses
+        unsigned long long pos = 0;
+        for (uint32_t o = 0; o < n_parts; ++o) {
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, owner == o);
+            if (!bal) continue;
+            unsigned long long base = 0;
+            if (lane == __ffs(bal) - 1)
+                base = atomicAdd(reinterpret_cast<unsigned long long *>(&out[(uint64_t)o * region].h1),
+                                 (unsigned long long)__popc(bal));
+            base = __shfl_sync(0xFFFFFFFFu, base, __ffs(bal) - 1);
+            if (owner == o) pos = 1ull + base + __popc(bal & ((1u << lane) - 1u));
+        }
+        if (used) {
+            if (pos < region) {
+                scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = h2; e.first_idx = ~s.inv_first; e.count = s.count;
+                e.sample = (uint16_t)s.sample; e.pad = 0;
+                out[(uint64_t)owner * region + pos] = e;
+            } else atomicOr(status, 4);
+        }
     }
 }
 

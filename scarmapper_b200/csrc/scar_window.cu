@@ -16,6 +16,8 @@
 //
 //   left  search: positions p = len-20 .. 16 descending, first hit -> clj = p+10, tlj = cut - i
 //   right search: positions p = 10 .. len-26 ascending,  first hit -> crj = p,    trj = cut + i
+#include <cstdlib>
+
 #include "scar_internal.cuh"
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -617,6 +619,7 @@ cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    if (const char *e = getenv("SCAR_K3_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
     // persistent grid: a whole number of resident CTAs per SM, never more than the work needs
     int64_t want = (P.n_reads + threads - 1) / threads;
     int64_t grid = (int64_t)sm_count * per_sm;
