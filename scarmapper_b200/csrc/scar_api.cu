@@ -414,7 +414,8 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
     bytes.resize(align16(bytes.size() + nmax.size() * sizeof(uint16_t)));
     memcpy(bytes.data() + c->nmax_off, nmax.data(), nmax.size() * sizeof(uint16_t));
     c->blob_bytes = (uint32_t)bytes.size();
-    c->smem_tables = c->blob_bytes <= 200 * 1024;
+    // larger blobs (many loci) are read through the read-only global path instead of shared memory
+    c->smem_tables = c->blob_bytes <= 200 * 1024 && !getenv("SCAR_FORCE_GLOBAL_TABLES");
 
     int rc;
     if ((rc = upload(&c->d_blob, bytes))) return rc;

@@ -474,3 +474,111 @@ def test_multi_gpu_merges_match_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("anchor", ["anchor", "scan"])
+def test_tables_in_global_memory_path(anchor, monkeypatch):
+    """Blobs too large for shared memory are read through the global read-only path: same results."""
+    monkeypatch.setenv("SCAR_FORCE_GLOBAL_TABLES", "1")
+    if anchor == "scan":
+        monkeypatch.setenv("SCAR_NO_ANCHOR", "1")
+    blob = gu.load("ragged_hr_donor")
+    case = blob["case"]
+    pin = gu.problem_inputs(case)
+    f0, f1 = gu.index_fields(case)
+    eng = engine_for(pin, max(len(r) for r in case["reads"]))
+    rec = eng.process_host(case["reads"], f0, f1)
+    assert_records_equal(rec, orc.classify_batch(orc.Problem(**pin), case["reads"], f0, f1), case["reads"])
+    eng.close()
+
+
+@pytest.mark.parametrize("anchor", ["anchor", "scan"])
+def test_long_reads_up_to_1024(anchor, monkeypatch):
+    """Reads of 300-1000 nt on a 1.2-kb locus (W up to 64 cells), large deletions and insertions."""
+    import random
+    if anchor == "scan":
+        monkeypatch.setenv("SCAR_NO_ANCHOR", "1")
+    rng = random.Random(77)
+    while True:
+        target = "".join(rng.choice("ACGT") for _ in range(1200))
+        if len({target[i:i + 10] for i in range(1191)}) == 1191:
+            break
+    cut = 600
+    reads = []
+    for i in range(3000):
+        rl = rng.choice([300, 512, 513, 700, 1000, 1024])
+        dl, dr = rng.choice([0, 0, 3, 40, 200]), rng.choice([0, 0, 5, 60, 250])
+        ins = "".join(rng.choice("ACGTN" if i % 9 == 0 else "ACGT") for _ in range(rng.choice([0, 0, 2, 30])))
+        a = rl // 2
+        lo = max(0, cut - dl - a)
+        r = (target[lo:cut - dl] + ins + target[cut + dr:])[:rl]
+        r += "".join(rng.choice("ACGT") for _ in range(rl - len(r)))
+        if i % 11 == 0:
+            p = rng.randrange(len(r)); r = r[:p] + rng.choice("ACGTN") + r[p + 1:]
+        reads.append(r)
+    pin = dict(targets=[target], cutsites=[cut], sample_target=[0], left_index=["TATAGCCT"], right_index=["ATTACTCG"],
+               platform="Illumina", n_limit=0.01, min_length=100)
+    f0, f1 = ["ATTACTCG"] * len(reads), ["TATAGCCT"] * len(reads)
+    want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
+    assert (want["status"] == orc.ST_SCAR).sum() > 1000
+    eng = engine_for(pin, 1024)
+    rec = eng.process_host(reads, f0, f1)
+    assert_records_equal(rec, want, reads)
+    eng.close()
+
+
+def test_many_samples_global_counter_path():
+    """600 samples: the per-CTA shared-memory histogram does not fit, counters go through global atomics."""
+    import random
+    rng = random.Random(5)
+    pool7 = ["".join(rng.choice("ACGT") for _ in range(8)) for _ in range(25)]
+    pool5 = ["".join(rng.choice("ACGT") for _ in range(8)) for _ in range(24)]
+    right = [a for a in pool7 for _ in pool5]
+    left = [b for _ in pool7 for b in pool5]
+    cfg = synth.make_config("C1", n_reads=30000, seed=41)
+    batch = cfg.generate(0, 30000)
+    reads = cfg.reads_as_strings(batch)
+    f0, f1 = [], []
+    for i in range(len(reads)):
+        s = rng.randrange(len(right))
+        a, b = right[s], left[s]
+        if rng.random() < 0.1:
+            p = rng.randrange(8); a = a[:p] + rng.choice("ACGT") + a[p + 1:]
+        f0.append(a); f1.append(b)
+    pin = dict(targets=cfg.targets, cutsites=cfg.cutsites, sample_target=[0] * len(right), left_index=left,
+               right_index=right, platform="Illumina", phasing=cfg.phasing_lists(), n_limit=0.01, min_length=100)
+    prob = orc.Problem(**pin)
+    want = orc.classify_batch(prob, reads, f0, f1)
+    eng = engine_for(pin, cfg.read_len)
+    rec = eng.process_host(reads, f0, f1)
+    assert_records_equal(rec, want, reads)
+    cnt, un = eng.counters()
+    assert (cnt == orc.counters(prob, want)).all()
+    eng.close()
+
+
+def test_index_sequences_with_non_acgt_symbols():
+    """Index strings that are not pure ACGT disable the 2-bit shortcut: class-mapped bit-vector distance."""
+    import random
+    rng = random.Random(6)
+    right = ["ATTANTCG", "TCCGGAGA", "CGCTCATT", "NNNNNNNN"]
+    left = ["TATAGCCT", "ATAGAGGC", "CCTRYCCT", "GGCTCTGA"]
+    f0, f1 = [], []
+    for i in range(4000):
+        s = rng.randrange(4)
+        a, b = list(right[s]), list(left[s])
+        for _ in range(rng.choice([0, 0, 1, 2])):
+            side = a if rng.random() < 0.5 else b
+            side[rng.randrange(8)] = rng.choice("ACGTNRY")
+        if rng.random() < 0.1:
+            del a[rng.randrange(len(a))]
+        f0.append("".join(a)); f1.append("".join(b))
+    cfg = synth.make_config("C1", n_reads=4000, seed=42)
+    reads = cfg.reads_as_strings(cfg.generate(0, 4000))
+    pin = dict(targets=cfg.targets, cutsites=cfg.cutsites, sample_target=[0] * 4, left_index=left, right_index=right,
+               platform="Illumina", n_limit=0.01, min_length=100)
+    want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
+    assert len(set(want["sample"].tolist())) >= 4
+    eng = engine_for(pin, cfg.read_len)
+    assert_records_equal(eng.process_host(reads, f0, f1), want, reads)
+    eng.close()
