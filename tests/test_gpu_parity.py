@@ -582,3 +582,78 @@ def test_index_sequences_with_non_acgt_symbols():
     eng = engine_for(pin, cfg.read_len)
     assert_records_equal(eng.process_host(reads, f0, f1), want, reads)
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["c3_12_targets_mh", "ragged_hr_donor", "truseq", "ramsden"])
+def test_dropin_glue_on_gpu_from_fastq_file(name, tmp_path):
+    """scarmapper_b200.dropin.batched_consensus_demultiplex with the REAL engine, fed from a gz FASTQ file
+    and the reference's input file formats, driven through stand-ins for the reference objects it touches
+    (index_dict, target_dict, phase_dict, args, a FastaFile reader).  What it hands back - read_count_dict,
+    phase_count, per-sample SampleResult (counters, table with the first read's sub_list, read_results) -
+    must equal what the unmodified reference driver produced (golden)."""
+    import argparse
+    import collections
+    import sys
+    import types
+    sys.path.insert(0, str(gu.GOLDEN_DIR))
+    import make_golden
+    from oracle import ref_shims
+    from scarmapper_b200 import dropin
+
+    blob = gu.load(name)
+    case, golden = blob["case"], blob["golden"]
+    wd = str(tmp_path) + "/"
+    make_golden.write_inputs(wd, case)
+    args = argparse.Namespace(
+        WorkingFolder=wd, Job_Name="g", Verbose="ERROR", Platform=case["platform"], PEAR=True, Demultiplex=False,
+        HR_Donor=case["hr_donor"], N_Limit=case["n_limit"], Minimum_Length=case["min_length"], OutputRawData=True,
+        PatternThreshold=0.0001, RefSeq=wd + "refseq.fa", FASTQ1=wd + "reads.fastq.gz")
+
+    # stand-ins shaped like the reference's objects (DataProcessing.dictionary_build / TargetMapper)
+    pin = gu.problem_inputs(case)
+    index_dict = collections.OrderedDict()
+    for s, iid in enumerate(case["sample_ids"]):
+        index_dict[iid] = [pin["left_index"][s], 0, pin["right_index"][s], 0, iid, "S%d" % s, "1",
+                           case["target_names"][case["sample_target"][s]]]
+    target_dict = {nm: (nm, "ctg_" + nm, 0, len(t), sg.upper(), "YES" if rc else "NO")
+                   for nm, t, sg, rc in zip(case["target_names"], case["targets"], case["sgrnas"], case["reverse_comp"])}
+    phase_dict = collections.defaultdict(lambda: collections.defaultdict(list))
+    if case["platform"] != "TruSeq":
+        for t, (r1, r2) in zip(case["target_names"], gu.phasing_lists(case)):
+            phase_dict[t]["R1"] = [[p, "F%d" % k] for k, p in enumerate(r1)]
+            phase_dict[t]["R2"] = [[p, "R%d" % k] for k, p in enumerate(r2)]
+
+    class Fasta:                       # pysam.FastaFile stand-in (same semantics as oracle/ref_shims.py)
+        def __init__(self, path):
+            self.recs = dict(ref_shims._read_fasta(path))
+
+        def fetch(self, chrom, start=None, stop=None):
+            if chrom not in self.recs:
+                raise KeyError(chrom)
+            return self.recs[chrom][start:stop]
+
+    from scipy import stats
+    module = types.SimpleNamespace(pysam=types.SimpleNamespace(FastaFile=Fasta), pyfaidx=None, stats=stats)
+    log = types.SimpleNamespace(info=lambda *a: None, error=lambda *a: None)
+    dp = types.SimpleNamespace(
+        args=args, log=log, index_dict=index_dict, target_dict=target_dict, phase_dict=phase_dict,
+        phase_count=collections.defaultdict(lambda: collections.defaultdict(int)),
+        read_count_dict=collections.defaultdict(), sequence_dict=collections.defaultdict(list), read_count=0,
+        fastq1=types.SimpleNamespace(input_file=args.FASTQ1))
+    indexed, lower_limit = dropin.batched_consensus_demultiplex(dp, module)
+    assert dp.read_count == golden["read_count"]
+    assert dict(dp.read_count_dict) == golden["read_count_dict"]
+    # (data_output later touches phase_count[key] for every sample, leaving empty dicts on non-Illumina runs)
+    assert {k: dict(v) for k, v in dp.phase_count.items()} == {k: v for k, v in golden["phase_count"].items() if v}
+    assert indexed == sum(v for k, v in golden["read_count_dict"].items() if k != "unidentified")
+    assert set(dp.sequence_dict) == set(golden["samples"])
+    for iid, g in golden["samples"].items():
+        res = dp.sequence_dict[iid]
+        c = res.counters
+        assert [int(c[1]), int(c[2]), int(c[3]), int(c[4]), int(c[5]), [int(c[6]), int(c[7])], [int(c[8]), 0],
+                [int(c[9]), int(c[10])]] == g["summary"]
+        assert res.cutsite == g["cutsite"]
+        got = [["{}|{}|{}|{}|{}".format(s[0], s[1], s[2], s[3], s[9]), n] + [s[i] for i in (0, 1, 2, 3, 5, 6, 7, 8, 9)] + [s[4]]
+               for n, s in res.table]
+        assert got == g.get("table", []), iid
+        assert [[s[5], s[6], s[7], s[8], s[9]] for s in (res.read_results or [])] == g.get("read_results", [])
