@@ -372,6 +372,41 @@ def main():
             dscar.merge_partitioned(region_capacity=region_capacity)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # the same from FASTQ TEXT (uncompressed, pinned): one H2D copy of the text, record indexing on the GPU
+    fastq_e2e = None
+    if world == 1:
+        head = b"@SYN:1:FC:1:0:0:0 1:N:0:"
+        rl = cfg.read_len
+        rec_bytes = len(head) + 8 + 1 + 8 + 1 + rl + 3 + rl + 1
+        p_txt = torch.empty((n, rec_bytes), dtype=torch.uint8, pin_memory=True)
+        tn = p_txt.numpy()
+        o = 0
+        tn[:, o:o + len(head)] = np.frombuffer(head, dtype=np.uint8); o += len(head)
+        tn[:, o:o + 8] = batch["f0"]; o += 8
+        tn[:, o] = ord("+"); o += 1
+        tn[:, o:o + 8] = batch["f1"]; o += 8
+        tn[:, o] = 10; o += 1
+        tn[:, o:o + rl] = batch["seq"]; o += rl
+        tn[:, o:o + 3] = np.frombuffer(b"\n+\n", dtype=np.uint8); o += 3
+        tn[:, o:o + rl] = ord("I"); o += rl
+        tn[:, o] = 10
+        flat = tn.reshape(-1)
+        eng.reset_async()
+        got = eng.process_fastq_text(flat, first_index=first, out=rec_out)
+        if len(got) != n or got[:chk].tobytes() != want.tobytes():
+            raise SystemExit("bench: FASTQ-text path disagrees with the oracle")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.reset_async()
+            eng.process_fastq_text(flat, first_index=first, out=rec_out)
+        torch.cuda.synchronize()
+        fq_s = time.perf_counter() - t0
+        fastq_e2e = {"value": n * 3 / fq_s, "unit": "reads/s", "h2d_bytes_per_step": int(flat.size),
+                     "d2h_bytes_per_step": int(n * 16), "steps": 3,
+                     "path": "ScarEngine.process_fastq_text -> scar_process_fastq_host (uncompressed FASTQ text, pinned; "
+                             "records indexed on the GPU)"}
+        del p_txt, tn, flat
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
@@ -418,6 +453,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if fastq_e2e:
+            line["e2e_fastq_text"] = fastq_e2e
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)

@@ -177,6 +177,17 @@ int scar_fastq_index(const uint8_t *text, int64_t n_bytes, int32_t is_final, int
                      int64_t capacity, int64_t *seq_off, int32_t *seq_len, int64_t *f0_off, int32_t *f0_len,
                      int64_t *f1_off, int32_t *f1_len, int64_t *n_records, int64_t *consumed);
 
+/* The same from FASTQ TEXT in host memory (whole records; a last record may lack its newline): the text is
+ * copied to the GPU once, the records are indexed there (newline count / scan / positions, one thread per
+ * record for the views), and the whole path runs on the views.  records (may be NULL) receives one record
+ * per FASTQ record in file order; *n_records the count. */
+int scar_process_fastq_host(scar_ctx *ctx, const uint8_t *text, int64_t n_bytes, uint64_t first_index,
+                            scar_record *records, int64_t records_capacity, int64_t *n_records);
+
+/* After scar_process_fastq_host(records = NULL): copy the records of that call to the host once their number
+ * is known. */
+int scar_fastq_records_fetch(scar_ctx *ctx, scar_record *records, int64_t n_records);
+
 /* Sequence_Magic.match_maker over a batch on the device (host buffers): out[i] = lev(q_i,u_i) - (|u_i|-|q_i|). */
 int scar_match_maker_batch(int32_t device, const scar_ragged *query, const scar_ragged *unknown,
                            int64_t n, int32_t *out);

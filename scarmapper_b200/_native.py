@@ -101,6 +101,8 @@ PROTOTYPES = {
     "scar_accumulators_import_dev": (C.c_int, [_P, _P, _P]),
     "scar_fastq_index": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P,
                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "scar_process_fastq_host": (C.c_int, [_P, _P, C.c_int64, C.c_uint64, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "scar_fastq_records_fetch": (C.c_int, [_P, _P, C.c_int64]),
     "scar_match_maker_batch": (C.c_int, [C.c_int32, _RP, _RP, C.c_int64, _P]),
 }
 

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscar_b200.so")
-SOURCES = ["scar_api.cu", "scar_pack.cu", "scar_demux.cu", "scar_window.cu", "scar_table.cu", "scar_fastq.cu"]
+SOURCES = ["scar_api.cu", "scar_pack.cu", "scar_demux.cu", "scar_window.cu", "scar_table.cu", "scar_fastq.cu", "scar_fastq_dev.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-cudart", "static"]
 
@@ -32,7 +32,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        extra = os.environ.get("SCAR_NVCC_EXTRA", "").split()
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         subprocess.check_call(cmd)
         objs.append(obj)
     subprocess.check_call([nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",

@@ -130,6 +130,11 @@ struct scar_ctx {
     unsigned long long *d_counters = nullptr, *d_phase_hist = nullptr; size_t acc_words = 0;
     int32_t *d_status = nullptr;
     HostBuf buf[NBUF]; int64_t chunk_reads = 1 << 20;
+    // GPU FASTQ path
+    uint8_t *d_text = nullptr; size_t text_cap = 0;
+    uint32_t *d_tile_counts = nullptr; size_t tile_counts_cap = 0;
+    int64_t *d_tile_offsets = nullptr; size_t tile_offsets_cap = 0;
+    int64_t *d_nl = nullptr; size_t nl_cap = 0;
     int launches = 0;
 };
 
@@ -151,6 +156,7 @@ extern "C" void scar_ctx_destroy(scar_ctx *c)
     cudaFree(c->d_sample_target); cudaFree(c->d_blob);
     cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample); cudaFree(c->d_fast_codes);
     cudaFree(c->d_slots); cudaFree(c->d_acc); cudaFree(c->d_status);
+    cudaFree(c->d_text); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offsets); cudaFree(c->d_nl);
     delete c;
 }
 
@@ -851,6 +857,68 @@ extern "C" int scar_process_host(scar_ctx *c, const scar_ragged *seq, const scar
     }
     for (int i = 0; i < NBUF; ++i) if (c->buf[i].stream) CU(cudaStreamSynchronize(c->buf[i].stream));
     return check_status(c);
+}
+
+// ---- FASTQ text in host memory -> records: the text is copied to the GPU once and indexed THERE ----------
+extern "C" int scar_process_fastq_host(scar_ctx *c, const uint8_t *text, int64_t n_bytes, uint64_t first_index,
+                                       scar_record *records, int64_t records_capacity, int64_t *n_records_out)
+{
+    if (!c || !text || n_bytes < 0 || !n_records_out) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    *n_records_out = 0;
+    if (n_bytes == 0) return SCAR_OK;
+    HostBuf &B = c->buf[0];
+    int rc = ensure_hostbuf(c, B, 1);
+    if (rc) return rc;
+    cudaStream_t s = B.stream;
+    if ((rc = ensure(&c->d_text, &c->text_cap, (size_t)n_bytes + 64))) return rc;
+    const int64_t piece = 64ll << 20;                       // plain byte pieces: the record boundaries are found on the GPU
+    for (int64_t off = 0; off < n_bytes; off += piece)
+        CU(cudaMemcpyAsync(c->d_text + off, text + off, (size_t)std::min(piece, n_bytes - off), cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(c->d_text + n_bytes, 0, 64, s));
+    const int64_t n_tiles = (n_bytes + 4095) / 4096;
+    if ((rc = ensure(&c->d_tile_counts, &c->tile_counts_cap, (size_t)n_tiles))) return rc;
+    if ((rc = ensure(&c->d_tile_offsets, &c->tile_offsets_cap, (size_t)n_tiles))) return rc;
+    CU(scar_fastq_index_launch(c->d_text, n_bytes, c->d_tile_counts, c->d_tile_offsets, c->d_export_n, s));
+    c->launches += 2;
+    unsigned long long n_nl = 0;
+    CU(cudaMemcpyAsync(&n_nl, c->d_export_n, sizeof(n_nl), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    // whole records only; a last record may lack its final newline
+    int64_t n_rec = (int64_t)(n_nl / 4);
+    if (n_nl % 4 == 3 && text[n_bytes - 1] != '\n') ++n_rec;
+    *n_records_out = n_rec;
+    if (n_rec == 0) return SCAR_OK;
+    if (records && records_capacity < n_rec) return fail(SCAR_ERR_INVALID, "records buffer too small: %lld records", (long long)n_rec);
+    if ((rc = ensure(&c->d_nl, &c->nl_cap, (size_t)n_nl + 1))) return rc;
+    CU(scar_fastq_positions_launch(c->d_text, n_bytes, c->d_tile_offsets, c->d_nl, (int64_t)n_nl, s));
+    if ((rc = ensure_hostbuf(c, B, n_rec))) return rc;
+    const int want = c->platform == SCAR_PLATFORM_ILLUMINA;
+    CU(scar_fastq_records_launch(c->d_text, n_bytes, c->d_nl, (int64_t)n_nl, n_rec, want, B.seq_off, B.seq_len, B.f0_off,
+                                 B.f0_len, B.f1_off, B.f1_len, c->d_status, c->sm_count, s));
+    c->launches += 2;
+    scar_ragged dseq{c->d_text, B.seq_off, B.seq_len, 0}, df0{c->d_text, B.f0_off, B.f0_len, 0}, df1{c->d_text, B.f1_off, B.f1_len, 0};
+    if ((rc = scar_run_dev(c, &dseq, want ? &df0 : nullptr, want ? &df1 : nullptr, n_rec, first_index, B.cells, B.lens,
+                           B.samples, B.records, s))) return rc;
+    if (records) CU(cudaMemcpyAsync(records, B.records, (size_t)n_rec * sizeof(scar_record), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    int32_t st = 0;
+    CU(cudaMemcpy(&st, c->d_status, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st & 24) {
+        CU(cudaMemset(c->d_status, 0, sizeof(int32_t)));
+        if (st & 8) return fail(SCAR_ERR_INVALID, "FASTQ: sequence and quality scores of different lengths");
+        return fail(SCAR_ERR_INVALID, "FASTQ: a header has no '+' between the index reads (the reference raises IndexError)");
+    }
+    return check_status(c);
+}
+
+extern "C" int scar_fastq_records_fetch(scar_ctx *c, scar_record *records, int64_t n_records)
+{
+    if (!c || !records || n_records < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (n_records > c->buf[0].reads_cap) return fail(SCAR_ERR_INVALID, "no such records on the device");
+    if (n_records) CU(cudaMemcpy(records, c->buf[0].records, (size_t)n_records * sizeof(scar_record), cudaMemcpyDeviceToHost));
+    return SCAR_OK;
 }
 
 // ---- Sequence_Magic.match_maker batch -------------------------------------------------------------

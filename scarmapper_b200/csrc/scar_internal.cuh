@@ -194,3 +194,13 @@ cudaError_t scar_launch_export_parts(const ScarTableSlot *slots, uint64_t capaci
                                      uint64_t region, int32_t *status, int sm_count, cudaStream_t stream);
 cudaError_t scar_launch_merge_parts(const K4Params &P, const scar_entry *in, uint32_t n_parts, uint64_t region,
                                     int sm_count, cudaStream_t stream);
+
+// GPU FASTQ indexer (scar_fastq_dev.cu); tiles are 4096 bytes
+cudaError_t scar_fastq_index_launch(const uint8_t *text, int64_t n_bytes, uint32_t *tile_counts, int64_t *tile_offsets,
+                                    unsigned long long *total, cudaStream_t s);
+cudaError_t scar_fastq_positions_launch(const uint8_t *text, int64_t n_bytes, const int64_t *tile_offsets, int64_t *nl_pos,
+                                        int64_t nl_capacity, cudaStream_t s);
+cudaError_t scar_fastq_records_launch(const uint8_t *text, int64_t n_bytes, const int64_t *nl_pos, int64_t n_newlines,
+                                      int64_t n_records, int want_fields, int64_t *seq_off, int32_t *seq_len,
+                                      int64_t *f0_off, int32_t *f0_len, int64_t *f1_off, int32_t *f1_len, int32_t *status,
+                                      int sm_count, cudaStream_t s);

@@ -20,6 +20,13 @@
 
 #include "scar_internal.cuh"
 
+#ifndef SCAR_ANCHOR_BATCH
+#define SCAR_ANCHOR_BATCH 14
+#endif
+#ifndef SCAR_K3_MIN_CTAS
+#define SCAR_K3_MIN_CTAS 4
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -85,19 +92,26 @@ template <> struct TableRef<false> {
 // 16 table loads are issued back to back (16 independent shared-memory loads in flight per thread);
 // m[o] = i (< 4095) on a hit and a value >= 4095 otherwise.  Returns min(m): "any window of this cell
 // is in the table" costs one compare per cell, and the scan-order resolution runs only then.
-template <bool SMEM>
-__device__ __forceinline__ uint32_t probe16(const TableRef<SMEM> &tab, uint32_t wlo, uint32_t whi, uint32_t mult,
-                                            uint32_t nbuckets, uint32_t (&m)[16])
+template <bool SMEM, int N>
+__device__ __forceinline__ void probe_n(const TableRef<SMEM> &tab, uint32_t wlo, uint32_t whi, uint32_t mult,
+                                        uint32_t nbuckets, uint32_t (&m)[N])
 {
-    uint32_t t[16];
-    uint2 e[16];
+    uint32_t t[N];
+    uint2 e[N];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) {
+    for (int o = 0; o < N; ++o) {
         t[o] = __funnelshift_r(wlo, whi, 2 * o) << 12;
         e[o] = tab.load(__umulhi(t[o] * mult, nbuckets));
     }
 #pragma unroll
-    for (int o = 0; o < 16; ++o) m[o] = min(e[o].x ^ t[o], e[o].y ^ t[o]);
+    for (int o = 0; o < N; ++o) m[o] = min(e[o].x ^ t[o], e[o].y ^ t[o]);
+}
+
+template <bool SMEM>
+__device__ __forceinline__ uint32_t probe16(const TableRef<SMEM> &tab, uint32_t wlo, uint32_t whi, uint32_t mult,
+                                            uint32_t nbuckets, uint32_t (&m)[16])
+{
+    probe_n<SMEM, 16>(tab, wlo, whi, mult, nbuckets, m);
     const uint32_t a = min(min(m[0], m[1]), min(m[2], m[3])), b = min(min(m[4], m[5]), min(m[6], m[7]));
     const uint32_t c = min(min(m[8], m[9]), min(m[10], m[11])), d = min(min(m[12], m[13]), min(m[14], m[15]));
     return min(min(a, b), min(c, d));
@@ -266,7 +280,7 @@ __device__ __forceinline__ void store_record(scar_record *dst, const scar_record
 }
 
 template <bool SMEM, bool HR>
-__global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
+__global__ void __launch_bounds__(256, SCAR_K3_MIN_CTAS) scar_window_kernel(const K3Params P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [mbarrier 16 B][static blob: tables | target metas | phases | N-limit table]
@@ -361,6 +375,10 @@ __global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
         // (1) one anchor probe + flank verification and (2) one batch of 16 back-to-back probes, for all
         // lanes that are still scanning, so the lanes of a warp stay in step.
         {
+            // batch width: a clean deletion's junction window is the 10th position past the break, 1-3 nt
+            // insertions push it to the 11th-13th; wider batches cost every read, narrower ones cost rounds
+            constexpr int NB = SCAR_ANCHOR_BATCH;
+            constexpr uint32_t NBMASK = (1u << NB) - 1u;
             const bool fast = live && T.fast;
             const TableRef<SMEM> ptab(blob, P.blob, T.pos_off);
             const uint32_t *tw = reinterpret_cast<const uint32_t *>(blob + T.tw_off);
@@ -387,22 +405,22 @@ __global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
                     } else if (--p < 16) scanning = false;
                 }
                 __syncwarp();
-                if (scanning) {                                    // (2) positions p, p-1, .. p-15 in one batch
-                    const int b = p - 15;                          // >= 1 because p >= 16
-                    uint32_t wlo, whi, vlo, vhi, m[16];
+                if (scanning) {                                    // (2) positions p, p-1, .. p-NB+1 in one batch
+                    const int b = p - (NB - 1);                    // >= 0 because p >= 16
+                    uint32_t wlo, whi, vlo, vhi, m[NB];
                     rc.word16(b + 16, whi, vhi);
                     rc.word16(b, wlo, vlo);
-                    probe16<SMEM>(ptab, wlo, whi, mult, nb, m);
+                    probe_n<SMEM, NB>(ptab, wlo, whi, mult, nb, m);
                     // left window iff (t - 6) <= cut-16: one bit per position, then the first in scan order
                     uint32_t hm = 0;
 #pragma unroll
-                    for (int o = 0; o < 16; ++o) hm |= ((m[o] - 6u) <= (uint32_t)(cut - 16)) ? (1u << o) : 0u;
-                    if (hm) hm &= runs_of_ten(vlo | (vhi << 16)) & (b >= 16 ? 0xFFFFu : (0xFFFFu << (16 - b)));
+                    for (int o = 0; o < NB; ++o) hm |= ((m[o] - 6u) <= (uint32_t)(cut - 16)) ? (1u << o) : 0u;
+                    if (hm) hm &= runs_of_ten(vlo | (vhi << 16)) & (b >= 16 ? NBMASK : ((NBMASK << (16 - b)) & NBMASK));
                     if (hm) {
                         const int o = 31 - __clz(hm);              // highest position = first going down
                         uint32_t t = 0;
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) t = (q == o) ? m[q] : t;
+                        for (int q = 0; q < NB; ++q) t = (q == o) ? m[q] : t;
                         clj = b + o + 10; tlj = (int)t + 10; scanning = false;
                     }
                     if (scanning) { p = b - 1; if (p < 16) scanning = false; }
@@ -439,27 +457,27 @@ __global__ void __launch_bounds__(256, 4) scar_window_kernel(const K3Params P)
                     } else if (++p > plast) scanning = false;
                 }
                 __syncwarp();
-                if (scanning) {                                    // positions p .. p+15 in one batch
-                    uint32_t wlo, whi, vlo, vhi, m[16];
+                if (scanning) {                                    // positions p .. p+NB-1 in one batch
+                    uint32_t wlo, whi, vlo, vhi, m[NB];
                     rc.word16(p, wlo, vlo);
                     rc.word16(p + 16, whi, vhi);
-                    probe16<SMEM>(ptab, wlo, whi, mult, nb, m);
+                    probe_n<SMEM, NB>(ptab, wlo, whi, mult, nb, m);
                     const uint32_t span = (uint32_t)(L - 16 - cut);   // right window iff (t - cut) <= span
-                    uint32_t hm = 0;                               // right window iff (t - cut) <= span
+                    uint32_t hm = 0;
 #pragma unroll
-                    for (int o = 0; o < 16; ++o) hm |= ((m[o] - (uint32_t)cut) <= span) ? (1u << o) : 0u;
+                    for (int o = 0; o < NB; ++o) hm |= ((m[o] - (uint32_t)cut) <= span) ? (1u << o) : 0u;
                     if (hm) {
                         const int top = plast - p;                 // >= 0
-                        hm &= runs_of_ten(vlo | (vhi << 16)) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
+                        hm &= runs_of_ten(vlo | (vhi << 16)) & (top >= NB - 1 ? NBMASK : ((2u << top) - 1u));
                     }
                     if (hm) {
                         const int o = __ffs(hm) - 1;               // lowest position = first going up
                         uint32_t t = 0;
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) t = (q == o) ? m[q] : t;
+                        for (int q = 0; q < NB; ++q) t = (q == o) ? m[q] : t;
                         crj = p + o; trj = (int)t; scanning = false;
                     }
-                    if (scanning) { p += 16; if (p > plast) scanning = false; }
+                    if (scanning) { p += NB; if (p > plast) scanning = false; }
                 }
                 __syncwarp();
             }

@@ -220,6 +220,20 @@ class ScarEngine:
                                           rec.ctypes.data if rec is not None else None))
         return rec
 
+    def process_fastq_text(self, text, first_index: int = 0, want_records: bool = True, out=None):
+        """Whole path from FASTQ TEXT (uint8 array, whole records): one H2D copy of the text, record indexing
+        on the GPU, then K2/K1/K3/K4 on views into the text.  Returns the records in file order (or their
+        number when want_records is False)."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        n = C.c_int64(0)
+        N.check(self._L.scar_process_fastq_host(self._ctx, text.ctypes.data, text.size, first_index, None, 0,
+                                                C.byref(n)))
+        if not want_records:
+            return n.value
+        rec = out[:n.value] if out is not None else np.empty(n.value, dtype=N.RECORD_DTYPE)
+        N.check(self._L.scar_fastq_records_fetch(self._ctx, rec.ctypes.data, n.value))
+        return rec
+
     # ---- device-resident path -------------------------------------------------------------------
     def make_resident(self, reads, f0=None, f1=None):
         """Copy a host batch into HBM (torch tensors) and allocate its scratch/outputs."""

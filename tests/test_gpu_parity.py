@@ -657,3 +657,48 @@ def test_dropin_glue_on_gpu_from_fastq_file(name, tmp_path):
                for n, s in res.table]
         assert got == g.get("table", []), iid
         assert [[s[5], s[6], s[7], s[8], s[9]] for s in (res.read_results or [])] == g.get("read_results", [])
+
+
+def test_gpu_fastq_indexer_matches_host_indexer_and_oracle():
+    """FASTQ text -> GPU indexer (newline count / scan / positions, one thread per record) -> whole path.
+    Records must equal the host-indexed views path and the oracle; malformed text must raise where the
+    reference raises."""
+    import random
+    from scarmapper_b200 import fastq
+    from scarmapper_b200._native import ScarError
+    cfg = synth.make_config("C3", n_reads=30000, seed=61, min_len=40, p_n=0.02)
+    batch = cfg.generate(0, 30000)
+    reads = cfg.reads_as_strings(batch)
+    f0, f1 = cfg.fields_as_strings(batch)
+    rng = random.Random(3)
+    parts = []
+    for i, (r, a, b) in enumerate(zip(reads, f0, f1)):
+        e = "\r\n" if i % 3 == 0 else "\n"
+        pad = " " if i % 17 == 0 else ""
+        extra = "+X" if i % 29 == 0 else ""
+        parts.append("@{}SYN:{}:x y:N:0:{}+{}{}{}{}{}{}+{}{}{}".format("@" * (i % 2), i, a, b, extra, e, r, pad, e, e,
+                                                                    "I" * len(r), e))
+    for final_newline in (True, False):
+        text = "".join(parts)
+        if not final_newline:
+            text = text.rstrip("\r\n")
+        arr = np.frombuffer(text.encode(), dtype=np.uint8)
+        pin = synth_problem(cfg)
+        eng = engine_for(pin, cfg.read_len)
+        rec = eng.process_fastq_text(arr)
+        assert len(rec) == len(reads)
+        want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
+        assert_records_equal(rec, want, reads)
+        tab = eng.table().copy()
+        eng.reset()
+        fb = fastq.index_text(arr)
+        rec2 = eng.process_host(fb.seq, fb.f0, fb.f1)
+        assert rec2.tobytes() == rec.tobytes() and eng.table().tobytes() == tab.tobytes()
+        eng.close()
+    eng = engine_for(synth_problem(cfg), cfg.read_len)
+    with pytest.raises(ScarError):
+        eng.process_fastq_text(np.frombuffer(b"@a:AC+GT\nACGT\n+\nII\n", dtype=np.uint8))
+    with pytest.raises(ScarError):
+        eng.process_fastq_text(np.frombuffer(b"@a:ACGT\nACGT\n+\nIIII\n", dtype=np.uint8))
+    assert len(eng.process_fastq_text(np.frombuffer(b"@a:AC+GT\nACGT\n+\nIIII\n@trunc\nAC\n", dtype=np.uint8))) == 1
+    eng.close()
