@@ -213,9 +213,9 @@ def main():
     n = args.reads
     first = rank * n
     batch = cfg.generate(first, n)
-    # scar-table slots: ~1 M patterns per 10 M reads of this spectrum, ~3.7 M after an 8-rank merge; keep the
-    # load factor under 0.5 so that probe sequences stay short during the fold
-    table_capacity = 1 << (22 if world <= 2 else 23)
+    # scar-table slots: ~1 M patterns per 10 M reads of this spectrum; after the owner-partitioned merge a rank
+    # holds ~1/world of the merged patterns, so the load factor stays near 0.25 for every world size
+    table_capacity = 1 << 22
     eng = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=table_capacity, **pin), device=local)
 
     # pinned host buffers for the end-to-end arm
