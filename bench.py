@@ -215,7 +215,7 @@ def main():
     batch = cfg.generate(first, n)
     # scar-table slots: ~1 M patterns per 10 M reads of this spectrum; after the owner-partitioned merge a rank
     # holds ~1/world of the merged patterns, so the load factor stays near 0.25 for every world size
-    table_capacity = 1 << 22
+    table_capacity = 1 << int(os.environ.get("SCAR_BENCH_TABLE_LOG2", "22"))
     eng = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=table_capacity, **pin), device=local)
 
     # pinned host buffers for the end-to-end arm
