@@ -71,3 +71,45 @@ def test_reference_driver_with_dropin_writes_identical_files(name):
         dropin._ENGINE_FACTORY[0] = None
         INDEL_Processing.DataProcessing.consensus_demultiplex, INDEL_Processing.ScarSearch.data_processing = saved
         shutil.rmtree(wd, ignore_errors=True)
+
+
+def test_launcher_runs_the_reference_pipeline_from_an_options_file(tmp_path):
+    """scarmapper_b200.launcher.main with a real tab-delimited options file (docs/run_ScarMapper_IndelProcessing.sh
+    format), the reference tree, and the oracle-backed engine: the files written equal the golden files."""
+    import make_golden
+    from oracle_engine import OracleEngine
+    blob = gu.load("c2_96_samples")
+    case, golden = blob["case"], blob["golden"]
+    ref_shims.install()
+    from scarmapper import INDEL_Processing
+    from scarmapper_b200 import dropin, launcher
+    saved = (INDEL_Processing.DataProcessing.consensus_demultiplex, INDEL_Processing.ScarSearch.data_processing)
+    wd = str(tmp_path) + os.sep
+    make_golden.write_inputs(wd, case)
+    opts = {
+        "IndelProcessing": "True", "FASTQ1": wd + "reads.fastq.gz", "FASTQ2": "", "RefSeq": wd + "refseq.fa",
+        "Master_Index_File": wd + "master_index.tsv", "SampleManifest": wd + "manifest.tsv",
+        "TargetFile": wd + "targets.tsv", "WorkingFolder": wd, "Verbose": "ERROR", "Job_Name": "golden", "Spawn": "1",
+        "Demultiplex": "False", "DeleteConsensusFASTQ": "True", "HR_Donor": "", "Platform": "Illumina",
+        "Search_KMER": "10", "N_Limit": "0.01", "Minimum_Length": "100 # Length after trimming",
+        "OutputRawData": "True", "PatternThreshold": "0.0001 # cutoff", "FigureType": "pdf",
+    }
+    with open(wd + "run.sh", "w") as f:
+        f.write("#!/bin/bash\n#Parameter file\n\npython3 scarmapper.py --options_file run.sh\nexit\n\n")
+        for k, v in opts.items():
+            f.write("--{}\t{}\n".format(k, v))
+    try:
+        dropin._ENGINE_FACTORY[0] = OracleEngine
+        launcher.main(["--options_file", wd + "run.sh", "--reference", ref_shims.REFERENCE])
+        seen = 0
+        for fn, want in golden["files"].items():
+            got = open(os.path.join(wd, fn)).read().split("\n")
+            got = "\n".join(ln for ln in got if not ln.startswith(("# Run Start", "# Run End", "Start:", "End:",
+                                                                   "FASTQ1:", "FASTQ2:", "ScarMapper v", "# ScarMapper Search v")))
+            want = "\n".join(ln for ln in want.split("\n") if not ln.startswith(("ScarMapper v", "# ScarMapper Search v")))
+            assert got == want, fn
+            seen += 1
+        assert seen == len(golden["files"]) == 97
+    finally:
+        dropin._ENGINE_FACTORY[0] = None
+        INDEL_Processing.DataProcessing.consensus_demultiplex, INDEL_Processing.ScarSearch.data_processing = saved
