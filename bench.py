@@ -417,11 +417,18 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = ALGO_BYTES_PER_READ * n / (k3 * 1e-3) / 1e9
-        traffic = None
+        traffic, secondary = None, None
         tp = os.path.join(ROOT, "profiles", "k3_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                prof = json.load(open(tp))
+                traffic = prof.get("dram_bytes_per_launch")
+                # SURVEY.md §8d secondary bound: the kernel is integer-ALU / issue bound, not DRAM bound
+                secondary = {"bound": "int_alu_pipe", "alu_pipe_pct_of_peak": prof.get("alu_pipe_pct_of_peak"),
+                             "issue_active_pct_of_peak": prof.get("issue_active_pct_of_peak"),
+                             "dram_throughput_pct_of_peak": prof.get("dram_throughput_pct_of_peak"),
+                             "warp_instructions_per_read": prof.get("warp_instructions_per_read"),
+                             "source": "ncu --set full, profiles/r01_final_ncu_full.csv (not measured in this run)"}
             except Exception:
                 traffic = None
         h2d = int(p_seq.numel() + p_f0.numel() + p_f1.numel())
@@ -446,7 +453,7 @@ def main():
                           "merge": merge_ms if world > 1 else 0.0},
             "roofline": {"bound": "hbm", "kernel": "scar_window_kernel (K3)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ},
+                         "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ, "secondary": secondary},
             "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(n * 16), "steps": e2e_steps,
                     "path": "ScarEngine.process_host -> scar_process_host (pinned host buffers)"},

@@ -105,6 +105,9 @@ void scar_ctx_destroy(scar_ctx *ctx);
  * N mask << 48 for bases 16j .. 16j+15). */
 int scar_cells_per_read(const scar_ctx *ctx);
 int scar_window_counts(const scar_ctx *ctx, int32_t target, int32_t *n_left, int32_t *n_right);
+/* size of the static blob K3 stages per CTA, whether it fits shared memory, and how many loci use the
+ * anchor-and-extend search (unique 10-mers) */
+int scar_ctx_info(const scar_ctx *ctx, int64_t *static_bytes, int32_t *tables_in_smem, int32_t *n_anchor_targets);
 
 /* K1: raw bytes -> packed rows (2-bit codes + ACGT mask + N mask), applying the platform's stored-
  * sequence transform (Illumina as is, TruSeq seq[6:-6], Ramsden rcomp; INDEL_Processing.py:946,978,981). */

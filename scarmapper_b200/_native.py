@@ -76,6 +76,7 @@ PROTOTYPES = {
     "scar_ctx_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     "scar_ctx_destroy": (None, [_P]),
     "scar_cells_per_read": (C.c_int, [_P]),
+    "scar_ctx_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "scar_window_counts": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "scar_pack_dev": (C.c_int, [_P, _RP, C.c_int64, _P, _P, _P]),
     "scar_demux_dev": (C.c_int, [_P, _RP, _RP, _RP, C.c_int64, _P, _P]),

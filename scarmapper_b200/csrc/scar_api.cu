@@ -3,6 +3,7 @@
 // scarmapper/INDEL_Processing.py:57-80,1063-1124 and TargetMapper.py:30-71), the stage entry points
 // and the host-buffer pipeline.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -74,22 +75,24 @@ static uint64_t encode_bases(const uint8_t *p, int n)
 struct BucketTable { std::vector<uint2> buckets; uint32_t mult, nbuckets; };
 
 // window list -> bucketed perfect hash "10-mer -> smallest i" (two entries per bucket, one probe)
-static bool build_table(const std::vector<std::pair<uint32_t, uint32_t>> &kv /* key, min i */, BucketTable &out)
+static bool build_table(const std::vector<std::pair<uint32_t, uint32_t>> &kv /* key, payload */, BucketTable &out)
 {
-    size_t n = kv.size();
-    uint32_t log2b = 6;
-    while ((1u << log2b) < 2 * n) ++log2b;      // load <= 0.5 keys per bucket; a few hundred tries find a multiplier
+    // bucket = mulhi((key << 12) * mult, B): any B works, not only powers of two.  With two entries per bucket a
+    // collision-free multiplier exists with fair probability once n^3 / (6 B^2) is a few units, so start at
+    // B ~ n^1.5 / 5.5 (at least 1.5 n) and grow by 10 % per round of attempts.
+    const size_t n = kv.size();
+    double want = std::max(1.5 * (double)n, std::pow((double)n, 1.5) / 5.5);
+    uint32_t B = std::max<uint32_t>(16, ((uint32_t)want + 1) & ~1u);
     uint64_t rng = 0x853C49E6748FEA9Bull ^ (n * 0x9E3779B97F4A7C15ull);
-    for (; log2b <= 16; ++log2b) {
-        const uint32_t B = 1u << log2b;
-        for (int attempt = 0; attempt < 20000; ++attempt) {
+    for (int round = 0; round < 40 && B <= (1u << 17); ++round, B = ((uint32_t)(B * 1.1) + 2) & ~1u) {
+        for (int attempt = 0; attempt < 3000; ++attempt) {
             rng = rng * 6364136223846793005ull + 1442695040888963407ull;
             const uint32_t mult = (uint32_t)(rng >> 32) | 1u;
             std::vector<uint2> b(B, make_uint2(SCAR_TABLE_EMPTY, SCAR_TABLE_EMPTY));
             bool ok = true;
             for (const auto &e : kv) {
                 const uint32_t t = e.first << 12;                  // key in the top 20 bits, as the kernel forms it
-                const uint32_t slot = (t * mult) >> (32 - log2b);
+                const uint32_t slot = (uint32_t)(((uint64_t)(t * mult) * B) >> 32);
                 const uint32_t val = t | e.second;
                 if (b[slot].x == SCAR_TABLE_EMPTY) b[slot].x = val;
                 else if (b[slot].y == SCAR_TABLE_EMPTY) b[slot].y = val;
@@ -471,6 +474,15 @@ extern "C" int scar_reset_dev(scar_ctx *c, void *stream)
 extern "C" int64_t scar_launch_count(const scar_ctx *c) { return c ? c->launches : 0; }
 
 extern "C" int scar_cells_per_read(const scar_ctx *c) { return c ? c->W : 0; }
+
+extern "C" int scar_ctx_info(const scar_ctx *c, int64_t *static_bytes, int32_t *tables_in_smem, int32_t *n_anchor_targets)
+{
+    if (!c) return fail(SCAR_ERR_INVALID, "null context");
+    if (static_bytes) *static_bytes = c->blob_bytes;
+    if (tables_in_smem) *tables_in_smem = c->smem_tables ? 1 : 0;
+    if (n_anchor_targets) { int k = 0; for (const auto &m : c->h_targets) k += m.fast; *n_anchor_targets = k; }
+    return SCAR_OK;
+}
 
 extern "C" int scar_window_counts(const scar_ctx *c, int32_t t, int32_t *n_left, int32_t *n_right)
 {

@@ -98,8 +98,11 @@ __device__ __forceinline__ void classify4(uint32_t w, uint32_t &code8, uint32_t 
     uint32_t v = zero_bytes(w ^ canon);            // 0x80 per valid byte
     v = (v >> 7);
     valid4 = (v | (v >> 7) | (v >> 14) | (v >> 21)) & 0xFu;
-    uint32_t n = zero_bytes(w ^ 0x4E4E4E4Eu) >> 7; // 'N'
-    n4 = (n | (n >> 7) | (n >> 14) | (n >> 21)) & 0xFu;
+    n4 = 0;
+    if (valid4 != 0xFu) {                          // only a non-ACGT byte can be 'N' (uniform branch: rare)
+        uint32_t n = zero_bytes(w ^ 0x4E4E4E4Eu) >> 7;
+        n4 = (n | (n >> 7) | (n >> 14) | (n >> 21)) & 0xFu;
+    }
 }
 
 

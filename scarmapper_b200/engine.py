@@ -199,6 +199,11 @@ class ScarEngine:
     def launch_count(self) -> int:
         return int(self._L.scar_launch_count(self._ctx))
 
+    def info(self) -> dict:
+        b, s, k = C.c_int64(), C.c_int32(), C.c_int32()
+        N.check(self._L.scar_ctx_info(self._ctx, C.byref(b), C.byref(s), C.byref(k)))
+        return {"static_bytes": b.value, "tables_in_smem": bool(s.value), "anchor_targets": k.value}
+
     def window_counts(self, target: int):
         a, b = C.c_int32(), C.c_int32()
         N.check(self._L.scar_window_counts(self._ctx, target, C.byref(a), C.byref(b)))

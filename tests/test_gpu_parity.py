@@ -702,3 +702,15 @@ def test_gpu_fastq_indexer_matches_host_indexer_and_oracle():
         eng.process_fastq_text(np.frombuffer(b"@a:ACGT\nACGT\n+\nIIII\n", dtype=np.uint8))
     assert len(eng.process_fastq_text(np.frombuffer(b"@a:AC+GT\nACGT\n+\nIIII\n@trunc\nAC\n", dtype=np.uint8))) == 1
     eng.close()
+
+
+def test_context_info_config3_stays_in_shared_memory():
+    cfg = synth.make_config("C3", n_reads=10, seed=101)
+    eng = engine_for(synth_problem(cfg), cfg.read_len)
+    info = eng.info()
+    assert info["anchor_targets"] == 12 and info["tables_in_smem"] and info["static_bytes"] < 200 * 1024
+    eng.close()
+    blob = gu.load("c4_repeat_locus")
+    eng = engine_for(gu.problem_inputs(blob["case"]), 300)
+    assert eng.info()["anchor_targets"] == 0          # a 10-mer repeat forces the exhaustive scan
+    eng.close()
