@@ -246,6 +246,13 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
     if (cfg->n_targets < 1 || cfg->n_samples < 1 || cfg->n_samples >= 0xFFFF)
         return fail(SCAR_ERR_INVALID, "n_targets/n_samples out of range");
     if (cfg->platform < 0 || cfg->platform > 2) return fail(SCAR_ERR_INVALID, "unknown platform %d", cfg->platform);
+    if (!cfg->target_bytes || !cfg->target_off || !cfg->target_cutsite || !cfg->sample_target)
+        return fail(SCAR_ERR_INVALID, "target_bytes / target_off / target_cutsite / sample_target must not be NULL");
+    if ((cfg->left_index_bytes && !cfg->left_index_off) || (cfg->right_index_bytes && !cfg->right_index_off))
+        return fail(SCAR_ERR_INVALID, "index bytes given without offsets");
+    if (cfg->phase_off && (!cfg->phase_r1_bytes || !cfg->phase_r1_off || !cfg->phase_r2_bytes || !cfg->phase_r2_off))
+        return fail(SCAR_ERR_INVALID, "phase_off given without the phase string lists");
+    if (cfg->hr_len > 0 && !cfg->hr_donor) return fail(SCAR_ERR_INVALID, "hr_len > 0 with a NULL donor");
     if (cfg->max_read_len < 1 || cfg->max_read_len > 1024)
         return fail(SCAR_ERR_UNSUPPORTED, "max_read_len %d outside 1..1024", cfg->max_read_len);
     int ndev = 0;
@@ -807,6 +814,8 @@ static int ensure_hostbuf(scar_ctx *c, HostBuf &b, int64_t reads)
     if (reads <= b.reads_cap) return SCAR_OK;
     cudaFree(b.seq_off); cudaFree(b.f0_off); cudaFree(b.f1_off); cudaFree(b.seq_len); cudaFree(b.f0_len); cudaFree(b.f1_len);
     cudaFree(b.cells); cudaFree(b.lens); cudaFree(b.samples); cudaFree(b.records);
+    b.seq_off = b.f0_off = b.f1_off = nullptr; b.seq_len = b.f0_len = b.f1_len = nullptr;
+    b.cells = nullptr; b.lens = nullptr; b.samples = nullptr; b.records = nullptr;
     b.reads_cap = 0;
     const size_t n = (size_t)reads;
     CU(cudaMalloc((void **)&b.seq_off, (n + 1) * sizeof(int64_t)));
