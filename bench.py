@@ -12,7 +12,8 @@ A step is one pass of the hot path over the rank's batch:
   value : inputs (packed rows, raw bytes, index fields) already resident in HBM; the timed region is
           reset -> K2 demux -> K3 sliding window -> K4 aggregation (-> table merge across ranks when
           N > 1), CUDA events on the launching stream, barrier + synchronize on both sides, max over
-          ranks.  K1 (pack) is timed separately (stages_ms.k1_pack), as SURVEY.md §8d defines.
+          ranks.  K1 (pack) is timed separately (stages_ms.k1_pack), as SURVEY.md §8d defines;
+          from_raw_bytes is the same step INCLUDING K1 (scar_run_dev on raw read bytes in HBM).
   e2e   : the same batch from pinned HOST buffers through the public API (ScarEngine.process_host ->
           scar_process_host): H2D of reads + index fields, K2, K1, K3, K4, D2H of the 16-byte records.
   roofline : K3 (scar_window_kernel): algorithmic bytes = 182 B/read (150 read + 16 index + 16 record,
@@ -356,6 +357,20 @@ def main():
         dist.all_reduce(t)
         n_entries = int(t.item())
 
+    # the same step from RAW read bytes resident in HBM (scar_run_dev: K2, K1 pack, K3, K4), single stream
+    raw_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        eng.reset_async()
+        eng.run_resident(res, first_index=first)
+    barrier()
+    r0 = ev()
+    for _ in range(raw_steps):
+        eng.reset_async()
+        eng.run_resident(res, first_index=first)
+    r1 = ev()
+    barrier()
+    raw_ms = r0.elapsed_time(r1) / raw_steps
+
     # end-to-end arm: host buffers -> records on the host, through the public API
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -410,9 +425,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_s, k3], dtype=torch.float64, device="cuda")
+        t = torch.tensor([elapsed_ms, e2e_s, k3, raw_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_s, k3 = (float(x) for x in t.tolist())
+        elapsed_ms, e2e_s, k3, raw_ms = (float(x) for x in t.tolist())
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -449,6 +464,10 @@ def main():
                                         if world > 1 else ""),
                        "scar_patterns": int(n_entries), "unassigned_reads": int(un),
                        "table_slots": table_capacity},
+            "from_raw_bytes": {"value": world * n / (raw_ms * 1e-3), "unit": "reads/s", "ms_per_step": raw_ms,
+                               "steps": raw_steps,
+                               "timed_region": "reset, K2 demux, K1 pack, K3, K4 (scar_run_dev) from raw read bytes "
+                                               "resident in HBM; no cross-rank merge"},
             "stages_ms": {"k1_pack": k1_ms, "k2_demux": k2, "k3_window": k3, "k4_aggregate": k4,
                           "merge": merge_ms if world > 1 else 0.0},
             "roofline": {"bound": "hbm", "kernel": "scar_window_kernel (K3)", "achieved": achieved, "peak": peak,

@@ -12,43 +12,52 @@
 // the one-thread-per-read kernels downstream load coalesced.
 #include "scar_internal.cuh"
 
+// canonical-letter difference of four bytes: byte k of the result is 0 iff byte k of w is A, C, G or T.
+// The code (w>>1)&3 names the only letter the byte could be; 'A'|(w&6) is that letter for A, C, G and
+// 'E' for code 2, which +15 turns into 'T'.
+__device__ __forceinline__ uint32_t acgt_diff4(uint32_t w)
+{
+    const uint32_t t = ((w >> 2) & ~(w >> 1)) & 0x01010101u;            // 1 where the code is 2
+    const uint32_t canon = (0x41414141u | (w & 0x06060606u)) + t * 15u;
+    return w ^ canon;
+}
+
+// 0x80 flags of four bytes -> 4-bit mask (one multiply: the four partial products land on distinct bits)
+__device__ __forceinline__ uint32_t flags_to_nibble(uint32_t v) { return (v * 0x00204081u) >> 28; }
+
 __global__ void __launch_bounds__(256) scar_pack_kernel(const K1Params P)
 {
     // a CTA owns a tile of blockDim.x consecutive reads and walks their cells j = 0..W-1: the tile's
     // raw bytes (~38 KB at 150 nt) stay in L1 across the j loop, the stores of one j are coalesced
     const int64_t tiles = (P.n_reads + blockDim.x - 1) / blockDim.x;
+    const bool rc = P.platform == SCAR_PLATFORM_RAMSDEN;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t r = tile * blockDim.x + threadIdx.x;
         if (r >= P.n_reads) continue;
         const uint8_t *rp; int len;
         get_item(P.seq, r, rp, len);
-        const int64_t start = rp - P.seq.bytes;
         int slen = len, shift = 0;
         if (P.platform == SCAR_PLATFORM_TRUSEQ) { slen = len > 12 ? len - 12 : 0; shift = 6; }
         if (slen > 16 * P.W) { atomicOr(P.status, 1); slen = 16 * P.W; }
-        const bool rc = P.platform == SCAR_PLATFORM_RAMSDEN;
-        const uintptr_t base = (uintptr_t)P.seq.bytes;
+        // aligned words of the raw read: word k covers raw bytes 4k-mis .. 4k-mis+3
+        const uint32_t *rp4 = reinterpret_cast<const uint32_t *>((uintptr_t)rp & ~(uintptr_t)3);
+        const int mis = (int)((uintptr_t)rp & 3);
+        const int kend = (mis + len + 3) >> 2;          // never touches a word outside the read
         int n_count = 0;
-        for (int j = 0; j < P.W; ++j) {
-            uint64_t *out = P.cells + (int64_t)j * P.stride + r;
-            int nb = slen - 16 * j;                    // bases of this cell
+        uint64_t *out = P.cells + r;
+        for (int j = 0; j < P.W; ++j, out += P.stride) {
+            const int nb = slen - 16 * j;               // bases of this cell (may exceed 16)
             if (nb <= 0) { *out = 0ull; continue; }
-            if (nb > 16) nb = 16;
-            // 16-byte window of raw bytes: forward [ws, ws+16) holds stored bases 16j.. in order;
-            // reverse-complement: window ends at raw index len-16j, stored base k = comp(window[15-k])
-            const int64_t ws = rc ? start + (len - 16 * j) - 16 : start + shift + 16 * j;
-            const int64_t lo = rc ? start + (len - 16 * j) - nb : ws;          // first needed byte
-            const int64_t hi = rc ? start + (len - 16 * j) : ws + nb;          // one past the last
-            const uintptr_t a = base + (uintptr_t)ws;
-            const uintptr_t a0 = a & ~(uintptr_t)3;
-            const uint32_t sh = (uint32_t)(a & 3) * 8;
+            // 16-byte window of raw bytes: forward, window byte k is stored base 16j+k; reverse
+            // complement, the window ends at raw index len-16j and stored base k = comp(window[15-k])
+            const int q = mis + (rc ? len - 16 * j - 16 : shift + 16 * j);
+            const int k0 = q >> 2;                      // floor, q < 0 only in the last reverse cell
+            const uint32_t sh = (uint32_t)(q & 3) * 8;
             uint32_t w[5];
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                const uintptr_t wa = a0 + 4 * i;
-                // load only words that contain a needed byte (never touches memory outside the read)
-                const bool need = wa + 4 > base + (uintptr_t)lo && wa < base + (uintptr_t)hi;
-                w[i] = need ? __ldg(reinterpret_cast<const uint32_t *>(wa)) : 0u;
+                const int k = k0 + i;
+                w[i] = (k >= 0 && k < kend) ? __ldg(rp4 + k) : 0u;
             }
             uint32_t v[4];
 #pragma unroll
@@ -58,22 +67,32 @@ __global__ void __launch_bounds__(256) scar_pack_kernel(const K1Params P)
                 const uint32_t r2 = __byte_perm(v[1], 0, 0x0123), r3 = __byte_perm(v[0], 0, 0x0123);
                 v[0] = r0; v[1] = r1; v[2] = r2; v[3] = r3;
             }
-            uint32_t code = 0, valid = 0, nmask = 0;
+            // 2-bit codes: (w>>1)&3 per byte, gathered into the top byte by one multiply per word
+            uint32_t p[4], x[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                uint32_t c8, v4, n4;
-                classify4(v[i], c8, v4, n4);
-                code |= c8 << (8 * i); valid |= v4 << (4 * i); nmask |= n4 << (4 * i);
+                p[i] = ((v[i] >> 1) & 0x03030303u) * 0x01041040u;
+                x[i] = acgt_diff4(v[i]);
             }
+            uint32_t code = __byte_perm(__byte_perm(p[0], p[1], 0x0073), __byte_perm(p[2], p[3], 0x0073), 0x5410);
             if (rc) code ^= 0xAAAAAAAAu;                               // complement: code ^ 2
-            const uint32_t bm = nb == 16 ? 0xFFFFu : ((1u << nb) - 1u);
-            valid &= bm; nmask &= bm;
-            n_count += __popc(nmask);
-            // spread the ACGT mask to 2 bits per base to clear the codes of non-ACGT / absent bases
-            uint32_t m2 = valid;
-            m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
-            m2 = (m2 | (m2 << 2)) & 0x33333333u; m2 = (m2 | (m2 << 1)) & 0x55555555u;
-            code &= m2 * 3u;
+            uint32_t valid = 0xFFFFu, nmask = 0u;
+            if (nb < 16 || (x[0] | x[1] | x[2] | x[3]) != 0u) {        // rare: last cell, or a non-ACGT byte
+                valid = 0u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    valid |= flags_to_nibble(zero_bytes(x[i])) << (4 * i);
+                    nmask |= flags_to_nibble(zero_bytes(v[i] ^ 0x4E4E4E4Eu)) << (4 * i);
+                }
+                const uint32_t bm = nb >= 16 ? 0xFFFFu : ((1u << nb) - 1u);
+                valid &= bm; nmask &= bm;
+                n_count += __popc(nmask);
+                // spread the ACGT mask to 2 bits per base to clear the codes of non-ACGT / absent bases
+                uint32_t m2 = valid;
+                m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
+                m2 = (m2 | (m2 << 2)) & 0x33333333u; m2 = (m2 | (m2 << 1)) & 0x55555555u;
+                code &= m2 * 3u;
+            }
             *out = (uint64_t)code | ((uint64_t)valid << 32) | ((uint64_t)nmask << 48);
         }
         P.lens[r] = (uint32_t)slen | ((uint32_t)n_count << 16);     // length and literal-'N' count for the filter
