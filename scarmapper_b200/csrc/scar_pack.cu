@@ -6,10 +6,12 @@
 // applied on the way (INDEL_Processing.py:946 Illumina as is; :978,1181-1182 TruSeq seq[6:-6];
 // :981 Ramsden rcomp(seq)), so K3 always sees the sequence ScarSearch would be handed.
 //
-// One thread packs one read, one cell (16 bases) at a time: up to five aligned 32-bit loads covering
-// the cell's 16-byte window, a funnel-shift realignment, then SWAR classification of four bytes at a
-// time.  The output is cell-major ([cell][read]) so that each store of a warp is one 256-byte line and
-// the one-thread-per-read kernels downstream load coalesced.
+// A CTA takes tiles of 256 consecutive reads; the tile's raw bytes (one contiguous span of the input)
+// are brought into shared memory by ONE TMA bulk copy, then one thread packs one read, one cell
+// (16 bases) at a time: five aligned 32-bit loads covering the cell's 16-byte window, a funnel-shift
+// realignment, then SWAR classification of four bytes at a time.  The output is cell-major
+// ([cell][read]) so that each store of a warp is one 256-byte line and the one-thread-per-read
+// kernels downstream load coalesced.
 #include "scar_internal.cuh"
 
 // canonical-letter difference of four bytes: byte k of the result is 0 iff byte k of w is A, C, G or T.
@@ -22,80 +24,156 @@ __device__ __forceinline__ uint32_t acgt_diff4(uint32_t w)
     return w ^ canon;
 }
 
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // 0x80 flags of four bytes -> 4-bit mask (one multiply: the four partial products land on distinct bits)
 __device__ __forceinline__ uint32_t flags_to_nibble(uint32_t v) { return (v * 0x00204081u) >> 28; }
 
-__global__ void __launch_bounds__(256) scar_pack_kernel(const K1Params P)
+#define PACK_TILE_BYTES (55 * 1024)     // staged raw bytes of one 256-read tile; 4 CTAs per SM
+
+// pack one read.  STAGED: the tile's raw bytes are in shared memory (word k of the read at sword + 4k),
+// otherwise they are read from global memory through rp4.
+template <bool STAGED>
+__device__ __forceinline__ void pack_read(const K1Params &P, int64_t r, const uint32_t *rp4, uint32_t sword, int mis,
+                                          int len, bool rc)
 {
-    // a CTA owns a tile of blockDim.x consecutive reads and walks their cells j = 0..W-1: the tile's
-    // raw bytes (~38 KB at 150 nt) stay in L1 across the j loop, the stores of one j are coalesced
-    const int64_t tiles = (P.n_reads + blockDim.x - 1) / blockDim.x;
-    const bool rc = P.platform == SCAR_PLATFORM_RAMSDEN;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t r = tile * blockDim.x + threadIdx.x;
-        if (r >= P.n_reads) continue;
-        const uint8_t *rp; int len;
-        get_item(P.seq, r, rp, len);
-        int slen = len, shift = 0;
-        if (P.platform == SCAR_PLATFORM_TRUSEQ) { slen = len > 12 ? len - 12 : 0; shift = 6; }
-        if (slen > 16 * P.W) { atomicOr(P.status, 1); slen = 16 * P.W; }
-        // aligned words of the raw read: word k covers raw bytes 4k-mis .. 4k-mis+3
-        const uint32_t *rp4 = reinterpret_cast<const uint32_t *>((uintptr_t)rp & ~(uintptr_t)3);
-        const int mis = (int)((uintptr_t)rp & 3);
-        const int kend = (mis + len + 3) >> 2;          // never touches a word outside the read
-        int n_count = 0;
-        uint64_t *out = P.cells + r;
-        for (int j = 0; j < P.W; ++j, out += P.stride) {
-            const int nb = slen - 16 * j;               // bases of this cell (may exceed 16)
-            if (nb <= 0) { *out = 0ull; continue; }
-            // 16-byte window of raw bytes: forward, window byte k is stored base 16j+k; reverse
-            // complement, the window ends at raw index len-16j and stored base k = comp(window[15-k])
-            const int q = mis + (rc ? len - 16 * j - 16 : shift + 16 * j);
-            const int k0 = q >> 2;                      // floor, q < 0 only in the last reverse cell
-            const uint32_t sh = (uint32_t)(q & 3) * 8;
-            uint32_t w[5];
+    int slen = len, shift = 0;
+    if (P.platform == SCAR_PLATFORM_TRUSEQ) { slen = len > 12 ? len - 12 : 0; shift = 6; }
+    if (slen > 16 * P.W) { atomicOr(P.status, 1); slen = 16 * P.W; }
+    const int kend = (mis + len + 3) >> 2;          // aligned words that overlap the raw read
+    int n_count = 0;
+    uint64_t *out = P.cells + r;
+    for (int j = 0; j < P.W; ++j, out += P.stride) {
+        const int nb = slen - 16 * j;               // bases of this cell (may exceed 16)
+        if (nb <= 0) { *out = 0ull; continue; }
+        // 16-byte window of raw bytes: forward, window byte k is stored base 16j+k; reverse
+        // complement, the window ends at raw index len-16j and stored base k = comp(window[15-k])
+        const int q = mis + (rc ? len - 16 * j - 16 : shift + 16 * j);
+        const int k0 = q >> 2;                      // floor, q < 0 only in the last reverse cell
+        const uint32_t sh = (uint32_t)(q & 3) * 8;
+        uint32_t w[5];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int k = k0 + i;
-                w[i] = (k >= 0 && k < kend) ? __ldg(rp4 + k) : 0u;
+        for (int i = 0; i < 5; ++i) {
+            const int k = k0 + i;
+            w[i] = 0u;
+            if (k >= 0 && k < kend) {               // never touches a word outside the read
+                if (STAGED) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(sword + 4u * (uint32_t)k));
+                else w[i] = __ldg(rp4 + k);
             }
-            uint32_t v[4];
+        }
+        uint32_t v[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
-            if (rc) {   // reverse the 16 bytes
-                const uint32_t r0 = __byte_perm(v[3], 0, 0x0123), r1 = __byte_perm(v[2], 0, 0x0123);
-                const uint32_t r2 = __byte_perm(v[1], 0, 0x0123), r3 = __byte_perm(v[0], 0, 0x0123);
-                v[0] = r0; v[1] = r1; v[2] = r2; v[3] = r3;
-            }
-            // 2-bit codes: (w>>1)&3 per byte, gathered into the top byte by one multiply per word
-            uint32_t p[4], x[4];
+        for (int i = 0; i < 4; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
+        if (rc) {   // reverse the 16 bytes
+            const uint32_t r0 = __byte_perm(v[3], 0, 0x0123), r1 = __byte_perm(v[2], 0, 0x0123);
+            const uint32_t r2 = __byte_perm(v[1], 0, 0x0123), r3 = __byte_perm(v[0], 0, 0x0123);
+            v[0] = r0; v[1] = r1; v[2] = r2; v[3] = r3;
+        }
+        // 2-bit codes: (w>>1)&3 per byte, gathered into the top byte by one multiply per word
+        uint32_t p[4], x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            p[i] = ((v[i] >> 1) & 0x03030303u) * 0x01041040u;
+            x[i] = acgt_diff4(v[i]);
+        }
+        uint32_t code = __byte_perm(__byte_perm(p[0], p[1], 0x0073), __byte_perm(p[2], p[3], 0x0073), 0x5410);
+        if (rc) code ^= 0xAAAAAAAAu;                               // complement: code ^ 2
+        uint32_t valid = 0xFFFFu, nmask = 0u;
+        if (nb < 16 || (x[0] | x[1] | x[2] | x[3]) != 0u) {        // rare: last cell, or a non-ACGT byte
+            valid = 0u;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                p[i] = ((v[i] >> 1) & 0x03030303u) * 0x01041040u;
-                x[i] = acgt_diff4(v[i]);
+                valid |= flags_to_nibble(zero_bytes(x[i])) << (4 * i);
+                nmask |= flags_to_nibble(zero_bytes(v[i] ^ 0x4E4E4E4Eu)) << (4 * i);
             }
-            uint32_t code = __byte_perm(__byte_perm(p[0], p[1], 0x0073), __byte_perm(p[2], p[3], 0x0073), 0x5410);
-            if (rc) code ^= 0xAAAAAAAAu;                               // complement: code ^ 2
-            uint32_t valid = 0xFFFFu, nmask = 0u;
-            if (nb < 16 || (x[0] | x[1] | x[2] | x[3]) != 0u) {        // rare: last cell, or a non-ACGT byte
-                valid = 0u;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    valid |= flags_to_nibble(zero_bytes(x[i])) << (4 * i);
-                    nmask |= flags_to_nibble(zero_bytes(v[i] ^ 0x4E4E4E4Eu)) << (4 * i);
-                }
-                const uint32_t bm = nb >= 16 ? 0xFFFFu : ((1u << nb) - 1u);
-                valid &= bm; nmask &= bm;
-                n_count += __popc(nmask);
-                // spread the ACGT mask to 2 bits per base to clear the codes of non-ACGT / absent bases
-                uint32_t m2 = valid;
-                m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
-                m2 = (m2 | (m2 << 2)) & 0x33333333u; m2 = (m2 | (m2 << 1)) & 0x55555555u;
-                code &= m2 * 3u;
-            }
-            *out = (uint64_t)code | ((uint64_t)valid << 32) | ((uint64_t)nmask << 48);
+            const uint32_t bm = nb >= 16 ? 0xFFFFu : ((1u << nb) - 1u);
+            valid &= bm; nmask &= bm;
+            n_count += __popc(nmask);
+            // spread the ACGT mask to 2 bits per base to clear the codes of non-ACGT / absent bases
+            uint32_t m2 = valid;
+            m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
+            m2 = (m2 | (m2 << 2)) & 0x33333333u; m2 = (m2 | (m2 << 1)) & 0x55555555u;
+            code &= m2 * 3u;
         }
-        P.lens[r] = (uint32_t)slen | ((uint32_t)n_count << 16);     // length and literal-'N' count for the filter
+        *out = (uint64_t)code | ((uint64_t)valid << 32) | ((uint64_t)nmask << 48);
+    }
+    P.lens[r] = (uint32_t)slen | ((uint32_t)n_count << 16);     // length and literal-'N' count for the filter
+}
+
+__global__ void __launch_bounds__(256, 4) scar_pack_kernel(const K1Params P)
+{
+    // A CTA owns tiles of 256 consecutive reads.  The raw bytes of a tile are one contiguous span of the
+    // input (CSR / fixed stride; also FASTQ views in file order): ONE TMA bulk copy brings the span into
+    // shared memory (coalesced, no register traffic), then each thread packs its read out of shared
+    // memory with word loads.  A span that does not fit (very long reads, scattered views) is read
+    // straight from global memory instead.  The stores of one cell index j are coalesced either way.
+    extern __shared__ __align__(128) unsigned char tile_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile_raw);
+    unsigned char *tile = tile_raw + 16;
+    __shared__ unsigned long long s_lo, s_hi;
+    __shared__ unsigned long long s_red[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    const bool views = P.seq.offsets && P.seq.lengths;
+    const bool rc = P.platform == SCAR_PLATFORM_RAMSDEN;
+    const int64_t tiles = (P.n_reads + blockDim.x - 1) / blockDim.x;
+    for (int64_t tile_no = blockIdx.x; tile_no < tiles; tile_no += gridDim.x) {
+        const int64_t r0 = tile_no * blockDim.x;
+        const int64_t r = r0 + threadIdx.x;
+        const bool active = r < P.n_reads;
+        const uint8_t *rp = P.seq.bytes; int len = 0;
+        if (active) get_item(P.seq, r, rp, len);
+        // span of the tile: [lo, hi) as addresses
+        if (views) {                                  // arbitrary order: min start / max end over the tile
+            unsigned long long a = active ? (unsigned long long)(uintptr_t)rp : ~0ull;
+            unsigned long long b = active ? (unsigned long long)(uintptr_t)rp + (unsigned long long)len : 0ull;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                const unsigned long long a2 = __shfl_xor_sync(0xFFFFFFFFu, a, d), b2 = __shfl_xor_sync(0xFFFFFFFFu, b, d);
+                a = a2 < a ? a2 : a; b = b2 > b ? b2 : b;
+            }
+            if (lane == 0) { s_red[0][warp] = a; s_red[1][warp] = b; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int i = 1; i < 8; ++i) { a = s_red[0][i] < a ? s_red[0][i] : a; b = s_red[1][i] > b ? s_red[1][i] : b; }
+                s_lo = a; s_hi = b;
+            }
+        } else if (threadIdx.x == 0) {                // monotonic layouts: first read's start, last read's end
+            const int64_t rl = (r0 + blockDim.x <= P.n_reads ? r0 + blockDim.x : P.n_reads) - 1;
+            const uint8_t *q; int ql;
+            get_item(P.seq, rl, q, ql);
+            s_lo = (unsigned long long)(uintptr_t)rp; s_hi = (unsigned long long)(uintptr_t)q + (unsigned long long)ql;
+        }
+        __syncthreads();
+        const unsigned long long lo16 = s_lo & ~15ull;
+        const unsigned long long span = s_hi > lo16 ? ((s_hi - lo16 + 15ull) & ~15ull) : 0ull;
+        const bool staged = span != 0ull && span <= (unsigned long long)PACK_TILE_BYTES;
+        if (staged) {
+            if (threadIdx.x == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                             "r"((uint32_t)span) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_addr(tile)), "l"(lo16), "r"((uint32_t)span), "r"(smem_addr(bar)) : "memory");
+            }
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                             "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+            }
+            parity ^= 1u;
+        }
+        if (active) {
+            const uintptr_t a4 = (uintptr_t)rp & ~(uintptr_t)3;
+            const int mis = (int)((uintptr_t)rp & 3);
+            if (staged) pack_read<true>(P, r, nullptr, smem_addr(tile) + (uint32_t)(a4 - lo16), mis, len, rc);
+            else pack_read<false>(P, r, reinterpret_cast<const uint32_t *>(a4), 0u, mis, len, rc);
+        }
+        __syncthreads();                              // the tile buffer and s_lo / s_hi are reused
     }
 }
 
@@ -108,9 +186,12 @@ cudaError_t scar_launch_pack(const scar_ragged &seq, int64_t n, int W, int platf
     P.platform = platform; P.status = status;
     const int threads = 256;
     int64_t blocks = (n + threads - 1) / threads;
-    const int64_t cap = (int64_t)sm_count * 8;          // 8 resident CTAs per SM, grid-stride over tiles
+    const int64_t cap = (int64_t)sm_count * 4;          // 4 resident CTAs per SM, grid-stride over tiles
     if (blocks > cap) blocks = cap;
-    scar_pack_kernel<<<(unsigned)blocks, threads, 0, stream>>>(P);
+    const int smem = PACK_TILE_BYTES + 16;
+    cudaError_t e = cudaFuncSetAttribute(scar_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;     // per device, cheap; a process may hold contexts on several devices
+    scar_pack_kernel<<<(unsigned)blocks, threads, smem, stream>>>(P);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
