@@ -127,6 +127,7 @@ struct scar_ctx {
     uint8_t *d_class_map = nullptr; DemuxString *d_right = nullptr, *d_left = nullptr; uint64_t *d_peq = nullptr;
     uint16_t *d_first_sample = nullptr; int n_right = 0, n_left = 0, n_classes = 0;
     uint8_t *d_fast_codes = nullptr; int demux_fast = 0;
+    uint64_t *d_lut_right = nullptr, *d_lut_left = nullptr; int lut_n_right = 0, lut_n_left = 0;
     ScarTableSlot *d_slots = nullptr; uint64_t capacity = 0;
     unsigned long long *d_acc = nullptr;   // [n_entries, unassigned, collisions, export_count] + counters + phase hist
     unsigned long long *d_n_entries = nullptr, *d_unassigned = nullptr, *d_collisions = nullptr, *d_export_n = nullptr;
@@ -158,6 +159,7 @@ extern "C" void scar_ctx_destroy(scar_ctx *c)
     for (auto &b : c->buf) free_hostbuf(b);
     cudaFree(c->d_sample_target); cudaFree(c->d_blob);
     cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample); cudaFree(c->d_fast_codes);
+    cudaFree(c->d_lut_right); cudaFree(c->d_lut_left);
     cudaFree(c->d_slots); cudaFree(c->d_acc); cudaFree(c->d_status);
     cudaFree(c->d_text); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offsets); cudaFree(c->d_nl);
     delete c;
@@ -236,6 +238,38 @@ static int build_demux(scar_ctx *c, const scar_config *cfg)
     if ((rc = upload(&c->d_left, hl))) return rc;
     if ((rc = upload(&c->d_peq, peq))) return rc;
     if ((rc = upload(&c->d_first_sample, first))) return rc;
+    // Direct tables: when every distinct string of a side has the same length n <= 8 (Illumina 8, TruSeq 6),
+    // the set of strings that accept a field is tabulated for every all-ACGT field of n bases (4^n entries,
+    // indexed by the field's 2-bit code) with the arithmetic K2 uses (accepts(): match_maker <= mismatch).
+    if (all_fast && c->platform != SCAR_PLATFORM_RAMSDEN) {
+        for (int side = 0; side < 2; ++side) {
+            const auto &v = side ? left_s : right_s;
+            const auto &hs = side ? hl : hr;
+            if (v.empty()) continue;
+            const size_t n = v[0].size();
+            bool same = n >= 1 && n <= 8;
+            for (const auto &x : v) same = same && x.size() == n;
+            if (!same) continue;
+            std::vector<uint64_t> lut((size_t)1 << (2 * n));
+            uint8_t u[8];
+            const uint64_t no_code[2] = {0, 0};
+            for (size_t code = 0; code < lut.size(); ++code) {
+                for (size_t k = 0; k < n; ++k) u[k] = (uint8_t)"ACTG"[(code >> (2 * k)) & 3];
+                uint64_t m = 0;
+                for (size_t d = 0; d < v.size(); ++d) {
+                    int h = 0;                         // equal lengths: Hamming decides for mismatch <= 1
+                    for (size_t k = 0; k < n; ++k) h += u[k] != (uint8_t)v[d][k];
+                    bool ok = h <= c->mismatch;
+                    if (!ok && c->mismatch > 1)
+                        ok = accepts(hs[d], peq.data(), u, (int)n, no_code, cmap.data(), c->mismatch, false);
+                    if (ok) m |= 1ull << d;
+                }
+                lut[code] = m;
+            }
+            if ((rc = upload(side ? &c->d_lut_left : &c->d_lut_right, lut))) return rc;
+            (side ? c->lut_n_left : c->lut_n_right) = (int)n;
+        }
+    }
     return SCAR_OK;
 }
 
@@ -521,6 +555,7 @@ extern "C" int scar_demux_dev(scar_ctx *c, const scar_ragged *seq, const scar_ra
     P.peq = c->d_peq; P.first_sample = c->d_first_sample; P.n_right = c->n_right; P.n_left = c->n_left;
     P.n_classes = c->n_classes; P.platform = c->platform; P.mismatch = c->mismatch;
     P.fast_codes = c->d_fast_codes; P.fast = c->demux_fast;
+    P.lut_right = c->d_lut_right; P.lut_left = c->d_lut_left; P.lut_n_right = c->lut_n_right; P.lut_n_left = c->lut_n_left;
     CU(scar_launch_demux(P, c->sm_count, (cudaStream_t)stream, &c->launches));
     return SCAR_OK;
 }

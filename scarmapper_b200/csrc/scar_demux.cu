@@ -26,9 +26,9 @@ __device__ __forceinline__ void encode16(const uint8_t *u, int n, uint32_t &code
     const uintptr_t a = (uintptr_t)u, a0 = a & ~(uintptr_t)3;
     if (n == 8 && (a & 7) == 0) {                 // the usual Illumina field: one aligned 8-byte load
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a));
-        uint32_t c8, v4, n4, c8b, v4b;
-        classify4(v.x, c8, v4, n4);
-        classify4(v.y, c8b, v4b, n4);
+        uint32_t c8, v4, c8b, v4b;
+        classify4(v.x, c8, v4);
+        classify4(v.y, c8b, v4b);
         code = c8 | (c8b << 8); valid = v4 | (v4b << 4);
         return;
     }
@@ -43,8 +43,8 @@ __device__ __forceinline__ void encode16(const uint8_t *u, int n, uint32_t &code
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         if (4 * i < n) {                          // (8-nt Illumina fields: two words)
-            uint32_t c8, v4, n4;
-            classify4(__funnelshift_r(w[i], w[i + 1], sh), c8, v4, n4);
+            uint32_t c8, v4;
+            classify4(__funnelshift_r(w[i], w[i + 1], sh), c8, v4);
             code |= c8 << (8 * i); valid |= v4 << (4 * i);
         }
     }
@@ -118,22 +118,29 @@ __global__ void __launch_bounds__(256) scar_demux_kernel(const K2Params P)
             // other lengths go to the slow list (quick reject / bit-vector edit distance)
             // bit d of `hit`: Hamming(u, string d) <= t over the first 16 positions; strings of another length
             // are masked out with the per-length bit mask and go to the slow list
-            const uint64_t all_r = P.n_right >= 64 ? ~0ull : ((1ull << P.n_right) - 1ull);
+            // an all-ACGT field of the tabulated length: the accepted strings of EVERY such field were
+            // worked out at context creation (same arithmetic), one load answers the side
             uint32_t hit_lo = 0, hit_hi = 0;
+            uint64_t hit, eq, slow;
+            if (P.lut_right && n0 == P.lut_n_right && x0 == 0u) ok_r = __ldg(P.lut_right + e0);
+            else {
+            const uint64_t all_r = P.n_right >= 64 ? ~0ull : ((1ull << P.n_right) - 1ull);
             for (int d = 0; d < P.n_right; ++d) {
                 const uint32_t x = e0 ^ s_code[0][d];
                 const uint32_t h = __popc(((x | (x >> 1)) & 0x55555555u) | x0) <= thr ? 1u : 0u;
                 if (d < 32) hit_lo |= h << d; else hit_hi |= h << (d - 32);
             }
-            uint64_t hit = ((uint64_t)hit_hi << 32) | hit_lo;
-            uint64_t eq = n0 <= 16 ? s_lenmask[0][n0] : 0ull;
+            hit = ((uint64_t)hit_hi << 32) | hit_lo;
+            eq = n0 <= 16 ? s_lenmask[0][n0] : 0ull;
             ok_r = hit & eq;
-            uint64_t slow = all_r & (~eq | (thr > 1 ? ~hit : 0ull));
+            slow = all_r & (~eq | (thr > 1 ? ~hit : 0ull));
             for (uint64_t a = slow; a; a &= a - 1) {
                 const int d = __ffsll((long long)a) - 1;
                 if (accepts(P.right[d], P.peq, u0, n0, c0, cmap, thr, false)) ok_r |= 1ull << d;
             }
-            if (ok_r) {
+            }
+            if (ok_r && P.lut_left && n1 == P.lut_n_left && x1 == 0u) ok_l = __ldg(P.lut_left + e1);
+            else if (ok_r) {
                 const uint64_t all_l = P.n_left >= 64 ? ~0ull : ((1ull << P.n_left) - 1ull);
                 hit_lo = hit_hi = 0;
                 for (int d = 0; d < P.n_left; ++d) {

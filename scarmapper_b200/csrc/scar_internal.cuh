@@ -86,23 +86,25 @@ __device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
     return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
 }
 
-// four bytes -> 8-bit codes, 4-bit ACGT mask, 4-bit N mask
-__device__ __forceinline__ void classify4(uint32_t w, uint32_t &code8, uint32_t &valid4, uint32_t &n4)
+// canonical-letter difference of four bytes: byte k of the result is 0 iff byte k of w is A, C, G or T.
+// The code (w>>1)&3 names the only letter the byte could be; 'A'|(w&6) is that letter for A, C, G and
+// 'E' for code 2, which +15 turns into 'T'.
+__device__ __forceinline__ uint32_t acgt_diff4(uint32_t w)
 {
-    uint32_t c = (w >> 1) & 0x03030303u;           // A=0 C=1 T=2 G=3 in each byte
-    uint32_t t = c | (c >> 6);
-    code8 = (t | (t >> 12)) & 0xFFu;
-    // canonical letter of each code, then compare with the input byte
-    uint32_t sel = (c & 0x3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
-    uint32_t canon = __byte_perm(0x47544341u /* 'A','C','T','G' */, 0u, sel);
-    uint32_t v = zero_bytes(w ^ canon);            // 0x80 per valid byte
-    v = (v >> 7);
-    valid4 = (v | (v >> 7) | (v >> 14) | (v >> 21)) & 0xFu;
-    n4 = 0;
-    if (valid4 != 0xFu) {                          // only a non-ACGT byte can be 'N' (uniform branch: rare)
-        uint32_t n = zero_bytes(w ^ 0x4E4E4E4Eu) >> 7;
-        n4 = (n | (n >> 7) | (n >> 14) | (n >> 21)) & 0xFu;
-    }
+    const uint32_t t = ((w >> 2) & ~(w >> 1)) & 0x01010101u;            // 1 where the code is 2
+    const uint32_t canon = (0x41414141u | (w & 0x06060606u)) + t * 15u;
+    return w ^ canon;
+}
+
+// 0x80 flags of four bytes -> 4-bit mask (one multiply: the four partial products land on distinct bits)
+__device__ __forceinline__ uint32_t flags_to_nibble(uint32_t v) { return (v * 0x00204081u) >> 28; }
+
+// four bytes -> 8-bit codes (A=0 C=1 T=2 G=3, one multiply gathers them), 4-bit ACGT mask
+__device__ __forceinline__ void classify4(uint32_t w, uint32_t &code8, uint32_t &valid4)
+{
+    code8 = (((w >> 1) & 0x03030303u) * 0x01041040u) >> 24;
+    const uint32_t x = acgt_diff4(w);
+    valid4 = x ? flags_to_nibble(zero_bytes(x)) : 0xFu;
 }
 
 
@@ -134,6 +136,10 @@ struct K2Params {
     int32_t platform, mismatch;
     int32_t fast;              // every index string is ACGT-only and <= 16 nt: 2-bit Hamming shortcut
     int32_t pad;
+    // direct tables (fast only, every distinct string of the side n <= 8 nt long): accepted-string mask of
+    // every possible all-ACGT field of n bases, indexed by its 2-bit code; null when not applicable
+    const uint64_t *lut_right, *lut_left;
+    int32_t lut_n_right, lut_n_left;
 };
 
 struct K3Params {

@@ -14,20 +14,7 @@
 // kernels downstream load coalesced.
 #include "scar_internal.cuh"
 
-// canonical-letter difference of four bytes: byte k of the result is 0 iff byte k of w is A, C, G or T.
-// The code (w>>1)&3 names the only letter the byte could be; 'A'|(w&6) is that letter for A, C, G and
-// 'E' for code 2, which +15 turns into 'T'.
-__device__ __forceinline__ uint32_t acgt_diff4(uint32_t w)
-{
-    const uint32_t t = ((w >> 2) & ~(w >> 1)) & 0x01010101u;            // 1 where the code is 2
-    const uint32_t canon = (0x41414141u | (w & 0x06060606u)) + t * 15u;
-    return w ^ canon;
-}
-
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// 0x80 flags of four bytes -> 4-bit mask (one multiply: the four partial products land on distinct bits)
-__device__ __forceinline__ uint32_t flags_to_nibble(uint32_t v) { return (v * 0x00204081u) >> 28; }
 
 #define PACK_TILE_BYTES (55 * 1024)     // staged raw bytes of one 256-read tile; 4 CTAs per SM
 
