@@ -279,8 +279,136 @@ __device__ __forceinline__ void store_record(scar_record *dst, const scar_record
     *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(&rec);
 }
 
+// ---- anchor-and-extend steps.  A junction search alternates two steps until it is resolved:
+//   anchor: one probe of the position table at p; when the window lies on the far side of the cut the flank
+//           is verified against the locus 32 bases per XOR and the scan jumps over it;
+//   batch : the next SCAR_ANCHOR_BATCH positions probed back to back (around a mismatch or the junction).
+// Each returns true while the search is still open (p updated) and false when it is finished (clj/tlj or
+// crj/trj set, or left at "not found").
+struct LocusRef {                  // what a step needs to know about the read's target
+    uint32_t pos_off, mult, nbuckets;
+    const uint32_t *tw;
+    int cut, L;
+};
+
+template <bool SMEM>
+__device__ __forceinline__ bool left_anchor(ReadCursor &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int &p,
+                                            int &clj, int &tlj)
+{
+    // left junction (SlidingWindow.pyx:49-69): the largest p in 16 .. len-20 whose window is a left window,
+    // i.e. lies at locus position 6 <= t <= cut-10 (window i = cut-10-t)
+    const uint32_t t = locus_position<SMEM>(rc, ptab, T.mult, T.nbuckets, p);
+    if (t != 0xFFFFFFFFu && (int)t > T.cut - 10) {
+        const int need = (int)t - (T.cut - 10), limit = min(need, p - 16);
+        const int k = match_left<SMEM>(rc, T.tw, p, (int)t, limit);
+        if (k == limit) {                              // the whole stretch is locus sequence
+            if (limit == need) { clj = p - need + 10; tlj = T.cut; }
+            return false;                              // else: ran out of read positions
+        }
+        p -= k + 1;                                    // windows p-1 .. p-k are right of the cut
+        return true;
+    }
+    if (t != 0xFFFFFFFFu && t >= 6u) { clj = p + 10; tlj = (int)t + 10; return false; }
+    return --p >= 16;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ bool left_batch(ReadCursor &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int &p,
+                                           int &clj, int &tlj)
+{
+    // batch width: a clean deletion's junction window is the 10th position past the break, 1-3 nt
+    // insertions push it to the 11th-13th; wider batches cost every read, narrower ones cost rounds
+    constexpr int NB = SCAR_ANCHOR_BATCH;
+    constexpr uint32_t NBMASK = (1u << NB) - 1u;
+    const int b = p - (NB - 1);                        // positions p, p-1, .. b; b >= 0 because p >= 16
+    uint32_t wlo, whi, vlo, vhi, m[NB];
+    rc.word16(b + 16, whi, vhi);
+    rc.word16(b, wlo, vlo);
+    probe_n<SMEM, NB>(ptab, wlo, whi, T.mult, T.nbuckets, m);
+    // left window iff (t - 6) <= cut-16: one bit per position, then the first in scan order
+    uint32_t hm = 0;
+#pragma unroll
+    for (int o = 0; o < NB; ++o) hm |= ((m[o] - 6u) <= (uint32_t)(T.cut - 16)) ? (1u << o) : 0u;
+    if (hm) hm &= runs_of_ten(vlo | (vhi << 16)) & (b >= 16 ? NBMASK : ((NBMASK << (16 - b)) & NBMASK));
+    if (hm) {
+        const int o = 31 - __clz(hm);                  // highest position = first going down
+        uint32_t t = 0;
+#pragma unroll
+        for (int q = 0; q < NB; ++q) t = (q == o) ? m[q] : t;
+        clj = b + o + 10; tlj = (int)t + 10;
+        return false;
+    }
+    p = b - 1;
+    return p >= 16;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ bool right_anchor(ReadCursor &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int plast,
+                                             int &p, int &crj, int &trj)
+{
+    // right junction (SlidingWindow.pyx:79-93): the smallest p in 10 .. len-26 whose window is a right window,
+    // i.e. lies at locus position cut <= t <= L-16 (window i = t-cut)
+    const uint32_t t = locus_position<SMEM>(rc, ptab, T.mult, T.nbuckets, p);
+    if (t != 0xFFFFFFFFu && (int)t < T.cut) {
+        const int need = T.cut - (int)t, limit = min(need, plast - p);
+        const int k = match_right<SMEM>(rc, T.tw, p + 10, (int)t + 10, limit);
+        if (k == limit) {
+            if (limit == need) { crj = p + need; trj = T.cut; }
+            return false;
+        }
+        p += k + 1;                                    // windows p+1 .. p+k are left of the cut
+        return true;
+    }
+    if (t != 0xFFFFFFFFu && (int)t <= T.L - 16) { crj = p; trj = (int)t; return false; }
+    return ++p <= plast;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ bool right_batch(ReadCursor &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int plast,
+                                            int &p, int &crj, int &trj)
+{
+    constexpr int NB = SCAR_ANCHOR_BATCH;
+    constexpr uint32_t NBMASK = (1u << NB) - 1u;
+    uint32_t wlo, whi, vlo, vhi, m[NB];
+    rc.word16(p, wlo, vlo);                            // positions p .. p+NB-1
+    rc.word16(p + 16, whi, vhi);
+    probe_n<SMEM, NB>(ptab, wlo, whi, T.mult, T.nbuckets, m);
+    const uint32_t span = (uint32_t)(T.L - 16 - T.cut);   // right window iff (t - cut) <= span
+    uint32_t hm = 0;
+#pragma unroll
+    for (int o = 0; o < NB; ++o) hm |= ((m[o] - (uint32_t)T.cut) <= span) ? (1u << o) : 0u;
+    if (hm) {
+        const int top = plast - p;                     // >= 0
+        hm &= runs_of_ten(vlo | (vhi << 16)) & (top >= NB - 1 ? NBMASK : ((2u << top) - 1u));
+    }
+    if (hm) {
+        const int o = __ffs(hm) - 1;                   // lowest position = first going up
+        uint32_t t = 0;
+#pragma unroll
+        for (int q = 0; q < NB; ++q) t = (q == o) ? m[q] : t;
+        crj = p + o; trj = (int)t;
+        return false;
+    }
+    p += NB;
+    return p <= plast;
+}
+
+// append the lanes with `pending` to a CTA queue: one shared-memory atomic per warp
+__device__ __forceinline__ void queue_push(bool pending, uint32_t item, uint32_t *queue, int dir, uint32_t *counter)
+{
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pending);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == __ffs(mask) - 1) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mask) - 1);
+    if (pending) queue[dir * (int)(base + __popc(mask & ((1u << lane) - 1u)))] = item;
+}
+
+#define K3_TILE 256
+
 template <bool SMEM, bool HR>
-__global__ void __launch_bounds__(256, SCAR_K3_MIN_CTAS) scar_window_kernel(const K3Params P)
+__global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(const K3Params P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [mbarrier 16 B][static blob: tables | target metas | phases | N-limit table]
@@ -295,12 +423,22 @@ __global__ void __launch_bounds__(256, SCAR_K3_MIN_CTAS) scar_window_kernel(cons
     const uint16_t *nmax = reinterpret_cast<const uint16_t *>(blob + P.nmax_off);
     const int64_t S = P.stride;      // reads per cell row
 
-    // Warps walk the batch in lock step (uniform trip count) and early exits are flags, not jumps, so
-    // that the lanes of a warp re-converge (__syncwarp) after each variable-length scan instead of
-    // running the rest of the body in separate passes.
-    const int64_t n_round = (P.n_reads + 31) & ~(int64_t)31;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_round;
-         r += (int64_t)gridDim.x * blockDim.x) {
+    // A CTA takes tiles of 256 reads.  Phase 1 is one thread per read: phasing, filters, and the FIRST anchor
+    // step of both junction searches (a wild-type read is finished there).  Searches that are still open
+    // become items (read, position) in a shared-memory queue - left items from the front, right items from
+    // the back - and are then worked off in rounds by WHICHEVER thread comes next (batch step + anchor step,
+    // re-queued while open), so every warp of a round runs one code path with all lanes busy instead of
+    // waiting for the slowest read of the warp.  Phase 3 is one thread per read again: junction call, record.
+    __shared__ uint32_t s_left[K3_TILE], s_right[K3_TILE];   // clj | tlj << 16,  crj | trj << 16
+    __shared__ uint32_t s_ctx[K3_TILE];                      // stored length | target id << 16
+    __shared__ uint32_t s_queue[2][2 * K3_TILE];             // item = local read | p << 8
+    __shared__ uint32_t s_count[3][2];                       // [round % 3][side]
+    if (threadIdx.x < 6) s_count[threadIdx.x >> 1][threadIdx.x & 1] = 0;
+    __syncthreads();
+    uint32_t round = 0;
+
+    for (int64_t tile = (int64_t)blockIdx.x * K3_TILE; tile < P.n_reads; tile += (int64_t)gridDim.x * K3_TILE) {
+        const int64_t r = tile + threadIdx.x;
         bool live = r < P.n_reads;
         __align__(16) scar_record rec;
         rec.status = SCAR_ST_UNASSIGNED; rec.flags = 0; rec.sample = SCAR_SAMPLE_NONE;
@@ -371,118 +509,28 @@ __global__ void __launch_bounds__(256, SCAR_K3_MIN_CTAS) scar_window_kernel(cons
             }
         }
 
-        // ---- both junctions, anchor-and-extend path.  The loops are warp-synchronous: every round does
-        // (1) one anchor probe + flank verification and (2) one batch of 16 back-to-back probes, for all
-        // lanes that are still scanning, so the lanes of a warp stay in step.
+
+        // ---- phase 1: first anchor step of both searches (loci whose 10-mers are all distinct)
+        const bool fast = live && T.fast;
         {
-            // batch width: a clean deletion's junction window is the 10th position past the break, 1-3 nt
-            // insertions push it to the 11th-13th; wider batches cost every read, narrower ones cost rounds
-            constexpr int NB = SCAR_ANCHOR_BATCH;
-            constexpr uint32_t NBMASK = (1u << NB) - 1u;
-            const bool fast = live && T.fast;
             const TableRef<SMEM> ptab(blob, P.blob, T.pos_off);
-            const uint32_t *tw = reinterpret_cast<const uint32_t *>(blob + T.tw_off);
-            const uint32_t mult = T.pos_mult, nb = T.pos_buckets;
+            LocusRef LR; LR.mult = T.pos_mult; LR.nbuckets = T.pos_buckets; LR.cut = cut; LR.L = T.length;
+            LR.tw = reinterpret_cast<const uint32_t *>(blob + T.tw_off);
             ReadCursor rc; rc.col = col; rc.S = S; rc.Wr = Wr;
-            const int L = T.length;
-
-            // left junction (SlidingWindow.pyx:49-69): the largest p in 16 .. len-20 whose window is a left
-            // window, i.e. lies at locus position 6 <= t <= cut-10 (window i = cut-10-t)
             int p = len - 20;
-            bool scanning = fast && p >= 16;
-            while (__any_sync(0xFFFFFFFFu, scanning)) {
-                if (scanning) {                                    // (1) anchor at p
-                    const uint32_t t = locus_position<SMEM>(rc, ptab, mult, nb, p);
-                    if (t != 0xFFFFFFFFu && (int)t > cut - 10) {
-                        const int need = (int)t - (cut - 10), limit = min(need, p - 16);
-                        const int k = match_left<SMEM>(rc, tw, p, (int)t, limit);
-                        if (k == limit) {                          // the whole stretch is locus sequence
-                            if (limit == need) { clj = p - need + 10; tlj = cut; }
-                            scanning = false;                      // else: ran out of read positions
-                        } else p -= k + 1;                         // windows p-1 .. p-k are right of the cut
-                    } else if (t != 0xFFFFFFFFu && t >= 6u) {
-                        clj = p + 10; tlj = (int)t + 10; scanning = false;
-                    } else if (--p < 16) scanning = false;
-                }
-                __syncwarp();
-                if (scanning) {                                    // (2) positions p, p-1, .. p-NB+1 in one batch
-                    const int b = p - (NB - 1);                    // >= 0 because p >= 16
-                    uint32_t wlo, whi, vlo, vhi, m[NB];
-                    rc.word16(b + 16, whi, vhi);
-                    rc.word16(b, wlo, vlo);
-                    probe_n<SMEM, NB>(ptab, wlo, whi, mult, nb, m);
-                    // left window iff (t - 6) <= cut-16: one bit per position, then the first in scan order
-                    uint32_t hm = 0;
-#pragma unroll
-                    for (int o = 0; o < NB; ++o) hm |= ((m[o] - 6u) <= (uint32_t)(cut - 16)) ? (1u << o) : 0u;
-                    if (hm) hm &= runs_of_ten(vlo | (vhi << 16)) & (b >= 16 ? NBMASK : ((NBMASK << (16 - b)) & NBMASK));
-                    if (hm) {
-                        const int o = 31 - __clz(hm);              // highest position = first going down
-                        uint32_t t = 0;
-#pragma unroll
-                        for (int q = 0; q < NB; ++q) t = (q == o) ? m[q] : t;
-                        clj = b + o + 10; tlj = (int)t + 10; scanning = false;
-                    }
-                    if (scanning) { p = b - 1; if (p < 16) scanning = false; }
-                }
-                __syncwarp();
-            }
-            if (fast && clj && T.cutwindow_key != 0xFFFFFFFFu) {   // SlidingWindow.pyx:56-60 (per-read drop-in only)
-                uint32_t code, valid;
-                rc.word16(clj - 10, code, valid);
-                if ((code & SCAR_KEY_MASK) == T.cutwindow_key) {
-                    rec.status = SCAR_ST_NO_CUT; rec.flags = SCAR_FL_CUTWINDOW;
-                    rec.tlj = rec.trj = (uint16_t)cut;
-                    live = false;
-                }
-            }
-
-            // right junction (SlidingWindow.pyx:79-93): the smallest p in 10 .. len-26 whose window is a right
-            // window, i.e. lies at locus position cut <= t <= L-16 (window i = t-cut)
+            bool open = fast && p >= 16;
+            if (open) open = left_anchor<SMEM>(rc, ptab, LR, p, clj, tlj);
+            __syncwarp();
+            queue_push(open, (uint32_t)threadIdx.x | ((uint32_t)p << 8), &s_queue[round & 1][0], 1, &s_count[round % 3][0]);
             const int plast = len - 26;
             p = 10;
-            scanning = live && T.fast && plast >= 10;
-            while (__any_sync(0xFFFFFFFFu, scanning)) {
-                if (scanning) {
-                    const uint32_t t = locus_position<SMEM>(rc, ptab, mult, nb, p);
-                    if (t != 0xFFFFFFFFu && (int)t < cut) {
-                        const int need = cut - (int)t, limit = min(need, plast - p);
-                        const int k = match_right<SMEM>(rc, tw, p + 10, (int)t + 10, limit);
-                        if (k == limit) {
-                            if (limit == need) { crj = p + need; trj = cut; }
-                            scanning = false;
-                        } else p += k + 1;                         // windows p+1 .. p+k are left of the cut
-                    } else if (t != 0xFFFFFFFFu && (int)t <= L - 16) {
-                        crj = p; trj = (int)t; scanning = false;
-                    } else if (++p > plast) scanning = false;
-                }
-                __syncwarp();
-                if (scanning) {                                    // positions p .. p+NB-1 in one batch
-                    uint32_t wlo, whi, vlo, vhi, m[NB];
-                    rc.word16(p, wlo, vlo);
-                    rc.word16(p + 16, whi, vhi);
-                    probe_n<SMEM, NB>(ptab, wlo, whi, mult, nb, m);
-                    const uint32_t span = (uint32_t)(L - 16 - cut);   // right window iff (t - cut) <= span
-                    uint32_t hm = 0;
-#pragma unroll
-                    for (int o = 0; o < NB; ++o) hm |= ((m[o] - (uint32_t)cut) <= span) ? (1u << o) : 0u;
-                    if (hm) {
-                        const int top = plast - p;                 // >= 0
-                        hm &= runs_of_ten(vlo | (vhi << 16)) & (top >= NB - 1 ? NBMASK : ((2u << top) - 1u));
-                    }
-                    if (hm) {
-                        const int o = __ffs(hm) - 1;               // lowest position = first going up
-                        uint32_t t = 0;
-#pragma unroll
-                        for (int q = 0; q < NB; ++q) t = (q == o) ? m[q] : t;
-                        crj = p + o; trj = (int)t; scanning = false;
-                    }
-                    if (scanning) { p += NB; if (p > plast) scanning = false; }
-                }
-                __syncwarp();
-            }
+            open = fast && plast >= 10;
+            if (open) open = right_anchor<SMEM>(rc, ptab, LR, plast, p, crj, trj);
+            __syncwarp();
+            queue_push(open, (uint32_t)threadIdx.x | ((uint32_t)p << 8), &s_queue[round & 1][2 * K3_TILE - 1], -1,
+                       &s_count[round % 3][1]);
         }
-
+        bool cutwindow_done = false;          // the exhaustive path checks the cut window itself
         // ---- left junction (SlidingWindow.pyx:49-69): p = len-20 .. 16, descending
         if (live && !T.fast) {
             const TableRef<SMEM> ltab(blob, P.blob, T.left_off);
@@ -527,6 +575,7 @@ __global__ void __launch_bounds__(256, SCAR_K3_MIN_CTAS) scar_window_kernel(cons
                     }
                 }
             }
+            cutwindow_done = true;
         }
         __syncwarp();
 
@@ -560,6 +609,75 @@ __global__ void __launch_bounds__(256, SCAR_K3_MIN_CTAS) scar_window_kernel(cons
             }
         }
         __syncwarp();
+
+
+        s_left[threadIdx.x] = (uint32_t)clj | ((uint32_t)tlj << 16);
+        s_right[threadIdx.x] = (uint32_t)crj | ((uint32_t)trj << 16);
+        s_ctx[threadIdx.x] = (uint32_t)len | ((uint32_t)tid << 16);
+
+        // ---- phase 2: rounds over the open searches of the tile
+        for (;;) {
+            __syncthreads();
+            const uint32_t *q = s_queue[round & 1];
+            uint32_t *qn = s_queue[(round + 1) & 1];
+            const int nl = (int)s_count[round % 3][0], nr = (int)s_count[round % 3][1];
+            if (threadIdx.x == 0) { s_count[(round + 2) % 3][0] = 0; s_count[(round + 2) % 3][1] = 0; }
+            // (the next tile queues into the NEXT slot: a thread that leaves early must not be seen by one that
+            // has not read this round's counts yet)
+            if (nl + nr == 0) { ++round; break; }
+            const int nl32 = (nl + 31) & ~31;                 // warps are pure left or pure right
+            for (int v = threadIdx.x; v < nl32 + ((nr + 31) & ~31); v += K3_TILE) {
+                const bool is_left = v < nl32;
+                const int k = is_left ? v : v - nl32;
+                const bool have = k < (is_left ? nl : nr);
+                const uint32_t item = have ? q[is_left ? k : 2 * K3_TILE - 1 - k] : 0u;
+                const int rl = (int)(item & 0xFFu);
+                int p = (int)(item >> 8);
+                const uint32_t ctx = s_ctx[rl];
+                const int ilen = (int)(ctx & 0xFFFFu);
+                const ScarTargetMeta &IT = metas[ctx >> 16];
+                const TableRef<SMEM> ptab(blob, P.blob, IT.pos_off);
+                LocusRef LR; LR.mult = IT.pos_mult; LR.nbuckets = IT.pos_buckets; LR.cut = IT.cutsite; LR.L = IT.length;
+                LR.tw = reinterpret_cast<const uint32_t *>(blob + IT.tw_off);
+                ReadCursor rc; rc.col = P.cells + tile + rl; rc.S = S; rc.Wr = (ilen + 15) >> 4;
+                bool open = have;
+                if (is_left) {
+                    int a = 0, b = LR.cut;
+                    if (open) open = left_batch<SMEM>(rc, ptab, LR, p, a, b);
+                    __syncwarp();
+                    if (open) open = left_anchor<SMEM>(rc, ptab, LR, p, a, b);
+                    __syncwarp();
+                    if (have && !open && a) s_left[rl] = (uint32_t)a | ((uint32_t)b << 16);
+                    queue_push(open, (uint32_t)rl | ((uint32_t)p << 8), qn, 1, &s_count[(round + 1) % 3][0]);
+                } else {
+                    const int plast = ilen - 26;
+                    int a = 0, b = LR.cut;
+                    if (open) open = right_batch<SMEM>(rc, ptab, LR, plast, p, a, b);
+                    __syncwarp();
+                    if (open) open = right_anchor<SMEM>(rc, ptab, LR, plast, p, a, b);
+                    __syncwarp();
+                    if (have && !open && a) s_right[rl] = (uint32_t)a | ((uint32_t)b << 16);
+                    queue_push(open, (uint32_t)rl | ((uint32_t)p << 8), qn + 2 * K3_TILE - 1, -1, &s_count[(round + 1) % 3][1]);
+                }
+            }
+            ++round;
+        }
+
+        // ---- phase 3: one thread per read again
+        {
+            const uint32_t a = s_left[threadIdx.x], b = s_right[threadIdx.x];
+            clj = (int)(a & 0xFFFFu); tlj = (int)(a >> 16); crj = (int)(b & 0xFFFFu); trj = (int)(b >> 16);
+        }
+        if (live && !cutwindow_done && clj && T.cutwindow_key != 0xFFFFFFFFu) {   // SlidingWindow.pyx:56-60 (per-read drop-in only)
+            ReadCursor rc; rc.col = col; rc.S = S; rc.Wr = Wr;
+            uint32_t code, valid;
+            rc.word16(clj - 10, code, valid);
+            if ((code & SCAR_KEY_MASK) == T.cutwindow_key) {
+                rec.status = SCAR_ST_NO_CUT; rec.flags = SCAR_FL_CUTWINDOW;
+                rec.tlj = rec.trj = (uint16_t)cut;
+                live = false;
+            }
+        }
 
         if (live) {
             rec.clj = (uint16_t)clj; rec.crj = (uint16_t)crj; rec.tlj = (uint16_t)tlj; rec.trj = (uint16_t)trj;
