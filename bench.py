@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=50_000, help="reads of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true",
+                    help="tuning runs: skip the end-to-end arms (the line then carries e2e.value = null)")
     ap.add_argument("--seed", type=int, default=20260101)
     return ap.parse_args()
 
@@ -372,8 +374,8 @@ def main():
     raw_ms = r0.elapsed_time(r1) / raw_steps
 
     # end-to-end arm: host buffers -> records on the host, through the public API
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    e2e_steps = 0 if args.kernels_only else max(3, min(args.steps, 10))
+    for _ in range(0 if args.kernels_only else 2):
         eng.reset_async()
         eng.process_host(h_seq, h_f0, h_f1, first_index=first, out=rec_out)
         if dscar:
@@ -389,7 +391,7 @@ def main():
     e2e_s = time.perf_counter() - t0
     # the same from FASTQ TEXT (uncompressed, pinned): one H2D copy of the text, record indexing on the GPU
     fastq_e2e = None
-    if world == 1:
+    if world == 1 and not args.kernels_only:
         head = b"@SYN:1:FC:1:0:0:0 1:N:0:"
         rl = cfg.read_len
         rec_bytes = len(head) + 8 + 1 + 8 + 1 + rl + 3 + rl + 1
@@ -473,7 +475,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "scar_window_kernel (K3)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ, "secondary": secondary},
-            "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": h2d,
+            "e2e": {"value": world * n * e2e_steps / e2e_s if e2e_steps else None, "unit": "reads/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(n * 16), "steps": e2e_steps,
                     "path": "ScarEngine.process_host -> scar_process_host (pinned host buffers)"},
             "gpu_launches": int(launches),

@@ -13,5 +13,5 @@ for line in src:
     st = {k: round(v, 3) for k, v in d.get("stages_ms", {}).items()}
     raw = d.get("from_raw_bytes", {})
     print(label, "n_gpus", d.get("n_gpus"), "value %.4g" % d["value"], "ms/step %.3f" % d["ms_per_step"], st,
-          "frac %.3f" % d.get("roofline", {}).get("frac", 0), "e2e %.4g" % d["e2e"]["value"],
+          "frac %.3f" % d.get("roofline", {}).get("frac", 0), "e2e %.4g" % (d["e2e"]["value"] or 0),
           "raw %.4g (%.3f ms)" % (raw.get("value", 0), raw.get("ms_per_step", 0)), "launches", d.get("gpu_launches"))

@@ -87,80 +87,109 @@ __device__ __forceinline__ void pack_read(const K1Params &P, int64_t r, const ui
     P.lens[r] = (uint32_t)slen | ((uint32_t)n_count << 16);     // length and literal-'N' count for the filter
 }
 
+// smallest start / largest end address over the threads with `mine` (CTA-wide; contains two barriers)
+__device__ __forceinline__ void span_reduce(bool mine, const uint8_t *rp, int len, unsigned long long (*s_red)[8],
+                                            unsigned long long &lo, unsigned long long &hi)
+{
+    unsigned long long a = mine ? (unsigned long long)(uintptr_t)rp : ~0ull;
+    unsigned long long b = mine ? (unsigned long long)(uintptr_t)rp + (unsigned long long)len : 0ull;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const unsigned long long a2 = __shfl_xor_sync(0xFFFFFFFFu, a, d), b2 = __shfl_xor_sync(0xFFFFFFFFu, b, d);
+        a = a2 < a ? a2 : a; b = b2 > b ? b2 : b;
+    }
+    __syncthreads();                                  // s_red may still be read from the previous use
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = a; s_red[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    lo = s_red[0][0]; hi = s_red[1][0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { lo = s_red[0][i] < lo ? s_red[0][i] : lo; hi = s_red[1][i] > hi ? s_red[1][i] : hi; }
+}
+
 __global__ void __launch_bounds__(256, 4) scar_pack_kernel(const K1Params P)
 {
     // A CTA owns tiles of 256 consecutive reads.  The raw bytes of a tile are one contiguous span of the
     // input (CSR / fixed stride; also FASTQ views in file order): ONE TMA bulk copy brings the span into
     // shared memory (coalesced, no register traffic), then each thread packs its read out of shared
-    // memory with word loads.  A span that does not fit (very long reads, scattered views) is read
-    // straight from global memory instead.  The stores of one cell index j are coalesced either way.
+    // memory with word loads.  A span larger than the buffer (FASTQ text: the reads are a third of the
+    // bytes) is taken in 2, 4 or 8 passes over 128, 64 or 32 reads; what still does not fit (very long
+    // reads, scattered views) is read straight from global memory.  The stores of one cell index j are
+    // coalesced either way.
     extern __shared__ __align__(128) unsigned char tile_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(tile_raw);
     unsigned char *tile = tile_raw + 16;
-    __shared__ unsigned long long s_lo, s_hi;
     __shared__ unsigned long long s_red[2][8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     uint32_t parity = 0;
-    const bool views = P.seq.offsets && P.seq.lengths;
     const bool rc = P.platform == SCAR_PLATFORM_RAMSDEN;
+    const bool views = P.seq.offsets && P.seq.lengths;
     const int64_t tiles = (P.n_reads + blockDim.x - 1) / blockDim.x;
     for (int64_t tile_no = blockIdx.x; tile_no < tiles; tile_no += gridDim.x) {
-        const int64_t r0 = tile_no * blockDim.x;
-        const int64_t r = r0 + threadIdx.x;
+        const int64_t r = tile_no * blockDim.x + threadIdx.x;
         const bool active = r < P.n_reads;
         const uint8_t *rp = P.seq.bytes; int len = 0;
         if (active) get_item(P.seq, r, rp, len);
-        // span of the tile: [lo, hi) as addresses
-        if (views) {                                  // arbitrary order: min start / max end over the tile
-            unsigned long long a = active ? (unsigned long long)(uintptr_t)rp : ~0ull;
-            unsigned long long b = active ? (unsigned long long)(uintptr_t)rp + (unsigned long long)len : 0ull;
-#pragma unroll
-            for (int d = 16; d; d >>= 1) {
-                const unsigned long long a2 = __shfl_xor_sync(0xFFFFFFFFu, a, d), b2 = __shfl_xor_sync(0xFFFFFFFFu, b, d);
-                a = a2 < a ? a2 : a; b = b2 > b ? b2 : b;
-            }
-            if (lane == 0) { s_red[0][warp] = a; s_red[1][warp] = b; }
-            __syncthreads();
+        // span of reads [a, b] of the batch: monotonic layouts (CSR, fixed stride) need only the two end items
+        // (thread 0 looks them up); views may be in any order and take a CTA-wide min / max
+        const int64_t r0 = tile_no * blockDim.x;
+        auto span_of = [&](int64_t a, int64_t b, bool mine, unsigned long long &lo, unsigned long long &hi) {
+            if (views) { span_reduce(mine, rp, len, s_red, lo, hi); return; }
             if (threadIdx.x == 0) {
-                for (int i = 1; i < 8; ++i) { a = s_red[0][i] < a ? s_red[0][i] : a; b = s_red[1][i] > b ? s_red[1][i] : b; }
-                s_lo = a; s_hi = b;
+                if (b >= P.n_reads) b = P.n_reads - 1;
+                unsigned long long x = ~0ull, y = 0ull;
+                if (a <= b) {
+                    const uint8_t *q0, *q1; int l0, l1;
+                    get_item(P.seq, a, q0, l0);
+                    get_item(P.seq, b, q1, l1);
+                    x = (unsigned long long)(uintptr_t)q0; y = (unsigned long long)(uintptr_t)q1 + (unsigned long long)l1;
+                }
+                s_red[0][0] = x; s_red[1][0] = y;
             }
-        } else if (threadIdx.x == 0) {                // monotonic layouts: first read's start, last read's end
-            const int64_t rl = (r0 + blockDim.x <= P.n_reads ? r0 + blockDim.x : P.n_reads) - 1;
-            const uint8_t *q; int ql;
-            get_item(P.seq, rl, q, ql);
-            s_lo = (unsigned long long)(uintptr_t)rp; s_hi = (unsigned long long)(uintptr_t)q + (unsigned long long)ql;
+            __syncthreads();                          // (the barrier that ends a pass protects the reuse)
+            lo = s_red[0][0]; hi = s_red[1][0];
+        };
+        unsigned long long lo, hi;
+        span_of(r0, r0 + blockDim.x - 1, active, lo, hi);
+        // passes: 1 when the whole tile fits, else the power of two that brings the average pass under the budget
+        int passes = 1;
+        {
+            const unsigned long long whole = hi > lo ? hi - (lo & ~15ull) + 15ull : 0ull;
+            while (passes < 8 && whole > (unsigned long long)passes * (PACK_TILE_BYTES - 64)) passes *= 2;
         }
-        __syncthreads();
-        const unsigned long long lo16 = s_lo & ~15ull;
-        const unsigned long long span = s_hi > lo16 ? ((s_hi - lo16 + 15ull) & ~15ull) : 0ull;
-        const bool staged = span != 0ull && span <= (unsigned long long)PACK_TILE_BYTES;
-        if (staged) {
-            if (threadIdx.x == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
-                             "r"((uint32_t)span) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_addr(tile)), "l"(lo16), "r"((uint32_t)span), "r"(smem_addr(bar)) : "memory");
+        const int sub_shift = 8 - (31 - __clz(passes)), sub = 1 << sub_shift;      // blockDim.x = 256
+        for (int ps = 0; ps < passes; ++ps) {
+            if (passes > 1) __syncthreads();          // everyone has read the previous span
+            const bool mine = active && ((int)threadIdx.x >> sub_shift) == ps;
+            if (passes > 1) span_of(r0 + (int64_t)ps * sub, r0 + (int64_t)(ps + 1) * sub - 1, mine, lo, hi);
+            const unsigned long long lo16 = lo & ~15ull;
+            const unsigned long long span = hi > lo16 ? ((hi - lo16 + 15ull) & ~15ull) : 0ull;
+            const bool staged = span != 0ull && span <= (unsigned long long)PACK_TILE_BYTES;
+            if (staged) {
+                if (threadIdx.x == 0) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                                 "r"((uint32_t)span) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_addr(tile)), "l"(lo16), "r"((uint32_t)span), "r"(smem_addr(bar)) : "memory");
+                }
+                uint32_t done = 0;
+                while (!done) {
+                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                                 "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+                }
+                parity ^= 1u;
             }
-            uint32_t done = 0;
-            while (!done) {
-                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-                             "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+            if (mine) {
+                const uintptr_t a4 = (uintptr_t)rp & ~(uintptr_t)3;
+                const int mis = (int)((uintptr_t)rp & 3);
+                if (staged) pack_read<true>(P, r, nullptr, smem_addr(tile) + (uint32_t)(a4 - lo16), mis, len, rc);
+                else pack_read<false>(P, r, reinterpret_cast<const uint32_t *>(a4), 0u, mis, len, rc);
             }
-            parity ^= 1u;
+            __syncthreads();                          // the tile buffer is reused by the next pass / tile
         }
-        if (active) {
-            const uintptr_t a4 = (uintptr_t)rp & ~(uintptr_t)3;
-            const int mis = (int)((uintptr_t)rp & 3);
-            if (staged) pack_read<true>(P, r, nullptr, smem_addr(tile) + (uint32_t)(a4 - lo16), mis, len, rc);
-            else pack_read<false>(P, r, reinterpret_cast<const uint32_t *>(a4), 0u, mis, len, rc);
-        }
-        __syncthreads();                              // the tile buffer and s_lo / s_hi are reused
     }
 }
 

@@ -24,7 +24,7 @@
 #define SCAR_ANCHOR_BATCH 14
 #endif
 #ifndef SCAR_K3_MIN_CTAS
-#define SCAR_K3_MIN_CTAS 4
+#define SCAR_K3_MIN_CTAS 5
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
