@@ -6,6 +6,7 @@
 
 #include "../../include/scar_b200.h"
 #include "scar_demux_core.h"
+#include "scar_swar.h"
 
 #define SCAR_KMER 10                 // hard-coded window (INDEL_Processing.py:67,76; SlidingWindow.pyx:49-50)
 #define SCAR_KEY_MASK 0xFFFFFu       // 10 bases x 2 bits
@@ -78,37 +79,6 @@ struct __align__(16) ScarTableSlot {    // 32 bytes, zero-initialised
     uint32_t sample;
 };
 
-#ifdef __CUDACC__
-// ---- SWAR byte classification shared by K1 (pack) and K2 (demux fast path) --------------------------
-__device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
-{
-    // 0x80 in every byte of x that is zero (exact, no borrow propagation)
-    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
-}
-
-// canonical-letter difference of four bytes: byte k of the result is 0 iff byte k of w is A, C, G or T.
-// The code (w>>1)&3 names the only letter the byte could be; 'A'|(w&6) is that letter for A, C, G and
-// 'E' for code 2, which +15 turns into 'T'.
-__device__ __forceinline__ uint32_t acgt_diff4(uint32_t w)
-{
-    const uint32_t t = ((w >> 2) & ~(w >> 1)) & 0x01010101u;            // 1 where the code is 2
-    const uint32_t canon = (0x41414141u | (w & 0x06060606u)) + t * 15u;
-    return w ^ canon;
-}
-
-// 0x80 flags of four bytes -> 4-bit mask (one multiply: the four partial products land on distinct bits)
-__device__ __forceinline__ uint32_t flags_to_nibble(uint32_t v) { return (v * 0x00204081u) >> 28; }
-
-// four bytes -> 8-bit codes (A=0 C=1 T=2 G=3, one multiply gathers them), 4-bit ACGT mask
-__device__ __forceinline__ void classify4(uint32_t w, uint32_t &code8, uint32_t &valid4)
-{
-    code8 = (((w >> 1) & 0x03030303u) * 0x01041040u) >> 24;
-    const uint32_t x = acgt_diff4(w);
-    valid4 = x ? flags_to_nibble(zero_bytes(x)) : 0xFu;
-}
-
-
-#endif
 
 // ---- kernel parameter blocks and launchers ---------------------------------------------------------
 struct K1Params {

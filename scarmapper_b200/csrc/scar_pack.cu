@@ -60,7 +60,7 @@ __device__ __forceinline__ void pack_read(const K1Params &P, int64_t r, const ui
         uint32_t p[4], x[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            p[i] = ((v[i] >> 1) & 0x03030303u) * 0x01041040u;
+            p[i] = codes_to_top_byte(v[i]);
             x[i] = acgt_diff4(v[i]);
         }
         uint32_t code = __byte_perm(__byte_perm(p[0], p[1], 0x0073), __byte_perm(p[2], p[3], 0x0073), 0x5410);

@@ -152,7 +152,10 @@ __device__ __forceinline__ void k4_flush(const K4Params &P, unsigned int *s_hist
     }
 }
 
-__global__ void __launch_bounds__(256) scar_aggregate_kernel(const K4Params P)
+#ifndef SCAR_K4_CTAS
+#define SCAR_K4_CTAS 6
+#endif
+__global__ void __launch_bounds__(256, SCAR_K4_CTAS) scar_aggregate_kernel(const K4Params P)
 {
     extern __shared__ __align__(8) unsigned int s_hist[];
     const int pb = P.phase_joint;                       // 0: separate marginals
@@ -433,7 +436,7 @@ cudaError_t scar_launch_aggregate(K4Params P, int sm_count, cudaStream_t stream,
     cudaError_t e = cudaFuncSetAttribute(scar_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
     if (e != cudaSuccess) return e;
     int64_t blocks = (P.n_reads + threads - 1) / threads;
-    const int64_t cap = (int64_t)sm_count * 6;
+    const int64_t cap = (int64_t)sm_count * SCAR_K4_CTAS;
     if (blocks > cap) blocks = cap;
     scar_aggregate_kernel<<<(unsigned)blocks, threads, smem, stream>>>(P);
     if (launches) ++*launches;
