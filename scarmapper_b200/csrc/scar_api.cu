@@ -934,9 +934,9 @@ extern "C" int scar_process_fastq_host(scar_ctx *c, const uint8_t *text, int64_t
     CU(cudaMemsetAsync(c->d_text + n_bytes, 0, 64, s));
     const int64_t n_tiles = (n_bytes + 4095) / 4096;
     if ((rc = ensure(&c->d_tile_counts, &c->tile_counts_cap, (size_t)n_tiles))) return rc;
-    if ((rc = ensure(&c->d_tile_offsets, &c->tile_offsets_cap, (size_t)n_tiles))) return rc;
+    if ((rc = ensure(&c->d_tile_offsets, &c->tile_offsets_cap, (size_t)scar_fastq_offsets_elems(n_bytes)))) return rc;
     CU(scar_fastq_index_launch(c->d_text, n_bytes, c->d_tile_counts, c->d_tile_offsets, c->d_export_n, s));
-    c->launches += 2;
+    c->launches += 3;
     unsigned long long n_nl = 0;
     CU(cudaMemcpyAsync(&n_nl, c->d_export_n, sizeof(n_nl), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));

@@ -4,7 +4,7 @@
 // (reference Valkyries/FASTQ_Tools.py:623-653) + the header split of index_matching
 // (scarmapper/INDEL_Processing.py:1155-1156) — but over a text buffer resident in device memory:
 //   pass 1  count '\n' per 4 KB tile (16-byte vector loads, popcount of the byte-equality mask)
-//   pass 2  exclusive scan of the tile counts (one CTA)
+//   pass 2  exclusive scan of the tile counts (two levels: 1024 tiles per CTA, then one CTA over the CTA sums)
 //   pass 3  every tile writes the positions of its newlines at its scanned offset
 //   pass 4  one thread per record: lines 4r .. 4r+3 -> (offset, length) views of the sequence and of
 //           name.split(":")[-1].split("+")[0..1]; whitespace stripped as str.strip() does; a
@@ -53,47 +53,69 @@ __global__ void __launch_bounds__(256) fq_count_kernel(const uint8_t *text, int6
     }
 }
 
-// exclusive scan of tile_counts into tile_offsets (int64), total in *total; one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) fq_scan_kernel(const uint32_t *tile_counts, int64_t n_tiles, int64_t *tile_offsets,
-                                                      unsigned long long *total)
+// Two-level exclusive scan of the tile counts.  Level 1: every CTA scans 1024 tile counts (local prefix into
+// tile_offsets, the CTA's sum into block_sums).  Level 2: ONE CTA scans the block sums in place (a 3.5 GB
+// text has 845 K tiles = 826 block sums) and writes the grand total.  A tile's offset is then
+// block_sums[tile / 1024] + tile_offsets[tile].
+#define FQ_SCAN_BLOCK 1024
+
+__device__ __forceinline__ unsigned long long cta_exclusive_scan(unsigned long long v, unsigned long long *s_warp,
+                                                                 unsigned long long &cta_total)
 {
-    __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n_tiles; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const unsigned long long v = i < n_tiles ? tile_counts[i] : 0ull;
-        unsigned long long x = v;
+    unsigned long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = s_warp[lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-            if (lane >= d) x += y;
+            const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+            if (lane >= d) w += y;
         }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = s_warp[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, w, d);
-                if (lane >= d) w += y;
-            }
-            s_warp[lane] = w;                         // inclusive over warps
-        }
-        __syncthreads();
-        const unsigned long long before = s_carry + (warp ? s_warp[warp - 1] : 0ull) + (x - v);
-        if (i < n_tiles) tile_offsets[i] = (int64_t)before;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry += s_warp[31];
-        __syncthreads();
+        s_warp[lane] = w;                             // inclusive over warps
     }
-    if (threadIdx.x == 0) *total = s_carry;
+    __syncthreads();
+    cta_total = s_warp[31];
+    const unsigned long long before = (warp ? s_warp[warp - 1] : 0ull) + (x - v);
+    __syncthreads();                                  // s_warp is reused by the caller's next round
+    return before;
+}
+
+__global__ void __launch_bounds__(FQ_SCAN_BLOCK) fq_scan1_kernel(const uint32_t *tile_counts, int64_t n_tiles,
+                                                                 int64_t *tile_offsets, unsigned long long *block_sums)
+{
+    __shared__ unsigned long long s_warp[32];
+    const int64_t i = (int64_t)blockIdx.x * FQ_SCAN_BLOCK + threadIdx.x;
+    unsigned long long total;
+    const unsigned long long before = cta_exclusive_scan(i < n_tiles ? tile_counts[i] : 0ull, s_warp, total);
+    if (i < n_tiles) tile_offsets[i] = (int64_t)before;
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(FQ_SCAN_BLOCK) fq_scan2_kernel(unsigned long long *block_sums, int64_t n_blocks,
+                                                                 unsigned long long *total)
+{
+    __shared__ unsigned long long s_warp[32];
+    unsigned long long carry = 0;
+    for (int64_t base = 0; base < n_blocks; base += FQ_SCAN_BLOCK) {
+        const int64_t i = base + threadIdx.x;
+        unsigned long long round_total;
+        const unsigned long long before = cta_exclusive_scan(i < n_blocks ? block_sums[i] : 0ull, s_warp, round_total);
+        if (i < n_blocks) block_sums[i] = carry + before;
+        carry += round_total;
+    }
+    if (threadIdx.x == 0) *total = carry;
 }
 
 __global__ void __launch_bounds__(256) fq_positions_kernel(const uint8_t *text, int64_t n_bytes, const int64_t *tile_offsets,
-                                                           int64_t *nl_pos, int64_t nl_capacity)
+                                                           const unsigned long long *block_sums, int64_t *nl_pos,
+                                                           int64_t nl_capacity)
 {
     const int64_t off = (int64_t)blockIdx.x * FQ_TILE + threadIdx.x * 16;
     const uint32_t m = off < n_bytes ? newline_mask16(load16(text, off, n_bytes)) : 0u;
@@ -111,7 +133,7 @@ __global__ void __launch_bounds__(256) fq_positions_kernel(const uint8_t *text, 
     __syncthreads();
     int before = x - c;
     for (int w = 0; w < warp; ++w) before += s[w];
-    int64_t dst = tile_offsets[blockIdx.x] + before;
+    int64_t dst = (int64_t)block_sums[blockIdx.x / FQ_SCAN_BLOCK] + tile_offsets[blockIdx.x] + before;
     for (uint32_t mm = m; mm; mm &= mm - 1) {
         if (dst < nl_capacity) nl_pos[dst] = off + (__ffs(mm) - 1);
         ++dst;
@@ -170,13 +192,23 @@ __global__ void __launch_bounds__(256) fq_records_kernel(const uint8_t *text, in
 // host orchestration -----------------------------------------------------------------------------------
 int scar_fail(int code, const char *fmt, ...);
 
+// elements (int64) the tile_offsets buffer needs: one per tile + one per 1024 tiles (block sums)
+int64_t scar_fastq_offsets_elems(int64_t n_bytes)
+{
+    const int64_t n_tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
+    return n_tiles + (n_tiles + FQ_SCAN_BLOCK - 1) / FQ_SCAN_BLOCK + 1;
+}
+
 cudaError_t scar_fastq_index_launch(const uint8_t *text, int64_t n_bytes, uint32_t *tile_counts, int64_t *tile_offsets,
                                     unsigned long long *total, cudaStream_t s)
 {
     const int64_t n_tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
     if (n_tiles == 0) return cudaMemsetAsync(total, 0, sizeof(unsigned long long), s);
+    const int64_t n_blocks = (n_tiles + FQ_SCAN_BLOCK - 1) / FQ_SCAN_BLOCK;
+    unsigned long long *block_sums = reinterpret_cast<unsigned long long *>(tile_offsets + n_tiles);   // see scar_fastq_offsets_elems
     fq_count_kernel<<<(unsigned)n_tiles, 256, 0, s>>>(text, n_bytes, tile_counts);
-    fq_scan_kernel<<<1, 1024, 0, s>>>(tile_counts, n_tiles, tile_offsets, total);
+    fq_scan1_kernel<<<(unsigned)n_blocks, FQ_SCAN_BLOCK, 0, s>>>(tile_counts, n_tiles, tile_offsets, block_sums);
+    fq_scan2_kernel<<<1, FQ_SCAN_BLOCK, 0, s>>>(block_sums, n_blocks, total);
     return cudaGetLastError();
 }
 
@@ -185,7 +217,8 @@ cudaError_t scar_fastq_positions_launch(const uint8_t *text, int64_t n_bytes, co
 {
     const int64_t n_tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
     if (n_tiles == 0) return cudaSuccess;
-    fq_positions_kernel<<<(unsigned)n_tiles, 256, 0, s>>>(text, n_bytes, tile_offsets, nl_pos, nl_capacity);
+    const unsigned long long *block_sums = reinterpret_cast<const unsigned long long *>(tile_offsets + n_tiles);
+    fq_positions_kernel<<<(unsigned)n_tiles, 256, 0, s>>>(text, n_bytes, tile_offsets, block_sums, nl_pos, nl_capacity);
     return cudaGetLastError();
 }
 

@@ -175,6 +175,7 @@ cudaError_t scar_launch_merge_parts(const K4Params &P, const scar_entry *in, uin
                                     int sm_count, cudaStream_t stream);
 
 // GPU FASTQ indexer (scar_fastq_dev.cu); tiles are 4096 bytes
+int64_t scar_fastq_offsets_elems(int64_t n_bytes);
 cudaError_t scar_fastq_index_launch(const uint8_t *text, int64_t n_bytes, uint32_t *tile_counts, int64_t *tile_offsets,
                                     unsigned long long *total, cudaStream_t s);
 cudaError_t scar_fastq_positions_launch(const uint8_t *text, int64_t n_bytes, const int64_t *tile_offsets, int64_t *nl_pos,
