@@ -255,8 +255,18 @@ def main():
         engines.append(eng_b)
         dscars.append(DistributedScar(eng_b, entry_capacity=1 << 21))
     side = torch.cuda.Stream() if world > 1 else None
-    # owner-partitioned merge: a rank sends each peer the entries that peer owns (~1.1 M / world per region)
-    region_capacity = 1 << max(10, int(np.ceil(np.log2(2.2 * 1.1e6 * (n / 1e7) / world + 16))))
+    # owner-partitioned merge: a rank sends each peer the entries that peer owns.  The exchange moves whole
+    # regions, so they are sized from the table this batch actually produces (one untimed pass): the largest
+    # per-rank entry count / world (owners are hash-uniform) + 25 % + 4096, in multiples of 4096 entries.
+    region_capacity = 4096
+    if world > 1:
+        eng.reset_async()
+        eng.run_resident(res, first_index=first)
+        torch.cuda.synchronize()
+        t = torch.tensor([eng.table_size()], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        region_capacity = int(-(-(int(t.item()) * 1.25 / world + 4096) // 4096) * 4096)
+        eng.reset()
     merge_done = [None, None]
     step_no = [0]
 
