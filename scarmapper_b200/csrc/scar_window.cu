@@ -134,15 +134,22 @@ __device__ __forceinline__ uint32_t runs_of_ten(uint32_t vwin)
 // decided by that position alone — so the scan jumps over the stretch instead of probing each window.
 // Positions around a mismatch or the junction are still probed one by one: results are identical to
 // the exhaustive scan.
-struct ReadCursor {
-    const uint64_t *col; int64_t S; int Wr;
-    // 16 bases starting at base b >= 0: 2-bit codes and ACGT mask (two L1-resident cell loads)
+#define K3_TILE 256
+#ifndef K3_STAGE_MAX_CELLS
+#define K3_STAGE_MAX_CELLS 12          // reads up to 192 nt: 24 KB of cells per tile
+#endif
+
+// The cells of one read.  ST: the tile's cells were copied to shared memory (cell j of local read rl at
+// sc[j * K3_TILE]); otherwise they are read through the read-only global path (cell-major, stride S).
+template <bool ST> struct ReadCursorT {
+    const uint64_t *col; int64_t S; const uint64_t *sc; int Wr;
+    __device__ __forceinline__ uint64_t cell(int j) const { return ST ? sc[j * K3_TILE] : __ldg(col + (int64_t)j * S); }
+    __device__ __forceinline__ uint64_t cell_or_zero(int j) const { return j < Wr ? cell(j) : 0ull; }
+    // 16 bases starting at base b >= 0: 2-bit codes and ACGT mask
     __device__ __forceinline__ void word16(int b, uint32_t &code, uint32_t &valid) const
     {
         const int j = b >> 4, o = b & 15;
-        const uint64_t *pc = col + (int64_t)j * S;
-        const uint64_t c0 = j < Wr ? __ldg(pc) : 0ull;
-        const uint64_t c1 = j + 1 < Wr ? __ldg(pc + S) : 0ull;
+        const uint64_t c0 = cell_or_zero(j), c1 = cell_or_zero(j + 1);
         code = __funnelshift_r((uint32_t)c0, (uint32_t)c1, 2 * o);
         valid = __funnelshift_r((uint32_t)(c0 >> 32) << 16, (uint32_t)(c1 >> 32), 16 + o) & 0xFFFFu;
     }
@@ -178,13 +185,11 @@ __device__ __forceinline__ uint32_t mismatch16(uint32_t rcode, uint32_t rvalid, 
 
 // 32 bases starting at base b >= 0 of the read (2-bit codes, ACGT mask) and of the locus
 struct Word32 { uint64_t code; uint32_t valid; };
-__device__ __forceinline__ Word32 read32(const ReadCursor &rc, int b)
+template <class RC>
+__device__ __forceinline__ Word32 read32(const RC &rc, int b)
 {
     const int j = b >> 4, o = b & 15;
-    const uint64_t *pc = rc.col + (int64_t)j * rc.S;
-    const uint64_t c0 = j < rc.Wr ? __ldg(pc) : 0ull;
-    const uint64_t c1 = j + 1 < rc.Wr ? __ldg(pc + rc.S) : 0ull;
-    const uint64_t c2 = j + 2 < rc.Wr ? __ldg(pc + 2 * rc.S) : 0ull;
+    const uint64_t c0 = rc.cell_or_zero(j), c1 = rc.cell_or_zero(j + 1), c2 = rc.cell_or_zero(j + 2);
     Word32 w;
     const uint32_t lo = __funnelshift_r((uint32_t)c0, (uint32_t)c1, 2 * o);
     const uint32_t hi = __funnelshift_r((uint32_t)c1, (uint32_t)c2, 2 * o);
@@ -226,8 +231,8 @@ __device__ __forceinline__ uint64_t mismatch32(const Word32 &r, uint64_t tcode)
 // number of bases, going LEFT from read base q-1 / locus base tq-1, that match; at most n.
 // 32 bases per step; the window may start before base 0 of the read on the last step (q-k >= 16 only
 // guarantees 16 bases), so the step is clamped to what exists.
-template <bool SMEM>
-__device__ __forceinline__ int match_left(ReadCursor &rc, const uint32_t *tw, int q, int tq, int n)
+template <bool SMEM, class RC>
+__device__ __forceinline__ int match_left(const RC &rc, const uint32_t *tw, int q, int tq, int n)
 {
     int k = 0;
     while (k < n) {
@@ -245,8 +250,8 @@ __device__ __forceinline__ int match_left(ReadCursor &rc, const uint32_t *tw, in
 }
 
 // number of bases, going RIGHT from read base q / locus base tq, that match; at most n
-template <bool SMEM>
-__device__ __forceinline__ int match_right(ReadCursor &rc, const uint32_t *tw, int q, int tq, int n)
+template <bool SMEM, class RC>
+__device__ __forceinline__ int match_right(const RC &rc, const uint32_t *tw, int q, int tq, int n)
 {
     int k = 0;
     while (k < n) {
@@ -261,8 +266,8 @@ __device__ __forceinline__ int match_right(ReadCursor &rc, const uint32_t *tw, i
 }
 
 // position in the locus of the read window at p, or 0xFFFFFFFF (not a locus 10-mer / not all ACGT)
-template <bool SMEM>
-__device__ __forceinline__ uint32_t locus_position(ReadCursor &rc, const TableRef<SMEM> &ptab, uint32_t mult,
+template <bool SMEM, class RC>
+__device__ __forceinline__ uint32_t locus_position(const RC &rc, const TableRef<SMEM> &ptab, uint32_t mult,
                                                    uint32_t nbuckets, int p)
 {
     uint32_t code, valid;
@@ -291,8 +296,8 @@ struct LocusRef {                  // what a step needs to know about the read's
     int cut, L;
 };
 
-template <bool SMEM>
-__device__ __forceinline__ bool left_anchor(ReadCursor &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int &p,
+template <bool SMEM, class RC>
+__device__ __forceinline__ bool left_anchor(const RC &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int &p,
                                             int &clj, int &tlj)
 {
     // left junction (SlidingWindow.pyx:49-69): the largest p in 16 .. len-20 whose window is a left window,
@@ -312,8 +317,8 @@ __device__ __forceinline__ bool left_anchor(ReadCursor &rc, const TableRef<SMEM>
     return --p >= 16;
 }
 
-template <bool SMEM>
-__device__ __forceinline__ bool left_batch(ReadCursor &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int &p,
+template <bool SMEM, class RC>
+__device__ __forceinline__ bool left_batch(const RC &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int &p,
                                            int &clj, int &tlj)
 {
     // batch width: a clean deletion's junction window is the 10th position past the break, 1-3 nt
@@ -342,8 +347,8 @@ __device__ __forceinline__ bool left_batch(ReadCursor &rc, const TableRef<SMEM> 
     return p >= 16;
 }
 
-template <bool SMEM>
-__device__ __forceinline__ bool right_anchor(ReadCursor &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int plast,
+template <bool SMEM, class RC>
+__device__ __forceinline__ bool right_anchor(const RC &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int plast,
                                              int &p, int &crj, int &trj)
 {
     // right junction (SlidingWindow.pyx:79-93): the smallest p in 10 .. len-26 whose window is a right window,
@@ -363,8 +368,8 @@ __device__ __forceinline__ bool right_anchor(ReadCursor &rc, const TableRef<SMEM
     return ++p <= plast;
 }
 
-template <bool SMEM>
-__device__ __forceinline__ bool right_batch(ReadCursor &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int plast,
+template <bool SMEM, class RC>
+__device__ __forceinline__ bool right_batch(const RC &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int plast,
                                             int &p, int &crj, int &trj)
 {
     constexpr int NB = SCAR_ANCHOR_BATCH;
@@ -405,9 +410,7 @@ __device__ __forceinline__ void queue_push(bool pending, uint32_t item, uint32_t
     if (pending) queue[dir * (int)(base + __popc(mask & ((1u << lane) - 1u)))] = item;
 }
 
-#define K3_TILE 256
-
-template <bool SMEM, bool HR>
+template <bool SMEM, bool HR, bool ST>
 __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(const K3Params P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -422,6 +425,10 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
     const ScarPhase *phases = reinterpret_cast<const ScarPhase *>(blob + P.phase_off);
     const uint16_t *nmax = reinterpret_cast<const uint16_t *>(blob + P.nmax_off);
     const int64_t S = P.stride;      // reads per cell row
+    using RC = ReadCursorT<ST>;
+    // ST: the tile's cells (W rows of 256 x 8 bytes) live in shared memory behind the blob; every thread copies
+    // its own read's cells there with asynchronous 8-byte copies (no registers, all W in flight at once)
+    uint64_t *s_cells = reinterpret_cast<uint64_t *>(smem_raw + 16 + (SMEM ? P.blob_bytes : 0u));
 
     // A CTA takes tiles of 256 reads.  Phase 1 is one thread per read: phasing, filters, and the FIRST anchor
     // step of both junction searches (a wild-type read is finished there).  Searches that are still open
@@ -440,6 +447,13 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
     for (int64_t tile = (int64_t)blockIdx.x * K3_TILE; tile < P.n_reads; tile += (int64_t)gridDim.x * K3_TILE) {
         const int64_t r = tile + threadIdx.x;
         bool live = r < P.n_reads;
+        if (ST && live) {
+            const uint64_t *src = P.cells + r;
+            uint32_t dst = smem_u32(s_cells + threadIdx.x);
+            for (int j = 0; j < P.W; ++j, src += S, dst += K3_TILE * 8)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         __align__(16) scar_record rec;
         rec.status = SCAR_ST_UNASSIGNED; rec.flags = 0; rec.sample = SCAR_SAMPLE_NONE;
         rec.clj = rec.crj = rec.tlj = rec.trj = 0; rec.hr_n = 0;
@@ -456,13 +470,15 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
         const int Wr = (len + 15) >> 4;                          // cells that hold bases
         const int cut = T.cutsite;
         int clj = 0, crj = 0, tlj = cut, trj = cut;
+        RC rc0; rc0.col = col; rc0.S = S; rc0.sc = s_cells + threadIdx.x; rc0.Wr = Wr;
+        if (ST) asm volatile("cp.async.wait_all;" ::: "memory");
 
         if (live) {
             const int n_count = (int)(info >> 16);
             // ---- phasing (INDEL_Processing.py:948-975): first k matching the prefix / the suffix.
             // The first 16 bases and the last 16 bases are extracted once; a phase is a shift + compare.
             if (P.do_phasing && T.n_phase > 0) {
-                ReadCursor pc; pc.col = col; pc.S = S; pc.Wr = Wr;
+                const RC &pc = rc0;
                 uint32_t hcode, hvalid, scode, svalid;
                 pc.word16(0, hcode, hvalid);
                 const int sb = len > 16 ? len - 16 : 0;          // suffix window = bases sb .. sb+15
@@ -516,7 +532,7 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
             const TableRef<SMEM> ptab(blob, P.blob, T.pos_off);
             LocusRef LR; LR.mult = T.pos_mult; LR.nbuckets = T.pos_buckets; LR.cut = cut; LR.L = T.length;
             LR.tw = reinterpret_cast<const uint32_t *>(blob + T.tw_off);
-            ReadCursor rc; rc.col = col; rc.S = S; rc.Wr = Wr;
+            const RC &rc = rc0;
             int p = len - 20;
             bool open = fast && p >= 16;
             if (open) open = left_anchor<SMEM>(rc, ptab, LR, p, clj, tlj);
@@ -538,10 +554,10 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
             const int p0 = len - 20;
             if (p0 >= 16) {
                 int j = p0 >> 4;
-                uint64_t hi = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
+                uint64_t hi = rc0.cell_or_zero(j + 1);
                 uint32_t best = 0;
                 for (; j >= 1; --j) {
-                    const uint64_t lo = __ldg(col + j * S);
+                    const uint64_t lo = rc0.cell(j);
                     const uint32_t wlo = (uint32_t)lo, whi = (uint32_t)hi;
                     uint32_t m[16];
                     if (probe16<SMEM>(ltab, wlo, whi, mult, nb, m) < 4095u) {
@@ -565,8 +581,8 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
                     // SlidingWindow.pyx:56-60 (reachable only through the per-read drop-in)
                     if (T.cutwindow_key != 0xFFFFFFFFu) {
                         const int jj = p >> 4, o = p & 15;
-                        const uint64_t a = __ldg(col + jj * S);
-                        const uint64_t b = jj + 1 < Wr ? __ldg(col + (jj + 1) * S) : 0ull;
+                        const uint64_t a = rc0.cell(jj);
+                        const uint64_t b = rc0.cell_or_zero(jj + 1);
                         if ((__funnelshift_r((uint32_t)a, (uint32_t)b, 2 * o) & SCAR_KEY_MASK) == T.cutwindow_key) {
                             rec.status = SCAR_ST_NO_CUT; rec.flags = SCAR_FL_CUTWINDOW;
                             rec.tlj = rec.trj = (uint16_t)cut;
@@ -585,10 +601,10 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
             const uint32_t mult = T.right_mult, nb = T.right_buckets;
             const int plast = len - 26;
             if (plast >= 10) {
-                uint64_t lo = __ldg(col);
+                uint64_t lo = rc0.cell(0);
                 uint32_t best = 0xFFFFFFFFu;
                 for (int j = 0; 16 * j <= plast; ++j) {
-                    const uint64_t hi = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
+                    const uint64_t hi = rc0.cell_or_zero(j + 1);
                     const uint32_t wlo = (uint32_t)lo, whi = (uint32_t)hi;
                     uint32_t m[16];
                     if (probe16<SMEM>(rtab, wlo, whi, mult, nb, m) < 4095u) {
@@ -639,7 +655,7 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
                 const TableRef<SMEM> ptab(blob, P.blob, IT.pos_off);
                 LocusRef LR; LR.mult = IT.pos_mult; LR.nbuckets = IT.pos_buckets; LR.cut = IT.cutsite; LR.L = IT.length;
                 LR.tw = reinterpret_cast<const uint32_t *>(blob + IT.tw_off);
-                ReadCursor rc; rc.col = P.cells + tile + rl; rc.S = S; rc.Wr = (ilen + 15) >> 4;
+                RC rc; rc.col = P.cells + tile + rl; rc.S = S; rc.sc = s_cells + rl; rc.Wr = (ilen + 15) >> 4;
                 bool open = have;
                 if (is_left) {
                     int a = 0, b = LR.cut;
@@ -669,9 +685,8 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
             clj = (int)(a & 0xFFFFu); tlj = (int)(a >> 16); crj = (int)(b & 0xFFFFu); trj = (int)(b >> 16);
         }
         if (live && !cutwindow_done && clj && T.cutwindow_key != 0xFFFFFFFFu) {   // SlidingWindow.pyx:56-60 (per-read drop-in only)
-            ReadCursor rc; rc.col = col; rc.S = S; rc.Wr = Wr;
             uint32_t code, valid;
-            rc.word16(clj - 10, code, valid);
+            rc0.word16(clj - 10, code, valid);
             if ((code & SCAR_KEY_MASK) == T.cutwindow_key) {
                 rec.status = SCAR_ST_NO_CUT; rec.flags = SCAR_FL_CUTWINDOW;
                 rec.tlj = rec.trj = (uint16_t)cut;
@@ -696,11 +711,11 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
             int n = 0;
             if (plast >= 25) {
                 int j = 25 >> 4;
-                uint64_t c0 = __ldg(col + j * S);
-                uint64_t c1 = j + 1 < Wr ? __ldg(col + (j + 1) * S) : 0ull;
-                uint64_t c2 = j + 2 < Wr ? __ldg(col + (j + 2) * S) : 0ull;
+                uint64_t c0 = rc0.cell(j);
+                uint64_t c1 = rc0.cell_or_zero(j + 1);
+                uint64_t c2 = rc0.cell_or_zero(j + 2);
                 for (int p = 25; p <= plast; ++p) {
-                    if ((p >> 4) != j) { j = p >> 4; c0 = c1; c1 = c2; c2 = j + 2 < Wr ? __ldg(col + (j + 2) * S) : 0ull; }
+                    if ((p >> 4) != j) { j = p >> 4; c0 = c1; c1 = c2; c2 = rc0.cell_or_zero(j + 2); }
                     const int o = p & 15;
                     const uint32_t lo = __funnelshift_r((uint32_t)c0, (uint32_t)c1, 2 * o);
                     const uint32_t hi = __funnelshift_r((uint32_t)c1, (uint32_t)c2, 2 * o);
@@ -722,7 +737,7 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
                 for (int j = clj >> 4; 16 * j < crj; ++j) {
                     const int lo = max(clj, 16 * j) - 16 * j, hi = min(crj, 16 * j + 16) - 16 * j;
                     const uint32_t m = ((1u << (hi - lo)) - 1u) << lo;
-                    has_n |= (((uint32_t)(__ldg(col + j * S) >> 48)) & m) != 0;
+                    has_n |= (((uint32_t)(rc0.cell(j) >> 48)) & m) != 0;
                 }
                 if (!has_n) { cut_found = true; rec.flags |= SCAR_FL_INSERTION; }
             }
@@ -744,11 +759,18 @@ cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count
 {
     if (P.n_reads <= 0) return cudaSuccess;
     const int threads = 256;
-    const size_t smem = 16 + (smem_tables ? P.blob_bytes : 0);
+    // short reads: the tile's cells are staged in shared memory as well (W rows of 2 KB)
+    static const bool no_stage = getenv("SCAR_K3_NO_STAGE") != nullptr;
+    const bool stage = P.W <= K3_STAGE_MAX_CELLS && !no_stage;
+    const size_t smem = 16 + (smem_tables ? P.blob_bytes : 0) + (stage ? (size_t)P.W * K3_TILE * 8 : 0);
     const bool hr = P.hr_len > 0;
-    void (*kern)(const K3Params) =
-        smem_tables ? (hr ? scar_window_kernel<true, true> : scar_window_kernel<true, false>)
-                    : (hr ? scar_window_kernel<false, true> : scar_window_kernel<false, false>);
+    void (*kern)(const K3Params);
+    if (stage)
+        kern = smem_tables ? (hr ? scar_window_kernel<true, true, true> : scar_window_kernel<true, false, true>)
+                           : (hr ? scar_window_kernel<false, true, true> : scar_window_kernel<false, false, true>);
+    else
+        kern = smem_tables ? (hr ? scar_window_kernel<true, true, false> : scar_window_kernel<true, false, false>)
+                           : (hr ? scar_window_kernel<false, true, false> : scar_window_kernel<false, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
