@@ -348,9 +348,9 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
             if (!build_table(pos_kv, bt)) return fail(SCAR_ERR_UNSUPPORTED, "target %d: could not build a position table", t);
             m.pos_off = (uint32_t)blob.size(); m.pos_mult = bt.mult; m.pos_buckets = bt.nbuckets;
             blob.insert(blob.end(), bt.buckets.begin(), bt.buckets.end());
-            // packed locus: one word (16 bases) of padding in front, five behind (32-base compare windows
-            // read three words from an aligned start)
-            std::vector<uint32_t> tw((size_t)(L + 15) / 16 + 6, 0u);
+            // packed locus: one word (16 bases) of padding in front, eight behind (a 64-base compare step may
+            // start up to 10 bases past the cut and reads three words per 32 bases from an aligned start)
+            std::vector<uint32_t> tw((size_t)(L + 15) / 16 + 9, 0u);
             for (int p = 0; p < L; ++p) tw[1 + p / 16] |= scar_base_code(T[p]) << (2 * (p % 16));
             locus_words.push_back(tw);
         } else {

@@ -24,7 +24,7 @@
 #define SCAR_ANCHOR_BATCH 14
 #endif
 #ifndef SCAR_K3_MIN_CTAS
-#define SCAR_K3_MIN_CTAS 5
+#define SCAR_K3_MIN_CTAS 4
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -229,8 +229,8 @@ __device__ __forceinline__ uint64_t mismatch32(const Word32 &r, uint64_t tcode)
 }
 
 // number of bases, going LEFT from read base q-1 / locus base tq-1, that match; at most n.
-// 32 bases per step; the window may start before base 0 of the read on the last step (q-k >= 16 only
-// guarantees 16 bases), so the step is clamped to what exists.
+// The window may start before base 0 of the read on the last step (q-k >= 16 only guarantees 16 bases), so
+// a step is clamped to what exists.
 template <bool SMEM, class RC>
 __device__ __forceinline__ int match_left(const RC &rc, const uint32_t *tw, int q, int tq, int n)
 {
