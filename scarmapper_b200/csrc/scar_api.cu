@@ -139,6 +139,8 @@ struct scar_ctx {
     uint32_t *d_tile_counts = nullptr; size_t tile_counts_cap = 0;
     int64_t *d_tile_offsets = nullptr; size_t tile_offsets_cap = 0;
     int64_t *d_nl = nullptr; size_t nl_cap = 0;
+    scar_record *d_fq_records = nullptr; size_t fq_records_cap = 0; int64_t fq_records_n = 0;   // records of the last FASTQ-text call
+    std::vector<cudaEvent_t> fq_events;
     int launches = 0;
 };
 
@@ -161,7 +163,8 @@ extern "C" void scar_ctx_destroy(scar_ctx *c)
     cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample); cudaFree(c->d_fast_codes);
     cudaFree(c->d_lut_right); cudaFree(c->d_lut_left);
     cudaFree(c->d_slots); cudaFree(c->d_acc); cudaFree(c->d_status);
-    cudaFree(c->d_text); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offsets); cudaFree(c->d_nl);
+    cudaFree(c->d_text); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offsets); cudaFree(c->d_nl); cudaFree(c->d_fq_records);
+    for (cudaEvent_t e : c->fq_events) cudaEventDestroy(e);
     delete c;
 }
 
@@ -916,48 +919,99 @@ extern "C" int scar_process_host(scar_ctx *c, const scar_ragged *seq, const scar
 }
 
 // ---- FASTQ text in host memory -> records: the text is copied to the GPU once and indexed THERE ----------
+// grow a device array and keep its first `keep` elements
+template <typename T> static int ensure_keep(T **p, size_t *cap, size_t need, size_t keep)
+{
+    if (need <= *cap && *p) return SCAR_OK;
+    T *q = nullptr;
+    const size_t n = std::max<size_t>(need + need / 4, 256);
+    CU(cudaMalloc((void **)&q, n * sizeof(T)));
+    if (*p && keep) CU(cudaMemcpy(q, *p, keep * sizeof(T), cudaMemcpyDeviceToDevice));
+    if (*p) CU(cudaFree(*p));
+    *p = q; *cap = n;
+    return SCAR_OK;
+}
+
 extern "C" int scar_process_fastq_host(scar_ctx *c, const uint8_t *text, int64_t n_bytes, uint64_t first_index,
                                        scar_record *records, int64_t records_capacity, int64_t *n_records_out)
 {
     if (!c || !text || n_bytes < 0 || !n_records_out) return fail(SCAR_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));
     *n_records_out = 0;
+    c->fq_records_n = 0;
     if (n_bytes == 0) return SCAR_OK;
     HostBuf &B = c->buf[0];
     int rc = ensure_hostbuf(c, B, 1);
     if (rc) return rc;
-    cudaStream_t s = B.stream;
+    if ((rc = ensure_hostbuf(c, c->buf[1], 1))) return rc;
+    cudaStream_t s = B.stream, sc = c->buf[1].stream;
     if ((rc = ensure(&c->d_text, &c->text_cap, (size_t)n_bytes + 64))) return rc;
-    const int64_t piece = 64ll << 20;                       // plain byte pieces: the record boundaries are found on the GPU
-    for (int64_t off = 0; off < n_bytes; off += piece)
-        CU(cudaMemcpyAsync(c->d_text + off, text + off, (size_t)std::min(piece, n_bytes - off), cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(c->d_text + n_bytes, 0, 64, s));
-    const int64_t n_tiles = (n_bytes + 4095) / 4096;
-    if ((rc = ensure(&c->d_tile_counts, &c->tile_counts_cap, (size_t)n_tiles))) return rc;
-    if ((rc = ensure(&c->d_tile_offsets, &c->tile_offsets_cap, (size_t)scar_fastq_offsets_elems(n_bytes)))) return rc;
-    CU(scar_fastq_index_launch(c->d_text, n_bytes, c->d_tile_counts, c->d_tile_offsets, c->d_export_n, s));
-    c->launches += 3;
-    unsigned long long n_nl = 0;
-    CU(cudaMemcpyAsync(&n_nl, c->d_export_n, sizeof(n_nl), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    // whole records only; a last record may lack its final newline
-    int64_t n_rec = (int64_t)(n_nl / 4);
-    if (n_nl % 4 == 3 && text[n_bytes - 1] != '\n') ++n_rec;
-    *n_records_out = n_rec;
-    if (n_rec == 0) return SCAR_OK;
-    if (records && records_capacity < n_rec) return fail(SCAR_ERR_INVALID, "records buffer too small: %lld records", (long long)n_rec);
-    if ((rc = ensure(&c->d_nl, &c->nl_cap, (size_t)n_nl + 1))) return rc;
-    CU(scar_fastq_positions_launch(c->d_text, n_bytes, c->d_tile_offsets, c->d_nl, (int64_t)n_nl, s));
-    if ((rc = ensure_hostbuf(c, B, n_rec))) return rc;
+    // The text is copied in pieces of plain bytes on one stream; a second stream indexes every piece as soon as
+    // it has landed (newline count, scan, positions - all global offsets into the one device buffer) and runs
+    // the records that have become complete through K2/K1/K3/K4, so the kernels hide under the copy of the
+    // next piece.  A record may straddle pieces: it is simply picked up with the piece that completes it.
+    int64_t piece = 256ll << 20;
+    if (const char *e = getenv("SCAR_FASTQ_PIECE_BYTES")) { const long long v = atoll(e); if (v > 0) piece = v; }
+    piece = std::max<int64_t>(4096, (piece + 4095) / 4096 * 4096);
+    const int64_t n_pieces = (n_bytes + piece - 1) / piece;
+    while ((int64_t)c->fq_events.size() < n_pieces) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->fq_events.push_back(e);
+    }
+    for (int64_t k = 0; k < n_pieces; ++k) {
+        const int64_t b0 = k * piece, len = std::min(piece, n_bytes - b0);
+        CU(cudaMemcpyAsync(c->d_text + b0, text + b0, (size_t)len, cudaMemcpyHostToDevice, sc));
+        if (k == n_pieces - 1) CU(cudaMemsetAsync(c->d_text + n_bytes, 0, 64, sc));
+        CU(cudaEventRecord(c->fq_events[k], sc));
+    }
+    if ((rc = ensure(&c->d_tile_counts, &c->tile_counts_cap, (size_t)((piece + 4095) / 4096)))) return rc;
+    if ((rc = ensure(&c->d_tile_offsets, &c->tile_offsets_cap, (size_t)scar_fastq_offsets_elems(piece)))) return rc;
     const int want = c->platform == SCAR_PLATFORM_ILLUMINA;
-    CU(scar_fastq_records_launch(c->d_text, n_bytes, c->d_nl, (int64_t)n_nl, n_rec, want, B.seq_off, B.seq_len, B.f0_off,
-                                 B.f0_len, B.f1_off, B.f1_len, c->d_status, c->sm_count, s));
-    c->launches += 2;
-    scar_ragged dseq{c->d_text, B.seq_off, B.seq_len, 0}, df0{c->d_text, B.f0_off, B.f0_len, 0}, df1{c->d_text, B.f1_off, B.f1_len, 0};
-    if ((rc = scar_run_dev(c, &dseq, want ? &df0 : nullptr, want ? &df1 : nullptr, n_rec, first_index, B.cells, B.lens,
-                           B.samples, B.records, s))) return rc;
-    if (records) CU(cudaMemcpyAsync(records, B.records, (size_t)n_rec * sizeof(scar_record), cudaMemcpyDeviceToHost, s));
+    int64_t nl_total = 0, rec_done = 0;
+    for (int64_t k = 0; k < n_pieces; ++k) {
+        const int64_t b0 = k * piece, len = std::min(piece, n_bytes - b0);
+        CU(cudaStreamWaitEvent(s, c->fq_events[k], 0));
+        CU(scar_fastq_index_launch(c->d_text + b0, len, c->d_tile_counts, c->d_tile_offsets, c->d_export_n, s));
+        c->launches += 3;
+        unsigned long long n_nl = 0;
+        CU(cudaMemcpyAsync(&n_nl, c->d_export_n, sizeof(n_nl), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        // newline positions of the whole text, grown from the density seen so far
+        size_t want_nl = (size_t)(nl_total + (int64_t)n_nl) + 1;
+        if (want_nl > c->nl_cap && k + 1 < n_pieces)
+            want_nl = (size_t)((double)want_nl * (double)n_bytes / (double)(b0 + len) * 1.02) + 1024;
+        if ((rc = ensure_keep(&c->d_nl, &c->nl_cap, want_nl, (size_t)nl_total))) return rc;
+        CU(scar_fastq_positions_launch(c->d_text + b0, len, c->d_tile_offsets, c->d_nl + nl_total, (int64_t)n_nl, b0, s));
+        ++c->launches;
+        nl_total += (int64_t)n_nl;
+        // whole records only; the last record may lack its final newline
+        int64_t rec_avail = nl_total / 4;
+        if (k == n_pieces - 1 && nl_total % 4 == 3 && text[n_bytes - 1] != '\n') ++rec_avail;
+        const int64_t m = rec_avail - rec_done;
+        if (m <= 0) continue;
+        if (records && records_capacity < rec_avail)
+            return fail(SCAR_ERR_INVALID, "records buffer too small: more than %lld records", (long long)records_capacity);
+        if ((rc = ensure_hostbuf(c, B, m))) return rc;
+        size_t want_rec = (size_t)rec_avail;
+        if (want_rec > c->fq_records_cap && k + 1 < n_pieces)
+            want_rec = (size_t)((double)want_rec * (double)n_bytes / (double)(b0 + len) * 1.02) + 1024;
+        if ((rc = ensure_keep(&c->d_fq_records, &c->fq_records_cap, want_rec, (size_t)rec_done))) return rc;
+        CU(scar_fastq_records_launch(c->d_text, n_bytes, c->d_nl, nl_total, rec_done, m, want, B.seq_off, B.seq_len, B.f0_off,
+                                     B.f0_len, B.f1_off, B.f1_len, c->d_status, c->sm_count, s));
+        ++c->launches;
+        scar_ragged dseq{c->d_text, B.seq_off, B.seq_len, 0}, df0{c->d_text, B.f0_off, B.f0_len, 0}, df1{c->d_text, B.f1_off, B.f1_len, 0};
+        if ((rc = scar_run_dev(c, &dseq, want ? &df0 : nullptr, want ? &df1 : nullptr, m, first_index + (uint64_t)rec_done,
+                               B.cells, B.lens, B.samples, c->d_fq_records + rec_done, s))) return rc;
+        if (records)
+            CU(cudaMemcpyAsync(records + rec_done, c->d_fq_records + rec_done, (size_t)m * sizeof(scar_record),
+                               cudaMemcpyDeviceToHost, s));
+        rec_done = rec_avail;
+    }
     CU(cudaStreamSynchronize(s));
+    CU(cudaStreamSynchronize(sc));
+    *n_records_out = rec_done;
+    c->fq_records_n = rec_done;
     int32_t st = 0;
     CU(cudaMemcpy(&st, c->d_status, sizeof(st), cudaMemcpyDeviceToHost));
     if (st & 24) {
@@ -972,8 +1026,8 @@ extern "C" int scar_fastq_records_fetch(scar_ctx *c, scar_record *records, int64
 {
     if (!c || !records || n_records < 0) return fail(SCAR_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));
-    if (n_records > c->buf[0].reads_cap) return fail(SCAR_ERR_INVALID, "no such records on the device");
-    if (n_records) CU(cudaMemcpy(records, c->buf[0].records, (size_t)n_records * sizeof(scar_record), cudaMemcpyDeviceToHost));
+    if (n_records > c->fq_records_n) return fail(SCAR_ERR_INVALID, "no such records on the device");
+    if (n_records) CU(cudaMemcpy(records, c->d_fq_records, (size_t)n_records * sizeof(scar_record), cudaMemcpyDeviceToHost));
     return SCAR_OK;
 }
 

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(FQ_SCAN_BLOCK) fq_scan2_kernel(unsigned long l
 
 __global__ void __launch_bounds__(256) fq_positions_kernel(const uint8_t *text, int64_t n_bytes, const int64_t *tile_offsets,
                                                            const unsigned long long *block_sums, int64_t *nl_pos,
-                                                           int64_t nl_capacity)
+                                                           int64_t nl_capacity, int64_t byte_base)
 {
     const int64_t off = (int64_t)blockIdx.x * FQ_TILE + threadIdx.x * 16;
     const uint32_t m = off < n_bytes ? newline_mask16(load16(text, off, n_bytes)) : 0u;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) fq_positions_kernel(const uint8_t *text, 
     for (int w = 0; w < warp; ++w) before += s[w];
     int64_t dst = (int64_t)block_sums[blockIdx.x / FQ_SCAN_BLOCK] + tile_offsets[blockIdx.x] + before;
     for (uint32_t mm = m; mm; mm &= mm - 1) {
-        if (dst < nl_capacity) nl_pos[dst] = off + (__ffs(mm) - 1);
+        if (dst < nl_capacity) nl_pos[dst] = byte_base + off + (__ffs(mm) - 1);
         ++dst;
     }
 }
@@ -150,16 +150,17 @@ struct FqViews {
 };
 
 // status bits: 8 = sequence/quality length mismatch, 16 = header without '+'
+// records first_record .. first_record + n_records - 1 of the text; view r - first_record is written
 __global__ void __launch_bounds__(256) fq_records_kernel(const uint8_t *text, int64_t n_bytes, const int64_t *nl_pos,
-                                                         int64_t n_newlines, int64_t n_records, int want_fields,
-                                                         FqViews V, int32_t *status)
+                                                         int64_t n_newlines, int64_t first_record, int64_t n_records,
+                                                         int want_fields, FqViews V, int32_t *status)
 {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_records;
          r += (int64_t)gridDim.x * blockDim.x) {
         int64_t ls[4], le[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int64_t i = 4 * r + k;
+            const int64_t i = 4 * (first_record + r) + k;
             ls[k] = i == 0 ? 0 : nl_pos[i - 1] + 1;
             le[k] = i < n_newlines ? nl_pos[i] : n_bytes;          // last record without a final newline
         }
@@ -212,18 +213,19 @@ cudaError_t scar_fastq_index_launch(const uint8_t *text, int64_t n_bytes, uint32
     return cudaGetLastError();
 }
 
+// `text` may be a piece of a larger buffer: byte_base is added to every position written
 cudaError_t scar_fastq_positions_launch(const uint8_t *text, int64_t n_bytes, const int64_t *tile_offsets, int64_t *nl_pos,
-                                        int64_t nl_capacity, cudaStream_t s)
+                                        int64_t nl_capacity, int64_t byte_base, cudaStream_t s)
 {
     const int64_t n_tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
     if (n_tiles == 0) return cudaSuccess;
     const unsigned long long *block_sums = reinterpret_cast<const unsigned long long *>(tile_offsets + n_tiles);
-    fq_positions_kernel<<<(unsigned)n_tiles, 256, 0, s>>>(text, n_bytes, tile_offsets, block_sums, nl_pos, nl_capacity);
+    fq_positions_kernel<<<(unsigned)n_tiles, 256, 0, s>>>(text, n_bytes, tile_offsets, block_sums, nl_pos, nl_capacity, byte_base);
     return cudaGetLastError();
 }
 
 cudaError_t scar_fastq_records_launch(const uint8_t *text, int64_t n_bytes, const int64_t *nl_pos, int64_t n_newlines,
-                                      int64_t n_records, int want_fields, int64_t *seq_off, int32_t *seq_len,
+                                      int64_t first_record, int64_t n_records, int want_fields, int64_t *seq_off, int32_t *seq_len,
                                       int64_t *f0_off, int32_t *f0_len, int64_t *f1_off, int32_t *f1_len, int32_t *status,
                                       int sm_count, cudaStream_t s)
 {
@@ -232,6 +234,6 @@ cudaError_t scar_fastq_records_launch(const uint8_t *text, int64_t n_bytes, cons
     int64_t blocks = (n_records + 255) / 256;
     const int64_t cap = (int64_t)sm_count * 16;
     if (blocks > cap) blocks = cap;
-    fq_records_kernel<<<(unsigned)blocks, 256, 0, s>>>(text, n_bytes, nl_pos, n_newlines, n_records, want_fields, V, status);
+    fq_records_kernel<<<(unsigned)blocks, 256, 0, s>>>(text, n_bytes, nl_pos, n_newlines, first_record, n_records, want_fields, V, status);
     return cudaGetLastError();
 }

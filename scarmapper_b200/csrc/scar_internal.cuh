@@ -179,8 +179,8 @@ int64_t scar_fastq_offsets_elems(int64_t n_bytes);
 cudaError_t scar_fastq_index_launch(const uint8_t *text, int64_t n_bytes, uint32_t *tile_counts, int64_t *tile_offsets,
                                     unsigned long long *total, cudaStream_t s);
 cudaError_t scar_fastq_positions_launch(const uint8_t *text, int64_t n_bytes, const int64_t *tile_offsets, int64_t *nl_pos,
-                                        int64_t nl_capacity, cudaStream_t s);
+                                        int64_t nl_capacity, int64_t byte_base, cudaStream_t s);
 cudaError_t scar_fastq_records_launch(const uint8_t *text, int64_t n_bytes, const int64_t *nl_pos, int64_t n_newlines,
-                                      int64_t n_records, int want_fields, int64_t *seq_off, int32_t *seq_len,
+                                      int64_t first_record, int64_t n_records, int want_fields, int64_t *seq_off, int32_t *seq_len,
                                       int64_t *f0_off, int32_t *f0_len, int64_t *f1_off, int32_t *f1_len, int32_t *status,
                                       int sm_count, cudaStream_t s);

@@ -659,11 +659,15 @@ def test_dropin_glue_on_gpu_from_fastq_file(name, tmp_path):
         assert [[s[5], s[6], s[7], s[8], s[9]] for s in (res.read_results or [])] == g.get("read_results", [])
 
 
-def test_gpu_fastq_indexer_matches_host_indexer_and_oracle():
+@pytest.mark.parametrize("piece_bytes", [None, 4096, 65536])
+def test_gpu_fastq_indexer_matches_host_indexer_and_oracle(piece_bytes, monkeypatch):
     """FASTQ text -> GPU indexer (newline count / scan / positions, one thread per record) -> whole path.
     Records must equal the host-indexed views path and the oracle; malformed text must raise where the
-    reference raises."""
+    reference raises.  Small pieces force the pipelined path through many pieces (records straddling a piece
+    boundary, pieces that complete no record, the unterminated last record in the last piece)."""
     import random
+    if piece_bytes:
+        monkeypatch.setenv("SCAR_FASTQ_PIECE_BYTES", str(piece_bytes))
     from scarmapper_b200 import fastq
     from scarmapper_b200._native import ScarError
     cfg = synth.make_config("C3", n_reads=30000, seed=61, min_len=40, p_n=0.02)
