@@ -761,8 +761,10 @@ cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count
     const int threads = 256;
     // short reads: the tile's cells are staged in shared memory as well (W rows of 2 KB)
     static const bool no_stage = getenv("SCAR_K3_NO_STAGE") != nullptr;
-    const bool stage = P.W <= K3_STAGE_MAX_CELLS && !no_stage;
-    const size_t smem = 16 + (smem_tables ? P.blob_bytes : 0) + (stage ? (size_t)P.W * K3_TILE * 8 : 0);
+    const size_t smem_base = 16 + (smem_tables ? P.blob_bytes : 0), cell_bytes = (size_t)P.W * K3_TILE * 8;
+    // (227 KB per CTA on sm_100, 7.5 KB of it the kernel's static queues and result arrays)
+    const bool stage = P.W <= K3_STAGE_MAX_CELLS && !no_stage && smem_base + cell_bytes + 7680 <= 227 * 1024;
+    const size_t smem = smem_base + (stage ? cell_bytes : 0);
     const bool hr = P.hr_len > 0;
     void (*kern)(const K3Params);
     if (stage)
