@@ -4,15 +4,20 @@
 // (reference scarmapper/INDEL_Processing.py:135-196) and SlidingWindow.sliding_window
 // (scarmapper/SlidingWindow.pyx:20-171), plus the phasing scan of consensus_demultiplex
 // (INDEL_Processing.py:948-975).  Not a translation: the reference compares every 10-nt read
-// window with every target window.  Here each target side is a bucketed perfect-hash table
-// "10-mer -> smallest window index i" (two entries per 8-byte bucket, one probe, no chains) staged in
-// shared memory by one TMA bulk copy per CTA; ONE THREAD owns a read.  The packed batch is
-// cell-major ([cell][read]), so a warp's loads of cell j are one coalesced 256-byte request, and the
-// per-read bookkeeping (filters, phasing, junction call) costs one instruction per 32 reads instead of
-// one per read.  A thread walks its read 16 positions (one cell) at a time: the 16 window keys are
-// independent funnel shifts of a 64-bit register pair, the 16 probes are issued back to back
-// (16 shared-memory loads in flight per thread), and the first hit in scan order is kept with a
-// max / min of (position << 12 | i).
+// window with every target window.  Here a window is a 20-bit key probed in a bucketed perfect-hash
+// table (two entries per 8-byte bucket, one probe, no chains); the tables, the packed loci and the
+// per-target metadata are one blob staged in shared memory by one TMA bulk copy per CTA.
+//
+// A CTA works on tiles of 256 reads.  The packed batch is cell-major ([cell][read]), so the tile's cells
+// are W rows of 2 KB; for short reads they are copied into shared memory up front (cp.async).  Per tile:
+//   phase 1  one thread per read: filters, phasing, the first anchor step of both junction searches;
+//   phase 2  the searches that are still open are items in a shared-memory queue and are worked off in
+//            rounds by dense warps (batch step + anchor step, re-queued while open);
+//   phase 3  one thread per read: cut-window check, HR donor scan, N-in-insertion test, junction call,
+//            one 16-byte record store.
+// Two search strategies, both bit-exact: anchor-and-extend for loci whose 10-mers are all distinct
+// (position table + 32-base packed compares), and an exhaustive cell scan for any locus (16 probes per
+// cell issued back to back, first hit in scan order kept with a max / min of (position << 12 | i)).
 //
 //   left  search: positions p = len-20 .. 16 descending, first hit -> clj = p+10, tlj = cut - i
 //   right search: positions p = 10 .. len-26 ascending,  first hit -> crj = p,    trj = cut + i
