@@ -139,7 +139,9 @@ __device__ __forceinline__ uint32_t runs_of_ten(uint32_t vwin)
 // decided by that position alone — so the scan jumps over the stretch instead of probing each window.
 // Positions around a mismatch or the junction are still probed one by one: results are identical to
 // the exhaustive scan.
+#ifndef K3_TILE
 #define K3_TILE 256
+#endif
 #ifndef K3_STAGE_MAX_CELLS
 #define K3_STAGE_MAX_CELLS 12          // reads up to 192 nt: 24 KB of cells per tile
 #endif
@@ -763,7 +765,7 @@ cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count
                                int *launches)
 {
     if (P.n_reads <= 0) return cudaSuccess;
-    const int threads = 256;
+    const int threads = K3_TILE;
     // short reads: the tile's cells are staged in shared memory as well (W rows of 2 KB)
     static const bool no_stage = getenv("SCAR_K3_NO_STAGE") != nullptr;
     const size_t smem_base = 16 + (smem_tables ? P.blob_bytes : 0), cell_bytes = (size_t)P.W * K3_TILE * 8;
