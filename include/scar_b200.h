@@ -181,9 +181,10 @@ int scar_fastq_index(const uint8_t *text, int64_t n_bytes, int32_t is_final, int
                      int64_t *f1_off, int32_t *f1_len, int64_t *n_records, int64_t *consumed);
 
 /* The same from FASTQ TEXT in host memory (whole records; a last record may lack its newline): the text is
- * copied to the GPU once, the records are indexed there (newline count / scan / positions, one thread per
- * record for the views), and the whole path runs on the views.  records (may be NULL) receives one record
- * per FASTQ record in file order; *n_records the count. */
+ * copied to the GPU once, in pieces (256 MB; SCAR_FASTQ_PIECE_BYTES overrides) on one stream, while a second
+ * stream indexes each piece there (newline count / scan / positions, one thread per record for the views)
+ * and runs the records that have become complete through the whole path, on the views.  records (may be
+ * NULL) receives one record per FASTQ record in file order; *n_records the count. */
 int scar_process_fastq_host(scar_ctx *ctx, const uint8_t *text, int64_t n_bytes, uint64_t first_index,
                             scar_record *records, int64_t records_capacity, int64_t *n_records);
 
