@@ -969,6 +969,8 @@ extern "C" int scar_process_fastq_host(scar_ctx *c, const uint8_t *text, int64_t
     if ((rc = ensure(&c->d_tile_offsets, &c->tile_offsets_cap, (size_t)scar_fastq_offsets_elems(piece)))) return rc;
     const int want = c->platform == SCAR_PLATFORM_ILLUMINA;
     int64_t nl_total = 0, rec_done = 0;
+    // an early return must not leave copies out of the caller's buffer in flight
+    auto drain = [&](int code) { cudaStreamSynchronize(sc); cudaStreamSynchronize(s); return code; };
     for (int64_t k = 0; k < n_pieces; ++k) {
         const int64_t b0 = k * piece, len = std::min(piece, n_bytes - b0);
         CU(cudaStreamWaitEvent(s, c->fq_events[k], 0));
@@ -981,7 +983,7 @@ extern "C" int scar_process_fastq_host(scar_ctx *c, const uint8_t *text, int64_t
         size_t want_nl = (size_t)(nl_total + (int64_t)n_nl) + 1;
         if (want_nl > c->nl_cap && k + 1 < n_pieces)
             want_nl = (size_t)((double)want_nl * (double)n_bytes / (double)(b0 + len) * 1.02) + 1024;
-        if ((rc = ensure_keep(&c->d_nl, &c->nl_cap, want_nl, (size_t)nl_total))) return rc;
+        if ((rc = ensure_keep(&c->d_nl, &c->nl_cap, want_nl, (size_t)nl_total))) return drain(rc);
         CU(scar_fastq_positions_launch(c->d_text + b0, len, c->d_tile_offsets, c->d_nl + nl_total, (int64_t)n_nl, b0, s));
         ++c->launches;
         nl_total += (int64_t)n_nl;
@@ -991,18 +993,18 @@ extern "C" int scar_process_fastq_host(scar_ctx *c, const uint8_t *text, int64_t
         const int64_t m = rec_avail - rec_done;
         if (m <= 0) continue;
         if (records && records_capacity < rec_avail)
-            return fail(SCAR_ERR_INVALID, "records buffer too small: more than %lld records", (long long)records_capacity);
-        if ((rc = ensure_hostbuf(c, B, m))) return rc;
+            return drain(fail(SCAR_ERR_INVALID, "records buffer too small: more than %lld records", (long long)records_capacity));
+        if ((rc = ensure_hostbuf(c, B, m))) return drain(rc);
         size_t want_rec = (size_t)rec_avail;
         if (want_rec > c->fq_records_cap && k + 1 < n_pieces)
             want_rec = (size_t)((double)want_rec * (double)n_bytes / (double)(b0 + len) * 1.02) + 1024;
-        if ((rc = ensure_keep(&c->d_fq_records, &c->fq_records_cap, want_rec, (size_t)rec_done))) return rc;
+        if ((rc = ensure_keep(&c->d_fq_records, &c->fq_records_cap, want_rec, (size_t)rec_done))) return drain(rc);
         CU(scar_fastq_records_launch(c->d_text, n_bytes, c->d_nl, nl_total, rec_done, m, want, B.seq_off, B.seq_len, B.f0_off,
                                      B.f0_len, B.f1_off, B.f1_len, c->d_status, c->sm_count, s));
         ++c->launches;
         scar_ragged dseq{c->d_text, B.seq_off, B.seq_len, 0}, df0{c->d_text, B.f0_off, B.f0_len, 0}, df1{c->d_text, B.f1_off, B.f1_len, 0};
         if ((rc = scar_run_dev(c, &dseq, want ? &df0 : nullptr, want ? &df1 : nullptr, m, first_index + (uint64_t)rec_done,
-                               B.cells, B.lens, B.samples, c->d_fq_records + rec_done, s))) return rc;
+                               B.cells, B.lens, B.samples, c->d_fq_records + rec_done, s))) return drain(rc);
         if (records)
             CU(cudaMemcpyAsync(records + rec_done, c->d_fq_records + rec_done, (size_t)m * sizeof(scar_record),
                                cudaMemcpyDeviceToHost, s));

@@ -767,7 +767,7 @@ cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count
     if (P.n_reads <= 0) return cudaSuccess;
     const int threads = K3_TILE;
     // short reads: the tile's cells are staged in shared memory as well (W rows of 2 KB)
-    static const bool no_stage = getenv("SCAR_K3_NO_STAGE") != nullptr;
+    const bool no_stage = getenv("SCAR_K3_NO_STAGE") != nullptr;
     const size_t smem_base = 16 + (smem_tables ? P.blob_bytes : 0), cell_bytes = (size_t)P.W * K3_TILE * 8;
     // (227 KB per CTA on sm_100, 7.5 KB of it the kernel's static queues and result arrays)
     const bool stage = P.W <= K3_STAGE_MAX_CELLS && !no_stage && smem_base + cell_bytes + 7680 <= 227 * 1024;

@@ -493,6 +493,29 @@ def test_tables_in_global_memory_path(anchor, monkeypatch):
 
 
 @pytest.mark.parametrize("anchor", ["anchor", "scan"])
+def test_cells_read_from_global_memory_path(anchor, monkeypatch):
+    """Short reads normally have their tile's cells staged in shared memory; SCAR_K3_NO_STAGE=1 runs the same
+    batch through the global-memory cell path (what reads longer than 192 nt take): same records and table."""
+    if anchor == "scan":
+        monkeypatch.setenv("SCAR_NO_ANCHOR", "1")
+    cfg = synth.make_config("C2", n_reads=40000, seed=77, min_len=60, p_n=0.02)
+    batch = cfg.generate(0, 40000)
+    reads = cfg.reads_as_strings(batch)
+    f0, f1 = cfg.fields_as_strings(batch)
+    pin = synth_problem(cfg)
+    eng = engine_for(pin, cfg.read_len)
+    staged = eng.process_host(reads, f0, f1).copy()
+    tab = eng.table().copy()
+    eng.close()
+    monkeypatch.setenv("SCAR_K3_NO_STAGE", "1")
+    eng = engine_for(pin, cfg.read_len)
+    rec = eng.process_host(reads, f0, f1)
+    assert rec.tobytes() == staged.tobytes() and eng.table().tobytes() == tab.tobytes()
+    assert_records_equal(rec, orc.classify_batch(orc.Problem(**pin), reads, f0, f1), reads)
+    eng.close()
+
+
+@pytest.mark.parametrize("anchor", ["anchor", "scan"])
 def test_long_reads_up_to_1024(anchor, monkeypatch):
     """Reads of 300-1000 nt on a 1.2-kb locus (W up to 64 cells), large deletions and insertions."""
     import random
