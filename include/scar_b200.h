@@ -162,6 +162,14 @@ int scar_table_merge_dev(scar_ctx *ctx, const scar_entry *entries, int64_t n_ent
  * (owner = (h2 >> 40) % n_parts).  Exchange the regions with one all-to-all, scar_table_clear_dev, then fold the
  * received regions: every rank ends up holding the merged entries it owns.  All three are stream-ordered. */
 int scar_table_export_parts_dev(scar_ctx *ctx, scar_entry *regions, int32_t n_parts, int64_t region_capacity, void *stream);
+/* The export fused with the exchange over NVLink peer memory: peer_regions[o] (host array of n_parts DEVICE
+ * pointers) is rank o's receive buffer ([n_parts][region_capacity] entries) mapped into this process (CUDA IPC /
+ * symmetric memory; peer_regions[my_rank] is this rank's own).  Every entry is stored directly into region
+ * `my_rank` of its owner's buffer and the count is published as that region's header - no all-to-all pass.
+ * The caller orders the ranks (a barrier before: the peers have consumed their buffers; a barrier after: all
+ * stores have landed), then scar_table_clear_dev + scar_table_merge_parts_dev on its own receive buffer. */
+int scar_table_export_p2p_dev(scar_ctx *ctx, void *const *peer_regions, int32_t n_parts, int32_t my_rank,
+                              int64_t region_capacity, void *stream);
 int scar_table_clear_dev(scar_ctx *ctx, void *stream);
 int scar_table_merge_parts_dev(scar_ctx *ctx, const scar_entry *regions, int32_t n_parts, int64_t region_capacity, void *stream);
 

@@ -9,7 +9,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import synth  # noqa: E402
-from scarmapper_b200.distributed import exchange_regions, reduce_accumulators  # noqa: E402
+from scarmapper_b200.distributed import exchange_regions, peer_receive_buffers, reduce_accumulators  # noqa: E402
 from scarmapper_b200.engine import HostRagged, ScarEngine, ScarProblem  # noqa: E402
 
 
@@ -49,6 +49,28 @@ def main():
             if rank == 0:
                 print("merge_probe iter", it, " ".join("{:.3f}".format(ev[i].elapsed_time(ev[i + 1])) for i in range(len(names))),
                       flush=True)
+    # the same with the export fused with the exchange over peer memory
+    got = peer_receive_buffers(world * region, torch.device("cuda", local))
+    if got is not None:
+        precv, hdl = got
+        names2 = ["barrier0", "export_p2p", "barrier1", "clear", "merge_parts"]
+        tot2 = {k: 0.0 for k in names2}
+        for it in range(reps + 2):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names2) + 1)]
+            eng.reset_async(); eng.run_resident(res, first_index=rank * n)
+            dist.barrier(); torch.cuda.synchronize()
+            ev[0].record(); hdl.barrier(channel=0)
+            ev[1].record(); eng.export_p2p_dev(hdl.buffer_ptrs, rank, region)
+            ev[2].record(); hdl.barrier(channel=1)
+            ev[3].record(); eng.clear_table_dev()
+            ev[4].record(); eng.merge_parts_dev(precv, world)
+            ev[5].record(); torch.cuda.synchronize()
+            if it >= 2:
+                for i, k in enumerate(names2):
+                    tot2[k] += ev[i].elapsed_time(ev[i + 1])
+        if rank == 0:
+            print("merge_probe p2p world={} ".format(world) + " ".join("{}={:.3f}ms".format(k, v / reps) for k, v in tot2.items()),
+                  flush=True)
     if rank == 0:
         print("merge_probe world={} ".format(world) + " ".join("{}={:.3f}ms".format(k, v / reps) for k, v in tot.items()),
               flush=True)

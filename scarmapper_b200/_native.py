@@ -93,6 +93,7 @@ PROTOTYPES = {
     "scar_table_export_dev": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
     "scar_table_merge_dev": (C.c_int, [_P, _P, C.c_int64, _P]),
     "scar_table_export_parts_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
+    "scar_table_export_p2p_dev": (C.c_int, [_P, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64, _P]),
     "scar_table_clear_dev": (C.c_int, [_P, _P]),
     "scar_table_merge_parts_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
     "scar_reset_dev": (C.c_int, [_P, _P]),

@@ -139,6 +139,7 @@ struct scar_ctx {
     uint32_t *d_tile_counts = nullptr; size_t tile_counts_cap = 0;
     int64_t *d_tile_offsets = nullptr; size_t tile_offsets_cap = 0;
     int64_t *d_nl = nullptr; size_t nl_cap = 0;
+    unsigned long long *d_part_cursor = nullptr;     // region cursors of the peer-memory export
     scar_record *d_fq_records = nullptr; size_t fq_records_cap = 0; int64_t fq_records_n = 0;   // records of the last FASTQ-text call
     std::vector<cudaEvent_t> fq_events;
     int launches = 0;
@@ -163,7 +164,7 @@ extern "C" void scar_ctx_destroy(scar_ctx *c)
     cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample); cudaFree(c->d_fast_codes);
     cudaFree(c->d_lut_right); cudaFree(c->d_lut_left);
     cudaFree(c->d_slots); cudaFree(c->d_acc); cudaFree(c->d_status);
-    cudaFree(c->d_text); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offsets); cudaFree(c->d_nl); cudaFree(c->d_fq_records);
+    cudaFree(c->d_text); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offsets); cudaFree(c->d_nl); cudaFree(c->d_fq_records); cudaFree(c->d_part_cursor);
     for (cudaEvent_t e : c->fq_events) cudaEventDestroy(e);
     delete c;
 }
@@ -714,6 +715,26 @@ extern "C" int scar_table_export_parts_dev(scar_ctx *c, scar_entry *regions, int
     CU(scar_launch_export_parts(c->d_slots, c->capacity, regions, (uint32_t)n_parts, (uint64_t)region_capacity,
                                 c->d_status, c->sm_count, s));
     ++c->launches;
+    return SCAR_OK;
+}
+
+extern "C" int scar_table_export_p2p_dev(scar_ctx *c, void *const *peer_regions, int32_t n_parts, int32_t my_rank,
+                                         int64_t region_capacity, void *stream)
+{
+    if (!c || !peer_regions || n_parts < 1 || my_rank < 0 || my_rank >= n_parts || region_capacity < 2)
+        return fail(SCAR_ERR_INVALID, "bad argument");
+    if (n_parts > SCAR_MAX_PEERS) return fail(SCAR_ERR_UNSUPPORTED, "more than %d peers", SCAR_MAX_PEERS);
+    for (int o = 0; o < n_parts; ++o)
+        if (!peer_regions[o]) return fail(SCAR_ERR_INVALID, "peer %d: null receive buffer", o);
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c->d_part_cursor) {
+        CU(cudaMalloc((void **)&c->d_part_cursor, SCAR_MAX_PEERS * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->d_part_cursor, 0, SCAR_MAX_PEERS * sizeof(unsigned long long), s));
+    }
+    CU(scar_launch_export_p2p(c->d_slots, c->capacity, reinterpret_cast<scar_entry *const *>(peer_regions), (uint32_t)n_parts,
+                              (uint32_t)my_rank, (uint64_t)region_capacity, c->d_part_cursor, c->d_status, c->sm_count, s));
+    c->launches += 2;
     return SCAR_OK;
 }
 

@@ -171,6 +171,10 @@ cudaError_t scar_launch_export(const ScarTableSlot *slots, uint64_t capacity, sc
 cudaError_t scar_launch_merge(const K4Params &P, const scar_entry *in, uint64_t n_in, int sm_count, cudaStream_t stream);
 cudaError_t scar_launch_export_parts(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint32_t n_parts,
                                      uint64_t region, int32_t *status, int sm_count, cudaStream_t stream);
+#define SCAR_MAX_PEERS 32
+cudaError_t scar_launch_export_p2p(const ScarTableSlot *slots, uint64_t capacity, scar_entry *const *peer_base,
+                                   uint32_t n_parts, uint32_t my_rank, uint64_t region, unsigned long long *cursors,
+                                   int32_t *status, int sm_count, cudaStream_t stream);
 cudaError_t scar_launch_merge_parts(const K4Params &P, const scar_entry *in, uint32_t n_parts, uint64_t region,
                                     int sm_count, cudaStream_t stream);
 

@@ -387,6 +387,74 @@ __global__ void scar_export_parts_kernel(const ScarTableSlot *slots, uint64_t ca
     }
 }
 
+// The same export fused with the exchange: every entry is stored straight into the receive buffer of its
+// OWNER GPU through NVLink peer memory (peers.base[o] is rank o's receive buffer mapped into this process;
+// this rank writes region `my_rank` of it), so no separate all-to-all pass runs and the transfer overlaps
+// the table scan.  The region cursors stay local; a second tiny kernel publishes the counts as headers.
+struct ScarPeers { scar_entry *base[SCAR_MAX_PEERS]; };
+
+__global__ void scar_export_p2p_kernel(const ScarTableSlot *slots, uint64_t capacity, ScarPeers peers, uint32_t n_parts,
+                                       uint32_t my_rank, uint64_t region, unsigned long long *cursors)
+{
+    const uint64_t n_round = (capacity + 31) & ~(uint64_t)31;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        ScarTableSlot s;
+        s.tag = 0;
+        if (i < capacity) s = slots[i];
+        const bool used = s.tag != 0;
+        if (!__any_sync(0xFFFFFFFFu, used)) continue;
+        const uint64_t h2 = (uint64_t)(s.tag >> 64);
+        const uint32_t owner = used ? (uint32_t)(h2 >> 40) % n_parts : 0xFFFFFFFFu;
+        unsigned long long pos = 0;
+        for (uint32_t o = 0; o < n_parts; ++o) {       // one atomic per (warp, owner)
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, owner == o);
+            if (!bal) continue;
+            unsigned long long base = 0;
+            if (lane == __ffs(bal) - 1) base = atomicAdd(cursors + o, (unsigned long long)__popc(bal));
+            base = __shfl_sync(0xFFFFFFFFu, base, __ffs(bal) - 1);
+            if (owner == o) pos = 1ull + base + __popc(bal & ((1u << lane) - 1u));
+        }
+        if (used && pos < region) {                    // (an overflow is reported by the header kernel)
+            scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = h2; e.first_idx = ~s.inv_first; e.count = s.count;
+            e.sample = (uint16_t)s.sample; e.pad = 0;
+            uint4 *dst = reinterpret_cast<uint4 *>(peers.base[owner] + (uint64_t)my_rank * region + pos);
+            const uint4 *src = reinterpret_cast<const uint4 *>(&e);
+            dst[0] = src[0]; dst[1] = src[1];          // two 16-byte stores over NVLink
+        }
+    }
+}
+
+__global__ void scar_export_p2p_headers_kernel(ScarPeers peers, uint32_t n_parts, uint32_t my_rank, uint64_t region,
+                                               unsigned long long *cursors, int32_t *status)
+{
+    const uint32_t o = threadIdx.x;
+    if (o >= n_parts) return;
+    unsigned long long n = cursors[o];
+    cursors[o] = 0;                                    // ready for the next export
+    if (n > region - 1) { atomicOr(status, 4); n = region - 1; }
+    scar_entry h; h.h1 = n; h.h2 = 0; h.first_idx = 0; h.count = 0; h.sample = 0; h.pad = 0;
+    uint4 *dst = reinterpret_cast<uint4 *>(peers.base[o] + (uint64_t)my_rank * region);
+    const uint4 *src = reinterpret_cast<const uint4 *>(&h);
+    dst[0] = src[0]; dst[1] = src[1];
+}
+
+cudaError_t scar_launch_export_p2p(const ScarTableSlot *slots, uint64_t capacity, scar_entry *const *peer_base,
+                                   uint32_t n_parts, uint32_t my_rank, uint64_t region, unsigned long long *cursors,
+                                   int32_t *status, int sm_count, cudaStream_t stream)
+{
+    ScarPeers peers;
+    for (uint32_t o = 0; o < SCAR_MAX_PEERS; ++o) peers.base[o] = o < n_parts ? peer_base[o] : nullptr;
+    const int threads = 256;
+    int64_t blocks = (int64_t)((capacity + threads - 1) / threads);
+    const int64_t cap = (int64_t)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    scar_export_p2p_kernel<<<(unsigned)blocks, threads, 0, stream>>>(slots, capacity, peers, n_parts, my_rank, region, cursors);
+    scar_export_p2p_headers_kernel<<<1, 32, 0, stream>>>(peers, n_parts, my_rank, region, cursors, status);
+    return cudaGetLastError();
+}
+
 __global__ void scar_merge_parts_kernel(K4Params P, const scar_entry *in, uint32_t n_parts, uint64_t region)
 {
     __shared__ unsigned int s_new;

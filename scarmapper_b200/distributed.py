@@ -97,6 +97,26 @@ def merge_tables_partitioned(export_parts_fn, clear_fn, merge_parts_fn, send: to
     merge_parts_fn(recv, world)
 
 
+def peer_receive_buffers(rows: int, device, group=None):
+    """A receive buffer of `rows` 32-byte entries on every rank, each mapped into every other rank's address
+    space (torch symmetric memory: CUDA IPC over NVLink).  Returns (local tensor, handle) or None when the
+    backend cannot do it (CPU tests, no peer access)."""
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        if dist.get_backend(group) != "nccl":
+            return None
+        pg = group if group is not None else dist.group.WORLD
+        buf = symm_mem.empty((rows, 32), dtype=torch.uint8, device=device)
+        hdl = symm_mem.rendezvous(buf, pg)
+        if len(hdl.buffer_ptrs) != dist.get_world_size(group):
+            return None
+        return buf, hdl
+    except Exception as exc:  # noqa: BLE001 - any failure here means "use the all-to-all instead"
+        import warnings
+        warnings.warn("peer-memory receive buffers unavailable ({}); using NCCL all-to-all".format(exc))
+        return None
+
+
 class DistributedScar:
     """Glue between a ScarEngine and the process group."""
 
@@ -106,12 +126,37 @@ class DistributedScar:
         self.device = torch.device("cuda", engine.device)
         self.entry_buf = torch.empty((entry_capacity, 32), dtype=torch.uint8, device=self.device)
         self._send = self._recv = None
+        self._peer = None          # (recv tensor, symmetric-memory handle, region_capacity) of the fused export
+        # Export fused with the exchange over NVLink peer memory (scar_table_export_p2p_dev).  Off by default: in
+        # isolation it costs the same as export + NCCL all-to-all (0.23 ms per 10 M reads at N=2), but its remote
+        # stores hold SMs longer than NCCL's copy does and bench.py runs the merge under the next step's kernels
+        # (1.25e10 vs 1.32e10 reads/s at N=2).
+        self.use_peer_memory = False
+
+    def _peer_buffers(self, world: int, region_capacity: int):
+        if self._peer is None or self._peer[2] != region_capacity:
+            got = peer_receive_buffers(world * region_capacity, self.device, self.group) if self.use_peer_memory else None
+            self._peer = (got[0], got[1], region_capacity) if got else (None, None, region_capacity)
+        return self._peer
 
     def merge_partitioned(self, region_capacity: int = 1 << 18):
         """Owner-partitioned merge (cost independent of the GPU count): afterwards this rank's table holds the
-        merged entries whose key it owns; the dense accumulators are all-reduced.  Fully asynchronous."""
+        merged entries whose key it owns; the dense accumulators are all-reduced.  Fully asynchronous.
+        With use_peer_memory (NCCL on NVLink) the export kernel stores every entry directly into its owner's
+        receive buffer - export and exchange are one kernel, fenced by two device-side barriers; otherwise the
+        regions are exchanged with one all-to-all."""
         e = self.engine
         world = dist.get_world_size(self.group)
+        recv, hdl, _ = self._peer_buffers(world, region_capacity)
+        if hdl is not None:
+            hdl.barrier(channel=0)                     # every peer has folded what it received last time
+            e.export_p2p_dev(hdl.buffer_ptrs, dist.get_rank(self.group), region_capacity)
+            hdl.barrier(channel=1)                     # every peer's stores into this rank's buffer have landed
+            e.clear_table_dev()
+            e.merge_parts_dev(recv, world)
+            reduce_accumulators(e.export_accumulators_dev, e.import_accumulators_dev, e.accumulator_words(),
+                                self.device, self.group)
+            return
         if self._send is None or self._send.shape[0] != world * region_capacity:
             self._send = torch.empty((world * region_capacity, 32), dtype=torch.uint8, device=self.device)
             self._recv = torch.empty_like(self._send)

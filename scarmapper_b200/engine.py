@@ -324,6 +324,13 @@ class ScarEngine:
         N.check(self._L.scar_table_export_parts_dev(self._ctx, regions.data_ptr(), n_parts, regions.shape[0] // n_parts,
                                                     self._stream()))
 
+    def export_p2p_dev(self, peer_ptrs, my_rank: int, region_capacity: int):
+        """Owner-partitioned export straight into the peers' receive buffers (device pointers mapped into this
+        process, one per rank): the exchange is part of the kernel, over NVLink peer memory."""
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        N.check(self._L.scar_table_export_p2p_dev(self._ctx, arr, len(peer_ptrs), int(my_rank), int(region_capacity),
+                                                  self._stream()))
+
     def clear_table_dev(self):
         N.check(self._L.scar_table_clear_dev(self._ctx, self._stream()))
 

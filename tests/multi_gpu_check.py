@@ -48,12 +48,26 @@ def main():
     torch.cuda.synchronize()
     tab_a = ea.table()
     cnt_a, un_a = ea.counters()
-    # (b) owner-partitioned all-to-all
+    # (b) owner-partitioned, export fused with the exchange over NVLink peer memory (twice: the second merge
+    #     reuses the peer buffers and must see the barriers)
     eb = shard_engine()
-    DistributedScar(eb).merge_partitioned(region_capacity=1 << 17)
+    db = DistributedScar(eb)
+    db.use_peer_memory = True
+    db.merge_partitioned(region_capacity=1 << 17)
     torch.cuda.synchronize()
+    peer_path = db._peer is not None and db._peer[1] is not None
     tab_b = eb.table()
     cnt_b, un_b = eb.counters()
+    # (c) owner-partitioned with the NCCL all-to-all
+    ec = shard_engine()
+    dc = DistributedScar(ec)
+    dc.merge_partitioned(region_capacity=1 << 17)
+    torch.cuda.synchronize()
+    tab_c = ec.table()
+    cnt_c, un_c = ec.counters()
+    same_bc = tab_b.tobytes() == tab_c.tobytes() and bool((cnt_b == cnt_c).all()) and un_b == un_c
+    flags = [None] * world
+    dist.all_gather_object(flags, (same_bc, peer_path))
     sizes = [None] * world
     dist.all_gather_object(sizes, tab_b)
     ok = True
@@ -70,6 +84,8 @@ def main():
             "partitioned table": full_b.tobytes() == want.tobytes(),
             "partitioned counters": bool((cnt_b == cnt).all()) and un_b == un,
             "partitions disjoint": len(full_b) == len(want),
+            "peer-memory path == all-to-all path": all(f[0] for f in flags),
+            "peer-memory path taken": all(f[1] for f in flags),
         }
         ok = all(checks.values())
         print("multi_gpu_check world={} entries={} {}".format(world, len(want), checks), flush=True)
