@@ -56,6 +56,7 @@ __device__ __forceinline__ void encode16(const uint8_t *u, int n, uint32_t &code
 __device__ __forceinline__ uint32_t spread_invalid(uint32_t valid, int n)
 {
     uint32_t m = ~valid & (n >= 16 ? 0xFFFFu : ((1u << n) - 1u));
+    if (m == 0u) return 0u;                       // the usual case: every base is A, C, G or T
     m = (m | (m << 8)) & 0x00FF00FFu; m = (m | (m << 4)) & 0x0F0F0F0Fu;
     m = (m | (m << 2)) & 0x33333333u; m = (m | (m << 1)) & 0x55555555u;
     return m;
@@ -68,6 +69,10 @@ __global__ void __launch_bounds__(256) scar_demux_kernel(const K2Params P)
     __shared__ uint32_t s_code[2][64];     // 2-bit codes of the distinct index strings (FAST)
     __shared__ int32_t s_len[2][64];
     __shared__ unsigned long long s_lenmask[2][17];   // bit d set: string d of that side is n nt long (FAST)
+    __shared__ uint16_t s_first[1024];                // first_sample matrix when it is small enough
+    const int n_pairs = P.n_right * P.n_left;
+    const bool first_in_smem = n_pairs <= 1024;
+    if (first_in_smem) for (int i = threadIdx.x; i < n_pairs; i += blockDim.x) s_first[i] = P.first_sample[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = P.class_map[i];
     for (int i = threadIdx.x; i < P.n_right + P.n_left; i += blockDim.x) {
         const int side = i >= P.n_right, d = side ? i - P.n_right : i;
@@ -180,13 +185,17 @@ __global__ void __launch_bounds__(256) scar_demux_kernel(const K2Params P)
             }
         }
         uint32_t best = SCAR_SAMPLE_NONE;
-        if (ok_r && ok_l) {
+        if (ok_r && ok_l && !(ok_r & (ok_r - 1)) && !(ok_l & (ok_l - 1))) {
+            // one acceptable string on each side (the usual case): a single matrix entry
+            const int idx = (__ffsll((long long)ok_r) - 1) * P.n_left + (__ffsll((long long)ok_l) - 1);
+            best = first_in_smem ? s_first[idx] : P.first_sample[idx];
+        } else if (ok_r && ok_l) {
             // first manifest row whose (right, left) strings are both acceptable
             for (uint64_t a = ok_r; a; a &= a - 1) {
                 const int dr = __ffsll((long long)a) - 1;
                 for (uint64_t b = ok_l; b; b &= b - 1) {
                     const int dl = __ffsll((long long)b) - 1;
-                    const uint32_t s = P.first_sample[dr * P.n_left + dl];
+                    const uint32_t s = first_in_smem ? s_first[dr * P.n_left + dl] : P.first_sample[dr * P.n_left + dl];
                     best = s < best ? s : best;
                 }
             }
