@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=50_000, help="reads of the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=120_000, help="reads of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels-only", action="store_true",
                     help="tuning runs: skip the end-to-end arms (the line then carries e2e.value = null)")
