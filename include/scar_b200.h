@@ -9,6 +9,7 @@
  *   scarmapper/INDEL_Processing.py:891-1024 consensus_demultiplex loop      -> scar_demux_dev (+ phasing in scar_classify_dev)
  *   scarmapper/INDEL_Processing.py:1126-1201 index_matching                 -> scar_demux_dev
  *   Valkyries/Sequence_Magic.py:123-136     match_maker(query, unknown)     -> scar_match_maker_batch
+ *   scarmapper/INDEL_Processing.py:550-700  homeology_search / templated_insertion_search -> scar_homeology_batch
  *   scarmapper/INDEL_Processing.py:57-80,759-795 window_mapping/cutsite_search -> scar_ctx_create (tables), scar_cutsite_search
  *
  * Conventions: every function returns 0 on success or a negative SCAR_ERR_* code;
@@ -199,6 +200,20 @@ int scar_process_fastq_host(scar_ctx *ctx, const uint8_t *text, int64_t n_bytes,
 /* After scar_process_fastq_host(records = NULL): copy the records of that call to the host once their number
  * is known. */
 int scar_fastq_records_fetch(scar_ctx *ctx, scar_record *records, int64_t n_records);
+
+/* ScarSearch.homeology_search (scarmapper/INDEL_Processing.py:550-657) and templated_insertion_search (:659-700)
+ * for a batch of scar patterns on the device (host buffers), one thread per key.  Key i: consensus_i, its
+ * junctions clj_i / crj_i, insertion_i, the target junctions tlj_i / trj_i as frequency_output passes them (i.e.
+ * already swapped for 3'-strand guides) and target_idx_i into `targets` (the sequence homeology_search is given:
+ * the target region, reverse-complemented for 3'-strand guides) and `regions` (self.target_region as stored,
+ * which templated_insertion_search slices).  out[i] = 16 int32 (struct ScarHomeology in
+ * scarmapper_b200/csrc/scar_homeology_core.h): left and right homeology {distance 0/1 or -1, position, query
+ * start/length in the consensus, segment start/length in the target} and the start of the left / right 5-nt
+ * template in the region (-1 = none; searched when the insertion has at least 5 nt). */
+int scar_homeology_batch(int32_t device, const scar_ragged *consensus, const scar_ragged *insertion,
+                         const int32_t *clj, const int32_t *crj, const int32_t *tlj, const int32_t *trj,
+                         const int32_t *target_idx, const scar_ragged *targets, const scar_ragged *regions,
+                         int32_t n_targets, int64_t n, int32_t *out);
 
 /* Sequence_Magic.match_maker over a batch on the device (host buffers): out[i] = lev(q_i,u_i) - (|u_i|-|q_i|). */
 int scar_match_maker_batch(int32_t device, const scar_ragged *query, const scar_ragged *unknown,

@@ -1085,3 +1085,59 @@ extern "C" int scar_match_maker_batch(int32_t device, const scar_ragged *query, 
     cleanup();
     return rc;
 }
+
+// ---- homeology / templated-insertion searches over a batch of scar patterns -------------------------
+namespace {
+struct StagedList {                 // one host ragged list copied to the device
+    uint8_t *bytes = nullptr; size_t cap = 0; int64_t *off = nullptr; int32_t *len = nullptr; scar_ragged dev{};
+    ~StagedList() { cudaFree(bytes); cudaFree(off); cudaFree(len); }
+    int stage(const scar_ragged &H, int64_t n)
+    {
+        int64_t h2d = 0;
+        if (cudaMalloc((void **)&off, (size_t)(n + 1) * sizeof(int64_t)) != cudaSuccess ||
+            cudaMalloc((void **)&len, (size_t)std::max<int64_t>(n, 1) * sizeof(int32_t)) != cudaSuccess)
+            return fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
+        return stage_ragged(H, 0, n, &bytes, &cap, &off, &len, 0, nullptr, &dev, &h2d);
+    }
+};
+struct DevInts {
+    int32_t *p = nullptr;
+    ~DevInts() { cudaFree(p); }
+    int upload(const int32_t *h, int64_t n)
+    {
+        if (cudaMalloc((void **)&p, (size_t)std::max<int64_t>(n, 1) * sizeof(int32_t)) != cudaSuccess)
+            return fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
+        CU(cudaMemcpy(p, h, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        return SCAR_OK;
+    }
+};
+}   // namespace
+
+extern "C" int scar_homeology_batch(int32_t device, const scar_ragged *consensus, const scar_ragged *insertion,
+                                    const int32_t *clj, const int32_t *crj, const int32_t *tlj, const int32_t *trj,
+                                    const int32_t *target_idx, const scar_ragged *targets, const scar_ragged *regions,
+                                    int32_t n_targets, int64_t n, int32_t *out)
+{
+    if (!consensus || !insertion || !clj || !crj || !tlj || !trj || !target_idx || !targets || !regions || !out || n < 0 ||
+        n_targets < 0)
+        return fail(SCAR_ERR_INVALID, "bad argument");
+    if (n == 0) return SCAR_OK;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SCAR_ERR_CUDA, "CUDA device %d not present", device);
+    CU(cudaSetDevice(device));
+    StagedList dc, di, dt, dr;
+    DevInts a, b, c, d, e;
+    int rc;
+    if ((rc = dc.stage(*consensus, n)) || (rc = di.stage(*insertion, n)) || (rc = dt.stage(*targets, n_targets)) ||
+        (rc = dr.stage(*regions, n_targets)) || (rc = a.upload(clj, n)) || (rc = b.upload(crj, n)) ||
+        (rc = c.upload(tlj, n)) || (rc = d.upload(trj, n)) || (rc = e.upload(target_idx, n)))
+        return rc;
+    int32_t *dout = nullptr;
+    if (cudaMalloc((void **)&dout, (size_t)n * 16 * sizeof(int32_t)) != cudaSuccess) return fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
+    cudaError_t err = scar_launch_homeology(dc.dev, di.dev, dt.dev, dr.dev, a.p, b.p, c.p, d.p, e.p, n_targets, n, dout, nullptr);
+    if (err == cudaSuccess) err = cudaMemcpy(out, dout, (size_t)n * 16 * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaFree(dout);
+    if (err != cudaSuccess) return fail(SCAR_ERR_CUDA, "homeology kernel failed: %s", cudaGetErrorString(err));
+    return SCAR_OK;
+}

@@ -171,6 +171,10 @@ cudaError_t scar_launch_export(const ScarTableSlot *slots, uint64_t capacity, sc
 cudaError_t scar_launch_merge(const K4Params &P, const scar_entry *in, uint64_t n_in, int sm_count, cudaStream_t stream);
 cudaError_t scar_launch_export_parts(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint32_t n_parts,
                                      uint64_t region, int32_t *status, int sm_count, cudaStream_t stream);
+cudaError_t scar_launch_homeology(const scar_ragged &cons, const scar_ragged &ins, const scar_ragged &targets,
+                                  const scar_ragged &regions, const int32_t *clj, const int32_t *crj, const int32_t *tlj,
+                                  const int32_t *trj, const int32_t *target_idx, int32_t n_targets, int64_t n, void *out,
+                                  cudaStream_t stream);
 #define SCAR_MAX_PEERS 32
 cudaError_t scar_launch_export_p2p(const ScarTableSlot *slots, uint64_t capacity, scar_entry *const *peer_base,
                                    uint32_t n_parts, uint32_t my_rank, uint64_t region, unsigned long long *cursors,

@@ -30,6 +30,8 @@ from . import fastq
 from .engine import ScarEngine, ScarProblem, cutsite_search
 
 _ENGINE_FACTORY = [None]      # tests substitute a CPU stand-in here; None -> ScarEngine
+_HOMEOLOGY_BATCH = [None]     # likewise for the per-pattern searches; None -> engine.homeology_batch (GPU)
+PATTERN_SEARCH_STATS = {"served": 0, "missed": 0}   # calls answered from the batch / handed to the reference's method
 
 
 def _make_engine(prob: ScarProblem, device: int):
@@ -49,6 +51,7 @@ class SampleResult:
         self.counters = None          # int64[SCAR_N_COUNTERS]
         self.table = []               # [(count, sub_list of the first read)] in first-seen order
         self.read_results = None      # every SCAR read's sub_list (OutputRawData only)
+        self.device = 0               # CUDA device the sample's GPU work runs on
 
     def __len__(self):
         return self.n_reads
@@ -173,6 +176,7 @@ def batched_consensus_demultiplex(self, module, device=0):
         iid = sample_ids[s]
         t = prob.sample_target[s]
         res = SampleResult(iid, int(counters[s, N.CT_ASSIGNED]))
+        res.device = device
         res.target_region, res.cutsite, res.counters = targets[t], cutsites[t], counters[s].copy()
 
         def sub(r):
@@ -235,10 +239,77 @@ def batched_data_processing(self):
         key = "{}|{}|{}|{}|{}".format(sub_list[0], sub_list[1], sub_list[2], sub_list[3], sub_list[9])
         results_freq_dict[key] = [count, sub_list]
     self.log.info("Finished Processing {}".format(self.index_name))
+    batched_pattern_searches(self, results_freq_dict, getattr(res, "device", 0))
     self.frequency_output(self.index_name, results_freq_dict, junction_type_data)
     if self.args.OutputRawData:
         self.raw_data_output(self.index_name, res.read_results or [])
     return self.summary_data
+
+
+def batched_pattern_searches(self, results_freq_dict, device: int = 0):
+    """The two per-pattern searches frequency_output runs in its Python loop - homeology_search and
+    templated_insertion_search (scarmapper/INDEL_Processing.py:550-700) - for EVERY pattern of the sample in
+    one batched GPU call (scar_homeology_batch), served to the unchanged frequency_output through instance
+    attributes of the same names.  The arguments are derived per key exactly as frequency_output derives them
+    (:299-328, incl. the swaps for 3'-strand guides); a call whose arguments are not in the batch simply runs
+    the reference's own method, so correctness never rests on this derivation."""
+    from .Sequence_Magic import rcomp
+    from . import engine as _engine
+    n = len(results_freq_dict)
+    if n == 0:
+        return
+    target_name = self.index_dict[self.index_name][7]
+    rc = self.target_dict[target_name][5] == "YES"
+    region = self.target_region
+    oriented = rcomp(region) if rc else region
+    keys, cons, inss, clj, crj, tlj, trj = [], [], [], [], [], [], []
+    for _count, sub in results_freq_dict.values():
+        insertion, consensus = sub[2], sub[4]
+        a, b, c, d = sub[5], sub[6], sub[7], sub[8]
+        if rc:
+            insertion, consensus = rcomp(insertion), rcomp(consensus)
+            a, b = len(consensus) - sub[6], len(consensus) - sub[5]
+            c, d = len(region) - sub[8], len(region) - sub[7]
+        keys.append((consensus, a, b, insertion, c, d))
+        cons.append(consensus); inss.append(insertion)
+        clj.append(a); crj.append(b); tlj.append(c); trj.append(d)
+    batch = _HOMEOLOGY_BATCH[0] or _engine.homeology_batch
+    out = batch(cons, inss, clj, crj, tlj, trj, np.zeros(n, dtype=np.int32), [oriented], [region], device)
+    hom, tmpl = {}, {}
+    for key, o in zip(keys, out.tolist()):
+        consensus, _a, _b, insertion, c, d = key
+        left = ["", "", "", ""] if o[0] < 0 else (o[0], o[1], consensus[o[2]:o[2] + o[3]], oriented[o[4]:o[4] + o[5]])
+        right = ["", "", "", ""] if o[6] < 0 else (o[6], o[7], consensus[o[8]:o[8] + o[9]], oriented[o[10]:o[10] + o[11]])
+        hom[key] = (left, right)
+        if len(insertion) >= 5:
+            lt = "" if o[12] < 0 else region[o[12]:o[12] + 5]
+            rt = "" if o[13] < 0 else region[o[13]:o[13] + 5]
+            tmpl[(insertion, c, d)] = (rcomp(lt), rcomp(rt)) if rc else (lt, rt)
+    cls = type(self)
+    misses = [0]
+
+    def homeology_search(consensus, consensus_lft_junction, consensus_rt_junction, target_sequence, insertion,
+                         ref_lft_junction, ref_rt_junction):
+        got = hom.get((consensus, consensus_lft_junction, consensus_rt_junction, insertion, ref_lft_junction,
+                       ref_rt_junction)) if target_sequence == oriented else None
+        PATTERN_SEARCH_STATS["served" if got is not None else "missed"] += 1
+        if got is None:
+            misses[0] += 1
+            return cls.homeology_search(self, consensus, consensus_lft_junction, consensus_rt_junction, target_sequence,
+                                        insertion, ref_lft_junction, ref_rt_junction)
+        return got
+
+    def templated_insertion_search(insertion, lft_target_junction, rt_target_junction, name):
+        got = tmpl.get((insertion, lft_target_junction, rt_target_junction)) if name == target_name else None
+        PATTERN_SEARCH_STATS["served" if got is not None else "missed"] += 1
+        if got is None:
+            misses[0] += 1
+            return cls.templated_insertion_search(self, insertion, lft_target_junction, rt_target_junction, name)
+        return got
+
+    self.homeology_search = homeology_search
+    self.templated_insertion_search = templated_insertion_search
+    self.pattern_search_misses = misses
 
 
 def install(module, device: int = 0):

@@ -377,6 +377,21 @@ class ScarEngine:
         return out[:got.value]
 
 
+def homeology_batch(consensus, insertions, clj, crj, tlj, trj, target_idx, targets, regions, device: int = 0) -> np.ndarray:
+    """ScarSearch.homeology_search + templated_insertion_search (scarmapper/INDEL_Processing.py:550-700) for a
+    batch of scar patterns on the GPU: [n, 16] int32 (struct ScarHomeology, include/scar_b200.h)."""
+    c, i, t, r = as_ragged(consensus), as_ragged(insertions), as_ragged(targets), as_ragged(regions)
+    n = c.n
+    assert i.n == n and t.n == r.n
+    ints = [np.ascontiguousarray(v, dtype=np.int32) for v in (clj, crj, tlj, trj, target_idx)]
+    assert all(v.size == n for v in ints)
+    out = np.zeros((n, 16), dtype=np.int32)
+    cs, is_, ts, rs = c.c_struct(), i.c_struct(), t.c_struct(), r.c_struct()
+    N.check(N.lib().scar_homeology_batch(device, C.byref(cs), C.byref(is_), *[v.ctypes.data for v in ints],
+                                         C.byref(ts), C.byref(rs), t.n, n, out.ctypes.data))
+    return out
+
+
 def match_maker_batch(queries, unknowns, device: int = 0) -> np.ndarray:
     """Sequence_Magic.match_maker over a batch on the GPU (Valkyries/Sequence_Magic.py:123-136)."""
     q, u = as_ragged(queries), as_ragged(unknowns)

@@ -3,6 +3,8 @@ Test double with ScarEngine's result interface, computed by the CPU oracle.  Let
 (scarmapper_b200/dropin.py: unpacking GPU results into the reference's objects and files) be tested in
 the build container, where the reference is present but no GPU is.  Lives in tests/ only.
 """
+import os
+
 import numpy as np
 
 from oracle import scar_oracle as orc
@@ -46,3 +48,44 @@ class OracleEngine:
 
     def close(self):
         pass
+
+
+_HOM_LIB = [None]
+
+
+def host_homeology_batch(consensus, insertions, clj, crj, tlj, trj, target_idx, targets, regions, device=0):
+    """CPU stand-in for engine.homeology_batch: the same header (scar_homeology_core.h) compiled for the host."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+    import numpy as np
+    if _HOM_LIB[0] is None:
+        d = tempfile.mkdtemp(prefix="scar_hom_")
+        src = os.path.join(d, "h.cpp")
+        csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scarmapper_b200", "csrc")
+        open(src, "w").write(r"""
+#include "scar_homeology_core.h"
+extern "C" void hom_eval(const uint8_t *cons, int n_cons, int clj, int crj, const uint8_t *target, int n_target,
+                         const uint8_t *ins, int n_ins, const uint8_t *region, int n_region, int tlj, int trj, int32_t *out)
+{
+    ScarHomeology h;
+    hom_homeology(cons, n_cons, clj, crj, target, n_target, n_ins, tlj, trj, h);
+    h.lt_start = h.rt_start = -1;
+    if (n_ins >= 5) hom_templates(ins, n_ins, region, n_region, tlj, trj, h);
+    h.pad0 = h.pad1 = 0;
+    const int32_t *p = reinterpret_cast<const int32_t *>(&h);
+    for (int i = 0; i < 16; ++i) out[i] = p[i];
+}
+""")
+        so = os.path.join(d, "h.so")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", csrc, src, "-o", so])
+        _HOM_LIB[0] = C.CDLL(so)
+    lib = _HOM_LIB[0]
+    out = np.zeros((len(consensus), 16), dtype=np.int32)
+    row = (C.c_int32 * 16)()
+    for i, (c, s) in enumerate(zip(consensus, insertions)):
+        t, r = targets[int(target_idx[i])].encode(), regions[int(target_idx[i])].encode()
+        lib.hom_eval(c.encode(), len(c), int(clj[i]), int(crj[i]), t, len(t), s.encode(), len(s), r, len(r),
+                     int(tlj[i]), int(trj[i]), row)
+        out[i] = list(row)
+    return out

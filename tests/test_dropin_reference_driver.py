@@ -26,7 +26,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gol
 @pytest.mark.parametrize("name", ["c1_single_target", "c3_12_targets_mh", "ragged_hr_donor", "truseq", "ramsden"])
 def test_reference_driver_with_dropin_writes_identical_files(name):
     import make_golden
-    from oracle_engine import OracleEngine
+    from oracle_engine import OracleEngine, host_homeology_batch
     blob = gu.load(name)
     case, golden = blob["case"], blob["golden"]
     ref_shims.install()
@@ -47,6 +47,7 @@ def test_reference_driver_with_dropin_writes_identical_files(name):
             Search_KMER=10, FigureType="pdf", IndelProcessing=True)
         log = Tool_Box.Logger(args)
         dropin._ENGINE_FACTORY[0] = OracleEngine
+        dropin._HOMEOLOGY_BATCH[0] = host_homeology_batch
         dropin.install(INDEL_Processing)
 
         class _Fastq:
@@ -55,7 +56,11 @@ def test_reference_driver_with_dropin_writes_identical_files(name):
         manifest = Tool_Box.FileParser.indices(log, args.SampleManifest)
         dp = INDEL_Processing.DataProcessing(log, args, "run-start", "golden",
                                              TargetMapper.TargetMapper(log, args, manifest), _Fastq(), None)
+        dropin.PATTERN_SEARCH_STATS.update(served=0, missed=0)
         dp.main_loop()
+        # every homeology / templated-insertion search of frequency_output was answered from the batch
+        assert dropin.PATTERN_SEARCH_STATS["missed"] == 0, dropin.PATTERN_SEARCH_STATS
+        assert dropin.PATTERN_SEARCH_STATS["served"] > 0
         assert dp.read_count == golden["read_count"]
         assert dict(dp.read_count_dict) == golden["read_count_dict"]
         assert {k: dict(v) for k, v in dp.phase_count.items()} == golden["phase_count"]
@@ -69,6 +74,7 @@ def test_reference_driver_with_dropin_writes_identical_files(name):
         assert seen == len(golden["files"]) and seen >= 2
     finally:
         dropin._ENGINE_FACTORY[0] = None
+        dropin._HOMEOLOGY_BATCH[0] = None
         INDEL_Processing.DataProcessing.consensus_demultiplex, INDEL_Processing.ScarSearch.data_processing = saved
         shutil.rmtree(wd, ignore_errors=True)
 
@@ -77,7 +83,7 @@ def test_launcher_runs_the_reference_pipeline_from_an_options_file(tmp_path):
     """scarmapper_b200.launcher.main with a real tab-delimited options file (docs/run_ScarMapper_IndelProcessing.sh
     format), the reference tree, and the oracle-backed engine: the files written equal the golden files."""
     import make_golden
-    from oracle_engine import OracleEngine
+    from oracle_engine import OracleEngine, host_homeology_batch
     blob = gu.load("c2_96_samples")
     case, golden = blob["case"], blob["golden"]
     ref_shims.install()
@@ -100,6 +106,7 @@ def test_launcher_runs_the_reference_pipeline_from_an_options_file(tmp_path):
             f.write("--{}\t{}\n".format(k, v))
     try:
         dropin._ENGINE_FACTORY[0] = OracleEngine
+        dropin._HOMEOLOGY_BATCH[0] = host_homeology_batch
         launcher.main(["--options_file", wd + "run.sh", "--reference", ref_shims.REFERENCE])
         seen = 0
         for fn, want in golden["files"].items():
@@ -112,4 +119,5 @@ def test_launcher_runs_the_reference_pipeline_from_an_options_file(tmp_path):
         assert seen == len(golden["files"]) == 97
     finally:
         dropin._ENGINE_FACTORY[0] = None
+        dropin._HOMEOLOGY_BATCH[0] = None
         INDEL_Processing.DataProcessing.consensus_demultiplex, INDEL_Processing.ScarSearch.data_processing = saved

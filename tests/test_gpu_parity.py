@@ -741,3 +741,45 @@ def test_context_info_config3_stays_in_shared_memory():
     eng = engine_for(gu.problem_inputs(blob["case"]), 300)
     assert eng.info()["anchor_targets"] == 0          # a 10-mer repeat forces the exhaustive scan
     eng.close()
+
+
+@pytest.mark.gpu
+def test_homeology_batch_kernel_equals_the_host_build_of_the_same_header():
+    """scar_homeology_batch (one thread per scar pattern) against scar_homeology_core.h compiled for the host,
+    which tests/test_homeology_host.py pins to the reference's homeology_search / templated_insertion_search.
+    Includes junctions at the string ends (Python slice wrap-around), empty strings, non-ACGT insertions and
+    two targets with separate oriented / stored sequences."""
+    import random
+    from oracle_engine import host_homeology_batch
+    from scarmapper_b200 import Sequence_Magic
+    from scarmapper_b200.engine import homeology_batch
+    rng = random.Random(23)
+    regions = ["".join(rng.choice("ACGT") for _ in range(L)) for L in (472, 97)]
+    targets = [regions[0], Sequence_Magic.rcomp(regions[1])]
+    cons, inss, clj, crj, tlj, trj, tix = [], [], [], [], [], [], []
+    for case in range(20000):
+        t = case % 2
+        L = len(regions[t])
+        cut = rng.randint(5, L - 5)
+        dl, dr = rng.randint(0, min(30, cut)), rng.randint(0, min(30, L - cut))
+        ins = "".join(rng.choice("ACGT" if case % 6 else "ACGTNacgr") for _ in range(rng.choice([0, 0, 1, 3, 5, 8, 20])))
+        if len(ins) >= 5 and rng.random() < 0.5:
+            a = rng.randint(max(0, cut - 45), max(0, cut - 6))
+            ins = regions[t][a:a + len(ins)]
+            if rng.random() < 0.5:
+                ins = Sequence_Magic.rcomp(ins)
+        lf = targets[t][max(0, cut - dl - rng.randint(0, 60)):cut - dl]
+        rf = targets[t][cut + dr:cut + dr + rng.randint(0, 60)]
+        c = lf + ins + rf
+        a, b, x, y = len(lf), len(lf) + len(ins), cut - dl, cut + dr
+        if case % 9 == 0:
+            a, b = rng.randint(0, len(c)), rng.randint(0, len(c))
+            x = rng.randint(0, L)
+            y = rng.randint(x, L)
+        cons.append(c); inss.append(ins); clj.append(a); crj.append(b); tlj.append(x); trj.append(y); tix.append(t)
+    got = homeology_batch(cons, inss, clj, crj, tlj, trj, tix, targets, regions)
+    want = host_homeology_batch(cons, inss, clj, crj, tlj, trj, tix, targets, regions)
+    assert got.shape == want.shape == (20000, 16)
+    assert np.array_equal(got, want)
+    assert (want[:, 0] >= 0).sum() > 2000 and (want[:, 12] >= 0).sum() > 200      # the searches really find things
+    assert homeology_batch([], [], [], [], [], [], [], targets, regions).shape == (0, 16)
