@@ -781,5 +781,5 @@ def test_homeology_batch_kernel_equals_the_host_build_of_the_same_header():
     want = host_homeology_batch(cons, inss, clj, crj, tlj, trj, tix, targets, regions)
     assert got.shape == want.shape == (20000, 16)
     assert np.array_equal(got, want)
-    assert (want[:, 0] >= 0).sum() > 2000 and (want[:, 12] >= 0).sum() > 200      # the searches really find things
+    assert (want[:, 0] >= 0).sum() > 1000 and (want[:, 12] >= 0).sum() > 200      # the searches really find things
     assert homeology_batch([], [], [], [], [], [], [], targets, regions).shape == (0, 16)
