@@ -434,6 +434,29 @@ def main():
                      "path": "ScarEngine.process_fastq_text -> scar_process_fastq_host (uncompressed FASTQ text, pinned; "
                              "records indexed on the GPU)"}
         del p_txt, tn, flat
+    # SURVEY 8f F1 (outside the metric): the per-pattern homeology / templated-insertion searches of
+    # frequency_output as one batched kernel, timed through the host-buffer C ABI on synthetic patterns
+    pattern_searches = None
+    if world == 1 and not args.kernels_only:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "profiles"))
+            import homeology_bench as hb
+            from scarmapper_b200.engine import homeology_batch
+            nk = 200_000
+            region, pc, pi, a4, b4, c4, d4 = hb.patterns(nk)
+            tix = np.zeros(nk, dtype=np.int32)
+            homeology_batch(pc[:1000], pi[:1000], a4[:1000], b4[:1000], c4[:1000], d4[:1000], tix[:1000], [region], [region])
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                homeology_batch(pc, pi, a4, b4, c4, d4, tix, [region], [region])
+                dt = time.perf_counter() - t0
+                best = dt if best is None or dt < best else best
+            pattern_searches = {"value": nk / best, "unit": "scar patterns/s", "patterns": nk, "best_of": 3,
+                                "path": "engine.homeology_batch -> scar_homeology_batch (host buffers; Python string "
+                                        "packing, H2D, kernel, D2H)"}
+        except Exception as exc:   # diagnostic only: never lose the bench line over it
+            pattern_searches = {"error": str(exc)[:200]}
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
@@ -493,6 +516,8 @@ def main():
         }
         if fastq_e2e:
             line["e2e_fastq_text"] = fastq_e2e
+        if pattern_searches:
+            line["pattern_searches"] = pattern_searches
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
