@@ -97,3 +97,59 @@ def test_searches_match_the_reference_methods(lib):
             n_tmpl += 1
             n_found += bool(want_lt or want_rt)
     assert n_hom > 500 and n_tmpl > 500 and n_found > 50       # the generator really exercises the searches
+
+
+def test_dropin_serves_batch_results_and_falls_back_to_the_reference_method():
+    """dropin.batched_pattern_searches: calls with the arguments frequency_output derives are answered from the
+    batch (identical to the reference's methods, 5' and 3' guides); any other call runs the reference's method."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_engine import host_homeology_batch
+    ref_shims.install()
+    from scarmapper import INDEL_Processing
+    from Valkyries import Sequence_Magic
+    from scarmapper_b200 import dropin
+    rng = random.Random(5)
+    region = "".join(rng.choice("ACGT") for _ in range(300))
+    cut = 150
+    for rc in (False, True):
+        class Search(INDEL_Processing.ScarSearch):
+            def __init__(self):                      # none of the reference's constructor work is needed here
+                self.index_name = "s1"
+                self.index_dict = {"s1": [None] * 7 + ["t"]}
+                self.target_dict = {"t": [None] * 5 + ["YES" if rc else "NO"]}
+                self.target_region = region
+        me = Search()
+        table = {}
+        for k in range(300):
+            dl, dr = rng.randint(0, 25), rng.randint(0, 25)
+            ins = "".join(rng.choice("ACGT") for _ in range(rng.choice([0, 0, 2, 5, 9])))
+            if len(ins) >= 5 and k % 2:
+                ins = region[cut - 30:cut - 30 + len(ins)]
+            lf, rf = region[cut - dl - 40:cut - dl], region[cut + dr:cut + dr + 40]
+            sub = ["x" * dl, "y" * dr, ins, "", lf + ins + rf, len(lf), len(lf) + len(ins), cut - dl, cut + dr, ""]
+            table["k%d" % k] = [1, sub]
+        dropin._HOMEOLOGY_BATCH[0] = host_homeology_batch
+        dropin.PATTERN_SEARCH_STATS.update(served=0, missed=0)
+        try:
+            dropin.batched_pattern_searches(me, table)
+        finally:
+            dropin._HOMEOLOGY_BATCH[0] = None
+        oriented = Sequence_Magic.rcomp(region) if rc else region
+        for _count, sub in table.values():           # the derivation of frequency_output (:299-328)
+            ins, cons, a, b, c, d = sub[2], sub[4], sub[5], sub[6], sub[7], sub[8]
+            if rc:
+                ins, cons = Sequence_Magic.rcomp(ins), Sequence_Magic.rcomp(cons)
+                a, b = len(cons) - sub[6], len(cons) - sub[5]
+                c, d = len(region) - sub[8], len(region) - sub[7]
+            want = INDEL_Processing.ScarSearch.homeology_search(me, cons, a, b, oriented, ins, c, d)
+            got = me.homeology_search(cons, a, b, oriented, ins, c, d)
+            assert [list(x) for x in want] == [list(x) for x in got]
+            if len(ins) >= 5:
+                assert INDEL_Processing.ScarSearch.templated_insertion_search(me, ins, c, d, "t") == \
+                    me.templated_insertion_search(ins, c, d, "t")
+        assert dropin.PATTERN_SEARCH_STATS["missed"] == 0 and dropin.PATTERN_SEARCH_STATS["served"] >= 300
+        # arguments that are not in the batch: the reference's own method answers
+        want = INDEL_Processing.ScarSearch.homeology_search(me, region[100:180], 40, 40, oriented, "", 140, 160)
+        assert [list(x) for x in me.homeology_search(region[100:180], 40, 40, oriented, "", 140, 160)] == [list(x) for x in want]
+        assert dropin.PATTERN_SEARCH_STATS["missed"] == 1
