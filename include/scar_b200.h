@@ -10,6 +10,7 @@
  *   scarmapper/INDEL_Processing.py:1126-1201 index_matching                 -> scar_demux_dev
  *   Valkyries/Sequence_Magic.py:123-136     match_maker(query, unknown)     -> scar_match_maker_batch
  *   scarmapper/INDEL_Processing.py:550-700  homeology_search / templated_insertion_search -> scar_homeology_batch
+ *   scarmapper/INDEL_Processing.py:702-757  raw_data_output (body)         -> scar_raw_rows_host
  *   scarmapper/INDEL_Processing.py:57-80,759-795 window_mapping/cutsite_search -> scar_ctx_create (tables), scar_cutsite_search
  *
  * Conventions: every function returns 0 on success or a negative SCAR_ERR_* code;
@@ -200,6 +201,14 @@ int scar_process_fastq_host(scar_ctx *ctx, const uint8_t *text, int64_t n_bytes,
 /* After scar_process_fastq_host(records = NULL): copy the records of that call to the host once their number
  * is known. */
 int scar_fastq_records_fetch(scar_ctx *ctx, scar_record *records, int64_t n_records);
+
+/* The body of ScarSearch.raw_data_output (scarmapper/INDEL_Processing.py:702-757), host side: one text line per
+ * scarred read of `sample` (records[r].status == SCAR_ST_SCAR), in read order, built from the records and the raw
+ * reads (host buffers; `platform` selects the stored-sequence transform), with the swaps and reverse complements
+ * of 3'-strand guides (reverse_comp != 0).  Call with out = NULL to get the size, then with a buffer. */
+int scar_raw_rows_host(const scar_record *records, const scar_ragged *reads, int64_t n, int32_t sample,
+                       int32_t platform, const uint8_t *target_region, int32_t target_len, int32_t cutsite,
+                       int32_t reverse_comp, uint8_t *out, int64_t out_capacity, int64_t *out_bytes);
 
 /* ScarSearch.homeology_search (scarmapper/INDEL_Processing.py:550-657) and templated_insertion_search (:659-700)
  * for a batch of scar patterns on the device (host buffers), one thread per key.  Key i: consensus_i, its

@@ -105,6 +105,8 @@ PROTOTYPES = {
                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "scar_process_fastq_host": (C.c_int, [_P, _P, C.c_int64, C.c_uint64, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "scar_fastq_records_fetch": (C.c_int, [_P, _P, C.c_int64]),
+    "scar_raw_rows_host": (C.c_int, [_P, _RP, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,
+                                     C.POINTER(C.c_int64)]),
     "scar_homeology_batch": (C.c_int, [C.c_int32, _RP, _RP, _P, _P, _P, _P, _P, _RP, _RP, C.c_int32, C.c_int64, _P]),
     "scar_match_maker_batch": (C.c_int, [C.c_int32, _RP, _RP, C.c_int64, _P]),
 }

@@ -1,0 +1,93 @@
+// scar_rawdata.cu — the body of ScarSearch.raw_data_output (reference scarmapper/INDEL_Processing.py:702-757)
+// written natively from the per-read records: one line per scarred read of a sample,
+//   left deletions, right deletions, deletion size, microhomology, insertion, insertion size,
+//   consensus left / right junction, reference left / right junction, consensus, target region
+// with the swaps and reverse complements the reference applies for 3'-strand guides (:733-746) and its
+// "skip unaltered reads" rule (:748-750).  Host code (formatting and file output are the host's job);
+// the reference builds the same text by Python string concatenation over a per-read list of lists.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "scar_internal.cuh"
+
+int scar_fail(int code, const char *fmt, ...);
+
+namespace {
+// Sequence_Magic.rcomp's translate table (Valkyries/Sequence_Magic.py:97-118); unmapped bytes pass
+inline uint8_t comp(uint8_t c)
+{
+    switch (c) {
+    case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+    case 'M': return 'K'; case 'R': return 'Y'; case 'Y': return 'R'; case 'K': return 'M';
+    case 'V': return 'B'; case 'H': return 'D'; case 'D': return 'H'; case 'B': return 'V';
+    case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+    case 'm': return 'k'; case 'r': return 'y'; case 'y': return 'r'; case 'k': return 'm';
+    case 'v': return 'b'; case 'h': return 'd'; case 'd': return 'h'; case 'b': return 'v';
+    default: return c;
+    }
+}
+
+struct Sink {                       // counts, and writes when there is a buffer
+    uint8_t *out; int64_t cap, n;
+    void put(const uint8_t *p, int64_t len) { if (out && n + len <= cap) memcpy(out + n, p, (size_t)len); n += len; }
+    void put(char c) { if (out && n + 1 <= cap) out[n] = (uint8_t)c; ++n; }
+    void num(long long v) { char b[24]; const int k = snprintf(b, sizeof b, "%lld", v); put((const uint8_t *)b, k); }
+    // s[a:b) forward, or its reverse complement
+    void seq(const std::string &s, int a, int b, bool rc)
+    {
+        if (b <= a) return;
+        if (!rc) { put((const uint8_t *)s.data() + a, b - a); return; }
+        for (int k = b - 1; k >= a; --k) put((char)comp((uint8_t)s[(size_t)k]));
+    }
+};
+}   // namespace
+
+extern "C" int scar_raw_rows_host(const scar_record *records, const scar_ragged *reads, int64_t n, int32_t sample,
+                                  int32_t platform, const uint8_t *target_region, int32_t target_len, int32_t cutsite,
+                                  int32_t reverse_comp, uint8_t *out, int64_t out_capacity, int64_t *out_bytes)
+{
+    if (!records || !reads || !target_region || !out_bytes || n < 0 || target_len < 0)
+        return scar_fail(SCAR_ERR_INVALID, "bad argument");
+    Sink S{out, out ? out_capacity : 0, 0};
+    const std::string region((const char *)target_region, (size_t)target_len);
+    const bool rc = reverse_comp != 0;
+    std::string stored;
+    for (int64_t r = 0; r < n; ++r) {
+        const scar_record &R = records[r];
+        if (R.status != SCAR_ST_SCAR || (int32_t)R.sample != sample) continue;
+        const uint8_t *raw; int rawlen;
+        get_item(*reads, r, raw, rawlen);
+        // the sequence ScarSearch is handed (INDEL_Processing.py:946,978,981)
+        if (platform == SCAR_PLATFORM_TRUSEQ) stored.assign((const char *)raw + (rawlen > 6 ? 6 : rawlen), (size_t)(rawlen > 12 ? rawlen - 12 : 0));
+        else if (platform == SCAR_PLATFORM_RAMSDEN) {
+            stored.resize((size_t)rawlen);
+            for (int k = 0; k < rawlen; ++k) stored[(size_t)k] = (char)comp(raw[rawlen - 1 - k]);
+        } else stored.assign((const char *)raw, (size_t)rawlen);
+        const int len = (int)stored.size();
+        const int clj = R.clj, crj = R.crj, tlj = R.tlj, trj = R.trj;
+        const int ldel = cutsite > tlj ? cutsite - tlj : 0;                       // len(target[tlj:cutsite])
+        const int rdel = (trj < target_len ? trj : target_len) > cutsite ? (trj < target_len ? trj : target_len) - cutsite : 0;
+        int ia = 0, ib = 0, ma = 0, mb = 0;                                         // insertion / microhomology slices
+        if (R.flags & SCAR_FL_INSERTION) { ia = clj < len ? clj : len; ib = crj < len ? crj : len; if (ib < ia) ib = ia; }
+        if (R.flags & SCAR_FL_MICROHOM) { ma = crj < len ? crj : len; mb = clj < len ? clj : len; if (mb < ma) mb = ma; }
+        const int ins_size = ib - ia, mh_size = mb - ma;
+        const int del_size = ldel + rdel + mh_size;
+        if (del_size == 0 && ins_size == 0) continue;                               // skip unaltered reads (:748-750)
+        S.num(rc ? rdel : ldel); S.put('\t');
+        S.num(rc ? ldel : rdel); S.put('\t');
+        S.num(del_size); S.put('\t');
+        S.seq(stored, ma, mb, rc); S.put('\t');
+        S.seq(stored, ia, ib, rc); S.put('\t');
+        S.num(ins_size); S.put('\t');
+        S.num(rc ? len - crj : clj); S.put('\t');
+        S.num(rc ? len - clj : crj); S.put('\t');
+        S.num(rc ? target_len - trj : tlj); S.put('\t');
+        S.num(rc ? target_len - tlj : trj); S.put('\t');
+        S.seq(stored, 0, len, rc); S.put('\t');
+        S.seq(region, 0, target_len, rc); S.put('\n');
+    }
+    *out_bytes = S.n;
+    if (out && S.n > out_capacity) return scar_fail(SCAR_ERR_INVALID, "raw rows: %lld bytes needed", (long long)S.n);
+    return SCAR_OK;
+}

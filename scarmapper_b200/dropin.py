@@ -50,8 +50,20 @@ class SampleResult:
         self.cutsite = None
         self.counters = None          # int64[SCAR_N_COUNTERS]
         self.table = []               # [(count, sub_list of the first read)] in first-seen order
-        self.read_results = None      # every SCAR read's sub_list (OutputRawData only)
+        self._read_results = None     # every SCAR read's sub_list (OutputRawData only), built on first use
+        self._read_results_fn = None
+        self.raw_source = None        # what the native Raw_Data writer needs (records, reads, sample, ...)
         self.device = 0               # CUDA device the sample's GPU work runs on
+
+    @property
+    def read_results(self):
+        if self._read_results is None and self._read_results_fn is not None:
+            self._read_results = self._read_results_fn()
+        return self._read_results
+
+    @read_results.setter
+    def read_results(self, value):
+        self._read_results = value
 
     def __len__(self):
         return self.n_reads
@@ -179,11 +191,15 @@ def batched_consensus_demultiplex(self, module, device=0):
         res.device = device
         res.target_region, res.cutsite, res.counters = targets[t], cutsites[t], counters[s].copy()
 
-        def sub(r):
+        def sub(r, t=t):
             return record_to_sublist(records[r], stored_sequence(args.Platform, batch.seq.item(r)), targets[t], cutsites[t])
         res.table = [(count, sub(first)) for count, first in by_sample.get(s, [])]
         if args.OutputRawData:
-            res.read_results = [sub(r) for r in scar_reads.get(s, [])]
+            # the per-read list of lists the reference's raw_data_output consumes is only built if somebody asks
+            # for it; the Raw_Data file itself is written natively from the records (native_raw_data_output)
+            res._read_results_fn = (lambda rows=scar_reads.get(s, []), sub=sub: [sub(r) for r in rows])
+            res.raw_source = dict(records=records, reads=batch.seq, sample=s, platform=args.Platform,
+                                  region=targets[t], cutsite=cutsites[t])
         self.sequence_dict[iid] = res
 
         # phase_count (:948-975)
@@ -242,8 +258,32 @@ def batched_data_processing(self):
     batched_pattern_searches(self, results_freq_dict, getattr(res, "device", 0))
     self.frequency_output(self.index_name, results_freq_dict, junction_type_data)
     if self.args.OutputRawData:
-        self.raw_data_output(self.index_name, res.read_results or [])
+        if res.raw_source is not None:
+            native_raw_data_output(self, self.index_name, res)
+        else:
+            self.raw_data_output(self.index_name, res.read_results or [])
     return self.summary_data
+
+
+RAW_DATA_COLUMNS = ("Left Deletions\tRight Deletions\tDeletion Size\tMicrohomology\tInsertion\tInsertion Size\t"
+                    "Consensus Left Junction\tConsensus Right Junction\tRef Left Junction\tRef Right Junction\t"
+                    "Consensus\tTarget Region\n")
+
+
+def native_raw_data_output(self, index_name, res):
+    """ScarSearch.raw_data_output (scarmapper/INDEL_Processing.py:702-757) without the per-read Python lists:
+    same file name, the reference's own page header, and the rows written by scar_raw_rows_host straight from the
+    records (one line per scarred read, swaps and reverse complements for 3'-strand guides, unaltered reads
+    skipped)."""
+    from . import engine as _engine
+    src = res.raw_source
+    target_name = self.index_dict[index_name][7]
+    body = _engine.raw_rows(src["records"], src["reads"], src["sample"], src["platform"], src["region"], src["cutsite"],
+                            self.target_dict[target_name][5] == "YES")
+    path = "{}{}_{}_ScarMapper_Raw_Data.txt".format(self.args.WorkingFolder, self.args.Job_Name, index_name)
+    with open(path, "wb") as f:
+        f.write("{}{}".format(self.common_page_header(index_name), RAW_DATA_COLUMNS).encode())
+        f.write(body)
 
 
 def batched_pattern_searches(self, results_freq_dict, device: int = 0):

@@ -377,6 +377,24 @@ class ScarEngine:
         return out[:got.value]
 
 
+def raw_rows(records, reads, sample: int, platform, target_region: str, cutsite: int, reverse_comp: bool) -> bytes:
+    """The body of ScarSearch.raw_data_output (scarmapper/INDEL_Processing.py:702-757) for one sample, built
+    natively from the per-read records and the raw reads (host buffers)."""
+    r = as_ragged(reads)
+    rec = np.ascontiguousarray(records)
+    assert rec.dtype == N.RECORD_DTYPE and rec.shape[0] == r.n
+    plat = N.PLATFORMS[platform] if isinstance(platform, str) else int(platform)
+    reg = target_region.encode("latin-1")
+    rs = r.c_struct()
+    need = C.c_int64(0)
+    N.check(N.lib().scar_raw_rows_host(rec.ctypes.data, C.byref(rs), r.n, int(sample), plat, reg, len(reg), int(cutsite),
+                                       1 if reverse_comp else 0, None, 0, C.byref(need)))
+    buf = np.empty(max(need.value, 1), dtype=np.uint8)
+    N.check(N.lib().scar_raw_rows_host(rec.ctypes.data, C.byref(rs), r.n, int(sample), plat, reg, len(reg), int(cutsite),
+                                       1 if reverse_comp else 0, buf.ctypes.data, need.value, C.byref(need)))
+    return buf[:need.value].tobytes()
+
+
 def homeology_batch(consensus, insertions, clj, crj, tlj, trj, target_idx, targets, regions, device: int = 0) -> np.ndarray:
     """ScarSearch.homeology_search + templated_insertion_search (scarmapper/INDEL_Processing.py:550-700) for a
     batch of scar patterns on the GPU: [n, 16] int32 (struct ScarHomeology, include/scar_b200.h)."""

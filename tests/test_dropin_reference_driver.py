@@ -57,7 +57,16 @@ def test_reference_driver_with_dropin_writes_identical_files(name):
         dp = INDEL_Processing.DataProcessing(log, args, "run-start", "golden",
                                              TargetMapper.TargetMapper(log, args, manifest), _Fastq(), None)
         dropin.PATTERN_SEARCH_STATS.update(served=0, missed=0)
-        dp.main_loop()
+        written, native_writer = {}, dropin.native_raw_data_output
+
+        def recording_writer(search, index_name, res):       # main_loop drops sequence_dict; keep what was written
+            written[index_name] = (res, dict(search.index_dict), dict(search.target_dict))
+            return native_writer(search, index_name, res)
+        dropin.native_raw_data_output = recording_writer
+        try:
+            dp.main_loop()
+        finally:
+            dropin.native_raw_data_output = native_writer
         # every homeology / templated-insertion search of frequency_output was answered from the batch
         assert dropin.PATTERN_SEARCH_STATS["missed"] == 0, dropin.PATTERN_SEARCH_STATS
         assert dropin.PATTERN_SEARCH_STATS["served"] > 0
@@ -72,6 +81,23 @@ def test_reference_driver_with_dropin_writes_identical_files(name):
             assert got == want, fn
             seen += 1
         assert seen == len(golden["files"]) and seen >= 2
+        # Raw_Data files: written natively from the records (scar_raw_rows_host); the rows must equal what the
+        # reference's own raw_data_output writes from the per-read lists
+        import types
+        ref_dir = tempfile.mkdtemp(prefix="scar_raw_ref_") + "/"
+        checked = 0
+        for iid, (res, index_dict, target_dict) in written.items():
+            stub = types.SimpleNamespace(args=argparse.Namespace(WorkingFolder=ref_dir, Job_Name="golden"),
+                                         target_region=res.target_region, index_dict=index_dict,
+                                         target_dict=target_dict, common_page_header=lambda idx: "")
+            INDEL_Processing.ScarSearch.raw_data_output(stub, iid, res.read_results or [])
+            fn = "golden_{}_ScarMapper_Raw_Data.txt".format(iid)
+            want_rows = open(ref_dir + fn).read().split(dropin.RAW_DATA_COLUMNS, 1)[1]
+            got_rows = open(wd + fn).read().split(dropin.RAW_DATA_COLUMNS, 1)[1]
+            assert got_rows == want_rows, iid
+            checked += bool(want_rows)
+        shutil.rmtree(ref_dir, ignore_errors=True)
+        assert checked >= 1 and len(written) == len(golden["samples"])
     finally:
         dropin._ENGINE_FACTORY[0] = None
         dropin._HOMEOLOGY_BATCH[0] = None
