@@ -433,6 +433,28 @@ def main():
                      "d2h_bytes_per_step": int(n * 16), "steps": 3,
                      "path": "ScarEngine.process_fastq_text -> scar_process_fastq_host (uncompressed FASTQ text, pinned; "
                              "records indexed on the GPU)"}
+        # and from GZIP-compressed FASTQ (what a sequencer delivers): the host inflates (zlib, one stream, one
+        # core - the floor of any gz path), the GPU does the rest; 1 M reads, bounded so the bench stays short
+        try:
+            import zlib
+            n_gz = min(n, 1_000_000)
+            gz_text = flat[:n_gz * rec_bytes]
+            co = zlib.compressobj(1, zlib.DEFLATED, 31)
+            gz = co.compress(gz_text.tobytes()) + co.flush()
+            eng.reset_async()
+            t0 = time.perf_counter()
+            raw = np.frombuffer(zlib.decompress(gz, 31), dtype=np.uint8)
+            t_inflate = time.perf_counter() - t0
+            got_gz = eng.process_fastq_text(raw, first_index=first, out=rec_out)
+            gz_s = time.perf_counter() - t0
+            if len(got_gz) != n_gz or got_gz[:chk].tobytes() != want.tobytes():
+                raise RuntimeError("gz path disagrees with the oracle")
+            fastq_e2e["from_gzip"] = {"value": n_gz / gz_s, "unit": "reads/s", "reads": int(n_gz), "gz_bytes": len(gz),
+                                      "inflate_s": t_inflate, "total_s": gz_s,
+                                      "path": "zlib.decompress on the host (single stream) -> process_fastq_text"}
+            del raw, gz, gz_text
+        except Exception as exc:   # diagnostic only
+            fastq_e2e["from_gzip"] = {"error": str(exc)[:200]}
         del p_txt, tn, flat
     # SURVEY 8f F1 (outside the metric): the per-pattern homeology / templated-insertion searches of
     # frequency_output as one batched kernel, timed through the host-buffer C ABI on synthetic patterns
