@@ -47,8 +47,10 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=120_000, help="reads of the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=60_000, help="reads of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-reads", type=int, default=1_000_000, help="reads of the launcher-only pipeline run")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1/C3/C4/C5-shape lines")
     ap.add_argument("--kernels-only", action="store_true",
                     help="tuning runs: skip the end-to-end arms (the line then carries e2e.value = null)")
     ap.add_argument("--seed", type=int, default=20260101)
@@ -142,28 +144,94 @@ def run_cpu_reference(cfg, n_sample, cores=None, repeats=1, warm=0):
     return runs, cores_used, cr.baseline_kind()
 
 
+def pipeline_available():
+    from oracle import ref_shims
+    return ref_shims.available()
+
+
+def run_pipeline(mode, wd, config, reads, seed, spawn, repeat=1, device=0, timeout=1500):
+    """baseline/run_pipeline.py in a fresh process: the whole IndelProcessing pipeline (gzip FASTQ -> output files),
+    mode 'reference' = the UNMODIFIED reference driver (DataProcessing.main_loop), 'dropin' = the same driver started
+    by scarmapper_b200.launcher with the CUDA hot path.  Returns one dict per repeat."""
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_pipeline.py"), "--mode", mode, "--workdir", wd,
+           "--config", config, "--reads", str(reads), "--seed", str(seed), "--spawn", str(spawn), "--repeat", str(repeat),
+           "--device", str(device), "--quiet"]
+    t0 = time.perf_counter()
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    wall = time.perf_counter() - t0
+    lines = [json.loads(ln[len("PIPELINE "):]) for ln in proc.stdout.splitlines() if ln.startswith("PIPELINE ")]
+    if proc.returncode != 0 or len(lines) != repeat:
+        raise RuntimeError("run_pipeline {} failed ({}): {}".format(mode, proc.returncode, proc.stderr[-1500:]))
+    for ln in lines:
+        ln["process_s"] = wall
+    return lines
+
+
+def compare_pipeline_outputs(wd):
+    """Frequency / SNV_Frequency / Summary files of out_reference and out_dropin, wall-clock lines excluded."""
+    skip = ("# Run Start", "# Run End", "Start:", "End:", "FASTQ1:", "FASTQ2:")
+    a, b = os.path.join(wd, "out_reference"), os.path.join(wd, "out_dropin")
+    keep = lambda d: sorted(f for f in os.listdir(d) if f.endswith(("_Frequency.txt", "_Summary.txt")))
+    fa, fb = keep(a), keep(b)
+    same = 0
+    for fn in fa:
+        if fn not in fb:
+            continue
+        x = [ln for ln in open(os.path.join(a, fn)).read().split("\n") if not ln.startswith(skip)]
+        y = [ln for ln in open(os.path.join(b, fn)).read().split("\n") if not ln.startswith(skip)]
+        same += x == y
+    return {"reference_files": len(fa), "dropin_files": len(fb), "identical": same,
+            "all_identical": same == len(fa) == len(fb) and same > 0}
+
+
+def reference_spawn(cfg):
+    return max(1, min(cfg.n_samples, (os.cpu_count() or 2) - 1))   # one library per process, Spawn <= CPUs - 1
+
+
 def reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores - the UNMODIFIED
+    DataProcessing.main_loop() (scarmapper/INDEL_Processing.py:1038-1061: serial consensus_demultiplex, then one
+    pathos process per sample library with the compiled SlidingWindow.pyx, then data_output) on a bounded gzip-FASTQ
+    sample of the workload; restated driver loops (oracle/cpu_reference.py) only where no reference tree is present."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import tempfile
     import synth  # noqa: F401
     cfg, _ = build_case(args, 0, 1)
-    # size each step so that the whole run ends within a few minutes: calibrate on a small sample
-    cal, cores, kind = run_cpu_reference(cfg, 12_000)
-    rate = cal[0]["n_reads"] / cal[0]["total_s"]
-    budget = min(20.0, 150.0 / max(1, args.steps + args.warmup))
-    n_sample = int(max(10_000, min(200_000, rate * budget)))
-    runs, cores, kind = run_cpu_reference(cfg, n_sample, repeats=args.steps, warm=args.warmup)
-    total = sum(r["total_s"] for r in runs)
-    value = n_sample * len(runs) / total
-    demux = n_sample * len(runs) / sum(r["demux_s"] for r in runs)
-    search = n_sample * len(runs) / sum(r["search_s"] for r in runs)
-    sample = ("{} reads of the workload per step; stage 1 serial in the main process ({:.0f} reads/s), stages 2-4 "
-              "one process per sample on {} workers ({:.0f} reads/s); {}").format(
-        n_sample, demux, cores, search,
-        "compiled reference SlidingWindow.pyx (oracle/_ref) inside the restated driver loops" if kind == "reference"
-        else "oracle C port (oracle/_ref absent)")
+    n_runs = args.steps + args.warmup
+    if pipeline_available():
+        spawn = reference_spawn(cfg)
+        wd = tempfile.mkdtemp(prefix="scar_ref_arm_")
+        try:
+            cal = run_pipeline("reference", os.path.join(wd, "cal"), "C2", 8000, args.seed, spawn)[0]
+            rate = cal["reads"] / cal["total_s"]
+            budget = min(25.0, 170.0 / max(1, n_runs))
+            n_sample = int(max(8000, min(300_000, rate * budget)) // 1000 * 1000)
+            runs = run_pipeline("reference", os.path.join(wd, "run"), "C2", n_sample, args.seed, spawn, repeat=n_runs)
+        finally:
+            import shutil
+            shutil.rmtree(wd, ignore_errors=True)
+        runs = runs[args.warmup:]
+        total = sum(r["total_s"] for r in runs)
+        value = n_sample * len(runs) / total
+        demux = n_sample * len(runs) / sum(r["demux_s"] for r in runs)
+        search = n_sample * len(runs) / sum(r["search_s"] for r in runs)
+        cores, kind = spawn, "reference"
+        sample = ("{} reads of the workload (gzip FASTQ) per step through the UNMODIFIED DataProcessing.main_loop(): "
+                  "consensus_demultiplex serial in the main process ({:.0f} reads/s), then Pool({}).starmap(ScarSearch) "
+                  "with the compiled reference SlidingWindow.pyx + frequency_output + data_output ({:.0f} reads/s); "
+                  "python-Levenshtein / pathos / natsort / pysam stand-ins from baseline/shims").format(
+                      n_sample, demux, spawn, search)
+    else:
+        cal, cores, kind = run_cpu_reference(cfg, 12_000)
+        rate = cal[0]["n_reads"] / cal[0]["total_s"]
+        budget = min(20.0, 150.0 / max(1, n_runs))
+        n_sample = int(max(10_000, min(200_000, rate * budget)))
+        runs, cores, kind = run_cpu_reference(cfg, n_sample, repeats=args.steps, warm=args.warmup)
+        total = sum(r["total_s"] for r in runs)
+        value = n_sample * len(runs) / total
+        sample = "{} reads per step, restated driver loops (no reference tree on this box), {} workers".format(n_sample, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(runs),
@@ -174,6 +242,75 @@ def reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def measure_config(name, n, seed, device, steps=5, chk=4000):
+    """One BASELINE.json config on one GPU: parity of the first `chk` reads against the oracle, then the resident-batch
+    step (reset, K2, K1, K3, K4 from raw bytes in HBM) timed with CUDA events."""
+    import numpy as np
+    import torch
+    import synth
+    from oracle import scar_oracle as orc
+    from scarmapper_b200.engine import HostRagged, ScarEngine, ScarProblem
+    cfg = synth.make_config(name, n_reads=n, seed=seed)
+    pin = dict(targets=cfg.targets, cutsites=cfg.cutsites, sample_target=cfg.sample_target,
+               left_index=cfg.index_d5, right_index=cfg.index_d7, platform="Illumina",
+               phasing=cfg.phasing_lists(), n_limit=cfg.n_limit, min_length=cfg.min_length)
+    log2 = 22
+    while (1 << log2) < n // 2:
+        log2 += 1
+    eng = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=1 << log2, **pin), device=device)
+    try:
+        batch = cfg.generate(0, n)
+        sub = {k: (v[:chk] if v is not None else None) for k, v in batch.items()}
+        want = orc.classify_batch(orc.Problem(**pin), cfg.reads_as_strings(sub), *cfg.fields_as_strings(sub))
+        got = eng.process_host(HostRagged.from_matrix(batch["seq"][:chk], lengths=batch["len"][:chk]), batch["f0"][:chk], batch["f1"][:chk])
+        parity = got.tobytes() == want.tobytes()
+        eng.reset()
+        res = eng.make_resident(HostRagged.from_matrix(batch["seq"], lengths=batch["len"]), HostRagged.from_matrix(batch["f0"]),
+                                HostRagged.from_matrix(batch["f1"]))
+        stream = torch.cuda.current_stream()
+
+        def ev():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            return e
+        for _ in range(2):
+            eng.reset_async()
+            eng.run_resident(res, first_index=0)
+        torch.cuda.synchronize()
+        marks = []
+        t0 = ev()
+        for _ in range(steps):
+            eng.reset_async()
+            m = [ev()]
+            eng.demux_resident(res); m.append(ev())
+            eng.pack_resident(res); m.append(ev())
+            eng.classify_resident(res); m.append(ev())
+            eng.aggregate_resident(res, first_index=0); m.append(ev())
+            marks.append(m)
+        t1 = ev()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / steps
+        st = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / steps for i in range(4)]
+        n_entries = eng.table_size()
+        cnt, un = eng.counters()
+        info = eng.info()
+        algo = cfg.read_len + 16 + 16
+        peak, _ = measured_peak()
+        return {"workload": "{}: {} reads x {} nt, {} samples, {} targets".format(name, n, cfg.read_len, cfg.n_samples, len(cfg.targets)),
+                "parity_first_{}_reads_vs_oracle".format(chk): bool(parity),
+                "value": n / (ms * 1e-3), "unit": "reads/s", "ms_per_step": ms, "steps": steps,
+                "read_bases_per_s": n * cfg.read_len / (ms * 1e-3),
+                "timed_region": "reset, K2 demux, K1 pack, K3, K4 from raw read bytes resident in HBM",
+                "stages_ms": {"k2_demux": st[0], "k1_pack": st[1], "k3_window": st[2], "k4_aggregate": st[3]},
+                "algorithmic_bytes_per_read": algo, "hbm_frac_of_step": algo * n / (ms * 1e-3) / 1e9 / peak,
+                "cells_per_read": eng.cells_per_read, "k3_cells_staged_in_smem": bool(info.get("k3_stage", False)),
+                "k3_ctas_per_sm": info.get("k3_ctas_per_sm"), "tables_in_smem": info["tables_in_smem"],
+                "static_blob_bytes": info["static_bytes"], "scar_patterns": int(n_entries), "unassigned_reads": int(un),
+                "scar_reads": int(cnt[:, 12].sum())}
+    finally:
+        eng.close()
 
 
 def main():
@@ -204,14 +341,30 @@ def main():
     # the CPU baseline runs first (rank 0, N=1 only), before this process touches the GPU
     cpu_baseline = None
     cfg, pin = build_case(args, rank, world)
+    pipeline, pipe_wd = None, None
     if world == 1 and not args.no_cpu_baseline:
-        runs, cores, kind = run_cpu_reference(cfg, args.cpu_sample)
-        r = runs[0]
-        cpu_baseline = {
-            "value": r["n_reads"] / r["total_s"], "unit": "reads/s", "cores": cores, "kind": kind,
-            "sample": "first {} reads of the workload: stage 1 serial {:.1f} s, stages 2-4 on {} processes {:.1f} s"
-                      .format(r["n_reads"], r["demux_s"], cores, r["search_s"]),
-        }
+        if pipeline_available():
+            import tempfile
+            pipe_wd = tempfile.mkdtemp(prefix="scar_pipeline_")
+            spawn = reference_spawn(cfg)
+            r = run_pipeline("reference", pipe_wd, "C2", args.cpu_sample, args.seed, spawn)[0]
+            cpu_baseline = {
+                "value": r["reads"] / r["total_s"], "unit": "reads/s", "cores": spawn, "kind": "reference",
+                "sample": "first {} reads of the workload as gzip FASTQ through the UNMODIFIED DataProcessing.main_loop(): "
+                          "consensus_demultiplex (serial) {:.1f} s, Pool({}).starmap(ScarSearch) + data_output {:.1f} s"
+                          .format(r["reads"], r["demux_s"], spawn, r["search_s"]),
+            }
+            pipeline = {"reads": r["reads"], "fastq": "gzip", "spawn": spawn, "reference_s": r["total_s"],
+                        "reference_demux_s": r["demux_s"], "reference_search_s": r["search_s"]}
+        else:
+            runs, cores, kind = run_cpu_reference(cfg, args.cpu_sample)
+            r = runs[0]
+            cpu_baseline = {
+                "value": r["n_reads"] / r["total_s"], "unit": "reads/s", "cores": cores, "kind": kind,
+                "sample": "first {} reads of the workload: stage 1 serial {:.1f} s, stages 2-4 on {} processes {:.1f} s "
+                          "(restated driver loops: no reference tree on this box)"
+                          .format(r["n_reads"], r["demux_s"], cores, r["search_s"]),
+            }
 
     n = args.reads
     first = rank * n
@@ -481,6 +634,42 @@ def main():
             pattern_searches = {"error": str(exc)[:200]}
     clocks = sampler.stop() if rank == 0 else None
 
+    # The whole pipeline a user runs (gzip FASTQ -> Frequency / Summary files): the reference's unmodified driver under
+    # scarmapper_b200.launcher with the CUDA hot path and a real forking pool, on the SAME files the reference arm
+    # above processed on this box's CPUs; the output files of the two runs are diffed.  Then the launcher alone on a
+    # larger file.  Wall times of launcher.main (context creation, inflate, GPU, pool, reporting all included).
+    if pipeline is not None and not args.kernels_only:
+        try:
+            d = run_pipeline("dropin", pipe_wd, "C2", args.cpu_sample, args.seed, pipeline["spawn"], device=local)[0]
+            pipeline.update(launcher_s=d["total_s"], launcher_stages_s=d["stages"], speedup=pipeline["reference_s"] / d["total_s"],
+                            outputs=compare_pipeline_outputs(pipe_wd),
+                            pattern_searches_served=d["pattern_searches"])
+            big = run_pipeline("dropin", os.path.join(pipe_wd, "big"), "C2", args.pipeline_reads, args.seed,
+                               pipeline["spawn"], device=local)[0]
+            pipeline["launcher_large"] = {"reads": args.pipeline_reads, "launcher_s": big["total_s"],
+                                          "reads_per_s": args.pipeline_reads / big["total_s"], "stages_s": big["stages"]}
+        except Exception as exc:   # diagnostic: never lose the bench line over it
+            pipeline["error"] = str(exc)[-600:]
+    if pipe_wd:
+        import shutil
+        shutil.rmtree(pipe_wd, ignore_errors=True)
+
+    # the other BASELINE.json configs (parity-checked against the oracle on a prefix, timed over resident batches)
+    configs = None
+    if world == 1 and not args.no_configs and not args.kernels_only:
+        for e in engines:
+            e.close()
+        engines = []
+        del res
+        torch.cuda.empty_cache()
+        configs = {}
+        for key, name, n_cfg in (("C1", "C1", 1_000_000), ("C3", "C3", 10_000_000), ("C4", "C4", 10_000_000),
+                                 ("C5shape", "C2", 25_000_000)):
+            try:
+                configs[key] = measure_config(name, n_cfg, args.seed, local, steps=max(3, min(args.steps, 5)))
+            except Exception as exc:
+                configs[key] = {"error": str(exc)[-400:]}
+
     if world > 1:
         t = torch.tensor([elapsed_ms, e2e_s, k3, raw_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -542,6 +731,10 @@ def main():
             line["pattern_searches"] = pattern_searches
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+        if pipeline:
+            line["pipeline"] = pipeline
+        if configs:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
     for e in engines:
         e.close()

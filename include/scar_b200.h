@@ -111,6 +111,10 @@ int scar_window_counts(const scar_ctx *ctx, int32_t target, int32_t *n_left, int
  * anchor-and-extend search (unique 10-mers) */
 int scar_ctx_info(const scar_ctx *ctx, int64_t *static_bytes, int32_t *tables_in_smem, int32_t *n_anchor_targets);
 
+/* how K3 is launched for this context: whether a tile's cells are staged in shared memory, resident CTAs per SM and
+ * dynamic shared memory per CTA (bench.py reports them per config) */
+int scar_k3_plan(const scar_ctx *ctx, int32_t *cells_staged, int32_t *ctas_per_sm, int32_t *smem_bytes);
+
 /* K1: raw bytes -> packed rows (2-bit codes + ACGT mask + N mask), applying the platform's stored-
  * sequence transform (Illumina as is, TruSeq seq[6:-6], Ramsden rcomp; INDEL_Processing.py:946,978,981). */
 int scar_pack_dev(scar_ctx *ctx, const scar_ragged *seq, int64_t n_reads,
@@ -209,6 +213,18 @@ int scar_fastq_records_fetch(scar_ctx *ctx, scar_record *records, int64_t n_reco
 int scar_raw_rows_host(const scar_record *records, const scar_ragged *reads, int64_t n, int32_t sample,
                        int32_t platform, const uint8_t *target_region, int32_t target_len, int32_t cutsite,
                        int32_t reverse_comp, uint8_t *out, int64_t out_capacity, int64_t *out_bytes);
+
+/* The same for a LIST of reads: rows[k] is a read index (the scarred reads of one sample, in read order).  A run with
+ * many samples buckets its reads once and pays O(reads of the sample) per Raw_Data file. */
+int scar_raw_rows_indexed_host(const scar_record *records, const scar_ragged *reads, const int64_t *rows, int64_t n_rows,
+                               int32_t platform, const uint8_t *target_region, int32_t target_len, int32_t cutsite,
+                               int32_t reverse_comp, uint8_t *out, int64_t out_capacity, int64_t *out_bytes);
+
+/* Stored sequences (what ScarSearch is handed per platform, scarmapper/INDEL_Processing.py:946,978,981) of a list of
+ * reads, gathered into one CSR buffer; row k is reverse-complemented when flip[k] != 0 (frequency_output works on
+ * rcomp(consensus) for 3'-strand guides, :312-327).  out_off receives n_rows + 1 offsets; out = NULL sizes only. */
+int scar_stored_gather_host(const scar_ragged *reads, const int64_t *rows, int64_t n_rows, int32_t platform,
+                            const uint8_t *flip, uint8_t *out, int64_t out_capacity, int64_t *out_off);
 
 /* ScarSearch.homeology_search (scarmapper/INDEL_Processing.py:550-657) and templated_insertion_search (:659-700)
  * for a batch of scar patterns on the device (host buffers), one thread per key.  Key i: consensus_i, its

@@ -65,6 +65,42 @@ def build(force: bool = False) -> str | None:
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+BASELINE_DIR = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "ScarMapper")
+
+
+def baseline_tree() -> str | None:
+    """baseline/_ref/ScarMapper when it holds the reference's driver modules, else None."""
+    return BASELINE_DIR if os.path.isfile(os.path.join(BASELINE_DIR, "scarmapper", "INDEL_Processing.py")) else None
+
+
+def build_baseline(force: bool = False) -> str | None:
+    """The reference is Python: its driver (DataProcessing.main_loop, INDEL_Processing.py:1038-1061) cannot be
+    compiled into a binary, and /root/reference does not exist on the GPU box.  So that the UNMODIFIED driver can
+    be run there - as the `--impl reference` arm of bench.py and under the drop-in in the GPU tests - its Python
+    modules are copied, byte for byte, into the git-ignored (but gpurun-shipped) baseline/_ref/ScarMapper/, together
+    with the compiled SlidingWindow module under the name `from scarmapper import SlidingWindow` resolves.
+    Nothing under baseline/_ref/ is committed; tests/test_baseline_tree.py checks the copy against the original."""
+    src = REFERENCE
+    if not os.path.isfile(os.path.join(src, "scarmapper", "INDEL_Processing.py")):
+        return baseline_tree()
+    for pkg in ("scarmapper", "Valkyries"):
+        dst = os.path.join(BASELINE_DIR, pkg)
+        os.makedirs(dst, exist_ok=True)
+        for fn in sorted(os.listdir(os.path.join(src, pkg))):
+            if not fn.endswith(".py") or fn == "setup.py":
+                continue
+            a, b = os.path.join(src, pkg, fn), os.path.join(dst, fn)
+            if force or not os.path.exists(b) or open(a, "rb").read() != open(b, "rb").read():
+                shutil.copyfile(a, b)
+                os.chmod(b, 0o644)
+    so = build()
+    if so:
+        dst = os.path.join(BASELINE_DIR, "scarmapper", os.path.basename(so))
+        if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(so):
+            shutil.copy2(so, dst)
+    return baseline_tree()
+
+
 def load():
     """Import the compiled reference module (oracle/_ref/SlidingWindow.*.so) or return None."""
     so = ref_so()
@@ -80,3 +116,4 @@ def load():
 if __name__ == "__main__":
     out = build(force="--force" in sys.argv)
     print(out or "reference tree not present and no prebuilt module")
+    print(build_baseline(force="--force" in sys.argv) or "no baseline tree")

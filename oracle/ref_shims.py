@@ -1,143 +1,79 @@
 """
-ref_shims.py — make the UNMODIFIED reference driver importable in this container.
+ref_shims.py — make the UNMODIFIED reference driver importable in this container and on the GPU box.
 
 The reference imports seven third-party packages that are absent here and cannot be installed
 (no network): Levenshtein, pysam, pyfaidx, pathos, natsort, magic, matplotlib.
-install() registers minimal stand-ins in sys.modules, puts /root/reference on sys.path and
-registers oracle/_ref/SlidingWindow.*.so (the reference's own compiled Cython) as
-scarmapper.SlidingWindow, so that `import scarmapper.INDEL_Processing` runs the reference code
-itself.  Used only by tests/golden/make_golden.py (fixture generation) and by tests that are
-skipped when /root/reference is absent.  TEST INFRASTRUCTURE ONLY.
+install() puts the stand-in packages of baseline/shims/ (documented in its README) and the reference tree on
+sys.path and registers oracle/_ref/SlidingWindow.*.so (the reference's own compiled Cython) as
+scarmapper.SlidingWindow, so that `import scarmapper.INDEL_Processing` runs the reference code itself.
+The reference tree is /root/reference in the build container and baseline/_ref/ScarMapper - a byte-for-byte,
+git-ignored copy made by oracle/build_ref.build_baseline - where /root/reference does not exist (GPU box).
+Used by tests/golden/make_golden.py (fixture generation), the tests that drive the reference, and bench.py's
+reference arm.  TEST / BENCH INFRASTRUCTURE ONLY.
 
-Stand-in semantics:
-  Levenshtein.distance  -> oracle C unit-cost distance (parity unpinned at this boundary)
-  natsort.natsorted     -> natural sort; for the (int, int) tuple keys and 'Phase F10'-style
-                           labels the reference sorts, numeric-aware tuple ordering
-  pathos.multiprocessing.Pool -> in-process serial starmap (same results, no pickling)
-  magic.from_file       -> gzip magic bytes -> 'application/gzip', else 'text/plain'
-  pysam.FastaFile.fetch -> plain FASTA reader raising KeyError on unknown contigs
-  pyfaidx.Fasta         -> first record
-  matplotlib            -> inert mocks (plots are not part of the parity surface)
+pathos.multiprocessing.Pool: install(real_pool=True) -> multiprocess.Pool, the class pathos itself re-exports
+(forked workers, dill pickling); install() -> an in-process serial pool (fixture generation, quick tests).
 """
 from __future__ import annotations
 
 import os
-import re
 import sys
-import types
-from unittest import mock
 
-REFERENCE = os.environ.get("SCARMAPPER_REFERENCE", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIMS = os.path.join(_ROOT, "baseline", "shims")
+BASELINE = os.path.join(_ROOT, "baseline", "_ref", "ScarMapper")   # byte-for-byte copy made by build_ref.build_baseline
+
+
+def _resolve() -> str:
+    """The reference tree: $SCARMAPPER_REFERENCE, else /root/reference (build container), else the git-ignored copy
+    that travels to the GPU box (baseline/_ref/ScarMapper)."""
+    for cand in (os.environ.get("SCARMAPPER_REFERENCE", ""), "/root/reference", BASELINE):
+        if cand and os.path.isfile(os.path.join(cand, "scarmapper", "INDEL_Processing.py")):
+            return cand
+    return os.environ.get("SCARMAPPER_REFERENCE", "/root/reference")
+
+
+REFERENCE = _resolve()
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE, "scarmapper"))
+    return os.path.isfile(os.path.join(REFERENCE, "scarmapper", "INDEL_Processing.py"))
 
 
-def _natural_key(x):
-    if isinstance(x, (tuple, list)):
-        return tuple(_natural_key(v) for v in x)
-    if isinstance(x, (int, float)):
-        return (0, x, "")
-    parts = re.split(r"(\d+)", str(x))
-    return tuple((0, int(p), "") if p.isdigit() else (1, 0, p) for p in parts)
+def baseline_available() -> bool:
+    return os.path.isfile(os.path.join(BASELINE, "scarmapper", "INDEL_Processing.py"))
 
 
-def _natsorted(seq, key=None, reverse=False, alg=None):
-    if key is None:
-        return sorted(seq, key=_natural_key, reverse=reverse)
-    return sorted(seq, key=lambda v: _natural_key(key(v)), reverse=reverse)
-
-
-def _read_fasta(path):
-    import gzip
-    opener = gzip.open if path.endswith((".gz", ".bgz")) else open
-    recs, name, chunks = [], None, []
-    with opener(path, "rt") as f:
-        for line in f:
-            line = line.rstrip("\n")
-            if line.startswith(">"):
-                if name is not None:
-                    recs.append((name, "".join(chunks)))
-                name, chunks = line[1:].split()[0], []
-            elif line:
-                chunks.append(line)
-    if name is not None:
-        recs.append((name, "".join(chunks)))
-    return recs
-
-
-def install():
+def install(real_pool: bool = False, reference: str | None = None):
+    """real_pool: pathos.multiprocessing.Pool is multiprocess.Pool (what pathos wraps: forked workers, dill
+    pickling) instead of the in-process serial stand-in.  reference: tree to import from (default REFERENCE)."""
+    global REFERENCE
+    if reference:
+        REFERENCE = reference
     if not available():
         raise RuntimeError("reference tree not present at " + REFERENCE)
-    from oracle import build_ref, scar_oracle
+    from oracle import build_ref
 
-    lev = types.ModuleType("Levenshtein")
-    lev.distance = lambda a, b: scar_oracle.levenshtein(a, b)
-    sys.modules["Levenshtein"] = lev
+    # the stand-in packages are real importable packages (baseline/shims/*, see its README), so forked and spawned
+    # workers resolve them like any installed package
+    if SHIMS not in sys.path:
+        sys.path.insert(0, SHIMS)
+    os.environ["SCAR_SHIM_SERIAL_POOL"] = "0" if real_pool else "1"
+    import Levenshtein
+    if not Levenshtein.compiled:
+        raise RuntimeError("baseline/shims/Levenshtein/_lev.so is not built (gcc missing?)")
 
-    ns = types.ModuleType("natsort")
-    ns.natsorted = _natsorted
-    ns_inner = types.ModuleType("natsort.natsort")
-    ns_inner.natsorted = _natsorted
-    ns.natsort = ns_inner
-    sys.modules["natsort"] = ns
-    sys.modules["natsort.natsort"] = ns_inner
-
-    class _SerialPool:
-        def __init__(self, *a, **k):
-            pass
-
-        def starmap(self, fn, it):
-            return [fn(*args) for args in it]
-
-        def map(self, fn, it):
-            return [fn(a) for a in it]
-
-    pathos = types.ModuleType("pathos")
-    pmp = types.ModuleType("pathos.multiprocessing")
-    pmp.Pool = _SerialPool
-    pathos.multiprocessing = pmp
-    sys.modules["pathos"] = pathos
-    sys.modules["pathos.multiprocessing"] = pmp
-
-    magic = types.ModuleType("magic")
-
-    def from_file(path, mime=True):
-        with open(path, "rb") as f:
-            return "application/gzip" if f.read(2) == b"\x1f\x8b" else "text/plain"
-    magic.from_file = from_file
-    sys.modules["magic"] = magic
-
-    pysam = types.ModuleType("pysam")
-
-    class FastaFile:
-        def __init__(self, path):
-            self._recs = dict(_read_fasta(path))
-
-        def fetch(self, chrom, start=None, stop=None):
-            if chrom not in self._recs:
-                raise KeyError(chrom)
-            return self._recs[chrom][start:stop]
-    pysam.FastaFile = FastaFile
-    pysam.depth = lambda *a, **k: []
-    sys.modules["pysam"] = pysam
-
-    pyfaidx = types.ModuleType("pyfaidx")
-
-    class Fasta:
-        def __init__(self, path):
-            self._recs = _read_fasta(path)
-
-        def __getitem__(self, i):
-            return self._recs[i][1]
-    pyfaidx.Fasta = Fasta
-    sys.modules["pyfaidx"] = pyfaidx
-
-    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.backends",
-                 "matplotlib.backends.backend_pdf"):
-        sys.modules[name] = mock.MagicMock()
-
+    # one reference tree at a time: a previous install() from another tree must not shadow this one
+    for other in ("/root/reference", BASELINE):
+        if other != REFERENCE and other in sys.path:
+            sys.path.remove(other)
+    for name in [m for m in sys.modules if m == "scarmapper" or m.startswith("scarmapper.") or m == "Valkyries"
+                 or m.startswith("Valkyries.")]:
+        mod = sys.modules[name]
+        f = getattr(mod, "__file__", None) or ""
+        if f and not os.path.abspath(f).startswith(os.path.abspath(REFERENCE) + os.sep) and "scarmapper_b200" not in f \
+                and os.sep + "oracle" + os.sep not in f:
+            del sys.modules[name]
     if REFERENCE not in sys.path:
         sys.path.insert(0, REFERENCE)
     build_ref.build()

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "scar_cells_per_read": (C.c_int, [_P]),
     "scar_ctx_info": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "scar_window_counts": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "scar_k3_plan": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "scar_pack_dev": (C.c_int, [_P, _RP, C.c_int64, _P, _P, _P]),
     "scar_demux_dev": (C.c_int, [_P, _RP, _RP, _RP, C.c_int64, _P, _P]),
     "scar_classify_dev": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P]),
@@ -107,6 +108,9 @@ PROTOTYPES = {
     "scar_fastq_records_fetch": (C.c_int, [_P, _P, C.c_int64]),
     "scar_raw_rows_host": (C.c_int, [_P, _RP, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,
                                      C.POINTER(C.c_int64)]),
+    "scar_raw_rows_indexed_host": (C.c_int, [_P, _RP, _P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,
+                                             C.POINTER(C.c_int64)]),
+    "scar_stored_gather_host": (C.c_int, [_RP, _P, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P]),
     "scar_homeology_batch": (C.c_int, [C.c_int32, _RP, _RP, _P, _P, _P, _P, _P, _RP, _RP, C.c_int32, C.c_int64, _P]),
     "scar_match_maker_batch": (C.c_int, [C.c_int32, _RP, _RP, C.c_int64, _P]),
 }

@@ -513,6 +513,7 @@ extern "C" int scar_reset_dev(scar_ctx *c, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaMemsetAsync(c->d_slots, 0, c->capacity * sizeof(ScarTableSlot), s));
     CU(cudaMemsetAsync(c->d_acc, 0, c->acc_words * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(c->d_status, 0, sizeof(int32_t), s));      // like scar_reset: a reset state carries no sticky error
     return SCAR_OK;
 }
 
@@ -564,17 +565,36 @@ extern "C" int scar_demux_dev(scar_ctx *c, const scar_ragged *seq, const scar_ra
     return SCAR_OK;
 }
 
+static K3Params k3_params(const scar_ctx *c)
+{
+    K3Params P; memset(&P, 0, sizeof(P));
+    P.sample_target = c->d_sample_target;
+    P.blob = c->d_blob; P.blob_bytes = c->blob_bytes; P.meta_off = c->meta_off; P.phase_off = c->phase_off;
+    P.nmax_off = c->nmax_off; P.W = c->W; P.n_samples = c->n_samples;
+    P.do_phasing = c->do_phasing; P.min_length = c->min_length; P.hr_code = c->hr_code; P.hr_len = c->hr_len;
+    return P;
+}
+
+extern "C" int scar_k3_plan(const scar_ctx *c, int32_t *cells_staged, int32_t *ctas_per_sm, int32_t *smem_bytes)
+{
+    if (!c) return fail(SCAR_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    int st = 0, per = 0, sm = 0;
+    CU(scar_window_plan(k3_params(c), c->smem_tables, &st, &per, &sm));
+    if (cells_staged) *cells_staged = st;
+    if (ctas_per_sm) *ctas_per_sm = per;
+    if (smem_bytes) *smem_bytes = sm;
+    return SCAR_OK;
+}
+
 extern "C" int scar_classify_dev(scar_ctx *c, const uint64_t *cells, const uint32_t *lens, const uint16_t *samples,
                                  int64_t n, scar_record *records, void *stream)
 {
     if (!c || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
     if (n == 0) return SCAR_OK;
     CU(cudaSetDevice(c->device));
-    K3Params P; memset(&P, 0, sizeof(P));
-    P.cells = cells; P.lens = lens; P.samples = samples; P.records = records; P.sample_target = c->d_sample_target;
-    P.blob = c->d_blob; P.blob_bytes = c->blob_bytes; P.meta_off = c->meta_off; P.phase_off = c->phase_off;
-    P.nmax_off = c->nmax_off; P.n_reads = n; P.stride = n; P.W = c->W; P.n_samples = c->n_samples;
-    P.do_phasing = c->do_phasing; P.min_length = c->min_length; P.hr_code = c->hr_code; P.hr_len = c->hr_len;
+    K3Params P = k3_params(c);
+    P.cells = cells; P.lens = lens; P.samples = samples; P.records = records; P.n_reads = n; P.stride = n;
     CU(scar_launch_window(P, c->smem_tables, c->sm_count, (cudaStream_t)stream, &c->launches));
     return SCAR_OK;
 }

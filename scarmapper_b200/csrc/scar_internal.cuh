@@ -159,6 +159,7 @@ struct K4VerifyParams {
 };
 
 cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count, cudaStream_t stream, int *launches);
+cudaError_t scar_window_plan(const K3Params &P, bool smem_tables, int *stage, int *per_sm, int *smem_bytes);
 cudaError_t scar_launch_pack(const scar_ragged &seq, int64_t n, int W, int platform, uint64_t *cells,
                              int64_t stride, uint32_t *lens, int32_t *status, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t scar_launch_demux(const K2Params &P, int sm_count, cudaStream_t stream, int *launches);

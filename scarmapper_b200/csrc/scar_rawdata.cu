@@ -43,6 +43,44 @@ struct Sink {                       // counts, and writes when there is a buffer
 };
 }   // namespace
 
+// the sequence ScarSearch is handed for a raw read (INDEL_Processing.py:946,978,981)
+static void stored_sequence(const uint8_t *raw, int rawlen, int32_t platform, std::string &stored)
+{
+    if (platform == SCAR_PLATFORM_TRUSEQ) stored.assign((const char *)raw + (rawlen > 6 ? 6 : rawlen), (size_t)(rawlen > 12 ? rawlen - 12 : 0));
+    else if (platform == SCAR_PLATFORM_RAMSDEN) {
+        stored.resize((size_t)rawlen);
+        for (int k = 0; k < rawlen; ++k) stored[(size_t)k] = (char)comp(raw[rawlen - 1 - k]);
+    } else stored.assign((const char *)raw, (size_t)rawlen);
+}
+
+// one Raw_Data line of a scarred read (nothing for an unaltered read, :748-750)
+static void raw_row(Sink &S, const scar_record &R, const std::string &stored, const std::string &region, int32_t target_len,
+                    int32_t cutsite, bool rc)
+{
+    const int len = (int)stored.size();
+    const int clj = R.clj, crj = R.crj, tlj = R.tlj, trj = R.trj;
+    const int ldel = cutsite > tlj ? cutsite - tlj : 0;                       // len(target[tlj:cutsite])
+    const int rdel = (trj < target_len ? trj : target_len) > cutsite ? (trj < target_len ? trj : target_len) - cutsite : 0;
+    int ia = 0, ib = 0, ma = 0, mb = 0;                                         // insertion / microhomology slices
+    if (R.flags & SCAR_FL_INSERTION) { ia = clj < len ? clj : len; ib = crj < len ? crj : len; if (ib < ia) ib = ia; }
+    if (R.flags & SCAR_FL_MICROHOM) { ma = crj < len ? crj : len; mb = clj < len ? clj : len; if (mb < ma) mb = ma; }
+    const int ins_size = ib - ia, mh_size = mb - ma;
+    const int del_size = ldel + rdel + mh_size;
+    if (del_size == 0 && ins_size == 0) return;                                 // skip unaltered reads (:748-750)
+    S.num(rc ? rdel : ldel); S.put('\t');
+    S.num(rc ? ldel : rdel); S.put('\t');
+    S.num(del_size); S.put('\t');
+    S.seq(stored, ma, mb, rc); S.put('\t');
+    S.seq(stored, ia, ib, rc); S.put('\t');
+    S.num(ins_size); S.put('\t');
+    S.num(rc ? len - crj : clj); S.put('\t');
+    S.num(rc ? len - clj : crj); S.put('\t');
+    S.num(rc ? target_len - trj : tlj); S.put('\t');
+    S.num(rc ? target_len - tlj : trj); S.put('\t');
+    S.seq(stored, 0, len, rc); S.put('\t');
+    S.seq(region, 0, target_len, rc); S.put('\n');
+}
+
 extern "C" int scar_raw_rows_host(const scar_record *records, const scar_ragged *reads, int64_t n, int32_t sample,
                                   int32_t platform, const uint8_t *target_region, int32_t target_len, int32_t cutsite,
                                   int32_t reverse_comp, uint8_t *out, int64_t out_capacity, int64_t *out_bytes)
@@ -51,43 +89,68 @@ extern "C" int scar_raw_rows_host(const scar_record *records, const scar_ragged 
         return scar_fail(SCAR_ERR_INVALID, "bad argument");
     Sink S{out, out ? out_capacity : 0, 0};
     const std::string region((const char *)target_region, (size_t)target_len);
-    const bool rc = reverse_comp != 0;
     std::string stored;
     for (int64_t r = 0; r < n; ++r) {
         const scar_record &R = records[r];
         if (R.status != SCAR_ST_SCAR || (int32_t)R.sample != sample) continue;
         const uint8_t *raw; int rawlen;
         get_item(*reads, r, raw, rawlen);
-        // the sequence ScarSearch is handed (INDEL_Processing.py:946,978,981)
-        if (platform == SCAR_PLATFORM_TRUSEQ) stored.assign((const char *)raw + (rawlen > 6 ? 6 : rawlen), (size_t)(rawlen > 12 ? rawlen - 12 : 0));
-        else if (platform == SCAR_PLATFORM_RAMSDEN) {
-            stored.resize((size_t)rawlen);
-            for (int k = 0; k < rawlen; ++k) stored[(size_t)k] = (char)comp(raw[rawlen - 1 - k]);
-        } else stored.assign((const char *)raw, (size_t)rawlen);
-        const int len = (int)stored.size();
-        const int clj = R.clj, crj = R.crj, tlj = R.tlj, trj = R.trj;
-        const int ldel = cutsite > tlj ? cutsite - tlj : 0;                       // len(target[tlj:cutsite])
-        const int rdel = (trj < target_len ? trj : target_len) > cutsite ? (trj < target_len ? trj : target_len) - cutsite : 0;
-        int ia = 0, ib = 0, ma = 0, mb = 0;                                         // insertion / microhomology slices
-        if (R.flags & SCAR_FL_INSERTION) { ia = clj < len ? clj : len; ib = crj < len ? crj : len; if (ib < ia) ib = ia; }
-        if (R.flags & SCAR_FL_MICROHOM) { ma = crj < len ? crj : len; mb = clj < len ? clj : len; if (mb < ma) mb = ma; }
-        const int ins_size = ib - ia, mh_size = mb - ma;
-        const int del_size = ldel + rdel + mh_size;
-        if (del_size == 0 && ins_size == 0) continue;                               // skip unaltered reads (:748-750)
-        S.num(rc ? rdel : ldel); S.put('\t');
-        S.num(rc ? ldel : rdel); S.put('\t');
-        S.num(del_size); S.put('\t');
-        S.seq(stored, ma, mb, rc); S.put('\t');
-        S.seq(stored, ia, ib, rc); S.put('\t');
-        S.num(ins_size); S.put('\t');
-        S.num(rc ? len - crj : clj); S.put('\t');
-        S.num(rc ? len - clj : crj); S.put('\t');
-        S.num(rc ? target_len - trj : tlj); S.put('\t');
-        S.num(rc ? target_len - tlj : trj); S.put('\t');
-        S.seq(stored, 0, len, rc); S.put('\t');
-        S.seq(region, 0, target_len, rc); S.put('\n');
+        stored_sequence(raw, rawlen, platform, stored);
+        raw_row(S, R, stored, region, target_len, cutsite, reverse_comp != 0);
     }
     *out_bytes = S.n;
     if (out && S.n > out_capacity) return scar_fail(SCAR_ERR_INVALID, "raw rows: %lld bytes needed", (long long)S.n);
+    return SCAR_OK;
+}
+
+// The same for a LIST of reads (rows[k] = read index, the scarred reads of one sample in read order): a run with
+// many samples buckets the reads once and pays O(reads of the sample) per file instead of a scan of the whole run.
+extern "C" int scar_raw_rows_indexed_host(const scar_record *records, const scar_ragged *reads, const int64_t *rows,
+                                          int64_t n_rows, int32_t platform, const uint8_t *target_region,
+                                          int32_t target_len, int32_t cutsite, int32_t reverse_comp, uint8_t *out,
+                                          int64_t out_capacity, int64_t *out_bytes)
+{
+    if (!records || !reads || (!rows && n_rows) || !target_region || !out_bytes || n_rows < 0 || target_len < 0)
+        return scar_fail(SCAR_ERR_INVALID, "bad argument");
+    Sink S{out, out ? out_capacity : 0, 0};
+    const std::string region((const char *)target_region, (size_t)target_len);
+    std::string stored;
+    for (int64_t k = 0; k < n_rows; ++k) {
+        const int64_t r = rows[k];
+        const scar_record &R = records[r];
+        if (R.status != SCAR_ST_SCAR) continue;
+        const uint8_t *raw; int rawlen;
+        get_item(*reads, r, raw, rawlen);
+        stored_sequence(raw, rawlen, platform, stored);
+        raw_row(S, R, stored, region, target_len, cutsite, reverse_comp != 0);
+    }
+    *out_bytes = S.n;
+    if (out && S.n > out_capacity) return scar_fail(SCAR_ERR_INVALID, "raw rows: %lld bytes needed", (long long)S.n);
+    return SCAR_OK;
+}
+
+// Stored sequences (platform transform applied) of a list of reads, gathered into one CSR buffer; row k is reverse-
+// complemented when flip[k] != 0 (3'-strand guides: frequency_output works on rcomp(consensus), :312-327).
+// out_off receives n_rows + 1 offsets; call with out = NULL for the size.
+extern "C" int scar_stored_gather_host(const scar_ragged *reads, const int64_t *rows, int64_t n_rows, int32_t platform,
+                                       const uint8_t *flip, uint8_t *out, int64_t out_capacity, int64_t *out_off)
+{
+    if (!reads || (!rows && n_rows) || !out_off || n_rows < 0) return scar_fail(SCAR_ERR_INVALID, "bad argument");
+    std::string stored;
+    int64_t pos = 0;
+    out_off[0] = 0;
+    for (int64_t k = 0; k < n_rows; ++k) {
+        const uint8_t *raw; int rawlen;
+        get_item(*reads, rows[k], raw, rawlen);
+        stored_sequence(raw, rawlen, platform, stored);
+        const int64_t len = (int64_t)stored.size();
+        if (out && pos + len <= out_capacity) {
+            if (flip && flip[k]) for (int64_t i = 0; i < len; ++i) out[pos + i] = comp((uint8_t)stored[(size_t)(len - 1 - i)]);
+            else memcpy(out + pos, stored.data(), (size_t)len);
+        }
+        pos += len;
+        out_off[k + 1] = pos;
+    }
+    if (out && pos > out_capacity) return scar_fail(SCAR_ERR_INVALID, "stored gather: %lld bytes needed", (long long)pos);
     return SCAR_OK;
 }

@@ -95,6 +95,10 @@ __device__ __forceinline__ int table_insert(const K4Params &P, uint64_t h1, uint
         ScarTableSlot *s = P.slots + slot;
         unsigned __int128 cur = load_tag(s);
         int claimed = 0;
+        // Both halves of a published tag are non-zero (key_hashes), so a value with exactly one zero half can only
+        // be a 16-byte load that was not single-copy atomic against a concurrent 128-bit CAS: read it again with an
+        // atomic (compare == swap leaves the slot unchanged) instead of mistaking the slot for another key's.
+        if (cur != 0 && ((uint64_t)cur == 0 || (uint64_t)(cur >> 64) == 0)) cur = atomicCAS(&s->tag, tag, tag);
         if (cur == 0) {
             cur = atomicCAS(&s->tag, (unsigned __int128)0, tag);
             claimed = cur == 0;

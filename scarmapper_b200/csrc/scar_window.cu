@@ -761,37 +761,61 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
 }
 
 // host-side launcher (called from scar_api.cu)
+struct K3Plan { void (*kern)(const K3Params); size_t smem; int per_sm; bool stage; };
+
+static cudaError_t plan_window(const K3Params &P, bool smem_tables, K3Plan &plan)
+{
+    const int threads = K3_TILE;
+    // short reads: the tile's cells are staged in shared memory as well (W rows of 2 KB)
+    const bool no_stage = getenv("SCAR_K3_NO_STAGE") != nullptr;
+    int stage_max = K3_STAGE_MAX_CELLS;
+    if (const char *e = getenv("SCAR_K3_STAGE_MAX_CELLS")) { const int v = atoi(e); if (v >= 1) stage_max = v; }
+    const size_t smem_base = 16 + (smem_tables ? P.blob_bytes : 0), cell_bytes = (size_t)P.W * K3_TILE * 8;
+    // (227 KB per CTA on sm_100, 7.5 KB of it the kernel's static queues and result arrays)
+    plan.stage = P.W <= stage_max && !no_stage && smem_base + cell_bytes + 7680 <= 227 * 1024;
+    plan.smem = smem_base + (plan.stage ? cell_bytes : 0);
+    const bool hr = P.hr_len > 0;
+    if (plan.stage)
+        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, true> : scar_window_kernel<true, false, true>)
+                                : (hr ? scar_window_kernel<false, true, true> : scar_window_kernel<false, false, true>);
+    else
+        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, false> : scar_window_kernel<true, false, false>)
+                                : (hr ? scar_window_kernel<false, true, false> : scar_window_kernel<false, false, false>);
+    cudaError_t e = cudaFuncSetAttribute(plan.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (e != cudaSuccess) return e;
+    plan.per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plan.per_sm, plan.kern, threads, plan.smem);
+    if (e != cudaSuccess) return e;
+    if (plan.per_sm < 1) plan.per_sm = 1;
+    if (const char *e2 = getenv("SCAR_K3_CTAS_PER_SM")) { const int v = atoi(e2); if (v >= 1 && v < plan.per_sm) plan.per_sm = v; }
+    return cudaSuccess;
+}
+
+// how K3 would be launched for this problem: cells staged in shared memory?, resident CTAs per SM, dynamic smem bytes
+cudaError_t scar_window_plan(const K3Params &P, bool smem_tables, int *stage, int *per_sm, int *smem_bytes)
+{
+    K3Plan plan;
+    cudaError_t e = plan_window(P, smem_tables, plan);
+    if (e != cudaSuccess) return e;
+    if (stage) *stage = plan.stage ? 1 : 0;
+    if (per_sm) *per_sm = plan.per_sm;
+    if (smem_bytes) *smem_bytes = (int)plan.smem;
+    return cudaSuccess;
+}
+
 cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count, cudaStream_t stream,
                                int *launches)
 {
     if (P.n_reads <= 0) return cudaSuccess;
     const int threads = K3_TILE;
-    // short reads: the tile's cells are staged in shared memory as well (W rows of 2 KB)
-    const bool no_stage = getenv("SCAR_K3_NO_STAGE") != nullptr;
-    const size_t smem_base = 16 + (smem_tables ? P.blob_bytes : 0), cell_bytes = (size_t)P.W * K3_TILE * 8;
-    // (227 KB per CTA on sm_100, 7.5 KB of it the kernel's static queues and result arrays)
-    const bool stage = P.W <= K3_STAGE_MAX_CELLS && !no_stage && smem_base + cell_bytes + 7680 <= 227 * 1024;
-    const size_t smem = smem_base + (stage ? cell_bytes : 0);
-    const bool hr = P.hr_len > 0;
-    void (*kern)(const K3Params);
-    if (stage)
-        kern = smem_tables ? (hr ? scar_window_kernel<true, true, true> : scar_window_kernel<true, false, true>)
-                           : (hr ? scar_window_kernel<false, true, true> : scar_window_kernel<false, false, true>);
-    else
-        kern = smem_tables ? (hr ? scar_window_kernel<true, true, false> : scar_window_kernel<true, false, false>)
-                           : (hr ? scar_window_kernel<false, true, false> : scar_window_kernel<false, false, false>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    K3Plan plan;
+    cudaError_t e = plan_window(P, smem_tables, plan);
     if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    if (const char *e = getenv("SCAR_K3_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
     // persistent grid: a whole number of resident CTAs per SM, never more than the work needs
     int64_t want = (P.n_reads + threads - 1) / threads;
-    int64_t grid = (int64_t)sm_count * per_sm;
+    int64_t grid = (int64_t)sm_count * plan.per_sm;
     if (grid > want) grid = want;
-    kern<<<(unsigned)grid, threads, smem, stream>>>(P);
+    plan.kern<<<(unsigned)grid, threads, plan.smem, stream>>>(P);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -6,13 +6,19 @@ install(INDEL_Processing) swaps two methods of the (otherwise unmodified) refere
   DataProcessing.consensus_demultiplex   (scarmapper/INDEL_Processing.py:891-1024, HOT LOOP A)
       reference: a serial Python loop, per read a loop over the manifest with two Levenshtein calls.
       here: the FASTQ text is indexed once, copied to the GPU, and ONE call (scar_process_host) runs
-      demultiplex -> pack -> sliding window -> aggregation for every read of the run.
+      demultiplex -> pack -> sliding window -> aggregation for every read of the run.  Everything that
+      needs the GPU or the whole run happens HERE, in the parent process, before main_loop forks its pool
+      (CUDA does not survive a fork): the homeology / templated-insertion searches of every scar pattern of
+      every sample (one scar_homeology_batch call) and, with --OutputRawData, the Raw_Data files (one pass
+      that buckets the scarred reads by sample, then scar_raw_rows_indexed_host per file).
   ScarSearch.data_processing             (:82-207, HOT LOOP B, one pathos process per sample)
       reference: per read filters + SlidingWindow.sliding_window + dict aggregation.
-      here: nothing is computed; the per-sample results of the GPU pass are unpacked into exactly
-      the objects the reference's reporting code consumes (summary_data, results_freq_dict in
-      first-seen order with the first read's sub_list, read_results_list) and frequency_output /
-      raw_data_output (unchanged reference code) write the files.
+      here: nothing is computed and no CUDA call is made; the worker unpacks ITS sample's slice of the GPU
+      results (counters, pattern counts, the first read of every pattern, the pattern-search results) into
+      exactly the objects the reference's reporting code consumes and runs the UNCHANGED frequency_output.
+
+What crosses the pool's pickling boundary is one SampleResult per sample, holding that sample's data only:
+O(patterns of the sample), never the run's records or FASTQ text.
 
 Everything else — options file, Logger, TargetMapper, main_loop, the pathos Pool, data_output,
 frequency_output, plots — stays the reference's own code.
@@ -22,16 +28,21 @@ from __future__ import annotations
 import collections
 import math
 import statistics
+import time
+import types
 
 import numpy as np
 
 from . import _native as N
 from . import fastq
-from .engine import ScarEngine, ScarProblem, cutsite_search
+from .engine import HostRagged, ScarEngine, ScarProblem, cutsite_search
 
 _ENGINE_FACTORY = [None]      # tests substitute a CPU stand-in here; None -> ScarEngine
 _HOMEOLOGY_BATCH = [None]     # likewise for the per-pattern searches; None -> engine.homeology_batch (GPU)
+_RAW_DATA_HOOK = [None]       # tests: called as hook(index_name, rows, records, reads, result) per Raw_Data file
 PATTERN_SEARCH_STATS = {"served": 0, "missed": 0}   # calls answered from the batch / handed to the reference's method
+STAGE_SECONDS = {}           # wall time of the stages of the last batched_consensus_demultiplex (parent process)
+READ_LIMIT_DEBUG = 1000002    # --Verbose DEBUG: the reference's loop stops after 1 000 002 reads (:906-914, see below)
 
 
 def _make_engine(prob: ScarProblem, device: int):
@@ -40,33 +51,39 @@ def _make_engine(prob: ScarProblem, device: int):
 
 
 class SampleResult:
-    """What the GPU pass produced for one sample library; stands in for sequence_dict[index]
-    (main_loop only takes its len() and hands it to ScarSearch; INDEL_Processing.py:1051-1053)."""
+    """What the GPU pass produced for ONE sample library; stands in for sequence_dict[index]
+    (main_loop only takes its len() and hands it to ScarSearch; INDEL_Processing.py:1051-1053).
+    Plain numpy arrays of this sample's own data, so pickling it to a pool worker costs O(patterns)."""
 
     def __init__(self, index_name, n_reads):
         self.index_name = index_name
         self.n_reads = n_reads
+        self.platform = "Illumina"
         self.target_region = None
         self.cutsite = None
+        self.reverse_comp = False
         self.counters = None          # int64[SCAR_N_COUNTERS]
-        self.table = []               # [(count, sub_list of the first read)] in first-seen order
-        self._read_results = None     # every SCAR read's sub_list (OutputRawData only), built on first use
-        self._read_results_fn = None
-        self.raw_source = None        # what the native Raw_Data writer needs (records, reads, sample, ...)
-        self.device = 0               # CUDA device the sample's GPU work runs on
-
-    @property
-    def read_results(self):
-        if self._read_results is None and self._read_results_fn is not None:
-            self._read_results = self._read_results_fn()
-        return self._read_results
-
-    @read_results.setter
-    def read_results(self, value):
-        self._read_results = value
+        self.counts = np.zeros(0, np.uint32)            # per pattern, first-seen order
+        self.first_records = np.zeros(0, N.RECORD_DTYPE)  # record of the first read of each pattern
+        self.first_bytes = np.zeros(0, np.uint8)        # stored sequences of those reads, CSR
+        self.first_off = np.zeros(1, np.int64)
+        self.pattern_out = None       # int32[n_patterns, 16] (struct ScarHomeology) or None
+        self.raw_written = False      # the Raw_Data file was written in the parent
+        self.read_results = None      # per-read lists for the reference's raw_data_output (only if somebody sets it)
 
     def __len__(self):
         return self.n_reads
+
+    def n_patterns(self) -> int:
+        return int(self.counts.size)
+
+    def first_read(self, k: int) -> str:
+        return self.first_bytes[int(self.first_off[k]):int(self.first_off[k + 1])].tobytes().decode("latin-1")
+
+    def table(self):
+        """[(count, sub_list of the first read)] in first-seen order (results_freq_dict's values)."""
+        return [(int(self.counts[k]), record_to_sublist(self.first_records[k], self.first_read(k), self.target_region,
+                                                        self.cutsite)) for k in range(self.n_patterns())]
 
 
 def record_to_sublist(rec, read, target, cutsite):
@@ -104,6 +121,39 @@ def fetch_target_region(module, args, target_dict, target_name, log):
         return str(module.pyfaidx.Fasta(args.RefSeq)[0]).upper()
 
 
+def _rcomp(s: str) -> str:
+    return s.encode("latin-1").translate(_COMP)[::-1].decode("latin-1")
+
+
+def pattern_search_batch(records, reads, platform, first, sample_of, sample_target, targets, target_rc, device):
+    """homeology_search + templated_insertion_search (INDEL_Processing.py:550-700) for every scar pattern of the run
+    in ONE batched call.  Pattern k is represented by its first read `first[k]` (record + stored sequence); the
+    arguments are derived per pattern exactly as frequency_output derives them (:299-328, incl. the swaps and
+    reverse complements for 3'-strand guides), vectorised.  Returns int32[n, 16] (struct ScarHomeology)."""
+    from . import engine as _engine
+    n = int(first.size)
+    if n == 0:
+        return np.zeros((0, 16), np.int32)
+    tix = np.asarray(sample_target, dtype=np.int32)[sample_of]
+    rc = np.asarray(target_rc, dtype=bool)[tix]
+    cons, off = _engine.stored_gather(reads, first, platform, flip=rc.astype(np.uint8) if rc.any() else None)
+    L = np.diff(off).astype(np.int64)
+    rec = records[first]
+    clj, crj = rec["clj"].astype(np.int64), rec["crj"].astype(np.int64)
+    tlj, trj = rec["tlj"].astype(np.int64), rec["trj"].astype(np.int64)
+    Lt = np.asarray([len(t) for t in targets], dtype=np.int64)[tix]
+    a = np.where(rc, L - crj, clj)
+    b = np.where(rc, L - clj, crj)
+    c = np.where(rc, Lt - trj, tlj)
+    d = np.where(rc, Lt - tlj, trj)
+    # the insertion frequency_output passes is consensus[a:b] in the orientation it works in
+    has_ins = (rec["flags"] & N.FL_INSERTION) != 0
+    ins = HostRagged.from_views(cons, off[:-1] + np.where(has_ins, a, 0), np.where(has_ins, b - a, 0).astype(np.int32))
+    oriented = [_rcomp(t) if r else t for t, r in zip(targets, target_rc)]
+    batch = _HOMEOLOGY_BATCH[0] or _engine.homeology_batch
+    return batch(HostRagged(cons, offsets=off), ins, a, b, c, d, tix, oriented, list(targets), device)
+
+
 def batched_consensus_demultiplex(self, module, device=0):
     """Replacement body of DataProcessing.consensus_demultiplex."""
     args, log = self.args, self.log
@@ -124,7 +174,7 @@ def batched_consensus_demultiplex(self, module, device=0):
         if t not in target_pos:
             target_pos[t] = len(target_names)
             target_names.append(t)
-    targets, cutsites = [], []
+    targets, cutsites, target_rc = [], [], []
     for t in target_names:
         region = fetch_target_region(module, args, self.target_dict, t, log)
         sgrna = self.target_dict[t][4]
@@ -136,17 +186,30 @@ def batched_consensus_demultiplex(self, module, device=0):
             raise SystemExit(1)
         targets.append(region)
         cutsites.append(cut)
+        target_rc.append(self.target_dict[t][5] == "YES")
     phasing = None
     if args.Platform == "Illumina":
         phasing = [([p[0] for p in self.phase_dict[t]["R1"]], [p[0] for p in self.phase_dict[t]["R2"]])
                    for t in target_names]
 
-    # ---- reads: one text buffer, views for the sequence and the two header index fields
-    limit = 1000001 if args.Verbose == "DEBUG" else None       # :906-914
+    # ---- reads: one text buffer, views for the sequence and the two header index fields.
+    # --Verbose DEBUG (:906-914): the reference tests `read_count > 1000000` at the top of an iteration that still
+    # reads and processes one more record, so it handles 1 000 002 reads.
+    limit = READ_LIMIT_DEBUG if args.Verbose == "DEBUG" else None
+    STAGE_SECONDS.clear()
+    t_stage = time.perf_counter()
+
+    def stage(name):
+        nonlocal t_stage
+        now = time.perf_counter()
+        STAGE_SECONDS[name] = STAGE_SECONDS.get(name, 0.0) + now - t_stage
+        t_stage = now
     batch = fastq.load(self.fastq1.input_file, want_index_fields=args.Platform == "Illumina", limit=limit)
     self.read_count = batch.n
+    stage("fastq_read_inflate_index")
+    sample_target = [target_pos[self.index_dict[i][7]] for i in sample_ids]
     prob = ScarProblem(
-        targets=targets, cutsites=cutsites, sample_target=[target_pos[self.index_dict[i][7]] for i in sample_ids],
+        targets=targets, cutsites=cutsites, sample_target=sample_target,
         left_index=[self.index_dict[i][0] for i in sample_ids], right_index=[self.index_dict[i][2] for i in sample_ids],
         platform=args.Platform, phasing=phasing, hr_donor=args.HR_Donor or "", n_limit=args.N_Limit,
         min_length=args.Minimum_Length, max_read_len=max(16, batch.seq.max_len()),
@@ -156,9 +219,10 @@ def batched_consensus_demultiplex(self, module, device=0):
         records = eng.process_host(batch.seq, batch.f0, batch.f1)
         counters, unassigned = eng.counters()
         phase_hist = eng.phase_hist()
-        table = eng.table()
+        table = eng.table()                     # sorted by (sample, first_idx): per-sample first-seen order
     finally:
         eng.close()
+    stage("gpu_classify_aggregate")
 
     # ---- unpack into the reference's bookkeeping
     assigned = records["status"] != N.ST_UNASSIGNED
@@ -177,29 +241,41 @@ def batched_consensus_demultiplex(self, module, device=0):
     if idx.size:
         u, first = np.unique(samples[idx], return_index=True)
         first_of = {int(s): int(idx[f]) for s, f in zip(u, first)}
-    by_sample = collections.defaultdict(list)
-    for e in table:
-        by_sample[int(e["sample"])].append((int(e["count"]), int(e["first_idx"])))
-    scar_reads = collections.defaultdict(list)
+
+    # ---- per-pattern work of the whole run, in the parent: first reads gathered once, searches in one GPU call
+    tab_sample = table["sample"].astype(np.int64)
+    tab_first = table["first_idx"].astype(np.int64)
+    bounds = np.searchsorted(tab_sample, np.arange(n_samples + 1))
+    first_bytes, first_off = _gather(batch.seq, tab_first, args.Platform)
+    stage("unpack")
+    pattern_out = pattern_search_batch(records, batch.seq, args.Platform, tab_first, tab_sample, sample_target, targets,
+                                       target_rc, device)
+    stage("gpu_pattern_searches")
+    # scarred reads bucketed by sample once (stable: read order inside a sample)
+    scar_rows, scar_bounds = None, None
     if args.OutputRawData:
-        for r in np.nonzero(records["status"] == N.ST_SCAR)[0]:
-            scar_reads[int(samples[r])].append(int(r))
+        scar_idx = np.nonzero(records["status"] == N.ST_SCAR)[0]
+        order = np.argsort(samples[scar_idx], kind="stable")
+        scar_rows = scar_idx[order].astype(np.int64)
+        scar_bounds = np.searchsorted(samples[scar_rows], np.arange(n_samples + 1))
+
     for s in sorted(first_of, key=first_of.get):
         iid = sample_ids[s]
-        t = prob.sample_target[s]
+        t = sample_target[s]
         res = SampleResult(iid, int(counters[s, N.CT_ASSIGNED]))
-        res.device = device
-        res.target_region, res.cutsite, res.counters = targets[t], cutsites[t], counters[s].copy()
-
-        def sub(r, t=t):
-            return record_to_sublist(records[r], stored_sequence(args.Platform, batch.seq.item(r)), targets[t], cutsites[t])
-        res.table = [(count, sub(first)) for count, first in by_sample.get(s, [])]
+        res.platform = args.Platform
+        res.target_region, res.cutsite, res.reverse_comp = targets[t], cutsites[t], target_rc[t]
+        res.counters = counters[s].copy()
+        lo, hi = int(bounds[s]), int(bounds[s + 1])
+        res.counts = table["count"][lo:hi].copy()
+        res.first_records = records[tab_first[lo:hi]]
+        b0, b1 = int(first_off[lo]), int(first_off[hi])
+        res.first_bytes = first_bytes[b0:b1].copy()
+        res.first_off = first_off[lo:hi + 1] - b0
+        res.pattern_out = pattern_out[lo:hi].copy()
         if args.OutputRawData:
-            # the per-read list of lists the reference's raw_data_output consumes is only built if somebody asks
-            # for it; the Raw_Data file itself is written natively from the records (native_raw_data_output)
-            res._read_results_fn = (lambda rows=scar_reads.get(s, []), sub=sub: [sub(r) for r in rows])
-            res.raw_source = dict(records=records, reads=batch.seq, sample=s, platform=args.Platform,
-                                  region=targets[t], cutsite=cutsites[t])
+            rows = scar_rows[int(scar_bounds[s]):int(scar_bounds[s + 1])]
+            write_raw_data(self, module, iid, res, rows, records, batch.seq)
         self.sequence_dict[iid] = res
 
         # phase_count (:948-975)
@@ -219,6 +295,10 @@ def batched_consensus_demultiplex(self, module, device=0):
             if phase_hist[s, 0, 0]:
                 self.phase_count[key]["No Read 1 Phasing"] += int(phase_hist[s, 0, 0])
 
+    stage("per_sample_results_and_raw_data")
+    log.info("Batched path: {} reads, {} scar patterns; ".format(batch.n, int(tab_first.size)) +
+             ", ".join("{} {:.2f} s".format(k, v) for k, v in STAGE_SECONDS.items()))
+
     # ---- lower limit for plots (:1003-1024, unchanged arithmetic)
     key_counts = [len(self.sequence_dict[k]) for k in self.sequence_dict]
     if len(key_counts) == 0:
@@ -234,8 +314,39 @@ def batched_consensus_demultiplex(self, module, device=0):
     return int(assigned.sum()), lower_limit
 
 
+def _gather(reads, rows, platform):
+    from . import engine as _engine
+    return _engine.stored_gather(reads, rows, platform)
+
+
+RAW_DATA_COLUMNS = ("Left Deletions\tRight Deletions\tDeletion Size\tMicrohomology\tInsertion\tInsertion Size\t"
+                    "Consensus Left Junction\tConsensus Right Junction\tRef Left Junction\tRef Right Junction\t"
+                    "Consensus\tTarget Region\n")
+
+
+def write_raw_data(self, module, index_name, res, rows, records, reads):
+    """ScarSearch.raw_data_output (scarmapper/INDEL_Processing.py:702-757) without the per-read Python lists, run
+    in the PARENT for one sample: same file name, the reference's own page header (ScarSearch.common_page_header
+    evaluated on a stand-in carrying the attributes it reads), and the rows written by scar_raw_rows_indexed_host
+    straight from the records of the sample's scarred reads `rows` (one line per scarred read, swaps and reverse
+    complements for 3'-strand guides, unaltered reads skipped)."""
+    from . import engine as _engine
+    stub = types.SimpleNamespace(version=self.version, run_start=self.run_start, index_dict=self.index_dict,
+                                 target_dict=self.target_dict, args=self.args)
+    header = module.ScarSearch.common_page_header(stub, index_name)
+    body = _engine.raw_rows_indexed(records, reads, rows, res.platform, res.target_region, res.cutsite, res.reverse_comp)
+    path = "{}{}_{}_ScarMapper_Raw_Data.txt".format(self.args.WorkingFolder, self.args.Job_Name, index_name)
+    with open(path, "wb") as f:
+        f.write("{}{}".format(header, RAW_DATA_COLUMNS).encode())
+        f.write(body)
+    res.raw_written = True
+    if _RAW_DATA_HOOK[0]:
+        _RAW_DATA_HOOK[0](index_name, rows, records, reads, res)
+
+
 def batched_data_processing(self):
-    """Replacement body of ScarSearch.data_processing: unpack, then the reference's own writers."""
+    """Replacement body of ScarSearch.data_processing: unpack, then the reference's own writers.  Runs inside a
+    forked pool worker: no CUDA call, only this sample's SampleResult."""
     res = self.sequence_list
     if not isinstance(res, SampleResult):
         raise TypeError("batched ScarSearch.data_processing needs the SampleResult produced by the batched demultiplex")
@@ -251,80 +362,47 @@ def batched_data_processing(self):
     self.cutsite = res.cutsite
     self.window_mapping()
     results_freq_dict = collections.defaultdict(list)
-    for count, sub_list in res.table:
+    for count, sub_list in res.table():
         key = "{}|{}|{}|{}|{}".format(sub_list[0], sub_list[1], sub_list[2], sub_list[3], sub_list[9])
         results_freq_dict[key] = [count, sub_list]
     self.log.info("Finished Processing {}".format(self.index_name))
-    batched_pattern_searches(self, results_freq_dict, getattr(res, "device", 0))
+    serve_pattern_searches(self, results_freq_dict, res.pattern_out)
     self.frequency_output(self.index_name, results_freq_dict, junction_type_data)
-    if self.args.OutputRawData:
-        if res.raw_source is not None:
-            native_raw_data_output(self, self.index_name, res)
-        else:
-            self.raw_data_output(self.index_name, res.read_results or [])
+    if self.args.OutputRawData and not res.raw_written:
+        self.raw_data_output(self.index_name, res.read_results or [])
+    # the returned ScarSearch objects are pickled back to the parent for data_output, which reads summary_data only
+    self.sequence_list = None
     return self.summary_data
 
 
-RAW_DATA_COLUMNS = ("Left Deletions\tRight Deletions\tDeletion Size\tMicrohomology\tInsertion\tInsertion Size\t"
-                    "Consensus Left Junction\tConsensus Right Junction\tRef Left Junction\tRef Right Junction\t"
-                    "Consensus\tTarget Region\n")
-
-
-def native_raw_data_output(self, index_name, res):
-    """ScarSearch.raw_data_output (scarmapper/INDEL_Processing.py:702-757) without the per-read Python lists:
-    same file name, the reference's own page header, and the rows written by scar_raw_rows_host straight from the
-    records (one line per scarred read, swaps and reverse complements for 3'-strand guides, unaltered reads
-    skipped)."""
-    from . import engine as _engine
-    src = res.raw_source
-    target_name = self.index_dict[index_name][7]
-    body = _engine.raw_rows(src["records"], src["reads"], src["sample"], src["platform"], src["region"], src["cutsite"],
-                            self.target_dict[target_name][5] == "YES")
-    path = "{}{}_{}_ScarMapper_Raw_Data.txt".format(self.args.WorkingFolder, self.args.Job_Name, index_name)
-    with open(path, "wb") as f:
-        f.write("{}{}".format(self.common_page_header(index_name), RAW_DATA_COLUMNS).encode())
-        f.write(body)
-
-
-def batched_pattern_searches(self, results_freq_dict, device: int = 0):
-    """The two per-pattern searches frequency_output runs in its Python loop - homeology_search and
-    templated_insertion_search (scarmapper/INDEL_Processing.py:550-700) - for EVERY pattern of the sample in
-    one batched GPU call (scar_homeology_batch), served to the unchanged frequency_output through instance
-    attributes of the same names.  The arguments are derived per key exactly as frequency_output derives them
-    (:299-328, incl. the swaps for 3'-strand guides); a call whose arguments are not in the batch simply runs
-    the reference's own method, so correctness never rests on this derivation."""
-    from .Sequence_Magic import rcomp
-    from . import engine as _engine
-    n = len(results_freq_dict)
-    if n == 0:
+def serve_pattern_searches(self, results_freq_dict, pattern_out):
+    """Serve the results of the batched pattern searches (computed in the parent, pattern_search_batch) to the
+    unchanged frequency_output through instance attributes named like the two methods it calls
+    (homeology_search / templated_insertion_search, scarmapper/INDEL_Processing.py:550-700).  The lookup keys are
+    derived per pattern exactly as frequency_output derives its arguments (:299-328); a call whose arguments are not
+    in the batch simply runs the reference's own method, so correctness never rests on this derivation."""
+    if pattern_out is None or len(results_freq_dict) == 0:
         return
+    assert len(pattern_out) == len(results_freq_dict)
     target_name = self.index_dict[self.index_name][7]
     rc = self.target_dict[target_name][5] == "YES"
     region = self.target_region
-    oriented = rcomp(region) if rc else region
-    keys, cons, inss, clj, crj, tlj, trj = [], [], [], [], [], [], []
-    for _count, sub in results_freq_dict.values():
+    oriented = _rcomp(region) if rc else region
+    hom, tmpl = {}, {}
+    for (_count, sub), o in zip(results_freq_dict.values(), pattern_out.tolist()):
         insertion, consensus = sub[2], sub[4]
         a, b, c, d = sub[5], sub[6], sub[7], sub[8]
         if rc:
-            insertion, consensus = rcomp(insertion), rcomp(consensus)
+            insertion, consensus = _rcomp(insertion), _rcomp(consensus)
             a, b = len(consensus) - sub[6], len(consensus) - sub[5]
             c, d = len(region) - sub[8], len(region) - sub[7]
-        keys.append((consensus, a, b, insertion, c, d))
-        cons.append(consensus); inss.append(insertion)
-        clj.append(a); crj.append(b); tlj.append(c); trj.append(d)
-    batch = _HOMEOLOGY_BATCH[0] or _engine.homeology_batch
-    out = batch(cons, inss, clj, crj, tlj, trj, np.zeros(n, dtype=np.int32), [oriented], [region], device)
-    hom, tmpl = {}, {}
-    for key, o in zip(keys, out.tolist()):
-        consensus, _a, _b, insertion, c, d = key
         left = ["", "", "", ""] if o[0] < 0 else (o[0], o[1], consensus[o[2]:o[2] + o[3]], oriented[o[4]:o[4] + o[5]])
         right = ["", "", "", ""] if o[6] < 0 else (o[6], o[7], consensus[o[8]:o[8] + o[9]], oriented[o[10]:o[10] + o[11]])
-        hom[key] = (left, right)
+        hom[(consensus, a, b, insertion, c, d)] = (left, right)
         if len(insertion) >= 5:
             lt = "" if o[12] < 0 else region[o[12]:o[12] + 5]
             rt = "" if o[13] < 0 else region[o[13]:o[13] + 5]
-            tmpl[(insertion, c, d)] = (rcomp(lt), rcomp(rt)) if rc else (lt, rt)
+            tmpl[(insertion, c, d)] = (_rcomp(lt), _rcomp(rt)) if rc else (lt, rt)
     cls = type(self)
     misses = [0]
 
@@ -352,10 +430,23 @@ def batched_pattern_searches(self, results_freq_dict, device: int = 0):
     self.pattern_search_misses = misses
 
 
+def _drop_served_searches(search):
+    """The two closures installed by serve_pattern_searches are not picklable and are not needed once
+    frequency_output has run; the pool pickles every ScarSearch back to the parent."""
+    for name in ("homeology_search", "templated_insertion_search"):
+        search.__dict__.pop(name, None)
+
+
 def install(module, device: int = 0):
     """Swap the two hot-loop bodies of the reference's INDEL_Processing module for the batched ones."""
     def consensus_demultiplex(self):
         return batched_consensus_demultiplex(self, module, device)
+
+    def data_processing(self):
+        try:
+            return batched_data_processing(self)
+        finally:
+            _drop_served_searches(self)
     module.DataProcessing.consensus_demultiplex = consensus_demultiplex
-    module.ScarSearch.data_processing = batched_data_processing
+    module.ScarSearch.data_processing = data_processing
     return module

@@ -202,7 +202,10 @@ class ScarEngine:
     def info(self) -> dict:
         b, s, k = C.c_int64(), C.c_int32(), C.c_int32()
         N.check(self._L.scar_ctx_info(self._ctx, C.byref(b), C.byref(s), C.byref(k)))
-        return {"static_bytes": b.value, "tables_in_smem": bool(s.value), "anchor_targets": k.value}
+        st, per, sm = C.c_int32(), C.c_int32(), C.c_int32()
+        N.check(self._L.scar_k3_plan(self._ctx, C.byref(st), C.byref(per), C.byref(sm)))
+        return {"static_bytes": b.value, "tables_in_smem": bool(s.value), "anchor_targets": k.value,
+                "k3_stage": bool(st.value), "k3_ctas_per_sm": per.value, "k3_smem_bytes": sm.value}
 
     def window_counts(self, target: int):
         a, b = C.c_int32(), C.c_int32()
@@ -393,6 +396,44 @@ def raw_rows(records, reads, sample: int, platform, target_region: str, cutsite:
     N.check(N.lib().scar_raw_rows_host(rec.ctypes.data, C.byref(rs), r.n, int(sample), plat, reg, len(reg), int(cutsite),
                                        1 if reverse_comp else 0, buf.ctypes.data, need.value, C.byref(need)))
     return buf[:need.value].tobytes()
+
+
+def raw_rows_indexed(records, reads, rows, platform, target_region: str, cutsite: int, reverse_comp: bool) -> bytes:
+    """raw_rows for a list of read indices (the scarred reads of one sample, in read order): O(len(rows))."""
+    r = as_ragged(reads)
+    rec = np.ascontiguousarray(records)
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    assert rec.dtype == N.RECORD_DTYPE and rec.shape[0] == r.n
+    assert rows.size == 0 or (0 <= int(rows.min()) and int(rows.max()) < r.n)
+    plat = N.PLATFORMS[platform] if isinstance(platform, str) else int(platform)
+    reg = target_region.encode("latin-1")
+    rs = r.c_struct()
+    need = C.c_int64(0)
+    args = (rec.ctypes.data, C.byref(rs), rows.ctypes.data, rows.size, plat, reg, len(reg), int(cutsite),
+            1 if reverse_comp else 0)
+    N.check(N.lib().scar_raw_rows_indexed_host(*args, None, 0, C.byref(need)))
+    buf = np.empty(max(need.value, 1), dtype=np.uint8)
+    N.check(N.lib().scar_raw_rows_indexed_host(*args, buf.ctypes.data, need.value, C.byref(need)))
+    return buf[:need.value].tobytes()
+
+
+def stored_gather(reads, rows, platform, flip=None):
+    """Stored sequences (platform transform applied; row k reverse-complemented when flip[k]) of the reads `rows`,
+    as one CSR buffer: (uint8 bytes, int64 offsets[len(rows) + 1])."""
+    r = as_ragged(reads)
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    assert rows.size == 0 or (0 <= int(rows.min()) and int(rows.max()) < r.n)
+    plat = N.PLATFORMS[platform] if isinstance(platform, str) else int(platform)
+    fl = None if flip is None else np.ascontiguousarray(flip, dtype=np.uint8)
+    assert fl is None or fl.size == rows.size
+    off = np.zeros(rows.size + 1, dtype=np.int64)
+    rs = r.c_struct()
+    fp = None if fl is None else fl.ctypes.data
+    N.check(N.lib().scar_stored_gather_host(C.byref(rs), rows.ctypes.data, rows.size, plat, fp, None, 0, off.ctypes.data))
+    out = np.empty(max(int(off[-1]), 1), dtype=np.uint8)
+    N.check(N.lib().scar_stored_gather_host(C.byref(rs), rows.ctypes.data, rows.size, plat, fp, out.ctypes.data,
+                                            int(off[-1]), off.ctypes.data))
+    return out[:int(off[-1])], off
 
 
 def homeology_batch(consensus, insertions, clj, crj, tlj, trj, target_idx, targets, regions, device: int = 0) -> np.ndarray:

@@ -56,6 +56,14 @@ def write_inputs(wd, case):
             f.write("@{}\n{}\n+\n{}\n".format(name, seq, "I" * len(seq)))
 
 
+def raw_data_digest(path):
+    """sha256 of a Raw_Data file without its wall-clock and version header lines."""
+    import hashlib
+    lines = open(path, "rb").read().split(b"\n")
+    keep = [ln for ln in lines if not ln.startswith((b"# Run Start", b"# Run End", b"# ScarMapper Search v"))]
+    return hashlib.sha256(b"\n".join(keep)).hexdigest()
+
+
 def run_reference(case):
     ref_shims.install()
     from scarmapper import INDEL_Processing, TargetMapper
@@ -116,19 +124,24 @@ def run_reference(case):
             INDEL_Processing.ScarSearch.raw_data_output = orig_raw
         for k in results:
             results[k].update(captured.get(k, {}))
-        files = {}
+        files, file_sha256 = {}, {}
         for fn in sorted(os.listdir(wd)):
-            if fn.endswith(("_ScarMapper_Frequency.txt", "_ScarMapper_Summary.txt")):
+            if fn.endswith(("_ScarMapper_Frequency.txt", "_ScarMapper_Summary.txt", "_SNV_Frequency.txt")):
                 lines = open(os.path.join(wd, fn)).read().split("\n")
                 keep = [ln for ln in lines if not ln.startswith(("# Run Start", "# Run End", "Start:", "End:",
                                                                  "FASTQ1:", "FASTQ2:"))]
                 files[fn] = "\n".join(keep)
+            elif fn.endswith("_ScarMapper_Raw_Data.txt"):
+                # one line per scarred read: too large to store, so the fixture keeps a digest of the file minus
+                # its wall-clock and version lines
+                file_sha256[fn] = raw_data_digest(os.path.join(wd, fn))
         return {
             "samples": results,
             "read_count": dp.read_count,
             "read_count_dict": dict(dp.read_count_dict),
             "phase_count": {k: dict(v) for k, v in dp.phase_count.items()},
             "files": files,
+            "file_sha256": file_sha256,
         }
     finally:
         shutil.rmtree(wd, ignore_errors=True)

@@ -136,3 +136,55 @@ def compare_with_golden(case, golden, records, table_fn=None):
                     m = int((records[col][sel] == k).sum())
                 assert m == n, ("phase", key, lab, m, n)
     return cnt
+
+
+WALL_CLOCK = ("# Run Start", "# Run End", "Start:", "End:", "FASTQ1:", "FASTQ2:")
+VERSION = ("ScarMapper v", "# ScarMapper Search v")     # the goldens were written with version="golden"
+
+
+def compare_output_files(wd, golden, ignore_version=False, expect_raw=True):
+    """Every Frequency / SNV_Frequency / Summary file the reference wrote for this case equals the file in `wd`
+    line for line (wall-clock lines excluded), no such file is extra, and every Raw_Data file has the digest the
+    reference's own file had.  Returns the number of files compared."""
+    import hashlib
+    skip = WALL_CLOCK + (VERSION if ignore_version else ())
+    seen = 0
+    for fn, want in golden["files"].items():
+        got = open(os.path.join(wd, fn)).read().split("\n")
+        got = "\n".join(ln for ln in got if not ln.startswith(skip))
+        if ignore_version:
+            want = "\n".join(ln for ln in want.split("\n") if not ln.startswith(VERSION))
+        assert got == want, fn
+        seen += 1
+    mine = sorted(fn for fn in os.listdir(wd)
+                  if fn.endswith(("_ScarMapper_Frequency.txt", "_ScarMapper_Summary.txt", "_SNV_Frequency.txt")))
+    assert mine == sorted(golden["files"]), (set(mine) ^ set(golden["files"]))
+    if expect_raw:
+        for fn, want in golden.get("file_sha256", {}).items():
+            lines = open(os.path.join(wd, fn), "rb").read().split(b"\n")
+            keep = [ln for ln in lines if not ln.startswith((b"# Run Start", b"# Run End", b"# ScarMapper Search v"))]
+            assert hashlib.sha256(b"\n".join(keep)).hexdigest() == want, fn
+            seen += 1
+        raw = sorted(fn for fn in os.listdir(wd) if fn.endswith("_ScarMapper_Raw_Data.txt"))
+        assert raw == sorted(golden.get("file_sha256", {})), "Raw_Data file set differs"
+    return seen
+
+
+def write_options_file(wd, case, spawn=1, verbose="ERROR", raw=True):
+    """A tab-delimited options file in the format of docs/run_ScarMapper_IndelProcessing.sh for the inputs that
+    make_golden.write_inputs put into `wd`."""
+    opts = {
+        "IndelProcessing": "True", "FASTQ1": wd + "reads.fastq.gz", "FASTQ2": "", "RefSeq": wd + "refseq.fa",
+        "Master_Index_File": wd + "master_index.tsv", "SampleManifest": wd + "manifest.tsv",
+        "TargetFile": wd + "targets.tsv", "WorkingFolder": wd, "Verbose": verbose, "Job_Name": "golden",
+        "Spawn": str(spawn), "Demultiplex": "False", "DeleteConsensusFASTQ": "True", "HR_Donor": case["hr_donor"],
+        "Platform": case["platform"], "Search_KMER": "10", "N_Limit": str(case["n_limit"]),
+        "Minimum_Length": "{} # Length after trimming".format(case["min_length"]),
+        "OutputRawData": "True" if raw else "False", "PatternThreshold": "0.0001 # cutoff", "FigureType": "pdf",
+    }
+    path = wd + "run.sh"
+    with open(path, "w") as f:
+        f.write("#!/bin/bash\n#Parameter file\n\npython3 scarmapper.py --options_file run.sh\nexit\n\n")
+        for k, v in opts.items():
+            f.write("--{}\t{}\n".format(k, v))
+    return path

@@ -81,11 +81,17 @@ extern "C" void hom_eval(const uint8_t *cons, int n_cons, int clj, int crj, cons
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", csrc, src, "-o", so])
         _HOM_LIB[0] = C.CDLL(so)
     lib = _HOM_LIB[0]
+
+    def items(x):        # list of str, or a HostRagged (what the drop-in passes)
+        if hasattr(x, "item"):
+            return [x.item(i) for i in range(x.n)]
+        return [v.encode("latin-1") if isinstance(v, str) else bytes(v) for v in x]
+    consensus, insertions = items(consensus), items(insertions)
     out = np.zeros((len(consensus), 16), dtype=np.int32)
     row = (C.c_int32 * 16)()
     for i, (c, s) in enumerate(zip(consensus, insertions)):
         t, r = targets[int(target_idx[i])].encode(), regions[int(target_idx[i])].encode()
-        lib.hom_eval(c.encode(), len(c), int(clj[i]), int(crj[i]), t, len(t), s.encode(), len(s), r, len(r),
+        lib.hom_eval(c, len(c), int(clj[i]), int(crj[i]), t, len(t), s, len(s), r, len(r),
                      int(tlj[i]), int(trj[i]), row)
         out[i] = list(row)
     return out

@@ -100,7 +100,7 @@ def test_searches_match_the_reference_methods(lib):
 
 
 def test_dropin_serves_batch_results_and_falls_back_to_the_reference_method():
-    """dropin.batched_pattern_searches: calls with the arguments frequency_output derives are answered from the
+    """dropin.pattern_search_batch + serve_pattern_searches: calls with the arguments frequency_output derives are answered from the
     batch (identical to the reference's methods, 5' and 3' guides); any other call runs the reference's method."""
     import sys
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -132,7 +132,19 @@ def test_dropin_serves_batch_results_and_falls_back_to_the_reference_method():
         dropin._HOMEOLOGY_BATCH[0] = host_homeology_batch
         dropin.PATTERN_SEARCH_STATS.update(served=0, missed=0)
         try:
-            dropin.batched_pattern_searches(me, table)
+            # what the parent does for the whole run (records + reads -> one batched call) ...
+            import numpy as np
+            from scarmapper_b200 import _native as N
+            rec = np.zeros(len(table), dtype=N.RECORD_DTYPE)
+            for k, (_c, sub) in enumerate(table.values()):
+                rec[k]["clj"], rec[k]["crj"], rec[k]["tlj"], rec[k]["trj"] = sub[5], sub[6], sub[7], sub[8]
+                rec[k]["flags"] = N.FL_INSERTION if sub[2] else 0
+                rec[k]["status"] = N.ST_SCAR
+            reads = [sub[4] for _c, sub in table.values()]
+            out = dropin.pattern_search_batch(rec, reads, "Illumina", np.arange(len(table)), np.zeros(len(table), np.int64),
+                                              [0], [region], [rc], 0)
+            # ... and what a pool worker does with its sample's slice
+            dropin.serve_pattern_searches(me, table, out)
         finally:
             dropin._HOMEOLOGY_BATCH[0] = None
         oriented = Sequence_Magic.rcomp(region) if rc else region
