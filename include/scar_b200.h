@@ -134,8 +134,20 @@ int scar_classify_dev(scar_ctx *ctx, const uint64_t *cells, const uint32_t *lens
 int scar_aggregate_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_record *records,
                        int64_t n_reads, uint64_t first_index, void *stream);
 
-/* Whole path over a batch already resident in HBM: K2 -> K1 -> K3 -> K4 on `stream`.
- * cells/lens/samples/records are caller-provided device scratch/outputs. */
+/* K1 + K3 (+ K4 when aggregate != 0) FUSED: one pass over the RAW read bytes.  A CTA stages a tile's raw bytes in
+ * shared memory (TMA bulk copies), packs them there, classifies, writes the records and - with `aggregate` - updates
+ * the per-sample counters, phase histograms and the scar table, so the packed batch never travels through HBM and
+ * the raw reads are read once.  Same records / tables as scar_pack_dev + scar_classify_dev + scar_aggregate_dev.
+ * Takes reads up to 320 nt on the Illumina and TruSeq platforms (scar_fused_info: eligible); SCAR_ERR_UNSUPPORTED
+ * otherwise. */
+int scar_classify_raw_dev(scar_ctx *ctx, const scar_ragged *seq, const uint16_t *samples, int64_t n_reads,
+                          uint64_t first_index, scar_record *records, int32_t aggregate, void *stream);
+int scar_fused_info(const scar_ctx *ctx, int32_t *eligible, int32_t *ctas_per_sm, int32_t *smem_bytes);
+
+/* Whole path over a batch already resident in HBM on `stream`: K2, then the fused kernel (scar_classify_raw_dev with
+ * aggregate = 1) when the context is eligible for it, else K1 -> K3 -> K4.  cells/lens/samples/records are
+ * caller-provided device scratch/outputs (cells and lens are untouched on the fused path; SCAR_NO_FUSE=1 forces
+ * the three-kernel path). */
 int scar_run_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_ragged *f0, const scar_ragged *f1,
                  int64_t n_reads, uint64_t first_index, uint64_t *cells, uint32_t *lens,
                  uint16_t *samples, scar_record *records, void *stream);

@@ -83,6 +83,8 @@ PROTOTYPES = {
     "scar_demux_dev": (C.c_int, [_P, _RP, _RP, _RP, C.c_int64, _P, _P]),
     "scar_classify_dev": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P]),
     "scar_aggregate_dev": (C.c_int, [_P, _RP, _P, C.c_int64, C.c_uint64, _P]),
+    "scar_classify_raw_dev": (C.c_int, [_P, _RP, _P, C.c_int64, C.c_uint64, _P, C.c_int32, _P]),
+    "scar_fused_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "scar_run_dev": (C.c_int, [_P, _RP, _RP, _RP, C.c_int64, C.c_uint64, _P, _P, _P, _P, _P]),
     "scar_process_host": (C.c_int, [_P, _RP, _RP, _RP, C.c_int64, C.c_uint64, _P]),
     "scar_counters_read": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),

@@ -607,8 +607,8 @@ static K4Params k4_params(scar_ctx *c)
     P.platform = c->platform; P.max_probe = (uint32_t)std::min<uint64_t>(c->capacity - 1, 1u << 16);
     int max_phase = 0;
     for (const auto &m : c->h_targets) max_phase = std::max(max_phase, (int)m.n_phase);
-    const int pb = max_phase + 2;                 // bins: none, 0..max_phase-1, n/a
-    P.phase_joint = pb * pb <= 128 ? pb : 0;
+    P.phase_bins = max_phase + 2;                 // bins: none, 0..max_phase-1, n/a
+    P.phase_joint = P.phase_bins * P.phase_bins <= 128 ? 1 : 0;
     return P;
 }
 
@@ -623,12 +623,58 @@ extern "C" int scar_aggregate_dev(scar_ctx *c, const scar_ragged *seq, const sca
     return SCAR_OK;
 }
 
+// parameters of the fused kernel (K1 + K3 and, with `aggregate`, K4 in one pass over the raw bytes)
+static K3Params fused_params(scar_ctx *c, const scar_ragged *seq, const uint16_t *samples, int64_t n, uint64_t first_index,
+                             scar_record *records, int aggregate)
+{
+    K3Params P = k3_params(c);
+    if (seq) P.seq = *seq;
+    P.samples = samples; P.records = records; P.n_reads = n; P.stride = n; P.platform = c->platform;
+    P.aggregate = aggregate; P.first_index = first_index;
+    const K4Params A = k4_params(c);
+    P.slots = A.slots; P.slot_mask = A.slot_mask; P.max_probe = A.max_probe; P.n_entries = A.n_entries;
+    P.counters = A.counters; P.unassigned = A.unassigned; P.phase_hist = A.phase_hist; P.status = c->d_status;
+    P.phase_bins = A.phase_bins; P.phase_joint = A.phase_joint;
+    return P;
+}
+
+extern "C" int scar_fused_info(const scar_ctx *c, int32_t *eligible, int32_t *ctas_per_sm, int32_t *smem_bytes)
+{
+    if (!c) return fail(SCAR_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    const bool ok = scar_fused_eligible(c->W, c->platform);
+    if (eligible) *eligible = ok ? 1 : 0;
+    int per = 0, sm = 0;
+    if (ok) CU(scar_fused_plan(fused_params(const_cast<scar_ctx *>(c), nullptr, nullptr, 0, 0, nullptr, 1), c->smem_tables,
+                               c->max_read_len, &per, &sm));
+    if (ctas_per_sm) *ctas_per_sm = per;
+    if (smem_bytes) *smem_bytes = sm;
+    return SCAR_OK;
+}
+
+extern "C" int scar_classify_raw_dev(scar_ctx *c, const scar_ragged *seq, const uint16_t *samples, int64_t n,
+                                     uint64_t first_index, scar_record *records, int32_t aggregate, void *stream)
+{
+    if (!c || !seq || !samples || !records || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    if (!scar_fused_eligible(c->W, c->platform))
+        return fail(SCAR_ERR_UNSUPPORTED, "the fused kernel takes reads up to 320 nt on the Illumina / TruSeq platforms "
+                                          "(use scar_pack_dev + scar_classify_dev + scar_aggregate_dev)");
+    if (n == 0) return SCAR_OK;
+    CU(cudaSetDevice(c->device));
+    CU(scar_launch_fused(fused_params(c, seq, samples, n, first_index, records, aggregate ? 1 : 0), c->smem_tables,
+                         c->max_read_len, c->sm_count, (cudaStream_t)stream, &c->launches));
+    return SCAR_OK;
+}
+
 extern "C" int scar_run_dev(scar_ctx *c, const scar_ragged *seq, const scar_ragged *f0, const scar_ragged *f1, int64_t n,
                             uint64_t first_index, uint64_t *cells, uint32_t *lens, uint16_t *samples,
                             scar_record *records, void *stream)
 {
     int rc;
     if ((rc = scar_demux_dev(c, seq, f0, f1, n, samples, stream))) return rc;
+    // one pass over the raw bytes (pack, classify, aggregate) when the fused kernel takes the problem
+    if (c && seq && scar_fused_eligible(c->W, c->platform))
+        return scar_classify_raw_dev(c, seq, samples, n, first_index, records, 1, stream);
     if ((rc = scar_pack_dev(c, seq, n, cells, lens, stream))) return rc;
     if ((rc = scar_classify_dev(c, cells, lens, samples, n, records, stream))) return rc;
     return scar_aggregate_dev(c, seq, records, n, first_index, stream);

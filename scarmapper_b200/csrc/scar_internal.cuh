@@ -129,7 +129,17 @@ struct K3Params {
     int32_t min_length;
     uint64_t hr_code;             // donor, 2 bits/base
     int32_t hr_len;
-    int32_t pad;
+    // ---- fused mode (scar_classify_raw_dev): raw read bytes in; packing (K1), classification (K3) and, when
+    // `aggregate`, the per-sample accumulators and the scar table (K4) in ONE pass over a tile in shared memory
+    int32_t platform;
+    scar_ragged seq;              // raw reads (device pointers)
+    uint32_t raw_cap;             // bytes of the tile's raw staging buffer (the packed cells reuse it)
+    int32_t aggregate;
+    uint64_t first_index;         // global index of read 0 (first-seen order across batches and ranks)
+    ScarTableSlot *slots; uint64_t slot_mask; uint32_t max_probe; int32_t hist_smem;
+    unsigned long long *n_entries, *counters, *unassigned, *phase_hist;
+    int32_t *status;              // bit 0: read longer than 16 W, bit 1: table full
+    int32_t phase_bins, phase_joint;
 };
 
 struct K4Params {
@@ -148,8 +158,8 @@ struct K4Params {
     int32_t platform;
     int32_t use_smem;            // counters + phase histograms staged in shared memory
     uint32_t max_probe;
-    int32_t phase_joint;         // PB > 0: joint [PB][PB] phase histogram in shared memory (PB = max phases + 2)
-    int32_t pad;
+    int32_t phase_joint;         // 1: joint [PB][PB] phase histogram in shared memory, 0: two [PB] marginals
+    int32_t phase_bins;          // PB = max phases + 2 (none, phase 0 .. max-1, n/a)
 };
 
 struct K4VerifyParams {
@@ -160,6 +170,11 @@ struct K4VerifyParams {
 
 cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t scar_window_plan(const K3Params &P, bool smem_tables, int *stage, int *per_sm, int *smem_bytes);
+// fused K1+K3(+K4) from raw bytes; false when the problem is outside what the fused kernel takes (the caller then
+// runs K1 -> K3 -> K4)
+bool scar_fused_eligible(int W, int platform);
+cudaError_t scar_launch_fused(K3Params P, bool smem_tables, int max_read_len, int sm_count, cudaStream_t stream, int *launches);
+cudaError_t scar_fused_plan(K3Params P, bool smem_tables, int max_read_len, int *per_sm, int *smem_bytes);
 cudaError_t scar_launch_pack(const scar_ragged &seq, int64_t n, int W, int platform, uint64_t *cells,
                              int64_t stride, uint32_t *lens, int32_t *status, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t scar_launch_demux(const K2Params &P, int sm_count, cudaStream_t stream, int *launches);

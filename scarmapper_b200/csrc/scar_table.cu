@@ -10,150 +10,18 @@
 // (128 bits; both must agree).  The table is open-addressed in HBM; a slot keeps the count and the
 // smallest global read index (the reference stores the FIRST read's record and orders ties by
 // first-seen rank).
-#include "scar_internal.cuh"
+#include "scar_table_core.cuh"
 
-
-__device__ __forceinline__ uint8_t comp_byte(uint8_t c)
+static __device__ __forceinline__ ScarTableRef table_ref(const K4Params &P)
 {
-    // Sequence_Magic.rcomp's translate table (Valkyries/Sequence_Magic.py:97-118); unmapped bytes pass
-    switch (c) {
-    case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
-    case 'M': return 'K'; case 'R': return 'Y'; case 'Y': return 'R'; case 'K': return 'M';
-    case 'V': return 'B'; case 'H': return 'D'; case 'D': return 'H'; case 'B': return 'V';
-    case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
-    case 'm': return 'k'; case 'r': return 'y'; case 'y': return 'r'; case 'k': return 'm';
-    case 'v': return 'b'; case 'h': return 'd'; case 'd': return 'h'; case 'b': return 'v';
-    default: return c;
-    }
+    ScarTableRef T; T.slots = P.slots; T.slot_mask = P.slot_mask; T.max_probe = P.max_probe; T.status = P.status;
+    return T;
 }
-
-// byte q of the STORED sequence (after the platform transform) of a raw read
-__device__ __forceinline__ uint8_t stored_byte(const uint8_t *raw, int rawlen, int platform, int q)
+static __device__ __forceinline__ ScarAccRef acc_ref(const K4Params &P)
 {
-    if (platform == SCAR_PLATFORM_TRUSEQ) return raw[q + 6];
-    if (platform == SCAR_PLATFORM_RAMSDEN) return comp_byte(raw[rawlen - 1 - q]);
-    return raw[q];
-}
-
-// the two key hashes of a SCAR record
-__device__ __forceinline__ void key_hashes(const scar_record &rec, const uint8_t *raw, int rawlen, int platform,
-                                           uint64_t &h1, uint64_t &h2)
-{
-    int lo = 0, hi = 0; uint64_t kind = 0;
-    if (rec.flags & SCAR_FL_INSERTION) { lo = rec.clj; hi = rec.crj; kind = 1; }
-    else if (rec.flags & SCAR_FL_MICROHOM) { lo = rec.crj; hi = rec.clj; kind = 2; }
-    const uint64_t hdr = (uint64_t)rec.sample | ((uint64_t)rec.tlj << 16) | ((uint64_t)rec.trj << 32) |
-                         (kind << 48) | ((uint64_t)((rec.flags & SCAR_FL_HR) ? 1 : 0) << 50) |
-                         ((uint64_t)(hi - lo) << 51);
-    h1 = scar_mix1(hdr ^ 0x9E3779B97F4A7C15ull);
-    h2 = scar_mix2(hdr + 0xD6E8FEB86659FD93ull);
-    for (int q = lo; q < hi; q += 8) {
-        uint64_t w = 0;
-        const int n = min(8, hi - q);
-        if (platform != SCAR_PLATFORM_RAMSDEN) {
-            // eight segment bytes with two aligned 8-byte loads (every raw buffer is padded by >= 16 bytes)
-            const uintptr_t a = (uintptr_t)(raw + q + (platform == SCAR_PLATFORM_TRUSEQ ? 6 : 0));
-            const uintptr_t a0 = a & ~(uintptr_t)7;
-            const uint32_t sh = (uint32_t)(a & 7) * 8;
-            const uint64_t lo8 = __ldg(reinterpret_cast<const unsigned long long *>(a0));
-            const uint64_t hi8 = sh ? __ldg(reinterpret_cast<const unsigned long long *>(a0 + 8)) : 0ull;
-            w = sh ? ((lo8 >> sh) | (hi8 << (64 - sh))) : lo8;
-            if (n < 8) w &= (1ull << (8 * n)) - 1ull;
-        } else {
-            for (int k = 0; k < n; ++k) w |= (uint64_t)stored_byte(raw, rawlen, platform, q + k) << (8 * k);
-        }
-        h1 = scar_mix1(h1 ^ w);
-        h2 = scar_mix2(h2 + w * 0xA24BAED4963EE407ull + 1ull);
-    }
-    if (h1 == 0) h1 = 1;
-    if (h2 == 0) h2 = 1;
-}
-
-__device__ __forceinline__ unsigned __int128 make_tag(uint64_t h1, uint64_t h2)
-{
-    return (unsigned __int128)h1 | ((unsigned __int128)h2 << 64);
-}
-
-// 16-byte load of a slot's tag that bypasses L1 (other SMs publish tags with L2 atomics)
-__device__ __forceinline__ unsigned __int128 load_tag(const ScarTableSlot *s)
-{
-    unsigned long long lo, hi;
-    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(&s->tag));
-    return (unsigned __int128)lo | ((unsigned __int128)hi << 64);
-}
-
-// Insert (or find) the key and fold n occurrences with smallest global index `first` into it.
-// One slot visit = one plain 16-byte load; only an empty slot costs an atomic (one 128-bit CAS that
-// publishes both hashes at once); count and first_idx are fire-and-forget reductions.
-// Returns 1 when a new slot was claimed.
-__device__ __forceinline__ int table_insert(const K4Params &P, uint64_t h1, uint64_t h2, uint32_t n,
-                                            uint64_t first, uint32_t sample)
-{
-    const unsigned __int128 tag = make_tag(h1, h2);
-    uint64_t slot = h1 & P.slot_mask;
-    for (uint32_t probe = 0; probe <= P.max_probe; ++probe) {
-        ScarTableSlot *s = P.slots + slot;
-        unsigned __int128 cur = load_tag(s);
-        int claimed = 0;
-        // Both halves of a published tag are non-zero (key_hashes), so a value with exactly one zero half can only
-        // be a 16-byte load that was not single-copy atomic against a concurrent 128-bit CAS: read it again with an
-        // atomic (compare == swap leaves the slot unchanged) instead of mistaking the slot for another key's.
-        if (cur != 0 && ((uint64_t)cur == 0 || (uint64_t)(cur >> 64) == 0)) cur = atomicCAS(&s->tag, tag, tag);
-        if (cur == 0) {
-            cur = atomicCAS(&s->tag, (unsigned __int128)0, tag);
-            claimed = cur == 0;
-            if (claimed) cur = tag;
-        }
-        if (cur == tag) {
-            atomicAdd(&s->count, n);
-            atomicMax(&s->inv_first, ~(unsigned long long)first);
-            if (claimed) s->sample = sample;
-            return claimed;
-        }
-        slot = (slot + 1) & P.slot_mask;
-    }
-    atomicOr(P.status, 2);
-    return 0;
-}
-
-// Shared-memory accumulators of one sample (32-bit words): six words of two 16-bit counters each (one
-// atomic bumps two counters; a CTA flushes before any field can reach 2^16), HR_MORE, and
-// the phase bins: a joint [PB][PB] histogram of (phase_r1, phase_r2) when PB*PB <= 128 (one atomic per
-// read instead of two), else two [SCAR_PHASE_BINS] marginals.
-//   word A: ASSIGNED | PASSING << 16 | FILTERED << 32 | NO_JUNCTION << 48
-//   word B: NO_CUT | N_INSERTION << 16 | SCAR << 32 | LEFT_DEL << 48
-//   word C: RIGHT_DEL | INSERTION << 16 | MICROHOM << 32 | HR_FIRST << 48
-#define K4_FIXED_WORDS 8
-#define K4_EPOCH_ITERS 255          // 255 x 256 threads < 65536 reads per CTA between flushes
-
-__device__ __forceinline__ void k4_flush(const K4Params &P, unsigned int *s_hist, int per_sample, int pb)
-{
-    static const int fieldA[4] = {SCAR_CT_ASSIGNED, SCAR_CT_PASSING, SCAR_CT_FILTERED, SCAR_CT_NO_JUNCTION};
-    static const int fieldB[4] = {SCAR_CT_NO_CUT, SCAR_CT_N_INSERTION, SCAR_CT_SCAR, SCAR_CT_LEFT_DEL};
-    static const int fieldC[4] = {SCAR_CT_RIGHT_DEL, SCAR_CT_INSERTION, SCAR_CT_MICROHOM, SCAR_CT_HR_FIRST};
-    for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) {
-        const unsigned int v = s_hist[i];
-        if (!v) continue;
-        s_hist[i] = 0;
-        const int s = i / per_sample, c = i - s * per_sample;
-        unsigned long long *cnt = P.counters + (size_t)s * SCAR_N_COUNTERS;
-        unsigned long long *ph = P.phase_hist + (size_t)s * 2 * SCAR_PHASE_BINS;
-        if (c < 6) {                                   // half of a packed 64-bit word: two 16-bit fields
-            const int *f = c < 2 ? fieldA : (c < 4 ? fieldB : fieldC);
-            const int k = (c & 1) * 2;
-            if (v & 0xFFFFu) atomicAdd(cnt + f[k], (unsigned long long)(v & 0xFFFFu));
-            if (v >> 16) atomicAdd(cnt + f[k + 1], (unsigned long long)(v >> 16));
-        } else if (c == 6) {
-            atomicAdd(cnt + SCAR_CT_HR_MORE, (unsigned long long)v);
-        } else if (c >= K4_FIXED_WORDS) {
-            const int b = c - K4_FIXED_WORDS;
-            if (pb) {                                  // joint bin (b1, b2): NA is the last joint index
-                const int b1 = b / pb, b2 = b - b1 * pb;
-                atomicAdd(ph + (b1 == pb - 1 ? SCAR_PHASE_BINS - 1 : b1), (unsigned long long)v);
-                atomicAdd(ph + SCAR_PHASE_BINS + (b2 == pb - 1 ? SCAR_PHASE_BINS - 1 : b2), (unsigned long long)v);
-            } else atomicAdd(ph + b, (unsigned long long)v);
-        }
-    }
+    ScarAccRef A; A.counters = P.counters; A.phase_hist = P.phase_hist; A.unassigned = P.unassigned;
+    A.n_samples = P.n_samples; A.pb = P.phase_bins; A.joint = P.phase_joint;
+    return A;
 }
 
 #ifndef SCAR_K4_CTAS
@@ -162,8 +30,9 @@ __device__ __forceinline__ void k4_flush(const K4Params &P, unsigned int *s_hist
 __global__ void __launch_bounds__(256, SCAR_K4_CTAS) scar_aggregate_kernel(const K4Params P)
 {
     extern __shared__ __align__(8) unsigned int s_hist[];
-    const int pb = P.phase_joint;                       // 0: separate marginals
-    const int per_sample = K4_FIXED_WORDS + (pb ? pb * pb : 2 * SCAR_PHASE_BINS);
+    const ScarTableRef T = table_ref(P);
+    const ScarAccRef A = acc_ref(P);
+    const int per_sample = acc_words_per_sample(A.pb, A.joint);
     __shared__ unsigned int s_unassigned, s_new;
     if (P.use_smem) {
         for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) s_hist[i] = 0;
@@ -176,7 +45,7 @@ __global__ void __launch_bounds__(256, SCAR_K4_CTAS) scar_aggregate_kernel(const
         const int64_t r = base + threadIdx.x;
         if (P.use_smem && ++iter > K4_EPOCH_ITERS) {
             __syncthreads();
-            k4_flush(P, s_hist, per_sample, pb);
+            acc_flush(A, s_hist, per_sample);
             __syncthreads();
             iter = 1;
         }
@@ -188,65 +57,8 @@ __global__ void __launch_bounds__(256, SCAR_K4_CTAS) scar_aggregate_kernel(const
         // ---- counters (summary_data, read_count_dict, phase_count)
         if (in_range) {
             if (rec.status == SCAR_ST_UNASSIGNED) atomicAdd(&s_unassigned, 1u);
-            else {
-                const uint32_t s = rec.sample;
-                const bool scar = rec.status == SCAR_ST_SCAR;
-                const int b1 = rec.phase_r1 == SCAR_PHASE_NA ? SCAR_PHASE_BINS - 1 : rec.phase_r1 + 1;
-                const int b2 = rec.phase_r2 == SCAR_PHASE_NA ? SCAR_PHASE_BINS - 1 : rec.phase_r2 + 1;
-                if (P.use_smem) {
-                    unsigned long long a = 1ull, b = 0ull, c = 0ull;
-                    if (rec.status >= SCAR_ST_NO_JUNCTION) a |= 1ull << 16;
-                    if (rec.status == SCAR_ST_FILTERED) a |= 1ull << 32;
-                    if (rec.status == SCAR_ST_NO_JUNCTION) a |= 1ull << 48;
-                    if (rec.status == SCAR_ST_NO_CUT) b |= 1ull;
-                    if (rec.status == SCAR_ST_N_INSERTION) b |= 1ull << 16;
-                    if (scar) {
-                        b |= 1ull << 32;
-                        if (rec.flags & SCAR_FL_LEFT_DEL) b |= 1ull << 48;
-                        if (rec.flags & SCAR_FL_RIGHT_DEL) c |= 1ull;
-                        if (rec.flags & SCAR_FL_INSERTION) c |= 1ull << 16;
-                        if (rec.flags & SCAR_FL_MICROHOM) c |= 1ull << 32;
-                    }
-                    if (rec.hr_n) c |= 1ull << 48;
-                    // 32-bit shared atomics (two 16-bit counters each); 64-bit shared atomics are a CAS loop
-                    unsigned int *h = s_hist + s * per_sample;
-                    atomicAdd(h, (unsigned int)a);
-                    if (a >> 32) atomicAdd(h + 1, (unsigned int)(a >> 32));
-                    if ((unsigned int)b) atomicAdd(h + 2, (unsigned int)b);
-                    if (b >> 32) atomicAdd(h + 3, (unsigned int)(b >> 32));
-                    if ((unsigned int)c) atomicAdd(h + 4, (unsigned int)c);
-                    if (c >> 32) atomicAdd(h + 5, (unsigned int)(c >> 32));
-                    if (rec.hr_n > 1) atomicAdd(h + 6, (unsigned)(rec.hr_n - 1));
-                    if (pb) {
-                        const int j1 = b1 == SCAR_PHASE_BINS - 1 ? pb - 1 : b1, j2 = b2 == SCAR_PHASE_BINS - 1 ? pb - 1 : b2;
-                        atomicAdd(h + K4_FIXED_WORDS + j1 * pb + j2, 1u);
-                    } else {
-                        atomicAdd(h + K4_FIXED_WORDS + b1, 1u);
-                        atomicAdd(h + K4_FIXED_WORDS + SCAR_PHASE_BINS + b2, 1u);
-                    }
-                } else {
-                    uint32_t inc = 1u << SCAR_CT_ASSIGNED;
-                    if (rec.status >= SCAR_ST_NO_JUNCTION) inc |= 1u << SCAR_CT_PASSING;
-                    if (rec.status == SCAR_ST_FILTERED) inc |= 1u << SCAR_CT_FILTERED;
-                    if (rec.status == SCAR_ST_NO_JUNCTION) inc |= 1u << SCAR_CT_NO_JUNCTION;
-                    if (rec.status == SCAR_ST_NO_CUT) inc |= 1u << SCAR_CT_NO_CUT;
-                    if (rec.status == SCAR_ST_N_INSERTION) inc |= 1u << SCAR_CT_N_INSERTION;
-                    if (scar) {
-                        inc |= 1u << SCAR_CT_SCAR;
-                        if (rec.flags & SCAR_FL_LEFT_DEL) inc |= 1u << SCAR_CT_LEFT_DEL;
-                        if (rec.flags & SCAR_FL_RIGHT_DEL) inc |= 1u << SCAR_CT_RIGHT_DEL;
-                        if (rec.flags & SCAR_FL_INSERTION) inc |= 1u << SCAR_CT_INSERTION;
-                        if (rec.flags & SCAR_FL_MICROHOM) inc |= 1u << SCAR_CT_MICROHOM;
-                    }
-                    if (rec.hr_n) inc |= 1u << SCAR_CT_HR_FIRST;
-                    unsigned long long *cnt = P.counters + (size_t)s * SCAR_N_COUNTERS;
-                    for (uint32_t m = inc; m; m &= m - 1) atomicAdd(cnt + (__ffs(m) - 1), 1ull);
-                    if (rec.hr_n > 1) atomicAdd(cnt + SCAR_CT_HR_MORE, (unsigned long long)(rec.hr_n - 1));
-                    unsigned long long *ph = P.phase_hist + (size_t)s * 2 * SCAR_PHASE_BINS;
-                    atomicAdd(ph + b1, 1ull);
-                    atomicAdd(ph + SCAR_PHASE_BINS + b2, 1ull);
-                }
-            }
+            else if (P.use_smem) acc_add_smem(s_hist, per_sample, A.pb, A.joint, rec);
+            else acc_add_global(A, rec);
         }
 
         // ---- scar table: every SCAR read inserts its own key.  (Combining equal keys inside a warp with
@@ -257,11 +69,11 @@ __global__ void __launch_bounds__(256, SCAR_K4_CTAS) scar_aggregate_kernel(const
             get_item(P.seq, r, raw, rawlen);
             uint64_t h1, h2;
             key_hashes(rec, raw, rawlen, P.platform, h1, h2);
-            if (table_insert(P, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample)) atomicAdd(&s_new, 1u);
+            if (table_insert(T, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample)) atomicAdd(&s_new, 1u);
         }
     }
     __syncthreads();
-    if (P.use_smem) k4_flush(P, s_hist, per_sample, pb);
+    if (P.use_smem) acc_flush(A, s_hist, per_sample);
     if (threadIdx.x == 0 && s_unassigned) atomicAdd(P.unassigned, (unsigned long long)s_unassigned);
     if (threadIdx.x == 0 && s_new) atomicAdd(P.n_entries, (unsigned long long)s_new);
 }
@@ -346,7 +158,7 @@ __global__ void scar_merge_kernel(K4Params P, const scar_entry *in, uint64_t n_i
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const scar_entry e = in[i];
-        if (table_insert(P, e.h1, e.h2, e.count, e.first_idx, e.sample)) atomicAdd(P.n_entries, 1ull);
+        if (table_insert(table_ref(P), e.h1, e.h2, e.count, e.first_idx, e.sample)) atomicAdd(P.n_entries, 1ull);
     }
 }
 
@@ -471,7 +283,7 @@ __global__ void scar_merge_parts_kernel(K4Params P, const scar_entry *in, uint32
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt;
              i += (uint64_t)gridDim.x * blockDim.x) {
             const scar_entry e = reg[1 + i];
-            if (table_insert(P, e.h1, e.h2, e.count, e.first_idx, e.sample)) atomicAdd(&s_new, 1u);
+            if (table_insert(table_ref(P), e.h1, e.h2, e.count, e.first_idx, e.sample)) atomicAdd(&s_new, 1u);
         }
     }
     __syncthreads();
@@ -500,8 +312,7 @@ cudaError_t scar_launch_aggregate(K4Params P, int sm_count, cudaStream_t stream,
 {
     if (P.n_reads <= 0) return cudaSuccess;
     const int threads = 256;
-    const int pb = P.phase_joint;
-    const size_t per_sample = (K4_FIXED_WORDS + (pb ? pb * pb : 2 * SCAR_PHASE_BINS)) * sizeof(unsigned int);
+    const size_t per_sample = (size_t)acc_words_per_sample(P.phase_bins, P.phase_joint) * sizeof(unsigned int);
     size_t smem = (size_t)P.n_samples * per_sample;
     P.use_smem = smem <= 96 * 1024;
     if (!P.use_smem) smem = 0;

@@ -21,9 +21,10 @@
 //
 //   left  search: positions p = len-20 .. 16 descending, first hit -> clj = p+10, tlj = cut - i
 //   right search: positions p = 10 .. len-26 ascending,  first hit -> crj = p,    trj = cut + i
+#include <algorithm>
 #include <cstdlib>
 
-#include "scar_internal.cuh"
+#include "scar_table_core.cuh"
 
 #ifndef SCAR_ANCHOR_BATCH
 #define SCAR_ANCHOR_BATCH 14
@@ -417,11 +418,100 @@ __device__ __forceinline__ void queue_push(bool pending, uint32_t item, uint32_t
     if (pending) queue[dir * (int)(base + __popc(mask & ((1u << lane) - 1u)))] = item;
 }
 
-template <bool SMEM, bool HR, bool ST>
-__global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(const K3Params P)
+// ---- fused mode: the tile's RAW bytes are staged in shared memory and packed there (what K1 does into HBM) ----
+// One read -> WMAX cells in registers.  STAGED: the raw bytes are in shared memory at byte address `saddr` (the
+// buffer is readable 32 bytes past the tile's span, so no load needs a bounds check); otherwise they are read from
+// global memory at `gp`, never touching a word outside the read.  `slen` bases are packed (<= 16 * WMAX), bases past
+// it are zero.  Returns the number of literal 'N' bytes.
+template <int WMAX, bool STAGED>
+__device__ __forceinline__ int pack_cells(uint32_t saddr, const uint8_t *gp, int slen, uint64_t (&pc)[WMAX])
 {
+    const uint32_t mis = STAGED ? (saddr & 3u) : (uint32_t)((uintptr_t)gp & 3u);
+    const uint32_t sh = mis * 8u;
+    const uint32_t a4 = saddr & ~3u;
+    const uint32_t *g4 = reinterpret_cast<const uint32_t *>((uintptr_t)gp & ~(uintptr_t)3);
+    const int kend = ((int)mis + slen + 3) >> 2;        // aligned words that overlap the read (global path)
+    auto ld = [&](int k) -> uint32_t {
+        uint32_t w = 0u;
+        if (STAGED) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(a4 + 4u * (uint32_t)k));
+        else if (k < kend) w = __ldg(g4 + k);
+        return w;
+    };
+    uint32_t wp = ld(0);
+    int n_count = 0;
+#pragma unroll
+    for (int j = 0; j < WMAX; ++j) {
+        const int nb = slen - 16 * j;                   // bases of this cell (may exceed 16)
+        uint64_t cell = 0ull;
+        if (nb > 0) {
+            const uint32_t w1 = ld(4 * j + 1), w2 = ld(4 * j + 2), w3 = ld(4 * j + 3), w4 = ld(4 * j + 4);
+            uint32_t v[4];
+            v[0] = __funnelshift_r(wp, w1, sh); v[1] = __funnelshift_r(w1, w2, sh);
+            v[2] = __funnelshift_r(w2, w3, sh); v[3] = __funnelshift_r(w3, w4, sh);
+            wp = w4;
+            // 2-bit codes: (w>>1)&3 per byte, gathered into the top byte by one multiply per word
+            uint32_t pt[4], x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { pt[i] = codes_to_top_byte(v[i]); x[i] = acgt_diff4(v[i]); }
+            uint32_t code = __byte_perm(__byte_perm(pt[0], pt[1], 0x0073), __byte_perm(pt[2], pt[3], 0x0073), 0x5410);
+            uint32_t valid = 0xFFFFu, nmask = 0u;
+            if (nb < 16 || (x[0] | x[1] | x[2] | x[3]) != 0u) {       // rare: last cell, or a non-ACGT byte
+                valid = 0u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    valid |= flags_to_nibble(zero_bytes(x[i])) << (4 * i);
+                    nmask |= flags_to_nibble(zero_bytes(v[i] ^ 0x4E4E4E4Eu)) << (4 * i);
+                }
+                const uint32_t bm = nb >= 16 ? 0xFFFFu : ((1u << nb) - 1u);
+                valid &= bm; nmask &= bm;
+                n_count += __popc(nmask);
+                // spread the ACGT mask to 2 bits per base to clear the codes of non-ACGT / absent bases
+                uint32_t m2 = valid;
+                m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
+                m2 = (m2 | (m2 << 2)) & 0x33333333u; m2 = (m2 | (m2 << 1)) & 0x55555555u;
+                code &= m2 * 3u;
+            }
+            cell = (uint64_t)code | ((uint64_t)valid << 32) | ((uint64_t)nmask << 48);
+        }
+        pc[j] = cell;
+    }
+    return n_count;
+}
+
+// smallest start / largest end address over the threads with `mine` (CTA-wide; contains two barriers)
+__device__ __forceinline__ void span_reduce(bool mine, const uint8_t *rp, int len, unsigned long long (*s_red)[8],
+                                            unsigned long long &lo, unsigned long long &hi)
+{
+    unsigned long long a = mine ? (unsigned long long)(uintptr_t)rp : ~0ull;
+    unsigned long long b = mine ? (unsigned long long)(uintptr_t)rp + (unsigned long long)len : 0ull;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const unsigned long long a2 = __shfl_xor_sync(0xFFFFFFFFu, a, d), b2 = __shfl_xor_sync(0xFFFFFFFFu, b, d);
+        a = a2 < a ? a2 : a; b = b2 > b ? b2 : b;
+    }
+    __syncthreads();                                  // s_red may still be read from the previous use
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = a; s_red[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    lo = s_red[0][0]; hi = s_red[1][0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { lo = s_red[0][i] < lo ? s_red[0][i] : lo; hi = s_red[1][i] > hi ? s_red[1][i] : hi; }
+}
+
+// MODE 0: the packed cells are read from global memory (cell-major)          } input = K1's packed batch
+// MODE 1: the tile's packed cells are first copied into shared memory        }
+// MODE 2: FUSED - input = raw read bytes: the tile's raw span is staged in shared memory by TMA bulk copies, packed
+//         there (the cells overwrite the raw bytes), classified, and in phase 3 the per-sample accumulators and the
+//         scar table are updated as well (what K1, K3 and K4 do in three passes over HBM).
+#ifndef SCAR_FUSED_MIN_CTAS
+#define SCAR_FUSED_MIN_CTAS 3
+#endif
+template <bool SMEM, bool HR, int MODE, int WMAX>
+__global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (WMAX > 10 ? 2 : SCAR_FUSED_MIN_CTAS) : SCAR_K3_MIN_CTAS) scar_window_kernel(const K3Params P)
+{
+    constexpr bool ST = MODE >= 1;      // the tile's cells live in shared memory
+    constexpr bool FUSED = MODE == 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [mbarrier 16 B][static blob: tables | target metas | phases | N-limit table]
+    // layout: [2 mbarriers 16 B][static blob: tables | target metas | phases | N-limit table][tile buffer][accumulators]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     const unsigned char *blob = reinterpret_cast<const unsigned char *>(P.blob);
     if (SMEM) {
@@ -433,9 +523,11 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
     const uint16_t *nmax = reinterpret_cast<const uint16_t *>(blob + P.nmax_off);
     const int64_t S = P.stride;      // reads per cell row
     using RC = ReadCursorT<ST>;
-    // ST: the tile's cells (W rows of 256 x 8 bytes) live in shared memory behind the blob; every thread copies
-    // its own read's cells there with asynchronous 8-byte copies (no registers, all W in flight at once)
-    uint64_t *s_cells = reinterpret_cast<uint64_t *>(smem_raw + 16 + (SMEM ? P.blob_bytes : 0u));
+    // ST: the tile's cells (W rows of 256 x 8 bytes) live in shared memory behind the blob.  MODE 1: every thread
+    // copies its own read's cells there with asynchronous 8-byte copies (no registers, all W in flight at once).
+    // MODE 2: the same buffer first receives the tile's raw bytes.
+    unsigned char *tile_buf = smem_raw + 16 + (SMEM ? P.blob_bytes : 0u);
+    uint64_t *s_cells = reinterpret_cast<uint64_t *>(tile_buf);
 
     // A CTA takes tiles of 256 reads.  Phase 1 is one thread per read: phasing, filters, and the FIRST anchor
     // step of both junction searches (a wild-type read is finished there).  Searches that are still open
@@ -447,29 +539,133 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
     __shared__ uint32_t s_ctx[K3_TILE];                      // stored length | target id << 16
     __shared__ uint32_t s_queue[2][2 * K3_TILE];             // item = local read | p << 8
     __shared__ uint32_t s_count[3][2];                       // [round % 3][side]
+    __shared__ unsigned long long s_red[2][8];               // fused: span reduction
+    __shared__ unsigned int s_unassigned, s_new;             // fused: aggregation
     if (threadIdx.x < 6) s_count[threadIdx.x >> 1][threadIdx.x & 1] = 0;
+
+    // ---- fused: accumulators of the aggregation, raw-span barrier
+    unsigned int *s_hist = nullptr;
+    int per_sample = 0;
+    ScarTableRef TB; ScarAccRef AC;
+    uint32_t raw_parity = 0;
+    if (FUSED) {
+        if (threadIdx.x == 0) {
+            s_unassigned = 0; s_new = 0;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 1)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        TB.slots = P.slots; TB.slot_mask = P.slot_mask; TB.max_probe = P.max_probe; TB.status = P.status;
+        AC.counters = P.counters; AC.phase_hist = P.phase_hist; AC.unassigned = P.unassigned; AC.n_samples = P.n_samples;
+        AC.pb = P.phase_bins; AC.joint = P.phase_joint;
+        per_sample = acc_words_per_sample(AC.pb, AC.joint);
+        const uint32_t buf_bytes = max(P.raw_cap + 32u, (uint32_t)P.W * K3_TILE * 8u);
+        s_hist = reinterpret_cast<unsigned int *>(tile_buf + ((buf_bytes + 15u) & ~15u));
+        if (P.aggregate && P.hist_smem)
+            for (int i = threadIdx.x; i < P.n_samples * per_sample; i += K3_TILE) s_hist[i] = 0;
+    }
     __syncthreads();
     uint32_t round = 0;
+    int epoch = 0;
 
     for (int64_t tile = (int64_t)blockIdx.x * K3_TILE; tile < P.n_reads; tile += (int64_t)gridDim.x * K3_TILE) {
         const int64_t r = tile + threadIdx.x;
         bool live = r < P.n_reads;
-        if (ST && live) {
+        const bool in_range = live;
+        uint32_t info = 0u;                                     // stored length | N count << 16
+        if (MODE == 1 && live) {
             const uint64_t *src = P.cells + r;
             uint32_t dst = smem_u32(s_cells + threadIdx.x);
             for (int j = 0; j < P.W; ++j, src += S, dst += K3_TILE * 8)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
+        if (FUSED) {
+            // ---- K1 in shared memory.  The raw bytes of the tile are one contiguous span of the input (CSR / fixed
+            // stride; FASTQ views in file order): TMA bulk copies bring it in - in 2, 4 or 8 passes over 128, 64 or
+            // 32 reads when the span is wider than the buffer (FASTQ text: the reads are a third of the bytes) - and
+            // each thread packs ITS read into registers; when every thread has read its bytes the cells are stored
+            // over them.  A span that still does not fit (scattered views) is read from global memory.
+            if (P.aggregate && P.hist_smem && ++epoch > K4_EPOCH_ITERS) {      // 16-bit packed counters: flush in time
+                __syncthreads();
+                acc_flush(AC, s_hist, per_sample);
+                epoch = 1;
+            }
+            const uint8_t *rp = P.seq.bytes; int rawlen = 0;
+            if (in_range) get_item(P.seq, r, rp, rawlen);
+            int slen = rawlen, shift = 0;
+            if (P.platform == SCAR_PLATFORM_TRUSEQ) { slen = rawlen > 12 ? rawlen - 12 : 0; shift = 6; }
+            if (slen > 16 * P.W) { atomicOr(P.status, 1); slen = 16 * P.W; }
+            const bool views = P.seq.offsets && P.seq.lengths;
+            auto span_of = [&](int64_t a, int64_t b, bool mine, unsigned long long &lo, unsigned long long &hi) {
+                if (views) { span_reduce(mine, rp, rawlen, s_red, lo, hi); return; }
+                __syncthreads();                          // s_red may still be read from the previous use
+                if (threadIdx.x == 0) {
+                    if (b >= P.n_reads) b = P.n_reads - 1;
+                    unsigned long long x = ~0ull, y = 0ull;
+                    if (a <= b) {
+                        const uint8_t *q0, *q1; int l0, l1;
+                        get_item(P.seq, a, q0, l0);
+                        get_item(P.seq, b, q1, l1);
+                        x = (unsigned long long)(uintptr_t)q0; y = (unsigned long long)(uintptr_t)q1 + (unsigned long long)l1;
+                    }
+                    s_red[0][0] = x; s_red[1][0] = y;
+                }
+                __syncthreads();
+                lo = s_red[0][0]; hi = s_red[1][0];
+            };
+            unsigned long long lo, hi;
+            span_of(tile, tile + K3_TILE - 1, in_range, lo, hi);     // (the barrier inside also ends the previous tile)
+            int passes = 1;
+            {
+                const unsigned long long whole = hi > lo ? hi - (lo & ~15ull) + 15ull : 0ull;
+                while (passes < 8 && whole > (unsigned long long)passes * (P.raw_cap - 64u)) passes *= 2;
+            }
+            const int sub_shift = 8 - (31 - __clz(passes)), sub = 1 << sub_shift;      // K3_TILE = 256
+            uint64_t pc[WMAX];
+            int n_count = 0;
+            for (int ps = 0; ps < passes; ++ps) {
+                const bool mine = in_range && ((int)threadIdx.x >> sub_shift) == ps;
+                if (passes > 1) span_of(tile + (int64_t)ps * sub, tile + (int64_t)(ps + 1) * sub - 1, mine, lo, hi);
+                const unsigned long long lo16 = lo & ~15ull;
+                const unsigned long long span = hi > lo16 ? ((hi - lo16 + 15ull) & ~15ull) : 0ull;
+                const bool staged = span != 0ull && span <= (unsigned long long)P.raw_cap;
+                if (staged) {
+                    if (threadIdx.x == 0) {
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + 1)),
+                                     "r"((uint32_t)span) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(smem_u32(tile_buf)), "l"(lo16), "r"((uint32_t)span), "r"(smem_u32(bar + 1)) : "memory");
+                    }
+                    uint32_t done = 0;
+                    while (!done) {
+                        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                                     "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(bar + 1)), "r"(raw_parity) : "memory");
+                    }
+                    raw_parity ^= 1u;
+                }
+                if (mine) {
+                    const uint8_t *sp = rp + shift;
+                    if (staged) n_count = pack_cells<WMAX, true>(smem_u32(tile_buf) + (uint32_t)((unsigned long long)(uintptr_t)sp - lo16), sp, slen, pc);
+                    else n_count = pack_cells<WMAX, false>(0u, sp, slen, pc);
+                }
+                __syncthreads();                          // every thread has read its raw bytes: the buffer is reused
+            }
+            if (in_range) {
+#pragma unroll
+                for (int j = 0; j < WMAX; ++j)
+                    if (j < P.W) s_cells[j * K3_TILE + threadIdx.x] = pc[j];
+            }
+            info = (uint32_t)slen | ((uint32_t)n_count << 16);
+        }
         __align__(16) scar_record rec;
         rec.status = SCAR_ST_UNASSIGNED; rec.flags = 0; rec.sample = SCAR_SAMPLE_NONE;
         rec.clj = rec.crj = rec.tlj = rec.trj = 0; rec.hr_n = 0;
         rec.phase_r1 = SCAR_PHASE_NA; rec.phase_r2 = SCAR_PHASE_NA;
-        const bool in_range = live;
         const uint32_t sample = live ? (uint32_t)P.samples[r] : 0xFFFFu;
         if (sample >= (uint32_t)P.n_samples) live = false;      // unidentified (INDEL_Processing.py:1194-1198)
         else rec.sample = (uint16_t)sample;
-        const uint32_t info = live ? P.lens[r] : 0u;             // stored length | N count << 16 (from K1)
+        if (!FUSED) info = live ? P.lens[r] : 0u;                // stored length | N count << 16 (from K1)
+        if (!live) info = 0u;
         const int len = (int)(info & 0xFFFFu);
         const int tid = live ? __ldg(P.sample_target + sample) : 0;
         const ScarTargetMeta &T = metas[tid];
@@ -478,18 +674,18 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
         const int cut = T.cutsite;
         int clj = 0, crj = 0, tlj = cut, trj = cut;
         RC rc0; rc0.col = col; rc0.S = S; rc0.sc = s_cells + threadIdx.x; rc0.Wr = Wr;
-        if (ST) asm volatile("cp.async.wait_all;" ::: "memory");
+        if (MODE == 1) asm volatile("cp.async.wait_all;" ::: "memory");
 
         if (live) {
             const int n_count = (int)(info >> 16);
             // ---- phasing (INDEL_Processing.py:948-975): first k matching the prefix / the suffix.
             // The first 16 bases and the last 16 bases are extracted once; a phase is a shift + compare.
             if (P.do_phasing && T.n_phase > 0) {
-                const RC &pc = rc0;
+                const RC &pc0 = rc0;
                 uint32_t hcode, hvalid, scode, svalid;
-                pc.word16(0, hcode, hvalid);
+                pc0.word16(0, hcode, hvalid);
                 const int sb = len > 16 ? len - 16 : 0;          // suffix window = bases sb .. sb+15
-                pc.word16(sb, scode, svalid);
+                pc0.word16(sb, scode, svalid);
                 int f1 = -1, f2 = -1;
                 if (T.ph_lut_off) {
                     // every non-empty phase string of a side has the same length (<= 6): the first matching
@@ -757,6 +953,41 @@ __global__ void __launch_bounds__(K3_TILE, SCAR_K3_MIN_CTAS) scar_window_kernel(
             }
         }
         if (in_range) store_record(P.records + r, rec);
+
+        // ---- fused: stage 4 (INDEL_Processing.py:186-196 and the summary / phasing bookkeeping), what K4 does from
+        // the records in a second pass.  The key's segment is hashed from the packed cells in shared memory; only a
+        // segment with a non-ACGT byte goes back to the raw read.
+        if (FUSED && P.aggregate && in_range) {
+            if (rec.status == SCAR_ST_UNASSIGNED) atomicAdd(&s_unassigned, 1u);
+            else if (P.hist_smem) acc_add_smem(s_hist, per_sample, AC.pb, AC.joint, rec);
+            else acc_add_global(AC, rec);
+            if (rec.status == SCAR_ST_SCAR) {
+                const KeySegment ks = key_segment(rec);
+                uint64_t h1, h2;
+                key_init(ks.hdr, h1, h2);
+                bool acgt = true;
+                for (int q = ks.lo; q < ks.hi; q += 32) {
+                    const int n = min(32, ks.hi - q);
+                    const Word32 w = read32(rc0, q);
+                    const uint32_t vm = n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+                    acgt = acgt && (w.valid & vm) == vm;
+                    key_step(n == 32 ? w.code : (w.code & ((1ull << (2 * n)) - 1ull)), h1, h2);
+                }
+                if (acgt) key_finish(h1, h2);
+                else {
+                    const uint8_t *raw; int rawlen;
+                    get_item(P.seq, r, raw, rawlen);
+                    key_hashes_bytes(ks, raw, rawlen, P.platform, h1, h2);
+                }
+                if (table_insert(TB, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample)) atomicAdd(&s_new, 1u);
+            }
+        }
+    }
+    if (FUSED && P.aggregate) {
+        __syncthreads();
+        if (P.hist_smem) acc_flush(AC, s_hist, per_sample);
+        if (threadIdx.x == 0 && s_unassigned) atomicAdd(P.unassigned, (unsigned long long)s_unassigned);
+        if (threadIdx.x == 0 && s_new) atomicAdd(P.n_entries, (unsigned long long)s_new);
     }
 }
 
@@ -776,11 +1007,11 @@ static cudaError_t plan_window(const K3Params &P, bool smem_tables, K3Plan &plan
     plan.smem = smem_base + (plan.stage ? cell_bytes : 0);
     const bool hr = P.hr_len > 0;
     if (plan.stage)
-        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, true> : scar_window_kernel<true, false, true>)
-                                : (hr ? scar_window_kernel<false, true, true> : scar_window_kernel<false, false, true>);
+        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 1, 1> : scar_window_kernel<true, false, 1, 1>)
+                                : (hr ? scar_window_kernel<false, true, 1, 1> : scar_window_kernel<false, false, 1, 1>);
     else
-        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, false> : scar_window_kernel<true, false, false>)
-                                : (hr ? scar_window_kernel<false, true, false> : scar_window_kernel<false, false, false>);
+        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 0, 1> : scar_window_kernel<true, false, 0, 1>)
+                                : (hr ? scar_window_kernel<false, true, 0, 1> : scar_window_kernel<false, false, 0, 1>);
     cudaError_t e = cudaFuncSetAttribute(plan.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return e;
     plan.per_sm = 0;
@@ -812,6 +1043,82 @@ cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count
     cudaError_t e = plan_window(P, smem_tables, plan);
     if (e != cudaSuccess) return e;
     // persistent grid: a whole number of resident CTAs per SM, never more than the work needs
+    int64_t want = (P.n_reads + threads - 1) / threads;
+    int64_t grid = (int64_t)sm_count * plan.per_sm;
+    if (grid > want) grid = want;
+    plan.kern<<<(unsigned)grid, threads, plan.smem, stream>>>(P);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// ---- fused K1 + K3 (+ K4) from raw bytes ----------------------------------------------------------------
+bool scar_fused_eligible(int W, int platform)
+{
+    // reads up to 320 nt (20 cells held in registers while the raw bytes are overwritten); the Ramsden platform
+    // stores the reverse complement of the read and stays on the K1 -> K3 -> K4 path
+    return W <= 20 && platform != SCAR_PLATFORM_RAMSDEN && getenv("SCAR_NO_FUSE") == nullptr;
+}
+
+static cudaError_t plan_fused(K3Params &P, bool smem_tables, int max_read_len, K3Plan &plan)
+{
+    const int threads = K3_TILE;
+    // raw staging buffer: one tile of fixed-stride reads of the longest length fits in one pass
+    const int raw_len = max_read_len + (P.platform == SCAR_PLATFORM_TRUSEQ ? 12 : 0);
+    // (long reads: at most ~40 KB, i.e. two passes for 300-nt reads - the packed cells need that much anyway)
+    const uint32_t cells_bytes = (uint32_t)P.W * threads * 8u;
+    uint32_t raw_cap = std::min<uint32_t>((uint32_t)threads * (uint32_t)raw_len + 48u, 40u * 1024u);
+    raw_cap = (std::max<uint32_t>(raw_cap, cells_bytes > 32u ? cells_bytes - 32u : 0u) + 15u) & ~15u;
+    if (const char *e = getenv("SCAR_FUSED_RAW_BYTES")) { const long v = atol(e); if (v >= 1024) raw_cap = ((uint32_t)v + 15u) & ~15u; }
+    P.raw_cap = raw_cap;
+    const size_t buf = ((size_t)std::max<uint32_t>(raw_cap + 32u, (uint32_t)P.W * threads * 8u) + 15) & ~(size_t)15;
+    const size_t base = 16 + (smem_tables ? P.blob_bytes : 0) + buf;
+    // accumulators: joint phase histogram when it is small, else two marginals; global atomics when neither fits
+    P.hist_smem = 0;
+    size_t hist = 0;
+    if (P.aggregate) {
+        const size_t budget = 227 * 1024 - 8192;
+        for (int joint = P.phase_bins * P.phase_bins <= 32 ? 1 : 0; joint >= 0 && !P.hist_smem; --joint) {
+            const size_t h = (size_t)P.n_samples * acc_words_per_sample(P.phase_bins, joint) * sizeof(unsigned int);
+            if (h <= 48 * 1024 && base + h <= budget) { P.hist_smem = 1; P.phase_joint = joint; hist = h; }
+        }
+    }
+    plan.stage = true;
+    plan.smem = base + hist;
+    if (plan.smem > 227 * 1024 - 8192) return cudaErrorInvalidConfiguration;
+    const bool hr = P.hr_len > 0, w10 = P.W <= 10;
+    if (w10)
+        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 10> : scar_window_kernel<true, false, 2, 10>)
+                                : (hr ? scar_window_kernel<false, true, 2, 10> : scar_window_kernel<false, false, 2, 10>);
+    else
+        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 20> : scar_window_kernel<true, false, 2, 20>)
+                                : (hr ? scar_window_kernel<false, true, 2, 20> : scar_window_kernel<false, false, 2, 20>);
+    cudaError_t e = cudaFuncSetAttribute(plan.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (e != cudaSuccess) return e;
+    plan.per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plan.per_sm, plan.kern, threads, plan.smem);
+    if (e != cudaSuccess) return e;
+    if (plan.per_sm < 1) plan.per_sm = 1;
+    if (const char *e2 = getenv("SCAR_K3_CTAS_PER_SM")) { const int v = atoi(e2); if (v >= 1 && v < plan.per_sm) plan.per_sm = v; }
+    return cudaSuccess;
+}
+
+cudaError_t scar_fused_plan(K3Params P, bool smem_tables, int max_read_len, int *per_sm, int *smem_bytes)
+{
+    K3Plan plan;
+    cudaError_t e = plan_fused(P, smem_tables, max_read_len, plan);
+    if (e != cudaSuccess) return e;
+    if (per_sm) *per_sm = plan.per_sm;
+    if (smem_bytes) *smem_bytes = (int)plan.smem;
+    return cudaSuccess;
+}
+
+cudaError_t scar_launch_fused(K3Params P, bool smem_tables, int max_read_len, int sm_count, cudaStream_t stream, int *launches)
+{
+    if (P.n_reads <= 0) return cudaSuccess;
+    const int threads = K3_TILE;
+    K3Plan plan;
+    cudaError_t e = plan_fused(P, smem_tables, max_read_len, plan);
+    if (e != cudaSuccess) return e;
     int64_t want = (P.n_reads + threads - 1) / threads;
     int64_t grid = (int64_t)sm_count * plan.per_sm;
     if (grid > want) grid = want;

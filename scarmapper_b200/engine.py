@@ -204,8 +204,11 @@ class ScarEngine:
         N.check(self._L.scar_ctx_info(self._ctx, C.byref(b), C.byref(s), C.byref(k)))
         st, per, sm = C.c_int32(), C.c_int32(), C.c_int32()
         N.check(self._L.scar_k3_plan(self._ctx, C.byref(st), C.byref(per), C.byref(sm)))
+        fe, fper, fsm = C.c_int32(), C.c_int32(), C.c_int32()
+        N.check(self._L.scar_fused_info(self._ctx, C.byref(fe), C.byref(fper), C.byref(fsm)))
         return {"static_bytes": b.value, "tables_in_smem": bool(s.value), "anchor_targets": k.value,
-                "k3_stage": bool(st.value), "k3_ctas_per_sm": per.value, "k3_smem_bytes": sm.value}
+                "k3_stage": bool(st.value), "k3_ctas_per_sm": per.value, "k3_smem_bytes": sm.value,
+                "fused": bool(fe.value), "fused_ctas_per_sm": fper.value, "fused_smem_bytes": fsm.value}
 
     def window_counts(self, target: int):
         a, b = C.c_int32(), C.c_int32()
@@ -291,6 +294,12 @@ class ScarEngine:
         N.check(self._L.scar_classify_dev(self._ctx, batch["cells"].data_ptr(), batch["lens"].data_ptr(),
                                           batch["samples"].data_ptr(), batch["n"], batch["records"].data_ptr(),
                                           self._stream()))
+
+    def classify_raw_resident(self, batch, first_index: int = 0, aggregate: bool = True):
+        """The fused kernel: raw bytes -> records (+ counters, phase histograms, scar table) in one pass."""
+        s = self._dev_ragged(batch["seq"])
+        N.check(self._L.scar_classify_raw_dev(self._ctx, C.byref(s), batch["samples"].data_ptr(), batch["n"], first_index,
+                                              batch["records"].data_ptr(), 1 if aggregate else 0, self._stream()))
 
     def aggregate_resident(self, batch, first_index: int = 0):
         s = self._dev_ragged(batch["seq"])

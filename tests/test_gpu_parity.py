@@ -612,8 +612,9 @@ def test_dropin_glue_on_gpu_from_fastq_file(name, tmp_path):
     """scarmapper_b200.dropin.batched_consensus_demultiplex with the REAL engine, fed from a gz FASTQ file
     and the reference's input file formats, driven through stand-ins for the reference objects it touches
     (index_dict, target_dict, phase_dict, args, a FastaFile reader).  What it hands back - read_count_dict,
-    phase_count, per-sample SampleResult (counters, table with the first read's sub_list, read_results) -
-    must equal what the unmodified reference driver produced (golden)."""
+    phase_count, per-sample SampleResult (counters, table with the first read's sub_list) - must equal what the
+    unmodified reference driver produced (golden).  (The files, Raw_Data included, are compared by
+    tests/test_dropin_forking_pool.py through the launcher.)"""
     import argparse
     import collections
     import sys
@@ -629,7 +630,7 @@ def test_dropin_glue_on_gpu_from_fastq_file(name, tmp_path):
     make_golden.write_inputs(wd, case)
     args = argparse.Namespace(
         WorkingFolder=wd, Job_Name="g", Verbose="ERROR", Platform=case["platform"], PEAR=True, Demultiplex=False,
-        HR_Donor=case["hr_donor"], N_Limit=case["n_limit"], Minimum_Length=case["min_length"], OutputRawData=True,
+        HR_Donor=case["hr_donor"], N_Limit=case["n_limit"], Minimum_Length=case["min_length"], OutputRawData=False,
         PatternThreshold=0.0001, RefSeq=wd + "refseq.fa", FASTQ1=wd + "reads.fastq.gz")
 
     # stand-ins shaped like the reference's objects (DataProcessing.dictionary_build / TargetMapper)
@@ -646,9 +647,12 @@ def test_dropin_glue_on_gpu_from_fastq_file(name, tmp_path):
             phase_dict[t]["R1"] = [[p, "F%d" % k] for k, p in enumerate(r1)]
             phase_dict[t]["R2"] = [[p, "R%d" % k] for k, p in enumerate(r2)]
 
-    class Fasta:                       # pysam.FastaFile stand-in (same semantics as oracle/ref_shims.py)
+    sys.path.insert(0, ref_shims.SHIMS)
+    import pysam as pysam_shim
+
+    class Fasta:                       # pysam.FastaFile stand-in (same semantics as baseline/shims/pysam)
         def __init__(self, path):
-            self.recs = dict(ref_shims._read_fasta(path))
+            self.recs = dict(pysam_shim.read_fasta(path))
 
         def fetch(self, chrom, start=None, stop=None):
             if chrom not in self.recs:
@@ -677,9 +681,9 @@ def test_dropin_glue_on_gpu_from_fastq_file(name, tmp_path):
                 [int(c[9]), int(c[10])]] == g["summary"]
         assert res.cutsite == g["cutsite"]
         got = [["{}|{}|{}|{}|{}".format(s[0], s[1], s[2], s[3], s[9]), n] + [s[i] for i in (0, 1, 2, 3, 5, 6, 7, 8, 9)] + [s[4]]
-               for n, s in res.table]
+               for n, s in res.table()]
         assert got == g.get("table", []), iid
-        assert [[s[5], s[6], s[7], s[8], s[9]] for s in (res.read_results or [])] == g.get("read_results", [])
+        assert res.pattern_out is not None and len(res.pattern_out) == res.n_patterns()     # searched in the parent
 
 
 @pytest.mark.parametrize("piece_bytes", [None, 4096, 65536])
@@ -783,3 +787,112 @@ def test_homeology_batch_kernel_equals_the_host_build_of_the_same_header():
     assert np.array_equal(got, want)
     assert (want[:, 0] >= 0).sum() > 1000 and (want[:, 12] >= 0).sum() > 200      # the searches really find things
     assert homeology_batch([], [], [], [], [], [], [], targets, regions).shape == (0, 16)
+
+
+# ---- fused kernel (K1 + K3 + K4 in one pass over the raw bytes) vs the three-kernel path ---------------------
+def _run_both_paths(cfg, n, pin, monkeypatch, mutate=None, max_read_len=None):
+    """(records, table, counters, unassigned, phase hist) of the same batch through scar_run_dev twice: fused
+    (default) and K1 -> K3 -> K4 (SCAR_NO_FUSE=1); also returns the oracle's records."""
+    import torch
+    from scarmapper_b200.engine import HostRagged
+    batch = cfg.generate(0, n)
+    if mutate:
+        mutate(batch)
+    seq = HostRagged.from_matrix(batch["seq"], lengths=batch["len"])
+    out = []
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("SCAR_NO_FUSE", raising=False)
+        else:
+            monkeypatch.setenv("SCAR_NO_FUSE", "1")
+        eng = engine_for(pin, max_read_len or cfg.read_len)
+        assert eng.info()["fused"] == fused
+        res = eng.make_resident(seq, batch["f0"], batch["f1"])
+        eng.run_resident(res, first_index=7)
+        torch.cuda.synchronize()
+        cnt, un = eng.counters()
+        out.append((eng.records_of(res).copy(), eng.table().copy(), cnt.copy(), un, eng.phase_hist().copy(),
+                    eng.verify_resident(res, first_index=7)))
+        eng.close()
+    reads = cfg.reads_as_strings(batch)
+    f0, f1 = cfg.fields_as_strings(batch)
+    want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
+    return out, want, reads
+
+
+@pytest.mark.parametrize("anchor", ["anchor", "scan"])
+@pytest.mark.parametrize("name,n,kw", [
+    ("C1", 40000, {}), ("C2", 60000, {}), ("C3", 60000, {}), ("C4", 30000, {}),
+    ("C3", 30000, dict(min_len=30, p_n=0.05, p_idx1=0.2, p_idx2=0.05)),
+])
+def test_fused_kernel_equals_three_kernel_path_and_oracle(name, n, kw, anchor, monkeypatch):
+    if anchor == "scan":
+        monkeypatch.setenv("SCAR_NO_ANCHOR", "1")
+    cfg = synth.make_config(name, n_reads=n, seed=321, **kw)
+    pin = synth_problem(cfg)
+
+    def mutate(batch):            # lower-case runs and N bytes inside reads: insertion segments with non-ACGT bytes
+        rng = np.random.Generator(np.random.PCG64(9))
+        seq, ln = batch["seq"], batch["len"]
+        for i in rng.integers(0, len(ln), max(50, len(ln) // 100)):
+            if ln[i] > 90:
+                p = int(rng.integers(60, ln[i] - 25))
+                seq[i, p:p + 4] = np.frombuffer(b"acgt", dtype=np.uint8) if rng.random() < 0.5 else ord("R")
+    (fu, un), want, reads = _run_both_paths(cfg, n, pin, monkeypatch, mutate=mutate)
+    assert_records_equal(fu[0], want, reads)
+    assert_records_equal(un[0], want, reads)
+    assert fu[1].tobytes() == un[1].tobytes(), "scar tables differ (entries, counts, first_idx, hashes)"
+    assert (fu[2] == un[2]).all() and fu[3] == un[3] and (fu[4] == un[4]).all()
+    assert fu[5] == 0 and un[5] == 0
+    prob = orc.Problem(**pin)
+    tables = orc.aggregate(prob, want, reads)
+    ref = [(s, v[1] + 7, v[0]) for s, d in enumerate(tables) for v in d.values()]
+    assert [(int(e["sample"]), int(e["first_idx"]), int(e["count"])) for e in fu[1]] == ref
+    assert (fu[2] == orc.counters(prob, want)).all()
+
+
+def test_fused_kernel_on_fastq_views_takes_several_passes():
+    """FASTQ text: the reads are a third of the bytes, so a tile's raw span is wider than the staging buffer and is
+    taken in passes (and, with a tiny buffer, read from global memory); same records either way."""
+    import os
+    cfg = synth.make_config("C2", n_reads=20000, seed=99)
+    batch = cfg.generate(0, 20000)
+    reads = cfg.reads_as_strings(batch)
+    f0, f1 = cfg.fields_as_strings(batch)
+    text = "".join("@SYN:1:FC:1:0:{}:0 1:N:0:{}+{}\n{}\n+\n{}\n".format(i, a, b, r, "I" * len(r))
+                   for i, (r, a, b) in enumerate(zip(reads, f0, f1))).encode()
+    pin = synth_problem(cfg)
+    want = orc.classify_batch(orc.Problem(**pin), reads, f0, f1)
+    for raw_bytes in (None, "16384", "2048"):
+        if raw_bytes is None:
+            os.environ.pop("SCAR_FUSED_RAW_BYTES", None)
+        else:
+            os.environ["SCAR_FUSED_RAW_BYTES"] = raw_bytes
+        try:
+            eng = engine_for(pin, cfg.read_len)
+            rec = eng.process_fastq_text(np.frombuffer(text, dtype=np.uint8))
+            assert_records_equal(rec, want, reads)
+            tables = orc.aggregate(orc.Problem(**pin), want, reads)
+            ref = [(s, v[1], v[0]) for s, d in enumerate(tables) for v in d.values()]
+            assert [(int(e["sample"]), int(e["first_idx"]), int(e["count"])) for e in eng.table()] == ref
+            eng.close()
+        finally:
+            os.environ.pop("SCAR_FUSED_RAW_BYTES", None)
+
+
+def test_fused_kernel_truseq_golden_and_many_samples(monkeypatch):
+    """TruSeq (stored sequence = seq[6:-6]) goes through the fused kernel; so does a manifest too large for the
+    shared-memory accumulators (global atomics)."""
+    blob = gu.load("truseq")
+    case, golden = blob["case"], blob["golden"]
+    pin = gu.problem_inputs(case)
+    reads = case["reads"]
+    eng = engine_for(pin, max(len(r) for r in reads))
+    assert eng.info()["fused"]
+    rec = eng.process_host(reads, None, None)
+    assert_records_equal(rec, orc.classify_batch(orc.Problem(**pin), reads, None, None), reads)
+    by_sample = {}
+    for e in eng.table():
+        by_sample.setdefault(int(e["sample"]), []).append((int(e["count"]), int(e["first_idx"])))
+    gu.compare_with_golden(case, golden, rec, table_fn=lambda s: by_sample.get(s, []))
+    eng.close()
