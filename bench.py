@@ -279,31 +279,37 @@ def measure_config(name, n, seed, device, steps=5, chk=4000):
             eng.reset_async()
             eng.run_resident(res, first_index=0)
         torch.cuda.synchronize()
+        info = eng.info()
         marks = []
         t0 = ev()
         for _ in range(steps):
             eng.reset_async()
             m = [ev()]
             eng.demux_resident(res); m.append(ev())
-            eng.pack_resident(res); m.append(ev())
-            eng.classify_resident(res); m.append(ev())
-            eng.aggregate_resident(res, first_index=0); m.append(ev())
+            if info["fused"]:
+                eng.classify_raw_resident(res, first_index=0); m.append(ev())
+            else:
+                eng.pack_resident(res); m.append(ev())
+                eng.classify_resident(res); m.append(ev())
+                eng.aggregate_resident(res, first_index=0); m.append(ev())
             marks.append(m)
         t1 = ev()
         torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / steps
-        st = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / steps for i in range(4)]
+        st = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / steps for i in range(len(marks[0]) - 1)]
         n_entries = eng.table_size()
         cnt, un = eng.counters()
-        info = eng.info()
         algo = cfg.read_len + 16 + 16
         peak, _ = measured_peak()
         return {"workload": "{}: {} reads x {} nt, {} samples, {} targets".format(name, n, cfg.read_len, cfg.n_samples, len(cfg.targets)),
                 "parity_first_{}_reads_vs_oracle".format(chk): bool(parity),
                 "value": n / (ms * 1e-3), "unit": "reads/s", "ms_per_step": ms, "steps": steps,
                 "read_bases_per_s": n * cfg.read_len / (ms * 1e-3),
-                "timed_region": "reset, K2 demux, K1 pack, K3, K4 from raw read bytes resident in HBM",
-                "stages_ms": {"k2_demux": st[0], "k1_pack": st[1], "k3_window": st[2], "k4_aggregate": st[3]},
+                "timed_region": "from raw read bytes resident in HBM: reset, K2 demux, " +
+                                ("fused kernel (K1 + K3 + K4)" if info["fused"] else "K1 pack, K3, K4"),
+                "stages_ms": ({"k2_demux": st[0], "fused_pack_window_aggregate": st[1]} if info["fused"] else
+                              {"k2_demux": st[0], "k1_pack": st[1], "k3_window": st[2], "k4_aggregate": st[3]}),
+                "fused": info["fused"], "fused_ctas_per_sm": info["fused_ctas_per_sm"], "fused_smem_bytes": info["fused_smem_bytes"],
                 "algorithmic_bytes_per_read": algo, "hbm_frac_of_step": algo * n / (ms * 1e-3) / 1e9 / peak,
                 "cells_per_read": eng.cells_per_read, "k3_cells_staged_in_smem": bool(info.get("k3_stage", False)),
                 "k3_ctas_per_sm": info.get("k3_ctas_per_sm"), "tables_in_smem": info["tables_in_smem"],
@@ -428,16 +434,24 @@ def main():
         e.record(stream)
         return e
 
-    # K1 (pack) timed on its own
-    for _ in range(2):
-        eng.pack_resident(res)
-    torch.cuda.synchronize()
-    a = ev()
-    for _ in range(3):
-        eng.pack_resident(res)
-    b = ev()
-    torch.cuda.synchronize()
-    k1_ms = a.elapsed_time(b) / 3
+    fused = eng.info()["fused"]
+
+    # the three-kernel path (K1 pack -> K3 -> K4 through HBM), each kernel timed on its own: what the fused kernel replaces
+    def timed(fn, reps=3):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a = ev()
+        for _ in range(reps):
+            fn()
+        b = ev()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    eng.demux_resident(res)
+    k1_ms = timed(lambda: eng.pack_resident(res))
+    k3_alone_ms = timed(lambda: eng.classify_resident(res))
+    k4_alone_ms = timed(lambda: eng.aggregate_resident(res, first_index=first))
+    eng.reset()
 
     marks = []
 
@@ -451,10 +465,15 @@ def main():
         m0 = ev() if record_marks else None
         e.demux_resident(res)
         m1 = ev() if record_marks else None
-        e.classify_resident(res)
-        m2 = ev() if record_marks else None
-        e.aggregate_resident(res, first_index=first)
-        m3 = ev() if record_marks else None
+        if fused:
+            e.classify_raw_resident(res, first_index=first)       # K1 + K3 + K4 in one pass over the raw bytes
+            m2 = m3 = ev() if record_marks else None
+        else:
+            e.pack_resident(res)
+            e.classify_resident(res)
+            m2 = ev() if record_marks else None
+            e.aggregate_resident(res, first_index=first)
+            m3 = ev() if record_marks else None
         if world > 1:
             computed = torch.cuda.Event()
             computed.record(stream)
@@ -511,7 +530,7 @@ def main():
     launches = sum(e.launch_count() for e in engines) - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     k2 = sum(m[0].elapsed_time(m[1]) for m in marks) / len(marks)
-    k3 = sum(m[1].elapsed_time(m[2]) for m in marks) / len(marks)
+    k3 = sum(m[1].elapsed_time(m[2]) for m in marks) / len(marks)      # fused: K1 + K3 + K4 in one kernel
     k4 = sum(m[2].elapsed_time(m[3]) for m in marks) / len(marks)
     merge_ms = sum(a.elapsed_time(b) for a, b in merge_marks) / len(merge_marks) if merge_marks else 0.0
     last = engines[(step_no[0] - 1) % len(engines)]
@@ -642,8 +661,7 @@ def main():
         try:
             d = run_pipeline("dropin", pipe_wd, "C2", args.cpu_sample, args.seed, pipeline["spawn"], device=local)[0]
             pipeline.update(launcher_s=d["total_s"], launcher_stages_s=d["stages"], speedup=pipeline["reference_s"] / d["total_s"],
-                            outputs=compare_pipeline_outputs(pipe_wd),
-                            pattern_searches_served=d["pattern_searches"])
+                            outputs=compare_pipeline_outputs(pipe_wd))
             big = run_pipeline("dropin", os.path.join(pipe_wd, "big"), "C2", args.pipeline_reads, args.seed,
                                pipeline["spawn"], device=local)[0]
             pipeline["launcher_large"] = {"reads": args.pipeline_reads, "launcher_s": big["total_s"],
@@ -689,7 +707,7 @@ def main():
                              "issue_active_pct_of_peak": prof.get("issue_active_pct_of_peak"),
                              "dram_throughput_pct_of_peak": prof.get("dram_throughput_pct_of_peak"),
                              "warp_instructions_per_read": prof.get("warp_instructions_per_read"),
-                             "source": "ncu --set full, profiles/r01_final_ncu_full.csv (not measured in this run)"}
+                             "source": prof.get("source", "ncu --set full under profiles/ (not measured in this run)")}
             except Exception:
                 traffic = None
         h2d = int(p_seq.numel() + p_f0.numel() + p_f1.numel())
@@ -703,7 +721,8 @@ def main():
                        "parallelism": "reads sharded in contiguous blocks, dp{}".format(world),
                        "l2": "inputs_exceed_l2 ({} MB packed rows + {} MB raw per step vs 126 MB L2)".format(
                            n * eng.cells_per_read * 8 // 2 ** 20, n * cfg.read_len // 2 ** 20),
-                       "timed_region": "reset, K2 demux, K3 sliding window, K4 aggregation" +
+                       "timed_region": "from raw read bytes resident in HBM: reset, K2 demux, fused kernel (K1 pack + K3 sliding "
+                                       "window + K4 aggregation in one pass)" +
                                        (", owner-partitioned table merge over NCCL all-to-all + accumulator all-reduce every "
                                         "step (side stream, overlapped with the next step's kernels; the last merge "
                                         "drains inside the timed region)"
@@ -714,9 +733,15 @@ def main():
                                "steps": raw_steps,
                                "timed_region": "reset, K2 demux, K1 pack, K3, K4 (scar_run_dev) from raw read bytes "
                                                "resident in HBM; no cross-rank merge"},
-            "stages_ms": {"k1_pack": k1_ms, "k2_demux": k2, "k3_window": k3, "k4_aggregate": k4,
-                          "merge": merge_ms if world > 1 else 0.0},
-            "roofline": {"bound": "hbm", "kernel": "scar_window_kernel (K3)", "achieved": achieved, "peak": peak,
+            "stages_ms": ({"k2_demux": k2, "fused_pack_window_aggregate": k3, "merge": merge_ms if world > 1 else 0.0}
+                          if fused else {"k2_demux": k2, "k1_pack_k3_window": k3, "k4_aggregate": k4,
+                                         "merge": merge_ms if world > 1 else 0.0}),
+            "three_kernel_path_ms": {"k1_pack": k1_ms, "k3_window": k3_alone_ms, "k4_aggregate": k4_alone_ms,
+                                     "note": "each kernel timed alone over the same resident batch (packed rows and "
+                                             "records travel through HBM); the fused kernel replaces all three"},
+            "roofline": {"bound": "hbm", "kernel": "scar_window_kernel<fused> (K1 pack + K3 sliding window + K4 aggregation, "
+                                                   "one pass over the raw bytes)" if fused else "scar_window_kernel (K3)",
+                         "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ, "secondary": secondary},
             "e2e": {"value": world * n * e2e_steps / e2e_s if e2e_steps else None, "unit": "reads/s", "h2d_bytes_per_step": h2d,
