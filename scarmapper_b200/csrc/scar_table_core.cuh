@@ -77,6 +77,22 @@ __device__ __forceinline__ void key_hashes_bytes(const KeySegment &k, const uint
     key_finish(h1, h2);
 }
 
+// the same for platforms whose stored sequence is a plain slice of the raw read (`stored` = first stored byte): the
+// fused kernel's rare path, kept out of line so that the hot path stays small
+static __device__ __noinline__ void key_hashes_bytes_fwd(uint64_t hdr, int lo, int hi, const uint8_t *stored, uint64_t *h)
+{
+    uint64_t h1, h2;
+    key_init(hdr | (1ull << 62), h1, h2);
+    for (int q = lo; q < hi; q += 8) {
+        uint64_t w = 0;
+        const int n = min(8, hi - q);
+        for (int i = 0; i < n; ++i) w |= (uint64_t)stored[q + i] << (8 * i);
+        key_step(w, h1, h2);
+    }
+    key_finish(h1, h2);
+    h[0] = h1; h[1] = h2;
+}
+
 // The two key hashes of a SCAR record from the RAW read (K4, verification).
 __device__ __forceinline__ void key_hashes(const scar_record &rec, const uint8_t *raw, int rawlen, int platform,
                                            uint64_t &h1, uint64_t &h2)

@@ -418,48 +418,102 @@ __device__ __forceinline__ void queue_push(bool pending, uint32_t item, uint32_t
     if (pending) queue[dir * (int)(base + __popc(mask & ((1u << lane) - 1u)))] = item;
 }
 
-// ---- fused mode: the tile's RAW bytes are staged in shared memory and packed there (what K1 does into HBM) ----
-// One read -> WMAX cells in registers.  STAGED: the raw bytes are in shared memory at byte address `saddr` (the
-// buffer is readable 32 bytes past the tile's span, so no load needs a bounds check); otherwise they are read from
-// global memory at `gp`, never touching a word outside the read.  `slen` bases are packed (<= 16 * WMAX), bases past
-// it are zero.  Returns the number of literal 'N' bytes.
-template <int WMAX, bool STAGED>
-__device__ __forceinline__ int pack_cells(uint32_t saddr, const uint8_t *gp, int slen, uint64_t (&pc)[WMAX])
+// ---- fused mode: raw bytes are staged in shared memory and packed there (what K1 does into HBM) -----------------
+// Every WARP runs its own small pipeline over the 32 reads it owns in a tile: chunks of FUSED_CHUNK reads are brought
+// into a warp-private two-slot ring by TMA bulk copies (lane 0 issues, a per-slot mbarrier signals the bytes), four
+// lanes pack one read (cells q, q+4, ... each), and the slot is refilled with the chunk two ahead - the first two
+// chunks of the NEXT tile while this tile is being searched.  No CTA barrier is involved: the cells a warp writes
+// are read by other warps only between the barriers of the search rounds.
+#define FUSED_CHUNK 8                     // reads per chunk (4 lanes per read)
+#define FUSED_SLOTS 2
+
+struct ChunkDesc { unsigned long long lo16; uint32_t span; bool staged; };
+
+// raw byte span of reads [r0, r0 + FUSED_CHUNK) (uniform over the warp)
+__device__ __forceinline__ ChunkDesc chunk_desc(const scar_ragged &seq, int64_t r0, int64_t n_reads, uint32_t slot_bytes)
 {
-    const uint32_t mis = STAGED ? (saddr & 3u) : (uint32_t)((uintptr_t)gp & 3u);
-    const uint32_t sh = mis * 8u;
-    const uint32_t a4 = saddr & ~3u;
-    const uint32_t *g4 = reinterpret_cast<const uint32_t *>((uintptr_t)gp & ~(uintptr_t)3);
+    ChunkDesc d; d.lo16 = 0; d.span = 0; d.staged = false;
+    if (r0 >= n_reads) return d;
+    const int64_t r1 = min(r0 + FUSED_CHUNK, n_reads) - 1;
+    const uint8_t *p0, *p1; int l0, l1;
+    get_item(seq, r0, p0, l0);
+    get_item(seq, r1, p1, l1);
+    const unsigned long long lo = (unsigned long long)(uintptr_t)p0, hi = (unsigned long long)(uintptr_t)p1 + (unsigned long long)l1;
+    d.lo16 = lo & ~15ull;
+    if (hi > d.lo16) {
+        const unsigned long long span = (hi - d.lo16 + 15ull) & ~15ull;
+        d.staged = span + 32ull <= (unsigned long long)slot_bytes;      // 32 bytes of slack: loads past a read's end
+        d.span = (uint32_t)span;
+    }
+    return d;
+}
+
+__device__ __forceinline__ void chunk_issue(const ChunkDesc &d, uint32_t slot_addr, uint32_t bar_addr)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(d.span) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(slot_addr), "l"(d.lo16), "r"(d.span), "r"(bar_addr) : "memory");
+}
+
+__device__ __forceinline__ void chunk_wait(uint32_t bar_addr, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar_addr), "r"(parity) : "memory");
+    }
+}
+
+// Pack the reads of one chunk: lane -> read k = lane / 4 of the chunk, cells q = lane % 4, q + 4, ...
+// `lr0` is the tile-local index of the chunk's first read; s_info[local read] receives stored length | N count << 16.
+__device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d, uint32_t slot_addr, int64_t r0, int lr0,
+                                           uint64_t *s_cells, uint32_t *s_info)
+{
+    const int lane = threadIdx.x & 31, k = lane >> 2, q = lane & 3;
+    const int64_t r = r0 + k;
+    const bool have = r < P.n_reads;
+    const uint8_t *rp = P.seq.bytes; int rawlen = 0;
+    if (have) get_item(P.seq, r, rp, rawlen);
+    int slen = rawlen, shift = 0;
+    if (P.platform == SCAR_PLATFORM_TRUSEQ) { slen = rawlen > 12 ? rawlen - 12 : 0; shift = 6; }
+    if (slen > 16 * P.W) { if (q == 0) atomicOr(P.status, 1); slen = 16 * P.W; }
+    const uint8_t *sp = rp + shift;
+    const unsigned long long a = (unsigned long long)(uintptr_t)sp;
+    // in the staged span?  (views that are not in file order may fall outside: those are read from global memory)
+    const bool inside = d.staged && a >= d.lo16 && (unsigned long long)(uintptr_t)rp + (unsigned long long)rawlen <= d.lo16 + d.span;
+    const uint32_t mis = (uint32_t)(a & 3ull), sh = mis * 8u;
+    const uint32_t s4 = slot_addr + (uint32_t)((a & ~3ull) - d.lo16);                     // shared address of the first aligned word
+    const uint32_t *g4 = reinterpret_cast<const uint32_t *>((uintptr_t)(a & ~3ull));
     const int kend = ((int)mis + slen + 3) >> 2;        // aligned words that overlap the read (global path)
-    auto ld = [&](int k) -> uint32_t {
-        uint32_t w = 0u;
-        if (STAGED) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(a4 + 4u * (uint32_t)k));
-        else if (k < kend) w = __ldg(g4 + k);
-        return w;
-    };
-    uint32_t wp = ld(0);
     int n_count = 0;
-#pragma unroll
-    for (int j = 0; j < WMAX; ++j) {
+    uint64_t *out = s_cells + lr0 + k;
+    for (int j = q; j < P.W; j += 4) {
         const int nb = slen - 16 * j;                   // bases of this cell (may exceed 16)
-        uint64_t cell = 0ull;
+        uint32_t code = 0u, hi = 0u;
         if (nb > 0) {
-            const uint32_t w1 = ld(4 * j + 1), w2 = ld(4 * j + 2), w3 = ld(4 * j + 3), w4 = ld(4 * j + 4);
-            uint32_t v[4];
-            v[0] = __funnelshift_r(wp, w1, sh); v[1] = __funnelshift_r(w1, w2, sh);
-            v[2] = __funnelshift_r(w2, w3, sh); v[3] = __funnelshift_r(w3, w4, sh);
-            wp = w4;
-            // 2-bit codes: (w>>1)&3 per byte, gathered into the top byte by one multiply per word
-            uint32_t pt[4], x[4];
+            uint32_t w[5];
+            if (inside) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { pt[i] = codes_to_top_byte(v[i]); x[i] = acgt_diff4(v[i]); }
-            uint32_t code = __byte_perm(__byte_perm(pt[0], pt[1], 0x0073), __byte_perm(pt[2], pt[3], 0x0073), 0x5410);
-            uint32_t valid = 0xFFFFu, nmask = 0u;
-            if (nb < 16 || (x[0] | x[1] | x[2] | x[3]) != 0u) {       // rare: last cell, or a non-ACGT byte
-                valid = 0u;
+                for (int i = 0; i < 5; ++i)
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(s4 + 4u * (uint32_t)(4 * j + i)));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) w[i] = (4 * j + i) < kend ? __ldg(g4 + 4 * j + i) : 0u;
+            }
+            uint32_t v[4], x = 0u, pt[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                v[i] = __funnelshift_r(w[i], w[i + 1], sh);
+                pt[i] = codes_to_top_byte(v[i]);
+                x |= acgt_diff4(v[i]);
+            }
+            code = __byte_perm(__byte_perm(pt[0], pt[1], 0x0073), __byte_perm(pt[2], pt[3], 0x0073), 0x5410);
+            hi = 0xFFFFu;                                               // ACGT mask | N mask << 16
+            if (nb < 16 || x != 0u) {                                   // rare: last cell, or a non-ACGT byte
+                uint32_t valid = 0u, nmask = 0u;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    valid |= flags_to_nibble(zero_bytes(x[i])) << (4 * i);
+                    valid |= flags_to_nibble(zero_bytes(acgt_diff4(v[i]))) << (4 * i);
                     nmask |= flags_to_nibble(zero_bytes(v[i] ^ 0x4E4E4E4Eu)) << (4 * i);
                 }
                 const uint32_t bm = nb >= 16 ? 0xFFFFu : ((1u << nb) - 1u);
@@ -470,31 +524,14 @@ __device__ __forceinline__ int pack_cells(uint32_t saddr, const uint8_t *gp, int
                 m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
                 m2 = (m2 | (m2 << 2)) & 0x33333333u; m2 = (m2 | (m2 << 1)) & 0x55555555u;
                 code &= m2 * 3u;
+                hi = valid | (nmask << 16);
             }
-            cell = (uint64_t)code | ((uint64_t)valid << 32) | ((uint64_t)nmask << 48);
         }
-        pc[j] = cell;
+        if (have) *reinterpret_cast<uint2 *>(out + j * K3_TILE) = make_uint2(code, hi);
     }
-    return n_count;
-}
-
-// smallest start / largest end address over the threads with `mine` (CTA-wide; contains two barriers)
-__device__ __forceinline__ void span_reduce(bool mine, const uint8_t *rp, int len, unsigned long long (*s_red)[8],
-                                            unsigned long long &lo, unsigned long long &hi)
-{
-    unsigned long long a = mine ? (unsigned long long)(uintptr_t)rp : ~0ull;
-    unsigned long long b = mine ? (unsigned long long)(uintptr_t)rp + (unsigned long long)len : 0ull;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-        const unsigned long long a2 = __shfl_xor_sync(0xFFFFFFFFu, a, d), b2 = __shfl_xor_sync(0xFFFFFFFFu, b, d);
-        a = a2 < a ? a2 : a; b = b2 > b ? b2 : b;
-    }
-    __syncthreads();                                  // s_red may still be read from the previous use
-    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = a; s_red[1][threadIdx.x >> 5] = b; }
-    __syncthreads();
-    lo = s_red[0][0]; hi = s_red[1][0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) { lo = s_red[0][i] < lo ? s_red[0][i] : lo; hi = s_red[1][i] > hi ? s_red[1][i] : hi; }
+    n_count += __shfl_xor_sync(0xFFFFFFFFu, n_count, 1);
+    n_count += __shfl_xor_sync(0xFFFFFFFFu, n_count, 2);
+    if (q == 0) s_info[lr0 + k] = have ? ((uint32_t)slen | ((uint32_t)n_count << 16)) : 0u;
 }
 
 // MODE 0: the packed cells are read from global memory (cell-major)          } input = K1's packed batch
@@ -511,12 +548,14 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (WMAX > 10 ? 2 : SCAR_FUS
     constexpr bool ST = MODE >= 1;      // the tile's cells live in shared memory
     constexpr bool FUSED = MODE == 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [2 mbarriers 16 B][static blob: tables | target metas | phases | N-limit table][tile buffer][accumulators]
+    // layout: [mbarriers: blob + (fused) one per warp and ring slot][static blob: tables | target metas | phases |
+    // N-limit table][tile buffer: cells (+ fused: raw rings)][fused: accumulators]
+    constexpr uint32_t HDR = FUSED ? 16u + (K3_TILE / 32) * FUSED_SLOTS * 8u : 16u;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     const unsigned char *blob = reinterpret_cast<const unsigned char *>(P.blob);
     if (SMEM) {
-        stage_tables_tma(smem_raw + 16, P.blob, P.blob_bytes, bar);
-        blob = smem_raw + 16;
+        stage_tables_tma(smem_raw + HDR, P.blob, P.blob_bytes, bar);
+        blob = smem_raw + HDR;
     }
     const ScarTargetMeta *metas = reinterpret_cast<const ScarTargetMeta *>(blob + P.meta_off);
     const ScarPhase *phases = reinterpret_cast<const ScarPhase *>(blob + P.phase_off);
@@ -525,8 +564,8 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (WMAX > 10 ? 2 : SCAR_FUS
     using RC = ReadCursorT<ST>;
     // ST: the tile's cells (W rows of 256 x 8 bytes) live in shared memory behind the blob.  MODE 1: every thread
     // copies its own read's cells there with asynchronous 8-byte copies (no registers, all W in flight at once).
-    // MODE 2: the same buffer first receives the tile's raw bytes.
-    unsigned char *tile_buf = smem_raw + 16 + (SMEM ? P.blob_bytes : 0u);
+    // MODE 2: they are packed there from the raw bytes in the warps' rings.
+    unsigned char *tile_buf = smem_raw + HDR + (SMEM ? P.blob_bytes : 0u);
     uint64_t *s_cells = reinterpret_cast<uint64_t *>(tile_buf);
 
     // A CTA takes tiles of 256 reads.  Phase 1 is one thread per read: phasing, filters, and the FIRST anchor
@@ -539,29 +578,39 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (WMAX > 10 ? 2 : SCAR_FUS
     __shared__ uint32_t s_ctx[K3_TILE];                      // stored length | target id << 16
     __shared__ uint32_t s_queue[2][2 * K3_TILE];             // item = local read | p << 8
     __shared__ uint32_t s_count[3][2];                       // [round % 3][side]
-    __shared__ unsigned long long s_red[2][8];               // fused: span reduction
     __shared__ unsigned int s_unassigned, s_new;             // fused: aggregation
     if (threadIdx.x < 6) s_count[threadIdx.x >> 1][threadIdx.x & 1] = 0;
 
-    // ---- fused: accumulators of the aggregation, raw-span barrier
+    // ---- fused: accumulators of the aggregation, the warps' raw rings and their mbarriers
     unsigned int *s_hist = nullptr;
     int per_sample = 0;
     ScarTableRef TB; ScarAccRef AC;
-    uint32_t raw_parity = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile_step = (int64_t)gridDim.x * K3_TILE;
+    uint32_t ring_addr = 0, ring_bar = 0, ring_use0 = 0, ring_use1 = 0;      // this warp's ring, slot use counts (parity)
     if (FUSED) {
-        if (threadIdx.x == 0) {
-            s_unassigned = 0; s_new = 0;
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 1)));
+        const uint32_t cells_bytes = ((uint32_t)P.W * K3_TILE * 8u + 15u) & ~15u;
+        ring_addr = smem_u32(tile_buf) + cells_bytes + (uint32_t)warp * FUSED_SLOTS * P.raw_cap;
+        ring_bar = smem_u32(bar) + 16u + (uint32_t)warp * FUSED_SLOTS * 8u;
+        if (threadIdx.x == 0) { s_unassigned = 0; s_new = 0; }
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bar));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bar + 8u));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         TB.slots = P.slots; TB.slot_mask = P.slot_mask; TB.max_probe = P.max_probe; TB.status = P.status;
         AC.counters = P.counters; AC.phase_hist = P.phase_hist; AC.unassigned = P.unassigned; AC.n_samples = P.n_samples;
         AC.pb = P.phase_bins; AC.joint = P.phase_joint;
         per_sample = acc_words_per_sample(AC.pb, AC.joint);
-        const uint32_t buf_bytes = max(P.raw_cap + 32u, (uint32_t)P.W * K3_TILE * 8u);
-        s_hist = reinterpret_cast<unsigned int *>(tile_buf + ((buf_bytes + 15u) & ~15u));
+        s_hist = reinterpret_cast<unsigned int *>(tile_buf + cells_bytes + (K3_TILE / 32) * FUSED_SLOTS * P.raw_cap);
         if (P.aggregate && P.hist_smem)
             for (int i = threadIdx.x; i < P.n_samples * per_sample; i += K3_TILE) s_hist[i] = 0;
+        __syncwarp();
+        // prologue of the warp's pipeline: the first two chunks of its first tile
+        for (int c = 0; c < FUSED_SLOTS; ++c) {
+            const ChunkDesc d = chunk_desc(P.seq, (int64_t)blockIdx.x * K3_TILE + 32 * warp + FUSED_CHUNK * c, P.n_reads, P.raw_cap);
+            if (d.staged && lane == 0) chunk_issue(d, ring_addr + (uint32_t)c * P.raw_cap, ring_bar + 8u * (uint32_t)c);
+        }
     }
     __syncthreads();
     uint32_t round = 0;
@@ -580,82 +629,32 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (WMAX > 10 ? 2 : SCAR_FUS
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         if (FUSED) {
-            // ---- K1 in shared memory.  The raw bytes of the tile are one contiguous span of the input (CSR / fixed
-            // stride; FASTQ views in file order): TMA bulk copies bring it in - in 2, 4 or 8 passes over 128, 64 or
-            // 32 reads when the span is wider than the buffer (FASTQ text: the reads are a third of the bytes) - and
-            // each thread packs ITS read into registers; when every thread has read its bytes the cells are stored
-            // over them.  A span that still does not fit (scattered views) is read from global memory.
             if (P.aggregate && P.hist_smem && ++epoch > K4_EPOCH_ITERS) {      // 16-bit packed counters: flush in time
                 __syncthreads();
                 acc_flush(AC, s_hist, per_sample);
                 epoch = 1;
             }
-            const uint8_t *rp = P.seq.bytes; int rawlen = 0;
-            if (in_range) get_item(P.seq, r, rp, rawlen);
-            int slen = rawlen, shift = 0;
-            if (P.platform == SCAR_PLATFORM_TRUSEQ) { slen = rawlen > 12 ? rawlen - 12 : 0; shift = 6; }
-            if (slen > 16 * P.W) { atomicOr(P.status, 1); slen = 16 * P.W; }
-            const bool views = P.seq.offsets && P.seq.lengths;
-            auto span_of = [&](int64_t a, int64_t b, bool mine, unsigned long long &lo, unsigned long long &hi) {
-                if (views) { span_reduce(mine, rp, rawlen, s_red, lo, hi); return; }
-                __syncthreads();                          // s_red may still be read from the previous use
-                if (threadIdx.x == 0) {
-                    if (b >= P.n_reads) b = P.n_reads - 1;
-                    unsigned long long x = ~0ull, y = 0ull;
-                    if (a <= b) {
-                        const uint8_t *q0, *q1; int l0, l1;
-                        get_item(P.seq, a, q0, l0);
-                        get_item(P.seq, b, q1, l1);
-                        x = (unsigned long long)(uintptr_t)q0; y = (unsigned long long)(uintptr_t)q1 + (unsigned long long)l1;
-                    }
-                    s_red[0][0] = x; s_red[1][0] = y;
+            // ---- K1 in shared memory, one pipeline per warp (see pack_chunk): the warp's 32 reads in 4 chunks
+            __syncwarp();                                 // phase 3 of the previous tile read this warp's cells
+            const int64_t w0 = tile + 32 * warp;
+#pragma unroll 1
+            for (int c = 0; c < 32 / FUSED_CHUNK; ++c) {
+                const int slot = c & 1;
+                const uint32_t slot_addr = ring_addr + (uint32_t)slot * P.raw_cap, slot_bar = ring_bar + 8u * (uint32_t)slot;
+                const ChunkDesc d = chunk_desc(P.seq, w0 + FUSED_CHUNK * c, P.n_reads, P.raw_cap);
+                if (d.staged) {
+                    chunk_wait(slot_bar, (slot ? ring_use1 : ring_use0) & 1u);
+                    if (slot) ++ring_use1; else ++ring_use0;
                 }
-                __syncthreads();
-                lo = s_red[0][0]; hi = s_red[1][0];
-            };
-            unsigned long long lo, hi;
-            span_of(tile, tile + K3_TILE - 1, in_range, lo, hi);     // (the barrier inside also ends the previous tile)
-            int passes = 1;
-            {
-                const unsigned long long whole = hi > lo ? hi - (lo & ~15ull) + 15ull : 0ull;
-                while (passes < 8 && whole > (unsigned long long)passes * (P.raw_cap - 64u)) passes *= 2;
+                pack_chunk(P, d, slot_addr, w0 + FUSED_CHUNK * c, 32 * warp + FUSED_CHUNK * c, s_cells, s_ctx);
+                __syncwarp();                             // every lane has read the slot: refill it two chunks ahead
+                const int64_t rn = c + FUSED_SLOTS < 32 / FUSED_CHUNK ? w0 + FUSED_CHUNK * (c + FUSED_SLOTS)
+                                                                      : w0 + tile_step + FUSED_CHUNK * (c + FUSED_SLOTS - 32 / FUSED_CHUNK);
+                const ChunkDesc dn = chunk_desc(P.seq, rn, P.n_reads, P.raw_cap);
+                if (dn.staged && lane == 0) chunk_issue(dn, slot_addr, slot_bar);
             }
-            const int sub_shift = 8 - (31 - __clz(passes)), sub = 1 << sub_shift;      // K3_TILE = 256
-            uint64_t pc[WMAX];
-            int n_count = 0;
-            for (int ps = 0; ps < passes; ++ps) {
-                const bool mine = in_range && ((int)threadIdx.x >> sub_shift) == ps;
-                if (passes > 1) span_of(tile + (int64_t)ps * sub, tile + (int64_t)(ps + 1) * sub - 1, mine, lo, hi);
-                const unsigned long long lo16 = lo & ~15ull;
-                const unsigned long long span = hi > lo16 ? ((hi - lo16 + 15ull) & ~15ull) : 0ull;
-                const bool staged = span != 0ull && span <= (unsigned long long)P.raw_cap;
-                if (staged) {
-                    if (threadIdx.x == 0) {
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + 1)),
-                                     "r"((uint32_t)span) : "memory");
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     ::"r"(smem_u32(tile_buf)), "l"(lo16), "r"((uint32_t)span), "r"(smem_u32(bar + 1)) : "memory");
-                    }
-                    uint32_t done = 0;
-                    while (!done) {
-                        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-                                     "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(bar + 1)), "r"(raw_parity) : "memory");
-                    }
-                    raw_parity ^= 1u;
-                }
-                if (mine) {
-                    const uint8_t *sp = rp + shift;
-                    if (staged) n_count = pack_cells<WMAX, true>(smem_u32(tile_buf) + (uint32_t)((unsigned long long)(uintptr_t)sp - lo16), sp, slen, pc);
-                    else n_count = pack_cells<WMAX, false>(0u, sp, slen, pc);
-                }
-                __syncthreads();                          // every thread has read its raw bytes: the buffer is reused
-            }
-            if (in_range) {
-#pragma unroll
-                for (int j = 0; j < WMAX; ++j)
-                    if (j < P.W) s_cells[j * K3_TILE + threadIdx.x] = pc[j];
-            }
-            info = (uint32_t)slen | ((uint32_t)n_count << 16);
+            __syncwarp();
+            info = in_range ? s_ctx[threadIdx.x] : 0u;
         }
         __align__(16) scar_record rec;
         rec.status = SCAR_ST_UNASSIGNED; rec.flags = 0; rec.sample = SCAR_SAMPLE_NONE;
@@ -975,9 +974,11 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (WMAX > 10 ? 2 : SCAR_FUS
                 }
                 if (acgt) key_finish(h1, h2);
                 else {
-                    const uint8_t *raw; int rawlen;
+                    const uint8_t *raw; int rawlen;          // (the fused kernel does not take the Ramsden platform)
                     get_item(P.seq, r, raw, rawlen);
-                    key_hashes_bytes(ks, raw, rawlen, P.platform, h1, h2);
+                    uint64_t hh[2];
+                    key_hashes_bytes_fwd(ks.hdr, ks.lo, ks.hi, raw + (P.platform == SCAR_PLATFORM_TRUSEQ ? 6 : 0), hh);
+                    h1 = hh[0]; h2 = hh[1];
                 }
                 if (table_insert(TB, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample)) atomicAdd(&s_new, 1u);
             }
@@ -1062,16 +1063,17 @@ bool scar_fused_eligible(int W, int platform)
 static cudaError_t plan_fused(K3Params &P, bool smem_tables, int max_read_len, K3Plan &plan)
 {
     const int threads = K3_TILE;
-    // raw staging buffer: one tile of fixed-stride reads of the longest length fits in one pass
+    // one ring slot holds a chunk of FUSED_CHUNK fixed-stride reads of the longest length (+ alignment, + 32 bytes of
+    // slack for word loads past a read's end); wider spans (FASTQ views) are read from global memory unless the
+    // caller asks for larger slots (SCAR_FUSED_SLOT_BYTES)
     const int raw_len = max_read_len + (P.platform == SCAR_PLATFORM_TRUSEQ ? 12 : 0);
-    // (long reads: at most ~40 KB, i.e. two passes for 300-nt reads - the packed cells need that much anyway)
-    const uint32_t cells_bytes = (uint32_t)P.W * threads * 8u;
-    uint32_t raw_cap = std::min<uint32_t>((uint32_t)threads * (uint32_t)raw_len + 48u, 40u * 1024u);
-    raw_cap = (std::max<uint32_t>(raw_cap, cells_bytes > 32u ? cells_bytes - 32u : 0u) + 15u) & ~15u;
-    if (const char *e = getenv("SCAR_FUSED_RAW_BYTES")) { const long v = atol(e); if (v >= 1024) raw_cap = ((uint32_t)v + 15u) & ~15u; }
-    P.raw_cap = raw_cap;
-    const size_t buf = ((size_t)std::max<uint32_t>(raw_cap + 32u, (uint32_t)P.W * threads * 8u) + 15) & ~(size_t)15;
-    const size_t base = 16 + (smem_tables ? P.blob_bytes : 0) + buf;
+    uint32_t slot = ((uint32_t)FUSED_CHUNK * (uint32_t)raw_len + 16u + 32u + 15u) & ~15u;
+    if (P.seq.offsets && P.seq.lengths) slot = ((uint32_t)FUSED_CHUNK * (2u * (uint32_t)raw_len + 64u) + 48u + 15u) & ~15u;   // FASTQ records
+    if (const char *e = getenv("SCAR_FUSED_SLOT_BYTES")) { const long v = atol(e); if (v >= 64) slot = ((uint32_t)v + 15u) & ~15u; }
+    P.raw_cap = slot;
+    const size_t cells_bytes = ((size_t)P.W * threads * 8 + 15) & ~(size_t)15;
+    const size_t buf = cells_bytes + (size_t)(threads / 32) * FUSED_SLOTS * slot;
+    const size_t base = 16 + (threads / 32) * FUSED_SLOTS * 8 + (smem_tables ? P.blob_bytes : 0) + buf;
     // accumulators: joint phase histogram when it is small, else two marginals; global atomics when neither fits
     P.hist_smem = 0;
     size_t hist = 0;
