@@ -420,25 +420,31 @@ __device__ __forceinline__ void queue_push(bool pending, uint32_t item, uint32_t
 
 // ---- fused mode: raw bytes are staged in shared memory and packed there (what K1 does into HBM) -----------------
 // Every WARP runs its own small pipeline over the 32 reads it owns in a tile: chunks of FUSED_CHUNK reads are brought
-// into a warp-private two-slot ring by TMA bulk copies (lane 0 issues, a per-slot mbarrier signals the bytes), four
-// lanes pack one read (cells q, q+4, ... each), and the slot is refilled with the chunk two ahead - the first two
-// chunks of the NEXT tile while this tile is being searched.  No CTA barrier is involved: the cells a warp writes
-// are read by other warps only between the barriers of the search rounds.
-#define FUSED_CHUNK 8                     // reads per chunk (4 lanes per read)
-#define FUSED_SLOTS 2
+// into warp-private slots by TMA bulk copies (lane 0 issues, a per-slot mbarrier signals the bytes), FUSED_LANES
+// lanes pack one read (a run of consecutive cells each), and the slot is refilled with the chunk FUSED_SLOTS ahead -
+// the first chunk(s) of the NEXT tile while this tile is being searched.  No CTA barrier is involved: the cells a
+// warp writes are read by other warps only between the barriers of the search rounds.
+// LANES (template parameter): lanes per read = chunks per warp per tile; a chunk holds 32 / LANES reads.
+#ifndef FUSED_SLOTS
+#define FUSED_SLOTS 1
+#endif
 
 struct ChunkDesc { unsigned long long lo16; uint32_t span; bool staged; };
 
-// raw byte span of reads [r0, r0 + FUSED_CHUNK) (uniform over the warp)
-__device__ __forceinline__ ChunkDesc chunk_desc(const scar_ragged &seq, int64_t r0, int64_t n_reads, uint32_t slot_bytes)
+// raw byte span of reads [r0, r0 + chunk_reads) (uniform over the warp)
+__device__ __forceinline__ ChunkDesc chunk_desc(const scar_ragged &seq, int64_t r0, int chunk_reads, int64_t n_reads, uint32_t slot_bytes)
 {
     ChunkDesc d; d.lo16 = 0; d.span = 0; d.staged = false;
     if (r0 >= n_reads) return d;
-    const int64_t r1 = min(r0 + FUSED_CHUNK, n_reads) - 1;
-    const uint8_t *p0, *p1; int l0, l1;
-    get_item(seq, r0, p0, l0);
-    get_item(seq, r1, p1, l1);
-    const unsigned long long lo = (unsigned long long)(uintptr_t)p0, hi = (unsigned long long)(uintptr_t)p1 + (unsigned long long)l1;
+    const int64_t r1 = min(r0 + chunk_reads, n_reads) - 1;
+    unsigned long long lo, hi;
+    if (seq.offsets) {
+        lo = (unsigned long long)(uintptr_t)seq.bytes + (unsigned long long)seq.offsets[r0];
+        hi = (unsigned long long)(uintptr_t)seq.bytes + (unsigned long long)(seq.lengths ? seq.offsets[r1] + seq.lengths[r1] : seq.offsets[r1 + 1]);
+    } else {
+        lo = (unsigned long long)(uintptr_t)seq.bytes + (unsigned long long)(r0 * seq.stride);
+        hi = lo + (unsigned long long)((r1 - r0) * seq.stride) + (unsigned long long)(seq.lengths ? seq.lengths[r1] : (int)seq.stride);
+    }
     d.lo16 = lo & ~15ull;
     if (hi > d.lo16) {
         const unsigned long long span = (hi - d.lo16 + 15ull) & ~15ull;
@@ -464,12 +470,27 @@ __device__ __forceinline__ void chunk_wait(uint32_t bar_addr, uint32_t parity)
     }
 }
 
-// Pack the reads of one chunk: lane -> read k = lane / 4 of the chunk, cells q = lane % 4, q + 4, ...
-// `lr0` is the tile-local index of the chunk's first read; s_info[local read] receives stored length | N count << 16.
+// cell j of a read straight from global memory, one byte at a time (a chunk whose span does not fit its slot:
+// scattered views, reads longer than the context was sized for); kept out of line - the hot path is pack_chunk's loop
+static __device__ __noinline__ uint2 pack_cell_bytes(const uint8_t *sp, int slen, int j)
+{
+    uint32_t code = 0u, valid = 0u, nmask = 0u;
+    for (int k = 0; k < 16 && 16 * j + k < slen; ++k) {
+        const uint8_t b = sp[16 * j + k];
+        if (scar_base_valid(b)) { valid |= 1u << k; code |= scar_base_code(b) << (2 * k); }
+        if (b == 'N') nmask |= 1u << k;
+    }
+    return make_uint2(code, valid | (nmask << 16));
+}
+
+// Pack the reads of one chunk: lane -> read k = lane / LANES of the chunk, cells [q * cpl, (q + 1) * cpl) with
+// q = lane % LANES and cpl = ceil(W / LANES).  `lr0` is the tile-local index of the chunk's first read;
+// s_info[local read] receives stored length | N count << 16.
+template <int LANES>
 __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d, uint32_t slot_addr, int64_t r0, int lr0,
                                            uint64_t *s_cells, uint32_t *s_info)
 {
-    const int lane = threadIdx.x & 31, k = lane >> 2, q = lane & 3;
+    const int lane = threadIdx.x & 31, k = lane / LANES, q = lane % LANES;
     const int64_t r = r0 + k;
     const bool have = r < P.n_reads;
     const uint8_t *rp = P.seq.bytes; int rawlen = 0;
@@ -478,59 +499,76 @@ __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d
     if (P.platform == SCAR_PLATFORM_TRUSEQ) { slen = rawlen > 12 ? rawlen - 12 : 0; shift = 6; }
     if (slen > 16 * P.W) { if (q == 0) atomicOr(P.status, 1); slen = 16 * P.W; }
     const uint8_t *sp = rp + shift;
-    const unsigned long long a = (unsigned long long)(uintptr_t)sp;
     // in the staged span?  (views that are not in file order may fall outside: those are read from global memory)
+    const unsigned long long a = (unsigned long long)(uintptr_t)sp;
     const bool inside = d.staged && a >= d.lo16 && (unsigned long long)(uintptr_t)rp + (unsigned long long)rawlen <= d.lo16 + d.span;
-    const uint32_t mis = (uint32_t)(a & 3ull), sh = mis * 8u;
-    const uint32_t s4 = slot_addr + (uint32_t)((a & ~3ull) - d.lo16);                     // shared address of the first aligned word
-    const uint32_t *g4 = reinterpret_cast<const uint32_t *>((uintptr_t)(a & ~3ull));
-    const int kend = ((int)mis + slen + 3) >> 2;        // aligned words that overlap the read (global path)
+    const int cpl = (P.W + LANES - 1) / LANES;
+    const int j0 = q * cpl, j1 = min(j0 + cpl, P.W);
+    uint2 *out = reinterpret_cast<uint2 *>(s_cells + lr0 + k) + (size_t)j0 * K3_TILE;
     int n_count = 0;
-    uint64_t *out = s_cells + lr0 + k;
-    for (int j = q; j < P.W; j += 4) {
-        const int nb = slen - 16 * j;                   // bases of this cell (may exceed 16)
-        uint32_t code = 0u, hi = 0u;
-        if (nb > 0) {
-            uint32_t w[5];
-            if (inside) {
+    if (inside) {
+        const uint32_t a0 = slot_addr + (uint32_t)(a - d.lo16) + 16u * (uint32_t)j0;     // shared address of cell j0's first byte
+        const uint32_t sh = (a0 & 3u) * 8u;
+        uint32_t a4 = a0 & ~3u, wp;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wp) : "r"(a4));
+        int nb = slen - 16 * j0;                            // bases from this cell on
+        for (int j = j0; j < j1; ++j, a4 += 16u, nb -= 16, out += K3_TILE) {
+            uint32_t code = 0u, hi = 0u;
+            if (nb > 0) {
+                uint32_t w1, w2, w3, w4;
+                asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a4));
+                asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a4));
+                asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(w3) : "r"(a4));
+                asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(w4) : "r"(a4));
+                uint32_t v[4];
+                v[0] = __funnelshift_r(wp, w1, sh); v[1] = __funnelshift_r(w1, w2, sh);
+                v[2] = __funnelshift_r(w2, w3, sh); v[3] = __funnelshift_r(w3, w4, sh);
+                wp = w4;
+                hi = 0xFFFFu;                               // ACGT mask | N mask << 16
+                if (nb < 16) {                              // last cell of the read: bytes past its end count as 'A' (code 0)
+                    hi = (1u << nb) - 1u;
 #pragma unroll
-                for (int i = 0; i < 5; ++i)
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(s4 + 4u * (uint32_t)(4 * j + i)));
-            } else {
-#pragma unroll
-                for (int i = 0; i < 5; ++i) w[i] = (4 * j + i) < kend ? __ldg(g4 + 4 * j + i) : 0u;
-            }
-            uint32_t v[4], x = 0u, pt[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                v[i] = __funnelshift_r(w[i], w[i + 1], sh);
-                pt[i] = codes_to_top_byte(v[i]);
-                x |= acgt_diff4(v[i]);
-            }
-            code = __byte_perm(__byte_perm(pt[0], pt[1], 0x0073), __byte_perm(pt[2], pt[3], 0x0073), 0x5410);
-            hi = 0xFFFFu;                                               // ACGT mask | N mask << 16
-            if (nb < 16 || x != 0u) {                                   // rare: last cell, or a non-ACGT byte
-                uint32_t valid = 0u, nmask = 0u;
+                    for (int i = 0; i < 4; ++i) {
+                        const int nbytes = min(max(nb - 4 * i, 0), 4);
+                        const uint32_t keep = nbytes == 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
+                        v[i] = (v[i] & keep) | (0x41414141u & ~keep);
+                    }
+                }
+                uint32_t x = 0u, pt[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    valid |= flags_to_nibble(zero_bytes(acgt_diff4(v[i]))) << (4 * i);
-                    nmask |= flags_to_nibble(zero_bytes(v[i] ^ 0x4E4E4E4Eu)) << (4 * i);
+                    pt[i] = codes_to_top_byte(v[i]);
+                    x |= acgt_diff4(v[i]);
                 }
-                const uint32_t bm = nb >= 16 ? 0xFFFFu : ((1u << nb) - 1u);
-                valid &= bm; nmask &= bm;
-                n_count += __popc(nmask);
-                // spread the ACGT mask to 2 bits per base to clear the codes of non-ACGT / absent bases
-                uint32_t m2 = valid;
-                m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
-                m2 = (m2 | (m2 << 2)) & 0x33333333u; m2 = (m2 | (m2 << 1)) & 0x55555555u;
-                code &= m2 * 3u;
-                hi = valid | (nmask << 16);
+                code = __byte_perm(__byte_perm(pt[0], pt[1], 0x0073), __byte_perm(pt[2], pt[3], 0x0073), 0x5410);
+                if (x != 0u) {                              // rare: a non-ACGT byte in the cell
+                    uint32_t valid = 0u, nmask = 0u;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        valid |= flags_to_nibble(zero_bytes(acgt_diff4(v[i]))) << (4 * i);
+                        nmask |= flags_to_nibble(zero_bytes(v[i] ^ 0x4E4E4E4Eu)) << (4 * i);
+                    }
+                    valid &= hi; nmask &= hi;
+                    n_count += __popc(nmask);
+                    // spread the ACGT mask to 2 bits per base to clear the codes of non-ACGT bases
+                    uint32_t m2 = valid;
+                    m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
+                    m2 = (m2 | (m2 << 2)) & 0x33333333u; m2 = (m2 | (m2 << 1)) & 0x55555555u;
+                    code &= m2 * 3u;
+                    hi = valid | (nmask << 16);
+                }
             }
+            if (have) *out = make_uint2(code, hi);
         }
-        if (have) *reinterpret_cast<uint2 *>(out + j * K3_TILE) = make_uint2(code, hi);
+    } else {
+        for (int j = j0; j < j1; ++j, out += K3_TILE) {
+            const uint2 c = have ? pack_cell_bytes(sp, slen, j) : make_uint2(0u, 0u);
+            n_count += __popc(c.y >> 16);
+            if (have) *out = c;
+        }
     }
-    n_count += __shfl_xor_sync(0xFFFFFFFFu, n_count, 1);
-    n_count += __shfl_xor_sync(0xFFFFFFFFu, n_count, 2);
+#pragma unroll
+    for (int m = 1; m < LANES; m <<= 1) n_count += __shfl_xor_sync(0xFFFFFFFFu, n_count, m);
     if (q == 0) s_info[lr0 + k] = have ? ((uint32_t)slen | ((uint32_t)n_count << 16)) : 0u;
 }
 
@@ -542,9 +580,10 @@ __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d
 #ifndef SCAR_FUSED_MIN_CTAS
 #define SCAR_FUSED_MIN_CTAS 3
 #endif
-template <bool SMEM, bool HR, int MODE, int WMAX>
-__global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (WMAX > 10 ? 2 : SCAR_FUSED_MIN_CTAS) : SCAR_K3_MIN_CTAS) scar_window_kernel(const K3Params P)
+template <bool SMEM, bool HR, int MODE, int LANES>
+__global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUSED_MIN_CTAS) : SCAR_K3_MIN_CTAS) scar_window_kernel(const K3Params P)
 {
+    constexpr int FUSED_CHUNK = 32 / LANES, FUSED_CHUNKS = LANES;      // reads per chunk, chunks per warp per tile
     constexpr bool ST = MODE >= 1;      // the tile's cells live in shared memory
     constexpr bool FUSED = MODE == 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -587,15 +626,17 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (WMAX > 10 ? 2 : SCAR_FUS
     ScarTableRef TB; ScarAccRef AC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tile_step = (int64_t)gridDim.x * K3_TILE;
-    uint32_t ring_addr = 0, ring_bar = 0, ring_use0 = 0, ring_use1 = 0;      // this warp's ring, slot use counts (parity)
+    uint32_t ring_addr = 0, ring_bar = 0;                    // this warp's slots and their mbarriers
+    uint32_t ring_phase[FUSED_SLOTS] = {};                   // staged chunks consumed per slot (mbarrier parity)
+    ChunkDesc ring_desc[FUSED_SLOTS];                        // descriptors of the chunks in flight (statically indexed)
     if (FUSED) {
         const uint32_t cells_bytes = ((uint32_t)P.W * K3_TILE * 8u + 15u) & ~15u;
         ring_addr = smem_u32(tile_buf) + cells_bytes + (uint32_t)warp * FUSED_SLOTS * P.raw_cap;
         ring_bar = smem_u32(bar) + 16u + (uint32_t)warp * FUSED_SLOTS * 8u;
         if (threadIdx.x == 0) { s_unassigned = 0; s_new = 0; }
         if (lane == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bar));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bar + 8u));
+#pragma unroll
+            for (int sl = 0; sl < FUSED_SLOTS; ++sl) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bar + 8u * sl));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         TB.slots = P.slots; TB.slot_mask = P.slot_mask; TB.max_probe = P.max_probe; TB.status = P.status;
@@ -606,10 +647,11 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (WMAX > 10 ? 2 : SCAR_FUS
         if (P.aggregate && P.hist_smem)
             for (int i = threadIdx.x; i < P.n_samples * per_sample; i += K3_TILE) s_hist[i] = 0;
         __syncwarp();
-        // prologue of the warp's pipeline: the first two chunks of its first tile
-        for (int c = 0; c < FUSED_SLOTS; ++c) {
-            const ChunkDesc d = chunk_desc(P.seq, (int64_t)blockIdx.x * K3_TILE + 32 * warp + FUSED_CHUNK * c, P.n_reads, P.raw_cap);
-            if (d.staged && lane == 0) chunk_issue(d, ring_addr + (uint32_t)c * P.raw_cap, ring_bar + 8u * (uint32_t)c);
+        // prologue of the warp's pipeline: the first chunk(s) of its first tile
+#pragma unroll
+        for (int sl = 0; sl < FUSED_SLOTS; ++sl) {
+            ring_desc[sl] = chunk_desc(P.seq, (int64_t)blockIdx.x * K3_TILE + 32 * warp + FUSED_CHUNK * sl, FUSED_CHUNK, P.n_reads, P.raw_cap);
+            if (ring_desc[sl].staged && lane == 0) chunk_issue(ring_desc[sl], ring_addr + (uint32_t)sl * P.raw_cap, ring_bar + 8u * sl);
         }
     }
     __syncthreads();
@@ -634,24 +676,24 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (WMAX > 10 ? 2 : SCAR_FUS
                 acc_flush(AC, s_hist, per_sample);
                 epoch = 1;
             }
-            // ---- K1 in shared memory, one pipeline per warp (see pack_chunk): the warp's 32 reads in 4 chunks
+            // ---- K1 in shared memory, one pipeline per warp (see pack_chunk): the warp's 32 reads in FUSED_CHUNKS chunks
             __syncwarp();                                 // phase 3 of the previous tile read this warp's cells
             const int64_t w0 = tile + 32 * warp;
+            static_assert(FUSED_CHUNKS % FUSED_SLOTS == 0, "a tile's chunks must cycle through the slots evenly");
 #pragma unroll 1
-            for (int c = 0; c < 32 / FUSED_CHUNK; ++c) {
-                const int slot = c & 1;
-                const uint32_t slot_addr = ring_addr + (uint32_t)slot * P.raw_cap, slot_bar = ring_bar + 8u * (uint32_t)slot;
-                const ChunkDesc d = chunk_desc(P.seq, w0 + FUSED_CHUNK * c, P.n_reads, P.raw_cap);
-                if (d.staged) {
-                    chunk_wait(slot_bar, (slot ? ring_use1 : ring_use0) & 1u);
-                    if (slot) ++ring_use1; else ++ring_use0;
+            for (int c0 = 0; c0 < FUSED_CHUNKS; c0 += FUSED_SLOTS) {
+#pragma unroll
+                for (int sl = 0; sl < FUSED_SLOTS; ++sl) {
+                    const int c = c0 + sl;
+                    const uint32_t slot_addr = ring_addr + (uint32_t)sl * P.raw_cap, slot_bar = ring_bar + 8u * sl;
+                    if (ring_desc[sl].staged) { chunk_wait(slot_bar, ring_phase[sl] & 1u); ++ring_phase[sl]; }
+                    pack_chunk<LANES>(P, ring_desc[sl], slot_addr, w0 + FUSED_CHUNK * c, 32 * warp + FUSED_CHUNK * c, s_cells, s_ctx);
+                    __syncwarp();                         // every lane has read the slot: refill it FUSED_SLOTS chunks ahead
+                    const int64_t rn = c + FUSED_SLOTS < FUSED_CHUNKS ? w0 + FUSED_CHUNK * (c + FUSED_SLOTS)
+                                                                      : w0 + tile_step + FUSED_CHUNK * (c + FUSED_SLOTS - FUSED_CHUNKS);
+                    ring_desc[sl] = chunk_desc(P.seq, rn, FUSED_CHUNK, P.n_reads, P.raw_cap);
+                    if (ring_desc[sl].staged && lane == 0) chunk_issue(ring_desc[sl], slot_addr, slot_bar);
                 }
-                pack_chunk(P, d, slot_addr, w0 + FUSED_CHUNK * c, 32 * warp + FUSED_CHUNK * c, s_cells, s_ctx);
-                __syncwarp();                             // every lane has read the slot: refill it two chunks ahead
-                const int64_t rn = c + FUSED_SLOTS < 32 / FUSED_CHUNK ? w0 + FUSED_CHUNK * (c + FUSED_SLOTS)
-                                                                      : w0 + tile_step + FUSED_CHUNK * (c + FUSED_SLOTS - 32 / FUSED_CHUNK);
-                const ChunkDesc dn = chunk_desc(P.seq, rn, P.n_reads, P.raw_cap);
-                if (dn.staged && lane == 0) chunk_issue(dn, slot_addr, slot_bar);
             }
             __syncwarp();
             info = in_range ? s_ctx[threadIdx.x] : 0u;
@@ -1063,12 +1105,14 @@ bool scar_fused_eligible(int W, int platform)
 static cudaError_t plan_fused(K3Params &P, bool smem_tables, int max_read_len, K3Plan &plan)
 {
     const int threads = K3_TILE;
-    // one ring slot holds a chunk of FUSED_CHUNK fixed-stride reads of the longest length (+ alignment, + 32 bytes of
+    // one ring slot holds a chunk of 32 / lanes fixed-stride reads of the longest length (+ alignment, + 32 bytes of
     // slack for word loads past a read's end); wider spans (FASTQ views) are read from global memory unless the
     // caller asks for larger slots (SCAR_FUSED_SLOT_BYTES)
     const int raw_len = max_read_len + (P.platform == SCAR_PLATFORM_TRUSEQ ? 12 : 0);
-    uint32_t slot = ((uint32_t)FUSED_CHUNK * (uint32_t)raw_len + 16u + 32u + 15u) & ~15u;
-    if (P.seq.offsets && P.seq.lengths) slot = ((uint32_t)FUSED_CHUNK * (2u * (uint32_t)raw_len + 64u) + 48u + 15u) & ~15u;   // FASTQ records
+    // lanes per read: 2 (16-read chunks) for reads up to 160 nt, 4 (8-read chunks: half the ring) for longer reads
+    const int lanes = P.W <= 10 ? 2 : 4, chunk = 32 / lanes;
+    uint32_t slot = ((uint32_t)chunk * (uint32_t)raw_len + 16u + 32u + 15u) & ~15u;
+    if (P.seq.offsets && P.seq.lengths) slot = ((uint32_t)chunk * (2u * (uint32_t)raw_len + 64u) + 48u + 15u) & ~15u;   // FASTQ records
     if (const char *e = getenv("SCAR_FUSED_SLOT_BYTES")) { const long v = atol(e); if (v >= 64) slot = ((uint32_t)v + 15u) & ~15u; }
     P.raw_cap = slot;
     const size_t cells_bytes = ((size_t)P.W * threads * 8 + 15) & ~(size_t)15;
@@ -1087,13 +1131,13 @@ static cudaError_t plan_fused(K3Params &P, bool smem_tables, int max_read_len, K
     plan.stage = true;
     plan.smem = base + hist;
     if (plan.smem > 227 * 1024 - 8192) return cudaErrorInvalidConfiguration;
-    const bool hr = P.hr_len > 0, w10 = P.W <= 10;
-    if (w10)
-        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 10> : scar_window_kernel<true, false, 2, 10>)
-                                : (hr ? scar_window_kernel<false, true, 2, 10> : scar_window_kernel<false, false, 2, 10>);
+    const bool hr = P.hr_len > 0;
+    if (lanes == 2)
+        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 2> : scar_window_kernel<true, false, 2, 2>)
+                                : (hr ? scar_window_kernel<false, true, 2, 2> : scar_window_kernel<false, false, 2, 2>);
     else
-        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 20> : scar_window_kernel<true, false, 2, 20>)
-                                : (hr ? scar_window_kernel<false, true, 2, 20> : scar_window_kernel<false, false, 2, 20>);
+        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 4> : scar_window_kernel<true, false, 2, 4>)
+                                : (hr ? scar_window_kernel<false, true, 2, 4> : scar_window_kernel<false, false, 2, 4>);
     cudaError_t e = cudaFuncSetAttribute(plan.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return e;
     plan.per_sm = 0;
