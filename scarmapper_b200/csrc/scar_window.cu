@@ -486,6 +486,15 @@ static __device__ __noinline__ uint2 pack_cell_bytes(const uint8_t *sp, int slen
 // Pack the reads of one chunk: lane -> read k = lane / LANES of the chunk, cells [q * cpl, (q + 1) * cpl) with
 // q = lane % LANES and cpl = ceil(W / LANES).  `lr0` is the tile-local index of the chunk's first read;
 // s_info[local read] receives stored length | N count << 16.
+// byte masks of the first nb (< 16) bytes of a 16-byte cell, one uint4 per nb (last cell of a read)
+__constant__ uint4 SCAR_KEEP_BYTES[16] = {
+    {0x00000000u, 0u, 0u, 0u}, {0x000000FFu, 0u, 0u, 0u}, {0x0000FFFFu, 0u, 0u, 0u}, {0x00FFFFFFu, 0u, 0u, 0u},
+    {0xFFFFFFFFu, 0x00000000u, 0u, 0u}, {0xFFFFFFFFu, 0x000000FFu, 0u, 0u}, {0xFFFFFFFFu, 0x0000FFFFu, 0u, 0u}, {0xFFFFFFFFu, 0x00FFFFFFu, 0u, 0u},
+    {0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u, 0u}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0x000000FFu, 0u}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0x0000FFFFu, 0u}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu, 0u},
+    {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x000000FFu}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x0000FFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu}};
+
+#define FUSED_CPL 5      // cells per lane (ceil(W / LANES) for W <= 10 with 2 lanes and W <= 20 with 4)
+
 template <int LANES>
 __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d, uint32_t slot_addr, int64_t r0, int lr0,
                                            uint64_t *s_cells, uint32_t *s_info)
@@ -502,37 +511,32 @@ __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d
     // in the staged span?  (views that are not in file order may fall outside: those are read from global memory)
     const unsigned long long a = (unsigned long long)(uintptr_t)sp;
     const bool inside = d.staged && a >= d.lo16 && (unsigned long long)(uintptr_t)rp + (unsigned long long)rawlen <= d.lo16 + d.span;
-    const int cpl = (P.W + LANES - 1) / LANES;
-    const int j0 = q * cpl, j1 = min(j0 + cpl, P.W);
+    const int j0 = q * FUSED_CPL;
     uint2 *out = reinterpret_cast<uint2 *>(s_cells + lr0 + k) + (size_t)j0 * K3_TILE;
     int n_count = 0;
     if (inside) {
         const uint32_t a0 = slot_addr + (uint32_t)(a - d.lo16) + 16u * (uint32_t)j0;     // shared address of cell j0's first byte
-        const uint32_t sh = (a0 & 3u) * 8u;
-        uint32_t a4 = a0 & ~3u, wp;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wp) : "r"(a4));
-        int nb = slen - 16 * j0;                            // bases from this cell on
-        for (int j = j0; j < j1; ++j, a4 += 16u, nb -= 16, out += K3_TILE) {
+        const uint32_t sh = (a0 & 3u) * 8u, a4 = a0 & ~3u;
+        const int nb0 = slen - 16 * j0;                     // bases from cell j0 on
+        // the lane's run of FUSED_CPL cells: 4 * FUSED_CPL + 1 aligned words, realigned by one funnel shift each
+        uint32_t w[4 * FUSED_CPL + 1];
+#pragma unroll
+        for (int i = 0; i <= 4 * FUSED_CPL; ++i)
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(a4 + 4u * (uint32_t)i));
+#pragma unroll
+        for (int jj = 0; jj < FUSED_CPL; ++jj) {
+            const int nb = nb0 - 16 * jj;
             uint32_t code = 0u, hi = 0u;
             if (nb > 0) {
-                uint32_t w1, w2, w3, w4;
-                asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a4));
-                asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a4));
-                asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(w3) : "r"(a4));
-                asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(w4) : "r"(a4));
                 uint32_t v[4];
-                v[0] = __funnelshift_r(wp, w1, sh); v[1] = __funnelshift_r(w1, w2, sh);
-                v[2] = __funnelshift_r(w2, w3, sh); v[3] = __funnelshift_r(w3, w4, sh);
-                wp = w4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = __funnelshift_r(w[4 * jj + i], w[4 * jj + i + 1], sh);
                 hi = 0xFFFFu;                               // ACGT mask | N mask << 16
                 if (nb < 16) {                              // last cell of the read: bytes past its end count as 'A' (code 0)
                     hi = (1u << nb) - 1u;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int nbytes = min(max(nb - 4 * i, 0), 4);
-                        const uint32_t keep = nbytes == 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
-                        v[i] = (v[i] & keep) | (0x41414141u & ~keep);
-                    }
+                    const uint4 keep = SCAR_KEEP_BYTES[nb];
+                    v[0] = (v[0] & keep.x) | (0x41414141u & ~keep.x); v[1] = (v[1] & keep.y) | (0x41414141u & ~keep.y);
+                    v[2] = (v[2] & keep.z) | (0x41414141u & ~keep.z); v[3] = (v[3] & keep.w) | (0x41414141u & ~keep.w);
                 }
                 uint32_t x = 0u, pt[4];
 #pragma unroll
@@ -558,13 +562,13 @@ __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d
                     hi = valid | (nmask << 16);
                 }
             }
-            if (have) *out = make_uint2(code, hi);
+            if (have && j0 + jj < P.W) out[(size_t)jj * K3_TILE] = make_uint2(code, hi);
         }
     } else {
-        for (int j = j0; j < j1; ++j, out += K3_TILE) {
-            const uint2 c = have ? pack_cell_bytes(sp, slen, j) : make_uint2(0u, 0u);
+        for (int jj = 0; jj < FUSED_CPL && j0 + jj < P.W; ++jj) {
+            const uint2 c = have ? pack_cell_bytes(sp, slen, j0 + jj) : make_uint2(0u, 0u);
             n_count += __popc(c.y >> 16);
-            if (have) *out = c;
+            if (have) out[(size_t)jj * K3_TILE] = c;
         }
     }
 #pragma unroll
@@ -663,6 +667,7 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
         bool live = r < P.n_reads;
         const bool in_range = live;
         uint32_t info = 0u;                                     // stored length | N count << 16
+        const uint32_t sample = live ? (uint32_t)P.samples[r] : 0xFFFFu;     // (loaded early: used after the pack)
         if (MODE == 1 && live) {
             const uint64_t *src = P.cells + r;
             uint32_t dst = smem_u32(s_cells + threadIdx.x);
@@ -686,13 +691,15 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
                 for (int sl = 0; sl < FUSED_SLOTS; ++sl) {
                     const int c = c0 + sl;
                     const uint32_t slot_addr = ring_addr + (uint32_t)sl * P.raw_cap, slot_bar = ring_bar + 8u * sl;
+                    // the descriptor of the refill first: its loads fly while the chunk is packed
+                    const int64_t rn = c + FUSED_SLOTS < FUSED_CHUNKS ? w0 + FUSED_CHUNK * (c + FUSED_SLOTS)
+                                                                      : w0 + tile_step + FUSED_CHUNK * (c + FUSED_SLOTS - FUSED_CHUNKS);
+                    const ChunkDesc dn = chunk_desc(P.seq, rn, FUSED_CHUNK, P.n_reads, P.raw_cap);
                     if (ring_desc[sl].staged) { chunk_wait(slot_bar, ring_phase[sl] & 1u); ++ring_phase[sl]; }
                     pack_chunk<LANES>(P, ring_desc[sl], slot_addr, w0 + FUSED_CHUNK * c, 32 * warp + FUSED_CHUNK * c, s_cells, s_ctx);
                     __syncwarp();                         // every lane has read the slot: refill it FUSED_SLOTS chunks ahead
-                    const int64_t rn = c + FUSED_SLOTS < FUSED_CHUNKS ? w0 + FUSED_CHUNK * (c + FUSED_SLOTS)
-                                                                      : w0 + tile_step + FUSED_CHUNK * (c + FUSED_SLOTS - FUSED_CHUNKS);
-                    ring_desc[sl] = chunk_desc(P.seq, rn, FUSED_CHUNK, P.n_reads, P.raw_cap);
-                    if (ring_desc[sl].staged && lane == 0) chunk_issue(ring_desc[sl], slot_addr, slot_bar);
+                    if (dn.staged && lane == 0) chunk_issue(dn, slot_addr, slot_bar);
+                    ring_desc[sl] = dn;
                 }
             }
             __syncwarp();
@@ -702,7 +709,6 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
         rec.status = SCAR_ST_UNASSIGNED; rec.flags = 0; rec.sample = SCAR_SAMPLE_NONE;
         rec.clj = rec.crj = rec.tlj = rec.trj = 0; rec.hr_n = 0;
         rec.phase_r1 = SCAR_PHASE_NA; rec.phase_r2 = SCAR_PHASE_NA;
-        const uint32_t sample = live ? (uint32_t)P.samples[r] : 0xFFFFu;
         if (sample >= (uint32_t)P.n_samples) live = false;      // unidentified (INDEL_Processing.py:1194-1198)
         else rec.sample = (uint16_t)sample;
         if (!FUSED) info = live ? P.lens[r] : 0u;                // stored length | N count << 16 (from K1)
