@@ -493,7 +493,24 @@ __constant__ uint4 SCAR_KEEP_BYTES[16] = {
     {0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u, 0u}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0x000000FFu, 0u}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0x0000FFFFu, 0u}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu, 0u},
     {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00000000u}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x000000FFu}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x0000FFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu}};
 
-#define FUSED_CPL 5      // cells per lane (ceil(W / LANES) for W <= 10 with 2 lanes and W <= 20 with 4)
+// exact masks of a cell that holds a non-ACGT byte (rare; out of line so that the pack loop stays small):
+// returns code | (ACGT mask | N mask << 16) << 32, `hi_in` = mask of the bases that exist
+static __device__ __noinline__ uint2 pack_cell_masks(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t code, uint32_t hi_in)
+{
+    const uint32_t v[4] = {v0, v1, v2, v3};
+    uint32_t valid = 0u, nmask = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        valid |= flags_to_nibble(zero_bytes(acgt_diff4(v[i]))) << (4 * i);
+        nmask |= flags_to_nibble(zero_bytes(v[i] ^ 0x4E4E4E4Eu)) << (4 * i);
+    }
+    valid &= hi_in; nmask &= hi_in;
+    // spread the ACGT mask to 2 bits per base to clear the codes of non-ACGT bases
+    uint32_t m2 = valid;
+    m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
+    m2 = (m2 | (m2 << 2)) & 0x33333333u; m2 = (m2 | (m2 << 1)) & 0x55555555u;
+    return make_uint2(code & (m2 * 3u), valid | (nmask << 16));
+}
 
 template <int LANES>
 __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d, uint32_t slot_addr, int64_t r0, int lr0,
@@ -511,64 +528,49 @@ __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d
     // in the staged span?  (views that are not in file order may fall outside: those are read from global memory)
     const unsigned long long a = (unsigned long long)(uintptr_t)sp;
     const bool inside = d.staged && a >= d.lo16 && (unsigned long long)(uintptr_t)rp + (unsigned long long)rawlen <= d.lo16 + d.span;
-    const int j0 = q * FUSED_CPL;
+    const int cpl = (P.W + LANES - 1) / LANES;
+    const int j0 = q * cpl, j1 = min(j0 + cpl, P.W);
     uint2 *out = reinterpret_cast<uint2 *>(s_cells + lr0 + k) + (size_t)j0 * K3_TILE;
     int n_count = 0;
     if (inside) {
         const uint32_t a0 = slot_addr + (uint32_t)(a - d.lo16) + 16u * (uint32_t)j0;     // shared address of cell j0's first byte
-        const uint32_t sh = (a0 & 3u) * 8u, a4 = a0 & ~3u;
-        const int nb0 = slen - 16 * j0;                     // bases from cell j0 on
-        // the lane's run of FUSED_CPL cells: 4 * FUSED_CPL + 1 aligned words, realigned by one funnel shift each
-        uint32_t w[4 * FUSED_CPL + 1];
-#pragma unroll
-        for (int i = 0; i <= 4 * FUSED_CPL; ++i)
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(a4 + 4u * (uint32_t)i));
-#pragma unroll
-        for (int jj = 0; jj < FUSED_CPL; ++jj) {
-            const int nb = nb0 - 16 * jj;
-            uint32_t code = 0u, hi = 0u;
-            if (nb > 0) {
-                uint32_t v[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = __funnelshift_r(w[4 * jj + i], w[4 * jj + i + 1], sh);
-                hi = 0xFFFFu;                               // ACGT mask | N mask << 16
-                if (nb < 16) {                              // last cell of the read: bytes past its end count as 'A' (code 0)
-                    hi = (1u << nb) - 1u;
-                    const uint4 keep = SCAR_KEEP_BYTES[nb];
-                    v[0] = (v[0] & keep.x) | (0x41414141u & ~keep.x); v[1] = (v[1] & keep.y) | (0x41414141u & ~keep.y);
-                    v[2] = (v[2] & keep.z) | (0x41414141u & ~keep.z); v[3] = (v[3] & keep.w) | (0x41414141u & ~keep.w);
-                }
-                uint32_t x = 0u, pt[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    pt[i] = codes_to_top_byte(v[i]);
-                    x |= acgt_diff4(v[i]);
-                }
-                code = __byte_perm(__byte_perm(pt[0], pt[1], 0x0073), __byte_perm(pt[2], pt[3], 0x0073), 0x5410);
-                if (x != 0u) {                              // rare: a non-ACGT byte in the cell
-                    uint32_t valid = 0u, nmask = 0u;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        valid |= flags_to_nibble(zero_bytes(acgt_diff4(v[i]))) << (4 * i);
-                        nmask |= flags_to_nibble(zero_bytes(v[i] ^ 0x4E4E4E4Eu)) << (4 * i);
-                    }
-                    valid &= hi; nmask &= hi;
-                    n_count += __popc(nmask);
-                    // spread the ACGT mask to 2 bits per base to clear the codes of non-ACGT bases
-                    uint32_t m2 = valid;
-                    m2 = (m2 | (m2 << 8)) & 0x00FF00FFu; m2 = (m2 | (m2 << 4)) & 0x0F0F0F0Fu;
-                    m2 = (m2 | (m2 << 2)) & 0x33333333u; m2 = (m2 | (m2 << 1)) & 0x55555555u;
-                    code &= m2 * 3u;
-                    hi = valid | (nmask << 16);
-                }
+        const uint32_t sh = (a0 & 3u) * 8u;
+        uint32_t a4 = a0 & ~3u, wp;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wp) : "r"(a4));
+        int nb = slen - 16 * j0;                            // bases from this cell on
+        for (int j = j0; j < j1; ++j, a4 += 16u, nb -= 16, out += K3_TILE) {
+            uint32_t w1, w2, w3, w4;
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a4));
+            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a4));
+            asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(w3) : "r"(a4));
+            asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(w4) : "r"(a4));
+            uint32_t v0 = __funnelshift_r(wp, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+            uint32_t v2 = __funnelshift_r(w2, w3, sh), v3 = __funnelshift_r(w3, w4, sh);
+            wp = w4;
+            uint32_t hi = 0xFFFFu;                          // ACGT mask | N mask << 16
+            if (nb < 16) {                                  // the read ends in (or before) this cell: bytes past its end count as 'A' (code 0)
+                const int nbc = max(nb, 0);
+                hi = (1u << nbc) - 1u;
+                const uint4 keep = SCAR_KEEP_BYTES[nbc];
+                v0 = (v0 & keep.x) | (0x41414141u & ~keep.x); v1 = (v1 & keep.y) | (0x41414141u & ~keep.y);
+                v2 = (v2 & keep.z) | (0x41414141u & ~keep.z); v3 = (v3 & keep.w) | (0x41414141u & ~keep.w);
             }
-            if (have && j0 + jj < P.W) out[(size_t)jj * K3_TILE] = make_uint2(code, hi);
+            const uint32_t x = acgt_diff4(v0) | acgt_diff4(v1) | acgt_diff4(v2) | acgt_diff4(v3);
+            uint2 cell;
+            cell.x = __byte_perm(__byte_perm(codes_to_top_byte(v0), codes_to_top_byte(v1), 0x0073),
+                                 __byte_perm(codes_to_top_byte(v2), codes_to_top_byte(v3), 0x0073), 0x5410);
+            cell.y = hi;
+            if (x != 0u) {                                  // rare: a non-ACGT byte in the cell
+                cell = pack_cell_masks(v0, v1, v2, v3, cell.x, hi);
+                n_count += __popc(cell.y >> 16);
+            }
+            if (have) *out = cell;
         }
     } else {
-        for (int jj = 0; jj < FUSED_CPL && j0 + jj < P.W; ++jj) {
-            const uint2 c = have ? pack_cell_bytes(sp, slen, j0 + jj) : make_uint2(0u, 0u);
+        for (int j = j0; j < j1; ++j, out += K3_TILE) {
+            const uint2 c = have ? pack_cell_bytes(sp, slen, j) : make_uint2(0u, 0u);
             n_count += __popc(c.y >> 16);
-            if (have) out[(size_t)jj * K3_TILE] = c;
+            if (have) *out = c;
         }
     }
 #pragma unroll
