@@ -293,3 +293,43 @@ __device__ __forceinline__ void acc_flush(const ScarAccRef &A, unsigned int *s_h
         }
     }
 }
+
+// The same without a barrier, for accumulators that other warps keep adding to: every word is emptied with an atomic
+// exchange, so an increment lands either in this flush or in a later one.  `t` / `nt`: index and number of the
+// calling threads.
+__device__ __forceinline__ void acc_flush_exch(const ScarAccRef &A, unsigned int *s_hist, int per_sample, int t, int nt)
+{
+    const int pb = A.pb;
+    constexpr unsigned long long FIELD_IDS =
+        ((unsigned long long)SCAR_CT_ASSIGNED << 0) | ((unsigned long long)SCAR_CT_PASSING << 4) |
+        ((unsigned long long)SCAR_CT_FILTERED << 8) | ((unsigned long long)SCAR_CT_NO_JUNCTION << 12) |
+        ((unsigned long long)SCAR_CT_NO_CUT << 16) | ((unsigned long long)SCAR_CT_N_INSERTION << 20) |
+        ((unsigned long long)SCAR_CT_SCAR << 24) | ((unsigned long long)SCAR_CT_LEFT_DEL << 28) |
+        ((unsigned long long)SCAR_CT_RIGHT_DEL << 32) | ((unsigned long long)SCAR_CT_INSERTION << 36) |
+        ((unsigned long long)SCAR_CT_MICROHOM << 40) | ((unsigned long long)SCAR_CT_HR_FIRST << 44);
+    for (int i = t; i < A.n_samples * per_sample; i += nt) {
+        if (!s_hist[i]) continue;
+        const unsigned int v = atomicExch(s_hist + i, 0u);
+        if (!v) continue;
+        const int s = i / per_sample, c = i - s * per_sample;
+        unsigned long long *cnt = A.counters + (size_t)s * SCAR_N_COUNTERS;
+        unsigned long long *ph = A.phase_hist + (size_t)s * 2 * SCAR_PHASE_BINS;
+        if (c < 6) {
+            const int f0 = (int)((FIELD_IDS >> (8 * c)) & 15ull), f1 = (int)((FIELD_IDS >> (8 * c + 4)) & 15ull);
+            if (v & 0xFFFFu) atomicAdd(cnt + f0, (unsigned long long)(v & 0xFFFFu));
+            if (v >> 16) atomicAdd(cnt + f1, (unsigned long long)(v >> 16));
+        } else if (c == 6) {
+            atomicAdd(cnt + SCAR_CT_HR_MORE, (unsigned long long)v);
+        } else if (c >= K4_FIXED_WORDS) {
+            const int b = c - K4_FIXED_WORDS;
+            if (A.joint) {
+                const int b1 = b / pb, b2 = b - b1 * pb;
+                atomicAdd(ph + (b1 == pb - 1 ? SCAR_PHASE_BINS - 1 : b1), (unsigned long long)v);
+                atomicAdd(ph + SCAR_PHASE_BINS + (b2 == pb - 1 ? SCAR_PHASE_BINS - 1 : b2), (unsigned long long)v);
+            } else {
+                const int side = b >= pb, k = b - side * pb;
+                atomicAdd(ph + side * SCAR_PHASE_BINS + (k == pb - 1 ? SCAR_PHASE_BINS - 1 : k), (unsigned long long)v);
+            }
+        }
+    }
+}

@@ -454,6 +454,12 @@ __device__ __forceinline__ ChunkDesc chunk_desc(const scar_ragged &seq, int64_t 
     return d;
 }
 
+// ask L2 for a span that a later TMA copy will take (the chunk after the one in flight)
+__device__ __forceinline__ void chunk_prefetch_l2(const ChunkDesc &d)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(d.lo16), "r"(d.span) : "memory");
+}
+
 __device__ __forceinline__ void chunk_issue(const ChunkDesc &d, uint32_t slot_addr, uint32_t bar_addr)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(d.span) : "memory");
@@ -583,19 +589,29 @@ __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d
 // MODE 2: FUSED - input = raw read bytes: the tile's raw span is staged in shared memory by TMA bulk copies, packed
 //         there (the cells overwrite the raw bytes), classified, and in phase 3 the per-sample accumulators and the
 //         scar table are updated as well (what K1, K3 and K4 do in three passes over HBM).
-#ifndef SCAR_FUSED_MIN_CTAS
-#define SCAR_FUSED_MIN_CTAS 3
-#endif
+// groups of 256 threads per CTA of the fused kernel (registers: 64 per thread with 4 groups, 128 with 2)
+__host__ __device__ constexpr int fused_groups_max(int lanes) { return lanes > 2 ? 2 : 4; }
 template <bool SMEM, bool HR, int MODE, int LANES>
-__global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUSED_MIN_CTAS) : SCAR_K3_MIN_CTAS) scar_window_kernel(const K3Params P)
+__global__ void __launch_bounds__(MODE == 2 ? fused_groups_max(LANES) * K3_TILE : K3_TILE, MODE == 2 ? 1 : SCAR_K3_MIN_CTAS)
+scar_window_kernel(const K3Params P)
 {
     constexpr int FUSED_CHUNK = 32 / LANES, FUSED_CHUNKS = LANES;      // reads per chunk, chunks per warp per tile
+    // FUSED: a CTA is up to GMAX independent GROUPS of 256 threads (one tile each at a time, named barriers) that share
+    // the static blob and the accumulators in shared memory - the occupancy of GMAX small CTAs without GMAX copies of
+    // the tables.  tx = thread index inside the group; the other modes have one group.
+    constexpr int GMAX = MODE == 2 ? fused_groups_max(LANES) : 1;
+    const int group = GMAX > 1 ? (int)(threadIdx.x / K3_TILE) : 0, tx = GMAX > 1 ? (int)(threadIdx.x % K3_TILE) : (int)threadIdx.x;
+    const int n_groups = GMAX > 1 ? (int)(blockDim.x / K3_TILE) : 1;
+    auto group_sync = [&]() {
+        if (GMAX > 1) asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(K3_TILE) : "memory");
+        else __syncthreads();
+    };
     constexpr bool ST = MODE >= 1;      // the tile's cells live in shared memory
     constexpr bool FUSED = MODE == 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [mbarriers: blob + (fused) one per warp and ring slot][static blob: tables | target metas | phases |
     // N-limit table][tile buffer: cells (+ fused: raw rings)][fused: accumulators]
-    constexpr uint32_t HDR = FUSED ? 16u + (K3_TILE / 32) * FUSED_SLOTS * 8u : 16u;
+    constexpr uint32_t HDR = FUSED ? 16u + GMAX * (K3_TILE / 32) * FUSED_SLOTS * 8u : 16u;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     const unsigned char *blob = reinterpret_cast<const unsigned char *>(P.blob);
     if (SMEM) {
@@ -611,7 +627,8 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
     // copies its own read's cells there with asynchronous 8-byte copies (no registers, all W in flight at once).
     // MODE 2: they are packed there from the raw bytes in the warps' rings.
     unsigned char *tile_buf = smem_raw + HDR + (SMEM ? P.blob_bytes : 0u);
-    uint64_t *s_cells = reinterpret_cast<uint64_t *>(tile_buf);
+    const uint32_t cells_bytes = ((uint32_t)P.W * K3_TILE * 8u + 15u) & ~15u;
+    uint64_t *s_cells = reinterpret_cast<uint64_t *>(tile_buf + (FUSED ? (uint32_t)group * cells_bytes : 0u));   // [groups][W][256]
 
     // A CTA takes tiles of 256 reads.  Phase 1 is one thread per read: phasing, filters, and the FIRST anchor
     // step of both junction searches (a wild-type read is finished there).  Searches that are still open
@@ -619,27 +636,31 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
     // the back - and are then worked off in rounds by WHICHEVER thread comes next (batch step + anchor step,
     // re-queued while open), so every warp of a round runs one code path with all lanes busy instead of
     // waiting for the slowest read of the warp.  Phase 3 is one thread per read again: junction call, record.
-    __shared__ uint32_t s_left[K3_TILE], s_right[K3_TILE];   // clj | tlj << 16,  crj | trj << 16
-    __shared__ uint32_t s_ctx[K3_TILE];                      // stored length | target id << 16
-    __shared__ uint32_t s_queue[2][2 * K3_TILE];             // item = local read | p << 8
-    __shared__ uint32_t s_count[3][2];                       // [round % 3][side]
-    __shared__ unsigned int s_unassigned, s_new;             // fused: aggregation
-    if (threadIdx.x < 6) s_count[threadIdx.x >> 1][threadIdx.x & 1] = 0;
+    __shared__ uint32_t g_left[GMAX][K3_TILE], g_right[GMAX][K3_TILE];   // clj | tlj << 16,  crj | trj << 16
+    __shared__ uint32_t g_ctx[GMAX][K3_TILE];                            // stored length | target id << 16
+    __shared__ uint32_t g_queue[GMAX][2][2 * K3_TILE];                   // item = local read | p << 8
+    __shared__ uint32_t g_count[GMAX][3][2];                             // [round % 3][side]
+    __shared__ unsigned int g_unassigned[GMAX], g_new[GMAX];             // fused: aggregation
+    uint32_t *s_left = g_left[group], *s_right = g_right[group], *s_ctx = g_ctx[group];
+    uint32_t (*s_queue)[2 * K3_TILE] = g_queue[group];
+    uint32_t (*s_count)[2] = g_count[group];
+    unsigned int &s_unassigned = g_unassigned[group], &s_new = g_new[group];
+    if (tx < 6) s_count[tx >> 1][tx & 1] = 0;
 
     // ---- fused: accumulators of the aggregation, the warps' raw rings and their mbarriers
     unsigned int *s_hist = nullptr;
     int per_sample = 0;
     ScarTableRef TB; ScarAccRef AC;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tile_step = (int64_t)gridDim.x * K3_TILE;
+    const int warp = tx >> 5, lane = tx & 31;                // warp inside the group
+    const int64_t tile_step = (int64_t)gridDim.x * n_groups * K3_TILE;
     uint32_t ring_addr = 0, ring_bar = 0;                    // this warp's slots and their mbarriers
     uint32_t ring_phase[FUSED_SLOTS] = {};                   // staged chunks consumed per slot (mbarrier parity)
     ChunkDesc ring_desc[FUSED_SLOTS];                        // descriptors of the chunks in flight (statically indexed)
     if (FUSED) {
-        const uint32_t cells_bytes = ((uint32_t)P.W * K3_TILE * 8u + 15u) & ~15u;
-        ring_addr = smem_u32(tile_buf) + cells_bytes + (uint32_t)warp * FUSED_SLOTS * P.raw_cap;
-        ring_bar = smem_u32(bar) + 16u + (uint32_t)warp * FUSED_SLOTS * 8u;
-        if (threadIdx.x == 0) { s_unassigned = 0; s_new = 0; }
+        const uint32_t warp_all = (uint32_t)(group * (K3_TILE / 32) + warp);
+        ring_addr = smem_u32(tile_buf) + (uint32_t)n_groups * cells_bytes + warp_all * FUSED_SLOTS * P.raw_cap;
+        ring_bar = smem_u32(bar) + 16u + warp_all * FUSED_SLOTS * 8u;
+        if (tx == 0) { s_unassigned = 0; s_new = 0; }
         if (lane == 0) {
 #pragma unroll
             for (int sl = 0; sl < FUSED_SLOTS; ++sl) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bar + 8u * sl));
@@ -649,14 +670,14 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
         AC.counters = P.counters; AC.phase_hist = P.phase_hist; AC.unassigned = P.unassigned; AC.n_samples = P.n_samples;
         AC.pb = P.phase_bins; AC.joint = P.phase_joint;
         per_sample = acc_words_per_sample(AC.pb, AC.joint);
-        s_hist = reinterpret_cast<unsigned int *>(tile_buf + cells_bytes + (K3_TILE / 32) * FUSED_SLOTS * P.raw_cap);
+        s_hist = reinterpret_cast<unsigned int *>(tile_buf + (uint32_t)n_groups * (cells_bytes + (K3_TILE / 32) * FUSED_SLOTS * P.raw_cap));
         if (P.aggregate && P.hist_smem)
-            for (int i = threadIdx.x; i < P.n_samples * per_sample; i += K3_TILE) s_hist[i] = 0;
+            for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) s_hist[i] = 0;
         __syncwarp();
         // prologue of the warp's pipeline: the first chunk(s) of its first tile
 #pragma unroll
         for (int sl = 0; sl < FUSED_SLOTS; ++sl) {
-            ring_desc[sl] = chunk_desc(P.seq, (int64_t)blockIdx.x * K3_TILE + 32 * warp + FUSED_CHUNK * sl, FUSED_CHUNK, P.n_reads, P.raw_cap);
+            ring_desc[sl] = chunk_desc(P.seq, ((int64_t)blockIdx.x * n_groups + group) * K3_TILE + 32 * warp + FUSED_CHUNK * sl, FUSED_CHUNK, P.n_reads, P.raw_cap);
             if (ring_desc[sl].staged && lane == 0) chunk_issue(ring_desc[sl], ring_addr + (uint32_t)sl * P.raw_cap, ring_bar + 8u * sl);
         }
     }
@@ -664,29 +685,30 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
     uint32_t round = 0;
     int epoch = 0;
 
-    for (int64_t tile = (int64_t)blockIdx.x * K3_TILE; tile < P.n_reads; tile += (int64_t)gridDim.x * K3_TILE) {
-        const int64_t r = tile + threadIdx.x;
+    for (int64_t tile = ((int64_t)blockIdx.x * n_groups + group) * K3_TILE; tile < P.n_reads; tile += tile_step) {
+        const int64_t r = tile + tx;
         bool live = r < P.n_reads;
         const bool in_range = live;
         uint32_t info = 0u;                                     // stored length | N count << 16
         const uint32_t sample = live ? (uint32_t)P.samples[r] : 0xFFFFu;     // (loaded early: used after the pack)
         if (MODE == 1 && live) {
             const uint64_t *src = P.cells + r;
-            uint32_t dst = smem_u32(s_cells + threadIdx.x);
+            uint32_t dst = smem_u32(s_cells + tx);
             for (int j = 0; j < P.W; ++j, src += S, dst += K3_TILE * 8)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         if (FUSED) {
-            if (P.aggregate && P.hist_smem && ++epoch > K4_EPOCH_ITERS) {      // 16-bit packed counters: flush in time
-                __syncthreads();
-                acc_flush(AC, s_hist, per_sample);
+            // 16-bit packed counters shared by the CTA's groups: every group empties them (atomic exchange, no barrier)
+            // before the reads taken by all groups since anybody's last flush can reach 2^16
+            if (P.aggregate && P.hist_smem && ++epoch > 65535 / (K3_TILE * n_groups) - 2) {
+                acc_flush_exch(AC, s_hist, per_sample, tx, K3_TILE);
                 epoch = 1;
             }
             // ---- K1 in shared memory, one pipeline per warp (see pack_chunk): the warp's 32 reads in FUSED_CHUNKS chunks
             __syncwarp();                                 // phase 3 of the previous tile read this warp's cells
             const int64_t w0 = tile + 32 * warp;
-            static_assert(FUSED_CHUNKS % FUSED_SLOTS == 0, "a tile's chunks must cycle through the slots evenly");
+            static_assert(!FUSED || FUSED_CHUNKS % FUSED_SLOTS == 0, "a tile's chunks must cycle through the slots evenly");
 #pragma unroll 1
             for (int c0 = 0; c0 < FUSED_CHUNKS; c0 += FUSED_SLOTS) {
 #pragma unroll
@@ -702,10 +724,19 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
                     __syncwarp();                         // every lane has read the slot: refill it FUSED_SLOTS chunks ahead
                     if (dn.staged && lane == 0) chunk_issue(dn, slot_addr, slot_bar);
                     ring_desc[sl] = dn;
+#ifdef FUSED_L2_PREFETCH
+                    {   // the chunk after the refill goes to L2 now, so that its copy (issued one pack later) is short
+                        const int cc = c + 2 * FUSED_SLOTS;
+                        const int64_t rp2 = cc < FUSED_CHUNKS ? w0 + FUSED_CHUNK * cc
+                                          : (cc < 2 * FUSED_CHUNKS ? w0 + tile_step + FUSED_CHUNK * (cc - FUSED_CHUNKS) : w0 + 2 * tile_step + FUSED_CHUNK * (cc - 2 * FUSED_CHUNKS));
+                        const ChunkDesc dp = chunk_desc(P.seq, rp2, FUSED_CHUNK, P.n_reads, P.raw_cap);
+                        if (dp.staged && lane == 0) chunk_prefetch_l2(dp);
+                    }
+#endif
                 }
             }
             __syncwarp();
-            info = in_range ? s_ctx[threadIdx.x] : 0u;
+            info = in_range ? s_ctx[tx] : 0u;
         }
         __align__(16) scar_record rec;
         rec.status = SCAR_ST_UNASSIGNED; rec.flags = 0; rec.sample = SCAR_SAMPLE_NONE;
@@ -722,7 +753,7 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
         const int Wr = (len + 15) >> 4;                          // cells that hold bases
         const int cut = T.cutsite;
         int clj = 0, crj = 0, tlj = cut, trj = cut;
-        RC rc0; rc0.col = col; rc0.S = S; rc0.sc = s_cells + threadIdx.x; rc0.Wr = Wr;
+        RC rc0; rc0.col = col; rc0.S = S; rc0.sc = s_cells + tx; rc0.Wr = Wr;
         if (MODE == 1) asm volatile("cp.async.wait_all;" ::: "memory");
 
         if (live) {
@@ -789,13 +820,13 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
             bool open = fast && p >= 16;
             if (open) open = left_anchor<SMEM>(rc, ptab, LR, p, clj, tlj);
             __syncwarp();
-            queue_push(open, (uint32_t)threadIdx.x | ((uint32_t)p << 8), &s_queue[round & 1][0], 1, &s_count[round % 3][0]);
+            queue_push(open, (uint32_t)tx | ((uint32_t)p << 8), &s_queue[round & 1][0], 1, &s_count[round % 3][0]);
             const int plast = len - 26;
             p = 10;
             open = fast && plast >= 10;
             if (open) open = right_anchor<SMEM>(rc, ptab, LR, plast, p, crj, trj);
             __syncwarp();
-            queue_push(open, (uint32_t)threadIdx.x | ((uint32_t)p << 8), &s_queue[round & 1][2 * K3_TILE - 1], -1,
+            queue_push(open, (uint32_t)tx | ((uint32_t)p << 8), &s_queue[round & 1][2 * K3_TILE - 1], -1,
                        &s_count[round % 3][1]);
         }
         bool cutwindow_done = false;          // the exhaustive path checks the cut window itself
@@ -879,22 +910,22 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
         __syncwarp();
 
 
-        s_left[threadIdx.x] = (uint32_t)clj | ((uint32_t)tlj << 16);
-        s_right[threadIdx.x] = (uint32_t)crj | ((uint32_t)trj << 16);
-        s_ctx[threadIdx.x] = (uint32_t)len | ((uint32_t)tid << 16);
+        s_left[tx] = (uint32_t)clj | ((uint32_t)tlj << 16);
+        s_right[tx] = (uint32_t)crj | ((uint32_t)trj << 16);
+        s_ctx[tx] = (uint32_t)len | ((uint32_t)tid << 16);
 
         // ---- phase 2: rounds over the open searches of the tile
         for (;;) {
-            __syncthreads();
+            group_sync();
             const uint32_t *q = s_queue[round & 1];
             uint32_t *qn = s_queue[(round + 1) & 1];
             const int nl = (int)s_count[round % 3][0], nr = (int)s_count[round % 3][1];
-            if (threadIdx.x == 0) { s_count[(round + 2) % 3][0] = 0; s_count[(round + 2) % 3][1] = 0; }
+            if (tx == 0) { s_count[(round + 2) % 3][0] = 0; s_count[(round + 2) % 3][1] = 0; }
             // (the next tile queues into the NEXT slot: a thread that leaves early must not be seen by one that
             // has not read this round's counts yet)
             if (nl + nr == 0) { ++round; break; }
             const int nl32 = (nl + 31) & ~31;                 // warps are pure left or pure right
-            for (int v = threadIdx.x; v < nl32 + ((nr + 31) & ~31); v += K3_TILE) {
+            for (int v = tx; v < nl32 + ((nr + 31) & ~31); v += K3_TILE) {
                 const bool is_left = v < nl32;
                 const int k = is_left ? v : v - nl32;
                 const bool have = k < (is_left ? nl : nr);
@@ -933,7 +964,7 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
 
         // ---- phase 3: one thread per read again
         {
-            const uint32_t a = s_left[threadIdx.x], b = s_right[threadIdx.x];
+            const uint32_t a = s_left[tx], b = s_right[tx];
             clj = (int)(a & 0xFFFFu); tlj = (int)(a >> 16); crj = (int)(b & 0xFFFFu); trj = (int)(b >> 16);
         }
         if (live && !cutwindow_done && clj && T.cutwindow_key != 0xFFFFFFFFu) {   // SlidingWindow.pyx:56-60 (per-read drop-in only)
@@ -1035,15 +1066,15 @@ __global__ void __launch_bounds__(K3_TILE, MODE == 2 ? (LANES > 2 ? 2 : SCAR_FUS
         }
     }
     if (FUSED && P.aggregate) {
-        __syncthreads();
-        if (P.hist_smem) acc_flush(AC, s_hist, per_sample);
-        if (threadIdx.x == 0 && s_unassigned) atomicAdd(P.unassigned, (unsigned long long)s_unassigned);
-        if (threadIdx.x == 0 && s_new) atomicAdd(P.n_entries, (unsigned long long)s_new);
+        group_sync();
+        if (P.hist_smem) acc_flush_exch(AC, s_hist, per_sample, tx, K3_TILE);      // (a slower group flushes what it adds later)
+        if (tx == 0 && s_unassigned) atomicAdd(P.unassigned, (unsigned long long)s_unassigned);
+        if (tx == 0 && s_new) atomicAdd(P.n_entries, (unsigned long long)s_new);
     }
 }
 
 // host-side launcher (called from scar_api.cu)
-struct K3Plan { void (*kern)(const K3Params); size_t smem; int per_sm; bool stage; };
+struct K3Plan { void (*kern)(const K3Params); size_t smem; int per_sm; bool stage; int groups = 1; };
 
 static cudaError_t plan_window(const K3Params &P, bool smem_tables, K3Plan &plan)
 {
@@ -1112,47 +1143,64 @@ bool scar_fused_eligible(int W, int platform)
 
 static cudaError_t plan_fused(K3Params &P, bool smem_tables, int max_read_len, K3Plan &plan)
 {
-    const int threads = K3_TILE;
+    const int threads = K3_TILE, warps = K3_TILE / 32;
     // one ring slot holds a chunk of 32 / lanes fixed-stride reads of the longest length (+ alignment, + 32 bytes of
     // slack for word loads past a read's end); wider spans (FASTQ views) are read from global memory unless the
     // caller asks for larger slots (SCAR_FUSED_SLOT_BYTES)
     const int raw_len = max_read_len + (P.platform == SCAR_PLATFORM_TRUSEQ ? 12 : 0);
     // lanes per read: 2 (16-read chunks) for reads up to 160 nt, 4 (8-read chunks: half the ring) for longer reads
-    const int lanes = P.W <= 10 ? 2 : 4, chunk = 32 / lanes;
+#ifndef FUSED_LANES_SHORT
+#define FUSED_LANES_SHORT 2
+#endif
+    const int lanes = P.W <= 10 ? FUSED_LANES_SHORT : 4, chunk = 32 / lanes, gmax = fused_groups_max(lanes);
     uint32_t slot = ((uint32_t)chunk * (uint32_t)raw_len + 16u + 32u + 15u) & ~15u;
     if (P.seq.offsets && P.seq.lengths) slot = ((uint32_t)chunk * (2u * (uint32_t)raw_len + 64u) + 48u + 15u) & ~15u;   // FASTQ records
     if (const char *e = getenv("SCAR_FUSED_SLOT_BYTES")) { const long v = atol(e); if (v >= 64) slot = ((uint32_t)v + 15u) & ~15u; }
     P.raw_cap = slot;
     const size_t cells_bytes = ((size_t)P.W * threads * 8 + 15) & ~(size_t)15;
-    const size_t buf = cells_bytes + (size_t)(threads / 32) * FUSED_SLOTS * slot;
-    const size_t base = 16 + (threads / 32) * FUSED_SLOTS * 8 + (smem_tables ? P.blob_bytes : 0) + buf;
-    // accumulators: joint phase histogram when it is small, else two marginals; global atomics when neither fits
-    P.hist_smem = 0;
-    size_t hist = 0;
-    if (P.aggregate) {
-        const size_t budget = 227 * 1024 - 8192;
-        for (int joint = P.phase_bins * P.phase_bins <= 32 ? 1 : 0; joint >= 0 && !P.hist_smem; --joint) {
-            const size_t h = (size_t)P.n_samples * acc_words_per_sample(P.phase_bins, joint) * sizeof(unsigned int);
-            if (h <= 48 * 1024 && base + h <= budget) { P.hist_smem = 1; P.phase_joint = joint; hist = h; }
-        }
-    }
-    plan.stage = true;
-    plan.smem = base + hist;
-    if (plan.smem > 227 * 1024 - 8192) return cudaErrorInvalidConfiguration;
+    const size_t per_group = cells_bytes + (size_t)warps * FUSED_SLOTS * slot;
+    const size_t fixed = 16 + (size_t)gmax * warps * FUSED_SLOTS * 8 + (smem_tables ? P.blob_bytes : 0);
     const bool hr = P.hr_len > 0;
+#if FUSED_LANES_SHORT == 1
+    if (lanes == 1)
+        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 1> : scar_window_kernel<true, false, 2, 1>)
+                                : (hr ? scar_window_kernel<false, true, 2, 1> : scar_window_kernel<false, false, 2, 1>);
+    else
+#endif
     if (lanes == 2)
         plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 2> : scar_window_kernel<true, false, 2, 2>)
                                 : (hr ? scar_window_kernel<false, true, 2, 2> : scar_window_kernel<false, false, 2, 2>);
     else
         plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 4> : scar_window_kernel<true, false, 2, 4>)
                                 : (hr ? scar_window_kernel<false, true, 2, 4> : scar_window_kernel<false, false, 2, 4>);
-    cudaError_t e = cudaFuncSetAttribute(plan.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, plan.kern);
+    if (e != cudaSuccess) return e;
+    // what one CTA may use: 227 KB minus the kernel's static arrays (queues and result arrays of gmax groups)
+    const size_t budget = 227 * 1024 - fa.sharedSizeBytes - 1024;
+    // accumulators: joint phase histogram when it is small, else two marginals; global atomics when neither fits
+    P.hist_smem = 0;
+    size_t hist = 0;
+    if (P.aggregate) {
+        for (int joint = P.phase_bins * P.phase_bins <= 32 ? 1 : 0; joint >= 0 && !P.hist_smem; --joint) {
+            const size_t h = (size_t)P.n_samples * acc_words_per_sample(P.phase_bins, joint) * sizeof(unsigned int);
+            if (h <= 48 * 1024 && fixed + per_group + h <= budget) { P.hist_smem = 1; P.phase_joint = joint; hist = h; }
+        }
+    }
+    if (fixed + per_group + hist > budget) return cudaErrorInvalidConfiguration;
+    // groups of 256 threads per CTA: as many as fit beside the shared blob and accumulators
+    int groups = gmax;
+    while (groups > 1 && fixed + (size_t)groups * per_group + hist > budget) --groups;
+    if (const char *e2 = getenv("SCAR_FUSED_GROUPS")) { const int v = atoi(e2); if (v >= 1 && v < groups) groups = v; }
+    plan.stage = true;
+    plan.groups = groups;
+    plan.smem = fixed + (size_t)groups * per_group + hist;
+    e = cudaFuncSetAttribute(plan.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return e;
     plan.per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plan.per_sm, plan.kern, threads, plan.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plan.per_sm, plan.kern, threads * groups, plan.smem);
     if (e != cudaSuccess) return e;
     if (plan.per_sm < 1) plan.per_sm = 1;
-    if (const char *e2 = getenv("SCAR_K3_CTAS_PER_SM")) { const int v = atoi(e2); if (v >= 1 && v < plan.per_sm) plan.per_sm = v; }
     return cudaSuccess;
 }
 
@@ -1161,7 +1209,7 @@ cudaError_t scar_fused_plan(K3Params P, bool smem_tables, int max_read_len, int 
     K3Plan plan;
     cudaError_t e = plan_fused(P, smem_tables, max_read_len, plan);
     if (e != cudaSuccess) return e;
-    if (per_sm) *per_sm = plan.per_sm;
+    if (per_sm) *per_sm = plan.per_sm * plan.groups;       // 256-thread groups resident per SM
     if (smem_bytes) *smem_bytes = (int)plan.smem;
     return cudaSuccess;
 }
@@ -1173,10 +1221,11 @@ cudaError_t scar_launch_fused(K3Params P, bool smem_tables, int max_read_len, in
     K3Plan plan;
     cudaError_t e = plan_fused(P, smem_tables, max_read_len, plan);
     if (e != cudaSuccess) return e;
-    int64_t want = (P.n_reads + threads - 1) / threads;
+    const int64_t tiles = (P.n_reads + threads - 1) / threads;
+    int64_t want = (tiles + plan.groups - 1) / plan.groups;
     int64_t grid = (int64_t)sm_count * plan.per_sm;
     if (grid > want) grid = want;
-    plan.kern<<<(unsigned)grid, threads, plan.smem, stream>>>(P);
+    plan.kern<<<(unsigned)grid, threads * plan.groups, plan.smem, stream>>>(P);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
