@@ -673,8 +673,15 @@ extern "C" int scar_run_dev(scar_ctx *c, const scar_ragged *seq, const scar_ragg
     int rc;
     if ((rc = scar_demux_dev(c, seq, f0, f1, n, samples, stream))) return rc;
     // one pass over the raw bytes (pack, classify, aggregate) when the fused kernel takes the problem
-    if (c && seq && scar_fused_eligible(c->W, c->platform))
-        return scar_classify_raw_dev(c, seq, samples, n, first_index, records, 1, stream);
+    if (c && seq && scar_fused_eligible(c->W, c->platform)) {
+        // (a static blob too large to leave room for a tile beside it: K1 -> K3 -> K4 below)
+        CU(cudaSetDevice(c->device));
+        int per = 0, sm = 0;
+        if (scar_fused_plan(fused_params(c, seq, samples, n, first_index, records, 1), c->smem_tables, c->max_read_len,
+                            &per, &sm) == cudaSuccess)
+            return scar_classify_raw_dev(c, seq, samples, n, first_index, records, 1, stream);
+        cudaGetLastError();
+    }
     if ((rc = scar_pack_dev(c, seq, n, cells, lens, stream))) return rc;
     if ((rc = scar_classify_dev(c, cells, lens, samples, n, records, stream))) return rc;
     return scar_aggregate_dev(c, seq, records, n, first_index, stream);

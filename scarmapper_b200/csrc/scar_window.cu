@@ -1153,12 +1153,7 @@ static cudaError_t plan_fused(K3Params &P, bool smem_tables, int max_read_len, K
 #define FUSED_LANES_SHORT 2
 #endif
     const int lanes = P.W <= 10 ? FUSED_LANES_SHORT : 4, chunk = 32 / lanes, gmax = fused_groups_max(lanes);
-    uint32_t slot = ((uint32_t)chunk * (uint32_t)raw_len + 16u + 32u + 15u) & ~15u;
-    if (P.seq.offsets && P.seq.lengths) slot = ((uint32_t)chunk * (2u * (uint32_t)raw_len + 64u) + 48u + 15u) & ~15u;   // FASTQ records
-    if (const char *e = getenv("SCAR_FUSED_SLOT_BYTES")) { const long v = atol(e); if (v >= 64) slot = ((uint32_t)v + 15u) & ~15u; }
-    P.raw_cap = slot;
     const size_t cells_bytes = ((size_t)P.W * threads * 8 + 15) & ~(size_t)15;
-    const size_t per_group = cells_bytes + (size_t)warps * FUSED_SLOTS * slot;
     const size_t fixed = 16 + (size_t)gmax * warps * FUSED_SLOTS * 8 + (smem_tables ? P.blob_bytes : 0);
     const bool hr = P.hr_len > 0;
 #if FUSED_LANES_SHORT == 1
@@ -1178,6 +1173,18 @@ static cudaError_t plan_fused(K3Params &P, bool smem_tables, int max_read_len, K
     if (e != cudaSuccess) return e;
     // what one CTA may use: 227 KB minus the kernel's static arrays (queues and result arrays of gmax groups)
     const size_t budget = 227 * 1024 - fa.sharedSizeBytes - 1024;
+    // Ring slot: a chunk of fixed-stride reads of the longest length (+ alignment, + 32 bytes of slack for word loads
+    // past a read's end); FASTQ views get slots wide enough for whole records when that still leaves room for two
+    // groups (a chunk whose span does not fit its slot is read from global memory).
+    const uint32_t slot_reads = ((uint32_t)chunk * (uint32_t)raw_len + 16u + 32u + 15u) & ~15u;
+    uint32_t slot = slot_reads;
+    if (P.seq.offsets && P.seq.lengths) {
+        const uint32_t slot_records = ((uint32_t)chunk * (2u * (uint32_t)raw_len + 64u) + 48u + 15u) & ~15u;
+        if (fixed + 2 * (cells_bytes + (size_t)warps * FUSED_SLOTS * slot_records) + 16 * 1024 <= budget) slot = slot_records;
+    }
+    if (const char *e3 = getenv("SCAR_FUSED_SLOT_BYTES")) { const long v = atol(e3); if (v >= 64) slot = ((uint32_t)v + 15u) & ~15u; }
+    P.raw_cap = slot;
+    const size_t per_group = cells_bytes + (size_t)warps * FUSED_SLOTS * slot;
     // accumulators: joint phase histogram when it is small, else two marginals; global atomics when neither fits
     P.hist_smem = 0;
     size_t hist = 0;
@@ -1187,7 +1194,7 @@ static cudaError_t plan_fused(K3Params &P, bool smem_tables, int max_read_len, K
             if (h <= 48 * 1024 && fixed + per_group + h <= budget) { P.hist_smem = 1; P.phase_joint = joint; hist = h; }
         }
     }
-    if (fixed + per_group + hist > budget) return cudaErrorInvalidConfiguration;
+    if (fixed + per_group + hist > budget) return cudaErrorInvalidConfiguration;     // the caller takes the three-kernel path
     // groups of 256 threads per CTA: as many as fit beside the shared blob and accumulators
     int groups = gmax;
     while (groups > 1 && fixed + (size_t)groups * per_group + hist > budget) --groups;
