@@ -72,10 +72,17 @@ static uint64_t encode_bases(const uint8_t *p, int n)
     return c;
 }
 
-struct BucketTable { std::vector<uint2> buckets; uint32_t mult, nbuckets; };
+// ---- "10-mer -> payload" tables of the static blob (layouts: ScarTableDesc, scar_internal.cuh) -------------------
+static void append_aligned(std::vector<unsigned char> &bytes, const void *p, size_t n, uint32_t *off)
+{
+    bytes.resize((bytes.size() + 15) & ~(size_t)15);
+    *off = (uint32_t)bytes.size();
+    bytes.insert(bytes.end(), (const unsigned char *)p, (const unsigned char *)p + n);
+}
 
-// window list -> bucketed perfect hash "10-mer -> smallest i" (two entries per bucket, one probe)
-static bool build_table(const std::vector<std::pair<uint32_t, uint32_t>> &kv /* key, payload */, BucketTable &out)
+// bucketed perfect hash (two entries per 8-byte bucket, one probe)
+static bool build_bucketed(const std::vector<std::pair<uint32_t, uint32_t>> &kv /* key, payload */,
+                           std::vector<unsigned char> &bytes, ScarTableDesc &out)
 {
     // bucket = mulhi((key << 12) * mult, B): any B works, not only powers of two.  With two entries per bucket a
     // collision-free multiplier exists with fair probability once n^3 / (6 B^2) is a few units, so start at
@@ -92,16 +99,78 @@ static bool build_table(const std::vector<std::pair<uint32_t, uint32_t>> &kv /* 
             bool ok = true;
             for (const auto &e : kv) {
                 const uint32_t t = e.first << 12;                  // key in the top 20 bits, as the kernel forms it
-                const uint32_t slot = (uint32_t)(((uint64_t)(t * mult) * B) >> 32);
+                const uint32_t slot = scar_mulhi32(t * mult, B);
                 const uint32_t val = t | e.second;
                 if (b[slot].x == SCAR_TABLE_EMPTY) b[slot].x = val;
                 else if (b[slot].y == SCAR_TABLE_EMPTY) b[slot].y = val;
                 else { ok = false; break; }
             }
-            if (ok) { out.buckets.swap(b); out.mult = mult; out.nbuckets = B; return true; }
+            if (ok) {
+                memset(&out, 0, sizeof(out));
+                append_aligned(bytes, b.data(), b.size() * sizeof(uint2), &out.off);
+                out.mult = mult; out.n = B;
+                return true;
+            }
         }
     }
     return false;
+}
+
+// compact hash-and-displace table: the keys of a displacement bucket are moved together (one displacement per
+// bucket, largest buckets first) until they all fall on free slots
+static bool build_compact(const std::vector<std::pair<uint32_t, uint32_t>> &kv, std::vector<unsigned char> &bytes, ScarTableDesc &out)
+{
+    const size_t n = kv.size();
+    uint32_t N = std::max<uint32_t>(8, (uint32_t)((double)n / 0.72) + 1);
+    const uint32_t nb = std::max<uint32_t>(4, (uint32_t)(n / 3) + 1);
+    uint64_t rng = 0xD1B54A32D192ED03ull ^ (n * 0x9E3779B97F4A7C15ull);
+    for (int round = 0; round < 24; ++round, N += N / 16 + 1) {
+        const uint32_t unit = (uint32_t)((0x100000000ull + N - 1) / N);
+        for (int attempt = 0; attempt < 16; ++attempt) {
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            const uint32_t mult = (uint32_t)(rng >> 32) | 1u;
+            std::vector<std::vector<uint32_t>> members(nb);
+            for (size_t i = 0; i < n; ++i) members[scar_chd_bucket((kv[i].first << 12) * mult, nb)].push_back((uint32_t)i);
+            std::vector<uint32_t> order(nb);
+            for (uint32_t i = 0; i < nb; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return members[a].size() > members[b].size(); });
+            std::vector<uint32_t> ent(N, SCAR_TABLE_EMPTY);
+            std::vector<uint16_t> disp(nb, 0);
+            bool ok = true;
+            for (uint32_t bi = 0; bi < nb && ok; ++bi) {
+                const auto &mem = members[order[bi]];
+                if (mem.empty()) break;
+                bool placed = false;
+                for (uint32_t d = 0; d < 65536u && !placed; ++d) {
+                    bool fit = true;
+                    std::vector<uint32_t> slots;
+                    for (uint32_t i : mem) {
+                        const uint32_t sl = scar_chd_slot((kv[i].first << 12) * mult, d, unit, N);
+                        if (ent[sl] != SCAR_TABLE_EMPTY || std::find(slots.begin(), slots.end(), sl) != slots.end()) { fit = false; break; }
+                        slots.push_back(sl);
+                    }
+                    if (!fit) continue;
+                    for (size_t q = 0; q < mem.size(); ++q) ent[slots[q]] = (kv[mem[q]].first << 12) | kv[mem[q]].second;
+                    disp[order[bi]] = (uint16_t)d;
+                    placed = true;
+                }
+                ok = placed;
+            }
+            if (!ok) continue;
+            memset(&out, 0, sizeof(out));
+            append_aligned(bytes, ent.data(), ent.size() * sizeof(uint32_t), &out.off);
+            append_aligned(bytes, disp.data(), disp.size() * sizeof(uint16_t), &out.doff);
+            out.mult = mult; out.n = N; out.nb = nb; out.unit = unit;
+            return true;
+        }
+    }
+    return false;
+}
+
+static bool build_table(const std::vector<std::pair<uint32_t, uint32_t>> &kv, bool compact, std::vector<unsigned char> &bytes,
+                        ScarTableDesc &out)
+{
+    return compact ? build_compact(kv, bytes, out) : build_bucketed(kv, bytes, out);
 }
 
 // ---- context --------------------------------------------------------------------------------------
@@ -123,7 +192,7 @@ struct scar_ctx {
     std::vector<ScarTargetMeta> h_targets;
     int32_t *d_sample_target = nullptr;
     unsigned char *d_blob = nullptr; uint32_t blob_bytes = 0, meta_off = 0, phase_off = 0, nmax_off = 0;
-    bool smem_tables = true;
+    bool smem_tables = true, compact_tables = false;
     uint8_t *d_class_map = nullptr; DemuxString *d_right = nullptr, *d_left = nullptr; uint64_t *d_peq = nullptr;
     uint16_t *d_first_sample = nullptr; int n_right = 0, n_left = 0, n_classes = 0;
     uint8_t *d_fast_codes = nullptr; int demux_fast = 0;
@@ -318,7 +387,7 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
     }
 
     // targets: window tables (window_mapping, INDEL_Processing.py:57-80)
-    std::vector<uint2> blob;
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> tab_pos(cfg->n_targets), tab_left(cfg->n_targets), tab_right(cfg->n_targets);
     std::vector<ScarPhase> phases;
     std::vector<std::vector<uint32_t>> locus_words;
     std::vector<std::vector<uint8_t>> phase_luts;
@@ -348,10 +417,7 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
         }
         m.fast = fast ? 1 : 0;
         if (fast) {
-            BucketTable bt;
-            if (!build_table(pos_kv, bt)) return fail(SCAR_ERR_UNSUPPORTED, "target %d: could not build a position table", t);
-            m.pos_off = (uint32_t)blob.size(); m.pos_mult = bt.mult; m.pos_buckets = bt.nbuckets;
-            blob.insert(blob.end(), bt.buckets.begin(), bt.buckets.end());
+            tab_pos[t] = pos_kv;
             // packed locus: one word (16 bases) of padding in front, eight behind (a 64-base compare step may
             // start up to 10 bases past the cut and reads three words per 32 bases from an aligned start)
             std::vector<uint32_t> tw((size_t)(L + 15) / 16 + 9, 0u);
@@ -371,12 +437,7 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
                 const uint32_t key = (uint32_t)encode_bases(T + a, 10);
                 if (!mn.count(key)) mn[key] = (uint32_t)i;  // list order: the smallest i wins
             }
-            std::vector<std::pair<uint32_t, uint32_t>> kv(mn.begin(), mn.end());
-            BucketTable bt;
-            if (!build_table(kv, bt)) return fail(SCAR_ERR_UNSUPPORTED, "target %d: could not build a window table", t);
-            if (side == 0) { m.left_off = (uint32_t)blob.size(); m.left_mult = bt.mult; m.left_buckets = bt.nbuckets; }
-            else { m.right_off = (uint32_t)blob.size(); m.right_mult = bt.mult; m.right_buckets = bt.nbuckets; }
-            blob.insert(blob.end(), bt.buckets.begin(), bt.buckets.end());
+            (side == 0 ? tab_left[t] : tab_right[t]).assign(mn.begin(), mn.end());
         }
         m.cutwindow_key = 0xFFFFFFFFu;
         if (cfg->cutwindow_bytes && acgt_only(cfg->cutwindow_bytes + 10 * t, 10))
@@ -442,9 +503,28 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
         // monotone in n, so the first n+1 that exceeds the limit ends the search
     }
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    // The tables: bucketed (one probe) while they are small; a dozen loci would leave a CTA no room for more than
+    // one tile beside them, so past 48 KB (or with SCAR_COMPACT_TABLES=1) the compact layout is built instead.
     std::vector<unsigned char> bytes;
-    bytes.resize(align16(blob.size() * sizeof(uint2)));
-    if (!blob.empty()) memcpy(bytes.data(), blob.data(), blob.size() * sizeof(uint2));
+    auto build_tables = [&](bool compact) -> int {
+        bytes.clear();
+        for (int t = 0; t < cfg->n_targets; ++t) {
+            ScarTargetMeta &m = c->h_targets[t];
+            if (m.fast) {
+                if (!build_table(tab_pos[t], compact, bytes, m.pos)) return t + 1;
+            } else if (!build_table(tab_left[t], compact, bytes, m.left) || !build_table(tab_right[t], compact, bytes, m.right)) return t + 1;
+        }
+        bytes.resize(align16(bytes.size()));
+        return 0;
+    };
+    const char *force = getenv("SCAR_COMPACT_TABLES");
+    c->compact_tables = force && atoi(force) != 0;
+    int bad = build_tables(c->compact_tables);
+    if (!bad && !c->compact_tables && !(force && atoi(force) == 0) && bytes.size() > 48 * 1024) {
+        c->compact_tables = true;
+        bad = build_tables(true);
+    }
+    if (bad) return fail(SCAR_ERR_UNSUPPORTED, "target %d: could not build a window table", bad - 1);
     for (int t = 0; t < cfg->n_targets; ++t) {
         if (!c->h_targets[t].fast) continue;
         c->h_targets[t].tw_off = (uint32_t)bytes.size();
@@ -572,6 +652,7 @@ static K3Params k3_params(const scar_ctx *c)
     P.blob = c->d_blob; P.blob_bytes = c->blob_bytes; P.meta_off = c->meta_off; P.phase_off = c->phase_off;
     P.nmax_off = c->nmax_off; P.W = c->W; P.n_samples = c->n_samples;
     P.do_phasing = c->do_phasing; P.min_length = c->min_length; P.hr_code = c->hr_code; P.hr_len = c->hr_len;
+    P.compact_tables = c->compact_tables ? 1 : 0;
     return P;
 }
 

@@ -32,18 +32,40 @@ __host__ __device__ __forceinline__ bool scar_base_valid(uint8_t b)
 //   bits 48..63  N mask    (1 = byte is 'N')
 // bases past the read's length have all three fields 0.
 
+// A "10-mer -> payload" table in the static blob, entries key << 12 | payload (payload <= 4094, empty = 0xFFFFFFFF).
+// Two layouts, one per context (K3Params.compact_tables):
+//   bucketed  perfect hash with two entries per 8-byte bucket, multiplier searched so that no bucket overflows:
+//             ONE probe (bucket = mulhi(t * mult, n), t = key << 12) - the fastest lookup, ~13 % full;
+//   compact   hash-and-displace (h = t * mult; d = disp[mulhi(h, nb)]; slot = mulhi((h << 8) + d * unit, n)):
+//             two dependent loads, ~72 % full - about a fifth of the shared memory, which is what lets several
+//             groups of a CTA work beside the tables of a dozen loci.
+struct ScarTableDesc {
+    uint32_t off;       // byte offset in the blob of the buckets (uint2) / of the entries (u32)
+    uint32_t mult;
+    uint32_t n;         // buckets / slots
+    uint32_t doff;      // compact: byte offset of the u16 displacements
+    uint32_t nb;        // compact: displacement buckets
+    uint32_t unit;      // compact: ceil(2^32 / n)
+};
+
+// the slot arithmetic of a compact table, shared by the host builder and the kernel
+__host__ __device__ __forceinline__ uint32_t scar_mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+__host__ __device__ __forceinline__ uint32_t scar_chd_bucket(uint32_t h, uint32_t nb) { return scar_mulhi32(h, nb); }
+__host__ __device__ __forceinline__ uint32_t scar_chd_slot(uint32_t h, uint32_t d, uint32_t unit, uint32_t n)
+{
+    return scar_mulhi32((h << 8) + d * unit, n);
+}
+
 struct ScarTargetMeta {
     int32_t cutsite, length;
     int32_t n_left, n_right;
-    uint32_t left_off, right_off;      // bucket (uint2) offsets into the table blob
-    uint32_t left_mult, right_mult;    // bucket = mulhi((key << 12) * mult, buckets)  (top log2(buckets) bits)
-    uint32_t left_buckets, right_buckets;
+    ScarTableDesc left, right;         // exhaustive scan: "10-mer -> smallest window index i" per side
     uint32_t cutwindow_key;            // SlidingWindow.pyx:56-60 test; 0xFFFFFFFF = none
     int32_t phase_off, n_phase;
     // anchor-and-extend path (locus is all ACGT and every 10-mer of it is unique): ONE table
     // "10-mer -> position t in the locus" and the locus itself 2-bit packed, 16 bases per word
-    int32_t fast;                      // 1: use pos_* / tw_off, the left/right tables are not built
-    uint32_t pos_off, pos_mult, pos_buckets;
+    int32_t fast;                      // 1: use pos / tw_off, the left/right tables are not built
+    ScarTableDesc pos;
     uint32_t tw_off;                   // byte offset in the blob of the packed locus (word 0 = 16 bases of padding)
     // phasing lookup (all non-empty phase strings of a side share one length <= 6): 2 x 4^n bytes in the
     // blob, entry = 1 + first matching k (0 = none), indexed by the prefix / suffix 2-bit code
@@ -129,6 +151,7 @@ struct K3Params {
     int32_t min_length;
     uint64_t hr_code;             // donor, 2 bits/base
     int32_t hr_len;
+    int32_t compact_tables;       // layout of the tables in the blob (ScarTableDesc)
     // ---- fused mode (scar_classify_raw_dev): raw read bytes in; packing (K1), classification (K3) and, when
     // `aggregate`, the per-sample accumulators and the scar table (K4) in ONE pass over a tile in shared memory
     int32_t platform;

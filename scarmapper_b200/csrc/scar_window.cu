@@ -70,54 +70,76 @@ __device__ __forceinline__ void stage_tables_tma(void *dst, const void *src, uin
     }
 }
 
-// Table access.  In shared memory the table is addressed with 32-bit shared-window addresses and a
-// plain ld.shared.v2 (no generic-address conversion in the loop); otherwise it is read through the
-// read-only global path.  Entries are (key << 12 | i), i <= 4094, empty = 0xFFFFFFFF.
-template <bool SMEM> struct TableRef;
-template <> struct TableRef<true> {
-    uint32_t base;
-    __device__ __forceinline__ TableRef(const void *smem_tab, const void *, uint32_t off)
-        : base(smem_u32(smem_tab) + off * 8u) {}
-    __device__ __forceinline__ uint2 load(uint32_t bucket) const
+// Table access (layouts: ScarTableDesc in scar_internal.cuh).  In shared memory the table is addressed with 32-bit
+// shared-window addresses and plain ld.shared (no generic-address conversion in the loop); otherwise it is read
+// through the read-only global path.  probe(t), t = key << 12, returns the payload (<= 4094) on a hit and a value
+// >= 4095 otherwise.
+template <bool SMEM, bool COMPACT> struct TableRef;
+template <> struct TableRef<true, false> {
+    uint32_t base, mult, n;
+    __device__ __forceinline__ TableRef(const void *smem_blob, const void *, const ScarTableDesc &d)
+        : base(smem_u32(smem_blob) + d.off), mult(d.mult), n(d.n) {}
+    __device__ __forceinline__ uint32_t probe(uint32_t t) const
     {
         uint2 v;
-        // volatile: the 16 loads of a cell stay in program order, ahead of their consumers
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(bucket * 8u + base));
-        return v;
+        // volatile: the loads of a batch stay in program order, ahead of their consumers
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(__umulhi(t * mult, n) * 8u + base));
+        return min(v.x ^ t, v.y ^ t);
     }
 };
-template <> struct TableRef<false> {
-    const uint2 *base;
-    __device__ __forceinline__ TableRef(const void *, const void *gmem_tab, uint32_t off)
-        : base(reinterpret_cast<const uint2 *>(gmem_tab) + off) {}
-    __device__ __forceinline__ uint2 load(uint32_t bucket) const { return __ldg(base + bucket); }
+template <> struct TableRef<false, false> {
+    const uint2 *base; uint32_t mult, n;
+    __device__ __forceinline__ TableRef(const void *, const void *gmem_blob, const ScarTableDesc &d)
+        : base(reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(gmem_blob) + d.off)), mult(d.mult), n(d.n) {}
+    __device__ __forceinline__ uint32_t probe(uint32_t t) const
+    {
+        const uint2 v = __ldg(base + __umulhi(t * mult, n));
+        return min(v.x ^ t, v.y ^ t);
+    }
+};
+template <> struct TableRef<true, true> {
+    uint32_t ent, disp, mult, n, nb, unit;
+    __device__ __forceinline__ TableRef(const void *smem_blob, const void *, const ScarTableDesc &d)
+        : ent(smem_u32(smem_blob) + d.off), disp(smem_u32(smem_blob) + d.doff), mult(d.mult), n(d.n), nb(d.nb), unit(d.unit) {}
+    __device__ __forceinline__ uint32_t probe(uint32_t t) const
+    {
+        const uint32_t h = t * mult;
+        uint32_t dv, e;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(dv) : "r"(scar_chd_bucket(h, nb) * 2u + disp));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(scar_chd_slot(h, dv, unit, n) * 4u + ent));
+        return e ^ t;
+    }
+};
+template <> struct TableRef<false, true> {
+    const uint32_t *ent; const uint16_t *disp; uint32_t mult, n, nb, unit;
+    __device__ __forceinline__ TableRef(const void *, const void *gmem_blob, const ScarTableDesc &d)
+        : ent(reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(gmem_blob) + d.off)),
+          disp(reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(gmem_blob) + d.doff)),
+          mult(d.mult), n(d.n), nb(d.nb), unit(d.unit) {}
+    __device__ __forceinline__ uint32_t probe(uint32_t t) const
+    {
+        const uint32_t h = t * mult;
+        const uint32_t dv = __ldg(disp + scar_chd_bucket(h, nb));
+        return __ldg(ent + scar_chd_slot(h, dv, unit, n)) ^ t;
+    }
 };
 
-// The 16 windows of one cell.  t[o] holds the window's 20 key bits in its TOP bits (raw << 12); the
-// bucket is the top log2(B) bits of t * mult, taken as mulhi(t * mult, B) (both on the FMA pipe); the
-// 16 table loads are issued back to back (16 independent shared-memory loads in flight per thread);
-// m[o] = i (< 4095) on a hit and a value >= 4095 otherwise.  Returns min(m): "any window of this cell
-// is in the table" costs one compare per cell, and the scan-order resolution runs only then.
-template <bool SMEM, int N>
-__device__ __forceinline__ void probe_n(const TableRef<SMEM> &tab, uint32_t wlo, uint32_t whi, uint32_t mult,
-                                        uint32_t nbuckets, uint32_t (&m)[N])
+// N consecutive windows starting at the low end of (wlo, whi).  t[o] holds the window's 20 key bits in its TOP bits
+// (raw << 12); the probes are issued back to back (N independent shared-memory loads in flight per thread);
+// m[o] = payload (< 4095) on a hit and a value >= 4095 otherwise.
+template <class TAB, int N>
+__device__ __forceinline__ void probe_n(const TAB &tab, uint32_t wlo, uint32_t whi, uint32_t (&m)[N])
 {
-    uint32_t t[N];
-    uint2 e[N];
 #pragma unroll
-    for (int o = 0; o < N; ++o) {
-        t[o] = __funnelshift_r(wlo, whi, 2 * o) << 12;
-        e[o] = tab.load(__umulhi(t[o] * mult, nbuckets));
-    }
-#pragma unroll
-    for (int o = 0; o < N; ++o) m[o] = min(e[o].x ^ t[o], e[o].y ^ t[o]);
+    for (int o = 0; o < N; ++o) m[o] = tab.probe(__funnelshift_r(wlo, whi, 2 * o) << 12);
 }
 
-template <bool SMEM>
-__device__ __forceinline__ uint32_t probe16(const TableRef<SMEM> &tab, uint32_t wlo, uint32_t whi, uint32_t mult,
-                                            uint32_t nbuckets, uint32_t (&m)[16])
+// the 16 windows of one cell; returns min(m): "any window of this cell is in the table" costs one compare per
+// cell, and the scan-order resolution runs only then
+template <class TAB>
+__device__ __forceinline__ uint32_t probe16(const TAB &tab, uint32_t wlo, uint32_t whi, uint32_t (&m)[16])
 {
-    probe_n<SMEM, 16>(tab, wlo, whi, mult, nbuckets, m);
+    probe_n<TAB, 16>(tab, wlo, whi, m);
     const uint32_t a = min(min(m[0], m[1]), min(m[2], m[3])), b = min(min(m[4], m[5]), min(m[6], m[7]));
     const uint32_t c = min(min(m[8], m[9]), min(m[10], m[11])), d = min(min(m[12], m[13]), min(m[14], m[15]));
     return min(min(a, b), min(c, d));
@@ -274,16 +296,13 @@ __device__ __forceinline__ int match_right(const RC &rc, const uint32_t *tw, int
 }
 
 // position in the locus of the read window at p, or 0xFFFFFFFF (not a locus 10-mer / not all ACGT)
-template <bool SMEM, class RC>
-__device__ __forceinline__ uint32_t locus_position(const RC &rc, const TableRef<SMEM> &ptab, uint32_t mult,
-                                                   uint32_t nbuckets, int p)
+template <class TAB, class RC>
+__device__ __forceinline__ uint32_t locus_position(const RC &rc, const TAB &ptab, int p)
 {
     uint32_t code, valid;
     rc.word16(p, code, valid);
     if ((valid & 0x3FFu) != 0x3FFu) return 0xFFFFFFFFu;
-    const uint32_t t = code << 12;
-    const uint2 e = ptab.load(__umulhi(t * mult, nbuckets));
-    const uint32_t m = min(e.x ^ t, e.y ^ t);
+    const uint32_t m = ptab.probe(code << 12);
     return m < 4095u ? m : 0xFFFFFFFFu;
 }
 
@@ -299,18 +318,17 @@ __device__ __forceinline__ void store_record(scar_record *dst, const scar_record
 // Each returns true while the search is still open (p updated) and false when it is finished (clj/tlj or
 // crj/trj set, or left at "not found").
 struct LocusRef {                  // what a step needs to know about the read's target
-    uint32_t pos_off, mult, nbuckets;
     const uint32_t *tw;
     int cut, L;
 };
 
-template <bool SMEM, class RC>
-__device__ __forceinline__ bool left_anchor(const RC &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int &p,
+template <bool SMEM, class TAB, class RC>
+__device__ __forceinline__ bool left_anchor(const RC &rc, const TAB &ptab, const LocusRef &T, int &p,
                                             int &clj, int &tlj)
 {
     // left junction (SlidingWindow.pyx:49-69): the largest p in 16 .. len-20 whose window is a left window,
     // i.e. lies at locus position 6 <= t <= cut-10 (window i = cut-10-t)
-    const uint32_t t = locus_position<SMEM>(rc, ptab, T.mult, T.nbuckets, p);
+    const uint32_t t = locus_position(rc, ptab, p);
     if (t != 0xFFFFFFFFu && (int)t > T.cut - 10) {
         const int need = (int)t - (T.cut - 10), limit = min(need, p - 16);
         const int k = match_left<SMEM>(rc, T.tw, p, (int)t, limit);
@@ -325,8 +343,8 @@ __device__ __forceinline__ bool left_anchor(const RC &rc, const TableRef<SMEM> &
     return --p >= 16;
 }
 
-template <bool SMEM, class RC>
-__device__ __forceinline__ bool left_batch(const RC &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int &p,
+template <bool SMEM, class TAB, class RC>
+__device__ __forceinline__ bool left_batch(const RC &rc, const TAB &ptab, const LocusRef &T, int &p,
                                            int &clj, int &tlj)
 {
     // batch width: a clean deletion's junction window is the 10th position past the break, 1-3 nt
@@ -337,7 +355,7 @@ __device__ __forceinline__ bool left_batch(const RC &rc, const TableRef<SMEM> &p
     uint32_t wlo, whi, vlo, vhi, m[NB];
     rc.word16(b + 16, whi, vhi);
     rc.word16(b, wlo, vlo);
-    probe_n<SMEM, NB>(ptab, wlo, whi, T.mult, T.nbuckets, m);
+    probe_n<TAB, NB>(ptab, wlo, whi, m);
     // left window iff (t - 6) <= cut-16: one bit per position, then the first in scan order
     uint32_t hm = 0;
 #pragma unroll
@@ -355,13 +373,13 @@ __device__ __forceinline__ bool left_batch(const RC &rc, const TableRef<SMEM> &p
     return p >= 16;
 }
 
-template <bool SMEM, class RC>
-__device__ __forceinline__ bool right_anchor(const RC &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int plast,
+template <bool SMEM, class TAB, class RC>
+__device__ __forceinline__ bool right_anchor(const RC &rc, const TAB &ptab, const LocusRef &T, int plast,
                                              int &p, int &crj, int &trj)
 {
     // right junction (SlidingWindow.pyx:79-93): the smallest p in 10 .. len-26 whose window is a right window,
     // i.e. lies at locus position cut <= t <= L-16 (window i = t-cut)
-    const uint32_t t = locus_position<SMEM>(rc, ptab, T.mult, T.nbuckets, p);
+    const uint32_t t = locus_position(rc, ptab, p);
     if (t != 0xFFFFFFFFu && (int)t < T.cut) {
         const int need = T.cut - (int)t, limit = min(need, plast - p);
         const int k = match_right<SMEM>(rc, T.tw, p + 10, (int)t + 10, limit);
@@ -376,8 +394,8 @@ __device__ __forceinline__ bool right_anchor(const RC &rc, const TableRef<SMEM> 
     return ++p <= plast;
 }
 
-template <bool SMEM, class RC>
-__device__ __forceinline__ bool right_batch(const RC &rc, const TableRef<SMEM> &ptab, const LocusRef &T, int plast,
+template <bool SMEM, class TAB, class RC>
+__device__ __forceinline__ bool right_batch(const RC &rc, const TAB &ptab, const LocusRef &T, int plast,
                                             int &p, int &crj, int &trj)
 {
     constexpr int NB = SCAR_ANCHOR_BATCH;
@@ -385,7 +403,7 @@ __device__ __forceinline__ bool right_batch(const RC &rc, const TableRef<SMEM> &
     uint32_t wlo, whi, vlo, vhi, m[NB];
     rc.word16(p, wlo, vlo);                            // positions p .. p+NB-1
     rc.word16(p + 16, whi, vhi);
-    probe_n<SMEM, NB>(ptab, wlo, whi, T.mult, T.nbuckets, m);
+    probe_n<TAB, NB>(ptab, wlo, whi, m);
     const uint32_t span = (uint32_t)(T.L - 16 - T.cut);   // right window iff (t - cut) <= span
     uint32_t hm = 0;
 #pragma unroll
@@ -591,7 +609,7 @@ __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d
 //         scar table are updated as well (what K1, K3 and K4 do in three passes over HBM).
 // groups of 256 threads per CTA of the fused kernel (registers: 64 per thread with 4 groups, 128 with 2)
 __host__ __device__ constexpr int fused_groups_max(int lanes) { return lanes > 2 ? 2 : 4; }
-template <bool SMEM, bool HR, int MODE, int LANES>
+template <bool SMEM, bool HR, int MODE, int LANES, bool COMPACT>
 __global__ void __launch_bounds__(MODE == 2 ? fused_groups_max(LANES) * K3_TILE : K3_TILE, MODE == 2 ? 1 : SCAR_K3_MIN_CTAS)
 scar_window_kernel(const K3Params P)
 {
@@ -623,6 +641,7 @@ scar_window_kernel(const K3Params P)
     const uint16_t *nmax = reinterpret_cast<const uint16_t *>(blob + P.nmax_off);
     const int64_t S = P.stride;      // reads per cell row
     using RC = ReadCursorT<ST>;
+    using TAB = TableRef<SMEM, COMPACT>;
     // ST: the tile's cells (W rows of 256 x 8 bytes) live in shared memory behind the blob.  MODE 1: every thread
     // copies its own read's cells there with asynchronous 8-byte copies (no registers, all W in flight at once).
     // MODE 2: they are packed there from the raw bytes in the warps' rings.
@@ -812,8 +831,8 @@ scar_window_kernel(const K3Params P)
         // ---- phase 1: first anchor step of both searches (loci whose 10-mers are all distinct)
         const bool fast = live && T.fast;
         {
-            const TableRef<SMEM> ptab(blob, P.blob, T.pos_off);
-            LocusRef LR; LR.mult = T.pos_mult; LR.nbuckets = T.pos_buckets; LR.cut = cut; LR.L = T.length;
+            const TAB ptab(blob, P.blob, T.pos);
+            LocusRef LR; LR.cut = cut; LR.L = T.length;
             LR.tw = reinterpret_cast<const uint32_t *>(blob + T.tw_off);
             const RC &rc = rc0;
             int p = len - 20;
@@ -832,8 +851,7 @@ scar_window_kernel(const K3Params P)
         bool cutwindow_done = false;          // the exhaustive path checks the cut window itself
         // ---- left junction (SlidingWindow.pyx:49-69): p = len-20 .. 16, descending
         if (live && !T.fast) {
-            const TableRef<SMEM> ltab(blob, P.blob, T.left_off);
-            const uint32_t mult = T.left_mult, nb = T.left_buckets;
+            const TAB ltab(blob, P.blob, T.left);
             const int p0 = len - 20;
             if (p0 >= 16) {
                 int j = p0 >> 4;
@@ -843,7 +861,7 @@ scar_window_kernel(const K3Params P)
                     const uint64_t lo = rc0.cell(j);
                     const uint32_t wlo = (uint32_t)lo, whi = (uint32_t)hi;
                     uint32_t m[16];
-                    if (probe16<SMEM>(ltab, wlo, whi, mult, nb, m) < 4095u) {
+                    if (probe16(ltab, wlo, whi, m) < 4095u) {
                         // some window of this cell is in the table: keep the first in scan order among
                         // the positions that are scanned (<= p0) and whose window is all ACGT
                         const uint32_t vwin = ((uint32_t)(lo >> 32) & 0xFFFFu) | ((uint32_t)(hi >> 32) << 16);
@@ -880,8 +898,7 @@ scar_window_kernel(const K3Params P)
 
         // ---- right junction (SlidingWindow.pyx:79-93): p = 10 .. len-26, ascending
         if (live && !T.fast) {
-            const TableRef<SMEM> rtab(blob, P.blob, T.right_off);
-            const uint32_t mult = T.right_mult, nb = T.right_buckets;
+            const TAB rtab(blob, P.blob, T.right);
             const int plast = len - 26;
             if (plast >= 10) {
                 uint64_t lo = rc0.cell(0);
@@ -890,7 +907,7 @@ scar_window_kernel(const K3Params P)
                     const uint64_t hi = rc0.cell_or_zero(j + 1);
                     const uint32_t wlo = (uint32_t)lo, whi = (uint32_t)hi;
                     uint32_t m[16];
-                    if (probe16<SMEM>(rtab, wlo, whi, mult, nb, m) < 4095u) {
+                    if (probe16(rtab, wlo, whi, m) < 4095u) {
                         const uint32_t vwin = ((uint32_t)(lo >> 32) & 0xFFFFu) | ((uint32_t)(hi >> 32) << 16);
                         const int pbase = 16 * j, top = plast - pbase;    // top >= 0 here
                         uint32_t okmask = runs_of_ten(vwin) & (top >= 15 ? 0xFFFFu : ((2u << top) - 1u));
@@ -935,8 +952,8 @@ scar_window_kernel(const K3Params P)
                 const uint32_t ctx = s_ctx[rl];
                 const int ilen = (int)(ctx & 0xFFFFu);
                 const ScarTargetMeta &IT = metas[ctx >> 16];
-                const TableRef<SMEM> ptab(blob, P.blob, IT.pos_off);
-                LocusRef LR; LR.mult = IT.pos_mult; LR.nbuckets = IT.pos_buckets; LR.cut = IT.cutsite; LR.L = IT.length;
+                const TAB ptab(blob, P.blob, IT.pos);
+                LocusRef LR; LR.cut = IT.cutsite; LR.L = IT.length;
                 LR.tw = reinterpret_cast<const uint32_t *>(blob + IT.tw_off);
                 RC rc; rc.col = P.cells + tile + rl; rc.S = S; rc.sc = s_cells + rl; rc.Wr = (ilen + 15) >> 4;
                 bool open = have;
@@ -1074,6 +1091,16 @@ scar_window_kernel(const K3Params P)
 }
 
 // host-side launcher (called from scar_api.cu)
+template <int MODE, int LANES>
+static void (*pick_kernel(bool smem, bool hr, bool compact))(const K3Params)
+{
+    if (compact)
+        return smem ? (hr ? scar_window_kernel<true, true, MODE, LANES, true> : scar_window_kernel<true, false, MODE, LANES, true>)
+                    : (hr ? scar_window_kernel<false, true, MODE, LANES, true> : scar_window_kernel<false, false, MODE, LANES, true>);
+    return smem ? (hr ? scar_window_kernel<true, true, MODE, LANES, false> : scar_window_kernel<true, false, MODE, LANES, false>)
+                : (hr ? scar_window_kernel<false, true, MODE, LANES, false> : scar_window_kernel<false, false, MODE, LANES, false>);
+}
+
 struct K3Plan { void (*kern)(const K3Params); size_t smem; int per_sm; bool stage; int groups = 1; };
 
 static cudaError_t plan_window(const K3Params &P, bool smem_tables, K3Plan &plan)
@@ -1088,12 +1115,7 @@ static cudaError_t plan_window(const K3Params &P, bool smem_tables, K3Plan &plan
     plan.stage = P.W <= stage_max && !no_stage && smem_base + cell_bytes + 7680 <= 227 * 1024;
     plan.smem = smem_base + (plan.stage ? cell_bytes : 0);
     const bool hr = P.hr_len > 0;
-    if (plan.stage)
-        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 1, 1> : scar_window_kernel<true, false, 1, 1>)
-                                : (hr ? scar_window_kernel<false, true, 1, 1> : scar_window_kernel<false, false, 1, 1>);
-    else
-        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 0, 1> : scar_window_kernel<true, false, 0, 1>)
-                                : (hr ? scar_window_kernel<false, true, 0, 1> : scar_window_kernel<false, false, 0, 1>);
+    plan.kern = plan.stage ? pick_kernel<1, 1>(smem_tables, hr, P.compact_tables != 0) : pick_kernel<0, 1>(smem_tables, hr, P.compact_tables != 0);
     cudaError_t e = cudaFuncSetAttribute(plan.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return e;
     plan.per_sm = 0;
@@ -1156,18 +1178,12 @@ static cudaError_t plan_fused(K3Params &P, bool smem_tables, int max_read_len, K
     const size_t cells_bytes = ((size_t)P.W * threads * 8 + 15) & ~(size_t)15;
     const size_t fixed = 16 + (size_t)gmax * warps * FUSED_SLOTS * 8 + (smem_tables ? P.blob_bytes : 0);
     const bool hr = P.hr_len > 0;
+    const bool compact = P.compact_tables != 0;
 #if FUSED_LANES_SHORT == 1
-    if (lanes == 1)
-        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 1> : scar_window_kernel<true, false, 2, 1>)
-                                : (hr ? scar_window_kernel<false, true, 2, 1> : scar_window_kernel<false, false, 2, 1>);
+    if (lanes == 1) plan.kern = pick_kernel<2, 1>(smem_tables, hr, compact);
     else
 #endif
-    if (lanes == 2)
-        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 2> : scar_window_kernel<true, false, 2, 2>)
-                                : (hr ? scar_window_kernel<false, true, 2, 2> : scar_window_kernel<false, false, 2, 2>);
-    else
-        plan.kern = smem_tables ? (hr ? scar_window_kernel<true, true, 2, 4> : scar_window_kernel<true, false, 2, 4>)
-                                : (hr ? scar_window_kernel<false, true, 2, 4> : scar_window_kernel<false, false, 2, 4>);
+    plan.kern = lanes == 2 ? pick_kernel<2, 2>(smem_tables, hr, compact) : pick_kernel<2, 4>(smem_tables, hr, compact);
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, plan.kern);
     if (e != cudaSuccess) return e;

@@ -34,12 +34,15 @@ def table_of(eng, s):
     return [(int(e["count"]), int(e["first_idx"])) for e in sel]
 
 
+@pytest.mark.parametrize("tables", ["bucketed", "compact"])
 @pytest.mark.parametrize("anchor", ["anchor", "scan"])
 @pytest.mark.parametrize("name", gu.golden_names())
-def test_golden_vectors_through_c_abi(name, anchor, monkeypatch):
-    # both K3 junction searches: anchor-and-extend (unique-10-mer loci) and the exhaustive cell scan
+def test_golden_vectors_through_c_abi(name, anchor, tables, monkeypatch):
+    # both K3 junction searches: anchor-and-extend (unique-10-mer loci) and the exhaustive cell scan; both layouts of
+    # the window tables: bucketed perfect hash (one probe) and compact hash-and-displace (many loci)
     if anchor == "scan":
         monkeypatch.setenv("SCAR_NO_ANCHOR", "1")
+    monkeypatch.setenv("SCAR_COMPACT_TABLES", "1" if tables == "compact" else "0")
     blob = gu.load(name)
     case, golden = blob["case"], blob["golden"]
     pin = gu.problem_inputs(case)
