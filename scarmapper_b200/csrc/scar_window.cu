@@ -76,62 +76,96 @@ __device__ __forceinline__ void stage_tables_tma(void *dst, const void *src, uin
 // >= 4095 otherwise.
 template <bool SMEM, bool COMPACT> struct TableRef;
 template <> struct TableRef<true, false> {
+    static constexpr bool compact = false;
     uint32_t base, mult, n;
     __device__ __forceinline__ TableRef(const void *smem_blob, const void *, const ScarTableDesc &d)
         : base(smem_u32(smem_blob) + d.off), mult(d.mult), n(d.n) {}
-    __device__ __forceinline__ uint32_t probe(uint32_t t) const
+    __device__ __forceinline__ uint2 fetch(uint32_t t) const
     {
         uint2 v;
         // volatile: the loads of a batch stay in program order, ahead of their consumers
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(__umulhi(t * mult, n) * 8u + base));
-        return min(v.x ^ t, v.y ^ t);
+        return v;
     }
 };
 template <> struct TableRef<false, false> {
+    static constexpr bool compact = false;
     const uint2 *base; uint32_t mult, n;
     __device__ __forceinline__ TableRef(const void *, const void *gmem_blob, const ScarTableDesc &d)
         : base(reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(gmem_blob) + d.off)), mult(d.mult), n(d.n) {}
-    __device__ __forceinline__ uint32_t probe(uint32_t t) const
-    {
-        const uint2 v = __ldg(base + __umulhi(t * mult, n));
-        return min(v.x ^ t, v.y ^ t);
-    }
+    __device__ __forceinline__ uint2 fetch(uint32_t t) const { return __ldg(base + __umulhi(t * mult, n)); }
 };
 template <> struct TableRef<true, true> {
+    static constexpr bool compact = true;
     uint32_t ent, disp, mult, n, nb, unit;
     __device__ __forceinline__ TableRef(const void *smem_blob, const void *, const ScarTableDesc &d)
         : ent(smem_u32(smem_blob) + d.off), disp(smem_u32(smem_blob) + d.doff), mult(d.mult), n(d.n), nb(d.nb), unit(d.unit) {}
-    __device__ __forceinline__ uint32_t probe(uint32_t t) const
+    __device__ __forceinline__ uint32_t fetch_disp(uint32_t h) const
     {
-        const uint32_t h = t * mult;
-        uint32_t dv, e;
+        uint32_t dv;
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(dv) : "r"(scar_chd_bucket(h, nb) * 2u + disp));
+        return dv;
+    }
+    __device__ __forceinline__ uint32_t fetch_entry(uint32_t h, uint32_t dv) const
+    {
+        uint32_t e;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(scar_chd_slot(h, dv, unit, n) * 4u + ent));
-        return e ^ t;
+        return e;
     }
 };
 template <> struct TableRef<false, true> {
+    static constexpr bool compact = true;
     const uint32_t *ent; const uint16_t *disp; uint32_t mult, n, nb, unit;
     __device__ __forceinline__ TableRef(const void *, const void *gmem_blob, const ScarTableDesc &d)
         : ent(reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(gmem_blob) + d.off)),
           disp(reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(gmem_blob) + d.doff)),
           mult(d.mult), n(d.n), nb(d.nb), unit(d.unit) {}
-    __device__ __forceinline__ uint32_t probe(uint32_t t) const
-    {
-        const uint32_t h = t * mult;
-        const uint32_t dv = __ldg(disp + scar_chd_bucket(h, nb));
-        return __ldg(ent + scar_chd_slot(h, dv, unit, n)) ^ t;
-    }
+    __device__ __forceinline__ uint32_t fetch_disp(uint32_t h) const { return __ldg(disp + scar_chd_bucket(h, nb)); }
+    __device__ __forceinline__ uint32_t fetch_entry(uint32_t h, uint32_t dv) const { return __ldg(ent + scar_chd_slot(h, dv, unit, n)); }
 };
 
+// one probe: the payload (<= 4094) on a hit and a value >= 4095 otherwise; t = key << 12
+template <class TAB>
+__device__ __forceinline__ uint32_t probe_one(const TAB &tab, uint32_t t)
+{
+    if constexpr (TAB::compact) {
+        const uint32_t h = t * tab.mult;
+        return tab.fetch_entry(h, tab.fetch_disp(h)) ^ t;
+    } else {
+        const uint2 v = tab.fetch(t);
+        return min(v.x ^ t, v.y ^ t);
+    }
+}
+
 // N consecutive windows starting at the low end of (wlo, whi).  t[o] holds the window's 20 key bits in its TOP bits
-// (raw << 12); the probes are issued back to back (N independent shared-memory loads in flight per thread);
-// m[o] = payload (< 4095) on a hit and a value >= 4095 otherwise.
+// (raw << 12); the loads of all N probes are issued back to back (N independent shared-memory loads in flight per
+// thread) before any result is formed; m[o] = payload (< 4095) on a hit and a value >= 4095 otherwise.
 template <class TAB, int N>
 __device__ __forceinline__ void probe_n(const TAB &tab, uint32_t wlo, uint32_t whi, uint32_t (&m)[N])
 {
+    uint32_t t[N];
+    if constexpr (TAB::compact) {
+        uint32_t h[N], dv[N];
 #pragma unroll
-    for (int o = 0; o < N; ++o) m[o] = tab.probe(__funnelshift_r(wlo, whi, 2 * o) << 12);
+        for (int o = 0; o < N; ++o) {
+            t[o] = __funnelshift_r(wlo, whi, 2 * o) << 12;
+            h[o] = t[o] * tab.mult;
+            dv[o] = tab.fetch_disp(h[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < N; ++o) m[o] = tab.fetch_entry(h[o], dv[o]);
+#pragma unroll
+        for (int o = 0; o < N; ++o) m[o] ^= t[o];
+    } else {
+        uint2 e[N];
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+            t[o] = __funnelshift_r(wlo, whi, 2 * o) << 12;
+            e[o] = tab.fetch(t[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < N; ++o) m[o] = min(e[o].x ^ t[o], e[o].y ^ t[o]);
+    }
 }
 
 // the 16 windows of one cell; returns min(m): "any window of this cell is in the table" costs one compare per
@@ -302,7 +336,7 @@ __device__ __forceinline__ uint32_t locus_position(const RC &rc, const TAB &ptab
     uint32_t code, valid;
     rc.word16(p, code, valid);
     if ((valid & 0x3FFu) != 0x3FFu) return 0xFFFFFFFFu;
-    const uint32_t m = ptab.probe(code << 12);
+    const uint32_t m = probe_one(ptab, code << 12);
     return m < 4095u ? m : 0xFFFFFFFFu;
 }
 
