@@ -428,6 +428,43 @@ def main():
         eng.reset()
     merge_done = [None, None]
     step_no = [0]
+    # N > 1: the persistent grids leave a few SMs to the merge kernels and NCCL, which then really run beside the
+    # next step instead of waiting for a CTA slot (SCAR_BENCH_SM_RESERVE, default 8 of the 148)
+    sm_reserve = 0
+    if world > 1:
+        sm_reserve = int(os.environ.get("SCAR_BENCH_SM_RESERVE", "8"))
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        for e in engines:
+            e.set_sm_limit(sms - sm_reserve)
+
+    # N > 1, untimed: the union of the ranks' merged partitions of a small sharded batch must be the table one GPU
+    # builds from the whole batch (entries, counts, first-seen indices, counters)
+    merge_check = None
+    if world > 1:
+        per = 50_000
+        chk_batch = cfg.generate(rank * per, per)
+        e_chk = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=1 << 20, **pin), device=local)
+        e_chk.process_host(HostRagged.from_matrix(chk_batch["seq"]), chk_batch["f0"], chk_batch["f1"], first_index=rank * per,
+                           want_records=False)
+        DistributedScar(e_chk).merge_partitioned(region_capacity=1 << 16)
+        torch.cuda.synchronize()
+        mine = e_chk.table()
+        cnt_m, un_m = e_chk.counters()
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        e_chk.close()
+        if rank == 0:
+            whole = cfg.generate(0, per * world)
+            e_one = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=1 << 20, **pin), device=local)
+            e_one.process_host(HostRagged.from_matrix(whole["seq"]), whole["f0"], whole["f1"], want_records=False)
+            want_tab = e_one.table()
+            cnt_1, un_1 = e_one.counters()
+            e_one.close()
+            union = np.concatenate(parts)
+            union = union[np.lexsort((union["first_idx"], union["sample"]))]
+            merge_check = {"reads": per * world, "entries": int(len(want_tab)),
+                           "union_of_partitions_equals_single_gpu_table": bool(union.tobytes() == want_tab.tobytes()),
+                           "counters_equal": bool((cnt_m == cnt_1).all()) and int(un_m) == int(un_1)}
 
     def ev():
         e = torch.cuda.Event(enable_timing=True)
@@ -756,6 +793,9 @@ def main():
             line["pattern_searches"] = pattern_searches
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+        if merge_check:
+            line["merge_check"] = merge_check
+            line["config"]["sm_reserved_for_merge"] = sm_reserve
         if pipeline:
             line["pipeline"] = pipeline
         if configs:

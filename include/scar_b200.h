@@ -169,6 +169,9 @@ int scar_verify_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_record *re
                     uint64_t first_index, int64_t *n_collisions, void *stream);
 int scar_reset(scar_ctx *ctx);
 int scar_reset_dev(scar_ctx *ctx, void *stream);      /* asynchronous on `stream` */
+/* Size the persistent grids of this context's kernels for n_sms SMs instead of all of them (0 = all): a multi-GPU
+ * job leaves a few SMs to the table merge and the NCCL kernels that run beside the next batch. */
+int scar_ctx_set_sm_limit(scar_ctx *ctx, int32_t n_sms);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t scar_launch_count(const scar_ctx *ctx);
 

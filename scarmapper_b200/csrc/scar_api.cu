@@ -186,7 +186,7 @@ struct HostBuf {   // device scratch of one in-flight chunk of scar_process_host
 };
 
 struct scar_ctx {
-    int device = 0, sm_count = 148, platform = 0, mismatch = 1, n_targets = 0, n_samples = 0;
+    int device = 0, sm_count = 148, sm_total = 148, platform = 0, mismatch = 1, n_targets = 0, n_samples = 0;
     int W = 0, max_read_len = 0, min_length = 0, hr_len = 0, do_phasing = 0;
     double n_limit = 0.0; uint64_t hr_code = 0;
     std::vector<ScarTargetMeta> h_targets;
@@ -198,6 +198,7 @@ struct scar_ctx {
     uint8_t *d_fast_codes = nullptr; int demux_fast = 0;
     uint64_t *d_lut_right = nullptr, *d_lut_left = nullptr; int lut_n_right = 0, lut_n_left = 0;
     ScarTableSlot *d_slots = nullptr; uint64_t capacity = 0;
+    uint32_t *d_claimed = nullptr;         // indices of the claimed slots, in claim order
     unsigned long long *d_acc = nullptr;   // [n_entries, unassigned, collisions, export_count] + counters + phase hist
     unsigned long long *d_n_entries = nullptr, *d_unassigned = nullptr, *d_collisions = nullptr, *d_export_n = nullptr;
     unsigned long long *d_counters = nullptr, *d_phase_hist = nullptr; size_t acc_words = 0;
@@ -232,7 +233,7 @@ extern "C" void scar_ctx_destroy(scar_ctx *c)
     cudaFree(c->d_sample_target); cudaFree(c->d_blob);
     cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample); cudaFree(c->d_fast_codes);
     cudaFree(c->d_lut_right); cudaFree(c->d_lut_left);
-    cudaFree(c->d_slots); cudaFree(c->d_acc); cudaFree(c->d_status);
+    cudaFree(c->d_slots); cudaFree(c->d_claimed); cudaFree(c->d_acc); cudaFree(c->d_status);
     cudaFree(c->d_text); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offsets); cudaFree(c->d_nl); cudaFree(c->d_fq_records); cudaFree(c->d_part_cursor);
     for (cudaEvent_t e : c->fq_events) cudaEventDestroy(e);
     delete c;
@@ -372,7 +373,7 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
 
     scar_ctx *c = new scar_ctx();
     struct Guard { scar_ctx *c; ~Guard() { if (c) scar_ctx_destroy(c); } } guard{c};
-    c->device = cfg->device; c->sm_count = prop.multiProcessorCount; c->platform = cfg->platform;
+    c->device = cfg->device; c->sm_count = c->sm_total = prop.multiProcessorCount; c->platform = cfg->platform;
     c->mismatch = cfg->mismatch >= 0 ? cfg->mismatch : (cfg->platform == 0 ? 1 : cfg->platform == 1 ? 0 : 3);
     c->n_targets = cfg->n_targets; c->n_samples = cfg->n_samples;
     c->max_read_len = cfg->max_read_len; c->W = (cfg->max_read_len + 15) / 16;
@@ -564,6 +565,7 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
     if (cap & (cap - 1)) return fail(SCAR_ERR_INVALID, "table_capacity must be a power of two");
     c->capacity = cap;
     CU(cudaMalloc((void **)&c->d_slots, cap * sizeof(ScarTableSlot)));
+    CU(cudaMalloc((void **)&c->d_claimed, cap * sizeof(uint32_t)));
     c->acc_words = 8 + (size_t)c->n_samples * SCAR_N_COUNTERS + (size_t)c->n_samples * 2 * SCAR_PHASE_BINS;
     CU(cudaMalloc((void **)&c->d_acc, c->acc_words * sizeof(unsigned long long)));
     c->d_n_entries = c->d_acc; c->d_unassigned = c->d_acc + 1; c->d_collisions = c->d_acc + 2; c->d_export_n = c->d_acc + 3;
@@ -591,9 +593,19 @@ extern "C" int scar_reset_dev(scar_ctx *c, void *stream)
     if (!c) return fail(SCAR_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream;
-    CU(cudaMemsetAsync(c->d_slots, 0, c->capacity * sizeof(ScarTableSlot), s));
+    // only the claimed slots are emptied (the list is complete: every insert path appends to it)
+    CU(scar_launch_clear(c->d_slots, c->d_claimed, c->d_n_entries, c->sm_count, s));
+    ++c->launches;
     CU(cudaMemsetAsync(c->d_acc, 0, c->acc_words * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(c->d_status, 0, sizeof(int32_t), s));      // like scar_reset: a reset state carries no sticky error
+    return SCAR_OK;
+}
+
+extern "C" int scar_ctx_set_sm_limit(scar_ctx *c, int32_t n_sms)
+{
+    if (!c) return fail(SCAR_ERR_INVALID, "null context");
+    if (n_sms <= 0 || n_sms > c->sm_total) n_sms = c->sm_total;
+    c->sm_count = n_sms;
     return SCAR_OK;
 }
 
@@ -683,7 +695,7 @@ extern "C" int scar_classify_dev(scar_ctx *c, const uint64_t *cells, const uint3
 static K4Params k4_params(scar_ctx *c)
 {
     K4Params P; memset(&P, 0, sizeof(P));
-    P.slots = c->d_slots; P.slot_mask = c->capacity - 1; P.n_entries = c->d_n_entries; P.counters = c->d_counters;
+    P.slots = c->d_slots; P.slot_mask = c->capacity - 1; P.claimed = c->d_claimed; P.n_entries = c->d_n_entries; P.counters = c->d_counters;
     P.unassigned = c->d_unassigned; P.phase_hist = c->d_phase_hist; P.status = c->d_status; P.n_samples = c->n_samples;
     P.platform = c->platform; P.max_probe = (uint32_t)std::min<uint64_t>(c->capacity - 1, 1u << 16);
     int max_phase = 0;
@@ -713,7 +725,7 @@ static K3Params fused_params(scar_ctx *c, const scar_ragged *seq, const uint16_t
     P.samples = samples; P.records = records; P.n_reads = n; P.stride = n; P.platform = c->platform;
     P.aggregate = aggregate; P.first_index = first_index;
     const K4Params A = k4_params(c);
-    P.slots = A.slots; P.slot_mask = A.slot_mask; P.max_probe = A.max_probe; P.n_entries = A.n_entries;
+    P.slots = A.slots; P.slot_mask = A.slot_mask; P.max_probe = A.max_probe; P.claimed = A.claimed; P.n_entries = A.n_entries;
     P.counters = A.counters; P.unassigned = A.unassigned; P.phase_hist = A.phase_hist; P.status = c->d_status;
     P.phase_bins = A.phase_bins; P.phase_joint = A.phase_joint;
     return P;
@@ -837,11 +849,10 @@ extern "C" int scar_table_export_dev(scar_ctx *c, scar_entry *entries, int64_t c
     if (!c || !n_entries || capacity < 0) return fail(SCAR_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream;
-    CU(cudaMemsetAsync(c->d_export_n, 0, sizeof(unsigned long long), s));
-    CU(scar_launch_export(c->d_slots, c->capacity, entries, (uint64_t)capacity, c->d_export_n, c->sm_count, s));
+    CU(scar_launch_export(c->d_slots, c->d_claimed, c->d_n_entries, entries, (uint64_t)capacity, c->sm_count, s));
     ++c->launches;
     unsigned long long v = 0;
-    CU(cudaMemcpyAsync(&v, c->d_export_n, sizeof(v), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&v, c->d_n_entries, sizeof(v), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     *n_entries = (int64_t)v;
     if ((int64_t)v > capacity) return fail(SCAR_ERR_INVALID, "export buffer too small: %llu entries, capacity %lld", v, (long long)capacity);
@@ -866,7 +877,7 @@ extern "C" int scar_table_export_parts_dev(scar_ctx *c, scar_entry *regions, int
     cudaStream_t s = (cudaStream_t)stream;
     for (int g = 0; g < n_parts; ++g)        // headers (count = 0)
         CU(cudaMemsetAsync(regions + (size_t)g * region_capacity, 0, sizeof(scar_entry), s));
-    CU(scar_launch_export_parts(c->d_slots, c->capacity, regions, (uint32_t)n_parts, (uint64_t)region_capacity,
+    CU(scar_launch_export_parts(c->d_slots, c->d_claimed, c->d_n_entries, regions, (uint32_t)n_parts, (uint64_t)region_capacity,
                                 c->d_status, c->sm_count, s));
     ++c->launches;
     return SCAR_OK;
@@ -886,7 +897,7 @@ extern "C" int scar_table_export_p2p_dev(scar_ctx *c, void *const *peer_regions,
         CU(cudaMalloc((void **)&c->d_part_cursor, SCAR_MAX_PEERS * sizeof(unsigned long long)));
         CU(cudaMemsetAsync(c->d_part_cursor, 0, SCAR_MAX_PEERS * sizeof(unsigned long long), s));
     }
-    CU(scar_launch_export_p2p(c->d_slots, c->capacity, reinterpret_cast<scar_entry *const *>(peer_regions), (uint32_t)n_parts,
+    CU(scar_launch_export_p2p(c->d_slots, c->d_claimed, c->d_n_entries, reinterpret_cast<scar_entry *const *>(peer_regions), (uint32_t)n_parts,
                               (uint32_t)my_rank, (uint64_t)region_capacity, c->d_part_cursor, c->d_status, c->sm_count, s));
     c->launches += 2;
     return SCAR_OK;
@@ -897,8 +908,8 @@ extern "C" int scar_table_clear_dev(scar_ctx *c, void *stream)
     if (!c) return fail(SCAR_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream;
-    CU(cudaMemsetAsync(c->d_slots, 0, c->capacity * sizeof(ScarTableSlot), s));
-    CU(cudaMemsetAsync(c->d_n_entries, 0, sizeof(unsigned long long), s));
+    CU(scar_launch_clear(c->d_slots, c->d_claimed, c->d_n_entries, c->sm_count, s));
+    ++c->launches;
     return SCAR_OK;
 }
 

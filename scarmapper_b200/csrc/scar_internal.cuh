@@ -160,6 +160,7 @@ struct K3Params {
     int32_t aggregate;
     uint64_t first_index;         // global index of read 0 (first-seen order across batches and ranks)
     ScarTableSlot *slots; uint64_t slot_mask; uint32_t max_probe; int32_t hist_smem;
+    uint32_t *claimed;            // claimed-slot list of the table
     unsigned long long *n_entries, *counters, *unassigned, *phase_hist;
     int32_t *status;              // bit 0: read longer than 16 W, bit 1: table full
     int32_t phase_bins, phase_joint;
@@ -172,6 +173,7 @@ struct K4Params {
     uint64_t first_index;
     ScarTableSlot *slots;
     uint64_t slot_mask;          // capacity - 1
+    uint32_t *claimed;           // claimed-slot list [capacity]
     unsigned long long *n_entries;
     unsigned long long *counters;   // [n_samples][SCAR_N_COUNTERS]
     unsigned long long *unassigned;
@@ -205,17 +207,21 @@ cudaError_t scar_launch_match_maker(const scar_ragged &q, const scar_ragged &u, 
                                     cudaStream_t stream);
 cudaError_t scar_launch_aggregate(K4Params P, int sm_count, cudaStream_t stream, int *launches);
 cudaError_t scar_launch_verify(const K4VerifyParams &P, int sm_count, cudaStream_t stream);
-cudaError_t scar_launch_export(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint64_t out_capacity,
-                               unsigned long long *n_out, int sm_count, cudaStream_t stream);
+cudaError_t scar_launch_export(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
+                               scar_entry *out, uint64_t out_capacity, int sm_count, cudaStream_t stream);
+cudaError_t scar_launch_clear(ScarTableSlot *slots, const uint32_t *claimed, unsigned long long *n_entries, int sm_count,
+                              cudaStream_t stream);
 cudaError_t scar_launch_merge(const K4Params &P, const scar_entry *in, uint64_t n_in, int sm_count, cudaStream_t stream);
-cudaError_t scar_launch_export_parts(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint32_t n_parts,
-                                     uint64_t region, int32_t *status, int sm_count, cudaStream_t stream);
+cudaError_t scar_launch_export_parts(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
+                                     scar_entry *out, uint32_t n_parts, uint64_t region, int32_t *status, int sm_count,
+                                     cudaStream_t stream);
 cudaError_t scar_launch_homeology(const scar_ragged &cons, const scar_ragged &ins, const scar_ragged &targets,
                                   const scar_ragged &regions, const int32_t *clj, const int32_t *crj, const int32_t *tlj,
                                   const int32_t *trj, const int32_t *target_idx, int32_t n_targets, int64_t n, void *out,
                                   cudaStream_t stream);
 #define SCAR_MAX_PEERS 32
-cudaError_t scar_launch_export_p2p(const ScarTableSlot *slots, uint64_t capacity, scar_entry *const *peer_base,
+cudaError_t scar_launch_export_p2p(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
+                                   scar_entry *const *peer_base,
                                    uint32_t n_parts, uint32_t my_rank, uint64_t region, unsigned long long *cursors,
                                    int32_t *status, int sm_count, cudaStream_t stream);
 cudaError_t scar_launch_merge_parts(const K4Params &P, const scar_entry *in, uint32_t n_parts, uint64_t region,

@@ -15,6 +15,7 @@
 static __device__ __forceinline__ ScarTableRef table_ref(const K4Params &P)
 {
     ScarTableRef T; T.slots = P.slots; T.slot_mask = P.slot_mask; T.max_probe = P.max_probe; T.status = P.status;
+    T.claimed = P.claimed; T.n_entries = P.n_entries;
     return T;
 }
 static __device__ __forceinline__ ScarAccRef acc_ref(const K4Params &P)
@@ -33,11 +34,11 @@ __global__ void __launch_bounds__(256, SCAR_K4_CTAS) scar_aggregate_kernel(const
     const ScarTableRef T = table_ref(P);
     const ScarAccRef A = acc_ref(P);
     const int per_sample = acc_words_per_sample(A.pb, A.joint);
-    __shared__ unsigned int s_unassigned, s_new;
+    __shared__ unsigned int s_unassigned;
     if (P.use_smem) {
         for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) s_hist[i] = 0;
     }
-    if (threadIdx.x == 0) { s_unassigned = 0; s_new = 0; }
+    if (threadIdx.x == 0) s_unassigned = 0;
     __syncthreads();
     int iter = 0;
     // the trip count is the same for every thread of a CTA (the epoch flush below is a CTA barrier)
@@ -64,18 +65,20 @@ __global__ void __launch_bounds__(256, SCAR_K4_CTAS) scar_aggregate_kernel(const
         // ---- scar table: every SCAR read inserts its own key.  (Combining equal keys inside a warp with
         // __match_any_sync / per-group shuffles was measured slower: most keys of a warp are distinct and
         // every distinct group is a separate divergent pass; the L2 atomics of equal keys coalesce anyway.)
+        bool claimed = false;
+        uint32_t slot = 0;
         if (in_range && rec.status == SCAR_ST_SCAR) {
             const uint8_t *raw; int rawlen;
             get_item(P.seq, r, raw, rawlen);
             uint64_t h1, h2;
             key_hashes(rec, raw, rawlen, P.platform, h1, h2);
-            if (table_insert(T, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample)) atomicAdd(&s_new, 1u);
+            claimed = table_insert(T, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample, slot);
         }
+        table_note_claims(T, claimed, slot);          // (the loop's trip count is uniform: the warp is converged)
     }
     __syncthreads();
     if (P.use_smem) acc_flush(A, s_hist, per_sample);
     if (threadIdx.x == 0 && s_unassigned) atomicAdd(P.unassigned, (unsigned long long)s_unassigned);
-    if (threadIdx.x == 0 && s_new) atomicAdd(P.n_entries, (unsigned long long)s_new);
 }
 
 // ---- verification: every SCAR read's full key equals the key of its slot's first read ------------
@@ -124,41 +127,45 @@ __global__ void __launch_bounds__(256) scar_verify_kernel(const K4VerifyParams P
     }
 }
 
-// ---- export (compaction) and merge ---------------------------------------------------------------
-__global__ void scar_export_kernel(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out,
-                                   uint64_t out_capacity, unsigned long long *n_out)
+// ---- export and merge: both walk the claimed-slot list, not the table ---------------------------------
+__device__ __forceinline__ scar_entry entry_of(const ScarTableSlot &s)
 {
-    // compaction with one atomic per warp: ballot the occupied slots, the first lane reserves the range
-    const uint64_t n_round = (capacity + 31) & ~(uint64_t)31;
-    const int lane = threadIdx.x & 31;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
-         i += (uint64_t)gridDim.x * blockDim.x) {
-        ScarTableSlot s;
-        s.tag = 0;
-        if (i < capacity) s = slots[i];
-        const bool used = s.tag != 0;
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, used);
-        if (!bal) continue;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(bal));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (used) {
-            const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
-            if (pos < out_capacity) {
-                scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = (uint64_t)(s.tag >> 64); e.first_idx = ~s.inv_first;
-                e.count = s.count; e.sample = (uint16_t)s.sample; e.pad = 0;
-                out[pos] = e;
-            }
-        }
+    scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = (uint64_t)(s.tag >> 64); e.first_idx = ~s.inv_first;
+    e.count = s.count; e.sample = (uint16_t)s.sample; e.pad = 0;
+    return e;
+}
+
+__global__ void scar_export_kernel(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
+                                   scar_entry *out, uint64_t out_capacity)
+{
+    const uint64_t n = *n_entries;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n && i < out_capacity;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = entry_of(slots[claimed[i]]);
+}
+
+// empty the claimed slots (the count is reset by the caller, stream-ordered after this kernel)
+__global__ void scar_clear_kernel(ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries)
+{
+    const uint64_t n = *n_entries;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 *p = reinterpret_cast<uint4 *>(slots + claimed[i]);
+        p[0] = make_uint4(0u, 0u, 0u, 0u); p[1] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
 __global__ void scar_merge_kernel(K4Params P, const scar_entry *in, uint64_t n_in)
 {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in;
-         i += (uint64_t)gridDim.x * blockDim.x) {
-        const scar_entry e = in[i];
-        if (table_insert(table_ref(P), e.h1, e.h2, e.count, e.first_idx, e.sample)) atomicAdd(P.n_entries, 1ull);
+    const ScarTableRef T = table_ref(P);
+    const uint64_t n_round = (n_in + 31) & ~(uint64_t)31;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (uint64_t)gridDim.x * blockDim.x) {
+        bool claimed = false;
+        uint32_t slot = 0;
+        if (i < n_in) {
+            const scar_entry e = in[i];
+            claimed = table_insert(T, e.h1, e.h2, e.count, e.first_idx, e.sample, slot);
+        }
+        table_note_claims(T, claimed, slot);
     }
 }
 
@@ -167,18 +174,17 @@ __global__ void scar_merge_kernel(K4Params P, const scar_entry *in, uint64_t n_i
 // `region` entries, entry 0 is a header whose h1 holds the count) receives this rank's entries owned by
 // rank o; the regions are exchanged with one all-to-all and every rank folds what it receives.  The
 // counts travel in band, so the whole merge is stream-ordered: no host synchronisation.
-__global__ void scar_export_parts_kernel(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out,
-                                         uint32_t n_parts, uint64_t region, int32_t *status)
+__global__ void scar_export_parts_kernel(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
+                                         scar_entry *out, uint32_t n_parts, uint64_t region, int32_t *status)
 {
-    const uint64_t n_round = (capacity + 31) & ~(uint64_t)31;
+    const uint64_t n = *n_entries, n_round = (n + 31) & ~(uint64_t)31;
     const int lane = threadIdx.x & 31;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
          i += (uint64_t)gridDim.x * blockDim.x) {
+        const bool used = i < n;
         ScarTableSlot s;
         s.tag = 0;
-        if (i < capacity) s = slots[i];
-        const bool used = s.tag != 0;
-        if (!__any_sync(0xFFFFFFFFu, used)) continue;
+        if (used) s = slots[claimed[i]];
         const uint64_t h2 = (uint64_t)(s.tag >> 64);
         const uint32_t owner = used ? (uint32_t)(h2 >> 40) % n_parts : 0xFFFFFFFFu;
         // one atomic per (warp, owner): the region cursors are only n_parts addresses
@@ -194,11 +200,8 @@ __global__ void scar_export_parts_kernel(const ScarTableSlot *slots, uint64_t ca
             if (owner == o) pos = 1ull + base + __popc(bal & ((1u << lane) - 1u));
         }
         if (used) {
-            if (pos < region) {
-                scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = h2; e.first_idx = ~s.inv_first; e.count = s.count;
-                e.sample = (uint16_t)s.sample; e.pad = 0;
-                out[(uint64_t)owner * region + pos] = e;
-            } else atomicOr(status, 4);
+            if (pos < region) out[(uint64_t)owner * region + pos] = entry_of(s);
+            else atomicOr(status, 4);
         }
     }
 }
@@ -206,21 +209,21 @@ __global__ void scar_export_parts_kernel(const ScarTableSlot *slots, uint64_t ca
 // The same export fused with the exchange: every entry is stored straight into the receive buffer of its
 // OWNER GPU through NVLink peer memory (peers.base[o] is rank o's receive buffer mapped into this process;
 // this rank writes region `my_rank` of it), so no separate all-to-all pass runs and the transfer overlaps
-// the table scan.  The region cursors stay local; a second tiny kernel publishes the counts as headers.
+// the table walk.  The region cursors stay local; a second tiny kernel publishes the counts as headers.
 struct ScarPeers { scar_entry *base[SCAR_MAX_PEERS]; };
 
-__global__ void scar_export_p2p_kernel(const ScarTableSlot *slots, uint64_t capacity, ScarPeers peers, uint32_t n_parts,
-                                       uint32_t my_rank, uint64_t region, unsigned long long *cursors)
+__global__ void scar_export_p2p_kernel(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
+                                       ScarPeers peers, uint32_t n_parts, uint32_t my_rank, uint64_t region,
+                                       unsigned long long *cursors)
 {
-    const uint64_t n_round = (capacity + 31) & ~(uint64_t)31;
+    const uint64_t n = *n_entries, n_round = (n + 31) & ~(uint64_t)31;
     const int lane = threadIdx.x & 31;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
          i += (uint64_t)gridDim.x * blockDim.x) {
+        const bool used = i < n;
         ScarTableSlot s;
         s.tag = 0;
-        if (i < capacity) s = slots[i];
-        const bool used = s.tag != 0;
-        if (!__any_sync(0xFFFFFFFFu, used)) continue;
+        if (used) s = slots[claimed[i]];
         const uint64_t h2 = (uint64_t)(s.tag >> 64);
         const uint32_t owner = used ? (uint32_t)(h2 >> 40) % n_parts : 0xFFFFFFFFu;
         unsigned long long pos = 0;
@@ -233,8 +236,7 @@ __global__ void scar_export_p2p_kernel(const ScarTableSlot *slots, uint64_t capa
             if (owner == o) pos = 1ull + base + __popc(bal & ((1u << lane) - 1u));
         }
         if (used && pos < region) {                    // (an overflow is reported by the header kernel)
-            scar_entry e; e.h1 = (uint64_t)s.tag; e.h2 = h2; e.first_idx = ~s.inv_first; e.count = s.count;
-            e.sample = (uint16_t)s.sample; e.pad = 0;
+            const scar_entry e = entry_of(s);
             uint4 *dst = reinterpret_cast<uint4 *>(peers.base[owner] + (uint64_t)my_rank * region + pos);
             const uint4 *src = reinterpret_cast<const uint4 *>(&e);
             dst[0] = src[0]; dst[1] = src[1];          // two 16-byte stores over NVLink
@@ -256,55 +258,50 @@ __global__ void scar_export_p2p_headers_kernel(ScarPeers peers, uint32_t n_parts
     dst[0] = src[0]; dst[1] = src[1];
 }
 
-cudaError_t scar_launch_export_p2p(const ScarTableSlot *slots, uint64_t capacity, scar_entry *const *peer_base,
-                                   uint32_t n_parts, uint32_t my_rank, uint64_t region, unsigned long long *cursors,
-                                   int32_t *status, int sm_count, cudaStream_t stream)
+cudaError_t scar_launch_export_p2p(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
+                                   scar_entry *const *peer_base, uint32_t n_parts, uint32_t my_rank, uint64_t region,
+                                   unsigned long long *cursors, int32_t *status, int sm_count, cudaStream_t stream)
 {
     ScarPeers peers;
     for (uint32_t o = 0; o < SCAR_MAX_PEERS; ++o) peers.base[o] = o < n_parts ? peer_base[o] : nullptr;
-    const int threads = 256;
-    int64_t blocks = (int64_t)((capacity + threads - 1) / threads);
-    const int64_t cap = (int64_t)sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    scar_export_p2p_kernel<<<(unsigned)blocks, threads, 0, stream>>>(slots, capacity, peers, n_parts, my_rank, region, cursors);
+    scar_export_p2p_kernel<<<(unsigned)(sm_count * 4), 256, 0, stream>>>(slots, claimed, n_entries, peers, n_parts, my_rank, region, cursors);
     scar_export_p2p_headers_kernel<<<1, 32, 0, stream>>>(peers, n_parts, my_rank, region, cursors, status);
     return cudaGetLastError();
 }
 
 __global__ void scar_merge_parts_kernel(K4Params P, const scar_entry *in, uint32_t n_parts, uint64_t region)
 {
-    __shared__ unsigned int s_new;
-    if (threadIdx.x == 0) s_new = 0;
-    __syncthreads();
+    const ScarTableRef T = table_ref(P);
     for (uint32_t g = 0; g < n_parts; ++g) {
         const scar_entry *reg = in + (uint64_t)g * region;
         uint64_t cnt = reg->h1;
         if (cnt > region - 1) cnt = region - 1;
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt;
+        const uint64_t n_round = (cnt + 31) & ~(uint64_t)31;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
              i += (uint64_t)gridDim.x * blockDim.x) {
-            const scar_entry e = reg[1 + i];
-            if (table_insert(table_ref(P), e.h1, e.h2, e.count, e.first_idx, e.sample)) atomicAdd(&s_new, 1u);
+            bool claimed = false;
+            uint32_t slot = 0;
+            if (i < cnt) {
+                const scar_entry e = reg[1 + i];
+                claimed = table_insert(T, e.h1, e.h2, e.count, e.first_idx, e.sample, slot);
+            }
+            table_note_claims(T, claimed, slot);
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_new) atomicAdd(P.n_entries, (unsigned long long)s_new);
 }
 
-cudaError_t scar_launch_export_parts(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint32_t n_parts,
-                                     uint64_t region, int32_t *status, int sm_count, cudaStream_t stream)
+cudaError_t scar_launch_export_parts(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
+                                     scar_entry *out, uint32_t n_parts, uint64_t region, int32_t *status, int sm_count,
+                                     cudaStream_t stream)
 {
-    const int threads = 256;
-    int64_t blocks = (int64_t)((capacity + threads - 1) / threads);
-    const int64_t cap = (int64_t)sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    scar_export_parts_kernel<<<(unsigned)blocks, threads, 0, stream>>>(slots, capacity, out, n_parts, region, status);
+    scar_export_parts_kernel<<<(unsigned)(sm_count * 4), 256, 0, stream>>>(slots, claimed, n_entries, out, n_parts, region, status);
     return cudaGetLastError();
 }
 
 cudaError_t scar_launch_merge_parts(const K4Params &P, const scar_entry *in, uint32_t n_parts, uint64_t region,
                                     int sm_count, cudaStream_t stream)
 {
-    scar_merge_parts_kernel<<<(unsigned)(sm_count * 8), 256, 0, stream>>>(P, in, n_parts, region);
+    scar_merge_parts_kernel<<<(unsigned)(sm_count * 4), 256, 0, stream>>>(P, in, n_parts, region);
     return cudaGetLastError();
 }
 
@@ -337,15 +334,20 @@ cudaError_t scar_launch_verify(const K4VerifyParams &P, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
-cudaError_t scar_launch_export(const ScarTableSlot *slots, uint64_t capacity, scar_entry *out, uint64_t out_capacity,
-                               unsigned long long *n_out, int sm_count, cudaStream_t stream)
+cudaError_t scar_launch_export(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
+                               scar_entry *out, uint64_t out_capacity, int sm_count, cudaStream_t stream)
 {
-    const int threads = 256;
-    int64_t blocks = (int64_t)((capacity + threads - 1) / threads);
-    const int64_t cap = (int64_t)sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    scar_export_kernel<<<(unsigned)blocks, threads, 0, stream>>>(slots, capacity, out, out_capacity, n_out);
+    scar_export_kernel<<<(unsigned)(sm_count * 4), 256, 0, stream>>>(slots, claimed, n_entries, out, out_capacity);
     return cudaGetLastError();
+}
+
+cudaError_t scar_launch_clear(ScarTableSlot *slots, const uint32_t *claimed, unsigned long long *n_entries, int sm_count,
+                              cudaStream_t stream)
+{
+    scar_clear_kernel<<<(unsigned)(sm_count * 4), 256, 0, stream>>>(slots, claimed, n_entries);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(n_entries, 0, sizeof(unsigned long long), stream);
 }
 
 cudaError_t scar_launch_merge(const K4Params &P, const scar_entry *in, uint64_t n_in, int sm_count, cudaStream_t stream)

@@ -120,6 +120,8 @@ struct ScarTableRef {
     uint64_t slot_mask;      // capacity - 1
     uint32_t max_probe;
     int32_t *status;         // bit 1: table full
+    uint32_t *claimed;       // indices of the claimed slots, in claim order ([capacity]; export / clear walk this list,
+    unsigned long long *n_entries;   // not the whole table) and their number
 };
 
 __device__ __forceinline__ unsigned __int128 make_tag(uint64_t h1, uint64_t h2)
@@ -140,7 +142,7 @@ __device__ __forceinline__ unsigned __int128 load_tag(const ScarTableSlot *s)
 // publishes both hashes at once); count and first_idx are fire-and-forget reductions.
 // Returns 1 when a new slot was claimed.
 __device__ __forceinline__ int table_insert(const ScarTableRef &T, uint64_t h1, uint64_t h2, uint32_t n,
-                                            uint64_t first, uint32_t sample)
+                                            uint64_t first, uint32_t sample, uint32_t &claimed_slot)
 {
     const unsigned __int128 tag = make_tag(h1, h2);
     uint64_t slot = h1 & T.slot_mask;
@@ -160,13 +162,25 @@ __device__ __forceinline__ int table_insert(const ScarTableRef &T, uint64_t h1, 
         if (cur == tag) {
             atomicAdd(&s->count, n);
             atomicMax(&s->inv_first, ~(unsigned long long)first);
-            if (claimed) s->sample = sample;
+            if (claimed) { s->sample = sample; claimed_slot = (uint32_t)slot; }
             return claimed;
         }
         slot = (slot + 1) & T.slot_mask;
     }
     atomicOr(T.status, 2);
     return 0;
+}
+
+// Append the slots claimed by the lanes of a (converged, full) warp to the claimed-slot list: one atomic per warp.
+__device__ __forceinline__ void table_note_claims(const ScarTableRef &T, bool claimed, uint32_t slot)
+{
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, claimed);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(T.n_entries, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (claimed) T.claimed[base + __popc(mask & ((1u << lane) - 1u))] = slot;
 }
 
 // ---- per-sample accumulators in shared memory (32-bit words) ------------------------------------------

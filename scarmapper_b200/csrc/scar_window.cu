@@ -693,11 +693,11 @@ scar_window_kernel(const K3Params P)
     __shared__ uint32_t g_ctx[GMAX][K3_TILE];                            // stored length | target id << 16
     __shared__ uint32_t g_queue[GMAX][2][2 * K3_TILE];                   // item = local read | p << 8
     __shared__ uint32_t g_count[GMAX][3][2];                             // [round % 3][side]
-    __shared__ unsigned int g_unassigned[GMAX], g_new[GMAX];             // fused: aggregation
+    __shared__ unsigned int g_unassigned[GMAX];                          // fused: aggregation
     uint32_t *s_left = g_left[group], *s_right = g_right[group], *s_ctx = g_ctx[group];
     uint32_t (*s_queue)[2 * K3_TILE] = g_queue[group];
     uint32_t (*s_count)[2] = g_count[group];
-    unsigned int &s_unassigned = g_unassigned[group], &s_new = g_new[group];
+    unsigned int &s_unassigned = g_unassigned[group];
     if (tx < 6) s_count[tx >> 1][tx & 1] = 0;
 
     // ---- fused: accumulators of the aggregation, the warps' raw rings and their mbarriers
@@ -713,13 +713,14 @@ scar_window_kernel(const K3Params P)
         const uint32_t warp_all = (uint32_t)(group * (K3_TILE / 32) + warp);
         ring_addr = smem_u32(tile_buf) + (uint32_t)n_groups * cells_bytes + warp_all * FUSED_SLOTS * P.raw_cap;
         ring_bar = smem_u32(bar) + 16u + warp_all * FUSED_SLOTS * 8u;
-        if (tx == 0) { s_unassigned = 0; s_new = 0; }
+        if (tx == 0) s_unassigned = 0;
         if (lane == 0) {
 #pragma unroll
             for (int sl = 0; sl < FUSED_SLOTS; ++sl) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bar + 8u * sl));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         TB.slots = P.slots; TB.slot_mask = P.slot_mask; TB.max_probe = P.max_probe; TB.status = P.status;
+        TB.claimed = P.claimed; TB.n_entries = P.n_entries;
         AC.counters = P.counters; AC.phase_hist = P.phase_hist; AC.unassigned = P.unassigned; AC.n_samples = P.n_samples;
         AC.pb = P.phase_bins; AC.joint = P.phase_joint;
         per_sample = acc_words_per_sample(AC.pb, AC.joint);
@@ -1088,39 +1089,44 @@ scar_window_kernel(const K3Params P)
         // ---- fused: stage 4 (INDEL_Processing.py:186-196 and the summary / phasing bookkeeping), what K4 does from
         // the records in a second pass.  The key's segment is hashed from the packed cells in shared memory; only a
         // segment with a non-ACGT byte goes back to the raw read.
-        if (FUSED && P.aggregate && in_range) {
-            if (rec.status == SCAR_ST_UNASSIGNED) atomicAdd(&s_unassigned, 1u);
-            else if (P.hist_smem) acc_add_smem(s_hist, per_sample, AC.pb, AC.joint, rec);
-            else acc_add_global(AC, rec);
-            if (rec.status == SCAR_ST_SCAR) {
-                const KeySegment ks = key_segment(rec);
-                uint64_t h1, h2;
-                key_init(ks.hdr, h1, h2);
-                bool acgt = true;
-                for (int q = ks.lo; q < ks.hi; q += 32) {
-                    const int n = min(32, ks.hi - q);
-                    const Word32 w = read32(rc0, q);
-                    const uint32_t vm = n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
-                    acgt = acgt && (w.valid & vm) == vm;
-                    key_step(n == 32 ? w.code : (w.code & ((1ull << (2 * n)) - 1ull)), h1, h2);
+        if (FUSED && P.aggregate) {
+            bool claimed = false;
+            uint32_t claimed_slot = 0;
+            if (in_range) {
+                if (rec.status == SCAR_ST_UNASSIGNED) atomicAdd(&s_unassigned, 1u);
+                else if (P.hist_smem) acc_add_smem(s_hist, per_sample, AC.pb, AC.joint, rec);
+                else acc_add_global(AC, rec);
+                if (rec.status == SCAR_ST_SCAR) {
+                    const KeySegment ks = key_segment(rec);
+                    uint64_t h1, h2;
+                    key_init(ks.hdr, h1, h2);
+                    bool acgt = true;
+                    for (int q = ks.lo; q < ks.hi; q += 32) {
+                        const int n = min(32, ks.hi - q);
+                        const Word32 w = read32(rc0, q);
+                        const uint32_t vm = n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+                        acgt = acgt && (w.valid & vm) == vm;
+                        key_step(n == 32 ? w.code : (w.code & ((1ull << (2 * n)) - 1ull)), h1, h2);
+                    }
+                    if (acgt) key_finish(h1, h2);
+                    else {
+                        const uint8_t *raw; int rawlen;          // (the fused kernel does not take the Ramsden platform)
+                        get_item(P.seq, r, raw, rawlen);
+                        uint64_t hh[2];
+                        key_hashes_bytes_fwd(ks.hdr, ks.lo, ks.hi, raw + (P.platform == SCAR_PLATFORM_TRUSEQ ? 6 : 0), hh);
+                        h1 = hh[0]; h2 = hh[1];
+                    }
+                    claimed = table_insert(TB, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample, claimed_slot);
                 }
-                if (acgt) key_finish(h1, h2);
-                else {
-                    const uint8_t *raw; int rawlen;          // (the fused kernel does not take the Ramsden platform)
-                    get_item(P.seq, r, raw, rawlen);
-                    uint64_t hh[2];
-                    key_hashes_bytes_fwd(ks.hdr, ks.lo, ks.hi, raw + (P.platform == SCAR_PLATFORM_TRUSEQ ? 6 : 0), hh);
-                    h1 = hh[0]; h2 = hh[1];
-                }
-                if (table_insert(TB, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample)) atomicAdd(&s_new, 1u);
             }
+            __syncwarp();
+            table_note_claims(TB, claimed, claimed_slot);      // one atomic per warp appends the new slots to the list
         }
     }
     if (FUSED && P.aggregate) {
         group_sync();
         if (P.hist_smem) acc_flush_exch(AC, s_hist, per_sample, tx, K3_TILE);      // (a slower group flushes what it adds later)
         if (tx == 0 && s_unassigned) atomicAdd(P.unassigned, (unsigned long long)s_unassigned);
-        if (tx == 0 && s_new) atomicAdd(P.n_entries, (unsigned long long)s_new);
     }
 }
 

@@ -196,6 +196,10 @@ class ScarEngine:
         """Clear table and accumulators on the current torch stream (no host synchronisation)."""
         N.check(self._L.scar_reset_dev(self._ctx, self._stream()))
 
+    def set_sm_limit(self, n_sms: int = 0):
+        """Size this engine's persistent grids for n_sms SMs (0 = all): leaves the rest to a merge running beside."""
+        N.check(self._L.scar_ctx_set_sm_limit(self._ctx, int(n_sms)))
+
     def launch_count(self) -> int:
         return int(self._L.scar_launch_count(self._ctx))
 
