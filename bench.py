@@ -429,10 +429,11 @@ def main():
     merge_done = [None, None]
     step_no = [0]
     # N > 1: the persistent grids leave a few SMs to the merge kernels and NCCL, which then really run beside the
-    # next step instead of waiting for a CTA slot (SCAR_BENCH_SM_RESERVE, default 8 of the 148)
+    # next step instead of waiting for a CTA slot (SCAR_BENCH_SM_RESERVE; measured at N=2: 0, 4 and 8 reserved SMs give
+    # 1.138e10, 1.135e10 and 1.115e10 reads/s, so the default is 0)
     sm_reserve = 0
     if world > 1:
-        sm_reserve = int(os.environ.get("SCAR_BENCH_SM_RESERVE", "8"))
+        sm_reserve = int(os.environ.get("SCAR_BENCH_SM_RESERVE", "0"))
         sms = torch.cuda.get_device_properties(local).multi_processor_count
         for e in engines:
             e.set_sm_limit(sms - sm_reserve)
