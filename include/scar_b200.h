@@ -12,6 +12,7 @@
  *   scarmapper/INDEL_Processing.py:550-700  homeology_search / templated_insertion_search -> scar_homeology_batch
  *   scarmapper/INDEL_Processing.py:702-757  raw_data_output (body)         -> scar_raw_rows_host
  *   scarmapper/INDEL_Processing.py:57-80,759-795 window_mapping/cutsite_search -> scar_ctx_create (tables), scar_cutsite_search
+ *   scarmapper/AlignmentProcessing.pyx:18-149 alignment_processing          -> scar_alignment_batch
  *
  * Conventions: every function returns 0 on success or a negative SCAR_ERR_* code;
  * scar_last_error() gives the text for the calling thread.  No exceptions cross the boundary.
@@ -254,6 +255,18 @@ int scar_homeology_batch(int32_t device, const scar_ragged *consensus, const sca
                          const int32_t *clj, const int32_t *crj, const int32_t *tlj, const int32_t *trj,
                          const int32_t *target_idx, const scar_ragged *targets, const scar_ragged *regions,
                          int32_t n_targets, int64_t n, int32_t *out);
+
+/* AlignmentProcessing.alignment_processing (scarmapper/AlignmentProcessing.pyx:18-149; legacy module of the reference:
+ * walks a gapped alignment of the consensus against the genome) for a batch of alignments on the device (host
+ * buffers), one thread per alignment.  Alignment i: gapped_genomic_i, gapped_consensus_i (one length, equal to
+ * gap_con_len_i), cutposition_i, gap_genome_len_i (the 10-90 % window is taken from it, as in the reference).
+ * counts[i] = 8 int32 (struct ScarAlignmentCounts, scarmapper_b200/csrc/scar_alignment_core.h): left / right deleted
+ * columns, left / right inserted columns, number of microhomology / insertion / snv strings, overflow flag;
+ * spans[i] = [3][max_spans][2] int32 (start, length) of those strings: microhomology slices of gapped_genomic,
+ * insertion and snv slices of gapped_consensus. */
+int scar_alignment_batch(int32_t device, const scar_ragged *genomic, const scar_ragged *consensus,
+                         const int32_t *cutposition, const int32_t *gap_con_len, const int32_t *gap_genome_len,
+                         int64_t n, int32_t max_spans, int32_t *counts, int32_t *spans);
 
 /* Sequence_Magic.match_maker over a batch on the device (host buffers): out[i] = lev(q_i,u_i) - (|u_i|-|q_i|). */
 int scar_match_maker_batch(int32_t device, const scar_ragged *query, const scar_ragged *unknown,

@@ -24,15 +24,17 @@ REFERENCE = os.environ.get("SCARMAPPER_REFERENCE", "/root/reference")
 PYX = os.path.join(REFERENCE, "scarmapper", "SlidingWindow.pyx")
 
 
-def ref_so() -> str | None:
-    hits = sorted(glob.glob(os.path.join(REF_DIR, "SlidingWindow.*.so")))
+def ref_so(name: str = "SlidingWindow") -> str | None:
+    hits = sorted(glob.glob(os.path.join(REF_DIR, name + ".*.so")))
     return hits[0] if hits else None
 
 
-def build(force: bool = False) -> str | None:
+def build(force: bool = False, name: str = "SlidingWindow") -> str | None:
     """Returns the path of the built module, or None when the reference tree is absent
-    (e.g. on the GPU box, where the prebuilt file is used as is)."""
-    have = ref_so()
+    (e.g. on the GPU box, where the prebuilt file is used as is).  name: SlidingWindow (the module the reference
+    builds) or AlignmentProcessing (its legacy sibling, scarmapper/AlignmentProcessing.pyx)."""
+    PYX = os.path.join(REFERENCE, "scarmapper", name + ".pyx")
+    have = ref_so(name)
     if not os.path.exists(PYX):
         return have
     if have and not force and os.path.getmtime(have) >= os.path.getmtime(PYX):
@@ -46,17 +48,17 @@ def build(force: bool = False) -> str | None:
     try:
         exts = cythonize([PYX], build_dir=tmp, quiet=True, language_level=3)
         for e in exts:
-            e.name = "SlidingWindow"
+            e.name = name
         dist = Distribution({"name": "scar_ref", "ext_modules": exts})
         cmd = build_ext(dist)
         cmd.build_lib = os.path.join(tmp, "lib")
         cmd.build_temp = os.path.join(tmp, "tmp")
         cmd.ensure_finalized()
         cmd.run()
-        built = glob.glob(os.path.join(tmp, "lib", "**", "SlidingWindow*.so"), recursive=True)
+        built = glob.glob(os.path.join(tmp, "lib", "**", name + "*.so"), recursive=True)
         if not built:
-            raise RuntimeError("cythonize produced no SlidingWindow shared object")
-        for old in glob.glob(os.path.join(REF_DIR, "SlidingWindow.*.so")):
+            raise RuntimeError("cythonize produced no {} shared object".format(name))
+        for old in glob.glob(os.path.join(REF_DIR, name + ".*.so")):
             os.remove(old)
         dst = os.path.join(REF_DIR, os.path.basename(built[0]))
         shutil.copy2(built[0], dst)
@@ -101,13 +103,13 @@ def build_baseline(force: bool = False) -> str | None:
     return baseline_tree()
 
 
-def load():
-    """Import the compiled reference module (oracle/_ref/SlidingWindow.*.so) or return None."""
-    so = ref_so()
+def load(name: str = "SlidingWindow"):
+    """Import the compiled reference module (oracle/_ref/<name>.*.so) or return None."""
+    so = ref_so(name)
     if so is None:
         return None
     import importlib.util
-    spec = importlib.util.spec_from_file_location("SlidingWindow", so)
+    spec = importlib.util.spec_from_file_location(name, so)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
@@ -116,4 +118,5 @@ def load():
 if __name__ == "__main__":
     out = build(force="--force" in sys.argv)
     print(out or "reference tree not present and no prebuilt module")
+    print(build(force="--force" in sys.argv, name="AlignmentProcessing") or "no AlignmentProcessing module")
     print(build_baseline(force="--force" in sys.argv) or "no baseline tree")

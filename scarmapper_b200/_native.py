@@ -115,6 +115,7 @@ PROTOTYPES = {
                                              C.POINTER(C.c_int64)]),
     "scar_stored_gather_host": (C.c_int, [_RP, _P, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P]),
     "scar_homeology_batch": (C.c_int, [C.c_int32, _RP, _RP, _P, _P, _P, _P, _P, _RP, _RP, C.c_int32, C.c_int64, _P]),
+    "scar_alignment_batch": (C.c_int, [C.c_int32, _RP, _RP, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
     "scar_match_maker_batch": (C.c_int, [C.c_int32, _RP, _RP, C.c_int64, _P]),
 }
 

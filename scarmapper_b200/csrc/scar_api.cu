@@ -1306,3 +1306,49 @@ extern "C" int scar_homeology_batch(int32_t device, const scar_ragged *consensus
     if (err != cudaSuccess) return fail(SCAR_ERR_CUDA, "homeology kernel failed: %s", cudaGetErrorString(err));
     return SCAR_OK;
 }
+
+// ---- AlignmentProcessing.alignment_processing over a batch of gapped alignments -------------------------
+extern "C" int scar_alignment_batch(int32_t device, const scar_ragged *genomic, const scar_ragged *consensus,
+                                    const int32_t *cutposition, const int32_t *gap_con_len, const int32_t *gap_genome_len,
+                                    int64_t n, int32_t max_spans, int32_t *counts, int32_t *spans)
+{
+    if (!genomic || !consensus || !cutposition || !gap_con_len || !gap_genome_len || !counts || !spans || n < 0 || max_spans < 1)
+        return fail(SCAR_ERR_INVALID, "bad argument");
+    if (n == 0) return SCAR_OK;
+    // the reference indexes both strings up to gap_con_len (an IndexError there): the batch takes well-formed
+    // alignments only - two strings of one length, gap_con_len equal to it
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t *g, *c; int ng, nc;
+        get_item(*genomic, i, g, ng);
+        get_item(*consensus, i, c, nc);
+        if (ng != nc || gap_con_len[i] != nc)
+            return fail(SCAR_ERR_UNSUPPORTED, "alignment %lld: the two gapped strings and gap_con_len must have one length", (long long)i);
+    }
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SCAR_ERR_CUDA, "CUDA device %d not present", device);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    StagedList dg, dc;
+    DevInts a, b, c;
+    int rc;
+    if ((rc = dg.stage(*genomic, n)) || (rc = dc.stage(*consensus, n)) || (rc = a.upload(cutposition, n)) ||
+        (rc = b.upload(gap_con_len, n)) || (rc = c.upload(gap_genome_len, n)))
+        return rc;
+    int32_t *dcounts = nullptr, *dspans = nullptr;
+    const size_t span_ints = (size_t)n * 3 * max_spans * 2;
+    if (cudaMalloc((void **)&dcounts, (size_t)n * 8 * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&dspans, span_ints * sizeof(int32_t)) != cudaSuccess) {
+        cudaFree(dcounts);
+        return fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
+    }
+    cudaError_t err = cudaMemset(dspans, 0, span_ints * sizeof(int32_t));
+    if (err == cudaSuccess)
+        err = scar_launch_alignment(dg.dev, dc.dev, a.p, b.p, c.p, n, max_spans, dcounts, dspans, prop.multiProcessorCount, nullptr);
+    if (err == cudaSuccess) err = cudaMemcpy(counts, dcounts, (size_t)n * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess) err = cudaMemcpy(spans, dspans, span_ints * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaFree(dcounts); cudaFree(dspans);
+    if (err != cudaSuccess) return fail(SCAR_ERR_CUDA, "alignment kernel failed: %s", cudaGetErrorString(err));
+    return SCAR_OK;
+}

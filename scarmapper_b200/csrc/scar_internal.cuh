@@ -219,6 +219,9 @@ cudaError_t scar_launch_homeology(const scar_ragged &cons, const scar_ragged &in
                                   const scar_ragged &regions, const int32_t *clj, const int32_t *crj, const int32_t *tlj,
                                   const int32_t *trj, const int32_t *target_idx, int32_t n_targets, int64_t n, void *out,
                                   cudaStream_t stream);
+cudaError_t scar_launch_alignment(const scar_ragged &genomic, const scar_ragged &consensus, const int32_t *cutposition,
+                                  const int32_t *gap_con_len, const int32_t *gap_genome_len, int64_t n, int32_t max_spans,
+                                  void *counts, int32_t *spans, int sm_count, cudaStream_t stream);
 #define SCAR_MAX_PEERS 32
 cudaError_t scar_launch_export_p2p(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
                                    scar_entry *const *peer_base,
