@@ -13,6 +13,7 @@
  *   scarmapper/INDEL_Processing.py:702-757  raw_data_output (body)         -> scar_raw_rows_host
  *   scarmapper/INDEL_Processing.py:57-80,759-795 window_mapping/cutsite_search -> scar_ctx_create (tables), scar_cutsite_search
  *   scarmapper/AlignmentProcessing.pyx:18-149 alignment_processing          -> scar_alignment_batch
+ *   scarmapper/INDEL_Processing.py:876-889,988-1002 demultiplexed FASTQ      -> scar_demux_fastq_rows_host
  *
  * Conventions: every function returns 0 on success or a negative SCAR_ERR_* code;
  * scar_last_error() gives the text for the calling thread.  No exceptions cross the boundary.
@@ -241,6 +242,14 @@ int scar_raw_rows_indexed_host(const scar_record *records, const scar_ragged *re
  * rcomp(consensus) for 3'-strand guides, :312-327).  out_off receives n_rows + 1 offsets; out = NULL sizes only. */
 int scar_stored_gather_host(const scar_ragged *reads, const int64_t *rows, int64_t n_rows, int32_t platform,
                             const uint8_t *flip, uint8_t *out, int64_t out_capacity, int64_t *out_off);
+
+/* The demultiplexed FASTQ of --Demultiplex True (scarmapper/INDEL_Processing.py:876-889,988-1002;
+ * Valkyries/FASTQ_Tools.py:532-551): "@name\nseq\n+\nqual\n" for the reads rows[0..n_rows) (one sample's reads in file
+ * order), formatted straight from the FASTQ text; seq_off / seq_len are the sequence views scar_fastq_index reports.
+ * name = header.strip("\n").strip("@"), seq and qual stripped of white space, as FASTQ_Reader.seq_read delivers them.
+ * out = NULL sizes only. */
+int scar_demux_fastq_rows_host(const uint8_t *text, int64_t n_bytes, const int64_t *seq_off, const int32_t *seq_len,
+                               const int64_t *rows, int64_t n_rows, uint8_t *out, int64_t out_capacity, int64_t *out_bytes);
 
 /* ScarSearch.homeology_search (scarmapper/INDEL_Processing.py:550-657) and templated_insertion_search (:659-700)
  * for a batch of scar patterns on the device (host buffers), one thread per key.  Key i: consensus_i, its

@@ -113,6 +113,7 @@ PROTOTYPES = {
                                      C.POINTER(C.c_int64)]),
     "scar_raw_rows_indexed_host": (C.c_int, [_P, _RP, _P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,
                                              C.POINTER(C.c_int64)]),
+    "scar_demux_fastq_rows_host": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int64, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "scar_stored_gather_host": (C.c_int, [_RP, _P, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P]),
     "scar_homeology_batch": (C.c_int, [C.c_int32, _RP, _RP, _P, _P, _P, _P, _P, _RP, _RP, C.c_int32, C.c_int64, _P]),
     "scar_alignment_batch": (C.c_int, [C.c_int32, _RP, _RP, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),

@@ -154,3 +154,51 @@ extern "C" int scar_stored_gather_host(const scar_ragged *reads, const int64_t *
     if (out && pos > out_capacity) return scar_fail(SCAR_ERR_INVALID, "stored gather: %lld bytes needed", (long long)pos);
     return SCAR_OK;
 }
+
+// ---- demultiplexed FASTQ (--Demultiplex True) -------------------------------------------------------------------
+// The reference keeps [name, seq, qual] of every read per sample and writes "@name\nseq\n+\nqual\n" per read at the
+// end of the run (scarmapper/INDEL_Processing.py:876-889,988-1002; Valkyries/FASTQ_Tools.py:532-551), with
+// name = header.strip("\n").strip("@") and seq / qual stripped of white space (FASTQ_Tools.py:640-643).  Here the
+// records are formatted straight from the FASTQ text: rows[k] is a read index, seq_off[r] the offset of read r's
+// (stripped) sequence in `text` as scar_fastq_index reports it; the header is the line before the sequence line, the
+// quality line the second line after it.  Call with out = NULL for the size.
+static inline bool fq_space(uint8_t c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f' || c == '\n'; }
+
+extern "C" int scar_demux_fastq_rows_host(const uint8_t *text, int64_t n_bytes, const int64_t *seq_off, const int32_t *seq_len,
+                                          const int64_t *rows, int64_t n_rows, uint8_t *out, int64_t out_capacity,
+                                          int64_t *out_bytes)
+{
+    if (!text || !seq_off || !seq_len || (!rows && n_rows) || !out_bytes || n_rows < 0 || n_bytes < 0)
+        return scar_fail(SCAR_ERR_INVALID, "bad argument");
+    Sink S{out, out ? out_capacity : 0, 0};
+    for (int64_t k = 0; k < n_rows; ++k) {
+        const int64_t r = rows[k];
+        const int64_t s0 = seq_off[r], s1 = s0 + seq_len[r];
+        if (s0 < 0 || s1 > n_bytes) return scar_fail(SCAR_ERR_INVALID, "row %lld: sequence view outside the text", (long long)k);
+        // header line: [h0, h1) is the line that ends just before the sequence line starts
+        int64_t ls = s0;
+        while (ls > 0 && text[ls - 1] != '\n') --ls;                 // start of the sequence line
+        if (ls == 0) return scar_fail(SCAR_ERR_INVALID, "row %lld: no header line before the sequence", (long long)k);
+        int64_t h1 = ls - 1, h0 = h1;                                // h1 = position of the header's newline
+        while (h0 > 0 && text[h0 - 1] != '\n') --h0;
+        if (h1 > h0 && text[h1 - 1] == '\r') --h1;                   // text mode: "\r\n" is one newline
+        while (h0 < h1 && text[h0] == '@') ++h0;                     // .strip("@")
+        while (h1 > h0 && text[h1 - 1] == '@') --h1;
+        // quality line: skip the rest of the sequence line and the '+' line
+        int64_t p = s1;
+        while (p < n_bytes && text[p] != '\n') ++p;
+        ++p;
+        while (p < n_bytes && text[p] != '\n') ++p;
+        int64_t q0 = p + 1, q1 = q0;
+        if (q0 > n_bytes) q0 = q1 = n_bytes;
+        while (q1 < n_bytes && text[q1] != '\n') ++q1;
+        while (q0 < q1 && fq_space(text[q0])) ++q0;
+        while (q1 > q0 && fq_space(text[q1 - 1])) --q1;
+        S.put('@'); S.put(text + h0, h1 - h0); S.put('\n');
+        S.put(text + s0, s1 - s0); S.put((const uint8_t *)"\n+\n", 3);
+        S.put(text + q0, q1 - q0); S.put('\n');
+    }
+    *out_bytes = S.n;
+    if (out && S.n > out_capacity) return scar_fail(SCAR_ERR_INVALID, "demultiplexed FASTQ: %lld bytes needed", (long long)S.n);
+    return SCAR_OK;
+}

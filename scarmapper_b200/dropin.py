@@ -158,10 +158,6 @@ def batched_consensus_demultiplex(self, module, device=0):
     """Replacement body of DataProcessing.consensus_demultiplex."""
     args, log = self.args, self.log
     log.info("Consensus Index Search (batched, GPU)")
-    if args.Demultiplex:
-        log.error("--Demultiplex True (writing demultiplexed FASTQ) is not part of the batched path; "
-                  "set it to False or run the reference loop.")
-        raise SystemExit(1)
     if args.Platform not in N.PLATFORMS:
         log.error("--Platform {} not correctly defined.  Edit parameter file and try again".format(args.Platform))
         raise SystemExit(1)
@@ -259,6 +255,10 @@ def batched_consensus_demultiplex(self, module, device=0):
         scar_rows = scar_idx[order].astype(np.int64)
         scar_bounds = np.searchsorted(samples[scar_rows], np.arange(n_samples + 1))
 
+    if args.Demultiplex:
+        write_demultiplexed_fastq(self, batch, records, sample_ids)
+        stage("demultiplexed_fastq")
+
     for s in sorted(first_of, key=first_of.get):
         iid = sample_ids[s]
         t = sample_target[s]
@@ -317,6 +317,33 @@ def batched_consensus_demultiplex(self, module, device=0):
 def _gather(reads, rows, platform):
     from . import engine as _engine
     return _engine.stored_gather(reads, rows, platform)
+
+
+def write_demultiplexed_fastq(self, batch, records, sample_ids):
+    """--Demultiplex True (scarmapper/INDEL_Processing.py:876-889,988-1002): the reference keeps [name, seq, qual] of
+    every read per sample in Python lists and writes "@name\\nseq\\n+\\nqual\\n" per read into the R1 file that
+    dictionary_build opened for the sample ({Job}_{index}_R1.fastq; unmatched reads into {Job}_Unknown_R1.fastq).
+    Here the reads are bucketed by sample once and every file is formatted natively from the FASTQ text
+    (scar_demux_fastq_rows_host).  The reference then asks gzip to compress files named *_Consensus.fastq, which it
+    never wrote (:986,1000,1002 -> Tool_Box.compress_files: gzip reports 'No such file'); that step has no effect
+    and is not repeated."""
+    from . import engine as _engine
+    if not self.args.PEAR:
+        self.log.error("--Demultiplex with un-merged read pairs (PEAR False) is not part of the batched path")
+        raise SystemExit(1)
+    samples = records["sample"].astype(np.int64)
+    samples[records["status"] == N.ST_UNASSIGNED] = len(sample_ids)         # 'Unknown' sorts last
+    order = np.argsort(samples, kind="stable").astype(np.int64)
+    bounds = np.searchsorted(samples[order], np.arange(len(sample_ids) + 2))
+    for s, key in enumerate(list(sample_ids) + ["Unknown"]):
+        rows = order[int(bounds[s]):int(bounds[s + 1])]
+        if rows.size == 0:
+            continue                                   # the reference writes (and closes) only the files that got reads
+        r1 = self.fastq_outfile_dict[key][0]           # FASTQ_Tools.Writer opened by dictionary_build
+        path = r1.file.name
+        r1.close()
+        with open(path, "wb") as f:
+            f.write(_engine.demux_fastq_rows(batch.text, batch.seq, rows))
 
 
 RAW_DATA_COLUMNS = ("Left Deletions\tRight Deletions\tDeletion Size\tMicrohomology\tInsertion\tInsertion Size\t"

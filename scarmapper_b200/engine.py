@@ -430,6 +430,20 @@ def raw_rows_indexed(records, reads, rows, platform, target_region: str, cutsite
     return buf[:need.value].tobytes()
 
 
+def demux_fastq_rows(text, seq_views, rows) -> bytes:
+    """"@name\\nseq\\n+\\nqual\\n" of the reads `rows` (file order), formatted from the FASTQ text; seq_views is the
+    HostRagged of sequence views over `text` (scarmapper_b200.fastq)."""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    assert seq_views.offsets is not None and seq_views.lengths is not None
+    need = C.c_int64(0)
+    args = (text.ctypes.data, text.size, seq_views.offsets.ctypes.data, seq_views.lengths.ctypes.data, rows.ctypes.data, rows.size)
+    N.check(N.lib().scar_demux_fastq_rows_host(*args, None, 0, C.byref(need)))
+    buf = np.empty(max(need.value, 1), dtype=np.uint8)
+    N.check(N.lib().scar_demux_fastq_rows_host(*args, buf.ctypes.data, need.value, C.byref(need)))
+    return buf[:need.value].tobytes()
+
+
 def stored_gather(reads, rows, platform, flip=None):
     """Stored sequences (platform transform applied; row k reverse-complemented when flip[k]) of the reads `rows`,
     as one CSR buffer: (uint8 bytes, int64 offsets[len(rows) + 1])."""

@@ -64,7 +64,7 @@ def raw_data_digest(path):
     return hashlib.sha256(b"\n".join(keep)).hexdigest()
 
 
-def run_reference(case):
+def run_reference(case, demultiplex=False):
     ref_shims.install()
     from scarmapper import INDEL_Processing, TargetMapper
     from Valkyries import FASTQ_Tools, Tool_Box
@@ -74,7 +74,7 @@ def run_reference(case):
         write_inputs(wd, case)
         args = argparse.Namespace(
             WorkingFolder=wd, Job_Name="golden", Verbose="ERROR", Platform=case["platform"], PEAR=True,
-            Demultiplex=False, HR_Donor=case["hr_donor"], N_Limit=case["n_limit"],
+            Demultiplex=demultiplex, HR_Donor=case["hr_donor"], N_Limit=case["n_limit"],
             Minimum_Length=case["min_length"], OutputRawData=True, PatternThreshold=0.0001,
             RefSeq=wd + "refseq.fa", TargetFile=wd + "targets.tsv", SampleManifest=wd + "manifest.tsv",
             Master_Index_File=wd + "master_index.tsv", Spawn=1, FASTQ1=wd + "reads.fastq.gz", FASTQ2=None,
@@ -131,6 +131,9 @@ def run_reference(case):
                 keep = [ln for ln in lines if not ln.startswith(("# Run Start", "# Run End", "Start:", "End:",
                                                                  "FASTQ1:", "FASTQ2:"))]
                 files[fn] = "\n".join(keep)
+            elif fn.endswith("_R1.fastq"):
+                import hashlib                 # --Demultiplex True: one FASTQ per sample (digest; empty files included)
+                file_sha256[fn] = hashlib.sha256(open(os.path.join(wd, fn), "rb").read()).hexdigest()
             elif fn.endswith("_ScarMapper_Raw_Data.txt"):
                 # one line per scarred read: too large to store, so the fixture keeps a digest of the file minus
                 # its wall-clock and version lines
@@ -265,10 +268,14 @@ def main():
     if not ref_shims.available():
         raise SystemExit("needs the reference tree at " + ref_shims.REFERENCE)
     only = set(sys.argv[1:])
-    for name, case in build_cases().items():
+    cases = build_cases()
+    # --Demultiplex True on two small cases: the same inputs, the per-sample FASTQ files digested as well
+    cases["demux_c2_96_samples"] = dict(cases["c2_96_samples"], demultiplex=True)
+    cases["demux_truseq"] = dict(cases["truseq"], demultiplex=True)
+    for name, case in cases.items():
         if only and name not in only:
             continue
-        out = run_reference(case)
+        out = run_reference(case, demultiplex=bool(case.get("demultiplex")))
         blob = {"case": case, "golden": out}
         path = os.path.join(HERE, name + ".json.gz")
         with gzip.GzipFile(path, "wb", mtime=0) as f:

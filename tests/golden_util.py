@@ -19,8 +19,18 @@ from oracle import scar_oracle as orc
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_names():
+def _all_names():
     return sorted(os.path.basename(p)[:-len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.json.gz")))
+
+
+def golden_names():
+    """The per-read / per-table fixtures (one reference run each)."""
+    return [n for n in _all_names() if n != "alignment_cases" and not n.startswith("demux_")]
+
+
+def launcher_golden_names():
+    """Fixtures whose output FILES are compared through the launcher: the above plus the --Demultiplex True runs."""
+    return [n for n in _all_names() if n != "alignment_cases"]
 
 
 def load(name):
@@ -161,12 +171,15 @@ def compare_output_files(wd, golden, ignore_version=False, expect_raw=True):
     assert mine == sorted(golden["files"]), (set(mine) ^ set(golden["files"]))
     if expect_raw:
         for fn, want in golden.get("file_sha256", {}).items():
-            lines = open(os.path.join(wd, fn), "rb").read().split(b"\n")
-            keep = [ln for ln in lines if not ln.startswith((b"# Run Start", b"# Run End", b"# ScarMapper Search v"))]
-            assert hashlib.sha256(b"\n".join(keep)).hexdigest() == want, fn
+            data = open(os.path.join(wd, fn), "rb").read()
+            if fn.endswith(".fastq"):                  # demultiplexed FASTQ (--Demultiplex True): byte for byte
+                assert hashlib.sha256(data).hexdigest() == want, fn
+            else:
+                keep = [ln for ln in data.split(b"\n") if not ln.startswith((b"# Run Start", b"# Run End", b"# ScarMapper Search v"))]
+                assert hashlib.sha256(b"\n".join(keep)).hexdigest() == want, fn
             seen += 1
-        raw = sorted(fn for fn in os.listdir(wd) if fn.endswith("_ScarMapper_Raw_Data.txt"))
-        assert raw == sorted(golden.get("file_sha256", {})), "Raw_Data file set differs"
+        mine = sorted(fn for fn in os.listdir(wd) if fn.endswith(("_ScarMapper_Raw_Data.txt", "_R1.fastq")))
+        assert mine == sorted(golden.get("file_sha256", {})), "Raw_Data / demultiplexed FASTQ file set differs"
     return seen
 
 
@@ -177,7 +190,8 @@ def write_options_file(wd, case, spawn=1, verbose="ERROR", raw=True):
         "IndelProcessing": "True", "FASTQ1": wd + "reads.fastq.gz", "FASTQ2": "", "RefSeq": wd + "refseq.fa",
         "Master_Index_File": wd + "master_index.tsv", "SampleManifest": wd + "manifest.tsv",
         "TargetFile": wd + "targets.tsv", "WorkingFolder": wd, "Verbose": verbose, "Job_Name": "golden",
-        "Spawn": str(spawn), "Demultiplex": "False", "DeleteConsensusFASTQ": "True", "HR_Donor": case["hr_donor"],
+        "Spawn": str(spawn), "Demultiplex": "True" if case.get("demultiplex") else "False", "DeleteConsensusFASTQ": "True",
+        "HR_Donor": case["hr_donor"],
         "Platform": case["platform"], "Search_KMER": "10", "N_Limit": str(case["n_limit"]),
         "Minimum_Length": "{} # Length after trimming".format(case["min_length"]),
         "OutputRawData": "True" if raw else "False", "PatternThreshold": "0.0001 # cutoff", "FigureType": "pdf",

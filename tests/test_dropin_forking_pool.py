@@ -40,7 +40,7 @@ def run_launcher(tmp_path, name, spawn, engine):
 
 
 @pytest.mark.skipif(not ref_shims.available(), reason="reference tree not present")
-@pytest.mark.parametrize("name", ["c2_96_samples", "ragged_hr_donor"])
+@pytest.mark.parametrize("name", ["c2_96_samples", "ragged_hr_donor", "demux_c2_96_samples", "demux_truseq"])
 def test_launcher_with_forked_workers_and_dill_pickling(tmp_path, name):
     run_launcher(tmp_path, name, 4, "oracle")
 
@@ -66,7 +66,7 @@ def test_sample_result_pickles_small():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", gu.golden_names())
+@pytest.mark.parametrize("name", gu.launcher_golden_names())
 def test_gpu_launcher_with_forked_workers_writes_the_reference_files(tmp_path, name):
     assert ref_shims.available(), ("no reference tree on this box: baseline/_ref/ScarMapper is made by "
                                    "__graft_entry__.build() in the build container and shipped by gpurun")
