@@ -171,6 +171,14 @@ int scar_verify_dev(scar_ctx *ctx, const scar_ragged *seq, const scar_record *re
                     uint64_t first_index, int64_t *n_collisions, void *stream);
 int scar_reset(scar_ctx *ctx);
 int scar_reset_dev(scar_ctx *ctx, void *stream);      /* asynchronous on `stream` */
+/* Exact-or-fail key identity for scar_process_host (off by default).  A scar-table entry is identified by a 128-bit
+ * tag of its key; with verification on, scar_process_host keeps the whole batch resident as ONE chunk and afterwards
+ * compares every scarred read's full key (sample, junctions, kind, segment bytes) with the first read of its entry
+ * (scar_verify_dev): a mismatch fails the call with SCAR_ERR_HASH_COLLISION instead of merging two keys silently.
+ * Needs ~ (raw bytes + 48) per read of device memory for the batch (scar_device_memory). */
+int scar_ctx_set_verify(scar_ctx *ctx, int32_t on);
+int scar_device_memory(int32_t device, int64_t *free_bytes, int64_t *total_bytes);
+
 /* Size the persistent grids of this context's kernels for n_sms SMs instead of all of them (0 = all): a multi-GPU
  * job leaves a few SMs to the table merge and the NCCL kernels that run beside the next batch. */
 int scar_ctx_set_sm_limit(scar_ctx *ctx, int32_t n_sms);

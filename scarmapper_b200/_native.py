@@ -100,6 +100,8 @@ PROTOTYPES = {
     "scar_table_clear_dev": (C.c_int, [_P, _P]),
     "scar_table_merge_parts_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
     "scar_reset_dev": (C.c_int, [_P, _P]),
+    "scar_ctx_set_verify": (C.c_int, [_P, C.c_int32]),
+    "scar_device_memory": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "scar_ctx_set_sm_limit": (C.c_int, [_P, C.c_int32]),
     "scar_launch_count": (C.c_int64, [_P]),
     "scar_accumulator_words": (C.c_int64, [_P]),

@@ -204,6 +204,9 @@ struct scar_ctx {
     unsigned long long *d_counters = nullptr, *d_phase_hist = nullptr; size_t acc_words = 0;
     int32_t *d_status = nullptr;
     HostBuf buf[NBUF]; int64_t chunk_reads = 1 << 20;
+    bool weak_keys = false;                 // test hook (scar_ctx_set_verify(ctx, 2)): key tags without the segment
+    bool verify = false;                    // scar_process_host: one resident chunk + exact key verification
+    int fused_ok = -1;                      // -1 unknown, 1: scar_run_dev takes the fused kernel, 0: K1 -> K3 -> K4
     // GPU FASTQ path
     uint8_t *d_text = nullptr; size_t text_cap = 0;
     uint32_t *d_tile_counts = nullptr; size_t tile_counts_cap = 0;
@@ -609,6 +612,24 @@ extern "C" int scar_ctx_set_sm_limit(scar_ctx *c, int32_t n_sms)
     return SCAR_OK;
 }
 
+extern "C" int scar_ctx_set_verify(scar_ctx *c, int32_t on)
+{
+    if (!c) return fail(SCAR_ERR_INVALID, "null context");
+    c->verify = on != 0;
+    c->weak_keys = on == 2;                 // test hook: tags that ignore the insertion / microhomology bytes collide
+    return SCAR_OK;
+}
+
+extern "C" int scar_device_memory(int32_t device, int64_t *free_bytes, int64_t *total_bytes)
+{
+    CU(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return SCAR_OK;
+}
+
 extern "C" int64_t scar_launch_count(const scar_ctx *c) { return c ? c->launches : 0; }
 
 extern "C" int scar_cells_per_read(const scar_ctx *c) { return c ? c->W : 0; }
@@ -700,6 +721,7 @@ static K4Params k4_params(scar_ctx *c)
     P.platform = c->platform; P.max_probe = (uint32_t)std::min<uint64_t>(c->capacity - 1, 1u << 16);
     int max_phase = 0;
     for (const auto &m : c->h_targets) max_phase = std::max(max_phase, (int)m.n_phase);
+    P.weak_keys = c->weak_keys ? 1 : 0;
     P.phase_bins = max_phase + 2;                 // bins: none, 0..max_phase-1, n/a
     P.phase_joint = P.phase_bins * P.phase_bins <= 128 ? 1 : 0;
     return P;
@@ -723,7 +745,7 @@ static K3Params fused_params(scar_ctx *c, const scar_ragged *seq, const uint16_t
     K3Params P = k3_params(c);
     if (seq) P.seq = *seq;
     P.samples = samples; P.records = records; P.n_reads = n; P.stride = n; P.platform = c->platform;
-    P.aggregate = aggregate; P.first_index = first_index;
+    P.aggregate = aggregate | (c->weak_keys ? 2 : 0); P.first_index = first_index;
     const K4Params A = k4_params(c);
     P.slots = A.slots; P.slot_mask = A.slot_mask; P.max_probe = A.max_probe; P.claimed = A.claimed; P.n_entries = A.n_entries;
     P.counters = A.counters; P.unassigned = A.unassigned; P.phase_hist = A.phase_hist; P.status = c->d_status;
@@ -731,11 +753,28 @@ static K3Params fused_params(scar_ctx *c, const scar_ragged *seq, const uint16_t
     return P;
 }
 
+// does scar_run_dev take the fused kernel for this context?  (eligible platform / read length, and a tile fits beside
+// the static blob in shared memory; independent of the layout of the reads)
+static bool fused_path(scar_ctx *c)
+{
+    if (c->fused_ok < 0) {
+        c->fused_ok = 0;
+        if (scar_fused_eligible(c->W, c->platform)) {
+            cudaSetDevice(c->device);
+            int per = 0, sm = 0;
+            if (scar_fused_plan(fused_params(c, nullptr, nullptr, 0, 0, nullptr, 1), c->smem_tables, c->max_read_len, &per, &sm) == cudaSuccess)
+                c->fused_ok = 1;
+            else cudaGetLastError();
+        }
+    }
+    return c->fused_ok == 1;
+}
+
 extern "C" int scar_fused_info(const scar_ctx *c, int32_t *eligible, int32_t *ctas_per_sm, int32_t *smem_bytes)
 {
     if (!c) return fail(SCAR_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->device));
-    const bool ok = scar_fused_eligible(c->W, c->platform);
+    const bool ok = fused_path(const_cast<scar_ctx *>(c));
     if (eligible) *eligible = ok ? 1 : 0;
     int per = 0, sm = 0;
     if (ok) CU(scar_fused_plan(fused_params(const_cast<scar_ctx *>(c), nullptr, nullptr, 0, 0, nullptr, 1), c->smem_tables,
@@ -766,15 +805,9 @@ extern "C" int scar_run_dev(scar_ctx *c, const scar_ragged *seq, const scar_ragg
     int rc;
     if ((rc = scar_demux_dev(c, seq, f0, f1, n, samples, stream))) return rc;
     // one pass over the raw bytes (pack, classify, aggregate) when the fused kernel takes the problem
-    if (c && seq && scar_fused_eligible(c->W, c->platform)) {
-        // (a static blob too large to leave room for a tile beside it: K1 -> K3 -> K4 below)
-        CU(cudaSetDevice(c->device));
-        int per = 0, sm = 0;
-        if (scar_fused_plan(fused_params(c, seq, samples, n, first_index, records, 1), c->smem_tables, c->max_read_len,
-                            &per, &sm) == cudaSuccess)
-            return scar_classify_raw_dev(c, seq, samples, n, first_index, records, 1, stream);
-        cudaGetLastError();
-    }
+    // (ineligible, or a static blob too large to leave room for a tile beside it: K1 -> K3 -> K4 below)
+    if (c && seq && fused_path(c)) return scar_classify_raw_dev(c, seq, samples, n, first_index, records, 1, stream);
+    if (!cells || !lens) return fail(SCAR_ERR_INVALID, "the three-kernel path needs the cells / lens scratch buffers");
     if ((rc = scar_pack_dev(c, seq, n, cells, lens, stream))) return rc;
     if ((rc = scar_classify_dev(c, cells, lens, samples, n, records, stream))) return rc;
     return scar_aggregate_dev(c, seq, records, n, first_index, stream);
@@ -799,7 +832,7 @@ extern "C" int scar_verify_dev(scar_ctx *c, const scar_ragged *seq, const scar_r
     CU(cudaMemsetAsync(c->d_collisions, 0, sizeof(unsigned long long), s));
     K4VerifyParams P; memset(&P, 0, sizeof(P));
     P.seq = *seq; P.records = records; P.n_reads = n; P.first_index = first_index; P.slots = c->d_slots;
-    P.slot_mask = c->capacity - 1; P.n_collisions = c->d_collisions; P.platform = c->platform;
+    P.slot_mask = c->capacity - 1; P.n_collisions = c->d_collisions; P.platform = c->platform; P.weak_keys = c->weak_keys ? 1 : 0;
     P.max_probe = (uint32_t)std::min<uint64_t>(c->capacity - 1, 1u << 16);
     CU(scar_launch_verify(P, c->sm_count, s));
     unsigned long long v = 0;
@@ -1048,8 +1081,10 @@ static int ensure_hostbuf(scar_ctx *c, HostBuf &b, int64_t reads)
     CU(cudaMalloc((void **)&b.seq_len, n * sizeof(int32_t)));
     CU(cudaMalloc((void **)&b.f0_len, n * sizeof(int32_t)));
     CU(cudaMalloc((void **)&b.f1_len, n * sizeof(int32_t)));
-    CU(cudaMalloc((void **)&b.cells, n * c->W * sizeof(uint64_t)));
-    CU(cudaMalloc((void **)&b.lens, n * sizeof(uint32_t)));
+    if (!fused_path(c)) {                                  // the packed batch exists only on the K1 -> K3 -> K4 path
+        CU(cudaMalloc((void **)&b.cells, n * c->W * sizeof(uint64_t)));
+        CU(cudaMalloc((void **)&b.lens, n * sizeof(uint32_t)));
+    }
     CU(cudaMalloc((void **)&b.samples, n * sizeof(uint16_t)));
     CU(cudaMalloc((void **)&b.records, n * sizeof(scar_record)));
     b.reads_cap = reads;
@@ -1062,7 +1097,9 @@ extern "C" int scar_process_host(scar_ctx *c, const scar_ragged *seq, const scar
     if (!c || !seq || n < 0) return fail(SCAR_ERR_INVALID, "bad argument");
     if (c->platform == SCAR_PLATFORM_ILLUMINA && (!f0 || !f1)) return fail(SCAR_ERR_INVALID, "Illumina needs the two header index fields");
     CU(cudaSetDevice(c->device));
-    const int64_t chunk = std::min<int64_t>(c->chunk_reads, std::max<int64_t>(n, 1));
+    // verify mode: the whole batch is ONE resident chunk, so that every key's first read is on the device when
+    // scar_verify_dev compares each scarred read's full key with it (exact-or-fail identity instead of 128 hash bits)
+    const int64_t chunk = c->verify ? std::max<int64_t>(n, 1) : std::min<int64_t>(c->chunk_reads, std::max<int64_t>(n, 1));
     int k = 0;
     int64_t h2d = 0;
     for (int64_t a = 0; a < n; a += chunk, ++k) {
@@ -1098,6 +1135,10 @@ extern "C" int scar_process_host(scar_ctx *c, const scar_ragged *seq, const scar
                                B.cells, B.lens, B.samples, B.records, B.stream))) return rc;
         if (records)
             CU(cudaMemcpyAsync(records + a, B.records, (size_t)(b - a) * sizeof(scar_record), cudaMemcpyDeviceToHost, B.stream));
+        if (c->verify) {
+            int64_t ncol = 0;
+            if ((rc = scar_verify_dev(c, &dseq, B.records, b - a, first_index + (uint64_t)a, &ncol, B.stream))) return rc;
+        }
         CU(cudaEventRecord(B.done, B.stream));
     }
     for (int i = 0; i < NBUF; ++i) if (c->buf[i].stream) CU(cudaStreamSynchronize(c->buf[i].stream));

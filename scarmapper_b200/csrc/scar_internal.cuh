@@ -157,7 +157,7 @@ struct K3Params {
     int32_t platform;
     scar_ragged seq;              // raw reads (device pointers)
     uint32_t raw_cap;             // bytes of the tile's raw staging buffer (the packed cells reuse it)
-    int32_t aggregate;
+    int32_t aggregate;            // bit 0: aggregate; bit 1 (test hook): key tags without the segment
     uint64_t first_index;         // global index of read 0 (first-seen order across batches and ranks)
     ScarTableSlot *slots; uint64_t slot_mask; uint32_t max_probe; int32_t hist_smem;
     uint32_t *claimed;            // claimed-slot list of the table
@@ -183,6 +183,7 @@ struct K4Params {
     int32_t platform;
     int32_t use_smem;            // counters + phase histograms staged in shared memory
     uint32_t max_probe;
+    int32_t weak_keys;           // test hook: key tags without the segment (see key_hashes)
     int32_t phase_joint;         // 1: joint [PB][PB] phase histogram in shared memory, 0: two [PB] marginals
     int32_t phase_bins;          // PB = max phases + 2 (none, phase 0 .. max-1, n/a)
 };
@@ -190,7 +191,7 @@ struct K4Params {
 struct K4VerifyParams {
     scar_ragged seq; const scar_record *records; int64_t n_reads; uint64_t first_index;
     const ScarTableSlot *slots; uint64_t slot_mask; unsigned long long *n_collisions; int32_t platform;
-    uint32_t max_probe;
+    uint32_t max_probe; int32_t weak_keys;
 };
 
 cudaError_t scar_launch_window(const K3Params &P, bool smem_tables, int sm_count, cudaStream_t stream, int *launches);

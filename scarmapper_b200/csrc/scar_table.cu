@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256, SCAR_K4_CTAS) scar_aggregate_kernel(const
             const uint8_t *raw; int rawlen;
             get_item(P.seq, r, raw, rawlen);
             uint64_t h1, h2;
-            key_hashes(rec, raw, rawlen, P.platform, h1, h2);
+            key_hashes(rec, raw, rawlen, P.platform, h1, h2, P.weak_keys != 0);
             claimed = table_insert(T, h1, h2, 1u, P.first_index + (uint64_t)r, rec.sample, slot);
         }
         table_note_claims(T, claimed, slot);          // (the loop's trip count is uniform: the warp is converged)
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) scar_verify_kernel(const K4VerifyParams P
         const uint8_t *raw; int rawlen;
         get_item(P.seq, r, raw, rawlen);
         uint64_t h1, h2;
-        key_hashes(rec, raw, rawlen, P.platform, h1, h2);
+        key_hashes(rec, raw, rawlen, P.platform, h1, h2, P.weak_keys != 0);
         uint64_t slot = h1 & P.slot_mask;
         bool found = false;
         for (uint32_t probe = 0; probe <= P.max_probe; ++probe) {

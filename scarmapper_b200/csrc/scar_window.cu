@@ -1101,7 +1101,7 @@ scar_window_kernel(const K3Params P)
                     uint64_t h1, h2;
                     key_init(ks.hdr, h1, h2);
                     bool acgt = true;
-                    for (int q = ks.lo; q < ks.hi; q += 32) {
+                    for (int q = ks.lo; q < ((P.aggregate & 2) ? ks.lo : ks.hi); q += 32) {
                         const int n = min(32, ks.hi - q);
                         const Word32 w = read32(rc0, q);
                         const uint32_t vm = n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);

@@ -212,6 +212,19 @@ def batched_consensus_demultiplex(self, module, device=0):
         table_capacity=1 << max(16, int(math.ceil(math.log2(max(2 * batch.n, 2))))))
     eng = _make_engine(prob, device)
     try:
+        # Exact-or-fail key identity: when the run fits the device (text + ~60 bytes of views / records per read) it is
+        # processed as one resident chunk and every scarred read's full key is compared with the first read of its
+        # table entry; a mismatch raises instead of merging two scar patterns under one 128-bit tag.
+        if hasattr(eng, "set_verify"):
+            free, _total = eng.device_memory()
+            need = int(batch.text.size) + 64 * batch.n + (256 << 20)
+            if need < 0.8 * free:
+                eng.set_verify(True)
+                STAGE_SECONDS["keys_verified_exactly"] = 1.0
+            else:
+                log.warning("Run too large for one resident chunk ({:.1f} GB needed, {:.1f} GB free): scar patterns are "
+                            "identified by their 128-bit key tags without the exact comparison".format(need / 1e9, free / 1e9))
+                STAGE_SECONDS["keys_verified_exactly"] = 0.0
         records = eng.process_host(batch.seq, batch.f0, batch.f1)
         counters, unassigned = eng.counters()
         phase_hist = eng.phase_hist()

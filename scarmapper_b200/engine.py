@@ -196,6 +196,16 @@ class ScarEngine:
         """Clear table and accumulators on the current torch stream (no host synchronisation)."""
         N.check(self._L.scar_reset_dev(self._ctx, self._stream()))
 
+    def set_verify(self, on: bool = True):
+        """process_host keeps the batch resident as one chunk and verifies every scarred read's full key against the
+        first read of its table entry (ScarError SCAR_ERR_HASH_COLLISION on a mismatch)."""
+        N.check(self._L.scar_ctx_set_verify(self._ctx, 1 if on else 0))
+
+    def device_memory(self):
+        f, t = C.c_int64(), C.c_int64()
+        N.check(self._L.scar_device_memory(self.device, C.byref(f), C.byref(t)))
+        return f.value, t.value
+
     def set_sm_limit(self, n_sms: int = 0):
         """Size this engine's persistent grids for n_sms SMs (0 = all): leaves the rest to a merge running beside."""
         N.check(self._L.scar_ctx_set_sm_limit(self._ctx, int(n_sms)))

@@ -899,3 +899,38 @@ def test_fused_kernel_truseq_golden_and_many_samples(monkeypatch):
         by_sample.setdefault(int(e["sample"]), []).append((int(e["count"]), int(e["first_idx"])))
     gu.compare_with_golden(case, golden, rec, table_fn=lambda s: by_sample.get(s, []))
     eng.close()
+
+
+def test_process_host_verify_mode_is_exact_or_fail():
+    """scar_ctx_set_verify: the batch is one resident chunk and every scarred read's full key is compared with the
+    first read of its table entry.  Same results as the chunked pipeline; and when the tags are made to collide
+    (test hook: tags that leave the insertion / microhomology bytes out) the call FAILS instead of merging keys."""
+    from scarmapper_b200._native import ScarError
+    cfg = synth.make_config("C3", n_reads=40000, seed=404)
+    batch = cfg.generate(0, 40000)
+    pin = synth_problem(cfg)
+    from scarmapper_b200.engine import HostRagged
+    seq = HostRagged.from_matrix(batch["seq"], lengths=batch["len"])
+    eng = engine_for(pin, cfg.read_len)
+    rec0 = eng.process_host(seq, batch["f0"], batch["f1"]).copy()
+    tab0 = eng.table().copy()
+    eng.close()
+    for fused in (True, False):
+        import os
+        if not fused:
+            os.environ["SCAR_NO_FUSE"] = "1"
+        try:
+            eng = engine_for(pin, cfg.read_len)
+            eng.set_verify(True)
+            rec1 = eng.process_host(seq, batch["f0"], batch["f1"])
+            assert_records_equal(rec1, rec0)
+            assert eng.table().tobytes() == tab0.tobytes()
+            eng.close()
+            eng = engine_for(pin, cfg.read_len)
+            eng._L.scar_ctx_set_verify(eng._ctx, 2)            # verification on, tags weakened
+            with pytest.raises(ScarError) as err:
+                eng.process_host(seq, batch["f0"], batch["f1"])
+            assert err.value.code == -6                          # SCAR_ERR_HASH_COLLISION
+            eng.close()
+        finally:
+            os.environ.pop("SCAR_NO_FUSE", None)
