@@ -725,7 +725,7 @@ scar_window_kernel(const K3Params P)
         AC.pb = P.phase_bins; AC.joint = P.phase_joint;
         per_sample = acc_words_per_sample(AC.pb, AC.joint);
         s_hist = reinterpret_cast<unsigned int *>(tile_buf + (uint32_t)n_groups * (cells_bytes + (K3_TILE / 32) * FUSED_SLOTS * P.raw_cap));
-        if (P.aggregate && P.hist_smem)
+        if ((P.aggregate & 1) && P.hist_smem)
             for (int i = threadIdx.x; i < P.n_samples * per_sample; i += blockDim.x) s_hist[i] = 0;
         __syncwarp();
         // prologue of the warp's pipeline: the first chunk(s) of its first tile
@@ -755,7 +755,7 @@ scar_window_kernel(const K3Params P)
         if (FUSED) {
             // 16-bit packed counters shared by the CTA's groups: every group empties them (atomic exchange, no barrier)
             // before the reads taken by all groups since anybody's last flush can reach 2^16
-            if (P.aggregate && P.hist_smem && ++epoch > 65535 / (K3_TILE * n_groups) - 2) {
+            if ((P.aggregate & 1) && P.hist_smem && ++epoch > 65535 / (K3_TILE * n_groups) - 2) {
                 acc_flush_exch(AC, s_hist, per_sample, tx, K3_TILE);
                 epoch = 1;
             }
@@ -1089,7 +1089,7 @@ scar_window_kernel(const K3Params P)
         // ---- fused: stage 4 (INDEL_Processing.py:186-196 and the summary / phasing bookkeeping), what K4 does from
         // the records in a second pass.  The key's segment is hashed from the packed cells in shared memory; only a
         // segment with a non-ACGT byte goes back to the raw read.
-        if (FUSED && P.aggregate) {
+        if (FUSED && (P.aggregate & 1)) {
             bool claimed = false;
             uint32_t claimed_slot = 0;
             if (in_range) {
@@ -1123,7 +1123,7 @@ scar_window_kernel(const K3Params P)
             table_note_claims(TB, claimed, claimed_slot);      // one atomic per warp appends the new slots to the list
         }
     }
-    if (FUSED && P.aggregate) {
+    if (FUSED && (P.aggregate & 1)) {
         group_sync();
         if (P.hist_smem) acc_flush_exch(AC, s_hist, per_sample, tx, K3_TILE);      // (a slower group flushes what it adds later)
         if (tx == 0 && s_unassigned) atomicAdd(P.unassigned, (unsigned long long)s_unassigned);
@@ -1244,7 +1244,7 @@ static cudaError_t plan_fused(K3Params &P, bool smem_tables, int max_read_len, K
     // accumulators: joint phase histogram when it is small, else two marginals; global atomics when neither fits
     P.hist_smem = 0;
     size_t hist = 0;
-    if (P.aggregate) {
+    if ((P.aggregate & 1)) {
         for (int joint = P.phase_bins * P.phase_bins <= 32 ? 1 : 0; joint >= 0 && !P.hist_smem; --joint) {
             const size_t h = (size_t)P.n_samples * acc_words_per_sample(P.phase_bins, joint) * sizeof(unsigned int);
             if (h <= 48 * 1024 && fixed + per_group + h <= budget) { P.hist_smem = 1; P.phase_joint = joint; hist = h; }
