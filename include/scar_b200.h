@@ -10,6 +10,7 @@
  *   scarmapper/INDEL_Processing.py:1126-1201 index_matching                 -> scar_demux_dev
  *   Valkyries/Sequence_Magic.py:123-136     match_maker(query, unknown)     -> scar_match_maker_batch
  *   scarmapper/INDEL_Processing.py:550-700  homeology_search / templated_insertion_search -> scar_homeology_batch
+ *   scarmapper/INDEL_Processing.py:233-478  frequency_output (per-pattern body, rows) -> scar_frequency_rows_host
  *   scarmapper/INDEL_Processing.py:702-757  raw_data_output (body)         -> scar_raw_rows_host
  *   scarmapper/INDEL_Processing.py:57-80,759-795 window_mapping/cutsite_search -> scar_ctx_create (tables), scar_cutsite_search
  *   scarmapper/AlignmentProcessing.pyx:18-149 alignment_processing          -> scar_alignment_batch
@@ -284,6 +285,35 @@ int scar_homeology_batch(int32_t device, const scar_ragged *consensus, const sca
 int scar_alignment_batch(int32_t device, const scar_ragged *genomic, const scar_ragged *consensus,
                          const int32_t *cutposition, const int32_t *gap_con_len, const int32_t *gap_genome_len,
                          int64_t n, int32_t max_spans, int32_t *counts, int32_t *spans);
+
+/* The per-pattern body of ScarSearch.frequency_output (scarmapper/INDEL_Processing.py:233-478) for ONE sample, host side:
+ * scar-type classification (HR / SNV / TMEJ / NHEJ / Non-MH Deletion / Insertion / Other), junction-type totals, SNV
+ * tallies, PatternThreshold filter, ordering (count, then first-seen rank, both descending) and the text rows of the
+ * *_ScarMapper_Frequency.txt file (26 tab-separated columns; the Frequency column is Python's str(count / total)).
+ * Inputs: what the GPU pass leaves per sample (scar_table_read order = first-seen) plus scar_homeology_batch's results. */
+typedef struct scar_frequency_in {
+    int64_t n;                     /* scar patterns of the sample, first-seen order */
+    const uint32_t *counts;        /* [n] */
+    const scar_record *first;      /* [n] record of the first read of each pattern */
+    const uint8_t *reads;          /* stored sequences of those reads (scar_stored_gather_host), CSR */
+    const int64_t *read_off;       /* [n + 1] */
+    const int32_t *pattern;        /* [n][16] scar_homeology_batch output */
+    const uint8_t *region; int32_t region_len;     /* ScarSearch.target_region */
+    int32_t cutsite, reverse_comp; /* ScarSearch.cutsite; target_dict[..][5] == "YES" */
+    int64_t passing, no_cut;       /* summary_data[1], summary_data[6][1] */
+    double pattern_threshold;      /* args.PatternThreshold */
+} scar_frequency_in;
+/* junction_type_data[6] (TMEJ, NHEJ, Insertion, Other, Non-MH Deletion, SNV read totals); label_sums[7] /
+ * label_order[7]: sum of count / total per scar type (HR, SNV, TMEJ, NHEJ, Non-MH Deletion, Insertion, Other) and the
+ * types in order of first appearance in the sorted list (-1 padded); snv[4][10][4]: SNV tallies (left, left x count,
+ * right, right x count) per k-mer position per nucleotide G, A, T, C; plot[n_plot][6]: per written row (type, pattern
+ * frequency count / (passing - no_cut), left deletion, right deletion, microhomology size, insertion size);
+ * totals[2]: number of patterns, number of scarred reads.  The rows are kept for the calling thread until
+ * scar_frequency_rows_fetch copies them out (*rows_bytes says how many bytes). */
+int scar_frequency_rows_host(const scar_frequency_in *in, int64_t *rows_bytes, int64_t *junction_type_data, double *label_sums,
+                             int32_t *label_order, int64_t *snv, double *plot, int64_t plot_capacity, int64_t *n_plot,
+                             int64_t *totals);
+int scar_frequency_rows_fetch(uint8_t *rows, int64_t capacity);
 
 /* Sequence_Magic.match_maker over a batch on the device (host buffers): out[i] = lev(q_i,u_i) - (|u_i|-|q_i|). */
 int scar_match_maker_batch(int32_t device, const scar_ragged *query, const scar_ragged *unknown,

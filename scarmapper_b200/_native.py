@@ -66,6 +66,13 @@ class Config(C.Structure):
     ]
 
 
+class FrequencyIn(C.Structure):
+    """struct scar_frequency_in"""
+    _fields_ = [("n", C.c_int64), ("counts", C.c_void_p), ("first", C.c_void_p), ("reads", C.c_void_p), ("read_off", C.c_void_p),
+                ("pattern", C.c_void_p), ("region", C.c_void_p), ("region_len", C.c_int32), ("cutsite", C.c_int32),
+                ("reverse_comp", C.c_int32), ("passing", C.c_int64), ("no_cut", C.c_int64), ("pattern_threshold", C.c_double)]
+
+
 # every symbol include/scar_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 _RP = C.POINTER(Ragged)
@@ -118,6 +125,9 @@ PROTOTYPES = {
     "scar_demux_fastq_rows_host": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int64, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "scar_stored_gather_host": (C.c_int, [_RP, _P, C.c_int64, C.c_int32, _P, _P, C.c_int64, _P]),
     "scar_homeology_batch": (C.c_int, [C.c_int32, _RP, _RP, _P, _P, _P, _P, _P, _RP, _RP, C.c_int32, C.c_int64, _P]),
+    "scar_frequency_rows_host": (C.c_int, [C.POINTER(FrequencyIn), C.POINTER(C.c_int64), _P, _P, _P, _P, _P, C.c_int64,
+                                          C.POINTER(C.c_int64), _P]),
+    "scar_frequency_rows_fetch": (C.c_int, [_P, C.c_int64]),
     "scar_alignment_batch": (C.c_int, [C.c_int32, _RP, _RP, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
     "scar_match_maker_batch": (C.c_int, [C.c_int32, _RP, _RP, C.c_int64, _P]),
 }

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscar_b200.so")
 SOURCES = ["scar_api.cu", "scar_pack.cu", "scar_demux.cu", "scar_window.cu", "scar_table.cu", "scar_fastq.cu", "scar_fastq_dev.cu",
-           "scar_homeology.cu", "scar_rawdata.cu", "scar_alignment.cu"]
+           "scar_homeology.cu", "scar_rawdata.cu", "scar_alignment.cu", "scar_frequency.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-cudart", "static"]
 

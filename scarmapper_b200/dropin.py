@@ -41,6 +41,7 @@ _ENGINE_FACTORY = [None]      # tests substitute a CPU stand-in here; None -> Sc
 _HOMEOLOGY_BATCH = [None]     # likewise for the per-pattern searches; None -> engine.homeology_batch (GPU)
 _RAW_DATA_HOOK = [None]       # tests: called as hook(index_name, rows, records, reads, result) per Raw_Data file
 PATTERN_SEARCH_STATS = {"served": 0, "missed": 0}   # calls answered from the batch / handed to the reference's method
+NATIVE_FREQUENCY = [True]     # False: the reference's own frequency_output runs over results_freq_dict (cross-check)
 STAGE_SECONDS = {}           # wall time of the stages of the last batched_consensus_demultiplex (parent process)
 READ_LIMIT_DEBUG = 1000002    # --Verbose DEBUG: the reference's loop stops after 1 000 002 reads (:906-914, see below)
 
@@ -401,18 +402,127 @@ def batched_data_processing(self):
     self.target_region = res.target_region
     self.cutsite = res.cutsite
     self.window_mapping()
-    results_freq_dict = collections.defaultdict(list)
-    for count, sub_list in res.table():
-        key = "{}|{}|{}|{}|{}".format(sub_list[0], sub_list[1], sub_list[2], sub_list[3], sub_list[9])
-        results_freq_dict[key] = [count, sub_list]
     self.log.info("Finished Processing {}".format(self.index_name))
-    serve_pattern_searches(self, results_freq_dict, res.pattern_out)
-    self.frequency_output(self.index_name, results_freq_dict, junction_type_data)
+    if NATIVE_FREQUENCY[0]:
+        # the per-pattern loop of frequency_output as one native call (no Python object per pattern)
+        native_frequency_output(self, self.index_name, res, junction_type_data)
+    else:
+        # the reference's own frequency_output over results_freq_dict, its two searches answered from the batch
+        results_freq_dict = collections.defaultdict(list)
+        for count, sub_list in res.table():
+            key = "{}|{}|{}|{}|{}".format(sub_list[0], sub_list[1], sub_list[2], sub_list[3], sub_list[9])
+            results_freq_dict[key] = [count, sub_list]
+        serve_pattern_searches(self, results_freq_dict, res.pattern_out)
+        self.frequency_output(self.index_name, results_freq_dict, junction_type_data)
     if self.args.OutputRawData and not res.raw_written:
         self.raw_data_output(self.index_name, res.read_results or [])
     # the returned ScarSearch objects are pickled back to the parent for data_output, which reads summary_data only
     self.sequence_list = None
     return self.summary_data
+
+
+FREQUENCY_COLUMNS = (
+    "# Total\tFrequency\tScar Type\tLeft Deletions\tRight Deletions\tDeletion Size\tMicrohomology\t"
+    "Microhomology Size\tInsertion\tInsertion Size\tLeft Template\tRight Template\tConsensus Left Junction\t"
+    "Consensus Right Junction\tTarget Left Junction\tTarget Right Junction\tLeft Homeology\t"
+    "Left Homeology Position\tLeft Query Seq\tLeft Homeologous Seq\tRight Homeology\t"
+    "Right Homeology Position\tRight Query Seq\tRight Homeologous Seq\tConsensus\tTarget Region\n")
+
+
+def native_frequency_output(self, index_name, res, junction_type_data):
+    """ScarSearch.frequency_output (scarmapper/INDEL_Processing.py:233-548) with its per-pattern Python loop replaced by
+    ONE native call (scar_frequency_rows_host: classification, junction-type totals, SNV tallies, threshold, ordering,
+    the rows of the file).  What stays here is the framing the reference does once per sample: the page header it
+    generates itself, the SNV file (:480-530) and the bookkeeping handed to its own plot routine (:396-470,531-548).
+    Files identical to the reference's on every golden case (tests/test_dropin_*.py run both this and the
+    unchanged frequency_output)."""
+    from . import engine as _engine
+    module = __import__(type(self).__module__, fromlist=["ScarMapperPlot"])
+    self.log.info("Working on Frequency Files for {}".format(index_name))
+    target_name = self.index_dict[index_name][7]
+    rc = self.target_dict[target_name][5] == "YES"
+    out = _engine.frequency_rows(res.counts, res.first_records, res.first_bytes, res.first_off, res.pattern_out,
+                                 self.target_region, self.cutsite, rc, self.summary_data[1], self.summary_data[6][1],
+                                 self.args.PatternThreshold)
+    for i, v in enumerate(out["junction_type_data"]):
+        junction_type_data[i] += v
+    path = "{}{}_{}_ScarMapper_Frequency.txt".format(self.args.WorkingFolder, self.args.Job_Name, index_name)
+    with open(path, "wb") as f:
+        f.write("{}{}".format(self.common_page_header(index_name), FREQUENCY_COLUMNS).encode())
+        f.write(out["rows"])
+    scar_count, total_scars = out["scar_count"], out["total_scars"]
+    lft_kmer, rt_kmer = self.left_target_windows[0], self.right_target_windows[0]
+    kmer_size = len(lft_kmer)
+    if rc and scar_count:            # (:315-316: swapped and reverse-complemented inside the loop, i.e. once any pattern exists)
+        lft_kmer, rt_kmer = _rcomp(self.right_target_windows[0]), _rcomp(self.left_target_windows[0])
+
+    # SNV file (:480-530)
+    if junction_type_data[5] > 0:
+        snv = out["snv"]             # [left, left x count, right, right x count][position][G, A, T, C]
+        lft_kmer_string, rt_kmer_string = "\t".join(lft_kmer), "\t".join(rt_kmer)
+        lft_position_label = "".join("\t{}".format(-1 * (kmer_size - i)) for i in range(kmer_size))
+        rt_position_label = "".join("\t{}".format(i + 1) for i in range(kmer_size))
+        snv_outstring = "{}\n\n# Values normalized to number of SNV scars\n\t{}\t{}\n# NT{}{}" \
+            .format(self.common_page_header(index_name), lft_kmer_string, rt_kmer_string, lft_position_label, rt_position_label)
+        snv_all_outstring = "\n\n\n# Values normalized to total number of scars\n\t{}\t{}\n# NT{}{}" \
+            .format(lft_kmer_string, rt_kmer_string, lft_position_label, rt_position_label)
+        for q, nt in enumerate(["G", "A", "T", "C"]):
+            snv_outstring += "\n# {}".format(nt)
+            snv_all_outstring += "\n# {}".format(nt)
+            data = [int(snv[0, i, q]) for i in range(kmer_size)] + [int(snv[2, i, q]) for i in range(kmer_size)]
+            data_all = [int(snv[1, i, q]) for i in range(kmer_size)] + [int(snv[3, i, q]) for i in range(kmer_size)]
+            for v in data:
+                snv_outstring += "\t{}".format(round(v / scar_count, 4))
+            for v in data_all:
+                snv_all_outstring += "\t{}".format(round(v / total_scars, 4))
+        with open("{}{}_{}_SNV_Frequency.txt".format(self.args.WorkingFolder, self.args.Job_Name, index_name), "w") as f:
+            f.write(snv_outstring + snv_all_outstring)
+
+    self.summary_data[8] = junction_type_data
+    scar_fraction = (junction_type_data[5] + self.summary_data[1] - self.summary_data[6][1] - self.summary_data[6][0]) / \
+        self.summary_data[1]
+    if self.summary_data[1] >= self.lower_limit_count and scar_fraction >= 0.08:
+        # the plot's inputs, built from the rows that were written exactly as :414-467 builds them
+        plot_data_dict = collections.defaultdict(list)
+        marker_list = []
+        label_dict = collections.defaultdict(float)
+        for t in out["label_order"]:
+            label_dict[_engine.SCAR_TYPES[t]] = float(out["label_sums"][t])
+        for t, freq, lft_del, rt_del, mh_size, ins_size in out["plot"].tolist():
+            scar_type = _engine.SCAR_TYPES[int(t)]
+            lft_del, rt_del, mh_size, ins_size = int(lft_del), int(rt_del), int(mh_size), int(ins_size)
+            if freq < 0.0025:
+                freq = 0.0025
+            y_value = freq * 0.5
+            lft_ins_width = rt_ins_width = freq
+            marker_list.extend([lft_del + (mh_size * 0.5), rt_del + (mh_size * 0.5), ins_size])
+            lft_del_plot_value = (lft_del + (mh_size * 0.5)) * -1
+            rt_del_plot_value = (rt_del + (mh_size * 0.5))
+            lft_ins_plot_value = (ins_size * 0.5) * -1
+            rt_ins_plot_value = (ins_size * 0.5)
+            if lft_del != 0:
+                lft_ins_width = freq * 0.5
+            if rt_del != 0:
+                rt_ins_width = freq * 0.5
+            if scar_type not in plot_data_dict:
+                plot_data_dict[scar_type] = [[freq], [lft_del_plot_value], [rt_del_plot_value], [lft_ins_plot_value],
+                                             [rt_ins_plot_value], [lft_ins_width], [rt_ins_width], [y_value]]
+            else:
+                count = len(plot_data_dict[scar_type][0])
+                previous_freq = plot_data_dict[scar_type][0][count - 1]
+                previous_y = plot_data_dict[scar_type][7][count - 1]
+                plot_data_dict[scar_type][0].append(freq)
+                plot_data_dict[scar_type][1].append(lft_del_plot_value)
+                plot_data_dict[scar_type][2].append(rt_del_plot_value)
+                plot_data_dict[scar_type][3].append(lft_ins_plot_value)
+                plot_data_dict[scar_type][4].append(rt_ins_plot_value)
+                plot_data_dict[scar_type][5].append(lft_ins_width)
+                plot_data_dict[scar_type][6].append(rt_ins_width)
+                plot_data_dict[scar_type][7].append(previous_y + 0.002 + (0.5 * previous_freq) + y_value)
+        sample_name = "{}.{}".format(self.index_dict[index_name][5], self.index_dict[index_name][6])
+        plot_data_dict['Marker'] = [(max(marker_list)) * -1, max(marker_list)]
+        module.ScarMapperPlot.scarmapperplot(self.args, datafile=None, sample_name=sample_name,
+                                             plot_data_dict=plot_data_dict, label_dict=label_dict)
 
 
 def serve_pattern_searches(self, results_freq_dict, pattern_out):

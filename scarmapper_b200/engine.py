@@ -473,6 +473,42 @@ def stored_gather(reads, rows, platform, flip=None):
     return out[:int(off[-1])], off
 
 
+SCAR_TYPES = ("HR", "SNV", "TMEJ", "NHEJ", "Non-MH Deletion", "Insertion", "Other")
+
+
+def frequency_rows(counts, first_records, first_bytes, first_off, pattern_out, region: str, cutsite: int, reverse_comp: bool,
+                   passing: int, no_cut: int, pattern_threshold: float) -> dict:
+    """The per-pattern body of ScarSearch.frequency_output for one sample (scar_frequency_rows_host): the rows of the
+    Frequency file (bytes), junction_type_data, label sums / order, SNV tallies, plot tuples, totals."""
+    n = int(len(counts))
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    first = np.ascontiguousarray(first_records)
+    assert first.dtype == N.RECORD_DTYPE and first.shape[0] == n
+    rb = np.ascontiguousarray(first_bytes, dtype=np.uint8)
+    if rb.size == 0:
+        rb = np.zeros(1, np.uint8)
+    ro = np.ascontiguousarray(first_off, dtype=np.int64)
+    pat = np.ascontiguousarray(pattern_out if pattern_out is not None and n else np.zeros((max(n, 1), 16)), dtype=np.int32)
+    reg = np.frombuffer(region.encode("latin-1"), dtype=np.uint8)
+    fin = N.FrequencyIn(n, counts.ctypes.data, first.ctypes.data, rb.ctypes.data, ro.ctypes.data, pat.ctypes.data,
+                        reg.ctypes.data, len(region), int(cutsite), 1 if reverse_comp else 0, int(passing), int(no_cut),
+                        float(pattern_threshold))
+    jtd = np.zeros(6, np.int64)
+    label_sums, label_order = np.zeros(7, np.float64), np.zeros(7, np.int32)
+    snv = np.zeros((4, 10, 4), np.int64)
+    plot = np.zeros((max(n, 1), 6), np.float64)
+    n_plot, nbytes = C.c_int64(0), C.c_int64(0)
+    totals = np.zeros(2, np.int64)
+    N.check(N.lib().scar_frequency_rows_host(C.byref(fin), C.byref(nbytes), jtd.ctypes.data, label_sums.ctypes.data,
+                                             label_order.ctypes.data, snv.ctypes.data, plot.ctypes.data, plot.shape[0],
+                                             C.byref(n_plot), totals.ctypes.data))
+    rows = np.empty(max(nbytes.value, 1), dtype=np.uint8)
+    N.check(N.lib().scar_frequency_rows_fetch(rows.ctypes.data, rows.size))
+    return {"rows": rows[:nbytes.value].tobytes(), "junction_type_data": [int(v) for v in jtd], "label_sums": label_sums,
+            "label_order": [int(t) for t in label_order if t >= 0], "snv": snv, "plot": plot[:n_plot.value],
+            "scar_count": int(totals[0]), "total_scars": int(totals[1])}
+
+
 def homeology_batch(consensus, insertions, clj, crj, tlj, trj, target_idx, targets, regions, device: int = 0) -> np.ndarray:
     """ScarSearch.homeology_search + templated_insertion_search (scarmapper/INDEL_Processing.py:550-700) for a
     batch of scar patterns on the GPU: [n, 16] int32 (struct ScarHomeology, include/scar_b200.h)."""

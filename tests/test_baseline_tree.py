@@ -24,7 +24,7 @@ def test_baseline_copy_is_byte_identical_and_untracked():
                 assert open(os.path.join(tree, pkg, fn), "rb").read() == open(os.path.join(ORIGINAL, pkg, fn), "rb").read(), fn
                 n += 1
     assert n >= 10
-    tracked = subprocess.run(["git", "ls-files", "baseline"], cwd=ROOT, stdout=subprocess.PIPE, text=True).stdout.strip()
+    tracked = subprocess.run(["git", "ls-files", "baseline/_ref"], cwd=ROOT, stdout=subprocess.PIPE, text=True).stdout.strip()
     assert tracked == "", "baseline/_ref must stay out of the repository"
     ignored = subprocess.run(["git", "check-ignore", "-q", "baseline/_ref/ScarMapper/scarmapper/INDEL_Processing.py"], cwd=ROOT)
     assert ignored.returncode == 0

@@ -23,8 +23,11 @@ pytestmark = pytest.mark.skipif(not ref_shims.available(), reason="reference tre
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
 
 
+@pytest.mark.parametrize("native_frequency", [True, False], ids=["native_frequency", "reference_frequency"])
 @pytest.mark.parametrize("name", ["c1_single_target", "c3_12_targets_mh", "ragged_hr_donor", "truseq", "ramsden"])
-def test_reference_driver_with_dropin_writes_identical_files(name):
+def test_reference_driver_with_dropin_writes_identical_files(name, native_frequency):
+    """native_frequency=True: the Frequency / SNV files come from scar_frequency_rows_host (the product default);
+    False: the reference's own frequency_output runs, its two searches served from the batched results."""
     import make_golden
     from oracle_engine import OracleEngine, host_homeology_batch
     blob = gu.load(name)
@@ -48,6 +51,7 @@ def test_reference_driver_with_dropin_writes_identical_files(name):
         log = Tool_Box.Logger(args)
         dropin._ENGINE_FACTORY[0] = OracleEngine
         dropin._HOMEOLOGY_BATCH[0] = host_homeology_batch
+        dropin.NATIVE_FREQUENCY[0] = native_frequency
         dropin.install(INDEL_Processing)
 
         class _Fastq:
@@ -70,7 +74,7 @@ def test_reference_driver_with_dropin_writes_identical_files(name):
             dropin._RAW_DATA_HOOK[0] = None
         # every homeology / templated-insertion search of frequency_output was answered from the batch
         assert dropin.PATTERN_SEARCH_STATS["missed"] == 0, dropin.PATTERN_SEARCH_STATS
-        assert dropin.PATTERN_SEARCH_STATS["served"] > 0
+        assert (dropin.PATTERN_SEARCH_STATS["served"] > 0) == (not native_frequency)
         assert dp.read_count == golden["read_count"]
         assert dict(dp.read_count_dict) == golden["read_count_dict"]
         assert {k: dict(v) for k, v in dp.phase_count.items()} == golden["phase_count"]
@@ -96,6 +100,7 @@ def test_reference_driver_with_dropin_writes_identical_files(name):
     finally:
         dropin._ENGINE_FACTORY[0] = None
         dropin._HOMEOLOGY_BATCH[0] = None
+        dropin.NATIVE_FREQUENCY[0] = True
         INDEL_Processing.DataProcessing.consensus_demultiplex, INDEL_Processing.ScarSearch.data_processing = saved
         shutil.rmtree(wd, ignore_errors=True)
 
