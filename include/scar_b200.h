@@ -10,6 +10,7 @@
  *   scarmapper/INDEL_Processing.py:1126-1201 index_matching                 -> scar_demux_dev
  *   Valkyries/Sequence_Magic.py:123-136     match_maker(query, unknown)     -> scar_match_maker_batch
  *   scarmapper/INDEL_Processing.py:550-700  homeology_search / templated_insertion_search -> scar_homeology_batch
+ *   Valkyries/FASTQ_Tools.py:562-653        FASTQ_Reader (text / gzip file)  -> scar_process_fastq_file
  *   scarmapper/INDEL_Processing.py:233-478  frequency_output (per-pattern body, rows) -> scar_frequency_rows_host
  *   scarmapper/INDEL_Processing.py:702-757  raw_data_output (body)         -> scar_raw_rows_host
  *   scarmapper/INDEL_Processing.py:57-80,759-795 window_mapping/cutsite_search -> scar_ctx_create (tables), scar_cutsite_search
@@ -231,6 +232,39 @@ int scar_process_fastq_host(scar_ctx *ctx, const uint8_t *text, int64_t n_bytes,
 /* After scar_process_fastq_host(records = NULL): copy the records of that call to the host once their number
  * is known. */
 int scar_fastq_records_fetch(scar_ctx *ctx, scar_record *records, int64_t n_records);
+
+/* A whole FASTQ FILE through the path (replaces FASTQ_Reader as the loader in front of consensus_demultiplex,
+ * Valkyries/FASTQ_Tools.py:562-653 + scarmapper/INDEL_Processing.py:891-1024): plain text, gzip (one stream or several
+ * members) or BGZF, told apart by the magic bytes as the reference tells them apart by MIME type.  A producer thread
+ * reads / inflates the file into pinned pieces (BGZF blocks and plain text by n_threads threads side by side; a
+ * single DEFLATE stream by one thread, overlapped with everything else) while the calling thread copies each piece to
+ * the GPU, indexes it there and runs the records that have become complete through the whole path.  The context
+ * adapts to the run: longer reads than max_read_len re-plan it, the scar table grows (scar_table_reserve).
+ * record_limit > 0 stops after that many records (--Verbose DEBUG).  With scar_ctx_set_verify the run is checked key
+ * by key at the end.  keep_text != 0 keeps the (inflated) text for the caller.  The arrays of `run` belong to the
+ * library until scar_fastq_run_release. */
+typedef struct scar_fastq_run {
+    int64_t n_records;             /* FASTQ records processed, file order */
+    int64_t text_bytes;            /* (inflated) text consumed */
+    const uint8_t *text;           /* the text (keep_text) or NULL */
+    const int64_t *seq_off;        /* [n_records] views of the sequence lines into the text */
+    const int32_t *seq_len;
+    const scar_record *records;    /* [n_records] */
+    int32_t max_seq_len;           /* longest sequence line */
+    int32_t source_kind;           /* 0 plain text, 1 gzip stream, 2 BGZF */
+    int32_t threads;               /* threads that read / inflated */
+    int32_t reserved;
+    double wait_seconds;           /* time the calling thread waited for the producer (inflate-bound when ~ total) */
+    double total_seconds;
+    void *owner;
+} scar_fastq_run;
+int scar_process_fastq_file(scar_ctx *ctx, const char *path, int64_t record_limit, uint64_t first_index,
+                            int32_t n_threads, int32_t keep_text, scar_fastq_run *run);
+void scar_fastq_run_release(scar_fastq_run *run);
+
+/* Room for n_more further scar patterns: rebuilds the table at a larger power of two when it would pass half full
+ * (entries re-inserted through the claimed-slot list; first-seen indices and counts kept).  Synchronises the device. */
+int scar_table_reserve(scar_ctx *ctx, int64_t n_more);
 
 /* The body of ScarSearch.raw_data_output (scarmapper/INDEL_Processing.py:702-757), host side: one text line per
  * scarred read of `sample` (records[r].status == SCAR_ST_SCAR), in read order, built from the records and the raw

@@ -73,6 +73,14 @@ class FrequencyIn(C.Structure):
                 ("reverse_comp", C.c_int32), ("passing", C.c_int64), ("no_cut", C.c_int64), ("pattern_threshold", C.c_double)]
 
 
+class FastqRun(C.Structure):
+    """struct scar_fastq_run"""
+    _fields_ = [("n_records", C.c_int64), ("text_bytes", C.c_int64), ("text", C.c_void_p), ("seq_off", C.c_void_p),
+                ("seq_len", C.c_void_p), ("records", C.c_void_p), ("max_seq_len", C.c_int32), ("source_kind", C.c_int32),
+                ("threads", C.c_int32), ("reserved", C.c_int32), ("wait_seconds", C.c_double), ("total_seconds", C.c_double),
+                ("owner", C.c_void_p)]
+
+
 # every symbol include/scar_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 _RP = C.POINTER(Ragged)
@@ -128,6 +136,9 @@ PROTOTYPES = {
     "scar_frequency_rows_host": (C.c_int, [C.POINTER(FrequencyIn), C.POINTER(C.c_int64), _P, _P, _P, _P, _P, C.c_int64,
                                           C.POINTER(C.c_int64), _P]),
     "scar_frequency_rows_fetch": (C.c_int, [_P, C.c_int64]),
+    "scar_process_fastq_file": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(FastqRun)]),
+    "scar_fastq_run_release": (None, [C.POINTER(FastqRun)]),
+    "scar_table_reserve": (C.c_int, [_P, C.c_int64]),
     "scar_alignment_batch": (C.c_int, [C.c_int32, _RP, _RP, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
     "scar_match_maker_batch": (C.c_int, [C.c_int32, _RP, _RP, C.c_int64, _P]),
 }

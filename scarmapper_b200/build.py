@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscar_b200.so")
 SOURCES = ["scar_api.cu", "scar_pack.cu", "scar_demux.cu", "scar_window.cu", "scar_table.cu", "scar_fastq.cu", "scar_fastq_dev.cu",
-           "scar_homeology.cu", "scar_rawdata.cu", "scar_alignment.cu", "scar_frequency.cu"]
+           "scar_homeology.cu", "scar_rawdata.cu", "scar_alignment.cu", "scar_frequency.cu", "scar_ingest.cu"]
+LINK_LIBS = ["-lz", "-lpthread"]          # zlib: gzip FASTQ inflated natively (scar_ingest.cu)
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-cudart", "static"]
 
@@ -30,15 +31,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(p) for p in _deps()):
         return LIB
-    objs = []
+    # an object is rebuilt when its source or any header is newer; the sources compile side by side
+    headers = [p for p in _deps() if not p.endswith((".cu", ".o"))]
+    newest_header = max(os.path.getmtime(p) for p in headers)
+    extra = os.environ.get("SCAR_NVCC_EXTRA", "").split()
+    jobs, objs = [], []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        extra = os.environ.get("SCAR_NVCC_EXTRA", "").split()
-        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
-        subprocess.check_call(cmd)
+        path, obj = os.path.join(CSRC, src), os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(obj)
+        if force or extra or verbose or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(path), newest_header):
+            jobs.append([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj])
+    procs = [subprocess.Popen(cmd) for cmd in jobs]
+    failed = [cmd for cmd, p in zip(jobs, procs) if p.wait() != 0]
+    if failed:
+        raise subprocess.CalledProcessError(1, failed[0])
     subprocess.check_call([nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-                           "-o", LIB] + objs)
+                           "-o", LIB] + objs + LINK_LIBS)
     return LIB
 
 

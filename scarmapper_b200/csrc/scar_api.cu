@@ -16,22 +16,13 @@
 
 // ---- errors ---------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static int fail(int code, const char *fmt, ...)
-{
-    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
-    return code;
-}
 int scar_fail(int code, const char *fmt, ...)      // for the other translation units
 {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return code;
 }
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess)                                                                     \
-            return fail(SCAR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
+#include "scar_ctx.cuh"
+#define fail scar_fail
 
 extern "C" const char *scar_last_error(void) { return g_err; }
 extern "C" int scar_version(void) { return 100; }
@@ -174,49 +165,7 @@ static bool build_table(const std::vector<std::pair<uint32_t, uint32_t>> &kv, bo
 }
 
 // ---- context --------------------------------------------------------------------------------------
-static const int NBUF = 3;
-
-struct HostBuf {   // device scratch of one in-flight chunk of scar_process_host
-    uint8_t *seq = nullptr, *f0 = nullptr, *f1 = nullptr; size_t seq_cap = 0, f0_cap = 0, f1_cap = 0;
-    int64_t *seq_off = nullptr, *f0_off = nullptr, *f1_off = nullptr;
-    int32_t *seq_len = nullptr, *f0_len = nullptr, *f1_len = nullptr;
-    uint64_t *cells = nullptr; uint32_t *lens = nullptr; uint16_t *samples = nullptr; scar_record *records = nullptr;
-    int64_t reads_cap = 0;
-    cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
-};
-
-struct scar_ctx {
-    int device = 0, sm_count = 148, sm_total = 148, platform = 0, mismatch = 1, n_targets = 0, n_samples = 0;
-    int W = 0, max_read_len = 0, min_length = 0, hr_len = 0, do_phasing = 0;
-    double n_limit = 0.0; uint64_t hr_code = 0;
-    std::vector<ScarTargetMeta> h_targets;
-    int32_t *d_sample_target = nullptr;
-    unsigned char *d_blob = nullptr; uint32_t blob_bytes = 0, meta_off = 0, phase_off = 0, nmax_off = 0;
-    bool smem_tables = true, compact_tables = false;
-    uint8_t *d_class_map = nullptr; DemuxString *d_right = nullptr, *d_left = nullptr; uint64_t *d_peq = nullptr;
-    uint16_t *d_first_sample = nullptr; int n_right = 0, n_left = 0, n_classes = 0;
-    uint8_t *d_fast_codes = nullptr; int demux_fast = 0;
-    uint64_t *d_lut_right = nullptr, *d_lut_left = nullptr; int lut_n_right = 0, lut_n_left = 0;
-    ScarTableSlot *d_slots = nullptr; uint64_t capacity = 0;
-    uint32_t *d_claimed = nullptr;         // indices of the claimed slots, in claim order
-    unsigned long long *d_acc = nullptr;   // [n_entries, unassigned, collisions, export_count] + counters + phase hist
-    unsigned long long *d_n_entries = nullptr, *d_unassigned = nullptr, *d_collisions = nullptr, *d_export_n = nullptr;
-    unsigned long long *d_counters = nullptr, *d_phase_hist = nullptr; size_t acc_words = 0;
-    int32_t *d_status = nullptr;
-    HostBuf buf[NBUF]; int64_t chunk_reads = 1 << 20;
-    bool weak_keys = false;                 // test hook (scar_ctx_set_verify(ctx, 2)): key tags without the segment
-    bool verify = false;                    // scar_process_host: one resident chunk + exact key verification
-    int fused_ok = -1;                      // -1 unknown, 1: scar_run_dev takes the fused kernel, 0: K1 -> K3 -> K4
-    // GPU FASTQ path
-    uint8_t *d_text = nullptr; size_t text_cap = 0;
-    uint32_t *d_tile_counts = nullptr; size_t tile_counts_cap = 0;
-    int64_t *d_tile_offsets = nullptr; size_t tile_offsets_cap = 0;
-    int64_t *d_nl = nullptr; size_t nl_cap = 0;
-    unsigned long long *d_part_cursor = nullptr;     // region cursors of the peer-memory export
-    scar_record *d_fq_records = nullptr; size_t fq_records_cap = 0; int64_t fq_records_n = 0;   // records of the last FASTQ-text call
-    std::vector<cudaEvent_t> fq_events;
-    int launches = 0;
-};
+// (struct HostBuf / struct scar_ctx: scar_ctx.cuh)
 
 static void free_hostbuf(HostBuf &b)
 {
@@ -237,6 +186,8 @@ extern "C" void scar_ctx_destroy(scar_ctx *c)
     cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample); cudaFree(c->d_fast_codes);
     cudaFree(c->d_lut_right); cudaFree(c->d_lut_left);
     cudaFree(c->d_slots); cudaFree(c->d_claimed); cudaFree(c->d_acc); cudaFree(c->d_status);
+    cudaFree(c->d_fq_seq_off); cudaFree(c->d_fq_seq_len);
+    for (uint8_t *p : c->h_piece) if (p) cudaFreeHost(p);
     cudaFree(c->d_text); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offsets); cudaFree(c->d_nl); cudaFree(c->d_fq_records); cudaFree(c->d_part_cursor);
     for (cudaEvent_t e : c->fq_events) cudaEventDestroy(e);
     delete c;
@@ -364,8 +315,8 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
     if (cfg->phase_off && (!cfg->phase_r1_bytes || !cfg->phase_r1_off || !cfg->phase_r2_bytes || !cfg->phase_r2_off))
         return fail(SCAR_ERR_INVALID, "phase_off given without the phase string lists");
     if (cfg->hr_len > 0 && !cfg->hr_donor) return fail(SCAR_ERR_INVALID, "hr_len > 0 with a NULL donor");
-    if (cfg->max_read_len < 1 || cfg->max_read_len > 1024)
-        return fail(SCAR_ERR_UNSUPPORTED, "max_read_len %d outside 1..1024", cfg->max_read_len);
+    if (cfg->max_read_len < 1 || cfg->max_read_len > SCAR_MAX_READ_LEN)
+        return fail(SCAR_ERR_UNSUPPORTED, "max_read_len %d outside 1..%d", cfg->max_read_len, SCAR_MAX_READ_LEN);
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(SCAR_ERR_CUDA, "CUDA device %d not present (%d devices)", cfg->device, ndev);
@@ -499,8 +450,9 @@ extern "C" int scar_ctx_create(const scar_config *cfg, scar_ctx **out)
     // nmax[len] = largest n with double(n)/double(len) <= N_Limit: the reference's filter
     // seq.count("N")/len(seq) > N_Limit (INDEL_Processing.py:147) evaluated once per length on the host
     // with the same IEEE-754 double division Python performs.
-    std::vector<uint16_t> nmax((size_t)16 * c->W + 1, 0);
-    for (int len = 1; len <= 16 * c->W; ++len) {
+    // (tabulated for every supported length, so that a context can be re-planned for longer reads: scar_grow_read_len)
+    std::vector<uint16_t> nmax((size_t)SCAR_MAX_READ_LEN + 1, 0);
+    for (int len = 1; len <= SCAR_MAX_READ_LEN; ++len) {
         int n = 0;
         while (n < len && !((double)(n + 1) / (double)len > cfg->n_limit)) ++n;
         nmax[len] = (uint16_t)n;
@@ -602,6 +554,61 @@ extern "C" int scar_reset_dev(scar_ctx *c, void *stream)
     CU(cudaMemsetAsync(c->d_acc, 0, c->acc_words * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(c->d_status, 0, sizeof(int32_t), s));      // like scar_reset: a reset state carries no sticky error
     return SCAR_OK;
+}
+
+static K4Params k4_params(scar_ctx *c);
+
+// Re-plan the context for reads up to max_len (the FASTQ file path learns the longest read while it streams).
+// Nothing that has been computed depends on W: records, tables and counters stay valid.  The caller's streams are idle.
+int scar_grow_read_len(scar_ctx *c, int max_len)
+{
+    if (max_len <= c->max_read_len) return SCAR_OK;
+    if (max_len > SCAR_MAX_READ_LEN) return fail(SCAR_ERR_UNSUPPORTED, "a read of %d nt is longer than the supported %d", max_len, SCAR_MAX_READ_LEN);
+    c->max_read_len = std::min(SCAR_MAX_READ_LEN, (max_len + 15) / 16 * 16);
+    c->W = (c->max_read_len + 15) / 16;
+    c->fused_ok = -1;
+    for (auto &b : c->buf) {               // the packed batch of the three-kernel path is W cells per read
+        cudaFree(b.cells); b.cells = nullptr;
+        if (b.reads_cap > 0 && !scar_fused_path(c)) CU(cudaMalloc((void **)&b.cells, (size_t)b.reads_cap * c->W * sizeof(uint64_t)));
+    }
+    return SCAR_OK;
+}
+
+// Room for n_more further scar patterns: when the table would pass half full it is rebuilt at a larger power of two
+// (entries exported through the claimed-slot list, folded into the new slots).  Synchronises the device.
+extern "C" int scar_table_reserve(scar_ctx *c, int64_t n_more)
+{
+    if (!c || n_more < 0) return fail(SCAR_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    unsigned long long n = 0;
+    CU(cudaMemcpy(&n, c->d_n_entries, sizeof(n), cudaMemcpyDeviceToHost));
+    const uint64_t want = 2 * (n + (uint64_t)n_more);
+    if (want <= c->capacity) return SCAR_OK;
+    uint64_t cap = c->capacity;
+    while (cap < 2 * want) cap <<= 1;      // ends at most a quarter full
+    if (cap > (1ull << 32)) { cap = 1ull << 32; if (want > cap) return fail(SCAR_ERR_TABLE_FULL, "scar table cannot grow past 2^32 slots"); }
+    scar_entry *d = nullptr;
+    if (n) {
+        CU(cudaMalloc((void **)&d, (size_t)n * sizeof(scar_entry)));
+        CU(scar_launch_export(c->d_slots, c->d_claimed, c->d_n_entries, d, n, c->sm_count, nullptr));
+        CU(cudaDeviceSynchronize());
+    }
+    cudaFree(c->d_slots); cudaFree(c->d_claimed);
+    c->d_slots = nullptr; c->d_claimed = nullptr;
+    cudaError_t e = cudaMalloc((void **)&c->d_slots, cap * sizeof(ScarTableSlot));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_claimed, cap * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(d); return fail(SCAR_ERR_NOMEM, "scar table: no device memory for %llu slots", (unsigned long long)cap); }
+    c->capacity = cap;
+    CU(cudaMemset(c->d_slots, 0, cap * sizeof(ScarTableSlot)));
+    CU(cudaMemset(c->d_n_entries, 0, sizeof(unsigned long long)));
+    if (n) {
+        CU(scar_launch_merge(k4_params(c), d, n, c->sm_count, nullptr));
+        ++c->launches;
+        CU(cudaDeviceSynchronize());
+        cudaFree(d);
+    }
+    return scar_check_status(c);
 }
 
 extern "C" int scar_ctx_set_sm_limit(scar_ctx *c, int32_t n_sms)
@@ -755,7 +762,7 @@ static K3Params fused_params(scar_ctx *c, const scar_ragged *seq, const uint16_t
 
 // does scar_run_dev take the fused kernel for this context?  (eligible platform / read length, and a tile fits beside
 // the static blob in shared memory; independent of the layout of the reads)
-static bool fused_path(scar_ctx *c)
+bool scar_fused_path(scar_ctx *c)
 {
     if (c->fused_ok < 0) {
         c->fused_ok = 0;
@@ -774,7 +781,7 @@ extern "C" int scar_fused_info(const scar_ctx *c, int32_t *eligible, int32_t *ct
 {
     if (!c) return fail(SCAR_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->device));
-    const bool ok = fused_path(const_cast<scar_ctx *>(c));
+    const bool ok = scar_fused_path(const_cast<scar_ctx *>(c));
     if (eligible) *eligible = ok ? 1 : 0;
     int per = 0, sm = 0;
     if (ok) CU(scar_fused_plan(fused_params(const_cast<scar_ctx *>(c), nullptr, nullptr, 0, 0, nullptr, 1), c->smem_tables,
@@ -806,14 +813,14 @@ extern "C" int scar_run_dev(scar_ctx *c, const scar_ragged *seq, const scar_ragg
     if ((rc = scar_demux_dev(c, seq, f0, f1, n, samples, stream))) return rc;
     // one pass over the raw bytes (pack, classify, aggregate) when the fused kernel takes the problem
     // (ineligible, or a static blob too large to leave room for a tile beside it: K1 -> K3 -> K4 below)
-    if (c && seq && fused_path(c)) return scar_classify_raw_dev(c, seq, samples, n, first_index, records, 1, stream);
+    if (c && seq && scar_fused_path(c)) return scar_classify_raw_dev(c, seq, samples, n, first_index, records, 1, stream);
     if (!cells || !lens) return fail(SCAR_ERR_INVALID, "the three-kernel path needs the cells / lens scratch buffers");
     if ((rc = scar_pack_dev(c, seq, n, cells, lens, stream))) return rc;
     if ((rc = scar_classify_dev(c, cells, lens, samples, n, records, stream))) return rc;
     return scar_aggregate_dev(c, seq, records, n, first_index, stream);
 }
 
-static int check_status(scar_ctx *c)
+int scar_check_status(scar_ctx *c)
 {
     int32_t st = 0;
     CU(cudaMemcpy(&st, c->d_status, sizeof(st), cudaMemcpyDeviceToHost));
@@ -848,7 +855,7 @@ extern "C" int scar_counters_read(scar_ctx *c, int64_t *counters, int64_t *unass
     if (!c) return fail(SCAR_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->device));
     CU(cudaDeviceSynchronize());
-    int rc = check_status(c);
+    int rc = scar_check_status(c);
     if (rc) return rc;
     if (counters) CU(cudaMemcpy(counters, c->d_counters, (size_t)c->n_samples * SCAR_N_COUNTERS * sizeof(int64_t), cudaMemcpyDeviceToHost));
     if (unassigned) CU(cudaMemcpy(unassigned, c->d_unassigned, sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -869,7 +876,7 @@ extern "C" int scar_table_size(scar_ctx *c, int64_t *n)
     if (!c || !n) return fail(SCAR_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(c->device));
     CU(cudaDeviceSynchronize());
-    int rc = check_status(c);
+    int rc = scar_check_status(c);
     if (rc) return rc;
     unsigned long long v = 0;
     CU(cudaMemcpy(&v, c->d_n_entries, sizeof(v), cudaMemcpyDeviceToHost));
@@ -1007,17 +1014,6 @@ extern "C" int scar_table_read(scar_ctx *c, scar_entry *entries, int64_t capacit
 }
 
 // ---- host-buffer pipeline -------------------------------------------------------------------------
-template <typename T> static int ensure(T **p, size_t *cap, size_t need)
-{
-    if (need <= *cap && *p) return SCAR_OK;
-    if (*p) CU(cudaFree(*p));
-    *p = nullptr;
-    size_t n = std::max<size_t>(need + need / 8, 256);
-    CU(cudaMalloc((void **)p, n * sizeof(T)));
-    *cap = n;
-    return SCAR_OK;
-}
-
 struct Span { int64_t byte0, byte1; };   // host byte range of items [a, b)
 static Span span_of(const scar_ragged &R, int64_t a, int64_t b)
 {
@@ -1065,7 +1061,7 @@ static int stage_ragged(const scar_ragged &H, int64_t a, int64_t b, uint8_t **db
     return stage_index(H, a, b, *dbytes, H.offsets ? sp.byte0 : 0, *doff, *dlen, s, D, h2d);
 }
 
-static int ensure_hostbuf(scar_ctx *c, HostBuf &b, int64_t reads)
+int scar_ensure_hostbuf(scar_ctx *c, HostBuf &b, int64_t reads)
 {
     if (!b.stream) { CU(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming)); }
     if (reads <= b.reads_cap) return SCAR_OK;
@@ -1081,7 +1077,7 @@ static int ensure_hostbuf(scar_ctx *c, HostBuf &b, int64_t reads)
     CU(cudaMalloc((void **)&b.seq_len, n * sizeof(int32_t)));
     CU(cudaMalloc((void **)&b.f0_len, n * sizeof(int32_t)));
     CU(cudaMalloc((void **)&b.f1_len, n * sizeof(int32_t)));
-    if (!fused_path(c)) {                                  // the packed batch exists only on the K1 -> K3 -> K4 path
+    if (!scar_fused_path(c)) {                                  // the packed batch exists only on the K1 -> K3 -> K4 path
         CU(cudaMalloc((void **)&b.cells, n * c->W * sizeof(uint64_t)));
         CU(cudaMalloc((void **)&b.lens, n * sizeof(uint32_t)));
     }
@@ -1105,7 +1101,7 @@ extern "C" int scar_process_host(scar_ctx *c, const scar_ragged *seq, const scar
     for (int64_t a = 0; a < n; a += chunk, ++k) {
         const int64_t b = std::min(n, a + chunk);
         HostBuf &B = c->buf[k % NBUF];
-        int rc = ensure_hostbuf(c, B, chunk);
+        int rc = scar_ensure_hostbuf(c, B, chunk);
         if (rc) return rc;
         if (k >= NBUF) CU(cudaEventSynchronize(B.done));     // buffer reuse: its previous chunk has drained
         scar_ragged dseq, df0, df1;
@@ -1142,23 +1138,10 @@ extern "C" int scar_process_host(scar_ctx *c, const scar_ragged *seq, const scar
         CU(cudaEventRecord(B.done, B.stream));
     }
     for (int i = 0; i < NBUF; ++i) if (c->buf[i].stream) CU(cudaStreamSynchronize(c->buf[i].stream));
-    return check_status(c);
+    return scar_check_status(c);
 }
 
 // ---- FASTQ text in host memory -> records: the text is copied to the GPU once and indexed THERE ----------
-// grow a device array and keep its first `keep` elements
-template <typename T> static int ensure_keep(T **p, size_t *cap, size_t need, size_t keep)
-{
-    if (need <= *cap && *p) return SCAR_OK;
-    T *q = nullptr;
-    const size_t n = std::max<size_t>(need + need / 4, 256);
-    CU(cudaMalloc((void **)&q, n * sizeof(T)));
-    if (*p && keep) CU(cudaMemcpy(q, *p, keep * sizeof(T), cudaMemcpyDeviceToDevice));
-    if (*p) CU(cudaFree(*p));
-    *p = q; *cap = n;
-    return SCAR_OK;
-}
-
 extern "C" int scar_process_fastq_host(scar_ctx *c, const uint8_t *text, int64_t n_bytes, uint64_t first_index,
                                        scar_record *records, int64_t records_capacity, int64_t *n_records_out)
 {
@@ -1168,9 +1151,9 @@ extern "C" int scar_process_fastq_host(scar_ctx *c, const uint8_t *text, int64_t
     c->fq_records_n = 0;
     if (n_bytes == 0) return SCAR_OK;
     HostBuf &B = c->buf[0];
-    int rc = ensure_hostbuf(c, B, 1);
+    int rc = scar_ensure_hostbuf(c, B, 1);
     if (rc) return rc;
-    if ((rc = ensure_hostbuf(c, c->buf[1], 1))) return rc;
+    if ((rc = scar_ensure_hostbuf(c, c->buf[1], 1))) return rc;
     cudaStream_t s = B.stream, sc = c->buf[1].stream;
     if ((rc = ensure(&c->d_text, &c->text_cap, (size_t)n_bytes + 64))) return rc;
     // The text is copied in pieces of plain bytes on one stream; a second stream indexes every piece as soon as
@@ -1221,7 +1204,7 @@ extern "C" int scar_process_fastq_host(scar_ctx *c, const uint8_t *text, int64_t
         if (m <= 0) continue;
         if (records && records_capacity < rec_avail)
             return drain(fail(SCAR_ERR_INVALID, "records buffer too small: more than %lld records", (long long)records_capacity));
-        if ((rc = ensure_hostbuf(c, B, m))) return drain(rc);
+        if ((rc = scar_ensure_hostbuf(c, B, m))) return drain(rc);
         size_t want_rec = (size_t)rec_avail;
         if (want_rec > c->fq_records_cap && k + 1 < n_pieces)
             want_rec = (size_t)((double)want_rec * (double)n_bytes / (double)(b0 + len) * 1.02) + 1024;
@@ -1248,7 +1231,7 @@ extern "C" int scar_process_fastq_host(scar_ctx *c, const uint8_t *text, int64_t
         if (st & 8) return fail(SCAR_ERR_INVALID, "FASTQ: sequence and quality scores of different lengths");
         return fail(SCAR_ERR_INVALID, "FASTQ: a header has no '+' between the index reads (the reference raises IndexError)");
     }
-    return check_status(c);
+    return scar_check_status(c);
 }
 
 extern "C" int scar_fastq_records_fetch(scar_ctx *c, scar_record *records, int64_t n_records)

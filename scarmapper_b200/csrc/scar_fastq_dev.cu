@@ -153,8 +153,9 @@ struct FqViews {
 // records first_record .. first_record + n_records - 1 of the text; view r - first_record is written
 __global__ void __launch_bounds__(256) fq_records_kernel(const uint8_t *text, int64_t n_bytes, const int64_t *nl_pos,
                                                          int64_t n_newlines, int64_t first_record, int64_t n_records,
-                                                         int want_fields, FqViews V, int32_t *status)
+                                                         int want_fields, FqViews V, int32_t *status, int32_t *max_len)
 {
+    int longest = 0;                    // longest sequence line this thread has seen (one atomic per warp at the end)
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_records;
          r += (int64_t)gridDim.x * blockDim.x) {
         int64_t ls[4], le[4];
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(256) fq_records_kernel(const uint8_t *text, in
         while (q1 > q0 && fq_space(text[q1 - 1])) --q1;
         if (s1 - s0 != q1 - q0) atomicOr(status, 8);
         V.seq_off[r] = s0; V.seq_len[r] = (int32_t)(s1 - s0);
+        longest = max(longest, (int)(s1 - s0));
         if (want_fields) {
             int64_t h0 = ls[0], h1 = le[0];
             if (h1 > h0 && text[h1 - 1] == '\r') --h1;             // text mode: "\r\n" is one newline
@@ -187,6 +189,10 @@ __global__ void __launch_bounds__(256) fq_records_kernel(const uint8_t *text, in
             V.f0_off[r] = c; V.f0_len[r] = (int32_t)(p1 - c);
             V.f1_off[r] = p1 < h1 ? p1 + 1 : h1; V.f1_len[r] = p1 < h1 ? (int32_t)(p2 - p1 - 1) : 0;
         }
+    }
+    if (max_len) {
+        longest = __reduce_max_sync(0xFFFFFFFFu, longest);
+        if ((threadIdx.x & 31) == 0 && longest > 0) atomicMax(max_len, longest);
     }
 }
 
@@ -227,13 +233,13 @@ cudaError_t scar_fastq_positions_launch(const uint8_t *text, int64_t n_bytes, co
 cudaError_t scar_fastq_records_launch(const uint8_t *text, int64_t n_bytes, const int64_t *nl_pos, int64_t n_newlines,
                                       int64_t first_record, int64_t n_records, int want_fields, int64_t *seq_off, int32_t *seq_len,
                                       int64_t *f0_off, int32_t *f0_len, int64_t *f1_off, int32_t *f1_len, int32_t *status,
-                                      int sm_count, cudaStream_t s)
+                                      int sm_count, cudaStream_t s, int32_t *max_len)
 {
     if (n_records <= 0) return cudaSuccess;
     FqViews V{seq_off, seq_len, f0_off, f0_len, f1_off, f1_len};
     int64_t blocks = (n_records + 255) / 256;
     const int64_t cap = (int64_t)sm_count * 16;
     if (blocks > cap) blocks = cap;
-    fq_records_kernel<<<(unsigned)blocks, 256, 0, s>>>(text, n_bytes, nl_pos, n_newlines, first_record, n_records, want_fields, V, status);
+    fq_records_kernel<<<(unsigned)blocks, 256, 0, s>>>(text, n_bytes, nl_pos, n_newlines, first_record, n_records, want_fields, V, status, max_len);
     return cudaGetLastError();
 }

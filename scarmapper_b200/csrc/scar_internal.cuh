@@ -223,6 +223,7 @@ cudaError_t scar_launch_homeology(const scar_ragged &cons, const scar_ragged &in
 cudaError_t scar_launch_alignment(const scar_ragged &genomic, const scar_ragged &consensus, const int32_t *cutposition,
                                   const int32_t *gap_con_len, const int32_t *gap_genome_len, int64_t n, int32_t max_spans,
                                   void *counts, int32_t *spans, int sm_count, cudaStream_t stream);
+#define SCAR_MAX_READ_LEN 1024        // stored length of a read (16-bit fields of the records, nmax table)
 #define SCAR_MAX_PEERS 32
 cudaError_t scar_launch_export_p2p(const ScarTableSlot *slots, const uint32_t *claimed, const unsigned long long *n_entries,
                                    scar_entry *const *peer_base,
@@ -240,4 +241,4 @@ cudaError_t scar_fastq_positions_launch(const uint8_t *text, int64_t n_bytes, co
 cudaError_t scar_fastq_records_launch(const uint8_t *text, int64_t n_bytes, const int64_t *nl_pos, int64_t n_newlines,
                                       int64_t first_record, int64_t n_records, int want_fields, int64_t *seq_off, int32_t *seq_len,
                                       int64_t *f0_off, int32_t *f0_len, int64_t *f1_off, int32_t *f1_len, int32_t *status,
-                                      int sm_count, cudaStream_t s);
+                                      int sm_count, cudaStream_t s, int32_t *max_len = nullptr);   // max_len: atomicMax of the sequence lengths

@@ -41,6 +41,8 @@ _ENGINE_FACTORY = [None]      # tests substitute a CPU stand-in here; None -> Sc
 _HOMEOLOGY_BATCH = [None]     # likewise for the per-pattern searches; None -> engine.homeology_batch (GPU)
 _RAW_DATA_HOOK = [None]       # tests: called as hook(index_name, rows, records, reads, result) per Raw_Data file
 PATTERN_SEARCH_STATS = {"served": 0, "missed": 0}   # calls answered from the batch / handed to the reference's method
+FILE_INGEST = [True]          # the FASTQ file is streamed through the GPU (scar_process_fastq_file); False: read + indexed on the host
+FILE_INGEST_THREADS = [0]     # threads of the producer (0: min(8, cores))
 NATIVE_FREQUENCY = [True]     # False: the reference's own frequency_output runs over results_freq_dict (cross-check)
 STAGE_SECONDS = {}           # wall time of the stages of the last batched_consensus_demultiplex (parent process)
 READ_LIMIT_DEBUG = 1000002    # --Verbose DEBUG: the reference's loop stops after 1 000 002 reads (:906-914, see below)
@@ -201,38 +203,65 @@ def batched_consensus_demultiplex(self, module, device=0):
         now = time.perf_counter()
         STAGE_SECONDS[name] = STAGE_SECONDS.get(name, 0.0) + now - t_stage
         t_stage = now
-    batch = fastq.load(self.fastq1.input_file, want_index_fields=args.Platform == "Illumina", limit=limit)
-    self.read_count = batch.n
-    stage("fastq_read_inflate_index")
     sample_target = [target_pos[self.index_dict[i][7]] for i in sample_ids]
-    prob = ScarProblem(
+    common = dict(
         targets=targets, cutsites=cutsites, sample_target=sample_target,
         left_index=[self.index_dict[i][0] for i in sample_ids], right_index=[self.index_dict[i][2] for i in sample_ids],
         platform=args.Platform, phasing=phasing, hr_donor=args.HR_Donor or "", n_limit=args.N_Limit,
-        min_length=args.Minimum_Length, max_read_len=max(16, batch.seq.max_len()),
-        table_capacity=1 << max(16, int(math.ceil(math.log2(max(2 * batch.n, 2))))))
-    eng = _make_engine(prob, device)
-    try:
-        # Exact-or-fail key identity: when the run fits the device (text + ~60 bytes of views / records per read) it is
-        # processed as one resident chunk and every scarred read's full key is compared with the first read of its
-        # table entry; a mismatch raises instead of merging two scar patterns under one 128-bit tag.
-        if hasattr(eng, "set_verify"):
-            free, _total = eng.device_memory()
-            need = int(batch.text.size) + 64 * batch.n + (256 << 20)
-            if need < 0.8 * free:
-                eng.set_verify(True)
-                STAGE_SECONDS["keys_verified_exactly"] = 1.0
-            else:
-                log.warning("Run too large for one resident chunk ({:.1f} GB needed, {:.1f} GB free): scar patterns are "
-                            "identified by their 128-bit key tags without the exact comparison".format(need / 1e9, free / 1e9))
-                STAGE_SECONDS["keys_verified_exactly"] = 0.0
-        records = eng.process_host(batch.seq, batch.f0, batch.f1)
-        counters, unassigned = eng.counters()
-        phase_hist = eng.phase_hist()
-        table = eng.table()                     # sorted by (sample, first_idx): per-sample first-seen order
-    finally:
-        eng.close()
-    stage("gpu_classify_aggregate")
+        min_length=args.Minimum_Length)
+    streaming = FILE_INGEST[0] and hasattr(_ENGINE_FACTORY[0] or ScarEngine, "process_fastq_file")
+    if streaming:
+        # The file is streamed through the GPU (scar_process_fastq_file): read / inflated by a producer thread while
+        # its pieces are copied, indexed and classified on the device.  Nothing about the run is known up front: the
+        # engine re-plans itself for the longest read and grows its scar table as the patterns arrive.  The text stays
+        # resident, so every scarred read's full key is compared with the first read of its table entry at the end
+        # (exact-or-fail identity; a mismatch raises instead of merging two scar patterns under one 128-bit tag).
+        import os
+        if len(self.fastq1.input_file) < 3 or not os.path.isfile(self.fastq1.input_file):
+            raise FileNotFoundError("FASTQ file {} not found".format(self.fastq1.input_file))
+        eng = _make_engine(ScarProblem(max_read_len=160, table_capacity=1 << 18, **common), device)
+        try:
+            eng.set_verify(True)
+            STAGE_SECONDS["keys_verified_exactly"] = 1.0
+            batch = eng.process_fastq_file(self.fastq1.input_file, limit=limit, threads=FILE_INGEST_THREADS[0])
+            records = batch.records
+            self.read_count = batch.n
+            STAGE_SECONDS["fastq_source_" + batch.source] = 1.0
+            STAGE_SECONDS["fastq_producer_wait"] = batch.wait_seconds
+            counters, unassigned = eng.counters()
+            phase_hist = eng.phase_hist()
+            table = eng.table()                 # sorted by (sample, first_idx): per-sample first-seen order
+        finally:
+            eng.close()
+        stage("fastq_stream_gpu_classify_aggregate")
+    else:
+        batch = fastq.load(self.fastq1.input_file, want_index_fields=args.Platform == "Illumina", limit=limit)
+        self.read_count = batch.n
+        stage("fastq_read_inflate_index")
+        prob = ScarProblem(max_read_len=max(16, batch.seq.max_len()),
+                           table_capacity=1 << max(16, int(math.ceil(math.log2(max(2 * batch.n, 2))))), **common)
+        eng = _make_engine(prob, device)
+        try:
+            # Exact-or-fail key identity: when the run fits the device (text + ~60 bytes of views / records per read) it
+            # is processed as one resident chunk and every scarred read's full key is compared with the first read of
+            # its table entry; a mismatch raises instead of merging two scar patterns under one 128-bit tag.
+            if hasattr(eng, "set_verify"):
+                free, _total = eng.device_memory()
+                need = int(batch.text.size) + 64 * batch.n + (256 << 20)
+                if need < 0.8 * free:
+                    eng.set_verify(True)
+                    STAGE_SECONDS["keys_verified_exactly"] = 1.0
+                else:
+                    log.warning("Run too large for one resident chunk ({:.1f} GB needed, {:.1f} GB free): scar patterns are "
+                                "identified by their 128-bit key tags without the exact comparison".format(need / 1e9, free / 1e9))
+                    STAGE_SECONDS["keys_verified_exactly"] = 0.0
+            records = eng.process_host(batch.seq, batch.f0, batch.f1)
+            counters, unassigned = eng.counters()
+            phase_hist = eng.phase_hist()
+            table = eng.table()                     # sorted by (sample, first_idx): per-sample first-seen order
+        finally:
+            eng.close()
+        stage("gpu_classify_aggregate")
 
     # ---- unpack into the reference's bookkeeping
     assigned = records["status"] != N.ST_UNASSIGNED

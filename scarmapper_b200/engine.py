@@ -87,6 +87,43 @@ class HostRagged:
                         None if self.lengths is None else self.lengths.ctypes.data, self.stride)
 
 
+def _view(ptr, count, dtype, writeable=True):
+    """numpy view of `count` items of library-owned memory at `ptr` (no copy)."""
+    dtype = np.dtype(dtype)
+    if not count or not ptr:
+        return np.zeros(0, dtype)
+    a = np.ctypeslib.as_array((C.c_uint8 * (int(count) * dtype.itemsize)).from_address(ptr)).view(dtype)
+    a.flags.writeable = writeable
+    return a
+
+
+class FastqFileRun:
+    """What ScarEngine.process_fastq_file returns.  The arrays are views of memory the library owns (for a plain-text
+    file the text IS the mapped file); they stay valid until close() or until this object is collected - copy what
+    must live longer."""
+    KINDS = ("text", "gzip", "bgzf")
+
+    def __init__(self, lib, raw):
+        import weakref
+        self._raw = raw
+        self.n = int(raw.n_records)
+        self.text_bytes = int(raw.text_bytes)
+        self.records = _view(raw.records, self.n, N.RECORD_DTYPE)
+        self.seq_off = _view(raw.seq_off, self.n, np.int64)
+        self.seq_len = _view(raw.seq_len, self.n, np.int32)
+        self.text = _view(raw.text, self.text_bytes, np.uint8, writeable=False) if raw.text else None
+        self.seq = HostRagged.from_views(self.text, self.seq_off, self.seq_len) if self.text is not None else None
+        self.max_seq_len = int(raw.max_seq_len)
+        self.source = self.KINDS[raw.source_kind]
+        self.threads = int(raw.threads)
+        self.wait_seconds, self.total_seconds = float(raw.wait_seconds), float(raw.total_seconds)
+        self._final = weakref.finalize(self, lib.scar_fastq_run_release, C.byref(raw))
+
+    def close(self):
+        self.records = self.seq_off = self.seq_len = self.text = self.seq = None
+        self._final()
+
+
 def as_ragged(x):
     if x is None or isinstance(x, HostRagged):
         return x
@@ -258,6 +295,20 @@ class ScarEngine:
         rec = out[:n.value] if out is not None else np.empty(n.value, dtype=N.RECORD_DTYPE)
         N.check(self._L.scar_fastq_records_fetch(self._ctx, rec.ctypes.data, n.value))
         return rec
+
+    def process_fastq_file(self, path: str, limit: int | None = None, first_index: int = 0, threads: int = 0,
+                           keep_text: bool = True) -> "FastqFileRun":
+        """Whole path from a FASTQ FILE (plain text, gzip or BGZF; scar_process_fastq_file): the file is read /
+        inflated by a producer thread while its pieces are copied to the GPU, indexed and classified there.
+        Returns the run: records, sequence views and (keep_text) the text, as numpy views of library-owned memory."""
+        raw = N.FastqRun()
+        N.check(self._L.scar_process_fastq_file(self._ctx, path.encode(), int(limit or 0), first_index, int(threads),
+                                                1 if keep_text else 0, C.byref(raw)))
+        return FastqFileRun(self._L, raw)
+
+    def table_reserve(self, n_more: int):
+        """Room for n_more further scar patterns (the table is rebuilt at a larger size when needed)."""
+        N.check(self._L.scar_table_reserve(self._ctx, int(n_more)))
 
     # ---- device-resident path -------------------------------------------------------------------
     def make_resident(self, reads, f0=None, f1=None):

@@ -610,14 +610,9 @@ def test_index_sequences_with_non_acgt_symbols():
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["c3_12_targets_mh", "ragged_hr_donor", "truseq", "ramsden"])
-def test_dropin_glue_on_gpu_from_fastq_file(name, tmp_path):
-    """scarmapper_b200.dropin.batched_consensus_demultiplex with the REAL engine, fed from a gz FASTQ file
-    and the reference's input file formats, driven through stand-ins for the reference objects it touches
-    (index_dict, target_dict, phase_dict, args, a FastaFile reader).  What it hands back - read_count_dict,
-    phase_count, per-sample SampleResult (counters, table with the first read's sub_list) - must equal what the
-    unmodified reference driver produced (golden).  (The files, Raw_Data included, are compared by
-    tests/test_dropin_forking_pool.py through the launcher.)"""
+def run_dropin_demultiplex(name, tmp_path):
+    """dropin.batched_consensus_demultiplex with the REAL engine on one golden case, driven through stand-ins for the
+    reference objects it touches; returns the DataProcessing stand-in (+ .indexed, .golden)."""
     import argparse
     import collections
     import sys
@@ -670,7 +665,21 @@ def test_dropin_glue_on_gpu_from_fastq_file(name, tmp_path):
         phase_count=collections.defaultdict(lambda: collections.defaultdict(int)),
         read_count_dict=collections.defaultdict(), sequence_dict=collections.defaultdict(list), read_count=0,
         fastq1=types.SimpleNamespace(input_file=args.FASTQ1))
-    indexed, lower_limit = dropin.batched_consensus_demultiplex(dp, module)
+    dp.indexed, dp.lower_limit = dropin.batched_consensus_demultiplex(dp, module)
+    dp.golden = golden
+    return dp
+
+
+@pytest.mark.parametrize("name", ["c3_12_targets_mh", "ragged_hr_donor", "truseq", "ramsden"])
+def test_dropin_glue_on_gpu_from_fastq_file(name, tmp_path):
+    """scarmapper_b200.dropin.batched_consensus_demultiplex with the REAL engine, fed from a gz FASTQ file
+    and the reference's input file formats, driven through stand-ins for the reference objects it touches
+    (index_dict, target_dict, phase_dict, args, a FastaFile reader).  What it hands back - read_count_dict,
+    phase_count, per-sample SampleResult (counters, table with the first read's sub_list) - must equal what the
+    unmodified reference driver produced (golden).  (The files, Raw_Data included, are compared by
+    tests/test_dropin_forking_pool.py through the launcher.)"""
+    dp = run_dropin_demultiplex(name, tmp_path)
+    golden, indexed = dp.golden, dp.indexed
     assert dp.read_count == golden["read_count"]
     assert dict(dp.read_count_dict) == golden["read_count_dict"]
     # (data_output later touches phase_count[key] for every sample, leaving empty dicts on non-Illumina runs)
