@@ -7,8 +7,8 @@ t0=time.perf_counter()
 import torch
 torch.zeros(1, device='cuda'); torch.cuda.synchronize()
 print('cuda init', time.perf_counter()-t0)
-cfg = synth.make_config("C2", n_reads=60000, seed=1)
-b = cfg.generate(0, 60000)
+cfg = synth.make_config("C2", n_reads=int(os.environ.get("PROBE_READS", "60000")), seed=1)
+b = cfg.generate(0, cfg.n_reads)
 reads = cfg.reads_as_strings(b); f0, f1 = cfg.fields_as_strings(b)
 text = fastq_text(reads, f0, f1, odd=False)
 p='/dev/shm/probe.fastq.gz'

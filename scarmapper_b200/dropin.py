@@ -339,7 +339,7 @@ def batched_consensus_demultiplex(self, module, device=0):
                 self.phase_count[key]["No Read 1 Phasing"] += int(phase_hist[s, 0, 0])
 
     stage("per_sample_results_and_raw_data")
-    log.info("Batched path: {} reads, {} scar patterns; ".format(batch.n, int(tab_first.size)) +
+    log.info("Batched path: {} reads, {} scar patterns; ".format(self.read_count, int(tab_first.size)) +
              ", ".join("{} {:.2f} s".format(k, v) for k, v in STAGE_SECONDS.items()))
 
     # ---- lower limit for plots (:1003-1024, unchanged arithmetic)

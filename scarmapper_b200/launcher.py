@@ -93,6 +93,18 @@ def main(argv=None):
         raise SystemExit("--reference must point at a ScarMapper checkout (the directory holding scarmapper.py)")
     start_time = time.time()
     sys.path.insert(0, own.reference)
+    # CUDA context creation (~1 s on a fresh process) runs beside the imports of the reference's modules (scipy alone
+    # takes as long); the thread has long finished when the reference forks its pool
+    import threading
+    from scarmapper_b200 import _native
+
+    def _warm_device():
+        try:
+            _native.lib().scar_device_memory(own.device, None, None)
+        except Exception:       # a missing library / device is reported by the first real call
+            pass
+    warm = threading.Thread(target=_warm_device, daemon=True)
+    warm.start()
 
     # deviation 2: the reference imports `scarmapper.SlidingWindow` at module import
     import scarmapper                                   # the reference package
@@ -117,6 +129,7 @@ def main(argv=None):
         input_file = consensus
 
     dropin.install(INDEL_Processing, device=own.device)
+    warm.join()
     sample_manifest = Tool_Box.FileParser.indices(log, args.SampleManifest)
     processing = INDEL_Processing.DataProcessing(log, args, run_start, INDEL_Processing.__version__,
                                                  TargetMapper.TargetMapper(log, args, sample_manifest), _Fastq(), None)
