@@ -52,7 +52,9 @@ cudaError_t scar_launch_homeology(const scar_ragged &cons, const scar_ragged &in
     P.clj = clj; P.crj = crj; P.tlj = tlj; P.trj = trj; P.target_idx = target_idx; P.n_targets = n_targets; P.n = n;
     P.out = reinterpret_cast<ScarHomeology *>(out);
     int64_t blocks = (n + 127) / 128;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    int dev = 0, sms = 148;                              // grid: at most 16 CTAs of 128 threads per SM of this device
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
     scar_homeology_kernel<<<(unsigned)blocks, 128, 0, stream>>>(P);
     return cudaGetLastError();
 }

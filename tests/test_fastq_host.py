@@ -57,3 +57,54 @@ def test_indexer_errors_where_the_reference_raises():
         fastq.index_text(np.frombuffer(b"@a:ACGT\nACGT\n+\nIIII\n", dtype=np.uint8))
     ok = fastq.index_text(np.frombuffer(b"@a:ACGT\nACGT\n+\nIIII\n", dtype=np.uint8), want_index_fields=False)
     assert ok.n == 1 and ok.read(0) == "ACGT"
+
+
+def _odd_header_corpus(n=2000, seed=5):
+    rng = random.Random(seed)
+    recs = []
+    for i in range(n):
+        k = rng.choice([0, 1, 30, 150, 151, 300])
+        seq = "".join(rng.choice("ACGTN") for _ in range(k))
+        a = "".join(rng.choice("ACGTN") for _ in range(rng.choice([0, 6, 8, 8, 8, 10])))
+        b = "".join(rng.choice("ACGT") for _ in range(rng.choice([0, 8, 8, 9])))
+        extra = rng.choice(["", "+TAIL", "+X+Y", " "])
+        pad = rng.choice(["", " ", "\t"])
+        eol = rng.choice(["\n", "\r\n"])
+        recs.append("@{}M0:{}:x y:N:0:{}+{}{}{}{}{}{}+{}{}{}".format("@" * rng.randint(0, 2), i, a, b, extra, eol,
+                                                                  seq, pad, eol, eol, "I" * k, eol))
+    return "".join(recs)
+
+
+def test_indexer_matches_the_reference_fastq_reader_on_gzip(tmp_path):
+    """The importable reference itself: Valkyries.FASTQ_Tools.FASTQ_Reader (gzip branch - its text branch opens the
+    file in mode 'rU', which Python 3.11+ rejects) driven the way consensus_demultiplex drives it
+    (next(fastq1.seq_read()), INDEL_Processing.py:900-903), plus the header split of index_matching (:1155-1156), on
+    a corpus of odd headers, CRLF line ends, padded sequence lines and empty reads.  scarmapper_b200.fastq.load must
+    deliver the same sequences and index fields."""
+    import gzip
+    from oracle import ref_shims
+    if not ref_shims.available():
+        pytest.skip("reference tree not present")
+    ref_shims.install()
+    from Valkyries import FASTQ_Tools
+    for final_newline in (True, False):
+        text = _odd_header_corpus()
+        if not final_newline:
+            text = text.rstrip("\r\n")
+        path = str(tmp_path / "odd_{}.fastq.gz".format(int(final_newline)))
+        with gzip.open(path, "wb") as f:
+            f.write(text.encode())
+        reader = FASTQ_Tools.FASTQ_Reader(path, None)
+        want = []
+        while True:
+            try:
+                r = next(reader.seq_read())
+            except StopIteration:
+                break
+            parts = r.name.split(":")[-1].split("+")
+            want.append((r.seq, parts[0], parts[1]))
+        fb = fastq.load(path)
+        assert fb.n == len(want) == 2000
+        for i, (seq, a, b) in enumerate(want):
+            assert fb.read(i) == seq, i
+            assert fb.f0.item(i).decode() == a and fb.f1.item(i).decode() == b, i
