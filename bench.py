@@ -793,6 +793,9 @@ def main():
                              "issue_active_pct_of_peak": prof.get("issue_active_pct_of_peak"),
                              "dram_throughput_pct_of_peak": prof.get("dram_throughput_pct_of_peak"),
                              "warp_instructions_per_read": prof.get("warp_instructions_per_read"),
+                             "warp_instructions_per_cycle_per_smsp": prof.get("warp_instructions_per_cycle_per_smsp"),
+                             "best_mixed_integer_issue_rate_measured": prof.get("best_mixed_integer_issue_rate_measured"),
+                             "issue_rate_source": prof.get("issue_rate_source"),
                              "source": prof.get("source", "ncu --set full under profiles/ (not measured in this run)")}
             except Exception:
                 traffic = None
