@@ -124,6 +124,21 @@ def test_fastq_file_matches_the_host_indexed_path(kind, threads, case, tmp_path,
     eng.close()
 
 
+def test_fastq_file_three_kernel_path_grows_its_packed_batch(case, tmp_path, monkeypatch):
+    """SCAR_NO_FUSE=1: K1 -> K3 -> K4 with the packed batch in HBM; the context starts at 48 nt, so the packed buffers
+    are re-planned for 150-nt reads in mid-file."""
+    monkeypatch.setenv("SCAR_NO_FUSE", "1")
+    monkeypatch.setenv("SCAR_FASTQ_FILE_PIECE_BYTES", str(1 << 18))
+    path = str(tmp_path / "reads.fastq")
+    write_source("text", case["text"], path)
+    eng = engine_for(case["pin"], 48, table_capacity=1 << 12)
+    assert not eng.info()["fused"]
+    run = eng.process_fastq_file(path)
+    assert run.records.tobytes() == case["want"].tobytes()
+    assert eng.table().tobytes() == case["ref"]["table"].tobytes()
+    eng.close()
+
+
 def test_fastq_file_record_limit_empty_file_and_last_record_without_newline(case, tmp_path):
     text = case["text"].rstrip(b"\r\n")
     path = str(tmp_path / "r.fastq.gz")
