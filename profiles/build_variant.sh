@@ -8,5 +8,5 @@ NAME=$1; shift
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -cudart static $@ \
      -c scarmapper_b200/csrc/scar_window.cu -o /tmp/scar_window_$NAME.o
 OBJS=$(ls scarmapper_b200/csrc/*.o | grep -v scar_window.o)
-nvcc -shared -cudart static -gencode arch=compute_100a,code=sm_100a -o gpurun_variants/$NAME.so $OBJS /tmp/scar_window_$NAME.o
+nvcc -shared -cudart static -gencode arch=compute_100a,code=sm_100a -o gpurun_variants/$NAME.so $OBJS /tmp/scar_window_$NAME.o -lz -lpthread
 echo gpurun_variants/$NAME.so

@@ -494,8 +494,10 @@ __device__ __forceinline__ ChunkDesc chunk_desc(const scar_ragged &seq, int64_t 
         lo = (unsigned long long)(uintptr_t)seq.bytes + (unsigned long long)seq.offsets[r0];
         hi = (unsigned long long)(uintptr_t)seq.bytes + (unsigned long long)(seq.lengths ? seq.offsets[r1] + seq.lengths[r1] : seq.offsets[r1 + 1]);
     } else {
+        // fixed stride: every read owns `stride` bytes of the buffer, so the span may end at the last read's stride
+        // boundary whatever its length (no load of lengths[r1] in front of the copy)
         lo = (unsigned long long)(uintptr_t)seq.bytes + (unsigned long long)(r0 * seq.stride);
-        hi = lo + (unsigned long long)((r1 - r0) * seq.stride) + (unsigned long long)(seq.lengths ? seq.lengths[r1] : (int)seq.stride);
+        hi = lo + (unsigned long long)((r1 - r0 + 1) * seq.stride);
     }
     d.lo16 = lo & ~15ull;
     if (hi > d.lo16) {
@@ -689,15 +691,21 @@ scar_window_kernel(const K3Params P)
     // the back - and are then worked off in rounds by WHICHEVER thread comes next (batch step + anchor step,
     // re-queued while open), so every warp of a round runs one code path with all lanes busy instead of
     // waiting for the slowest read of the warp.  Phase 3 is one thread per read again: junction call, record.
-    __shared__ uint32_t g_left[GMAX][K3_TILE], g_right[GMAX][K3_TILE];   // clj | tlj << 16,  crj | trj << 16
-    __shared__ uint32_t g_ctx[GMAX][K3_TILE];                            // stored length | target id << 16
-    __shared__ uint32_t g_queue[GMAX][2][2 * K3_TILE];                   // item = local read | p << 8
-    __shared__ uint32_t g_count[GMAX][3][2];                             // [round % 3][side]
-    __shared__ unsigned int g_unassigned[GMAX];                          // fused: aggregation
-    uint32_t *s_left = g_left[group], *s_right = g_right[group], *s_ctx = g_ctx[group];
-    uint32_t (*s_queue)[2 * K3_TILE] = g_queue[group];
-    uint32_t (*s_count)[2] = g_count[group];
-    unsigned int &s_unassigned = g_unassigned[group];
+    // (one struct per group: every access is one base register + a constant offset)
+    struct GroupState {
+        uint32_t left[K3_TILE], right[K3_TILE];     // clj | tlj << 16,  crj | trj << 16
+        uint32_t ctx[K3_TILE];                      // stored length | target id << 16
+        uint32_t queue[2][2 * K3_TILE];             // item = local read | p << 8
+        uint32_t count[3][2];                       // [round % 3][side]
+        unsigned int unassigned;                    // fused: aggregation
+        uint32_t pad;
+    };
+    __shared__ GroupState g_state[GMAX];
+    GroupState &G = g_state[group];
+    uint32_t *s_left = G.left, *s_right = G.right, *s_ctx = G.ctx;
+    uint32_t (*s_queue)[2 * K3_TILE] = G.queue;
+    uint32_t (*s_count)[2] = G.count;
+    unsigned int &s_unassigned = G.unassigned;
     if (tx < 6) s_count[tx >> 1][tx & 1] = 0;
 
     // ---- fused: accumulators of the aggregation, the warps' raw rings and their mbarriers
