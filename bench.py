@@ -108,6 +108,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(gpu_index):
+    """One rank per GPU: run on (and first-touch the pinned host buffers from) the CPUs NVML names as local to this GPU, so
+    that the H2D copies of the end-to-end arm do not all cross one socket.  Returns the CPU list, or None when NVML cannot
+    tell / the process may not change its affinity (a no-op on boxes whose GPUs all hang off one NUMA node)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(set(cpus) & allowed)
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+        return cpus or None
+    except Exception:
+        return None
+
+
 def build_case(args, rank, world):
     import numpy as np
     import synth
@@ -340,6 +359,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -845,6 +865,8 @@ def main():
             line["pattern_searches"] = pattern_searches
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+        if affinity:
+            line["config"]["rank0_cpu_affinity"] = "{} CPUs local to the GPU (NVML)".format(len(affinity))
         if merge_check:
             line["merge_check"] = merge_check
             line["config"]["sm_reserved_for_merge"] = sm_reserve
