@@ -38,6 +38,9 @@ ERRORS = {-1: "SCAR_ERR_CUDA", -2: "SCAR_ERR_INVALID", -3: "SCAR_ERR_UNSUPPORTED
           -5: "SCAR_ERR_NOMEM", -6: "SCAR_ERR_HASH_COLLISION"}
 
 
+ERR_NOMEM = -5
+
+
 class ScarError(RuntimeError):
     def __init__(self, code, text):
         super().__init__("{} ({}): {}".format(ERRORS.get(code, "SCAR_ERR"), code, text))

@@ -70,7 +70,12 @@ template <typename T> static inline int ensure(T **p, size_t *cap, size_t need)
     if (*p) CU(cudaFree(*p));
     *p = nullptr;
     size_t n = std::max<size_t>(need + need / 8, 256);
-    CU(cudaMalloc((void **)p, n * sizeof(T)));
+    if (cudaError_t e = cudaMalloc((void **)p, n * sizeof(T)); e != cudaSuccess) {
+        *p = nullptr; *cap = 0;
+        cudaGetLastError();
+        return scar_fail(e == cudaErrorMemoryAllocation ? SCAR_ERR_NOMEM : SCAR_ERR_CUDA, "no device memory for %zu bytes: %s",
+                         n * sizeof(T), cudaGetErrorString(e));
+    }
     *cap = n;
     return SCAR_OK;
 }
@@ -82,7 +87,11 @@ template <typename T> static inline int ensure_keep(T **p, size_t *cap, size_t n
     if (need <= *cap && *p) return SCAR_OK;
     T *q = nullptr;
     const size_t n = std::max<size_t>(need + need / 4, 256);
-    CU(cudaMalloc((void **)&q, n * sizeof(T)));
+    if (cudaError_t e = cudaMalloc((void **)&q, n * sizeof(T)); e != cudaSuccess) {
+        cudaGetLastError();
+        return scar_fail(e == cudaErrorMemoryAllocation ? SCAR_ERR_NOMEM : SCAR_ERR_CUDA, "no device memory for %zu bytes: %s",
+                         n * sizeof(T), cudaGetErrorString(e));
+    }
     if (*p && keep) CU(cudaMemcpy(q, *p, keep * sizeof(T), cudaMemcpyDeviceToDevice));
     if (*p) CU(cudaFree(*p));
     *p = q; *cap = n;

@@ -18,6 +18,7 @@
 // it could pass half full (scar_table_reserve).  With scar_ctx_set_verify the whole run - the text stays resident -
 // is checked key by key afterwards (exact-or-fail scar-pattern identity).
 #include <atomic>
+#include <cstdint>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -415,6 +416,9 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
     auto drain = [&](int code) { cudaStreamSynchronize(sc); cudaStreamSynchronize(s); return code; };
 
     const int want = c->platform == SCAR_PLATFORM_ILLUMINA;
+    // the text stays resident: a cap below the device's own limit (and the way the tests reach the out-of-memory exit)
+    int64_t text_limit = INT64_MAX;
+    if (const char *e = getenv("SCAR_FASTQ_FILE_MAX_TEXT_BYTES")) { const long long v = atoll(e); if (v > 0) text_limit = v; }
     int64_t n_bytes = 0, nl_total = 0, rec_done = 0;
     uint8_t last_byte = '\n';
     int32_t *d_maxlen = reinterpret_cast<int32_t *>(c->d_acc + 4);           // spare accumulator word (after export_n)
@@ -430,6 +434,8 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
         last = pc->last;
         const int64_t len = pc->len, b0 = n_bytes;
         if (len > 0) {
+            if (b0 + len > text_limit)
+                return drain(scar_fail(SCAR_ERR_NOMEM, "FASTQ text larger than SCAR_FASTQ_FILE_MAX_TEXT_BYTES=%lld", (long long)text_limit));
             if ((size_t)(b0 + len) + 64 > c->text_cap) {                       // grow the device text (rare: streams idle first)
                 cudaStreamSynchronize(sc); cudaStreamSynchronize(s);
                 if ((rc = ensure_keep(&c->d_text, &c->text_cap, (size_t)((double)(b0 + len) * 1.5) + 4096, (size_t)b0))) return drain(rc);

@@ -231,8 +231,15 @@ def batched_consensus_demultiplex(self, module, device=0):
             counters, unassigned = eng.counters()
             phase_hist = eng.phase_hist()
             table = eng.table()                 # sorted by (sample, first_idx): per-sample first-seen order
+        except N.ScarError as exc:
+            if exc.code != N.ERR_NOMEM:
+                raise
+            # the text does not fit the device: the host loader below feeds the GPU in chunks instead
+            log.warning("FASTQ text does not fit the device ({}); reading it on the host and processing in chunks".format(exc))
+            streaming = False
         finally:
             eng.close()
+    if streaming:
         stage("fastq_stream_gpu_classify_aggregate")
     else:
         batch = fastq.load(self.fastq1.input_file, want_index_fields=args.Platform == "Illumina", limit=limit)

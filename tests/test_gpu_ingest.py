@@ -231,16 +231,19 @@ def test_dropin_streams_the_file_and_matches_the_host_loader(name, tmp_path):
     import test_gpu_parity as tgp
     from scarmapper_b200 import dropin
     results = []
-    for ingest in (True, False):
-        dropin.FILE_INGEST[0] = ingest
+    for ingest in (True, False, "too large"):
+        dropin.FILE_INGEST[0] = bool(ingest)
+        if ingest == "too large":          # the text does not fit the device: the drop-in falls back to the host loader
+            os.environ["SCAR_FASTQ_FILE_MAX_TEXT_BYTES"] = "100000"
         try:
-            sub = tmp_path / ("a" if ingest else "b")
+            sub = tmp_path / str(ingest).replace(" ", "_")
             sub.mkdir()
             dp = tgp.run_dropin_demultiplex(name, sub)
         finally:
             dropin.FILE_INGEST[0] = True
-        assert ("fastq_stream_gpu_classify_aggregate" in dropin.STAGE_SECONDS) == ingest
+            os.environ.pop("SCAR_FASTQ_FILE_MAX_TEXT_BYTES", None)
+        assert ("fastq_stream_gpu_classify_aggregate" in dropin.STAGE_SECONDS) == (ingest is True)
         results.append((dp.read_count, dict(dp.read_count_dict), {k: dict(v) for k, v in dp.phase_count.items()},
                         {iid: (r.counters.tolist(), r.counts.tolist(), r.first_records.tobytes(), r.first_bytes.tobytes(),
                                r.pattern_out.tolist()) for iid, r in dp.sequence_dict.items()}))
-    assert results[0] == results[1]
+    assert results[0] == results[1] == results[2]

@@ -659,7 +659,7 @@ def run_dropin_demultiplex(name, tmp_path):
 
     from scipy import stats
     module = types.SimpleNamespace(pysam=types.SimpleNamespace(FastaFile=Fasta), pyfaidx=None, stats=stats)
-    log = types.SimpleNamespace(info=lambda *a: None, error=lambda *a: None)
+    log = types.SimpleNamespace(info=lambda *a: None, error=lambda *a: None, warning=lambda *a: None)
     dp = types.SimpleNamespace(
         args=args, log=log, index_dict=index_dict, target_dict=target_dict, phase_dict=phase_dict,
         phase_count=collections.defaultdict(lambda: collections.defaultdict(int)),
