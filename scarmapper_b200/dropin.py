@@ -128,7 +128,7 @@ def _rcomp(s: str) -> str:
     return s.encode("latin-1").translate(_COMP)[::-1].decode("latin-1")
 
 
-def pattern_search_batch(records, reads, platform, first, sample_of, sample_target, targets, target_rc, device):
+def pattern_search_batch(records, reads, platform, first, sample_of, sample_target, targets, target_rc, device, gathered=None):
     """homeology_search + templated_insertion_search (INDEL_Processing.py:550-700) for every scar pattern of the run
     in ONE batched call.  Pattern k is represented by its first read `first[k]` (record + stored sequence); the
     arguments are derived per pattern exactly as frequency_output derives them (:299-328, incl. the swaps and
@@ -139,7 +139,10 @@ def pattern_search_batch(records, reads, platform, first, sample_of, sample_targ
         return np.zeros((0, 16), np.int32)
     tix = np.asarray(sample_target, dtype=np.int32)[sample_of]
     rc = np.asarray(target_rc, dtype=bool)[tix]
-    cons, off = _engine.stored_gather(reads, first, platform, flip=rc.astype(np.uint8) if rc.any() else None)
+    if gathered is not None and not rc.any():
+        cons, off = gathered                # the first reads as already gathered by the caller (no 3'-strand guide: no flips)
+    else:
+        cons, off = _engine.stored_gather(reads, first, platform, flip=rc.astype(np.uint8) if rc.any() else None)
     L = np.diff(off).astype(np.int64)
     rec = records[first]
     clj, crj = rec["clj"].astype(np.int64), rec["crj"].astype(np.int64)
@@ -271,22 +274,24 @@ def batched_consensus_demultiplex(self, module, device=0):
         stage("gpu_classify_aggregate")
 
     # ---- unpack into the reference's bookkeeping
-    assigned = records["status"] != N.ST_UNASSIGNED
-    samples = records["sample"].astype(np.int64)
     n_samples = len(sample_ids)
+    n_assigned = int(counters[:, N.CT_ASSIGNED].sum())
     # read_count_dict: a key appears once the manifest loop has visited it (:1173-1174)
-    last_visited = n_samples - 1 if unassigned else (int(samples[assigned].max()) if assigned.any() else -1)
+    seen = np.nonzero(counters[:, N.CT_ASSIGNED])[0]
+    last_visited = n_samples - 1 if unassigned else (int(seen[-1]) if seen.size else -1)
     for s in range(last_visited + 1):
         self.read_count_dict[sample_ids[s]] = int(counters[s, N.CT_ASSIGNED])
     if unassigned:
         self.read_count_dict["unidentified"] = int(unassigned)
 
-    # sequence_dict in order of each sample's first read (dict insertion order, :946)
-    first_of = {}
-    idx = np.nonzero(assigned)[0]
-    if idx.size:
-        u, first = np.unique(samples[idx], return_index=True)
-        first_of = {int(s): int(idx[f]) for s, f in zip(u, first)}
+    # sequence_dict in order of each sample's first read (dict insertion order, :946).  One pass, no sort: a fancy
+    # assignment keeps the LAST value written to a repeated index, so writing the read numbers in descending order
+    # leaves every sample's first read.
+    samples16 = np.ascontiguousarray(records["sample"])              # unidentified reads carry SCAR_SAMPLE_NONE
+    first_read = np.full(N.SAMPLE_NONE + 1, -1, dtype=np.int64)
+    first_read[samples16[::-1]] = np.arange(samples16.size - 1, -1, -1, dtype=np.int64)
+    first_of = {int(s): int(first_read[s]) for s in np.nonzero(first_read[:n_samples] >= 0)[0]}
+    samples = None                                                   # (int64 copy: only the optional writers need it)
 
     # ---- per-pattern work of the whole run, in the parent: first reads gathered once, searches in one GPU call
     tab_sample = table["sample"].astype(np.int64)
@@ -295,12 +300,13 @@ def batched_consensus_demultiplex(self, module, device=0):
     first_bytes, first_off = _gather(batch.seq, tab_first, args.Platform)
     stage("unpack")
     pattern_out = pattern_search_batch(records, batch.seq, args.Platform, tab_first, tab_sample, sample_target, targets,
-                                       target_rc, device)
+                                       target_rc, device, gathered=(first_bytes, first_off))
     stage("gpu_pattern_searches")
     # scarred reads bucketed by sample once (stable: read order inside a sample)
     scar_rows, scar_bounds = None, None
     if args.OutputRawData:
         scar_idx = np.nonzero(records["status"] == N.ST_SCAR)[0]
+        samples = samples16.astype(np.int64)
         order = np.argsort(samples[scar_idx], kind="stable")
         scar_rows = scar_idx[order].astype(np.int64)
         scar_bounds = np.searchsorted(samples[scar_rows], np.arange(n_samples + 1))
@@ -361,7 +367,7 @@ def batched_consensus_demultiplex(self, module, device=0):
         lower_limit = float("NaN")
     if math.isnan(lower_limit):
         lower_limit = args.PatternThreshold * 0.00001
-    return int(assigned.sum()), lower_limit
+    return n_assigned, lower_limit
 
 
 def _gather(reads, rows, platform):
