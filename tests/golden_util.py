@@ -23,14 +23,17 @@ def _all_names():
     return sorted(os.path.basename(p)[:-len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.json.gz")))
 
 
+_VECTOR_FILES = ("alignment_cases", "homeology_cases")       # per-function vectors, not runs of the reference driver
+
+
 def golden_names():
     """The per-read / per-table fixtures (one reference run each)."""
-    return [n for n in _all_names() if n != "alignment_cases" and not n.startswith("demux_")]
+    return [n for n in _all_names() if n not in _VECTOR_FILES and not n.startswith("demux_")]
 
 
 def launcher_golden_names():
     """Fixtures whose output FILES are compared through the launcher: the above plus the --Demultiplex True runs."""
-    return [n for n in _all_names() if n != "alignment_cases"]
+    return [n for n in _all_names() if n not in _VECTOR_FILES]
 
 
 def load(name):
