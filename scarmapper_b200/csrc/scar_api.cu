@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <string>
 #include <vector>
@@ -1315,6 +1316,9 @@ extern "C" int scar_homeology_batch(int32_t device, const scar_ragged *consensus
     CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(SCAR_ERR_CUDA, "CUDA device %d not present", device);
     CU(cudaSetDevice(device));
+    const bool trace = getenv("SCAR_TRACE") != nullptr;
+    auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; };
+    const double t0 = now();
     StagedList dc, di, dt, dr;
     DevInts a, b, c, d, e;
     int rc;
@@ -1324,9 +1328,16 @@ extern "C" int scar_homeology_batch(int32_t device, const scar_ragged *consensus
         return rc;
     int32_t *dout = nullptr;
     if (cudaMalloc((void **)&dout, (size_t)n * 16 * sizeof(int32_t)) != cudaSuccess) return fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
+    if (trace) CU(cudaDeviceSynchronize());
+    const double t1 = now();
     cudaError_t err = scar_launch_homeology(dc.dev, di.dev, dt.dev, dr.dev, a.p, b.p, c.p, d.p, e.p, n_targets, n, dout, nullptr);
+    if (err == cudaSuccess && trace) err = cudaDeviceSynchronize();
+    const double t2 = now();
     if (err == cudaSuccess) err = cudaMemcpy(out, dout, (size_t)n * 16 * sizeof(int32_t), cudaMemcpyDeviceToHost);
     cudaFree(dout);
+    if (trace)
+        fprintf(stderr, "[scar homeology] %lld patterns: staged %.1f ms, kernel %.1f ms, results %.1f ms\n", (long long)n,
+                1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (now() - t2));
     if (err != cudaSuccess) return fail(SCAR_ERR_CUDA, "homeology kernel failed: %s", cudaGetErrorString(err));
     return SCAR_OK;
 }
