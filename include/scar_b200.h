@@ -262,6 +262,16 @@ int scar_process_fastq_file(scar_ctx *ctx, const char *path, int64_t record_limi
                             int32_t n_threads, int32_t keep_text, scar_fastq_run *run);
 void scar_fastq_run_release(scar_fastq_run *run);
 
+/* The inflate in front of that loader, on its own: ONE gzip stream (or several members back to back, zero padding
+ * allowed) -> text, by n_threads threads (<= 0: up to 8).  Replaces gzip.open() in FASTQ_Reader
+ * (Valkyries/FASTQ_Tools.py:571-575).  The stream is cut into chunks of chunk_bytes compressed bytes (<= 0: chosen);
+ * every chunk guesses a block start and decodes with an unknown 32 KiB window, a second pass resolves the windows in
+ * order (csrc/scar_pgzip.h).  Exact or fail: every chunk must start on the bit where the one before it ended, every
+ * member's CRC-32 and length are checked.  Host memory only, no CUDA.  stats (optional, 4 values): chunks, chunks whose
+ * guessed start was taken, chunks decoded again, threads.  The text must fit out_capacity. */
+int scar_gunzip_host(const uint8_t *gz, int64_t gz_bytes, int32_t n_threads, int64_t chunk_bytes, uint8_t *out,
+                     int64_t out_capacity, int64_t *out_bytes, int64_t *stats);
+
 /* Room for n_more further scar patterns: rebuilds the table at a larger power of two when it would pass half full
  * (entries re-inserted through the claimed-slot list; first-seen indices and counts kept).  Synchronises the device. */
 int scar_table_reserve(scar_ctx *ctx, int64_t n_more);

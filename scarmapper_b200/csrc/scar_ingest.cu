@@ -34,6 +34,7 @@
 #include <zlib.h>
 
 #include "scar_ctx.cuh"
+#include "scar_pgzip.h"
 
 namespace {
 
@@ -300,6 +301,28 @@ void produce_gzip(Stream &S, Workers &W, const MappedFile &F, HostText *keep)
     inflateEnd(&zs);
 }
 
+// one gzip stream (or several members) inflated by n_threads threads: two-pass speculative decoding, scar_pgzip.h
+void produce_gzip_parallel(Stream &S, Workers &W, const MappedFile &F, HostText *keep, int n_threads)
+{
+    scar_pgzip::ParallelGunzip pg(F.p, F.n, n_threads, 0);
+    bool finished = false;
+    while (!finished) {
+        Piece *pc = S.acquire_free();
+        if (!pc) break;
+        int64_t got = 0;
+        while (got < S.cap) {
+            const int64_t r = pg.read(pc->buf + got, S.cap - got);
+            if (r < 0) { S.fail(pg.error()); return; }
+            if (r == 0) { finished = true; break; }
+            got += r;
+        }
+        pc->len = got;
+        pc->last = finished;
+        if (keep && got && !keep->append(W, pc->buf, got)) { S.fail("out of host memory for the inflated text"); return; }
+        S.publish();
+    }
+}
+
 void produce_bgzf(Stream &S, Workers &W, const MappedFile &F, const std::vector<BgzfBlock> &blocks, HostText *keep)
 {
     size_t b0 = 0;
@@ -342,6 +365,29 @@ void produce_bgzf(Stream &S, Workers &W, const MappedFile &F, const std::vector<
 
 }   // namespace
 
+extern "C" int scar_gunzip_host(const uint8_t *gz, int64_t gz_bytes, int32_t n_threads, int64_t chunk_bytes, uint8_t *out,
+                                int64_t out_capacity, int64_t *out_bytes, int64_t *stats)
+{
+    if (!gz || gz_bytes < 0 || (!out && out_capacity > 0) || !out_bytes) return scar_fail(SCAR_ERR_INVALID, "bad argument");
+    *out_bytes = 0;
+    if (n_threads <= 0) n_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    scar_pgzip::ParallelGunzip pg(gz, gz_bytes, std::min(n_threads, 64), chunk_bytes);
+    int64_t got = 0;
+    uint8_t spill[4096];
+    for (;;) {
+        // (one more read once the buffer is full: the end of the stream, or text that does not fit)
+        const bool full = got >= out_capacity;
+        const int64_t r = full ? pg.read(spill, sizeof(spill)) : pg.read(out + got, std::min<int64_t>(out_capacity - got, 16 << 20));
+        if (r < 0) return scar_fail(SCAR_ERR_INVALID, "%s", pg.error().c_str());
+        if (r == 0) break;
+        if (full) return scar_fail(SCAR_ERR_INVALID, "gzip: the text is longer than the output buffer (%lld bytes)", (long long)out_capacity);
+        got += r;
+    }
+    *out_bytes = got;
+    if (stats) { stats[0] = pg.chunks_total(); stats[1] = pg.chunks_guessed(); stats[2] = pg.chunks_redone(); stats[3] = pg.threads(); }
+    return SCAR_OK;
+}
+
 extern "C" void scar_fastq_run_release(scar_fastq_run *run)
 {
     if (!run) return;
@@ -369,7 +415,9 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
     if (n_threads <= 0) n_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
     n_threads = std::min(n_threads, 64);
     run->source_kind = bgzf ? 2 : gz ? 1 : 0;
-    run->threads = gz && !bgzf ? 1 : n_threads;
+    // a single gzip stream: inflated side by side (scar_pgzip.h) unless the file is small or SCAR_GZIP_SERIAL is set
+    const bool gz_parallel = gz && !bgzf && n_threads > 1 && file.n >= (256 << 10) && !getenv("SCAR_GZIP_SERIAL");
+    run->threads = gz && !bgzf && !gz_parallel ? 1 : n_threads;
 
     // ---- staging pieces: pinned, allocated when the producer first needs them (a small file pays for what it uses),
     // kept in the context between calls.  16 MB keeps the per-piece overheads (two stream synchronisations, ten
@@ -409,6 +457,7 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
     std::thread producer([&] {
         if (file.n == 0) { Piece *pc = S.acquire_free(); if (pc) { pc->len = 0; pc->last = true; S.publish(); } }
         else if (bgzf) produce_bgzf(S, W, file, blocks, keep ? &inflated : nullptr);
+        else if (gz_parallel) produce_gzip_parallel(S, W, file, keep ? &inflated : nullptr, n_threads);
         else if (gz) produce_gzip(S, W, file, keep ? &inflated : nullptr);
         else produce_plain(S, W, file);
     });

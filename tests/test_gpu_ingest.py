@@ -106,6 +106,8 @@ def test_fastq_file_matches_the_host_indexed_path(kind, threads, case, tmp_path,
     run = eng.process_fastq_file(path, threads=threads)
     assert run.source == {"text": "text", "gzip": "gzip", "gzip_members": "gzip", "bgzf": "bgzf"}[kind]
     assert run.n == len(case["reads"]) and run.text_bytes == len(case["text"])
+    if kind.startswith("gzip"):      # one stream inflated by all the threads (csrc/scar_pgzip.h); zlib with one
+        assert run.threads == threads and os.path.getsize(path) > 256 << 10
     assert run.max_seq_len == max(len(r) for r in case["reads"])       # (stripped of white space, as the views are)
     assert run.records.tobytes() == case["want"].tobytes()
     assert run.text.tobytes() == case["text"]
