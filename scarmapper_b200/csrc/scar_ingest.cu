@@ -412,7 +412,8 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
     const bool gz = file.n >= 2 && file.p[0] == 0x1f && file.p[1] == 0x8b;
     std::vector<BgzfBlock> blocks;
     const bool bgzf = gz && scan_bgzf(file.p, file.n, blocks);
-    if (n_threads <= 0) n_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    // (a single gzip stream is inflate-bound: up to 16 threads; copies and BGZF blocks stop gaining at 8)
+    if (n_threads <= 0) n_threads = (int)std::min(gz && !bgzf ? 16u : 8u, std::max(1u, std::thread::hardware_concurrency()));
     n_threads = std::min(n_threads, 64);
     run->source_kind = bgzf ? 2 : gz ? 1 : 0;
     // a single gzip stream: inflated side by side (scar_pgzip.h) unless the file is small or SCAR_GZIP_SERIAL is set

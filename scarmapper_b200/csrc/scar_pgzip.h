@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <time.h>
+#include <sys/mman.h>
 #include <string.h>
 
 #include <atomic>
@@ -164,7 +165,7 @@ struct Tables {
 // bytes a FASTQ / text file is made of: what a guessed block must decode to
 inline bool text_byte(unsigned b) { return (b >= 32 && b < 127) || b == '\n' || b == '\r' || b == '\t'; }
 
-enum { PG_OK = 0, PG_BAD = 1, PG_NOMEM = 2 };
+enum { PG_OK = 0, PG_BAD = 1, PG_NOMEM = 2, PG_MORE = 3 };
 
 // 16-bit symbol buffer with the unknown window in front: sym[0 .. WINDOW) are the markers, output starts at WINDOW
 struct SymBuf {
@@ -180,6 +181,10 @@ struct SymBuf {
         while (c < want) c += c / 2 + (1 << 16);
         uint16_t *q = (uint16_t *)realloc(sym, sizeof(uint16_t) * (size_t)(WINDOW + c + 16));
         if (!q) return false;
+#if defined(MADV_HUGEPAGE)
+        static const bool thp = getenv("SCAR_PGZIP_THP") != nullptr;      // (experiment: transparent huge pages for the symbol buffers)
+        if (thp) madvise((void *)(((uintptr_t)q + 4095) & ~(uintptr_t)4095), (sizeof(uint16_t) * (size_t)(WINDOW + c)) & ~(size_t)4095, MADV_HUGEPAGE);
+#endif
         if (!sym) for (int i = 0; i < WINDOW; ++i) q[i] = (uint16_t)(256 + i);
         sym = q; cap = c;
         return true;
@@ -278,14 +283,14 @@ template <bool CHECK>
 inline int decode_huffman_block(Bits &br, const Tables &T, SymBuf &B, int64_t max_out)
 {
     uint16_t *out = B.out();
-    int64_t n = B.n, room = B.cap - 260;
+    int64_t n = B.n, room = B.cap - 272;
     for (;;) {
-        if (n > room) {
+        if (n > room || (CHECK && n > max_out)) {
             B.n = n;
-            if (CHECK && n > max_out) return PG_BAD;
+            if (CHECK && n > max_out) return PG_MORE;
             if (br.overrun()) return PG_BAD;                // (a truncated stream decodes zeros for ever)
             if (!B.reserve(n + (1 << 20))) return PG_NOMEM;
-            out = B.out(); room = B.cap - 260;
+            out = B.out(); room = B.cap - 272;
         }
         br.refill();
         Entry e = T.lit[br.peek(LIT_PRIM)];
@@ -320,7 +325,9 @@ inline int decode_huffman_block(Bits &br, const Tables &T, SymBuf &B, int64_t ma
         uint16_t *dst = out + n;
         const uint16_t *src = dst - dist;
         n += len;
-        if (dist >= 4) {
+        if (dist >= 8) {
+            for (int k = 0; k < len; k += 8) memcpy(dst + k, src + k, 16);
+        } else if (dist >= 4) {
             for (int k = 0; k < len; k += 4) memcpy(dst + k, src + k, 8);
         } else if (dist == 1) {
             const uint64_t v = 0x0001000100010001ull * (uint64_t)src[0];
@@ -378,15 +385,30 @@ inline uint64_t find_block_start(const uint8_t *in, int64_t n, uint64_t from, ui
         w >>= bit & 7;
         if ((w & 7u) != 4u) continue;                              // bits: final 0, type (LSB first) 0 1 -> value 2
         if (((w >> 3) & 31u) > 29u || ((w >> 8) & 31u) > 29u) continue;
+        if (byte + 17 <= n) {
+            // the code-length code must be complete: sum of 2^(7 - length) over its (HCLEN + 4) three-bit lengths = 128
+            uint64_t hi;
+            memcpy(&hi, in + byte + 8, 8);
+            const int sh = (int)(bit & 7);
+            // bits 17 .. 80 of the stream from `bit` (w holds its first 64 - sh bits)
+            const uint64_t s_lo = sh ? (w | (hi << (64 - sh))) : w, s_hi = hi >> sh;
+            uint64_t v = (s_lo >> 17) | (s_hi << 47);
+            const int hclen = (int)((w >> 13) & 15u) + 4;
+            int sum = 0;
+            for (int i = 0; i < hclen; ++i) { const int l = (int)(v & 7u); v >>= 3; sum += (128 >> l) & 127; }
+            if (sum != 128) continue;
+        }
         Bits br;
         br.init(in, n, bit + 3);
         if (!read_dynamic_header(br, T)) continue;
         scratch.n = 0;
         if (!scratch.reserve(1 << 16)) return UINT64_MAX;
-        if (decode_huffman_block<true>(br, T, scratch, 8 << 20) != PG_OK) continue;
-        if (scratch.n < 64) continue;                              // a real block of a large file holds thousands of symbols
+        // the first 32 K symbols of the block (or all of it, then a block header must follow)
+        const int rc = decode_huffman_block<true>(br, T, scratch, 1 << 15);
+        if (rc == PG_MORE) return bit;
+        if (rc != PG_OK || scratch.n < 64) continue;               // a real block of a large file holds thousands of symbols
         br.refill();
-        if (((br.peek(3) >> 1) & 3u) == 3u) continue;              // what follows must be a block header, too
+        if (((br.peek(3) >> 1) & 3u) == 3u) continue;
         return bit;
     }
     return UINT64_MAX;
@@ -421,7 +443,7 @@ inline void translate(const uint16_t *sym, int64_t n, const uint8_t *window, uin
         }
     }
 #endif
-    for (; i < n; ++i) { const uint16_t s = sym[i]; dst[i] = s < 256 ? (uint8_t)s : window[s - 256]; }
+    for (int64_t k = 0, left = n - i; k < left; ++k) { const uint16_t s = sym[i + k]; dst[i + k] = s < 256 ? (uint8_t)s : window[s - 256]; }
 }
 
 struct MemberEnd { int64_t out_at; uint32_t crc, isize; };          // a member ended after out_at symbols of the chunk
