@@ -1319,6 +1319,9 @@ extern "C" int scar_homeology_batch(int32_t device, const scar_ragged *consensus
     const bool trace = getenv("SCAR_TRACE") != nullptr;
     auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; };
     const double t0 = now();
+    double t1 = t0, t2 = t0, t3 = t0;
+    cudaError_t err = cudaSuccess;
+    {
     StagedList dc, di, dt, dr;
     DevInts a, b, c, d, e;
     int rc;
@@ -1328,16 +1331,18 @@ extern "C" int scar_homeology_batch(int32_t device, const scar_ragged *consensus
         return rc;
     int32_t *dout = nullptr;
     if (cudaMalloc((void **)&dout, (size_t)n * 16 * sizeof(int32_t)) != cudaSuccess) return fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
-    if (trace) CU(cudaDeviceSynchronize());
-    const double t1 = now();
-    cudaError_t err = scar_launch_homeology(dc.dev, di.dev, dt.dev, dr.dev, a.p, b.p, c.p, d.p, e.p, n_targets, n, dout, nullptr);
+    if (trace) cudaDeviceSynchronize();
+    t1 = now();
+    err = scar_launch_homeology(dc.dev, di.dev, dt.dev, dr.dev, a.p, b.p, c.p, d.p, e.p, n_targets, n, dout, nullptr);
     if (err == cudaSuccess && trace) err = cudaDeviceSynchronize();
-    const double t2 = now();
+    t2 = now();
     if (err == cudaSuccess) err = cudaMemcpy(out, dout, (size_t)n * 16 * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    t3 = now();
     cudaFree(dout);
+    }
     if (trace)
-        fprintf(stderr, "[scar homeology] %lld patterns: staged %.1f ms, kernel %.1f ms, results %.1f ms\n", (long long)n,
-                1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (now() - t2));
+        fprintf(stderr, "[scar homeology] %lld patterns: staged %.1f ms, kernel %.1f ms, results %.1f ms, buffers freed %.1f ms\n",
+                (long long)n, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (now() - t3));
     if (err != cudaSuccess) return fail(SCAR_ERR_CUDA, "homeology kernel failed: %s", cudaGetErrorString(err));
     return SCAR_OK;
 }

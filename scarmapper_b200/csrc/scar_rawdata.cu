@@ -8,6 +8,9 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <vector>
+#include <algorithm>
 
 #include "scar_internal.cuh"
 
@@ -132,26 +135,53 @@ extern "C" int scar_raw_rows_indexed_host(const scar_record *records, const scar
 // Stored sequences (platform transform applied) of a list of reads, gathered into one CSR buffer; row k is reverse-
 // complemented when flip[k] != 0 (3'-strand guides: frequency_output works on rcomp(consensus), :312-327).
 // out_off receives n_rows + 1 offsets; call with out = NULL for the size.
+namespace {
+struct CompTable { uint8_t t[256]; CompTable() { for (int i = 0; i < 256; ++i) t[i] = comp((uint8_t)i); } };
+const CompTable COMP_TABLE;
+
+// f(t, lo, hi) over [0, n) on up to 8 threads (row blocks); small jobs stay on the calling thread
+template <class F> void for_row_blocks(int64_t n, F f)
+{
+    const int threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, (int64_t)std::thread::hardware_concurrency()), n / 32768));
+    if (threads <= 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (n + threads - 1) / threads;
+    for (int t = 1; t < threads; ++t) th.emplace_back([=] { f(std::min(n, t * per), std::min(n, (t + 1) * per)); });
+    f(0, std::min(n, per));
+    for (auto &x : th) x.join();
+}
+}   // namespace
+
 extern "C" int scar_stored_gather_host(const scar_ragged *reads, const int64_t *rows, int64_t n_rows, int32_t platform,
                                        const uint8_t *flip, uint8_t *out, int64_t out_capacity, int64_t *out_off)
 {
     if (!reads || (!rows && n_rows) || !out_off || n_rows < 0) return scar_fail(SCAR_ERR_INVALID, "bad argument");
-    std::string stored;
-    int64_t pos = 0;
-    out_off[0] = 0;
-    for (int64_t k = 0; k < n_rows; ++k) {
+    // the stored sequence is a span of the raw read, forwards or as its reverse complement (Ramsden stores rcomp; a
+    // flipped row is complemented once more - comp is an involution, so the two cancel)
+    auto span = [&](int64_t k, const uint8_t *&p, int &len) {
         const uint8_t *raw; int rawlen;
         get_item(*reads, rows[k], raw, rawlen);
-        stored_sequence(raw, rawlen, platform, stored);
-        const int64_t len = (int64_t)stored.size();
-        if (out && pos + len <= out_capacity) {
-            if (flip && flip[k]) for (int64_t i = 0; i < len; ++i) out[pos + i] = comp((uint8_t)stored[(size_t)(len - 1 - i)]);
-            else memcpy(out + pos, stored.data(), (size_t)len);
+        if (platform == SCAR_PLATFORM_TRUSEQ) { p = raw + (rawlen > 6 ? 6 : rawlen); len = rawlen > 12 ? rawlen - 12 : 0; }
+        else { p = raw; len = rawlen; }
+    };
+    out_off[0] = 0;
+    for_row_blocks(n_rows, [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; ++k) { const uint8_t *p; int len; span(k, p, len); out_off[k + 1] = len; }
+    });
+    for (int64_t k = 0; k < n_rows; ++k) out_off[k + 1] += out_off[k];
+    const int64_t total = out_off[n_rows];
+    if (!out) return SCAR_OK;
+    if (total > out_capacity) return scar_fail(SCAR_ERR_INVALID, "stored gather: %lld bytes needed", (long long)total);
+    const bool ramsden = platform == SCAR_PLATFORM_RAMSDEN;
+    for_row_blocks(n_rows, [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; ++k) {
+            const uint8_t *p; int len;
+            span(k, p, len);
+            uint8_t *dst = out + out_off[k];
+            if (ramsden != (flip && flip[k])) for (int i = 0; i < len; ++i) dst[i] = COMP_TABLE.t[p[len - 1 - i]];
+            else memcpy(dst, p, (size_t)len);
         }
-        pos += len;
-        out_off[k + 1] = pos;
-    }
-    if (out && pos > out_capacity) return scar_fail(SCAR_ERR_INVALID, "stored gather: %lld bytes needed", (long long)pos);
+    });
     return SCAR_OK;
 }
 

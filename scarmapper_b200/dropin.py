@@ -27,7 +27,9 @@ from __future__ import annotations
 
 import collections
 import math
+import os
 import statistics
+import sys
 import time
 import types
 
@@ -134,6 +136,7 @@ def pattern_search_batch(records, reads, platform, first, sample_of, sample_targ
     arguments are derived per pattern exactly as frequency_output derives them (:299-328, incl. the swaps and
     reverse complements for 3'-strand guides), vectorised.  Returns int32[n, 16] (struct ScarHomeology)."""
     from . import engine as _engine
+    t0 = time.perf_counter()
     n = int(first.size)
     if n == 0:
         return np.zeros((0, 16), np.int32)
@@ -157,7 +160,12 @@ def pattern_search_batch(records, reads, platform, first, sample_of, sample_targ
     ins = HostRagged.from_views(cons, off[:-1] + np.where(has_ins, a, 0), np.where(has_ins, b - a, 0).astype(np.int32))
     oriented = [_rcomp(t) if r else t for t, r in zip(targets, target_rc)]
     batch = _HOMEOLOGY_BATCH[0] or _engine.homeology_batch
-    return batch(HostRagged(cons, offsets=off), ins, a, b, c, d, tix, oriented, list(targets), device)
+    t1 = time.perf_counter()
+    out = batch(HostRagged(cons, offsets=off), ins, a, b, c, d, tix, oriented, list(targets), device)
+    if os.environ.get("SCAR_TRACE"):
+        print("[scar dropin] pattern_search_batch: {} patterns, arguments {:.1f} ms, batched call {:.1f} ms".format(
+            n, 1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t1)), file=sys.stderr)
+    return out
 
 
 def batched_consensus_demultiplex(self, module, device=0):
