@@ -55,10 +55,33 @@ def _make_engine(prob: ScarProblem, device: int):
     return f(prob, device) if f else ScarEngine(prob, device)
 
 
+INHERIT_RESULTS = [True]      # pool workers take their SampleResult from the memory they were forked with (below)
+_INHERITED = {}               # token -> SampleResult of the current run, filled in the parent BEFORE main_loop forks its pool
+_RUN_SERIAL = [0]
+
+
+def _inherited_result(token, index_name):
+    """Unpickling side of SampleResult.__reduce_ex__: in a worker forked after batched_consensus_demultiplex the
+    registry still holds the parent's objects (copy-on-write pages, nothing travels through the pipe)."""
+    res = _INHERITED.get(token)
+    if res is None:
+        raise RuntimeError("the SampleResult of {} was not inherited by this process (a spawn-type pool?): set "
+                           "scarmapper_b200.dropin.INHERIT_RESULTS[0] = False to send it through the pipe".format(index_name))
+    return res
+
+
 class SampleResult:
     """What the GPU pass produced for ONE sample library; stands in for sequence_dict[index]
     (main_loop only takes its len() and hands it to ScarSearch; INDEL_Processing.py:1051-1053).
-    Plain numpy arrays of this sample's own data, so pickling it to a pool worker costs O(patterns)."""
+    Plain numpy arrays of this sample's own data.  main_loop creates its pool AFTER consensus_demultiplex (:1044-1047),
+    so a forked worker already holds every SampleResult: pickling one sends a token, not the arrays (dill-pickling
+    the ~250 MB of a 10 M-read run cost 0.5 s in the parent alone); INHERIT_RESULTS[0] = False pickles the arrays."""
+    _token = None
+
+    def __reduce_ex__(self, protocol):
+        if self._token is not None and INHERIT_RESULTS[0] and _INHERITED.get(self._token) is self:
+            return (_inherited_result, (self._token, self.index_name))
+        return object.__reduce_ex__(self, protocol)
 
     def __init__(self, index_name, n_reads):
         self.index_name = index_name
@@ -227,7 +250,6 @@ def batched_consensus_demultiplex(self, module, device=0):
         # engine re-plans itself for the longest read and grows its scar table as the patterns arrive.  The text stays
         # resident, so every scarred read's full key is compared with the first read of its table entry at the end
         # (exact-or-fail identity; a mismatch raises instead of merging two scar patterns under one 128-bit tag).
-        import os
         if len(self.fastq1.input_file) < 3 or not os.path.isfile(self.fastq1.input_file):
             raise FileNotFoundError("FASTQ file {} not found".format(self.fastq1.input_file))
         eng = _make_engine(ScarProblem(max_read_len=160, table_capacity=1 << 18, **common), device)
@@ -323,10 +345,14 @@ def batched_consensus_demultiplex(self, module, device=0):
         write_demultiplexed_fastq(self, batch, records, sample_ids)
         stage("demultiplexed_fastq")
 
+    _INHERITED.clear()
+    _RUN_SERIAL[0] += 1
     for s in sorted(first_of, key=first_of.get):
         iid = sample_ids[s]
         t = sample_target[s]
         res = SampleResult(iid, int(counters[s, N.CT_ASSIGNED]))
+        res._token = (os.getpid(), _RUN_SERIAL[0], iid)
+        _INHERITED[res._token] = res
         res.platform = args.Platform
         res.target_region, res.cutsite, res.reverse_comp = targets[t], cutsites[t], target_rc[t]
         res.counters = counters[s].copy()

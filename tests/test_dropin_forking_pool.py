@@ -65,6 +65,37 @@ def test_sample_result_pickles_small():
     assert back.n_patterns() == k and back.first_read(3) == "A" * 150 and len(back) == 1000
 
 
+def test_a_registered_sample_result_travels_as_a_token_to_forked_workers():
+    """main_loop forks its pool after consensus_demultiplex: a worker already holds every SampleResult of the run, so
+    what is pickled is a token (dropin._INHERITED), and a real forked multiprocess.Pool resolves it to the arrays."""
+    import dill
+    import multiprocess
+    import numpy as np
+    from scarmapper_b200 import dropin
+    res = dropin.SampleResult("D502+D703", 77)
+    res.counts = np.arange(5000, dtype=np.uint32)
+    res.first_bytes = np.full(150 * 5000, 67, np.uint8)
+    res.first_off = np.arange(5001, dtype=np.int64) * 150
+    res._token = (os.getpid(), 1, res.index_name)
+    dropin._INHERITED[res._token] = res
+    try:
+        assert len(dill.dumps(res)) < 400
+        assert dill.loads(dill.dumps(res)) is res                      # (same process: the registry answers)
+        with multiprocess.get_context("fork").Pool(2) as pool:          # created AFTER the registration, as in main_loop
+            got = pool.starmap(_probe_result, [[res, 4999], [res, 7]])
+        assert got == [(77, 4999, "C" * 150), (77, 7, "C" * 150)]
+        dropin.INHERIT_RESULTS[0] = False
+        assert len(dill.dumps(res)) > 150 * 5000                      # the arrays themselves
+    finally:
+        dropin.INHERIT_RESULTS[0] = True
+        dropin._INHERITED.clear()
+    assert len(dill.dumps(res)) > 150 * 5000                          # not registered any more: pickled whole
+
+
+def _probe_result(res, k):
+    return len(res), int(res.counts[k]), res.first_read(k)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", gu.launcher_golden_names())
 def test_gpu_launcher_with_forked_workers_writes_the_reference_files(tmp_path, name):
