@@ -262,6 +262,14 @@ int scar_process_fastq_file(scar_ctx *ctx, const char *path, int64_t record_limi
                             int32_t n_threads, int32_t keep_text, scar_fastq_run *run);
 void scar_fastq_run_release(scar_fastq_run *run);
 
+/* Stored sequences (as scar_stored_gather_host: platform transform, row k reverse-complemented when flip[k] != 0) of
+ * the reads `rows` of the run whose text is still resident on the device - the last scar_process_fastq_file of this
+ * context - gathered THERE: only the chosen reads come back (the first read of every scar pattern for
+ * frequency_output, scarmapper/INDEL_Processing.py:299-328), so a caller that needs no other text can run with
+ * keep_text = 0.  out_off receives n_rows + 1 offsets; out = NULL sizes only. */
+int scar_fastq_gather_host(scar_ctx *ctx, const int64_t *rows, int64_t n_rows, const uint8_t *flip, uint8_t *out,
+                           int64_t out_capacity, int64_t *out_off);
+
 /* The inflate in front of that loader, on its own: ONE gzip stream (or several members back to back, zero padding
  * allowed) -> text, by n_threads threads (<= 0: up to 8).  Replaces gzip.open() in FASTQ_Reader
  * (Valkyries/FASTQ_Tools.py:571-575).  The stream is cut into chunks of chunk_bytes compressed bytes (<= 0: chosen);

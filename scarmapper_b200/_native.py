@@ -141,6 +141,7 @@ PROTOTYPES = {
     "scar_frequency_rows_fetch": (C.c_int, [_P, C.c_int64]),
     "scar_process_fastq_file": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(FastqRun)]),
     "scar_fastq_run_release": (None, [C.POINTER(FastqRun)]),
+    "scar_fastq_gather_host": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int64, _P]),
     "scar_gunzip_host": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
     "scar_table_reserve": (C.c_int, [_P, C.c_int64]),
     "scar_alignment_batch": (C.c_int, [C.c_int32, _RP, _RP, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),

@@ -35,6 +35,7 @@
 
 #include "scar_ctx.cuh"
 #include "scar_pgzip.h"
+#include "scar_comp.h"
 
 namespace {
 
@@ -364,6 +365,92 @@ void produce_bgzf(Stream &S, Workers &W, const MappedFile &F, const std::vector<
 }
 
 }   // namespace
+
+// ---- stored sequences of chosen reads, gathered from the text that is resident on the device ----------------------
+namespace {
+__constant__ uint8_t GATHER_COMP[256];
+
+__device__ __forceinline__ void gather_span(int platform, int64_t off, int32_t rawlen, int64_t &a, int32_t &len)
+{
+    if (platform == SCAR_PLATFORM_TRUSEQ) { a = off + (rawlen > 6 ? 6 : rawlen); len = rawlen > 12 ? rawlen - 12 : 0; }
+    else { a = off; len = rawlen; }
+}
+
+__global__ void gather_lengths_kernel(const int64_t *rows, int64_t n, const int32_t *seq_len, int platform, int32_t *out_len)
+{
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t rawlen = seq_len[rows[k]];
+        out_len[k] = platform == SCAR_PLATFORM_TRUSEQ ? (rawlen > 12 ? rawlen - 12 : 0) : rawlen;
+    }
+}
+
+// one warp per row: coalesced stores; a reversed row reads its source backwards through the complement table
+__global__ void gather_rows_kernel(const uint8_t *text, const int64_t *seq_off, const int32_t *seq_len, const int64_t *rows,
+                                   const uint8_t *flip, const int64_t *out_off, int64_t n, int platform, uint8_t *out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t k = warp; k < n; k += n_warps) {
+        const int64_t r = rows[k];
+        int64_t a; int32_t len;
+        gather_span(platform, seq_off[r], seq_len[r], a, len);
+        const bool rev = (platform == SCAR_PLATFORM_RAMSDEN) != (flip && flip[k]);
+        uint8_t *dst = out + out_off[k];
+        const uint8_t *src = text + a;
+        if (rev) for (int i = lane; i < len; i += 32) dst[i] = GATHER_COMP[src[len - 1 - i]];
+        else for (int i = lane; i < len; i += 32) dst[i] = src[i];
+    }
+}
+}   // namespace
+
+extern "C" int scar_fastq_gather_host(scar_ctx *c, const int64_t *rows, int64_t n_rows, const uint8_t *flip, uint8_t *out,
+                                      int64_t out_capacity, int64_t *out_off)
+{
+    if (!c || (!rows && n_rows) || !out_off || n_rows < 0) return scar_fail(SCAR_ERR_INVALID, "bad argument");
+    out_off[0] = 0;
+    if (n_rows == 0) return SCAR_OK;
+    if (!c->d_text || !c->d_fq_seq_off || !c->d_fq_seq_len || c->fq_records_n <= 0)
+        return scar_fail(SCAR_ERR_INVALID, "no FASTQ text is resident on the device (scar_process_fastq_file first)");
+    for (int64_t k = 0; k < n_rows; ++k)
+        if (rows[k] < 0 || rows[k] >= c->fq_records_n) return scar_fail(SCAR_ERR_INVALID, "row %lld names read %lld of %lld", (long long)k, (long long)rows[k], (long long)c->fq_records_n);
+    CU(cudaSetDevice(c->device));
+    static bool table_ready[64] = {false};
+    if (!table_ready[c->device & 63]) {
+        uint8_t t[256];
+        for (int i = 0; i < 256; ++i) t[i] = scar_comp((uint8_t)i);
+        CU(cudaMemcpyToSymbol(GATHER_COMP, t, 256));
+        table_ready[c->device & 63] = true;
+    }
+    struct Dev { void *p = nullptr; ~Dev() { cudaFree(p); } } d_rows, d_flip, d_len, d_off, d_out;
+    const size_t n = (size_t)n_rows;
+    if (cudaMalloc(&d_rows.p, n * 8) != cudaSuccess || cudaMalloc(&d_len.p, n * 4) != cudaSuccess ||
+        cudaMalloc(&d_off.p, n * 8) != cudaSuccess || (flip && cudaMalloc(&d_flip.p, n) != cudaSuccess))
+        return scar_fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
+    cudaStream_t s = c->buf[0].stream;
+    CU(cudaMemcpyAsync(d_rows.p, rows, n * 8, cudaMemcpyHostToDevice, s));
+    if (flip) CU(cudaMemcpyAsync(d_flip.p, flip, n, cudaMemcpyHostToDevice, s));
+    const int grid = c->sm_count * 8;
+    gather_lengths_kernel<<<grid, 256, 0, s>>>((const int64_t *)d_rows.p, n_rows, c->d_fq_seq_len, c->platform, (int32_t *)d_len.p);
+    CU(cudaGetLastError());
+    std::vector<int32_t> len(n);
+    CU(cudaMemcpyAsync(len.data(), d_len.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (size_t k = 0; k < n; ++k) out_off[k + 1] = out_off[k] + len[k];
+    const int64_t total = out_off[n];
+    c->launches += 1;
+    if (!out) return SCAR_OK;
+    if (total > out_capacity) return scar_fail(SCAR_ERR_INVALID, "gather: %lld bytes needed", (long long)total);
+    if (total == 0) return SCAR_OK;
+    if (cudaMalloc(&d_out.p, (size_t)total) != cudaSuccess) return scar_fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
+    CU(cudaMemcpyAsync(d_off.p, out_off, n * 8, cudaMemcpyHostToDevice, s));
+    gather_rows_kernel<<<grid, 256, 0, s>>>(c->d_text, c->d_fq_seq_off, c->d_fq_seq_len, (const int64_t *)d_rows.p,
+                                            (const uint8_t *)d_flip.p, (const int64_t *)d_off.p, n_rows, c->platform, (uint8_t *)d_out.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out.p, (size_t)total, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    c->launches += 1;
+    return SCAR_OK;
+}
 
 extern "C" int scar_gunzip_host(const uint8_t *gz, int64_t gz_bytes, int32_t n_threads, int64_t chunk_bytes, uint8_t *out,
                                 int64_t out_capacity, int64_t *out_bytes, int64_t *stats)

@@ -13,23 +13,12 @@
 #include <algorithm>
 
 #include "scar_internal.cuh"
+#include "scar_comp.h"
 
 int scar_fail(int code, const char *fmt, ...);
 
 namespace {
-// Sequence_Magic.rcomp's translate table (Valkyries/Sequence_Magic.py:97-118); unmapped bytes pass
-inline uint8_t comp(uint8_t c)
-{
-    switch (c) {
-    case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
-    case 'M': return 'K'; case 'R': return 'Y'; case 'Y': return 'R'; case 'K': return 'M';
-    case 'V': return 'B'; case 'H': return 'D'; case 'D': return 'H'; case 'B': return 'V';
-    case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
-    case 'm': return 'k'; case 'r': return 'y'; case 'y': return 'r'; case 'k': return 'm';
-    case 'v': return 'b'; case 'h': return 'd'; case 'd': return 'h'; case 'b': return 'v';
-    default: return c;
-    }
-}
+inline uint8_t comp(uint8_t c) { return scar_comp(c); }
 
 struct Sink {                       // counts, and writes when there is a buffer
     uint8_t *out; int64_t cap, n;

@@ -153,7 +153,8 @@ def _rcomp(s: str) -> str:
     return s.encode("latin-1").translate(_COMP)[::-1].decode("latin-1")
 
 
-def pattern_search_batch(records, reads, platform, first, sample_of, sample_target, targets, target_rc, device, gathered=None):
+def pattern_search_batch(records, reads, platform, first, sample_of, sample_target, targets, target_rc, device, gathered=None,
+                         gathered_flipped=None):
     """homeology_search + templated_insertion_search (INDEL_Processing.py:550-700) for every scar pattern of the run
     in ONE batched call.  Pattern k is represented by its first read `first[k]` (record + stored sequence); the
     arguments are derived per pattern exactly as frequency_output derives them (:299-328, incl. the swaps and
@@ -167,6 +168,8 @@ def pattern_search_batch(records, reads, platform, first, sample_of, sample_targ
     rc = np.asarray(target_rc, dtype=bool)[tix]
     if gathered is not None and not rc.any():
         cons, off = gathered                # the first reads as already gathered by the caller (no 3'-strand guide: no flips)
+    elif gathered_flipped is not None:
+        cons, off = gathered_flipped        # ... gathered with the rows of 3'-strand guides reverse-complemented
     else:
         cons, off = _engine.stored_gather(reads, first, platform, flip=rc.astype(np.uint8) if rc.any() else None)
     L = np.diff(off).astype(np.int64)
@@ -244,6 +247,7 @@ def batched_consensus_demultiplex(self, module, device=0):
         platform=args.Platform, phasing=phasing, hr_donor=args.HR_Donor or "", n_limit=args.N_Limit,
         min_length=args.Minimum_Length)
     streaming = FILE_INGEST[0] and hasattr(_ENGINE_FACTORY[0] or ScarEngine, "process_fastq_file")
+    device_gather = device_gather_flipped = None
     if streaming:
         # The file is streamed through the GPU (scar_process_fastq_file): read / inflated by a producer thread while
         # its pieces are copied, indexed and classified on the device.  Nothing about the run is known up front: the
@@ -256,7 +260,11 @@ def batched_consensus_demultiplex(self, module, device=0):
         try:
             eng.set_verify(True)
             STAGE_SECONDS["keys_verified_exactly"] = 1.0
-            batch = eng.process_fastq_file(self.fastq1.input_file, limit=limit, threads=FILE_INGEST_THREADS[0])
+            # the host needs the text only for the Raw_Data / demultiplexed-FASTQ writers: otherwise the first read of
+            # every scar pattern is gathered on the device, where the text is (below), and no copy is kept
+            keep_text = bool(args.OutputRawData or args.Demultiplex) or not hasattr(eng, "fastq_gather")
+            batch = eng.process_fastq_file(self.fastq1.input_file, limit=limit, threads=FILE_INGEST_THREADS[0],
+                                           keep_text=keep_text)
             records = batch.records
             self.read_count = batch.n
             STAGE_SECONDS["fastq_source_" + batch.source] = 1.0
@@ -264,6 +272,12 @@ def batched_consensus_demultiplex(self, module, device=0):
             counters, unassigned = eng.counters()
             phase_hist = eng.phase_hist()
             table = eng.table()                 # sorted by (sample, first_idx): per-sample first-seen order
+            if not keep_text:
+                firsts = table["first_idx"].astype(np.int64)
+                device_gather = eng.fastq_gather(firsts)
+                if any(target_rc):
+                    flips = np.asarray(target_rc, dtype=bool)[np.asarray(sample_target, dtype=np.int64)[table["sample"].astype(np.int64)]]
+                    device_gather_flipped = eng.fastq_gather(firsts, flip=flips.astype(np.uint8))
         except N.ScarError as exc:
             if exc.code != N.ERR_NOMEM:
                 raise
@@ -327,10 +341,11 @@ def batched_consensus_demultiplex(self, module, device=0):
     tab_sample = table["sample"].astype(np.int64)
     tab_first = table["first_idx"].astype(np.int64)
     bounds = np.searchsorted(tab_sample, np.arange(n_samples + 1))
-    first_bytes, first_off = _gather(batch.seq, tab_first, args.Platform)
+    first_bytes, first_off = device_gather if device_gather is not None else _gather(batch.seq, tab_first, args.Platform)
     stage("unpack")
     pattern_out = pattern_search_batch(records, batch.seq, args.Platform, tab_first, tab_sample, sample_target, targets,
-                                       target_rc, device, gathered=(first_bytes, first_off))
+                                       target_rc, device, gathered=(first_bytes, first_off),
+                                       gathered_flipped=device_gather_flipped)
     stage("gpu_pattern_searches")
     # scarred reads bucketed by sample once (stable: read order inside a sample)
     scar_rows, scar_bounds = None, None

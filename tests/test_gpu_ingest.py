@@ -126,6 +126,38 @@ def test_fastq_file_matches_the_host_indexed_path(kind, threads, case, tmp_path,
     eng.close()
 
 
+@pytest.mark.parametrize("platform", ["Illumina", "TruSeq", "Ramsden"])
+def test_device_gather_of_stored_sequences_matches_the_host_gather(platform, case, tmp_path):
+    """scar_fastq_gather_host: the stored sequences of chosen reads, gathered on the device from the resident text, are
+    what scar_stored_gather_host builds from the host text (platform transform, flipped rows reverse-complemented)."""
+    from scarmapper_b200 import engine as E, fastq
+    path = str(tmp_path / "reads.fastq.gz")
+    write_source("gzip", case["text"], path)
+    pin = dict(case["pin"])
+    pin["platform"] = platform
+    if platform != "Illumina":
+        pin["left_index"] = pin["right_index"] = None
+        pin["phasing"] = None
+    try:
+        eng = engine_for(pin, 160, table_capacity=1 << 16)
+    except Exception:
+        pytest.skip("problem not expressible for " + platform)
+    run = eng.process_fastq_file(path, keep_text=False)
+    assert run.text is None and run.n == len(case["reads"])
+    fb = fastq.index_text(np.frombuffer(case["text"], dtype=np.uint8))
+    rng = np.random.default_rng(3)
+    for n_rows in (0, 1, 40000):
+        rows = rng.integers(0, run.n, n_rows).astype(np.int64)
+        for flip in (None, rng.integers(0, 2, n_rows).astype(np.uint8)):
+            got, got_off = eng.fastq_gather(rows, flip=flip)
+            want, want_off = E.stored_gather(fb.seq, rows, platform, flip=flip)
+            assert (got_off == want_off).all() and got.tobytes() == want.tobytes()
+    with pytest.raises(Exception):
+        eng.fastq_gather(np.asarray([run.n], dtype=np.int64))
+    run.close()
+    eng.close()
+
+
 def test_fastq_file_three_kernel_path_grows_its_packed_batch(case, tmp_path, monkeypatch):
     """SCAR_NO_FUSE=1: K1 -> K3 -> K4 with the packed batch in HBM; the context starts at 48 nt, so the packed buffers
     are re-planned for 150-nt reads in mid-file."""
