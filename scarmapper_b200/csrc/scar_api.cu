@@ -11,6 +11,7 @@
 #include <ctime>
 #include <map>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "scar_internal.cuh"
@@ -187,7 +188,7 @@ extern "C" void scar_ctx_destroy(scar_ctx *c)
     cudaFree(c->d_class_map); cudaFree(c->d_right); cudaFree(c->d_left); cudaFree(c->d_peq); cudaFree(c->d_first_sample); cudaFree(c->d_fast_codes);
     cudaFree(c->d_lut_right); cudaFree(c->d_lut_left);
     cudaFree(c->d_slots); cudaFree(c->d_claimed); cudaFree(c->d_acc); cudaFree(c->d_status);
-    cudaFree(c->d_fq_seq_off); cudaFree(c->d_fq_seq_len);
+    cudaFree(c->d_fq_seq_off); cudaFree(c->d_fq_seq_len); cudaFree(c->d_gather_small); cudaFree(c->d_gather_out);
     for (uint8_t *p : c->h_piece) if (p) cudaFreeHost(p);
     cudaFree(c->d_text); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offsets); cudaFree(c->d_nl); cudaFree(c->d_fq_records); cudaFree(c->d_part_cursor);
     for (cudaEvent_t e : c->fq_events) cudaEventDestroy(e);
@@ -1303,6 +1304,46 @@ struct DevInts {
 };
 }   // namespace
 
+namespace {
+// One grow-only block of device memory per device for the batch entry points that have no context: a call carves
+// its buffers out of it.  cudaMalloc / cudaFree per buffer cost more than the kernels here, and cudaFree stalls
+// unpredictably (hundreds of ms were measured inside a pipeline run) - nothing is freed on the way out.
+struct DeviceArena {
+    uint8_t *base = nullptr; size_t cap = 0, used = 0;
+    int reserve(size_t total)
+    {
+        used = 0;
+        if (total <= cap) return SCAR_OK;
+        if (base) cudaFree(base);
+        base = nullptr; cap = 0;
+        const size_t want = total + total / 8 + (1 << 20);
+        if (cudaMalloc((void **)&base, want) != cudaSuccess) { cudaGetLastError(); base = nullptr; return fail(SCAR_ERR_NOMEM, "no device memory for %zu bytes", want); }
+        cap = want;
+        return SCAR_OK;
+    }
+    template <typename T> T *take(size_t count) { T *p = reinterpret_cast<T *>(base + used); used += (count * sizeof(T) + 255) & ~(size_t)255; return p; }
+};
+std::mutex g_arena_mutex;
+DeviceArena g_arena[64];
+
+size_t ragged_device_bytes(const scar_ragged &H, int64_t n)
+{
+    const Span sp = span_of(H, 0, n);
+    return (size_t)(sp.byte1 - sp.byte0) + 16 + 256 + ((size_t)(n + 1) * 8 + 256) + ((size_t)std::max<int64_t>(n, 1) * 4 + 256);
+}
+
+int stage_from_arena(DeviceArena &A, const scar_ragged &H, int64_t n, scar_ragged *D)
+{
+    const Span sp = span_of(H, 0, n);
+    size_t cap = (size_t)(sp.byte1 - sp.byte0) + 16;
+    uint8_t *bytes = A.take<uint8_t>(cap);
+    int64_t *off = A.take<int64_t>((size_t)n + 1);
+    int32_t *len = A.take<int32_t>((size_t)std::max<int64_t>(n, 1));
+    int64_t h2d = 0;
+    return stage_ragged(H, 0, n, &bytes, &cap, &off, &len, 0, nullptr, D, &h2d);      // (cap suffices: nothing is allocated)
+}
+}   // namespace
+
 extern "C" int scar_homeology_batch(int32_t device, const scar_ragged *consensus, const scar_ragged *insertion,
                                     const int32_t *clj, const int32_t *crj, const int32_t *tlj, const int32_t *trj,
                                     const int32_t *target_idx, const scar_ragged *targets, const scar_ragged *regions,
@@ -1314,35 +1355,37 @@ extern "C" int scar_homeology_batch(int32_t device, const scar_ragged *consensus
     if (n == 0) return SCAR_OK;
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) return fail(SCAR_ERR_CUDA, "CUDA device %d not present", device);
+    if (device < 0 || device >= ndev || device >= 64) return fail(SCAR_ERR_CUDA, "CUDA device %d not present", device);
     CU(cudaSetDevice(device));
     const bool trace = getenv("SCAR_TRACE") != nullptr;
     auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; };
     const double t0 = now();
-    double t1 = t0, t2 = t0, t3 = t0;
-    cudaError_t err = cudaSuccess;
-    {
-    StagedList dc, di, dt, dr;
-    DevInts a, b, c, d, e;
-    int rc;
-    if ((rc = dc.stage(*consensus, n)) || (rc = di.stage(*insertion, n)) || (rc = dt.stage(*targets, n_targets)) ||
-        (rc = dr.stage(*regions, n_targets)) || (rc = a.upload(clj, n)) || (rc = b.upload(crj, n)) ||
-        (rc = c.upload(tlj, n)) || (rc = d.upload(trj, n)) || (rc = e.upload(target_idx, n)))
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    DeviceArena &A = g_arena[device];
+    const size_t ints = ((size_t)n * 4 + 256);
+    int rc = A.reserve(ragged_device_bytes(*consensus, n) + ragged_device_bytes(*insertion, n) + ragged_device_bytes(*targets, n_targets) +
+                       ragged_device_bytes(*regions, n_targets) + 5 * ints + (size_t)n * 64 + 256);
+    if (rc) return rc;
+    scar_ragged dc, di, dt, dr;
+    if ((rc = stage_from_arena(A, *consensus, n, &dc)) || (rc = stage_from_arena(A, *insertion, n, &di)) ||
+        (rc = stage_from_arena(A, *targets, n_targets, &dt)) || (rc = stage_from_arena(A, *regions, n_targets, &dr)))
         return rc;
-    int32_t *dout = nullptr;
-    if (cudaMalloc((void **)&dout, (size_t)n * 16 * sizeof(int32_t)) != cudaSuccess) return fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
-    if (trace) cudaDeviceSynchronize();
-    t1 = now();
-    err = scar_launch_homeology(dc.dev, di.dev, dt.dev, dr.dev, a.p, b.p, c.p, d.p, e.p, n_targets, n, dout, nullptr);
-    if (err == cudaSuccess && trace) err = cudaDeviceSynchronize();
-    t2 = now();
-    if (err == cudaSuccess) err = cudaMemcpy(out, dout, (size_t)n * 16 * sizeof(int32_t), cudaMemcpyDeviceToHost);
-    t3 = now();
-    cudaFree(dout);
+    int32_t *dint[5];
+    const int32_t *hint[5] = {clj, crj, tlj, trj, target_idx};
+    for (int k = 0; k < 5; ++k) {
+        dint[k] = A.take<int32_t>((size_t)n);
+        CU(cudaMemcpy(dint[k], hint[k], (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
+    int32_t *dout = A.take<int32_t>((size_t)n * 16);
+    if (trace) cudaDeviceSynchronize();
+    const double t1 = now();
+    cudaError_t err = scar_launch_homeology(dc, di, dt, dr, dint[0], dint[1], dint[2], dint[3], dint[4], n_targets, n, dout, nullptr);
+    if (err == cudaSuccess && trace) err = cudaDeviceSynchronize();
+    const double t2 = now();
+    if (err == cudaSuccess) err = cudaMemcpy(out, dout, (size_t)n * 16 * sizeof(int32_t), cudaMemcpyDeviceToHost);
     if (trace)
-        fprintf(stderr, "[scar homeology] %lld patterns: staged %.1f ms, kernel %.1f ms, results %.1f ms, buffers freed %.1f ms\n",
-                (long long)n, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (now() - t3));
+        fprintf(stderr, "[scar homeology] %lld patterns: staged %.1f ms, kernel %.1f ms, results %.1f ms (device arena %zu MB)\n",
+                (long long)n, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (now() - t2), A.cap >> 20);
     if (err != cudaSuccess) return fail(SCAR_ERR_CUDA, "homeology kernel failed: %s", cudaGetErrorString(err));
     return SCAR_OK;
 }

@@ -60,6 +60,7 @@ struct scar_ctx {
     int32_t *d_fq_seq_len = nullptr; size_t fq_seq_len_cap = 0;
     uint8_t *h_piece[4] = {nullptr, nullptr, nullptr, nullptr}; int64_t h_piece_bytes = 0;
     int launches = 0;
+    uint8_t *d_gather_small = nullptr, *d_gather_out = nullptr; size_t gather_small_cap = 0, gather_out_cap = 0;   // scar_fastq_gather_host scratch (kept: cudaFree stalls)
 };
 
 

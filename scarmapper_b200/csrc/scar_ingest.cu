@@ -414,6 +414,17 @@ extern "C" int scar_fastq_gather_host(scar_ctx *c, const int64_t *rows, int64_t 
     for (int64_t k = 0; k < n_rows; ++k)
         if (rows[k] < 0 || rows[k] >= c->fq_records_n) return scar_fail(SCAR_ERR_INVALID, "row %lld names read %lld of %lld", (long long)k, (long long)rows[k], (long long)c->fq_records_n);
     CU(cudaSetDevice(c->device));
+    const bool trace = getenv("SCAR_TRACE") != nullptr;
+    const double t_begin = now_s();
+    double t_prev = t_begin;
+    std::string timeline;
+    auto mark = [&](const char *what) {
+        if (!trace) return;
+        const double t = now_s();
+        char b[96];
+        snprintf(b, sizeof b, " %s %.1f ms,", what, 1e3 * (t - t_prev));
+        timeline += b; t_prev = t;
+    };
     static bool table_ready[64] = {false};
     if (!table_ready[c->device & 63]) {
         uint8_t t[256];
@@ -421,11 +432,16 @@ extern "C" int scar_fastq_gather_host(scar_ctx *c, const int64_t *rows, int64_t 
         CU(cudaMemcpyToSymbol(GATHER_COMP, t, 256));
         table_ready[c->device & 63] = true;
     }
-    struct Dev { void *p = nullptr; ~Dev() { cudaFree(p); } } d_rows, d_flip, d_len, d_off, d_out;
+    // (allocations are the expensive part of this call and cudaFree stalls unpredictably: two scratch blocks kept in
+    // the context, one for the small arrays, one for the bytes)
+    struct Part { void *p; } d_small, d_out, d_rows, d_off, d_len, d_flip;
     const size_t n = (size_t)n_rows;
-    if (cudaMalloc(&d_rows.p, n * 8) != cudaSuccess || cudaMalloc(&d_len.p, n * 4) != cudaSuccess ||
-        cudaMalloc(&d_off.p, n * 8) != cudaSuccess || (flip && cudaMalloc(&d_flip.p, n) != cudaSuccess))
-        return scar_fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
+    int rc = ensure(&c->d_gather_small, &c->gather_small_cap, n * 21 + 64);
+    if (rc) return rc;
+    d_small.p = c->d_gather_small; d_out.p = nullptr;
+    d_rows.p = d_small.p; d_off.p = (uint8_t *)d_small.p + n * 8; d_len.p = (uint8_t *)d_small.p + n * 16;
+    d_flip.p = flip ? (uint8_t *)d_small.p + n * 20 : nullptr;
+    mark("table + small buffers");
     cudaStream_t s = c->buf[0].stream;
     CU(cudaMemcpyAsync(d_rows.p, rows, n * 8, cudaMemcpyHostToDevice, s));
     if (flip) CU(cudaMemcpyAsync(d_flip.p, flip, n, cudaMemcpyHostToDevice, s));
@@ -435,19 +451,25 @@ extern "C" int scar_fastq_gather_host(scar_ctx *c, const int64_t *rows, int64_t 
     std::vector<int32_t> len(n);
     CU(cudaMemcpyAsync(len.data(), d_len.p, n * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    mark("lengths");
     for (size_t k = 0; k < n; ++k) out_off[k + 1] = out_off[k] + len[k];
     const int64_t total = out_off[n];
     c->launches += 1;
     if (!out) return SCAR_OK;
     if (total > out_capacity) return scar_fail(SCAR_ERR_INVALID, "gather: %lld bytes needed", (long long)total);
     if (total == 0) return SCAR_OK;
-    if (cudaMalloc(&d_out.p, (size_t)total) != cudaSuccess) return scar_fail(SCAR_ERR_NOMEM, "cudaMalloc failed");
+    if ((rc = ensure(&c->d_gather_out, &c->gather_out_cap, (size_t)total))) return rc;
+    d_out.p = c->d_gather_out;
+    mark("output buffer");
     CU(cudaMemcpyAsync(d_off.p, out_off, n * 8, cudaMemcpyHostToDevice, s));
     gather_rows_kernel<<<grid, 256, 0, s>>>(c->d_text, c->d_fq_seq_off, c->d_fq_seq_len, (const int64_t *)d_rows.p,
                                             (const uint8_t *)d_flip.p, (const int64_t *)d_off.p, n_rows, c->platform, (uint8_t *)d_out.p);
     CU(cudaGetLastError());
+    if (trace) { CU(cudaStreamSynchronize(s)); mark("gather kernel"); }
     CU(cudaMemcpyAsync(out, d_out.p, (size_t)total, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    mark("bytes to the host");
+    if (trace) fprintf(stderr, "[scar gather] %lld rows, %lld bytes:%s\n", (long long)n_rows, (long long)total, timeline.c_str());
     c->launches += 1;
     return SCAR_OK;
 }
@@ -535,8 +557,17 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
     c->fq_records_n = 0;
     if ((rc = ensure(&c->d_tile_counts, &c->tile_counts_cap, (size_t)((piece + 4095) / 4096)))) return rc;
     if ((rc = ensure(&c->d_tile_offsets, &c->tile_offsets_cap, (size_t)scar_fastq_offsets_elems(piece)))) return rc;
-    // first guess of the text size: the file itself, or a typical FASTQ compression ratio (grown on demand)
-    if ((rc = ensure_keep(&c->d_text, &c->text_cap, (size_t)(gz ? 5 * file.n : file.n) + 4096, 0))) return rc;
+    // the text size, to allocate once (every re-allocation in mid-stream is a cudaMalloc + copy + cudaFree with both
+    // streams idle): the file itself; BGZF: the sum of the blocks' sizes; gzip: the length field of the last trailer
+    // (exact for one member under 4 GiB; otherwise a typical FASTQ ratio) - grown on demand when the guess was low
+    int64_t text_hint = file.n;
+    if (bgzf) { text_hint = 0; for (const BgzfBlock &b : blocks) text_hint += b.out_len; }
+    else if (gz) {
+        const uint8_t *t = file.p + file.n - 4;
+        const int64_t isize = file.n >= 18 ? (int64_t)((uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24)) : 0;
+        text_hint = isize > file.n && isize < 1100 * file.n ? isize : 5 * file.n;
+    }
+    if ((rc = ensure_keep(&c->d_text, &c->text_cap, (size_t)text_hint + 4096, 0))) return rc;
 
     mark("device buffers ready");
     HostText inflated;
@@ -594,7 +625,11 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
         S.release();
         if (len > 0) {
             size_t want_nl = (size_t)(nl_total + (int64_t)n_nl) + 1;
-            if (want_nl > c->nl_cap) want_nl += want_nl / 2 + 1024;
+            if (want_nl > c->nl_cap) {
+                // lines of the whole text at the density seen so far (+ 3 %), else half as much again
+                const double scale = n_bytes > 0 && text_hint > n_bytes ? 1.03 * (double)text_hint / (double)n_bytes : 1.5;
+                want_nl = (size_t)((double)want_nl * std::max(scale, 1.0)) + 1024;
+            }
             if ((rc = ensure_keep(&c->d_nl, &c->nl_cap, want_nl, (size_t)nl_total))) return drain(rc);
             CU(scar_fastq_positions_launch(c->d_text + b0, len, c->d_tile_offsets, c->d_nl + nl_total, (int64_t)n_nl, b0, s));
             ++c->launches;
@@ -608,7 +643,10 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
         if (m <= 0) continue;
         if (m > B.reads_cap && (rc = scar_ensure_hostbuf(c, B, m + m / 8 + 1024))) return drain(rc);
         size_t want_rec = (size_t)rec_avail;
-        if (want_rec > c->fq_records_cap) want_rec += want_rec / 2 + 1024;
+        if (want_rec > c->fq_records_cap) {
+            const double scale = n_bytes > 0 && text_hint > n_bytes ? 1.03 * (double)text_hint / (double)n_bytes : 1.5;
+            want_rec = (size_t)((double)want_rec * std::max(scale, 1.0)) + 1024;
+        }
         if ((rc = ensure_keep(&c->d_fq_records, &c->fq_records_cap, want_rec, (size_t)rec_done))) return drain(rc);
         if ((rc = ensure_keep(&c->d_fq_seq_off, &c->fq_seq_off_cap, want_rec, (size_t)rec_done))) return drain(rc);
         if ((rc = ensure_keep(&c->d_fq_seq_len, &c->fq_seq_len_cap, want_rec, (size_t)rec_done))) return drain(rc);

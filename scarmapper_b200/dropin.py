@@ -256,7 +256,14 @@ def batched_consensus_demultiplex(self, module, device=0):
         # (exact-or-fail identity; a mismatch raises instead of merging two scar patterns under one 128-bit tag).
         if len(self.fastq1.input_file) < 3 or not os.path.isfile(self.fastq1.input_file):
             raise FileNotFoundError("FASTQ file {} not found".format(self.fastq1.input_file))
+        trace = [] if os.environ.get("SCAR_TRACE") else None
+
+        def mark(what):
+            if trace is not None:
+                trace.append((what, time.perf_counter()))
+        mark("start")
         eng = _make_engine(ScarProblem(max_read_len=160, table_capacity=1 << 18, **common), device)
+        mark("context created")
         try:
             eng.set_verify(True)
             STAGE_SECONDS["keys_verified_exactly"] = 1.0
@@ -265,6 +272,7 @@ def batched_consensus_demultiplex(self, module, device=0):
             keep_text = bool(args.OutputRawData or args.Demultiplex) or not hasattr(eng, "fastq_gather")
             batch = eng.process_fastq_file(self.fastq1.input_file, limit=limit, threads=FILE_INGEST_THREADS[0],
                                            keep_text=keep_text)
+            mark("file through the GPU")
             records = batch.records
             self.read_count = batch.n
             STAGE_SECONDS["fastq_source_" + batch.source] = 1.0
@@ -272,12 +280,14 @@ def batched_consensus_demultiplex(self, module, device=0):
             counters, unassigned = eng.counters()
             phase_hist = eng.phase_hist()
             table = eng.table()                 # sorted by (sample, first_idx): per-sample first-seen order
+            mark("counters and table read")
             if not keep_text:
                 firsts = table["first_idx"].astype(np.int64)
-                device_gather = eng.fastq_gather(firsts)
+                device_gather = eng.fastq_gather(firsts, max_len=batch.max_seq_len)
                 if any(target_rc):
                     flips = np.asarray(target_rc, dtype=bool)[np.asarray(sample_target, dtype=np.int64)[table["sample"].astype(np.int64)]]
-                    device_gather_flipped = eng.fastq_gather(firsts, flip=flips.astype(np.uint8))
+                    device_gather_flipped = eng.fastq_gather(firsts, flip=flips.astype(np.uint8), max_len=batch.max_seq_len)
+                mark("first reads gathered on the device")
         except N.ScarError as exc:
             if exc.code != N.ERR_NOMEM:
                 raise
@@ -286,6 +296,10 @@ def batched_consensus_demultiplex(self, module, device=0):
             streaming = False
         finally:
             eng.close()
+            mark("context closed")
+            if trace:
+                print("[scar dropin] " + ", ".join("{} {:.0f} ms".format(w, 1e3 * (t - trace[i][1])) for i, (w, t) in
+                                                   enumerate(trace[1:])), file=sys.stderr)
     if streaming:
         stage("fastq_stream_gpu_classify_aggregate")
     else:

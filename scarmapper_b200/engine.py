@@ -306,14 +306,20 @@ class ScarEngine:
                                                 1 if keep_text else 0, C.byref(raw)))
         return FastqFileRun(self._L, raw)
 
-    def fastq_gather(self, rows, flip=None):
+    def fastq_gather(self, rows, flip=None, max_len=None):
         """Stored sequences of the reads `rows` of the last process_fastq_file run, gathered on the device from the
-        resident text (scar_fastq_gather_host): (uint8 bytes, int64 offsets[len(rows) + 1]), as stored_gather."""
+        resident text (scar_fastq_gather_host): (uint8 bytes, int64 offsets[len(rows) + 1]), as stored_gather.
+        max_len: an upper bound of the stored length (FastqFileRun.max_seq_len) - one call instead of size + fill."""
         rows = np.ascontiguousarray(rows, dtype=np.int64)
         fl = None if flip is None else np.ascontiguousarray(flip, dtype=np.uint8)
         assert fl is None or fl.size == rows.size
         off = np.zeros(rows.size + 1, dtype=np.int64)
         fp = None if fl is None else fl.ctypes.data
+        if max_len is not None:
+            out = np.empty(max(int(rows.size) * int(max_len), 1), dtype=np.uint8)
+            N.check(self._L.scar_fastq_gather_host(self._ctx, rows.ctypes.data, rows.size, fp, out.ctypes.data, out.size,
+                                                   off.ctypes.data))
+            return out[:int(off[-1])], off
         N.check(self._L.scar_fastq_gather_host(self._ctx, rows.ctypes.data, rows.size, fp, None, 0, off.ctypes.data))
         out = np.empty(max(int(off[-1]), 1), dtype=np.uint8)
         N.check(self._L.scar_fastq_gather_host(self._ctx, rows.ctypes.data, rows.size, fp, out.ctypes.data, int(off[-1]),
