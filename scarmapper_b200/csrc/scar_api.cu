@@ -11,6 +11,8 @@
 #include <ctime>
 #include <map>
 #include <string>
+#include <atomic>
+#include <thread>
 #include <mutex>
 #include <vector>
 
@@ -998,20 +1000,42 @@ extern "C" int scar_table_read(scar_ctx *c, scar_entry *entries, int64_t capacit
     if (!entries) return SCAR_OK;
     if (capacity < n) return fail(SCAR_ERR_INVALID, "entries buffer too small: need %lld", (long long)n);
     if (n == 0) return SCAR_OK;
-    scar_entry *d = nullptr;
-    CU(cudaMalloc((void **)&d, (size_t)n * sizeof(scar_entry)));
+    // (device scratch kept in the context: no cudaMalloc / cudaFree per call)
+    if ((rc = ensure(&c->d_gather_out, &c->gather_out_cap, (size_t)n * sizeof(scar_entry)))) return rc;
+    scar_entry *d = reinterpret_cast<scar_entry *>(c->d_gather_out);
     int64_t got = 0;
     rc = scar_table_export_dev(c, d, n, &got, nullptr);
+    std::vector<scar_entry> tmp;
     if (!rc) {
-        cudaError_t e = cudaMemcpy(entries, d, (size_t)n * sizeof(scar_entry), cudaMemcpyDeviceToHost);
+        tmp.resize((size_t)n);
+        cudaError_t e = cudaMemcpy(tmp.data(), d, (size_t)n * sizeof(scar_entry), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(SCAR_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(d);
     if (rc) return rc;
-    // results_freq_dict order: per sample, first-seen (INDEL_Processing.py:193-196)
-    std::sort(entries, entries + n, [](const scar_entry &a, const scar_entry &b) {
-        return a.sample != b.sample ? a.sample < b.sample : a.first_idx < b.first_idx;
-    });
+    // results_freq_dict order: per sample, first-seen (INDEL_Processing.py:193-196).  Counting sort by sample, then
+    // every sample's entries by first index, the samples spread over a few threads.
+    std::vector<int64_t> start((size_t)c->n_samples + 2, 0);
+    for (int64_t k = 0; k < n; ++k) {
+        if ((int64_t)tmp[(size_t)k].sample > c->n_samples) return fail(SCAR_ERR_CUDA, "table entry with sample %u", (unsigned)tmp[(size_t)k].sample);
+        ++start[(size_t)tmp[(size_t)k].sample + 1];
+    }
+    for (size_t s = 1; s < start.size(); ++s) start[s] += start[s - 1];
+    {
+        std::vector<int64_t> cursor(start.begin(), start.end() - 1);
+        for (int64_t k = 0; k < n; ++k) entries[cursor[(size_t)tmp[(size_t)k].sample]++] = tmp[(size_t)k];
+    }
+    const int n_buckets = (int)start.size() - 1;
+    const int threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, (int64_t)std::thread::hardware_concurrency()), n / 65536));
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (int b = next++; b < n_buckets; b = next++)
+            std::sort(entries + start[(size_t)b], entries + start[(size_t)b + 1],
+                      [](const scar_entry &x, const scar_entry &y) { return x.first_idx < y.first_idx; });
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
     return SCAR_OK;
 }
 
