@@ -46,6 +46,33 @@ def main():
         assert rec.tobytes() == want.tobytes(), (name, "fastq")
         eng.close()
         os.environ.pop("SCAR_FASTQ_PIECE_BYTES", None)
+        # the FILE path (gzip stream inflated by several threads, pieces of 128 KB), then the first reads of the table's
+        # entries gathered on the device and the per-pattern searches
+        import tempfile
+        import zlib
+        from scarmapper_b200 import engine as E
+        os.environ["SCAR_FASTQ_FILE_PIECE_BYTES"] = str(1 << 17)
+        with tempfile.NamedTemporaryFile(suffix=".fastq.gz", delete=False) as f:
+            co = zlib.compressobj(4, zlib.DEFLATED, 31)
+            f.write(co.compress(text.encode() * 3) + co.flush())
+        eng = ScarEngine(ScarProblem(max_read_len=48, table_capacity=1 << 10, **pin), device=0)
+        run = eng.process_fastq_file(f.name, threads=4, keep_text=False)
+        assert run.n == 3 * n and run.records[:n].tobytes() == want.tobytes(), (name, "file")
+        tab = eng.table()
+        rows = tab["first_idx"].astype(np.int64)
+        flip = (np.arange(rows.size) % 2).astype(np.uint8)
+        got, off = eng.fastq_gather(rows, flip=flip, max_len=run.max_seq_len)
+        ref, ref_off = E.stored_gather(reads, rows % n, "Illumina", flip=flip)
+        assert (off == ref_off).all() and got.tobytes() == ref.tobytes(), (name, "gather")
+        run.close()
+        eng.close()
+        os.remove(f.name)
+        os.environ.pop("SCAR_FASTQ_FILE_PIECE_BYTES", None)
+        k = min(500, rows.size)
+        cons = [r for r in reads[:k]]
+        out = E.homeology_batch(cons, [c[60:66] for c in cons], np.full(k, 60), np.full(k, 66), np.full(k, cfg.cutsites[0] - 5),
+                                np.full(k, cfg.cutsites[0] + 5), np.zeros(k, np.int32), cfg.targets[:1], cfg.targets[:1], 0)
+        assert out.shape == (k, 16)
         print("sanitizer_probe", name, "ok", flush=True)
 
 
