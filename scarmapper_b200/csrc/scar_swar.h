@@ -16,14 +16,27 @@ SCAR_SWAR uint32_t zero_bytes(uint32_t x)
     return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
 }
 
-// canonical-letter difference of four bytes: byte k of the result is 0 iff byte k of w is A, C, G or T.
-// The code (w>>1)&3 names the only letter the byte could be; 'A'|(w&6) is that letter for A, C, G and
-// 'E' for code 2, which +15 turns into 'T'.
-SCAR_SWAR uint32_t acgt_diff4(uint32_t w)
+// canonical-letter difference of four bytes.  The code (w>>1)&3 names the only letter a byte could be; t marks the
+// bytes whose code is 2 (bits 2,1 = 1,0: 'T' if anything).  Outside bits 1 and 2 an A, C or G is 0x41 and a T is
+// 0x50 = 0x41 + 15, so  raw = w ^ (0x41414141 + 15 t)  has (byte k & 0xF9) == 0 iff byte k of w is A, C, G or T
+// ('E' = 0x45 has t = 1 and fails on 0x50; 'P','R','V' = 0x50,0x52,0x56 have t = 0 and fail on 0x41).
+SCAR_SWAR uint32_t acgt_raw4(uint32_t w)
 {
     const uint32_t t = ((w >> 2) & ~(w >> 1)) & 0x01010101u;            // 1 where the code is 2
-    const uint32_t canon = (0x41414141u | (w & 0x06060606u)) + t * 15u;
-    return w ^ canon;
+    return w ^ (t * 15u + 0x41414141u);
+}
+
+// byte k of the result is 0 iff byte k of w is A, C, G or T
+SCAR_SWAR uint32_t acgt_diff4(uint32_t w) { return acgt_raw4(w) & 0xF9F9F9F9u; }
+
+// non-zero iff any of the sixteen bytes is not A, C, G or T (one mask for the four words)
+SCAR_SWAR uint32_t acgt_any16(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3)
+{
+#ifdef SCAR_OLD_ACGT_TEST          // (A/B: the per-word test of round 2's first fused kernel)
+    return acgt_diff4(v0) | acgt_diff4(v1) | acgt_diff4(v2) | acgt_diff4(v3);
+#else
+    return (acgt_raw4(v0) | acgt_raw4(v1) | acgt_raw4(v2) | acgt_raw4(v3)) & 0xF9F9F9F9u;
+#endif
 }
 
 // 0x80 flags of four bytes -> 4-bit mask (one multiply: the four partial products land on distinct bits)

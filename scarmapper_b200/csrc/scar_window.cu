@@ -23,6 +23,7 @@
 //   right search: positions p = 10 .. len-26 ascending,  first hit -> crj = p,    trj = cut + i
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "scar_table_core.cuh"
 
@@ -592,13 +593,14 @@ __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d
     const int j0 = q * cpl, j1 = min(j0 + cpl, P.W);
     uint2 *out = reinterpret_cast<uint2 *>(s_cells + lr0 + k) + (size_t)j0 * K3_TILE;
     int n_count = 0;
-    if (inside) {
+    if (inside && have) {                                   // (a lane without a read takes the other branch: no store test per cell here)
         const uint32_t a0 = slot_addr + (uint32_t)(a - d.lo16) + 16u * (uint32_t)j0;     // shared address of cell j0's first byte
         const uint32_t sh = (a0 & 3u) * 8u;
         uint32_t a4 = a0 & ~3u, wp;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wp) : "r"(a4));
         int nb = slen - 16 * j0;                            // bases from this cell on
-        for (int j = j0; j < j1; ++j, a4 += 16u, nb -= 16, out += K3_TILE) {
+        // one cell: four words of the raw bytes -> 16 codes + masks.  PARTIAL: the read ends in (or before) this cell
+        auto pack_cell = [&](auto partial) {
             uint32_t w1, w2, w3, w4;
             asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a4));
             asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a4));
@@ -608,14 +610,14 @@ __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d
             uint32_t v2 = __funnelshift_r(w2, w3, sh), v3 = __funnelshift_r(w3, w4, sh);
             wp = w4;
             uint32_t hi = 0xFFFFu;                          // ACGT mask | N mask << 16
-            if (nb < 16) {                                  // the read ends in (or before) this cell: bytes past its end count as 'A' (code 0)
+            if (decltype(partial)::value) {                 // bytes past the read's end count as 'A' (code 0)
                 const int nbc = max(nb, 0);
                 hi = (1u << nbc) - 1u;
                 const uint4 keep = SCAR_KEEP_BYTES[nbc];
                 v0 = (v0 & keep.x) | (0x41414141u & ~keep.x); v1 = (v1 & keep.y) | (0x41414141u & ~keep.y);
                 v2 = (v2 & keep.z) | (0x41414141u & ~keep.z); v3 = (v3 & keep.w) | (0x41414141u & ~keep.w);
             }
-            const uint32_t x = acgt_diff4(v0) | acgt_diff4(v1) | acgt_diff4(v2) | acgt_diff4(v3);
+            const uint32_t x = acgt_any16(v0, v1, v2, v3);
             uint2 cell;
             cell.x = __byte_perm(__byte_perm(codes_to_top_byte(v0), codes_to_top_byte(v1), 0x0073),
                                  __byte_perm(codes_to_top_byte(v2), codes_to_top_byte(v3), 0x0073), 0x5410);
@@ -624,7 +626,36 @@ __device__ __forceinline__ void pack_chunk(const K3Params &P, const ChunkDesc &d
                 cell = pack_cell_masks(v0, v1, v2, v3, cell.x, hi);
                 n_count += __popc(cell.y >> 16);
             }
-            if (have) *out = cell;
+            *out = cell;
+        };
+#ifdef SCAR_PACK_ONE_LOOP
+        constexpr bool split = false;
+#elif defined(SCAR_PACK_SPLIT_LOOP)
+        constexpr bool split = true;
+#else
+        // measured (profiles/r02/pack_variants_sweep.txt): with 2 lanes per read the split loops take 6.8 % off the whole
+        // kernel on C2, with 4 lanes per read (reads over 160 nt) they cost 2.3 % on C4
+        constexpr bool split = LANES == 2;
+#endif
+        if (split) {
+            // the cells that lie wholly inside the read need no end-of-read test; then the cell the read ends in and
+            // whatever this lane still owns behind it
+            const int n_cells = j1 - j0, n_full = max(0, min(n_cells, nb >> 4));
+            int j = 0;
+#ifdef SCAR_PACK_UNROLL
+            constexpr int pack_unroll = SCAR_PACK_UNROLL;
+#pragma unroll pack_unroll
+#endif
+            for (; j < n_full; ++j, a4 += 16u, out += K3_TILE) pack_cell(std::false_type{});
+            nb -= 16 * n_full;
+#ifdef SCAR_PACK_PARTIAL_UNROLL1
+#pragma unroll 1
+#endif
+            for (; j < n_cells; ++j, a4 += 16u, nb -= 16, out += K3_TILE) pack_cell(std::true_type{});
+        } else {
+            for (int j = j0; j < j1; ++j, a4 += 16u, nb -= 16, out += K3_TILE) {
+                if (nb < 16) pack_cell(std::true_type{}); else pack_cell(std::false_type{});
+            }
         }
     } else {
         for (int j = j0; j < j1; ++j, out += K3_TILE) {

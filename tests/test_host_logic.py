@@ -34,6 +34,12 @@ void swar_eval(const uint32_t *w, int64_t n, uint32_t *code8, uint32_t *valid4, 
     }
 }
 
+// the 16-byte predicate of the fused pack: non-zero iff a byte is not A, C, G, T
+void swar_any16(const uint32_t *w, int64_t n_cells, uint32_t *any)
+{
+    for (int64_t i = 0; i < n_cells; ++i) any[i] = acgt_any16(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]) != 0u;
+}
+
 // pattern q (length m <= 64), text u (length n): the bit-vector distance and the accepts() verdict for t
 void demux_eval(const uint8_t *q, int m, const uint8_t *u, int n, int t, int *lev, int *ok_codes, int *ok_plain)
 {
@@ -106,6 +112,25 @@ def test_swar_classification_every_byte_in_every_lane(lib):
     assert np.array_equal(top, want_code)
     assert np.array_equal(valid4, want_valid)
     assert np.array_equal(zb, want_zb)
+
+
+def test_swar_sixteen_byte_predicate(lib):
+    """acgt_any16 (what the fused pack tests per cell): every byte value in every one of the 16 positions of an otherwise
+    valid cell, and random read-like cells."""
+    rng = np.random.default_rng(4)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    cells = letters[rng.integers(0, 4, (16 * 256, 16))].copy()
+    for pos in range(16):
+        cells[pos * 256:(pos + 1) * 256, pos] = np.arange(256, dtype=np.uint8)
+    noisy = letters[rng.integers(0, 4, (20000, 16))].copy()
+    hit = rng.random((20000, 16)) < 0.02
+    noisy[hit] = rng.integers(0, 256, int(hit.sum()), dtype=np.uint8)
+    allc = np.ascontiguousarray(np.concatenate([cells, noisy]))
+    words = allc.view(np.uint32).reshape(-1)
+    got = np.empty(allc.shape[0], dtype=np.uint32)
+    lib.swar_any16(words.ctypes.data_as(C.c_void_p), C.c_int64(allc.shape[0]), got.ctypes.data_as(C.c_void_p))
+    want = (~np.isin(allc, letters)).any(axis=1)
+    assert (got.astype(bool) == want).all()
 
 
 def test_swar_classification_read_like_words(lib):
