@@ -149,6 +149,25 @@ def fetch_target_region(module, args, target_dict, target_name, log):
         return str(module.pyfaidx.Fasta(args.RefSeq)[0]).upper()
 
 
+# scipy.stats.norm.interval(0.9, loc, scale)[0] and scipy.stats.sem(values) as consensus_demultiplex uses them
+# (scarmapper/INDEL_Processing.py:1016-1017), without importing scipy.stats (0.8 s of a ~1 s start-up; the launcher
+# defers that import).  interval(): ppf((1 - 0.9) / 2) = ndtri(0.04999999999999999) * scale + loc, the constant below;
+# sem(): std(ddof=1) / n ** 0.5 over the values as an int64 array.  Bit-identical to scipy 1.18 on random inputs
+# (tests/test_dropin_reference_driver.py); the value is only compared with read counts (:540), never printed.
+_NDTRI_LOWER_90 = -1.6448536269514729
+
+
+def norm_interval_lower(loc, scale):
+    if not (scale > 0) or loc != loc:          # rv_continuous.ppf: NaN unless scale > 0 (every sample with the same count)
+        return np.float64("nan")
+    return np.float64(_NDTRI_LOWER_90) * np.float64(scale) + np.float64(loc)
+
+
+def sem(values):
+    a = np.asarray(values)
+    return np.std(a, ddof=1) / a.shape[0] ** 0.5
+
+
 def _rcomp(s: str) -> str:
     return s.encode("latin-1").translate(_COMP)[::-1].decode("latin-1")
 
@@ -424,8 +443,7 @@ def batched_consensus_demultiplex(self, module, device=0):
         log.error("No Scar Patterns Found")
         raise SystemExit(1)
     if len(key_counts) > 1:
-        lower, _ = module.stats.norm.interval(0.9, loc=statistics.mean(key_counts), scale=module.stats.sem(key_counts))
-        lower_limit = statistics.mean(key_counts) - lower
+        lower_limit = statistics.mean(key_counts) - norm_interval_lower(statistics.mean(key_counts), sem(key_counts))
     else:
         lower_limit = float("NaN")
     if math.isnan(lower_limit):

@@ -83,6 +83,29 @@ def run_pear(reference, args, log):
     return "{}.assembled.fastq".format(prefix)
 
 
+def defer_scipy_stats():
+    """`from scipy import stats` (scarmapper/INDEL_Processing.py:16) takes 0.8 s of a start-up of about one second, for
+    two numbers of consensus_demultiplex that the batched path computes itself (dropin.norm_interval_lower / sem).
+    A stand-in module takes the name; the real scipy.stats is imported the moment anything else is asked of it."""
+    import importlib
+    import types
+    if "scipy.stats" in sys.modules:
+        return
+
+    class _Deferred(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__") and name.endswith("__"):
+                raise AttributeError(name)
+            real = self.__dict__.get("_real")
+            if real is None:
+                if sys.modules.get("scipy.stats") is self:
+                    del sys.modules["scipy.stats"]
+                real = importlib.import_module("scipy.stats")
+                self.__dict__["_real"] = real
+            return getattr(real, name)
+    sys.modules["scipy.stats"] = _Deferred("scipy.stats")
+
+
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     ap = argparse.ArgumentParser(add_help=False)
@@ -106,6 +129,7 @@ def main(argv=None):
     warm = threading.Thread(target=_warm_device, daemon=True)
     warm.start()
 
+    defer_scipy_stats()
     # deviation 2: the reference imports `scarmapper.SlidingWindow` at module import
     import scarmapper                                   # the reference package
     from scarmapper_b200 import SlidingWindow as sw, dropin

@@ -128,3 +128,40 @@ def test_launcher_runs_the_reference_pipeline_from_an_options_file(tmp_path):
         dropin._ENGINE_FACTORY[0] = None
         dropin._HOMEOLOGY_BATCH[0] = None
         INDEL_Processing.DataProcessing.consensus_demultiplex, INDEL_Processing.ScarSearch.data_processing = saved
+
+
+def test_lower_limit_arithmetic_is_scipys_bit_for_bit():
+    """consensus_demultiplex's plot threshold (scarmapper/INDEL_Processing.py:1014-1017): dropin.norm_interval_lower / sem
+    against scipy.stats.norm.interval / scipy.stats.sem on per-sample scar-pattern counts, compared as hex floats."""
+    stats = pytest.importorskip("scipy.stats")
+    import statistics
+
+    import numpy as np
+    from scarmapper_b200 import dropin
+    rng = np.random.default_rng(12)
+    cases = [[1, 2], [5, 5, 5], [0, 10 ** 7], list(range(96))]
+    for _ in range(3000):
+        n = int(rng.integers(2, 200))
+        hi = int(rng.choice([3, 50, 10 ** 4, 10 ** 7]))
+        cases.append([int(v) for v in rng.integers(0, hi, n)])
+    for key_counts in cases:
+        want_lower, _ = stats.norm.interval(0.9, loc=statistics.mean(key_counts), scale=stats.sem(key_counts))
+        assert float(dropin.sem(key_counts)).hex() == float(stats.sem(key_counts)).hex()
+        got = dropin.norm_interval_lower(statistics.mean(key_counts), dropin.sem(key_counts))
+        assert float(got).hex() == float(want_lower).hex(), key_counts[:5]
+
+
+def test_launcher_defers_scipy_stats_until_something_needs_it():
+    import subprocess
+    code = ("import sys; sys.path.insert(0, {root!r})\n"
+            "from scarmapper_b200 import launcher\n"
+            "launcher.defer_scipy_stats()\n"
+            "from scipy import stats\n"
+            "assert 'scipy.stats._stats_py' not in sys.modules\n"
+            "assert abs(stats.sem([1, 2, 4]) - 0.8819171036881969) < 1e-15\n"
+            "assert 'scipy.stats._stats_py' in sys.modules and sys.modules['scipy.stats'].__name__ == 'scipy.stats'\n"
+            "import scipy.stats as again\n"
+            "assert again.norm.interval(0.9)[1] > 1.6\n"
+            "print('ok')\n").format(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]
