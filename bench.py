@@ -439,6 +439,7 @@ def main():
         engines.append(eng_b)
         dscars.append(DistributedScar(eng_b, entry_capacity=1 << 21))
     merge_priority = os.environ.get("SCAR_BENCH_MERGE_PRIORITY", "normal")
+    merge_order = os.environ.get("SCAR_BENCH_MERGE_ORDER", "under_next_step")      # or "beside_k2"
     side = torch.cuda.Stream(priority=-1 if merge_priority == "high" else 0) if world > 1 else None
     # owner-partitioned merge: a rank sends each peer the entries that peer owns.  The exchange moves whole
     # regions, so they are sized from the table this batch actually produces (one untimed pass): the largest
@@ -529,6 +530,13 @@ def main():
         m0 = ev() if record_marks else None
         e.demux_resident(res)
         m1 = ev() if record_marks else None
+        if world > 1 and merge_order == "beside_k2":
+            # the previous step's merge goes to the side stream NOW and this step's fused kernel waits for it: the merge's
+            # small kernels and the all-to-all run beside reset + K2 (which leave SM resources free) instead of queueing
+            # behind a persistent kernel that holds every SM for 1.4 ms
+            done = run_pending_merge(record_marks)
+            if done is not None:
+                stream.wait_event(done)
         if fused:
             e.classify_raw_resident(res, first_index=first)       # K1 + K3 + K4 in one pass over the raw bytes
             m2 = m3 = ev() if record_marks else None
@@ -543,7 +551,8 @@ def main():
             computed.record(stream)
             # software pipeline on the host as well: this step's kernels are queued, NOW run the previous
             # step's merge (its small D2H syncs block the host while the GPU is busy with this step)
-            run_pending_merge(record_marks)
+            if merge_order != "beside_k2":
+                run_pending_merge(record_marks)
             pending.append((k, computed))
         if record_marks:
             marks.append((m0, m1, m2, m3))
@@ -552,7 +561,7 @@ def main():
 
     def run_pending_merge(record_marks):
         if not pending:
-            return
+            return None
         k, computed = pending.pop(0)
         with torch.cuda.stream(side):
             side.wait_event(computed)
@@ -564,6 +573,7 @@ def main():
         merge_done[k] = me
         if record_marks:
             merge_marks.append((ms, me))
+        return me
 
     merge_marks = []
 
@@ -907,6 +917,7 @@ def main():
             line["merge_check"] = merge_check
             line["config"]["sm_reserved_for_merge"] = sm_reserve
             line["config"]["merge_stream_priority"] = merge_priority
+            line["config"]["merge_order"] = merge_order
         if pipeline:
             line["pipeline"] = pipeline
         if configs:
