@@ -529,10 +529,22 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
     const bool gz_parallel = gz && !bgzf && n_threads > 1 && file.n >= (256 << 10) && !getenv("SCAR_GZIP_SERIAL");
     run->threads = gz && !bgzf && !gz_parallel ? 1 : n_threads;
 
+    // the text size, to allocate once (every re-allocation in mid-stream is a cudaMalloc + copy + cudaFree with both
+    // streams idle): the file itself; BGZF: the sum of the blocks' sizes; gzip: the length field of the last trailer
+    // (exact for one member under 4 GiB; otherwise a typical FASTQ ratio) - grown on demand when the guess was low
+    int64_t text_hint = file.n;
+    if (bgzf) { text_hint = 0; for (const BgzfBlock &b : blocks) text_hint += b.out_len; }
+    else if (gz) {
+        const uint8_t *t = file.p + file.n - 4;
+        const int64_t isize = file.n >= 18 ? (int64_t)((uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24)) : 0;
+        text_hint = isize > file.n && isize < 1100 * file.n ? isize : 5 * file.n;
+    }
     // ---- staging pieces: pinned, allocated when the producer first needs them (a small file pays for what it uses),
     // kept in the context between calls.  16 MB keeps the per-piece overheads (two stream synchronisations, ten
     // launches) under the copy time; a file smaller than that takes one piece of its own size.
-    int64_t piece = 16ll << 20;
+    // Measured on a 3.46 GB text (10 M reads, profiles/r02/ingest_piece_sizes.txt): 16 / 32 / 64 / 128 MB pieces take
+    // 0.76 / 0.62 / 0.65 / 0.71 s for the whole file - 32 MB once the text is large.
+    int64_t piece = text_hint >= (512ll << 20) ? 32ll << 20 : 16ll << 20;
     if (const char *e = getenv("SCAR_FASTQ_FILE_PIECE_BYTES")) { const long long v = atoll(e); if (v > 0) piece = v; }
     else if (!gz) piece = std::min(piece, std::max<int64_t>(file.n, 1));
     else piece = std::min(piece, std::max<int64_t>(16 * file.n, 1 << 20));
@@ -557,16 +569,6 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
     c->fq_records_n = 0;
     if ((rc = ensure(&c->d_tile_counts, &c->tile_counts_cap, (size_t)((piece + 4095) / 4096)))) return rc;
     if ((rc = ensure(&c->d_tile_offsets, &c->tile_offsets_cap, (size_t)scar_fastq_offsets_elems(piece)))) return rc;
-    // the text size, to allocate once (every re-allocation in mid-stream is a cudaMalloc + copy + cudaFree with both
-    // streams idle): the file itself; BGZF: the sum of the blocks' sizes; gzip: the length field of the last trailer
-    // (exact for one member under 4 GiB; otherwise a typical FASTQ ratio) - grown on demand when the guess was low
-    int64_t text_hint = file.n;
-    if (bgzf) { text_hint = 0; for (const BgzfBlock &b : blocks) text_hint += b.out_len; }
-    else if (gz) {
-        const uint8_t *t = file.p + file.n - 4;
-        const int64_t isize = file.n >= 18 ? (int64_t)((uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24)) : 0;
-        text_hint = isize > file.n && isize < 1100 * file.n ? isize : 5 * file.n;
-    }
     if ((rc = ensure_keep(&c->d_text, &c->text_cap, (size_t)text_hint + 4096, 0))) return rc;
 
     mark("device buffers ready");
