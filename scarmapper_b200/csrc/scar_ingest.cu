@@ -630,7 +630,7 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
             if (want_nl > c->nl_cap) {
                 // lines of the whole text at the density seen so far (+ 3 %), else half as much again
                 const double scale = n_bytes > 0 && text_hint > n_bytes ? 1.03 * (double)text_hint / (double)n_bytes : 1.5;
-                want_nl = (size_t)((double)want_nl * std::max(scale, 1.0)) + 1024;
+                want_nl = (size_t)((double)want_nl * (scale >= 1.0 ? scale : 1.5)) + 1024;
             }
             if ((rc = ensure_keep(&c->d_nl, &c->nl_cap, want_nl, (size_t)nl_total))) return drain(rc);
             CU(scar_fastq_positions_launch(c->d_text + b0, len, c->d_tile_offsets, c->d_nl + nl_total, (int64_t)n_nl, b0, s));
@@ -647,7 +647,7 @@ extern "C" int scar_process_fastq_file(scar_ctx *c, const char *path, int64_t re
         size_t want_rec = (size_t)rec_avail;
         if (want_rec > c->fq_records_cap) {
             const double scale = n_bytes > 0 && text_hint > n_bytes ? 1.03 * (double)text_hint / (double)n_bytes : 1.5;
-            want_rec = (size_t)((double)want_rec * std::max(scale, 1.0)) + 1024;
+            want_rec = (size_t)((double)want_rec * (scale >= 1.0 ? scale : 1.5)) + 1024;
         }
         if ((rc = ensure_keep(&c->d_fq_records, &c->fq_records_cap, want_rec, (size_t)rec_done))) return drain(rc);
         if ((rc = ensure_keep(&c->d_fq_seq_off, &c->fq_seq_off_cap, want_rec, (size_t)rec_done))) return drain(rc);
