@@ -92,8 +92,14 @@ def merge_tables_partitioned(export_parts_fn, clear_fn, merge_parts_fn, send: to
     synchronisation: the per-region counts travel inside the regions."""
     world = dist.get_world_size(group)
     export_parts_fn(send, world)
-    exchange_regions(send, recv, group)
-    clear_fn()
+    if dist.get_backend(group) == "nccl":
+        # the table is cleared (it only needs the export to be done) while the regions travel
+        work = dist.all_to_all_single(recv, send, group=group, async_op=True)
+        clear_fn()
+        work.wait()                      # stream-ordered: the current stream waits for NCCL's, the host does not
+    else:
+        exchange_regions(send, recv, group)
+        clear_fn()
     merge_parts_fn(recv, world)
 
 
