@@ -804,16 +804,8 @@ extern "C" int scar_classify_raw_dev(scar_ctx *c, const scar_ragged *seq, const 
                                           "(use scar_pack_dev + scar_classify_dev + scar_aggregate_dev)");
     if (n == 0) return SCAR_OK;
     CU(cudaSetDevice(c->device));
-    K3Params FP = fused_params(c, seq, samples, n, first_index, records, aggregate ? 1 : 0);
-    // tiles beyond every group's first two are handed out by a counter (a spare accumulator word, zeroed here): the
-    // launch ends when the work does, not when the slowest statically assigned group does.  SCAR_STATIC_TILES=1: the
-    // round-robin assignment
-    const bool static_tiles = getenv("SCAR_STATIC_TILES") != nullptr;
-    if (!static_tiles) {
-        FP.tile_counter = c->d_acc + 5;
-        CU(cudaMemsetAsync(FP.tile_counter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
-    }
-    CU(scar_launch_fused(FP, c->smem_tables, c->max_read_len, c->sm_count, (cudaStream_t)stream, &c->launches));
+    CU(scar_launch_fused(fused_params(c, seq, samples, n, first_index, records, aggregate ? 1 : 0), c->smem_tables,
+                         c->max_read_len, c->sm_count, (cudaStream_t)stream, &c->launches));
     return SCAR_OK;
 }
 

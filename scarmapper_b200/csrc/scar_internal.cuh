@@ -164,10 +164,6 @@ struct K3Params {
     unsigned long long *n_entries, *counters, *unassigned, *phase_hist;
     int32_t *status;              // bit 0: read longer than 16 W, bit 1: table full
     int32_t phase_bins, phase_joint;
-    // fused mode: tiles beyond every group's first two are handed out by this counter (zeroed before the launch; NULL:
-    // the static round-robin assignment).  Reads are independent and the table keeps the smallest read index per
-    // key, so the assignment does not show in any result.
-    unsigned long long *tile_counter;
 };
 
 struct K4Params {

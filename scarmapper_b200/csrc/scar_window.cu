@@ -730,7 +730,6 @@ scar_window_kernel(const K3Params P)
         uint32_t count[3][2];                       // [round % 3][side]
         unsigned int unassigned;                    // fused: aggregation
         uint32_t pad;
-        long long fetched[2];                       // fused, dynamic tiles: the tile after next, by iteration parity
     };
     __shared__ GroupState g_state[GMAX];
     GroupState &G = g_state[group];
@@ -779,17 +778,7 @@ scar_window_kernel(const K3Params P)
     uint32_t round = 0;
     int epoch = 0;
 
-    // Tile order of a group: its first two tiles are fixed (blockIdx, group); with a tile counter the later ones are
-    // taken from it one iteration AHEAD (the ring refills a slot with the next tile's bytes while this tile is packed,
-    // so the next tile must be known at the top of an iteration): thread 0 asks for the tile after next at the top of
-    // iteration t, publishes it before the first barrier of the search rounds, everybody reads it at the top of t + 1.
-    const bool dynamic = FUSED && P.tile_counter != nullptr;
-    int64_t next_tile = ((int64_t)blockIdx.x * n_groups + group) * K3_TILE + tile_step;
-    long long asked = 0;
-    uint32_t iter = 0;
-    for (int64_t tile = ((int64_t)blockIdx.x * n_groups + group) * K3_TILE; tile < P.n_reads; tile = next_tile, next_tile = dynamic ? (int64_t)G.fetched[(iter - 1) & 1] : next_tile + tile_step) {
-        if (dynamic && tx == 0) asked = 2 * tile_step + (long long)atomicAdd(P.tile_counter, (unsigned long long)K3_TILE);
-        const uint32_t it_now = iter++;
+    for (int64_t tile = ((int64_t)blockIdx.x * n_groups + group) * K3_TILE; tile < P.n_reads; tile += tile_step) {
         const int64_t r = tile + tx;
         bool live = r < P.n_reads;
         const bool in_range = live;
@@ -821,7 +810,7 @@ scar_window_kernel(const K3Params P)
                     const uint32_t slot_addr = ring_addr + (uint32_t)sl * P.raw_cap, slot_bar = ring_bar + 8u * sl;
                     // the descriptor of the refill first: its loads fly while the chunk is packed
                     const int64_t rn = c + FUSED_SLOTS < FUSED_CHUNKS ? w0 + FUSED_CHUNK * (c + FUSED_SLOTS)
-                                                                      : next_tile + 32 * warp + FUSED_CHUNK * (c + FUSED_SLOTS - FUSED_CHUNKS);
+                                                                      : w0 + tile_step + FUSED_CHUNK * (c + FUSED_SLOTS - FUSED_CHUNKS);
                     const ChunkDesc dn = chunk_desc(P.seq, rn, FUSED_CHUNK, P.n_reads, P.raw_cap);
                     if (ring_desc[sl].staged) { chunk_wait(slot_bar, ring_phase[sl] & 1u); ++ring_phase[sl]; }
                     pack_chunk<LANES>(P, ring_desc[sl], slot_addr, w0 + FUSED_CHUNK * c, 32 * warp + FUSED_CHUNK * c, s_cells, s_ctx);
@@ -1016,7 +1005,6 @@ scar_window_kernel(const K3Params P)
         s_right[tx] = (uint32_t)crj | ((uint32_t)trj << 16);
         s_ctx[tx] = (uint32_t)len | ((uint32_t)tid << 16);
 
-        if (dynamic && tx == 0) G.fetched[it_now & 1] = asked;       // (read at the top of the next iteration, a barrier later)
         // ---- phase 2: rounds over the open searches of the tile
         for (;;) {
             group_sync();

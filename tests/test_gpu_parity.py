@@ -863,48 +863,6 @@ def test_fused_kernel_equals_three_kernel_path_and_oracle(name, n, kw, anchor, m
     assert (fu[2] == orc.counters(prob, want)).all()
 
 
-@pytest.mark.parametrize("name,n,sms", [("C2", 150000, 12), ("C3", 90000, 5), ("C4", 60000, 9), ("C2", 2000000, 0)])
-def test_fused_kernel_dynamic_tiles_equal_static_tiles(name, n, sms, monkeypatch):
-    """Tiles beyond a group's first two are handed out by a device counter (the launch ends when the work does).  The
-    assignment must not show anywhere: records, table (entries, counts, first-seen indices), counters and phase bins
-    against the round-robin assignment (SCAR_STATIC_TILES=1) and, on a prefix, the oracle.  A small SM limit makes a
-    short batch span many rounds of tiles; the last case runs the full grid."""
-    import torch
-    from scarmapper_b200.engine import HostRagged
-    cfg = synth.make_config(name, n_reads=n, seed=77)
-    pin = synth_problem(cfg)
-    batch = cfg.generate(0, n)
-    seq = HostRagged.from_matrix(batch["seq"], lengths=batch["len"])
-    out = []
-    for static in (True, False):
-        if static:
-            monkeypatch.setenv("SCAR_STATIC_TILES", "1")
-        else:
-            monkeypatch.delenv("SCAR_STATIC_TILES", raising=False)
-        eng = engine_for(pin, cfg.read_len, table_capacity=1 << 20)
-        assert eng.info()["fused"]
-        if sms:
-            eng.set_sm_limit(sms)
-        res = eng.make_resident(seq, batch["f0"], batch["f1"])
-        for rep in range(2):                      # twice: the counter is zeroed per launch
-            eng.reset_async()
-            eng.run_resident(res, first_index=11)
-        torch.cuda.synchronize()
-        cnt, un = eng.counters()
-        out.append((eng.records_of(res).copy(), eng.table().copy(), cnt.copy(), un, eng.phase_hist().copy()))
-        eng.close()
-    a, b = out
-    assert a[0].tobytes() == b[0].tobytes()
-    assert a[1].tobytes() == b[1].tobytes()
-    assert (a[2] == b[2]).all() and a[3] == b[3] and (a[4] == b[4]).all()
-    k = 3000
-    all_reads = cfg.reads_as_strings(batch)
-    f0, f1 = cfg.fields_as_strings(batch)
-    for part in (slice(0, k), slice(n - k, n)):
-        want = orc.classify_batch(orc.Problem(**pin), all_reads[part], f0[part], f1[part])
-        assert_records_equal(b[0][part], want, all_reads[part])
-
-
 def test_fused_kernel_on_fastq_views_takes_several_passes():
     """FASTQ text: the reads are a third of the bytes, so a tile's raw span is wider than the staging buffer and is
     taken in passes (and, with a tiny buffer, read from global memory); same records either way."""
