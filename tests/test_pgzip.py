@@ -169,3 +169,45 @@ def test_text_that_inflates_beyond_the_chunk_budget_is_handed_back(monkeypatch):
     for threads, chunk in ((1, 0), (4, 2048), (4, 1 << 14)):
         assert fastq.gunzip(gz, threads=threads, chunk_bytes=chunk, stats=st).tobytes() == data
     assert st["redone"] > 0
+
+
+def test_seeded_fuzz_against_zlib():
+    """Random mixtures (text-like runs, repeats at random distances, binary noise), random deflate parameters, flush
+    points, member splits, chunk sizes and thread counts: always the bytes zlib gives."""
+    rng = np.random.default_rng(2026)
+    letters = np.frombuffer(b"ACGTN@+:IF#,0123456789\n", dtype=np.uint8)
+    for case in range(60):
+        parts = []
+        for _ in range(int(rng.integers(1, 12))):
+            kind = int(rng.integers(0, 4))
+            n = int(rng.integers(1, 60000))
+            if kind == 0:
+                parts.append(bytes(letters[rng.integers(0, len(letters), n)]))
+            elif kind == 1 and parts:
+                src = b"".join(parts)
+                a = int(rng.integers(0, len(src)))
+                parts.append(src[a:a + n] * int(rng.integers(1, 4)))
+            elif kind == 2:
+                parts.append(bytes(rng.integers(0, 256, n, dtype=np.uint8)))
+            else:
+                parts.append(bytes([int(rng.integers(32, 127))]) * n)
+        data = b"".join(parts)
+        level = int(rng.choice([1, 3, 6, 9]))
+        strategy = int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+        n_members = int(rng.integers(1, 4))
+        cuts = sorted(int(v) for v in rng.integers(0, len(data) + 1, n_members - 1))
+        gz = b""
+        for a, b in zip([0] + cuts, cuts + [len(data)]):
+            co = zlib.compressobj(level, zlib.DEFLATED, 31, int(rng.integers(1, 10)), strategy)
+            piece, out = data[a:b], []
+            step = max(1, len(piece) // int(rng.integers(1, 6)))
+            for q in range(0, len(piece), step):
+                out.append(co.compress(piece[q:q + step]))
+                if rng.random() < 0.3:
+                    out.append(co.flush(int(rng.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH]))))
+            out.append(co.flush())
+            gz += b"".join(out) + b"\0" * int(rng.integers(0, 3) * 8)
+        threads = int(rng.integers(1, 7))
+        chunk = int(rng.choice([0, 1024, 4096, 30000, 1 << 17]))
+        got = fastq.gunzip(gz, threads=threads, chunk_bytes=chunk, capacity=len(data))
+        assert got.tobytes() == data, (case, level, strategy, n_members, threads, chunk)
