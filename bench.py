@@ -848,11 +848,20 @@ def main():
         engines = []
         del res
         torch.cuda.empty_cache()
-        b5 = cfg.generate(rank * n5, n5)
-        eng5 = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=1 << 23, **pin), device=local)
-        res5 = eng5.make_resident(HostRagged.from_matrix(b5["seq"], lengths=b5["len"]), HostRagged.from_matrix(b5["f0"]),
-                                  HostRagged.from_matrix(b5["f1"]))
-        del b5
+        eng5 = res5 = None
+        try:                               # (host or device memory: every rank must get through, or all skip together)
+            b5 = cfg.generate(rank * n5, n5)
+            eng5 = ScarEngine(ScarProblem(max_read_len=cfg.read_len, table_capacity=1 << 23, **pin), device=local)
+            res5 = eng5.make_resident(HostRagged.from_matrix(b5["seq"], lengths=b5["len"]), HostRagged.from_matrix(b5["f0"]),
+                                      HostRagged.from_matrix(b5["f1"]))
+            del b5
+            ok5 = 1
+        except Exception:                  # noqa: BLE001
+            ok5 = 0
+        t = torch.tensor([ok5], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok5 = int(t.item())
+    if world > 1 and not args.kernels_only and not args.no_configs and ok5:
         d5 = DistributedScar(eng5, entry_capacity=1 << 22)
         first5 = rank * n5
         eng5.reset_async()
